@@ -1,0 +1,338 @@
+// fm_kernels.h - per-thread task bodies of the FM-index stage (seeding + suffix-array look-up).
+//
+// These are the bodies that the CUDA kernels in stages_cuda.cu run, one read (or one seed slot) per thread.
+// They are written as host/device functions so that the test-only host build (tests/hostemu) can execute the
+// very same arithmetic on the CPU to exercise the host orchestration without a GPU; the shipped library only
+// contains the CUDA instantiation.
+//
+// Semantics follow the reference line by line where the output depends on it:
+//   occ4 / extend            reference src/bwt.c:169-186, 262-275
+//   smem1a                   reference src/bwt.c:289-351   (max_intv is always 0 on the mem path)
+//   seed_strategy1           reference src/bwt.c:358-379
+//   collect_intv             reference src/bwamem.c:114-162
+//   sa_lookup                reference src/bwt.c:53-59, 86-96, 107-129
+//   pos2rid / intv2rid       reference src/bntseq.c:349-375
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define B200_HD __host__ __device__ __forceinline__
+#define B200_HDN __host__ __device__
+#else
+#define B200_HD inline
+#define B200_HDN inline
+#endif
+
+namespace b200 {
+
+struct Intv { uint64_t x0, x1, x2, info; };     // same 32-byte layout as bwtintv_t
+
+struct FmView {
+	const uint32_t *bwt;        // occ-interleaved BWT, 64-byte blocks
+	const uint64_t *sa;         // SA samples
+	uint64_t primary, L2[5], seq_len;
+	int sa_intv;
+	const uint8_t *pac;         // 2-bit forward strand
+	int64_t l_pac;
+	const int64_t *ctg_off;     // contig offsets (forward strand)
+	const int32_t *ctg_len;
+	int n_ctg;
+};
+
+struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads
+	int min_seed_len, split_len, split_width, max_occ;
+	int max_mem_intv;
+};
+
+B200_HD int popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+	return __popc(x);
+#else
+	return __builtin_popcount(x);
+#endif
+}
+
+// counts of A,C,G,T among the 16 two-bit symbols of w, packed one per byte (A in the low byte)
+B200_HD uint32_t sym_counts16(uint32_t w)
+{
+	uint32_t lo = w & 0x55555555u, hi = (w >> 1) & 0x55555555u;
+	uint32_t c3 = popc32(hi & lo), c2 = popc32(hi & ~lo & 0x55555555u), c1 = popc32(~hi & lo & 0x55555555u);
+	uint32_t c0 = 16 - c1 - c2 - c3;
+	return c0 | c1 << 8 | c2 << 16 | c3 << 24;
+}
+
+// Occ(c, k) for the four symbols; k == (uint64_t)-1 gives zeros.  *blk receives the 64-byte block index (or -1).
+B200_HD void fm_occ4(const FmView &fm, uint64_t k, uint64_t cnt[4], int64_t *blk)
+{
+	if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; if (blk) *blk = -1; return; }
+	k -= (k >= fm.primary);
+	const uint32_t *p = fm.bwt + ((k >> 7) << 4);
+	if (blk) *blk = (int64_t)(k >> 7);
+	const uint64_t *c = (const uint64_t *)p;
+	cnt[0] = c[0]; cnt[1] = c[1]; cnt[2] = c[2]; cnt[3] = c[3];
+	p += 8;
+	int full = (int)((k & 127) >> 4);
+	uint32_t x = 0;
+	for (int i = 0; i < full; ++i) x += sym_counts16(p[i]);
+	uint32_t drop = (uint32_t)(~k & 15);
+	uint32_t last = p[full] & ~((1u << (drop << 1)) - 1u);
+	x += sym_counts16(last) - drop;
+	cnt[0] += x & 0xff; cnt[1] += x >> 8 & 0xff; cnt[2] += x >> 16 & 0xff; cnt[3] += x >> 24;
+}
+
+// bi-directional extension of ik by each of the four bases
+B200_HD void fm_extend(const FmView &fm, const Intv &ik, Intv ok[4], int is_back, int64_t *n_blocks)
+{
+	uint64_t tk[4], tl[4];
+	uint64_t base = is_back ? ik.x0 : ik.x1;
+	int64_t b0, b1;
+	fm_occ4(fm, base - 1, tk, &b0);
+	fm_occ4(fm, base - 1 + ik.x2, tl, &b1);
+	if (n_blocks) *n_blocks += (b0 >= 0) + (b1 >= 0 && b1 != b0);
+	uint64_t nb[4];
+	for (int i = 0; i < 4; ++i) {
+		nb[i] = fm.L2[i] + 1 + tk[i];
+		ok[i].x2 = tl[i] - tk[i];
+	}
+	uint64_t other = is_back ? ik.x1 : ik.x0;
+	uint64_t o3 = other + (base <= fm.primary && base + ik.x2 - 1 >= fm.primary);
+	uint64_t o2 = o3 + ok[3].x2, o1 = o2 + ok[2].x2, o0 = o1 + ok[1].x2;
+	if (is_back) {
+		ok[0].x0 = nb[0]; ok[1].x0 = nb[1]; ok[2].x0 = nb[2]; ok[3].x0 = nb[3];
+		ok[0].x1 = o0; ok[1].x1 = o1; ok[2].x1 = o2; ok[3].x1 = o3;
+	} else {
+		ok[0].x1 = nb[0]; ok[1].x1 = nb[1]; ok[2].x1 = nb[2]; ok[3].x1 = nb[3];
+		ok[0].x0 = o0; ok[1].x0 = o1; ok[2].x0 = o2; ok[3].x0 = o3;
+	}
+}
+
+B200_HD void fm_set_intv(const FmView &fm, int c, Intv &ik)
+{
+	ik.x0 = fm.L2[c] + 1;
+	ik.x2 = fm.L2[c + 1] - fm.L2[c];
+	ik.x1 = fm.L2[3 - c] + 1;
+	ik.info = 0;
+}
+
+// All SMEMs through position x (max_intv == 0 flavour).  `a` and `b` are scratch of len+1 entries each,
+// `mem` receives the result (n_mem entries, sorted by start).  Returns the next x.
+B200_HDN int fm_smem1(const FmView &fm, int len, const uint8_t *q, int x, uint64_t min_intv,
+                      Intv *mem, int *n_mem, Intv *a, Intv *b, int64_t *n_blocks)
+{
+	*n_mem = 0;
+	if (q[x] > 3) return x + 1;
+	if (min_intv < 1) min_intv = 1;
+	Intv ik, ok[4];
+	Intv *prev = a, *curr = b;
+	int n_prev, n_curr = 0, i;
+	fm_set_intv(fm, q[x], ik);
+	ik.info = x + 1;
+	for (i = x + 1; i < len; ++i) {               // forward sweep
+		if (q[i] < 4) {
+			int c = 3 - q[i];
+			fm_extend(fm, ik, ok, 0, n_blocks);
+			if (ok[c].x2 != ik.x2) {
+				curr[n_curr++] = ik;
+				if (ok[c].x2 < min_intv) break;
+			}
+			ik = ok[c]; ik.info = i + 1;
+		} else {
+			curr[n_curr++] = ik;
+			break;
+		}
+	}
+	if (i == len) curr[n_curr++] = ik;
+	for (int j = 0; j < n_curr >> 1; ++j) { Intv t = curr[j]; curr[j] = curr[n_curr - 1 - j]; curr[n_curr - 1 - j] = t; }
+	int ret = (int)curr[0].info;
+	{ Intv *t = curr; curr = prev; prev = t; }
+	n_prev = n_curr;
+	int nm = 0;
+	for (i = x - 1; i >= -1; --i) {               // backward sweep
+		int c = i < 0 ? -1 : q[i] < 4 ? q[i] : -1;
+		n_curr = 0;
+		for (int j = 0; j < n_prev; ++j) {
+			const Intv p = prev[j];
+			if (c >= 0) fm_extend(fm, p, ok, 1, n_blocks);
+			if (c < 0 || ok[c].x2 < min_intv) {
+				if (n_curr == 0) {
+					if (nm == 0 || (uint64_t)(i + 1) < (mem[nm - 1].info >> 32)) {
+						ik = p; ik.info |= (uint64_t)(i + 1) << 32;
+						mem[nm++] = ik;
+					}
+				}
+			} else if (n_curr == 0 || ok[c].x2 != curr[n_curr - 1].x2) {
+				ok[c].info = p.info;
+				curr[n_curr++] = ok[c];
+			}
+		}
+		if (n_curr == 0) break;
+		{ Intv *t = curr; curr = prev; prev = t; }
+		n_prev = n_curr;
+	}
+	for (int j = 0; j < nm >> 1; ++j) { Intv t = mem[j]; mem[j] = mem[nm - 1 - j]; mem[nm - 1 - j] = t; }
+	*n_mem = nm;
+	return ret;
+}
+
+// forward-only greedy seed; m->x2 == 0 when nothing was found. Returns the next x.
+B200_HDN int fm_seed_strategy1(const FmView &fm, int len, const uint8_t *q, int x, int min_len, int max_intv,
+                               Intv *m, int64_t *n_blocks)
+{
+	Intv ik, ok[4];
+	m->x0 = m->x1 = m->x2 = m->info = 0;
+	if (q[x] > 3) return x + 1;
+	fm_set_intv(fm, q[x], ik);
+	for (int i = x + 1; i < len; ++i) {
+		if (q[i] < 4) {
+			int c = 3 - q[i];
+			fm_extend(fm, ik, ok, 0, n_blocks);
+			if (ok[c].x2 < (uint64_t)max_intv && i - x >= min_len) {
+				*m = ok[c];
+				m->info = (uint64_t)x << 32 | (uint32_t)(i + 1);
+				return i + 1;
+			}
+			ik = ok[c];
+		} else return i + 1;
+	}
+	return len;
+}
+
+// The three seeding passes of one read.  out[0..cap) receives the interval list sorted by info.
+// scratch = 3*(len+1) Intv.  Returns the number of intervals, or -(needed) when cap is too small.
+B200_HDN int fm_collect_intv(const FmView &fm, const SeedOpt &so, int len, const uint8_t *seq,
+                             Intv *out, int cap, Intv *scratch, int64_t *n_blocks)
+{
+	Intv *mem1 = scratch, *ta = scratch + (len + 1), *tb = scratch + 2 * (len + 1);
+	int n = 0, n1, x = 0;
+	while (x < len) {                             // pass 1: all SMEMs
+		if (seq[x] < 4) {
+			x = fm_smem1(fm, len, seq, x, 1, mem1, &n1, ta, tb, n_blocks);
+			for (int i = 0; i < n1; ++i) {
+				int slen = (int)(uint32_t)mem1[i].info - (int)(mem1[i].info >> 32);
+				if (slen >= so.min_seed_len) { if (n < cap) out[n] = mem1[i]; ++n; }
+			}
+		} else ++x;
+	}
+	int old_n = n < cap ? n : cap;                // pass 2: re-seed inside long, rare SMEMs
+	if (n <= cap)
+	for (int k = 0; k < old_n; ++k) {
+		const Intv p = out[k];
+		int start = (int)(p.info >> 32), end = (int)(int32_t)p.info;
+		if (end - start < so.split_len || p.x2 > (uint64_t)so.split_width) continue;
+		fm_smem1(fm, len, seq, (start + end) >> 1, p.x2 + 1, mem1, &n1, ta, tb, n_blocks);
+		for (int i = 0; i < n1; ++i) {
+			int slen = (int)(uint32_t)mem1[i].info - (int)(mem1[i].info >> 32);
+			if (slen >= so.min_seed_len) { if (n < cap) out[n] = mem1[i]; ++n; }
+		}
+	}
+	if (so.max_mem_intv > 0) {                    // pass 3: LAST-like greedy seeds
+		x = 0;
+		while (x < len) {
+			if (seq[x] < 4) {
+				Intv m;
+				x = fm_seed_strategy1(fm, len, seq, x, so.min_seed_len, so.max_mem_intv, &m, n_blocks);
+				if (m.x2 > 0) { if (n < cap) out[n] = m; ++n; }
+			} else ++x;
+		}
+	}
+	if (n > cap) return -n;
+	for (int i = 1; i < n; ++i) {                 // order by (start,end); equal keys are identical intervals
+		Intv v = out[i];
+		int j = i - 1;
+		while (j >= 0 && out[j].info > v.info) { out[j + 1] = out[j]; --j; }
+		out[j + 1] = v;
+	}
+	return n;
+}
+
+// number of suffix-array look-ups mem_chain() makes for one interval (reference src/bwamem.c:278-279)
+B200_HD int seed_slots(uint64_t x2, int max_occ)
+{
+	if (x2 <= (uint64_t)max_occ) return (int)x2;
+	uint64_t step = x2 / (uint64_t)max_occ;
+	uint64_t cnt = (x2 + step - 1) / step;
+	return cnt < (uint64_t)max_occ ? (int)cnt : max_occ;
+}
+B200_HD uint64_t seed_step(uint64_t x2, int max_occ) { return x2 > (uint64_t)max_occ ? x2 / (uint64_t)max_occ : 1; }
+
+B200_HD int fm_B0(const FmView &fm, uint64_t k)
+{
+	uint32_t w = fm.bwt[((k >> 7) << 4) + 8 + ((k & 0x7f) >> 4)];
+	return (int)(w >> ((~k & 0xf) << 1) & 3);
+}
+
+// Occ(c,k) for one symbol
+B200_HD uint64_t fm_occ1(const FmView &fm, uint64_t k, int c)
+{
+	if (k == fm.seq_len) return fm.L2[c + 1] - fm.L2[c];
+	if (k == (uint64_t)-1) return 0;
+	k -= (k >= fm.primary);
+	const uint32_t *p = fm.bwt + ((k >> 7) << 4);
+	uint64_t n = ((const uint64_t *)p)[c];
+	p += 8;
+	int full = (int)((k & 127) >> 4);
+	uint32_t x = 0;
+	for (int i = 0; i < full; ++i) x += sym_counts16(p[i]);
+	uint32_t drop = (uint32_t)(~k & 15);
+	uint32_t last = p[full] & ~((1u << (drop << 1)) - 1u);
+	x += sym_counts16(last) - drop;
+	return n + (x >> (c << 3) & 0xff);
+}
+
+// SA[k] by LF-walking to a sampled row
+B200_HD uint64_t fm_sa(const FmView &fm, uint64_t k, int *steps)
+{
+	uint64_t sa = 0, mask = (uint64_t)fm.sa_intv - 1;
+	int n = 0;
+	while (k & mask) {
+		++sa; ++n;
+		if (k == fm.primary) k = 0;
+		else {
+			uint64_t kk = k - (k > fm.primary);
+			int c = fm_B0(fm, kk);
+			k = fm.L2[c] + fm_occ1(fm, k, c);
+		}
+	}
+	if (steps) *steps = n;
+	return sa + fm.sa[k / (uint64_t)fm.sa_intv];
+}
+
+B200_HD int fm_pos2rid(const FmView &fm, int64_t pos_f)
+{
+	if (pos_f >= fm.l_pac) return -1;
+	int left = 0, mid = 0, right = fm.n_ctg;
+	while (left < right) {
+		mid = (left + right) >> 1;
+		if (pos_f >= fm.ctg_off[mid]) {
+			if (mid == fm.n_ctg - 1) break;
+			if (pos_f < fm.ctg_off[mid + 1]) break;
+			left = mid + 1;
+		} else right = mid;
+	}
+	return mid;
+}
+
+B200_HD int64_t fm_depos(const FmView &fm, int64_t pos, int *is_rev)
+{
+	return (*is_rev = (pos >= fm.l_pac)) ? (fm.l_pac << 1) - 1 - pos : pos;
+}
+
+B200_HD int fm_intv2rid(const FmView &fm, int64_t rb, int64_t re)
+{
+	int is_rev;
+	if (rb < fm.l_pac && re > fm.l_pac) return -2;
+	int rid_b = fm_pos2rid(fm, fm_depos(fm, rb, &is_rev));
+	int rid_e = rb < re ? fm_pos2rid(fm, fm_depos(fm, re - 1, &is_rev)) : rid_b;
+	return rid_b == rid_e ? rid_b : -1;
+}
+
+// base code (0-3) at position p of the forward+reverse-complement coordinate system [0, 2*l_pac)
+B200_HD int fm_base(const uint8_t *pac, int64_t l_pac, int64_t p)
+{
+	if (p < l_pac) return pac[p >> 2] >> ((~p & 3) << 1) & 3;
+	int64_t f = (l_pac << 1) - 1 - p;
+	return 3 - (pac[f >> 2] >> ((~f & 3) << 1) & 3);
+}
+
+} // namespace b200

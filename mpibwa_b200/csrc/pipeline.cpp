@@ -1,0 +1,478 @@
+// pipeline.cpp - mem_process_seqs: the reference's per-read thread loops (src/bwamem.c:1205-1234) re-organised
+// into batched stages so that the FM-index search, the seed extension and the mate-rescue Smith-Waterman of a
+// whole chunk run as device kernels, with the pointer-chasing steps in between on host threads:
+//
+//   encode -> [GPU] seeding + SA look-up -> chaining/filtering -> [GPU] chain2aln (ksw_extend2)
+//          -> dedup/patch -> insert-size statistics (chunk-global) -> [GPU] mate-rescue ksw_align2 -> replay
+//          -> primary marking, pairing, mapQ, CIGAR, SAM text
+//
+// Results do not depend on opt->n_threads or on batching: the extension of a seed does not depend
+// on the regions found so far (only the decision to extend does, and that decision is taken on the device in the
+// reference's order), and a rescue alignment depends only on (anchor, orientation, mate), so it can be computed
+// up front and the sequential insert/skip logic of mem_matesw replayed afterwards.
+#include "host_align.h"
+#include "stages.h"
+#include "util.h"
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <chrono>
+#include <mutex>
+#include <unordered_map>
+#include <algorithm>
+
+namespace b200 {
+
+static double now_ms()
+{
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+/* ------------------------------------------------------------------ engine registry */
+
+static std::mutex g_mu;
+static Engine *g_engine = nullptr;
+static const void *g_engine_key = nullptr;
+static int g_device = -1;
+
+Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g_engine && g_engine_key == (const void *)bwt->bwt) return g_engine;
+	if (g_engine) engine_destroy(g_engine);
+	int dev = g_device;
+	if (dev < 0) {
+		const char *lr = getenv("LOCAL_RANK");
+		dev = lr ? atoi(lr) : 0;
+		int nd = engine_device_count();
+		if (nd > 0) dev %= nd;
+	}
+	g_engine = engine_create(bwt, bns, pac, dev);
+	g_engine_key = (const void *)bwt->bwt;
+	return g_engine;
+}
+
+void engine_select_device(int dev) { g_device = dev; }
+void engine_release()
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g_engine) engine_destroy(g_engine);
+	g_engine = nullptr; g_engine_key = nullptr;
+}
+Engine *engine_current() { return g_engine; }
+
+/* ------------------------------------------------------------------ option packing */
+
+ExtOpt make_ext_opt(const mem_opt_t *opt)
+{
+	ExtOpt e;
+	e.a = opt->a; e.b = opt->b; e.o_del = opt->o_del; e.e_del = opt->e_del; e.o_ins = opt->o_ins; e.e_ins = opt->e_ins;
+	e.w = opt->w; e.zdrop = opt->zdrop; e.pen_clip5 = opt->pen_clip5; e.pen_clip3 = opt->pen_clip3;
+	e.max_sc = 0;
+	for (int i = 0; i < 25; ++i) { e.mat[i] = opt->mat[i]; if (opt->mat[i] > e.max_sc) e.max_sc = opt->mat[i]; }
+	return e;
+}
+
+SwOpt make_sw_opt(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins)
+{
+	SwOpt s;
+	s.o_del = o_del; s.e_del = e_del; s.o_ins = o_ins; s.e_ins = e_ins;
+	int mn = 127, mx = 0;
+	for (int i = 0; i < 25; ++i) { s.mat[i] = mat[i]; if (mat[i] < mn) mn = mat[i]; if (mat[i] > mx) mx = mat[i]; }
+	s.max_sc = mx; s.shift = (256 - (mn & 0xff)) & 0xff;
+	return s;
+}
+
+SeedOpt make_seed_opt(const mem_opt_t *opt)
+{
+	SeedOpt s;
+	s.min_seed_len = opt->min_seed_len;
+	s.split_len = (int)(opt->min_seed_len * opt->split_factor + .499);
+	s.split_width = opt->split_width;
+	s.max_occ = opt->max_occ;
+	s.max_mem_intv = (int)opt->max_mem_intv;
+	return s;
+}
+
+/* ------------------------------------------------------------------ mate rescue (reference src/bwamem_pair.c:111-180) */
+
+struct RescueKey { int end, anchor, r; };
+struct RescueRes { RescueKey key; int64_t rb; SwRes res; };
+
+// window of mem_matesw for orientation r; returns false when the reference would not run SW
+static bool rescue_window(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], const mem_alnreg_t *a,
+                          int l_ms, int r, int64_t *rb_, int64_t *re_, int *is_rev_)
+{
+	const int64_t l_pac = bns->l_pac;
+	int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1), rid = -1;
+	int64_t rb, re;
+	if (!is_rev) {
+		rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
+		re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
+	} else {
+		rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
+		re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
+	}
+	if (rb < 0) rb = 0;
+	if (re > l_pac << 1) re = l_pac << 1;
+	if (rb >= re) return false;
+	bns_clip_window(bns, &rb, (rb + re) >> 1, &re, &rid);
+	*rb_ = rb; *re_ = re; *is_rev_ = is_rev;
+	return a->rid == rid && re - rb >= opt->min_seed_len;
+}
+
+static void rescue_skip_mask(const mem_pestat_t pes[4], int64_t l_pac, const mem_alnreg_t *a, const RegVec &ma, int skip[4])
+{
+	for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+	for (size_t i = 0; i < ma.size(); ++i) {
+		int64_t dist;
+		int r = infer_dir(l_pac, a->rb, ma[i].rb, &dist);
+		if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+	}
+}
+
+// Replays mem_matesw for one anchor with precomputed SW results.  Returns false (and reports the missing job)
+// when a result that the reference would compute here is not in `have`.
+static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4],
+                                 const mem_alnreg_t *a, int l_ms, RegVec &ma, int end, int anchor,
+                                 const std::vector<RescueRes> &have, RescueKey *missing)
+{
+	const int64_t l_pac = bns->l_pac;
+	int skip[4], n = 0;
+	rescue_skip_mask(pes, l_pac, a, ma, skip);
+	if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return true;
+	for (int r = 0; r < 4; ++r) {
+		if (skip[r]) continue;
+		int64_t rb, re;
+		int is_rev;
+		if (rescue_window(opt, bns, pes, a, l_ms, r, &rb, &re, &is_rev)) {
+			const RescueRes *res = nullptr;
+			for (const RescueRes &h : have)
+				if (h.key.end == end && h.key.anchor == anchor && h.key.r == r) { res = &h; break; }
+			if (!res) { missing->end = end; missing->anchor = anchor; missing->r = r; return false; }
+			const SwRes &aln = res->res;
+			if (aln.score >= opt->min_seed_len && aln.qb >= 0) {
+				mem_alnreg_t b;
+				memset(&b, 0, sizeof b);
+				b.rid = a->rid;
+				b.is_alt = a->is_alt;
+				b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+				b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+				b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+				b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+				b.score = aln.score;
+				b.csub = aln.score2;
+				b.secondary = -1;
+				b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+				ma.push_back(b);
+				size_t i, tmp;
+				for (i = 0; i < ma.size() - 1; ++i)
+					if (ma[i].score < b.score) break;
+				tmp = i;
+				for (i = ma.size() - 1; i > tmp; --i) ma[i] = ma[i - 1];
+				ma[i] = b;
+			}
+			++n;
+		}
+		if (n) ma.resize(sort_dedup_patch(opt, 0, 0, 0, (int)ma.size(), ma.data()));
+	}
+	return true;
+}
+
+/* ------------------------------------------------------------------ the hot path */
+
+void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                  int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	Engine *eng = engine_for(bwt, bns, pac);
+	Stats &st = engine_stats(eng);
+	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
+	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
+	const double t_start = now_ms();
+	double t0 = t_start, t1;
+	const bool pe = (opt->flag & MEM_F_PE) != 0;
+	const int64_t l_pac = bns->l_pac;
+
+	// ---- encode (reference src/bwamem.c:1057-1058) and flatten
+	std::vector<int64_t> off(n + 1);
+	off[0] = 0;
+	for (int i = 0; i < n; ++i) off[i + 1] = off[i] + seqs[i].l_seq;
+	std::vector<uint8_t> codes(off[n] + 8);
+	parallel_for(nt, n, 4096, [&](int, int64_t b, int64_t e) {
+		for (int64_t i = b; i < e; ++i) {
+			char *s = seqs[i].seq;
+			uint8_t *d = &codes[off[i]];
+			for (int j = 0; j < seqs[i].l_seq; ++j) {
+				s[j] = s[j] < 4 ? s[j] : (char)kNt4[(uint8_t)s[j]];
+				d[j] = (uint8_t)s[j];
+			}
+		}
+	});
+	st.n_reads = n; st.n_bases = off[n];
+
+	// ---- seeding on the device
+	stage_upload_reads(eng, n, off.data(), codes.data());
+	std::vector<int64_t> seed_off;
+	std::vector<SeedRec> seed_recs;
+	std::vector<int32_t> l_rep;
+	stage_seed(eng, make_seed_opt(opt), seed_off, seed_recs, l_rep);
+	t1 = now_ms(); st.ms_seed = t1 - t0; t0 = t1;
+	st.n_seeds = (int64_t)seed_recs.size();
+
+	// ---- chaining + chain filtering on host threads
+	std::vector<std::vector<HChain>> chains(n);
+	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
+		for (int64_t i = b; i < e; ++i) {
+			build_chains(opt, bns, seqs[i].l_seq, seed_recs.data() + seed_off[i], seed_off[i + 1] - seed_off[i], l_rep[i], chains[i]);
+			filter_chains(opt, chains[i]);
+		}
+	});
+	seed_recs.clear(); seed_recs.shrink_to_fit();
+
+	// ---- mem_flt_chained_seeds (reference src/bwamem.c:571-615): only reads of >= ~730 bp get here
+	{
+		std::vector<SwJob> jobs;
+		std::vector<HSeed *> owner;
+		std::vector<int> long_reads;
+		for (int i = 0; i < n; ++i) {
+			int l_query = seqs[i].l_seq;
+			if (l_query <= 0 || chains[i].empty()) continue;
+			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
+			if (min_l > 0.05f * l_query) continue;
+			long_reads.push_back(i);
+			for (auto &c : chains[i])
+				for (HSeed &s : c.seeds) {
+					s.score = -1;                       // mem_seed_sw's "no need to do SW"
+					if (s.len >= 200) continue;
+					int qb = s.qbeg, qe = s.qbeg + s.len, rid;
+					int64_t rb = s.rbeg, re = s.rbeg + s.len, mid = (rb + re) >> 1;
+					qb -= 50; qb = qb > 0 ? qb : 0;
+					qe += 50; qe = qe < l_query ? qe : l_query;
+					rb -= 50; rb = rb > 0 ? rb : 0;
+					re += 50; re = re < l_pac << 1 ? re : l_pac << 1;
+					if (rb < l_pac && l_pac < re) { if (mid < l_pac) re = l_pac; else rb = l_pac; }
+					if (qe - qb >= 200 || re - rb >= 200) continue;
+					bns_clip_window(bns, &rb, mid, &re, &rid);
+					SwJob j;
+					j.rb = rb; j.tlen = (int)(re - rb); j.read = i; j.is_rev = 0; j.xtra = KSW_XSTART; j.q_beg = qb; j.q_len = qe - qb;
+					jobs.push_back(j);
+					owner.push_back(&s);
+				}
+		}
+		if (!jobs.empty()) {
+			std::vector<SwRes> res;
+			stage_sw(eng, make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins), jobs, res);
+			for (size_t x = 0; x < owner.size(); ++x) owner[x]->score = res[x].score;
+		}
+		for (int i : long_reads) {
+			int l_query = seqs[i].l_seq;
+			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
+			int min_HSP_score = (int)(opt->a * min_l + .499);
+			for (auto &c : chains[i]) {
+				size_t k = 0;
+				for (size_t j = 0; j < c.seeds.size(); ++j) {
+					HSeed s = c.seeds[j];
+					if (s.score < 0 || s.score >= min_HSP_score) {
+						s.score = s.score < 0 ? s.len * opt->a : s.score;
+						c.seeds[k++] = s;
+					}
+				}
+				c.seeds.resize(k);
+			}
+		}
+	}
+
+	// ---- flatten chains for the extension stage
+	std::vector<int32_t> chain_off(n + 1);
+	std::vector<DChain> dchains;
+	std::vector<DSeed> dseeds;
+	std::vector<int32_t> srt;
+	{
+		int64_t nc = 0, ns = 0;
+		for (int i = 0; i < n; ++i) { nc += chains[i].size(); for (auto &c : chains[i]) ns += c.seeds.size(); }
+		dchains.reserve(nc); dseeds.reserve(ns); srt.reserve(ns);
+		std::vector<uint64_t> key;
+		for (int i = 0; i < n; ++i) {
+			chain_off[i] = (int32_t)dchains.size();
+			for (auto &c : chains[i]) {
+				DChain d;
+				d.seed_beg = (int32_t)dseeds.size(); d.n_seeds = (int32_t)c.seeds.size();
+				d.rid = c.rid; d.frac_rep = c.frac_rep; d.rmax0 = d.rmax1 = 0;
+				if (!c.seeds.empty()) {
+					int64_t rmax[2];
+					chain_window(opt, bns, seqs[i].l_seq, c, rmax);
+					d.rmax0 = rmax[0]; d.rmax1 = rmax[1];
+				}
+				key.resize(c.seeds.size());
+				for (size_t k = 0; k < c.seeds.size(); ++k) {
+					const HSeed &s = c.seeds[k];
+					dseeds.push_back({s.rbeg, s.qbeg, s.len, s.score, 0});
+					key[k] = (uint64_t)s.score << 32 | k;
+				}
+				std::sort(key.begin(), key.end());
+				for (size_t k = 0; k < key.size(); ++k) srt.push_back((int32_t)(uint32_t)key[k]);
+				dchains.push_back(d);
+			}
+		}
+		chain_off[n] = (int32_t)dchains.size();
+		st.n_chains = (int64_t)dchains.size();
+	}
+	chains.clear(); chains.shrink_to_fit();
+	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
+
+	// ---- chain2aln / ksw_extend2 on the device
+	std::vector<DReg> dregs;
+	std::vector<int32_t> n_regs;
+	stage_extend(eng, make_ext_opt(opt), chain_off, dchains, dseeds, srt, dregs, n_regs);
+	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
+
+	// ---- mem_sort_dedup_patch + ALT marking (reference src/bwamem.c:1073-1085)
+	std::vector<RegVec> regs(n);
+	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
+		for (int64_t i = b; i < e; ++i) {
+			int nr = n_regs[i];
+			if (nr == 0) continue;
+			int64_t base = chain_off[i] < chain_off[i + 1] ? dchains[chain_off[i]].seed_beg : 0;
+			RegVec &rv = regs[i];
+			rv.resize(nr);
+			for (int k = 0; k < nr; ++k) {
+				const DReg &d = dregs[base + k];
+				mem_alnreg_t &a = rv[k];
+				memset(&a, 0, sizeof a);
+				a.rb = d.rb; a.re = d.re; a.qb = d.qb; a.qe = d.qe; a.rid = d.rid; a.score = d.score; a.truesc = d.truesc;
+				a.w = d.w; a.seedcov = d.seedcov; a.seedlen0 = d.seedlen0; a.frac_rep = d.frac_rep;
+			}
+			rv.resize(sort_dedup_patch(opt, bns, pac, (uint8_t *)seqs[i].seq, nr, rv.data()));
+			for (auto &p : rv)
+				if (p.rid >= 0 && bns->anns[p.rid].is_alt) p.is_alt = 1;
+		}
+	});
+	dregs.clear(); dregs.shrink_to_fit();
+	t1 = now_ms(); st.ms_regs_host = t1 - t0; t0 = t1;
+
+	// ---- insert-size statistics: the one chunk-global reduction (reference src/bwamem.c:1226-1229)
+	mem_pestat_t pes[4];
+	if (pe) {
+		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
+		else pestat(opt, l_pac, n, regs.data(), pes);
+	}
+
+	// ---- mate rescue: SW jobs on the device, then the sequential insert/skip logic replayed per pair
+	if (pe && !(opt->flag & MEM_F_NO_RESCUE)) {
+		const int n_pairs = n >> 1;
+		const int xtra_base = KSW_XSUBO | KSW_XSTART | (opt->min_seed_len * opt->a);
+		SwOpt so = make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins);
+		std::vector<int> pending(n_pairs);
+		for (int i = 0; i < n_pairs; ++i) pending[i] = i;
+		std::vector<std::vector<RescueKey>> want(n_pairs);           // jobs to run this round, by pair
+		std::unordered_map<int, std::vector<RescueRes>> known;       // results carried over by deferred pairs
+		// round 0: every (anchor, orientation) not ruled out by the mate's pre-rescue regions
+		parallel_for(nt, n_pairs, 1024, [&](int, int64_t b, int64_t e) {
+			for (int64_t p = b; p < e; ++p) {
+				for (int i = 0; i < 2; ++i) {
+					const RegVec &ai = regs[p << 1 | i], &ma = regs[p << 1 | !i];
+					int l_ms = seqs[p << 1 | !i].l_seq;
+					int nb = 0;
+					for (size_t j = 0; j < ai.size() && nb < opt->max_matesw; ++j) {
+						if (ai[j].score < ai[0].score - opt->pen_unpaired) continue;
+						int skip[4];
+						rescue_skip_mask(pes, l_pac, &ai[j], ma, skip);
+						for (int r = 0; r < 4; ++r) {
+							int64_t rb, re; int is_rev;
+							if (!skip[r] && rescue_window(opt, bns, pes, &ai[j], l_ms, r, &rb, &re, &is_rev))
+								want[p].push_back({i, nb, r});
+						}
+						++nb;
+					}
+				}
+			}
+		});
+		while (!pending.empty()) {
+			std::vector<SwJob> jobs;
+			std::vector<RescueKey> job_key;
+			std::vector<int64_t> first(pending.size() + 1, 0);
+			for (size_t x = 0; x < pending.size(); ++x) {
+				int p = pending[x];
+				for (const RescueKey &k : want[p]) {
+					const RegVec &ai = regs[p << 1 | k.end];
+					int nb = -1; const mem_alnreg_t *a = nullptr;
+					for (size_t j = 0; j < ai.size(); ++j) {
+						if (ai[j].score < ai[0].score - opt->pen_unpaired) continue;
+						if (++nb == k.anchor) { a = &ai[j]; break; }
+					}
+					int l_ms = seqs[p << 1 | !k.end].l_seq;
+					int64_t rb, re; int is_rev;
+					rescue_window(opt, bns, pes, a, l_ms, k.r, &rb, &re, &is_rev);
+					SwJob j;
+					j.rb = rb; j.tlen = (int)(re - rb); j.read = p << 1 | !k.end; j.is_rev = is_rev;
+					j.xtra = xtra_base | (l_ms * opt->a < 250 ? KSW_XBYTE : 0);
+					j.q_beg = 0; j.q_len = l_ms;
+					jobs.push_back(j); job_key.push_back(k);
+				}
+				first[x + 1] = (int64_t)jobs.size();
+			}
+			std::vector<SwRes> res;
+			if (!jobs.empty()) stage_sw(eng, so, jobs, res);
+			std::vector<char> done(pending.size(), 0);
+			std::vector<RescueKey> miss(pending.size());
+			std::vector<std::vector<RescueRes>> carry(pending.size());
+			parallel_for(nt, (int64_t)pending.size(), 1024, [&](int, int64_t b, int64_t e) {
+				std::vector<RescueRes> have;
+				for (int64_t x = b; x < e; ++x) {
+					int p = pending[x];
+					have.clear();
+					auto it = known.find(p);            // read-only during this loop
+					if (it != known.end()) have = it->second;
+					for (int64_t y = first[x]; y < first[x + 1]; ++y) have.push_back({job_key[y], jobs[y].rb, res[y]});
+					RegVec a[2] = { regs[p << 1], regs[p << 1 | 1] };
+					RegVec anchors[2];
+					for (int i = 0; i < 2; ++i)
+						for (size_t j = 0; j < a[i].size(); ++j)
+							if (a[i][j].score >= a[i][0].score - opt->pen_unpaired) anchors[i].push_back(a[i][j]);
+					bool ok = true;
+					for (int i = 0; i < 2 && ok; ++i)
+						for (size_t j = 0; j < anchors[i].size() && (int)j < opt->max_matesw && ok; ++j)
+							ok = rescue_replay_anchor(opt, bns, pes, &anchors[i][j], seqs[p << 1 | !i].l_seq, a[!i], i, (int)j, have, &miss[x]);
+					if (ok) { regs[p << 1].swap(a[0]); regs[p << 1 | 1].swap(a[1]); done[x] = 1; }
+					else carry[x].swap(have);
+				}
+			});
+			std::vector<int> again;
+			for (size_t x = 0; x < pending.size(); ++x) {
+				if (done[x]) continue;
+				int p = pending[x];
+				known[p].swap(carry[x]);
+				want[p].assign(1, miss[x]);
+				again.push_back(p);
+			}
+			pending.swap(again);
+		}
+	}
+	t1 = now_ms(); st.ms_rescue = t1 - t0; t0 = t1;
+
+	// ---- primary marking, pairing, mapQ, CIGAR and SAM text (reference worker2, src/bwamem.c:1187-1203)
+	if (!pe) {
+		parallel_for(nt, n, 256, [&](int, int64_t b, int64_t e) {
+			for (int64_t i = b; i < e; ++i) {
+				mark_primary_se(opt, (int)regs[i].size(), regs[i].data(), n_processed + i);
+				if (opt->flag & MEM_F_PRIMARY5) reorder_primary5(opt->T, regs[i]);
+				reg2sam(opt, bns, pac, &seqs[i], regs[i], 0, 0);
+			}
+		});
+	} else {
+		parallel_for(nt, n >> 1, 256, [&](int, int64_t b, int64_t e) {
+			for (int64_t i = b; i < e; ++i)
+				sam_pe_finish(opt, bns, pac, pes, (uint64_t)((n_processed >> 1) + i), &seqs[i << 1], &regs[i << 1]);
+		});
+	}
+	t1 = now_ms(); st.ms_sam_host = t1 - t0;
+	st.ms_total = t1 - t_start;
+	if (bwa_verbose >= 3)
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f)\n",
+		        "mem_process_seqs", n, st.ms_total * 1e-3, engine_kind(), st.ms_seed, st.ms_chain_host, st.ms_extend,
+		        st.ms_regs_host, st.ms_rescue, st.ms_sam_host);
+}
+
+} // namespace b200

@@ -1,0 +1,70 @@
+// stages.h - interface between the host orchestration (pipeline.cpp) and the device stages.
+//
+// stages_cuda.cu implements it with sm_100a kernels and is the only implementation in the shipped library.
+// tests/hostemu/stages_emu.cpp implements the same interface by looping the per-thread task bodies on the CPU;
+// it exists so that the host orchestration can be unit-tested in a container without a GPU and is never part
+// of the product.
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "../../include/mpibwa_b200.h"
+#include "fm_kernels.h"
+#include "ext_kernels.h"
+#include "sw_kernels.h"
+
+namespace b200 {
+
+struct SeedRec { int64_t rbeg; int32_t qbeg, len; int32_t rid; int32_t pad; };
+
+struct SwJob {
+	int64_t rb;             // first reference position of the target window (forward+reverse coordinate)
+	int32_t tlen;
+	int32_t read;           // index of the query read in the current batch
+	int32_t is_rev;         // use the reverse complement of the read as the query
+	int32_t xtra;
+	int32_t q_beg, q_len;   // sub-range of the read used as query (whole read for mate rescue)
+};
+
+struct GlobalJob {          // banded global alignment + traceback (bwa_gen_cigar2 / ksw_global2)
+	int64_t rb, re;
+	int32_t read, q_beg, q_len, w;
+};
+
+struct Stats : b200_stats_t {};
+
+class Engine;               // owns the device index, streams and scratch
+
+Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device);
+void    engine_destroy(Engine *e);
+Stats  &engine_stats(Engine *e);
+const char *engine_kind();                     // "cuda" or "hostemu"
+int     engine_device_count();
+
+// upload the encoded reads of the batch (codes 0-4, read r at codes[off[r] .. off[r+1]))
+void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes);
+
+// seeding + SA look-up: per read the seed list in mem_chain() order (interval order x SA order), with the
+// contig id already resolved (rid < 0 = bridging, to be dropped by the caller), and l_rep per read.
+void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds,
+                std::vector<int32_t> &l_rep);
+
+// extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); regs of read r are written to
+// regs[first seed index of its first chain ...] and counted in n_regs[r].
+void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
+                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs,
+                  std::vector<int32_t> &n_regs);
+
+// local SW batch against reference windows
+void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);
+
+// generic batches over caller-provided byte buffers (C-ABI b200_*_batch and the single-job wrappers)
+void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
+                        const uint8_t *query, int64_t qbytes, const uint8_t *target, int64_t tbytes);
+void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t *jobs,
+                    const uint8_t *query, int64_t qbytes, const uint8_t *target, int64_t tbytes);
+void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t *off, const uint8_t *codes,
+                        std::vector<int64_t> &intv_off, std::vector<Intv> &intv);
+void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa);
+void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back);
+
+} // namespace b200

@@ -1,0 +1,197 @@
+// TEST-ONLY implementation of mpibwa_b200/csrc/stages.h: runs the per-thread task bodies of the device stages in
+// plain loops on the CPU so that the host orchestration (chaining, dedup, pairing, SAM text, rescue replay) can be
+// checked against the oracle in a container without a GPU.  It is compiled into tests/_build/ only; the shipped
+// libmpibwa_b200.so links stages_cuda.cu and has no CPU execution path.
+#include "../../mpibwa_b200/csrc/stages.h"
+#include "../../mpibwa_b200/csrc/util.h"
+#include <cstring>
+#include <cstdlib>
+
+namespace b200 {
+
+class Engine {
+public:
+	FmView fm;
+	std::vector<int64_t> ctg_off;
+	std::vector<int32_t> ctg_len;
+	Stats stats;
+	int n_reads = 0;
+	std::vector<int64_t> off;
+	std::vector<uint8_t> codes;
+};
+
+Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
+{
+	Engine *e = new Engine();
+	e->fm.bwt = bwt->bwt; e->fm.sa = bwt->sa; e->fm.primary = bwt->primary;
+	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
+	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
+	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
+	for (int i = 0; i < bns->n_seqs; ++i) { e->ctg_off.push_back(bns->anns[i].offset); e->ctg_len.push_back(bns->anns[i].len); }
+	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data(); e->fm.n_ctg = bns->n_seqs;
+	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
+	return e;
+}
+void engine_destroy(Engine *e) { delete e; }
+Stats &engine_stats(Engine *e) { return e->stats; }
+const char *engine_kind() { return "hostemu"; }
+int engine_device_count() { return 1; }
+
+void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes)
+{
+	e->n_reads = n_reads;
+	e->off.assign(off, off + n_reads + 1);
+	e->codes.assign(codes, codes + off[n_reads]);
+	e->codes.resize(off[n_reads] + 8);
+}
+
+void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t *off, const uint8_t *codes,
+                        std::vector<int64_t> &intv_off, std::vector<Intv> &intv)
+{
+	intv_off.assign(n_reads + 1, 0);
+	intv.clear();
+	std::vector<Intv> scratch, out;
+	for (int r = 0; r < n_reads; ++r) {
+		int len = (int)(off[r + 1] - off[r]);
+		int n = 0;
+		if (len >= so.min_seed_len) {
+			scratch.resize(3 * (len + 1));
+			int cap = len + 32;
+			for (;;) {
+				out.resize(cap);
+				n = fm_collect_intv(e->fm, so, len, codes + off[r], out.data(), cap, scratch.data(), &e->stats.fm_occ_blocks);
+				if (n >= 0) break;
+				cap = -n * 2;
+			}
+		}
+		intv.insert(intv.end(), out.begin(), out.begin() + n);
+		intv_off[r + 1] = (int64_t)intv.size();
+	}
+}
+
+void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds,
+                std::vector<int32_t> &l_rep)
+{
+	std::vector<int64_t> io;
+	std::vector<Intv> iv;
+	stage_collect_intv(e, so, e->n_reads, e->off.data(), e->codes.data(), io, iv);
+	e->stats.n_intv = (int64_t)iv.size();
+	seed_off.assign(e->n_reads + 1, 0);
+	l_rep.assign(e->n_reads, 0);
+	seeds.clear();
+	for (int r = 0; r < e->n_reads; ++r) {
+		int b = 0, en = 0, rep = 0;
+		for (int64_t i = io[r]; i < io[r + 1]; ++i) {
+			const Intv &p = iv[i];
+			int sb = (int)(p.info >> 32), se = (int)(uint32_t)p.info;
+			if (p.x2 <= (uint64_t)so.max_occ) continue;
+			if (sb > en) { rep += en - b; b = sb; en = se; }
+			else en = en > se ? en : se;
+		}
+		rep += en - b;
+		l_rep[r] = rep;
+		for (int64_t i = io[r]; i < io[r + 1]; ++i) {
+			const Intv &p = iv[i];
+			int slen = (int)(uint32_t)p.info - (int)(p.info >> 32);
+			int cnt = seed_slots(p.x2, so.max_occ);
+			uint64_t step = seed_step(p.x2, so.max_occ);
+			for (int c = 0; c < cnt; ++c) {
+				int steps;
+				SeedRec s;
+				s.rbeg = (int64_t)fm_sa(e->fm, p.x0 + (uint64_t)c * step, &steps);
+				s.qbeg = (int32_t)(p.info >> 32); s.len = slen; s.pad = 0;
+				s.rid = fm_intv2rid(e->fm, s.rbeg, s.rbeg + s.len);
+				seeds.push_back(s);
+				e->stats.fm_sa_steps += steps; ++e->stats.fm_sa_lookups;
+			}
+		}
+		seed_off[r + 1] = (int64_t)seeds.size();
+	}
+}
+
+void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
+                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs,
+                  std::vector<int32_t> &n_regs)
+{
+	int n = (int)chain_off.size() - 1;
+	regs.assign(seeds.size() + 1, DReg());
+	n_regs.assign(n, 0);
+	std::vector<int32_t> eh;
+	for (int r = 0; r < n; ++r) {
+		int nc = chain_off[r + 1] - chain_off[r];
+		if (nc == 0) continue;
+		int l_query = (int)(e->off[r + 1] - e->off[r]);
+		eh.resize(2 * (l_query + 2));
+		EhStrided acc = { eh.data(), 1 };
+		int calls = 0;
+		int64_t base = chains[chain_off[r]].seed_beg;
+		n_regs[r] = chain2aln_read(eo, e->fm.pac, e->fm.l_pac, l_query, e->codes.data() + e->off[r], &chains[chain_off[r]], nc,
+		                           seeds.data(), srt.data(), acc, &regs[base], &e->stats.extend_cells, &calls);
+		e->stats.n_extend_jobs += calls;
+	}
+}
+
+void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)
+{
+	out.resize(jobs.size());
+	std::vector<uint16_t> H, E;
+	std::vector<uint64_t> b;
+	for (size_t x = 0; x < jobs.size(); ++x) {
+		const SwJob &j = jobs[x];
+		int qpad = j.q_len + 16;
+		H.resize(qpad); E.resize(qpad); b.resize(j.tlen / 2 + 2);
+		Row16 h = { H.data(), 1 }, ee = { E.data(), 1 };
+		List64 bl = { b.data(), 1 };
+		STPac ta = { e->fm.pac, e->fm.l_pac, j.rb };
+		const uint8_t *q = e->codes.data() + e->off[j.read] + j.q_beg;
+		if (j.is_rev) { SQRevComp qa = { q, j.q_len }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &out[x], &e->stats.sw_cells); }
+		else { SQFwd qa = { q }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &out[x], &e->stats.sw_cells); }
+		++e->stats.n_sw_jobs;
+	}
+}
+
+void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
+                        const uint8_t *query, int64_t, const uint8_t *target, int64_t)
+{
+	std::vector<int32_t> eh;
+	for (int64_t x = 0; x < n_jobs; ++x) {
+		b200_extend_job_t &j = jobs[x];
+		eh.resize(2 * (j.qlen + 2));
+		EhStrided acc = { eh.data(), 1 };
+		QFwd qa = { query + j.q_off };
+		TBytes ta = { target + j.t_off };
+		ExtOut o;
+		extend_core(j.qlen, qa, j.tlen, ta, eo, j.w, j.end_bonus, j.h0, acc, &o, &e->stats.extend_cells);
+		j.score = o.score; j.qle = o.qle; j.tle = o.tle; j.gtle = o.gtle; j.gscore = o.gscore; j.max_off = o.max_off;
+	}
+}
+
+void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t *jobs,
+                    const uint8_t *query, int64_t, const uint8_t *target, int64_t)
+{
+	std::vector<uint16_t> H, E;
+	std::vector<uint64_t> b;
+	for (int64_t x = 0; x < n_jobs; ++x) {
+		b200_align_job_t &j = jobs[x];
+		H.resize(j.qlen + 16); E.resize(j.qlen + 16); b.resize(j.tlen / 2 + 2);
+		Row16 h = { H.data(), 1 }, ee = { E.data(), 1 };
+		List64 bl = { b.data(), 1 };
+		SQFwd qa = { query + j.q_off };
+		STBytes ta = { target + j.t_off };
+		SwRes r;
+		sw_align(j.qlen, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &e->stats.sw_cells);
+		j.r.score = r.score; j.r.te = r.te; j.r.qe = r.qe; j.r.score2 = r.score2; j.r.te2 = r.te2; j.r.tb = r.tb; j.r.qb = r.qb;
+	}
+}
+
+void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
+{
+	for (int64_t i = 0; i < n; ++i) sa[i] = fm_sa(e->fm, k[i], nullptr);
+}
+
+void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
+{
+	fm_extend(e->fm, ik, ok, is_back, nullptr);
+}
+
+} // namespace b200

@@ -1,0 +1,128 @@
+/* b200_driver - minimal single-process stand-in for the mpiBWA chunk loop, driving the B200 alignment core through
+ * its C ABI exactly like the MPI hosts do (reference src/mainParallel.c:1146-1493): parse a fastq chunk in place into
+ * bseq1_t (src/mainParallel.c:1257-1304), call mem_process_seqs, write seqs[i].sam in input order.
+ * Chunks follow the reference rule "close when bases > maxsiz" (src/parallel_aux.c:1532-1549; maxsiz = K/2 of R1
+ * for same-size pairs, K of R1+R2 for trimmed pairs with a running n_processed, K for single-end).
+ * With -r RANK -n NRANKS chunk c is taken by rank c % NRANKS (the MPI hosts claim chunks from a shared counter;
+ * a static round-robin keeps runs reproducible) and only that rank's records are written.
+ *
+ * usage: b200_driver [-K bases] [-t threads] [-T] [-H] [-r rank -n nranks] [-d device] <idxprefix|.map> <r1.fq> [r2.fq]
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <ctype.h>
+#include <unistd.h>
+#include <time.h>
+#include "mpibwa_b200.h"
+
+static char *slurp(const char *fn, size_t *len)
+{
+	FILE *fp = fopen(fn, "rb");
+	char *buf;
+	if (!fp) { perror(fn); exit(1); }
+	fseek(fp, 0, SEEK_END); *len = ftell(fp); fseek(fp, 0, SEEK_SET);
+	buf = malloc(*len + 1);
+	if (fread(buf, 1, *len, fp) != *len) { perror("fread"); exit(1); }
+	buf[*len] = 0;
+	fclose(fp);
+	return buf;
+}
+
+static size_t parse_fastq(char *buf, size_t len, bseq1_t **out)
+{
+	size_t n = 0, m = 0, line = 0;
+	bseq1_t *s = 0;
+	char *p = buf, *q = buf, *e = buf + len;
+	while (q < e) {
+		if (*q != '\n') { ++q; continue; }
+		*q = 0;
+		switch (line & 3) {
+		case 0:
+			if (n == m) { m = m ? m << 1 : 1024; s = realloc(s, m * sizeof(bseq1_t)); }
+			memset(&s[n], 0, sizeof(bseq1_t));
+			s[n].name = p + 1;
+			while (*p && !isspace((unsigned char)*p)) ++p;
+			if (p - 2 > s[n].name && *(p-2) == '/' && isdigit((unsigned char)*(p-1))) *(p-2) = 0;
+			if (*p) *p = 0;
+			break;
+		case 1: s[n].seq = p; s[n].l_seq = (int)(q - p); break;
+		case 2: break;
+		case 3: s[n].qual = p; ++n; break;
+		}
+		p = ++q; ++line;
+	}
+	*out = s;
+	return n;
+}
+
+static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+int main(int argc, char **argv)
+{
+	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0;
+	long K = 0;
+	mem_opt_t *opt = mem_opt_init();
+	while ((c = getopt(argc, argv, "K:t:THv:r:n:d:")) >= 0) {
+		if (c == 'K') K = atol(optarg);
+		else if (c == 't') n_threads = atoi(optarg);
+		else if (c == 'T') trimmed = 1;
+		else if (c == 'H') header = 1;
+		else if (c == 'v') bwa_verbose = atoi(optarg);
+		else if (c == 'r') rank = atoi(optarg);
+		else if (c == 'n') nranks = atoi(optarg);
+		else if (c == 'd') device = atoi(optarg);
+	}
+	if (argc - optind < 2) { fprintf(stderr, "usage: b200_driver [-K n] [-t n] [-T] [-H] [-r rank -n nranks] [-d dev] idx r1.fq [r2.fq]\n"); return 1; }
+	opt->n_threads = n_threads;
+	if (K <= 0) K = (long)opt->chunk_size * n_threads;
+	int paired = argc - optind >= 3;
+	if (paired) opt->flag |= MEM_F_PE;
+	bwaidx_t *idx;
+	size_t la = strlen(argv[optind]);
+	if (la > 4 && strcmp(argv[optind] + la - 4, ".map") == 0) {
+		size_t l_mem;
+		uint8_t *mem = (uint8_t *)slurp(argv[optind], &l_mem);
+		idx = calloc(1, sizeof(bwaidx_t));
+		bwa_mem2idx((int64_t)l_mem, mem, idx);
+	} else idx = bwa_idx_load(argv[optind], BWA_IDX_ALL);
+	if (!idx) return 1;
+	b200_gpu_init(idx, device);
+	size_t l1, l2 = 0, n1, n2 = 0, i;
+	char *b1 = slurp(argv[optind+1], &l1), *b2 = 0;
+	bseq1_t *s1, *s2 = 0;
+	n1 = parse_fastq(b1, l1, &s1);
+	if (paired) { b2 = slurp(argv[optind+2], &l2); n2 = parse_fastq(b2, l2, &s2); if (n1 != n2) { fprintf(stderr, "unequal read counts\n"); return 1; } }
+	if (header && rank == 0)
+		for (i = 0; i < (size_t)idx->bns->n_seqs; ++i)
+			printf("@SQ\tSN:%s\tLN:%d\n", idx->bns->anns[i].name, idx->bns->anns[i].len);
+	long maxsiz = paired && !trimmed ? K / 2 : K;
+	size_t beg = 0, n_chunks = 0, mine = 0;
+	long bases = 0;
+	int64_t n_processed = 0;
+	double t_mem = 0;
+	bseq1_t *seqs = malloc((paired ? 2 : 1) * n1 * sizeof(bseq1_t));
+	for (i = 0; i < n1; ++i) {
+		bases += s1[i].l_seq;
+		if (paired && trimmed) bases += s2[i].l_seq;
+		if (bases > maxsiz || i + 1 == n1) {
+			if ((int)(n_chunks % nranks) == rank) {
+				size_t k, n = 0;
+				for (k = beg; k <= i; ++k) {
+					seqs[n++] = s1[k];
+					if (paired) seqs[n++] = s2[k];
+				}
+				double t0 = now();
+				mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, 0);
+				t_mem += now() - t0;
+				n_processed += n;
+				for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }
+				mine += n;
+			}
+			beg = i + 1; bases = 0; ++n_chunks;
+		}
+	}
+	fprintf(stderr, "[b200_driver] rank=%d reads=%zu chunks=%zu mem_process_seqs_sec=%.3f\n", rank, mine, n_chunks, t_mem);
+	b200_gpu_release();
+	return 0;
+}

@@ -1,0 +1,660 @@
+// stages_cuda.cu - the device stages of the alignment core (sm_100a).  The only implementation of stages.h that is
+// linked into libmpibwa_b200.so; there is no CPU execution path (every entry aborts when CUDA is unusable).
+//
+// Data resident in HBM for the life of the engine (uploaded once from the .map image / bwa_idx_load result):
+//   bwt   occ-interleaved BWT, 64-byte blocks (uint64 occ[4] | 128 two-bit symbols)   reference src/bwt.h:72-78
+//   sa    suffix-array samples (every sa_intv-th row)                                 reference src/bwt.c:86-96
+//   pac   2-bit forward strand                                                         reference src/bntseq.c:224-225
+//   contig offset/length tables                                                        reference src/bntseq.h:44-51
+// An L2 access-policy window (persisting) is laid over the BWT for the seeding kernels.
+//
+// Per chunk: encoded reads are uploaded once (stage_upload_reads) and stay resident for seeding, extension and
+// mate rescue; the kernels in ksw_extend_kernel.cuh / ksw_align_kernel.cuh / smem_kernel.cuh do the work.
+#include "stages.h"
+#include "util.h"
+#include <cuda_runtime.h>
+#include <cub/cub.cuh>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace b200 {
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	fprintf(stderr, "[mpibwa_b200] CUDA error %s at %s:%d: %s\n", cudaGetErrorName(e_), __FILE__, __LINE__, cudaGetErrorString(e_)); \
+	abort(); } } while (0)
+
+static void die(const char *msg) { fprintf(stderr, "[mpibwa_b200] %s\n", msg); abort(); }
+
+// growable device buffer
+struct DevBuf {
+	void *p = nullptr; size_t cap = 0;
+	void *need(size_t bytes)
+	{
+		if (bytes > cap) {
+			if (p) CK(cudaFree(p));
+			size_t n = bytes + (bytes >> 2) + 256;
+			CK(cudaMalloc(&p, n));
+			cap = n;
+		}
+		return p;
+	}
+	template <class T> T *as(size_t n) { return (T *)need(n * sizeof(T)); }
+	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Counters { unsigned long long occ_blocks, sa_steps, ext_cells, ext_calls, sw_cells; };
+
+class Engine {
+public:
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	FmView fm;                     // device pointers
+	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_ctg_off = nullptr, *d_ctg_len = nullptr;
+	size_t bwt_bytes = 0;
+	Stats stats;
+	// resident reads of the current chunk
+	int n_reads = 0, max_len = 0;
+	std::vector<int64_t> h_off;
+	DevBuf d_off, d_codes;
+	// scratch
+	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
+	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
+	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
+	Counters *d_cnt = nullptr;
+
+	void tic() { CK(cudaEventRecord(ev0, stream)); }
+	double toc()
+	{
+		float ms = 0;
+		CK(cudaEventRecord(ev1, stream));
+		CK(cudaEventSynchronize(ev1));
+		CK(cudaEventElapsedTime(&ms, ev0, ev1));
+		return ms;
+	}
+	void h2d(void *dst, const void *src, size_t n)
+	{
+		if (!n) return;
+		CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, stream));
+		stats.h2d_bytes += (int64_t)n;
+	}
+	void d2h(void *dst, const void *src, size_t n)
+	{
+		if (!n) return;
+		CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
+		stats.d2h_bytes += (int64_t)n;
+	}
+	void sync() { CK(cudaStreamSynchronize(stream)); }
+	void zero_counters() { CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), stream)); }
+	Counters read_counters()
+	{
+		Counters c;
+		CK(cudaMemcpyAsync(&c, d_cnt, sizeof c, cudaMemcpyDeviceToHost, stream));
+		sync();
+		return c;
+	}
+};
+
+int engine_device_count()
+{
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+const char *engine_kind() { return "cuda"; }
+Stats &engine_stats(Engine *e) { return e->stats; }
+
+Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
+{
+	int nd = engine_device_count();
+	if (nd <= 0) die("no usable CUDA device: the alignment core has no CPU path (sm_100a kernels only)");
+	if (device < 0 || device >= nd) die("requested CUDA device does not exist");
+	Engine *e = new Engine();
+	e->device = device;
+	CK(cudaSetDevice(device));
+	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&e->ev0));
+	CK(cudaEventCreate(&e->ev1));
+	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
+	e->bwt_bytes = (size_t)bwt->bwt_size * 4;
+	size_t sa_bytes = (size_t)bwt->n_sa * 8, pac_bytes = (size_t)(bns->l_pac / 4 + 1);
+	CK(cudaMalloc(&e->d_bwt, e->bwt_bytes + 64));
+	CK(cudaMalloc(&e->d_sa, sa_bytes));
+	CK(cudaMalloc(&e->d_pac, pac_bytes + 16));
+	CK(cudaMalloc(&e->d_ctg_off, sizeof(int64_t) * bns->n_seqs));
+	CK(cudaMalloc(&e->d_ctg_len, sizeof(int32_t) * bns->n_seqs));
+	CK(cudaMalloc(&e->d_cnt, sizeof(Counters)));
+	CK(cudaMemcpy(e->d_bwt, bwt->bwt, e->bwt_bytes, cudaMemcpyHostToDevice));
+	CK(cudaMemset((char *)e->d_bwt + e->bwt_bytes, 0, 64));
+	CK(cudaMemcpy(e->d_sa, bwt->sa, sa_bytes, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->d_pac, pac, pac_bytes, cudaMemcpyHostToDevice));
+	CK(cudaMemset((char *)e->d_pac + pac_bytes, 0, 16));
+	std::vector<int64_t> co(bns->n_seqs);
+	std::vector<int32_t> cl(bns->n_seqs);
+	for (int i = 0; i < bns->n_seqs; ++i) { co[i] = bns->anns[i].offset; cl[i] = bns->anns[i].len; }
+	CK(cudaMemcpy(e->d_ctg_off, co.data(), co.size() * 8, cudaMemcpyHostToDevice));
+	CK(cudaMemcpy(e->d_ctg_len, cl.data(), cl.size() * 4, cudaMemcpyHostToDevice));
+	FmView &fm = e->fm;
+	fm.bwt = (const uint32_t *)e->d_bwt; fm.sa = (const uint64_t *)e->d_sa;
+	fm.primary = bwt->primary;
+	for (int i = 0; i < 5; ++i) fm.L2[i] = bwt->L2[i];
+	fm.seq_len = bwt->seq_len; fm.sa_intv = bwt->sa_intv;
+	fm.pac = (const uint8_t *)e->d_pac; fm.l_pac = bns->l_pac;
+	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
+	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
+
+	// L2 persistence window over the occ/BWT blocks (north star: "L2-persistence windows for the hot Occ blocks")
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+		size_t persist = (size_t)prop.persistingL2CacheMaxSize;
+		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
+		cudaStreamAttrValue attr;
+		memset(&attr, 0, sizeof attr);
+		size_t win = std::min(e->bwt_bytes, (size_t)prop.accessPolicyMaxWindowSize);
+		attr.accessPolicyWindow.base_ptr = e->d_bwt;
+		attr.accessPolicyWindow.num_bytes = win;
+		attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
+		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+	}
+	return e;
+}
+
+void engine_destroy(Engine *e)
+{
+	if (!e) return;
+	cudaSetDevice(e->device);
+	cudaStreamSynchronize(e->stream);
+	DevBuf *bufs[] = { &e->d_off, &e->d_codes, &e->b_intv, &e->b_scr, &e->b_nintv, &e->b_ioff, &e->b_civ, &e->b_slots, &e->b_soff,
+		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
+		&e->b_nregs, &e->b_eh, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
+	for (DevBuf *b : bufs) b->release();
+	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
+	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+	cudaStreamDestroy(e->stream);
+	delete e;
+}
+
+/* ------------------------------------------------------------------ small device helpers */
+
+__device__ __forceinline__ void warp_add(unsigned long long *dst, long long v)
+{
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, (unsigned long long)v);
+}
+
+static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+/* ------------------------------------------------------------------ seeding */
+
+__global__ void __launch_bounds__(128) k_collect_intv(FmView fm, SeedOpt so, int n_reads, const int64_t *__restrict__ off,
+                                                      const uint8_t *__restrict__ codes, Intv *out, int cap, Intv *scratch,
+                                                      int scr_per_read, int32_t *n_intv, Counters *cnt)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t blocks = 0;
+	if (r < n_reads) {
+		int len = (int)(off[r + 1] - off[r]);
+		int n = 0;
+		if (len >= so.min_seed_len)
+			n = fm_collect_intv(fm, so, len, codes + off[r], out + (int64_t)r * cap, cap, scratch + (int64_t)r * scr_per_read, &blocks);
+		n_intv[r] = n;
+	}
+	warp_add(&cnt->occ_blocks, blocks);
+}
+
+// per read: l_rep (reference src/bwamem.c:261-269) and compaction of the interval list with per-interval slot counts
+__global__ void k_compact_intv(SeedOpt so, int n_reads, const Intv *__restrict__ in, int cap, const int32_t *__restrict__ n_intv,
+                               const int64_t *__restrict__ ioff, Intv *civ, int32_t *slots, int32_t *l_rep)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	int n = n_intv[r];
+	const Intv *p = in + (int64_t)r * cap;
+	int64_t o = ioff[r];
+	int b = 0, e = 0, rep = 0;
+	for (int i = 0; i < n; ++i) {
+		Intv v = p[i];
+		int sb = (int)(v.info >> 32), se = (int)(uint32_t)v.info;
+		civ[o + i] = v;
+		slots[o + i] = seed_slots(v.x2, so.max_occ);
+		if (v.x2 <= (uint64_t)so.max_occ) continue;
+		if (sb > e) { rep += e - b; b = sb; e = se; }
+		else e = e > se ? e : se;
+	}
+	rep += e - b;
+	if (l_rep) l_rep[r] = rep;
+}
+
+// one thread per suffix-array look-up
+__global__ void __launch_bounds__(256) k_sa_seeds(FmView fm, SeedOpt so, int64_t n_slots, int64_t n_intv, const Intv *__restrict__ civ,
+                                                   const int64_t *__restrict__ soff, SeedRec *seeds, Counters *cnt)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	long long steps_total = 0;
+	if (t < n_slots) {
+		int64_t lo = 0, hi = n_intv;            // largest i with soff[i] <= t
+		while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (soff[mid] <= t) lo = mid; else hi = mid; }
+		Intv p = civ[lo];
+		int c = (int)(t - soff[lo]);
+		uint64_t step = seed_step(p.x2, so.max_occ);
+		int steps;
+		SeedRec s;
+		s.rbeg = (int64_t)fm_sa(fm, p.x0 + (uint64_t)c * step, &steps);
+		s.qbeg = (int32_t)(p.info >> 32);
+		s.len = (int32_t)(uint32_t)p.info - s.qbeg;
+		s.rid = fm_intv2rid(fm, s.rbeg, s.rbeg + s.len);
+		s.pad = 0;
+		seeds[t] = s;
+		steps_total = steps;
+	}
+	warp_add(&cnt->sa_steps, steps_total);
+}
+
+__global__ void k_gather_seed_off(int n_reads, const int64_t *__restrict__ ioff, const int64_t *__restrict__ soff, int64_t *seed_off)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r <= n_reads) seed_off[r] = soff[ioff[r]];
+}
+
+__global__ void k_sa_plain(FmView fm, int64_t n, const uint64_t *__restrict__ k, uint64_t *sa)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) sa[t] = fm_sa(fm, k[t], nullptr);
+}
+
+__global__ void k_fm_extend1(FmView fm, Intv ik, Intv *ok, int is_back)
+{
+	Intv o[4];
+	fm_extend(fm, ik, o, is_back, nullptr);
+	for (int i = 0; i < 4; ++i) ok[i] = o[i];
+}
+
+__global__ void k_widen(int64_t n, const int32_t *__restrict__ in, int64_t *out)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) out[t] = in[t];
+}
+
+// exclusive prefix sum of n int32 counts into int64 offsets (cub::DeviceScan on a widened copy)
+static void exclusive_scan(Engine *e, const int32_t *in, int64_t *out, int64_t n)
+{
+	int64_t *wide = e->b_wide.as<int64_t>(n);
+	k_widen<<<grid_for(n, 256), 256, 0, e->stream>>>(n, in, wide);
+	CK(cudaGetLastError());
+	size_t tmp = 0;
+	CK(cub::DeviceScan::ExclusiveSum(nullptr, tmp, wide, out, n, e->stream));
+	void *d = e->b_cub.need(tmp);
+	CK(cub::DeviceScan::ExclusiveSum(d, tmp, wide, out, n, e->stream));
+	e->stats.n_launches += 2;
+}
+
+void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes)
+{
+	CK(cudaSetDevice(e->device));
+	e->n_reads = n_reads;
+	e->h_off.assign(off, off + n_reads + 1);
+	e->max_len = 0;
+	for (int i = 0; i < n_reads; ++i) e->max_len = std::max(e->max_len, (int)(off[i + 1] - off[i]));
+	e->h2d(e->d_off.as<int64_t>(n_reads + 1), off, sizeof(int64_t) * (n_reads + 1));
+	e->h2d(e->d_codes.as<uint8_t>(off[n_reads] + 16), codes, (size_t)off[n_reads]);
+	e->sync();
+}
+
+// steps A-C for reads [r0, r1): leaves the compacted interval list in b_civ, slot counts in b_slots, offsets in b_ioff
+static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const int64_t *d_off, const uint8_t *d_codes, int max_len,
+                           bool want_lrep)
+{
+	const int n = r1 - r0;
+	int cap = max_len + 32;
+	const int scr = 3 * (max_len + 1);
+	int32_t *n_intv = e->b_nintv.as<int32_t>(n + 1);
+	for (;;) {
+		Intv *out = e->b_intv.as<Intv>((size_t)n * cap);
+		Intv *scratch = e->b_scr.as<Intv>((size_t)n * scr);
+		k_collect_intv<<<grid_for(n, 128), 128, 0, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, scratch, scr, n_intv, e->d_cnt);
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+		// overflow check (rare: more intervals than len+32)
+		std::vector<int32_t> h(n);
+		e->d2h(h.data(), n_intv, sizeof(int32_t) * n);
+		e->sync();
+		int worst = 0;
+		for (int v : h) worst = std::min(worst, v);
+		if (worst >= 0) break;
+		cap = -worst + 32;
+	}
+	CK(cudaMemsetAsync(n_intv + n, 0, sizeof(int32_t), e->stream));
+	int64_t *ioff = e->b_ioff.as<int64_t>(n + 1);
+	exclusive_scan(e, n_intv, ioff, n + 1);
+	int64_t total = 0;
+	e->d2h(&total, ioff + n, sizeof(int64_t));
+	e->sync();
+	Intv *civ = e->b_civ.as<Intv>(total + 1);
+	int32_t *slots = e->b_slots.as<int32_t>(total + 1);
+	int32_t *lrep = want_lrep ? e->b_lrep.as<int32_t>(n) : nullptr;
+	k_compact_intv<<<grid_for(n, 128), 128, 0, e->stream>>>(so, n, (const Intv *)e->b_intv.p, cap, n_intv, ioff, civ, slots, lrep);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	return total;
+}
+
+static int seed_sub_batch(int max_len)
+{
+	// scratch per read: (3*(len+1) + len+32) intervals of 32 bytes; keep one sub-batch under ~12 GB
+	size_t per = (size_t)(4 * max_len + 40) * sizeof(Intv);
+	size_t n = ((size_t)12 << 30) / per;
+	return (int)std::max<size_t>(1024, std::min<size_t>(n, 1 << 20));
+}
+
+void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t *off, const uint8_t *codes,
+                        std::vector<int64_t> &intv_off, std::vector<Intv> &intv)
+{
+	stage_upload_reads(e, n_reads, off, codes);
+	intv_off.assign(n_reads + 1, 0);
+	intv.clear();
+	e->zero_counters();
+	const int sub = seed_sub_batch(e->max_len);
+	for (int r0 = 0; r0 < n_reads; r0 += sub) {
+		int r1 = std::min(n_reads, r0 + sub), n = r1 - r0;
+		int64_t total = run_collect(e, so, r0, r1, (const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, e->max_len, false);
+		std::vector<int64_t> io(n + 1);
+		e->d2h(io.data(), e->b_ioff.p, sizeof(int64_t) * (n + 1));
+		size_t base = intv.size();
+		intv.resize(base + total);
+		e->d2h(intv.data() + base, e->b_civ.p, sizeof(Intv) * total);
+		e->sync();
+		for (int i = 0; i <= n; ++i) intv_off[r0 + i] = (int64_t)base + io[i];
+	}
+	Counters c = e->read_counters();
+	e->stats.fm_occ_blocks += (int64_t)c.occ_blocks;
+	e->stats.n_intv += (int64_t)intv.size();
+}
+
+void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds, std::vector<int32_t> &l_rep)
+{
+	CK(cudaSetDevice(e->device));
+	const int n_reads = e->n_reads;
+	seed_off.assign(n_reads + 1, 0);
+	l_rep.assign(n_reads, 0);
+	seeds.clear();
+	e->zero_counters();
+	const int sub = seed_sub_batch(e->max_len);
+	double ms_smem = 0, ms_sa = 0;
+	for (int r0 = 0; r0 < n_reads; r0 += sub) {
+		int r1 = std::min(n_reads, r0 + sub), n = r1 - r0;
+		e->tic();
+		int64_t n_intv = run_collect(e, so, r0, r1, (const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, e->max_len, true);
+		ms_smem += e->toc();
+		e->stats.n_intv += n_intv;
+		e->tic();
+		int64_t *soff = e->b_soff.as<int64_t>(n_intv + 2);
+		CK(cudaMemsetAsync((int32_t *)e->b_slots.p + n_intv, 0, sizeof(int32_t), e->stream));
+		exclusive_scan(e, (const int32_t *)e->b_slots.p, soff, n_intv + 1);
+		int64_t n_slots = 0;
+		e->d2h(&n_slots, soff + n_intv, sizeof(int64_t));
+		e->sync();
+		SeedRec *d_seeds = e->b_seeds.as<SeedRec>(n_slots + 1);
+		if (n_slots > 0) {
+			k_sa_seeds<<<grid_for(n_slots, 256), 256, 0, e->stream>>>(e->fm, so, n_slots, n_intv, (const Intv *)e->b_civ.p, soff, d_seeds, e->d_cnt);
+			CK(cudaGetLastError());
+			e->stats.n_launches += 1;
+		}
+		int64_t *d_seed_off = e->b_seedoff.as<int64_t>(n + 1);
+		k_gather_seed_off<<<grid_for(n + 1, 256), 256, 0, e->stream>>>(n, (const int64_t *)e->b_ioff.p, soff, d_seed_off);
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+		ms_sa += e->toc();
+		size_t base = seeds.size();
+		seeds.resize(base + n_slots);
+		std::vector<int64_t> so_h(n + 1);
+		e->d2h(seeds.data() + base, d_seeds, sizeof(SeedRec) * n_slots);
+		e->d2h(so_h.data(), d_seed_off, sizeof(int64_t) * (n + 1));
+		e->d2h(l_rep.data() + r0, e->b_lrep.p, sizeof(int32_t) * n);
+		e->sync();
+		for (int i = 0; i <= n; ++i) seed_off[r0 + i] = (int64_t)base + so_h[i];
+		e->stats.fm_sa_lookups += n_slots;
+	}
+	Counters c = e->read_counters();
+	e->stats.fm_occ_blocks += (int64_t)c.occ_blocks;
+	e->stats.fm_sa_steps += (int64_t)c.sa_steps;
+	e->stats.ms_k_smem += ms_smem;
+	e->stats.ms_k_sa += ms_sa;
+}
+
+void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
+{
+	CK(cudaSetDevice(e->device));
+	if (n <= 0) return;
+	uint64_t *dk = e->b_q.as<uint64_t>(n), *ds = e->b_t.as<uint64_t>(n);
+	e->h2d(dk, k, sizeof(uint64_t) * n);
+	k_sa_plain<<<grid_for(n, 256), 256, 0, e->stream>>>(e->fm, n, dk, ds);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	e->d2h(sa, ds, sizeof(uint64_t) * n);
+	e->sync();
+}
+
+void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
+{
+	CK(cudaSetDevice(e->device));
+	Intv *d = e->b_t.as<Intv>(4);
+	k_fm_extend1<<<1, 1, 0, e->stream>>>(e->fm, ik, d, is_back);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	e->d2h(ok, d, sizeof(Intv) * 4);
+	e->sync();
+}
+
+/* ------------------------------------------------------------------ extension */
+
+__global__ void __launch_bounds__(128) k_chain2aln(ExtOpt eo, const uint8_t *__restrict__ pac, int64_t l_pac, int n_reads,
+                                                   const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
+                                                   const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains,
+                                                   const DSeed *__restrict__ seeds, int32_t *srt, int32_t *eh, int64_t stride,
+                                                   DReg *regs, int32_t *n_regs, Counters *cnt)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	int calls = 0;
+	if (r < n_reads) {
+		int c0 = chain_off[r], nc = chain_off[r + 1] - c0, n = 0;
+		if (nc > 0) {
+			int l_query = (int)(off[r + 1] - off[r]);
+			EhStrided acc = { eh + r, stride };
+			n = chain2aln_read(eo, pac, l_pac, l_query, codes + off[r], chains + c0, nc, seeds, srt, acc,
+			                   regs + chains[c0].seed_beg, &cells, &calls);
+		}
+		n_regs[r] = n;
+	}
+	warp_add(&cnt->ext_cells, cells);
+	warp_add(&cnt->ext_calls, calls);
+}
+
+void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
+                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int32_t> &n_regs)
+{
+	CK(cudaSetDevice(e->device));
+	const int n = (int)chain_off.size() - 1;
+	if (n != e->n_reads) die("stage_extend: chain table does not match the uploaded reads");
+	regs.assign(seeds.size() + 1, DReg());
+	n_regs.assign(n, 0);
+	if (n == 0) return;
+	e->zero_counters();
+	int32_t *d_co = e->b_chain_off.as<int32_t>(n + 1);
+	DChain *d_ch = e->b_chains.as<DChain>(chains.size() + 1);
+	DSeed *d_se = e->b_dseeds.as<DSeed>(seeds.size() + 1);
+	int32_t *d_srt = e->b_srt.as<int32_t>(srt.size() + 1);
+	DReg *d_regs = e->b_regs.as<DReg>(seeds.size() + 1);
+	int32_t *d_nr = e->b_nregs.as<int32_t>(n);
+	e->h2d(d_co, chain_off.data(), sizeof(int32_t) * (n + 1));
+	e->h2d(d_ch, chains.data(), sizeof(DChain) * chains.size());
+	e->h2d(d_se, seeds.data(), sizeof(DSeed) * seeds.size());
+	e->h2d(d_srt, srt.data(), sizeof(int32_t) * srt.size());
+	int64_t stride = ((int64_t)n + 31) & ~31ll;
+	int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
+	e->tic();
+	k_chain2aln<<<grid_for(n, 128), 128, 0, e->stream>>>(eo, e->fm.pac, e->fm.l_pac, n, (const int64_t *)e->d_off.p,
+		(const uint8_t *)e->d_codes.p, d_co, d_ch, d_se, d_srt, d_eh, stride, d_regs, d_nr, e->d_cnt);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	e->stats.ms_k_extend += e->toc();
+	e->d2h(regs.data(), d_regs, sizeof(DReg) * seeds.size());
+	e->d2h(n_regs.data(), d_nr, sizeof(int32_t) * n);
+	Counters c = e->read_counters();
+	e->stats.extend_cells += (int64_t)c.ext_cells;
+	e->stats.n_extend_jobs += (int64_t)c.ext_calls;
+}
+
+__global__ void __launch_bounds__(128) k_extend_bytes(ExtOpt eo, int64_t n_jobs, b200_extend_job_t *jobs, const uint8_t *__restrict__ query,
+                                                      const uint8_t *__restrict__ target, int32_t *eh, int64_t stride, Counters *cnt)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	if (t < n_jobs) {
+		b200_extend_job_t j = jobs[t];
+		EhStrided acc = { eh + t, stride };
+		QFwd qa = { query + j.q_off };
+		TBytes ta = { target + j.t_off };
+		ExtOut o;
+		extend_core(j.qlen, qa, j.tlen, ta, eo, j.w, j.end_bonus, j.h0, acc, &o, &cells);
+		j.score = o.score; j.qle = o.qle; j.tle = o.tle; j.gtle = o.gtle; j.gscore = o.gscore; j.max_off = o.max_off;
+		jobs[t] = j;
+	}
+	warp_add(&cnt->ext_cells, cells);
+}
+
+void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
+                        const uint8_t *query, int64_t qbytes, const uint8_t *target, int64_t tbytes)
+{
+	CK(cudaSetDevice(e->device));
+	if (n_jobs <= 0) return;
+	int max_q = 0;
+	for (int64_t i = 0; i < n_jobs; ++i) max_q = std::max(max_q, jobs[i].qlen);
+	e->zero_counters();
+	b200_extend_job_t *dj = e->b_jobs.as<b200_extend_job_t>(n_jobs);
+	uint8_t *dq = e->b_q.as<uint8_t>(qbytes + 16), *dt = e->b_t.as<uint8_t>(tbytes + 16);
+	e->h2d(dj, jobs, sizeof(b200_extend_job_t) * n_jobs);
+	e->h2d(dq, query, qbytes);
+	e->h2d(dt, target, tbytes);
+	int64_t stride = (n_jobs + 31) & ~31ll;
+	int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (max_q + 2));
+	e->tic();
+	k_extend_bytes<<<grid_for(n_jobs, 128), 128, 0, e->stream>>>(eo, n_jobs, dj, dq, dt, d_eh, stride, e->d_cnt);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	e->stats.ms_k_extend += e->toc();
+	e->d2h(jobs, dj, sizeof(b200_extend_job_t) * n_jobs);
+	Counters c = e->read_counters();
+	e->stats.extend_cells += (int64_t)c.ext_cells;
+	e->stats.n_extend_jobs += n_jobs;
+}
+
+/* ------------------------------------------------------------------ local Smith-Waterman (mate rescue, seed filter) */
+
+__global__ void __launch_bounds__(128) k_sw_jobs(SwOpt so, const uint8_t *__restrict__ pac, int64_t l_pac, int64_t n_jobs,
+                                                 const SwJob *__restrict__ jobs, const int64_t *__restrict__ off,
+                                                 const uint8_t *__restrict__ codes, uint16_t *H, uint16_t *E, uint64_t *B,
+                                                 int64_t stride, SwRes *res, Counters *cnt)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	if (t < n_jobs) {
+		SwJob j = jobs[t];
+		Row16 h = { H + t, stride }, ee = { E + t, stride };
+		List64 bl = { B + t, stride };
+		STPac ta = { pac, l_pac, j.rb };
+		const uint8_t *q = codes + off[j.read] + j.q_beg;
+		SwRes r;
+		if (j.is_rev) { SQRevComp qa = { q, j.q_len }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells); }
+		else { SQFwd qa = { q }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells); }
+		res[t] = r;
+	}
+	warp_add(&cnt->sw_cells, cells);
+}
+
+void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)
+{
+	CK(cudaSetDevice(e->device));
+	out.resize(jobs.size());
+	if (jobs.empty()) return;
+	e->zero_counters();
+	const int64_t sub = 1 << 18;
+	for (int64_t j0 = 0; j0 < (int64_t)jobs.size(); j0 += sub) {
+		int64_t n = std::min<int64_t>(sub, (int64_t)jobs.size() - j0);
+		int max_q = 0, max_t = 0;
+		for (int64_t i = 0; i < n; ++i) { max_q = std::max(max_q, jobs[j0 + i].q_len); max_t = std::max(max_t, jobs[j0 + i].tlen); }
+		SwJob *dj = e->b_jobs.as<SwJob>(n);
+		SwRes *dr = e->b_res.as<SwRes>(n);
+		int64_t stride = (n + 31) & ~31ll;
+		uint16_t *H = e->b_h.as<uint16_t>((size_t)stride * (max_q + 16));
+		uint16_t *E = e->b_e.as<uint16_t>((size_t)stride * (max_q + 16));
+		uint64_t *B = e->b_b.as<uint64_t>((size_t)stride * (max_t / 2 + 2));
+		e->h2d(dj, jobs.data() + j0, sizeof(SwJob) * n);
+		e->tic();
+		k_sw_jobs<<<grid_for(n, 128), 128, 0, e->stream>>>(so, e->fm.pac, e->fm.l_pac, n, dj, (const int64_t *)e->d_off.p,
+			(const uint8_t *)e->d_codes.p, H, E, B, stride, dr, e->d_cnt);
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+		e->stats.ms_k_sw += e->toc();
+		e->d2h(out.data() + j0, dr, sizeof(SwRes) * n);
+		e->sync();
+	}
+	Counters c = e->read_counters();
+	e->stats.sw_cells += (int64_t)c.sw_cells;
+	e->stats.n_sw_jobs += (int64_t)jobs.size();
+}
+
+__global__ void __launch_bounds__(128) k_sw_bytes(SwOpt so, int64_t n_jobs, b200_align_job_t *jobs, const uint8_t *__restrict__ query,
+                                                  const uint8_t *__restrict__ target, uint16_t *H, uint16_t *E, uint64_t *B,
+                                                  int64_t stride, Counters *cnt)
+{
+	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	if (t < n_jobs) {
+		b200_align_job_t j = jobs[t];
+		Row16 h = { H + t, stride }, ee = { E + t, stride };
+		List64 bl = { B + t, stride };
+		SQFwd qa = { query + j.q_off };
+		STBytes ta = { target + j.t_off };
+		SwRes r;
+		sw_align(j.qlen, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells);
+		j.r.score = r.score; j.r.te = r.te; j.r.qe = r.qe; j.r.score2 = r.score2; j.r.te2 = r.te2; j.r.tb = r.tb; j.r.qb = r.qb;
+		jobs[t] = j;
+	}
+	warp_add(&cnt->sw_cells, cells);
+}
+
+void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t *jobs,
+                    const uint8_t *query, int64_t qbytes, const uint8_t *target, int64_t tbytes)
+{
+	CK(cudaSetDevice(e->device));
+	if (n_jobs <= 0) return;
+	int max_q = 0, max_t = 0;
+	for (int64_t i = 0; i < n_jobs; ++i) { max_q = std::max(max_q, jobs[i].qlen); max_t = std::max(max_t, jobs[i].tlen); }
+	e->zero_counters();
+	b200_align_job_t *dj = e->b_jobs.as<b200_align_job_t>(n_jobs);
+	uint8_t *dq = e->b_q.as<uint8_t>(qbytes + 16), *dt = e->b_t.as<uint8_t>(tbytes + 16);
+	e->h2d(dj, jobs, sizeof(b200_align_job_t) * n_jobs);
+	e->h2d(dq, query, qbytes);
+	e->h2d(dt, target, tbytes);
+	int64_t stride = (n_jobs + 31) & ~31ll;
+	uint16_t *H = e->b_h.as<uint16_t>((size_t)stride * (max_q + 16));
+	uint16_t *E = e->b_e.as<uint16_t>((size_t)stride * (max_q + 16));
+	uint64_t *B = e->b_b.as<uint64_t>((size_t)stride * (max_t / 2 + 2));
+	e->tic();
+	k_sw_bytes<<<grid_for(n_jobs, 128), 128, 0, e->stream>>>(so, n_jobs, dj, dq, dt, H, E, B, stride, e->d_cnt);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	e->stats.ms_k_sw += e->toc();
+	e->d2h(jobs, dj, sizeof(b200_align_job_t) * n_jobs);
+	Counters c = e->read_counters();
+	e->stats.sw_cells += (int64_t)c.sw_cells;
+	e->stats.n_sw_jobs += n_jobs;
+}
+
+} // namespace b200

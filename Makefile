@@ -10,7 +10,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-pthread -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS := -O3 -std=c++17 -fPIC -pthread -Wall -Wno-unused-function
 CSRC     := mpibwa_b200/csrc
-HOSTSRC  := $(CSRC)/capi.cpp $(CSRC)/host_align.cpp $(CSRC)/pipeline.cpp
+HOSTSRC  := $(CSRC)/capi.cpp $(CSRC)/host_align.cpp $(CSRC)/pipeline.cpp $(CSRC)/hostshim.cpp
 HDRS     := $(wildcard $(CSRC)/*.h) include/mpibwa_b200.h
 LIB      := mpibwa_b200/libmpibwa_b200.so
 B        := build
@@ -27,7 +27,7 @@ $(B)/%.o: $(CSRC)/%.cu $(HDRS) $(wildcard $(CSRC)/*.cuh)
 	@mkdir -p $(B)
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(B)/$*.ptxas.log || (cat $(B)/$*.ptxas.log; false)
 
-$(LIB): $(B)/capi.o $(B)/host_align.o $(B)/pipeline.o $(B)/stages_cuda.o
+$(LIB): $(B)/capi.o $(B)/host_align.o $(B)/pipeline.o $(B)/hostshim.o $(B)/stages_cuda.o
 	$(NVCC) $(ARCH) -shared -o $@ $^ -cudart static -lpthread
 
 driver: tools/b200_driver

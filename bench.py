@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""bench.py - headline benchmark of the B200 alignment core (contract: see the task statement / DESIGN.md).
+
+Workload (BASELINE.json configs[1]): synthetic 100 Mbp reference (4 contigs, i.i.d. ACGT + 5 % planted diverged
+repeats), wgsim-style 2x150 bp pairs (insert N(400,50), 1 % substitutions, 0.1 % indels, 0.1 % N), chunked with the
+reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call on one chunk.
+
+  value  read pairs/s through mem_process_seqs with the chunk's encoded reads already resident in HBM
+  e2e    read pairs/s from raw fastq bytes in host memory to SAM bytes in host memory (in-place parse, interleave,
+         mem_process_seqs incl. every H2D/D2H copy, SAM concatenation) - the reference-facing call with host buffers
+  roofline / kernels   per device stage: algorithmic work / CUDA-event kernel time vs the measured peak
+  cpu_baseline         the compiled reference (oracle/_ref/ref_driver) on the box's host cores, bounded sample
+
+`--impl reference` times the reference's own CPU mem_process_seqs (oracle/_ref, all host threads) on bounded
+samples of the same workload.  Multi-GPU: one process per GPU (torchrun), full index replica per GPU, reads sharded
+by chunk, no collective on the data path (weak scaling: every rank aligns its own chunks).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CACHE = os.environ.get("B200_BENCH_CACHE", "/tmp/b200_bench_cache")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--ref-bp", type=int, default=100_000_000)
+    p.add_argument("--pairs", type=int, default=1_000_000, help="simulated pairs per rank")
+    p.add_argument("--read-len", type=int, default=150)
+    p.add_argument("-K", type=int, default=100_000_000, dest="K")
+    p.add_argument("--ref-sample-pairs", type=int, default=60_000, help="pairs per step of the CPU reference arm")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ workload
+
+def workload_dir(args):
+    d = os.path.join(CACHE, "ref%d_L%d" % (args.ref_bp, args.read_len))
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def ensure_index(args):
+    """synthetic reference + bwa-compatible index files, cached under CACHE"""
+    import numpy as np
+    from mpibwa_b200 import simulate, index_build
+    d = workload_dir(args)
+    prefix = os.path.join(d, "ref.fa")
+    if not os.path.exists(prefix + ".done"):
+        t = time.time()
+        names, lengths, codes = simulate.make_reference(args.ref_bp, 4, seed=1)
+        index_build.build_index_from_codes(prefix, names, lengths, codes)
+        np.save(os.path.join(d, "codes.npy"), codes)
+        np.save(os.path.join(d, "lengths.npy"), lengths)
+        open(prefix + ".done", "w").write("ok")
+        log("[bench] built %d bp reference + index in %.1f s" % (args.ref_bp, time.time() - t))
+    return prefix
+
+
+def ensure_reads(args, rank, n_pairs, tag="r"):
+    import numpy as np
+    from mpibwa_b200 import simulate
+    d = workload_dir(args)
+    f1 = os.path.join(d, "%s%d_n%d_1.fq" % (tag, rank, n_pairs))
+    f2 = f1[:-4] + "2.fq"
+    if not (os.path.exists(f1 + ".done")):
+        t = time.time()
+        codes = np.load(os.path.join(d, "codes.npy"), mmap_mode="r")
+        lengths = np.load(os.path.join(d, "lengths.npy"))
+        r1, r2 = simulate.simulate_pairs(np.asarray(codes), lengths, n_pairs, read_len=args.read_len, seed=2 + 1000 * rank)
+        open(f1, "wb").write(r1)
+        open(f2, "wb").write(r2)
+        open(f1 + ".done", "w").write("ok")
+        log("[bench] rank %d simulated %d pairs in %.1f s" % (rank, n_pairs, time.time() - t))
+    return f1, f2
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+
+class ClockSampler(threading.Thread):
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.samples, self.reasons, self.max_mhz, self.stop_flag = device, [], set(), None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(device)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # noqa: BLE001
+            self.nv = None
+            log("[bench] NVML unavailable:", e)
+
+    def run(self):
+        while not self.stop_flag and self.nv:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                m = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if m & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.1)
+
+    def result(self):
+        self.stop_flag = True
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+
+def run_ref_driver(prefix, f1, f2, K, threads):
+    drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    r = subprocess.run([drv, "-t", str(threads), "-K", str(K), "-v", "1", prefix, f1, f2], stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE, text=True, check=True)
+    for line in r.stderr.splitlines():
+        if line.startswith("[ref_driver]"):
+            kv = dict(x.split("=") for x in line.split()[1:])
+            return int(kv["reads"]), float(kv["mem_process_seqs_sec"])
+    raise RuntimeError("ref_driver printed no timing line:\n" + r.stderr[-2000:])
+
+
+def slice_fastq(src, dst, first_read, n_reads, rec_bytes):
+    with open(src, "rb") as fi:
+        fi.seek(first_read * rec_bytes)
+        data = fi.read(n_reads * rec_bytes)
+    with open(dst, "wb") as fo:
+        fo.write(data)
+
+
+def record_bytes(path):
+    with open(path, "rb") as fh:
+        return sum(len(fh.readline()) for _ in range(4))
+
+
+def reference_arm(args, prefix):
+    """the reference's own CPU implementation of the path, all host threads, bounded samples of the workload"""
+    cores = os.cpu_count() or 1
+    f1, f2 = ensure_reads(args, 0, args.pairs)
+    rb = record_bytes(f1)
+    n = args.ref_sample_pairs
+    d = workload_dir(args)
+    total_pairs, total_s = 0, 0.0
+    for step in range(args.warmup + args.steps):
+        first = (step * n) % max(1, args.pairs - n)
+        s1, s2 = os.path.join(d, "refsample_1.fq"), os.path.join(d, "refsample_2.fq")
+        slice_fastq(f1, s1, first, n, rb)
+        slice_fastq(f2, s2, first, n, rb)
+        reads, sec = run_ref_driver(prefix, s1, s2, args.K, cores)
+        log("[bench] reference step %d: %d reads in %.3f s" % (step, reads, sec))
+        if step >= args.warmup:
+            total_pairs += reads // 2
+            total_s += sec
+    v = total_pairs / total_s
+    sample = "%d pairs per step (one mem_process_seqs call, -t %d) of the same simulated read set" % (n, cores)
+    return {"metric": "aligned 2x150bp read pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total_s / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic", "impl": "reference",
+            "config": workload_config(args, "reference CPU mem_process_seqs (oracle/_ref, unmodified sources, gcc -O2)"),
+            "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def workload_config(args, what):
+    return {"workload": "configs[1]: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (4 contigs, 5%% planted repeats), -K %d"
+                        % (args.pairs, args.read_len, args.ref_bp, args.K),
+            "step": "one mem_process_seqs call on one chunk (%d pairs at full size)" % ((args.K // 2) // args.read_len + 1),
+            "path": what, "cache_policy": "every step aligns a different chunk; index (175 MB) + chunk buffers exceed the 126 MB L2; "
+                                          "an L2-sized buffer is rewritten between steps"}
+
+
+# ------------------------------------------------------------------------------------------------ b200 arm
+
+def int32_peak_gops(torch):
+    """measured int32 add/max issue rate of this GPU (alu pipe), via the library's micro-benchmark"""
+    import mpibwa_b200 as M
+    lib = M.load()
+    return lib.b200_int32_peak(torch.cuda.current_device())
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        prefix = ensure_index(args)
+        print(json.dumps(reference_arm(args, prefix)), flush=True)
+        return 0
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import mpibwa_b200 as M
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    if rank == 0:
+        prefix = ensure_index(args)
+    barrier()
+    prefix = os.path.join(workload_dir(args), "ref.fa")
+    f1, f2 = ensure_reads(args, rank, args.pairs)
+    n_threads = max(1, (os.cpu_count() or 1) // world)
+    al = M.Aligner(prefix, device=local_rank, n_threads=n_threads, verbose=1)
+    lib = al.lib
+    fq1, fq2 = open(f1, "rb").read(), open(f2, "rb").read()
+    rb1, rb2 = record_bytes(f1), record_bytes(f2)
+    # plan chunks once (untimed) with the reference hosts' rule
+    b1, s1, n1 = al.parse(fq1)
+    b2, s2, n2 = al.parse(fq2)
+    ends = al.plan(n1, s1, s2, args.K)
+    lib.b200_free(s1); lib.b200_free(s2)
+    del b1, b2
+    chunks = []
+    beg = 0
+    for e in ends:
+        chunks.append((beg, e))
+        beg = e
+    log("[bench] rank %d: %d pairs in %d chunks, %d host threads" % (rank, n1, len(chunks), n_threads))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def chunk_bytes(c):
+        b, e = chunks[c % len(chunks)]
+        return fq1[b * rb1:e * rb1], fq2[b * rb2:e * rb2], e - b
+
+    STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
+                 "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
+                 "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv", "n_seeds", "n_chains")
+
+    def e2e_step(c):
+        """raw fastq bytes -> SAM bytes, everything inside"""
+        a1, a2, n = chunk_bytes(c)
+        k1, p1, m1 = al.parse(a1)
+        k2, p2, m2 = al.parse(a2)
+        sam = C.c_void_p()
+        sam_len = C.c_int64()
+        lib.b200_align_chunk(al.opt, al.idx, 0, m1, p1, p2, C.byref(sam), C.byref(sam_len))
+        out_len = sam_len.value
+        lib.b200_free(sam); lib.b200_free(p1); lib.b200_free(p2)
+        return n, out_len
+
+    def resident_step(c, ev0, ev1):
+        """reads parsed, encoded and resident in HBM before the timed region; SAM left in seqs[i].sam"""
+        a1, a2, n = chunk_bytes(c)
+        k1, p1, m1 = al.parse(a1)
+        k2, p2, m2 = al.parse(a2)
+        seqs = lib.b200_chunk_seqs(m1, p1, p2)
+        lib.b200_stage_reads(al.opt, al.idx, 2 * m1, seqs)
+        flush_buf.add_(1)
+        torch.cuda.synchronize()
+        ev0.record()
+        lib.mem_process_seqs(al.opt, al.idx.contents.bwt, al.idx.contents.bns, al.idx.contents.pac, 0, 2 * m1, seqs, None)
+        ev1.record()
+        torch.cuda.synchronize()
+        lib.b200_collect_sam(2 * m1, seqs, None)
+        lib.b200_free(seqs); lib.b200_free(p1); lib.b200_free(p2)
+        return n, ev0.elapsed_time(ev1)
+
+    # ---- warm-up
+    for w in range(args.warmup):
+        e2e_step(w)
+    # ---- timed: device-resident inputs
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    agg = {k: 0.0 for k in STAT_KEYS}
+    res_pairs, res_ms = 0, 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for s in range(args.steps):
+        n, ms = resident_step(args.warmup + s, ev0, ev1)
+        res_pairs += n
+        res_ms += ms
+        st = al.stats()
+        for k in STAT_KEYS:
+            agg[k] += st[k]
+    barrier()
+    # ---- timed: end to end from host fastq bytes to host SAM bytes
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = d2h = 0
+    e2e_pairs = 0
+    sam_bytes = 0
+    barrier()
+    e0.record()
+    t0 = time.time()
+    for s in range(args.steps):
+        flush_buf.add_(1)
+        n, out_len = e2e_step(args.warmup + s)
+        e2e_pairs += n
+        sam_bytes += out_len
+        st = al.stats()
+        h2d += st["h2d_bytes"]
+        d2h += st["d2h_bytes"]
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    wall_ms = 1e3 * (time.time() - t0)
+    clocks = sampler.result()
+
+    # ---- reduce over ranks: MAX of times, SUM of pairs
+    t = torch.tensor([res_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([res_pairs, e2e_pairs], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    res_ms_max, e2e_ms_max = t.tolist()
+    res_pairs_all, e2e_pairs_all = cnt.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
+    i32_peak = int32_peak_gops(torch)
+    K = args.steps
+    kern = {}
+    if agg["ms_k_extend"] > 0:
+        gcups = agg["extend_cells"] / agg["ms_k_extend"] / 1e6
+        kern["ksw_extend2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_extend"] / K, "cells_per_step": agg["extend_cells"] / K,
+                               "gcups": gcups, "achieved": gcups * 14, "unit": "Gop/s (14 int32 ops per cell)", "peak": i32_peak,
+                               "frac": (gcups * 14 / i32_peak) if i32_peak else None}
+    if agg["ms_k_smem"] > 0:
+        gbs = 64.0 * agg["fm_occ_blocks"] / agg["ms_k_smem"] / 1e6
+        kern["smem_seeding"] = {"bound": "hbm", "ms_per_step": agg["ms_k_smem"] / K, "bytes_per_step": 64.0 * agg["fm_occ_blocks"] / K,
+                                "achieved": gbs, "unit": "GB/s", "peak": hbm_peak, "frac": gbs / hbm_peak}
+    if agg["ms_k_sa"] > 0:
+        b = 64.0 * agg["fm_sa_steps"] + 8.0 * agg["fm_sa_lookups"]
+        gbs = b / agg["ms_k_sa"] / 1e6
+        kern["sa_lookup"] = {"bound": "hbm", "ms_per_step": agg["ms_k_sa"] / K, "bytes_per_step": b / K, "achieved": gbs, "unit": "GB/s",
+                             "peak": hbm_peak, "frac": gbs / hbm_peak}
+    if agg["ms_k_sw"] > 0:
+        gc = agg["sw_cells"] / agg["ms_k_sw"] / 1e6
+        kern["ksw_align2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_sw"] / K, "cells_per_step": agg["sw_cells"] / K, "gcups": gc,
+                              "achieved": gc * 11, "unit": "Gop/s (11 ops per cell)", "peak": i32_peak, "frac": (gc * 11 / i32_peak) if i32_peak else None}
+    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    roof = None
+    if dom:
+        kd = kern[dom]
+        roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
+                "traffic": None, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()"}
+    line = {
+        "metric": "aligned 2x150bp read pairs/sec", "value": res_pairs_all / (res_ms_max * 1e-3), "unit": "pairs/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": workload_config(args, "mem_process_seqs through the C ABI of libmpibwa_b200.so (ctypes), %d host threads per rank" % n_threads),
+        "e2e": {"value": e2e_pairs_all / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
+                "d2h_bytes_per_step": d2h // args.steps, "sam_bytes_per_step": sam_bytes // args.steps, "wall_ms_rank0": wall_ms},
+        "gpu_launches": int(agg["n_launches"]), "clocks": clocks, "roofline": roof, "kernels": kern,
+        "ksw_extend2_gcups": kern.get("ksw_extend2", {}).get("gcups"),
+        "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total")},
+        "host_threads": n_threads,
+    }
+    if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
+        cores = os.cpu_count() or 1
+        n = min(args.ref_sample_pairs, args.pairs)
+        d = workload_dir(args)
+        s1, s2 = os.path.join(d, "cpusample_1.fq"), os.path.join(d, "cpusample_2.fq")
+        slice_fastq(f1, s1, 0, n, rb1)
+        slice_fastq(f2, s2, 0, n, rb2)
+        reads, sec = run_ref_driver(prefix, s1, s2, args.K, cores)
+        line["cpu_baseline"] = {"value": (reads // 2) / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",
+                                "sample": "first %d pairs of the workload, one mem_process_seqs call, -t %d (%.2f s)" % (n, cores, sec)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

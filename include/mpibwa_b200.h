@@ -235,6 +235,9 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
  * Returns 0 on success; aborts on CUDA failure.  The three-line patch for the mpiBWA hosts calls this right
  * after map_indexes(). */
 int  b200_gpu_init(const bwaidx_t *idx, int device);
+/* Optional: encode the reads of the coming mem_process_seqs(…, n, seqs, …) call in place and make them resident in HBM
+ * ahead of time (the call then skips its own encode + upload).  Used to time the path with device-resident inputs. */
+void b200_stage_reads(const mem_opt_t *opt, const bwaidx_t *idx, int n, bseq1_t *seqs);
 void b200_gpu_release(void);
 int  b200_device_count(void);
 
@@ -268,6 +271,19 @@ int b200_collect_intv_batch(const mem_opt_t *opt, int n_reads, const int64_t *of
 /* batched suffix-array look-up (reference src/bwt.c:86-96) */
 int b200_bwt_sa_batch(int64_t n, const bwtint_t *k, bwtint_t *sa);
 
+/* host-side lines of the mpiBWA mains around mem_process_seqs, for harnesses that stand in for the MPI host:
+ * in-place fastq parse (reference src/mainParallel.c:1257-1304), the chunk rule "close when bases > maxsiz"
+ * (reference src/parallel_aux.c:1532-1549, 1068-1082; src/mainParallel.c:2773) and "interleave mates, align,
+ * concatenate seqs[i].sam" (reference src/mainParallel.c:1271-1314, 103-127).  Buffers come from malloc();
+ * release them with b200_free(). */
+int64_t b200_fastq_parse(char *buf, int64_t len, bseq1_t **seqs);
+int64_t b200_plan_chunks(int64_t n, const bseq1_t *s1, const bseq1_t *s2, int64_t K, int trimmed, int64_t **ends);
+bseq1_t *b200_chunk_seqs(int64_t n, const bseq1_t *s1, const bseq1_t *s2);      /* interleaved mates 2i, 2i+1 */
+int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam);            /* concatenates and frees seqs[i].sam */
+int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2,
+                         char **sam, int64_t *sam_len);
+void b200_free(void *p);
+
 /* counters filled by the last mem_process_seqs call on this thread's context; used by bench.py */
 typedef struct {
 	double ms_total;          /* wall time of the call */
@@ -283,6 +299,10 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;
 } b200_stats_t;
 void b200_get_stats(b200_stats_t *out);
+/* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP
+ * roofline denominator) and with half of the work as IMAD on the FMA pipe (dual-pipe ceiling) */
+double b200_int32_peak(int device);
+double b200_int32_peak_dual_pipe(int device);
 const char *b200_version(void);
 
 #ifdef __cplusplus

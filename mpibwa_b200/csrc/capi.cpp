@@ -21,6 +21,7 @@ SwOpt make_sw_opt(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_i
 SeedOpt make_seed_opt(const mem_opt_t *opt);
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0);
+void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs);
 
 static void die(const char *what, const char *arg)
 {
@@ -372,6 +373,11 @@ int b200_gpu_init(const bwaidx_t *idx, int device)
 
 void b200_gpu_release(void) { engine_release(); }
 
+void b200_stage_reads(const mem_opt_t *opt, const bwaidx_t *idx, int n, bseq1_t *seqs)
+{
+	stage_reads(opt, idx->bwt, idx->bns, idx->pac, n, seqs);
+}
+
 void b200_get_stats(b200_stats_t *out)
 {
 	Engine *e = engine_current();
@@ -394,7 +400,8 @@ int b200_ksw_extend2_batch(int64_t n_jobs, b200_extend_job_t *jobs, const uint8_
                            const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
                            int o_del, int e_del, int o_ins, int e_ins, int zdrop)
 {
-	stage_extend_bytes(need_engine(), ext_opt_from(mat, o_del, e_del, o_ins, e_ins, zdrop), n_jobs, jobs,
+	Engine *eng = need_engine();
+	stage_extend_bytes(eng, ext_opt_from(mat, o_del, e_del, o_ins, e_ins, zdrop), n_jobs, jobs,
 	                   query, query_bytes, target, target_bytes);
 	return 0;
 }
@@ -403,7 +410,8 @@ int b200_ksw_align2_batch(int64_t n_jobs, b200_align_job_t *jobs, const uint8_t 
                           const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
                           int o_del, int e_del, int o_ins, int e_ins)
 {
-	stage_sw_bytes(need_engine(), make_sw_opt(mat, o_del, e_del, o_ins, e_ins), n_jobs, jobs, query, query_bytes, target, target_bytes);
+	Engine *eng = need_engine();
+	stage_sw_bytes(eng, make_sw_opt(mat, o_del, e_del, o_ins, e_ins), n_jobs, jobs, query, query_bytes, target, target_bytes);
 	return 0;
 }
 

@@ -183,19 +183,15 @@ static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, cons
 
 /* ------------------------------------------------------------------ the hot path */
 
-void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
-                  int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+static const void *g_staged_key = nullptr;
+static int g_staged_n = 0;
+static int64_t g_staged_bases = 0;
+
+// encode the reads in place, flatten them and make them resident in HBM for the coming mem_process_seqs call
+void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs)
 {
 	Engine *eng = engine_for(bwt, bns, pac);
-	Stats &st = engine_stats(eng);
-	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
-	const double t_start = now_ms();
-	double t0 = t_start, t1;
-	const bool pe = (opt->flag & MEM_F_PE) != 0;
-	const int64_t l_pac = bns->l_pac;
-
-	// ---- encode (reference src/bwamem.c:1057-1058) and flatten
 	std::vector<int64_t> off(n + 1);
 	off[0] = 0;
 	for (int i = 0; i < n; ++i) off[i + 1] = off[i] + seqs[i].l_seq;
@@ -210,10 +206,28 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 			}
 		}
 	});
-	st.n_reads = n; st.n_bases = off[n];
+	stage_upload_reads(eng, n, off.data(), codes.data());
+	g_staged_key = (const void *)seqs; g_staged_n = n; g_staged_bases = off[n];
+}
+
+void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                  int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	Engine *eng = engine_for(bwt, bns, pac);
+	Stats &st = engine_stats(eng);
+	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
+	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
+	const double t_start = now_ms();
+	double t0 = t_start, t1;
+	const bool pe = (opt->flag & MEM_F_PE) != 0;
+	const int64_t l_pac = bns->l_pac;
+
+	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload - unless b200_stage_reads() already did
+	if (!(g_staged_key == (const void *)seqs && g_staged_n == n)) stage_reads(opt, bwt, bns, pac, n, seqs);
+	g_staged_key = nullptr;
+	st.n_reads = n; st.n_bases = g_staged_bases;
 
 	// ---- seeding on the device
-	stage_upload_reads(eng, n, off.data(), codes.data());
 	std::vector<int64_t> seed_off;
 	std::vector<SeedRec> seed_recs;
 	std::vector<int32_t> l_rep;

@@ -657,4 +657,63 @@ void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t
 	e->stats.n_sw_jobs += n_jobs;
 }
 
+/* ------------------------------------------------------------------ int32 issue-rate micro-benchmark (roofline denominator)
+ * Measures the int32 instruction issue rate of this GPU ("measure it with a dependent-chain-free
+ * micro-benchmark on the box").  Eight independent chains per thread, fully unrolled, operands from memory.
+ * MODE 0: every chain alternates max / xor - both issue on the integer ALU pipe and have no fused 3-input form, so one
+ *         PTX op is one SASS instruction: this is the issue rate available to min/max/add/select, the ops of the DP.
+ * MODE 1: half the chains are integer multiply-adds (FMA pipe) - the dual-pipe ceiling when adds go through IMAD. */
+template <int MODE>
+__global__ void __launch_bounds__(256) k_int32_peak(const int *__restrict__ in, int *out, int iters)
+{
+	int x0 = in[threadIdx.x], x1 = x0 ^ 1, x2 = x0 ^ 2, x3 = x0 ^ 3, x4 = x0 ^ 4, x5 = x0 ^ 5, x6 = x0 ^ 6, x7 = x0 ^ 7;
+	const int a = in[256], b = in[257], one = in[258];
+	for (int i = 0; i < iters; ++i) {
+#pragma unroll
+		for (int u = 0; u < 16; ++u) {
+#define B200_MX(x) asm volatile("max.s32 %0, %0, %1;\n\txor.b32 %0, %0, %2;" : "+r"(x) : "r"(a), "r"(b))
+#define B200_MD(x) asm volatile("mad.lo.s32 %0, %0, %1, %2;\n\tmad.lo.s32 %0, %0, %1, %3;" : "+r"(x) : "r"(one), "r"(a), "r"(b))
+			B200_MX(x0); B200_MX(x1); B200_MX(x2); B200_MX(x3);
+			if (MODE == 0) { B200_MX(x4); B200_MX(x5); B200_MX(x6); B200_MX(x7); }
+			else { B200_MD(x4); B200_MD(x5); B200_MD(x6); B200_MD(x7); }
+		}
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+double int32_peak_gops(int device, int mode)
+{
+	CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+	int *in = nullptr, *out = nullptr;
+	CK(cudaMalloc(&in, 259 * sizeof(int)));
+	CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(int)));
+	int h[259];
+	for (int i = 0; i < 258; ++i) h[i] = i * 7 + 1;
+	h[258] = 1;
+	CK(cudaMemcpy(in, h, sizeof h, cudaMemcpyHostToDevice));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	float best = 1e30f;
+	for (int rep = 0; rep < 6; ++rep) {
+		CK(cudaEventRecord(e0));
+		if (mode == 0) k_int32_peak<0><<<blocks, threads>>>(in, out, iters);
+		else k_int32_peak<1><<<blocks, threads>>>(in, out, iters);
+		CK(cudaEventRecord(e1));
+		CK(cudaEventSynchronize(e1));
+		float ms;
+		CK(cudaEventElapsedTime(&ms, e0, e1));
+		if (rep > 0 && ms < best) best = ms;
+	}
+	CK(cudaFree(in)); CK(cudaFree(out));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	double ops = (double)blocks * threads * iters * 16.0 * 16.0;
+	return ops / (best * 1e-3) / 1e9;
+}
+
 } // namespace b200
+
+extern "C" double b200_int32_peak(int device) { return b200::int32_peak_gops(device, 0); }
+extern "C" double b200_int32_peak_dual_pipe(int device) { return b200::int32_peak_gops(device, 1); }

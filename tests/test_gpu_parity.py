@@ -1,0 +1,265 @@
+"""GPU parity tests (run with -m gpu on a B200).  Everything goes through the C ABI of libmpibwa_b200.so and is
+compared bit-exactly (integer/byte work: no tolerance) with
+  * oracle/liboracle.so, our C restatement pinned against the reference (kernel level),
+  * the golden vectors and SAM digests recorded from the reference (tests/golden),
+  * oracle/_ref/ref_driver, the compiled reference itself, when it travelled to the box (end to end)."""
+import ctypes as C
+import hashlib
+import json
+import os
+import subprocess
+import numpy as np
+import pytest
+from conftest import ROOT, have_ref, have_cuda
+import fuzzgen
+import oracle_lib as OL
+import mpibwa_b200 as M
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_cuda(), reason="no CUDA device")]
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def orc(oracle_built):
+    return OL.Oracle()
+
+
+@pytest.fixture(scope="module")
+def aligner(examples):
+    a = M.Aligner(examples["idx"], device=0, n_threads=8, verbose=1)
+    yield a
+
+
+def _run_extend_batch(lib, cases):
+    """group by (params, zdrop) because those are per-call arguments of the batch entry point"""
+    out = [None] * len(cases)
+    groups = {}
+    for i, c in enumerate(cases):
+        groups.setdefault((c["params"], c["zdrop"]), []).append(i)
+    for (params, zdrop), idxs in groups.items():
+        a, b, od, ed, oi, ei = params
+        jobs = (M.b200_extend_job_t * len(idxs))()
+        qs, ts, qo, to = [], [], 0, 0
+        for k, i in enumerate(idxs):
+            c = cases[i]
+            jobs[k].qlen, jobs[k].tlen, jobs[k].q_off, jobs[k].t_off = len(c["q"]), len(c["t"]), qo, to
+            jobs[k].h0, jobs[k].w, jobs[k].end_bonus = c["h0"], c["w"], c["end_bonus"]
+            qs.append(bytes(c["q"])); ts.append(bytes(c["t"]))
+            qo += len(c["q"]); to += len(c["t"])
+        qb, tb = b"".join(qs), b"".join(ts)
+        lib.b200_ksw_extend2_batch(len(idxs), jobs, qb, len(qb), tb, len(tb), OL.default_mat(a, b), od, ed, oi, ei, zdrop)
+        for k, i in enumerate(idxs):
+            j = jobs[k]
+            out[i] = (j.score, j.qle, j.tle, j.gtle, j.gscore, j.max_off)
+    return out
+
+
+def _run_align_batch(lib, cases):
+    out = [None] * len(cases)
+    groups = {}
+    for i, c in enumerate(cases):
+        groups.setdefault(c["params"], []).append(i)
+    for params, idxs in groups.items():
+        a, b, od, ed, oi, ei = params
+        jobs = (M.b200_align_job_t * len(idxs))()
+        qs, ts, qo, to = [], [], 0, 0
+        for k, i in enumerate(idxs):
+            c = cases[i]
+            jobs[k].qlen, jobs[k].tlen, jobs[k].q_off, jobs[k].t_off, jobs[k].xtra = len(c["q"]), len(c["t"]), qo, to, c["xtra"]
+            qs.append(bytes(c["q"])); ts.append(bytes(c["t"]))
+            qo += len(c["q"]); to += len(c["t"])
+        qb, tb = b"".join(qs), b"".join(ts)
+        lib.b200_ksw_align2_batch(len(idxs), jobs, qb, len(qb), tb, len(tb), OL.default_mat(a, b), od, ed, oi, ei)
+        for k, i in enumerate(idxs):
+            r = jobs[k].r
+            out[i] = (r.score, r.te, r.qe, r.score2, r.te2, r.tb, r.qb)
+    return out
+
+
+def test_extend_batch_vs_oracle(aligner, orc):
+    cases = fuzzgen.extend_cases(31, 20000) + fuzzgen.extend_cases(32, 2000, max_q=250, max_t=1100)
+    got = _run_extend_batch(aligner.lib, cases)
+    for c, g in zip(cases, got):
+        a, b, od, ed, oi, ei = c["params"]
+        want = orc.extend(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"], c["end_bonus"], c["zdrop"], c["h0"])[0]
+        assert g == want, c
+
+
+@pytest.mark.parametrize("sixteen", [False, True])
+def test_align_batch_vs_oracle(aligner, orc, sixteen):
+    cases = fuzzgen.align_cases(41 + sixteen, 6000, sixteen)
+    got = _run_align_batch(aligner.lib, cases)
+    for c, g in zip(cases, got):
+        a, b, od, ed, oi, ei = c["params"]
+        want = orc.align(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["xtra"])[0]
+        assert g == want, c
+
+
+def test_golden_vectors_through_cabi(aligner):
+    g = json.load(open(os.path.join(GOLD, "ksw_vectors.json")))
+    ext = [dict(q=np.array(v["q"], np.uint8), t=np.array(v["t"], np.uint8), params=(v["a"], v["b"], v["o_del"], v["e_del"], v["o_ins"], v["e_ins"]),
+                w=v["w"], end_bonus=v["end_bonus"], zdrop=v["zdrop"], h0=v["h0"]) for v in g["extend"]]
+    assert [list(x) for x in _run_extend_batch(aligner.lib, ext)] == [v["out"] for v in g["extend"]]
+    aln = [dict(q=np.array(v["q"], np.uint8), t=np.array(v["t"], np.uint8), params=(v["a"], v["b"], v["o_del"], v["e_del"], v["o_ins"], v["e_ins"]),
+                xtra=v["xtra"]) for v in g["align"]]
+    assert [list(x) for x in _run_align_batch(aligner.lib, aln)] == [v["out"] for v in g["align"]]
+
+
+def test_single_job_wrappers(aligner, orc):
+    """the reference's own call surface (ksw_extend2 / ksw_align2 / bwt_sa / bwt_extend) as batches of one"""
+    lib = aligner.lib
+    idxf = OL.IndexFiles(aligner_idx_prefix(aligner))
+    for c in fuzzgen.extend_cases(51, 20):
+        a, b, od, ed, oi, ei = c["params"]
+        o = [C.c_int() for _ in range(5)]
+        sc = lib.ksw_extend2(len(c["q"]), bytes(c["q"]), len(c["t"]), bytes(c["t"]), 5, OL.default_mat(a, b), od, ed, oi, ei, c["w"],
+                             c["end_bonus"], c["zdrop"], c["h0"], *[C.byref(x) for x in o])
+        want = orc.extend(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"], c["end_bonus"], c["zdrop"], c["h0"])[0]
+        assert (sc, *[x.value for x in o]) == want
+    for k in (1, 33, idxf.primary, idxf.seq_len):
+        assert lib.bwt_sa(aligner.idx.contents.bwt, k) == orc.lib.orc_sa(C.byref(idxf.fm), k)
+    ik = M.bwtintv_t((C.c_uint64 * 3)(idxf.L2[1] + 1, idxf.L2[2] + 1, idxf.L2[2] - idxf.L2[1]), 0)
+    ok = (M.bwtintv_t * 4)()
+    lib.bwt_extend(aligner.idx.contents.bwt, C.byref(ik), ok, 1)
+    oik = OL.orc_intv_t(ik.x[0], ik.x[1], ik.x[2], 0)
+    ook = (OL.orc_intv_t * 4)()
+    orc.lib.orc_extend(C.byref(idxf.fm), C.byref(oik), ook, 1)
+    assert [(ok[i].x[0], ok[i].x[1], ok[i].x[2]) for i in range(4)] == [(ook[i].x0, ook[i].x1, ook[i].x2) for i in range(4)]
+
+
+_PREFIX = {}
+
+
+def aligner_idx_prefix(aligner):
+    return _PREFIX["idx"]
+
+
+@pytest.fixture(autouse=True)
+def _remember_prefix(examples):
+    _PREFIX["idx"] = examples["idx"]
+
+
+def _reads_as_codes(path, n):
+    nt4 = np.full(256, 4, np.uint8)
+    for i, ch in enumerate(b"ACGT"):
+        nt4[ch] = i; nt4[ch + 32] = i
+    out = []
+    with open(path, "rb") as fh:
+        for k, line in enumerate(fh):
+            if k % 4 == 1:
+                out.append(nt4[np.frombuffer(line.rstrip(b"\n"), np.uint8)])
+                if len(out) == n:
+                    break
+    return out
+
+
+def test_seeding_and_sa_vs_oracle(aligner, orc, examples):
+    idxf = OL.IndexFiles(examples["idx"])
+    rng = np.random.default_rng(9)
+    reads = _reads_as_codes(examples["R1_10K"], 400)
+    pos = np.arange(idxf.l_pac)
+    text = (idxf.pac[pos >> 2] >> ((~pos & 3) << 1)) & 3
+    for _ in range(400):
+        L = int(rng.integers(10, 260))
+        s = int(rng.integers(0, idxf.l_pac - L))
+        q = fuzzgen.mutate(rng, text[s:s + L], 0.02, 0.004, 0.005)
+        reads.append(q if rng.random() < 0.5 else np.where(q < 4, 3 - q, 4)[::-1].astype(np.uint8))
+    reads.append(np.full(50, 4, np.uint8))                 # all N
+    reads.append(np.zeros(5, np.uint8))                    # shorter than a seed
+    reads.append(np.zeros(0, np.uint8))                    # empty
+    off = np.zeros(len(reads) + 1, np.int64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    flat = np.concatenate(reads + [np.zeros(8, np.uint8)])
+    intv = C.POINTER(M.bwtintv_t)()
+    ioff = C.POINTER(C.c_int64)()
+    aligner.lib.b200_collect_intv_batch(aligner.opt, len(reads), off.ctypes.data, flat.ctypes.data, C.byref(intv), C.byref(ioff))
+    n_total = 0
+    for r, q in enumerate(reads):
+        got = [(intv[i].x[0], intv[i].x[1], intv[i].x[2], intv[i].info) for i in range(ioff[r], ioff[r + 1])]
+        assert got == orc.collect_intv(idxf.fm, q), r
+        n_total += len(got)
+    assert n_total > 1000
+    aligner.lib.b200_free(intv); aligner.lib.b200_free(ioff)
+    ks = np.concatenate([[1, idxf.primary, idxf.seq_len, 32], rng.integers(1, idxf.seq_len + 1, size=20000)]).astype(np.uint64)
+    sa = np.zeros(len(ks), np.uint64)
+    aligner.lib.b200_bwt_sa_batch(len(ks), ks.ctypes.data, sa.ctypes.data)
+    want = [orc.lib.orc_sa(C.byref(idxf.fm), int(k)) for k in ks[:3000]]
+    assert sa[:3000].tolist() == want
+    # size-independent property: SA values of distinct rows are distinct text positions
+    assert len(set(sa.tolist())) == len(set(ks.tolist()))
+
+
+def _sq_header(aligner):
+    bns = aligner.idx.contents.bns.contents
+    return b"".join(b"@SQ\tSN:%s\tLN:%d\n" % (bns.anns[i].name, bns.anns[i].len) for i in range(bns.n_seqs))
+
+
+@pytest.mark.parametrize("shape", ["pe", "pe_K", "trim", "se"])
+def test_examples_sam_digest(examples, shape):
+    """bit-exact SAM vs the digests recorded from the reference on its own example data"""
+    want = json.load(open(os.path.join(GOLD, "sam_md5.json")))[shape]
+    rd = lambda k: open(examples[k], "rb").read()
+    a = M.Aligner(examples["idx"], device=0, n_threads=8, paired=(shape != "se"), verbose=1)
+    if shape == "pe":
+        sam = _sq_header(a) + a.align(rd("R1_10K"), rd("R2_10K"), K=10000000 * 8)
+    elif shape == "pe_K":
+        sam = a.align(rd("R1_10K"), rd("R2_10K"), K=500000)
+    elif shape == "trim":
+        sam = a.align(rd("R1_10K_TRIM"), rd("R2_10K_TRIM"), K=700000, trimmed=True)
+    else:
+        sam = a.align(rd("R1_10K"), None, K=300000)
+    assert sam.count(b"\n") == want["lines"]
+    assert hashlib.md5(sam).hexdigest() == want["md5"]
+    st = a.stats()
+    assert st["n_launches"] > 0 and st["extend_cells"] > 0
+
+
+SYN = {  # name: (ref bp, contigs, simulate kwargs, driver args)
+    "cfg2_like": (3_000_000, 4, dict(n_pairs=30000), ["-K", "4000000"]),
+    "cfg4_like": (2_000_000, 3, dict(n_pairs=8000, read_len=250, sub=0.03, indel=0.01, max_indel=50, trim_to=(100, 250),
+                                     unmappable_frac=0.2, seed=5), ["-T", "-K", "900000"]),
+    "se100": (2_000_000, 5, dict(n_pairs=20000, read_len=100, seed=8), ["-K", "500000"]),
+}
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+@pytest.mark.parametrize("name", list(SYN))
+def test_synthetic_vs_compiled_reference(tmp_path, name):
+    """fresh synthetic reference + wgsim-style reads: SAM of the B200 core == SAM of the compiled reference"""
+    from mpibwa_b200 import simulate, index_build
+    bp, nctg, kw, args = SYN[name]
+    names, lengths, codes = simulate.make_reference(bp, nctg, seed=17)
+    prefix = str(tmp_path / "ref.fa")
+    index_build.write_fasta(prefix, simulate.codes_to_fasta_contigs(names, lengths, codes, n_runs=2))
+    index_build.build_index(prefix)
+    r1, r2 = simulate.simulate_pairs(codes, lengths, **kw)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1); open(f2, "wb").write(r2)
+    fq = [f1] if name == "se100" else [f1, f2]
+    want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16"] + args + [prefix] + fq,
+                          capture_output=True, check=True).stdout
+    a = M.Aligner(prefix, device=0, n_threads=16, paired=(name != "se100"), verbose=1)
+    K = int(args[args.index("-K") + 1])
+    got = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
+    assert got == want
+    # through the stand-alone driver binary as well (the C host path)
+    got2 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
+    assert got2 == want
+
+
+def test_properties_at_scale(tmp_path):
+    """size-independent properties on a larger run: thread-count invariance, idempotence, record accounting"""
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(20_000_000, 4, seed=23)
+    prefix = str(tmp_path / "big.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+    r1, r2 = simulate.simulate_pairs(codes, lengths, 200000, seed=29)
+    a = M.Aligner(prefix, device=0, n_threads=16, verbose=1)
+    s16 = a.align(r1, r2, K=30_000_000)
+    again = a.align(r1, r2, K=30_000_000)
+    a.opt.contents.n_threads = 3
+    s3 = a.align(r1, r2, K=30_000_000)
+    assert s16 == again == s3
+    flags = np.array([int(l.split(b"\t", 2)[1]) for l in s16.split(b"\n") if l])
+    assert int(((flags & 0x900) == 0).sum()) == 400000            # one primary record per read
+    assert ((flags & 4) == 0).mean() > 0.98                        # simulated reads map

@@ -1,0 +1,49 @@
+"""CPU tests of the HOST orchestration (chaining, dedup/patch, insert-size statistics, rescue replay, pairing, mapQ,
+CIGAR/MD, SAM text) against the reference's SAM.  The device stages are stood in for by tests/hostemu (the same
+per-task bodies looped on the CPU) - a test scaffold only; the product library never contains it."""
+import gzip
+import hashlib
+import json
+import os
+import subprocess
+import pytest
+from conftest import ROOT, have_ref
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _head(path, n_reads, out):
+    with open(path, "rb") as fi:
+        lines = fi.read().split(b"\n")[:4 * n_reads]
+    with open(out, "wb") as fo:
+        fo.write(b"\n".join(lines) + b"\n")
+    return out
+
+
+def test_head1500_matches_golden_sam(hostemu_built, examples, tmp_path):
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    r1 = _head(examples["R1_10K"], 1500, str(tmp_path / "r1.fq"))
+    r2 = _head(examples["R2_10K"], 1500, str(tmp_path / "r2.fq"))
+    sam = subprocess.run([drv, "-t", "8", examples["idx"], r1, r2], capture_output=True, check=True).stdout
+    with gzip.open(os.path.join(GOLD, "pe_head1500.sam.gz"), "rb") as fh:
+        want = fh.read()
+    assert sam == want
+    assert hashlib.md5(sam).hexdigest() == json.load(open(os.path.join(GOLD, "sam_md5.json")))["pe_head1500"]["md5"]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("shape", ["se_chunks", "trim", "threads"])
+def test_shapes_match_reference(hostemu_built, examples, tmp_path, shape):
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if shape == "se_chunks":
+        args = ["-K", "60000", examples["idx"], _head(examples["R1_10K"], 2000, str(tmp_path / "a.fq"))]
+    elif shape == "trim":
+        args = ["-T", "-K", "100000", examples["idx"], _head(examples["R1_10K_TRIM"], 1200, str(tmp_path / "a.fq")),
+                _head(examples["R2_10K_TRIM"], 1200, str(tmp_path / "b.fq"))]
+    else:
+        args = ["-K", "150000", examples["idx"], _head(examples["R1_10K"], 1200, str(tmp_path / "a.fq")),
+                _head(examples["R2_10K"], 1200, str(tmp_path / "b.fq"))]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    got = subprocess.run([drv, "-t", "1" if shape == "threads" else "8"] + args, capture_output=True, check=True).stdout
+    assert got == want and want.count(b"\n") > 1000

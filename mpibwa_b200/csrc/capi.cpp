@@ -529,9 +529,9 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 	for (uint64_t k : key) srt.push_back((int32_t)(uint32_t)k);
 	if (av->n != 0) die("mem_chain2aln: a non-empty region list must go through mem_process_seqs", nullptr);
 	std::vector<DReg> regs;
-	std::vector<int32_t> n_regs;
-	stage_extend(eng, make_ext_opt(opt), chain_off, dc, ds, srt, regs, n_regs);
-	for (int i = 0; i < n_regs[0]; ++i) {
+	std::vector<int64_t> reg_off;
+	stage_extend(eng, make_ext_opt(opt), chain_off, dc, ds, srt, regs, reg_off);
+	for (int i = 0; i < (int)reg_off[1]; ++i) {
 		if (av->n == av->m) { av->m = av->m ? av->m << 1 : 2; av->a = (mem_alnreg_t *)realloc(av->a, av->m * sizeof(mem_alnreg_t)); }
 		mem_alnreg_t *a = &av->a[av->n++];
 		memset(a, 0, sizeof *a);

@@ -1,0 +1,346 @@
+// ext_rounds.cuh - seed extension (mem_chain2aln + ksw_extend2, reference src/bwamem.c:632-786, src/ksw.c:380-479)
+// as a device-resident state machine plus a batched DP kernel.
+//
+// Why not one thread per read (v1) and why not one warp per anti-diagonal: BWA's band is re-derived after every row
+// from the zero structure of the *completed* row (src/ksw.c:466-469) and cells outside the band keep stale values,
+// so a row cannot start before the previous one has finished - a wavefront would have to speculate and roll back.
+// The jobs are also small (median query 48 columns, ~45 live cells per row).  What maps well is ONE DP JOB PER LANE:
+// every lane runs the exact scalar recurrence on its own job, the H/E row lives in shared memory as packed 16-bit
+// pairs laid out [column][lane] (bank = lane, conflict-free for any per-lane column), the query is staged in shared
+// memory as bytes, substitution scores come from one PRMT over a 2-register score row, and warps are formed from
+// jobs SORTED by (query length, target length) so that lanes stay in step.
+//
+//   k_ext_advance   one thread per read with work left: finishes the region of the seed whose DP just returned,
+//                   walks the read's chains/seeds in the reference's order applying the containment tests
+//                   (src/bwamem.c:671-706) until the next seed that needs extending, and emits ONE DP job
+//                   (left or right side) for it.  The skip decision needs the regions found so far, hence rounds.
+//   k_ext_dp        the batched ksw_extend2 (with the caller's band-doubling retry, src/bwamem.c:723-734,751-762).
+//   k_ext_dp_big    same recurrence through extend_core with the row in global memory, for jobs that do not fit
+//                   the fast path (very long queries or scores that overflow 15 bits).
+#pragma once
+#include "ext_kernels.h"
+
+namespace b200 {
+
+struct ExtJob {                 // one pending ksw_extend2 call (+ retry) of a read; 64 bytes
+	int64_t qaddr;              // index into the code buffer of query base 0
+	int64_t f0;                 // forward-strand coordinate of target base 0
+	int32_t qstep, fstep, comp; // +-1 walking directions; comp: complement the target bases (reverse strand)
+	int32_t qlen, tlen, h0, prev, bonus;
+	int32_t score, qle, tle, gtle, gscore, aw;   // results
+};
+
+struct ExtState {               // per read
+	int32_t ci, k;              // cursor: chain index (relative to the read) and position in the chain's score order
+	int32_t n_av;               // regions emitted so far
+	int32_t phase;              // 0 search, 1 left DP pending, 2 right DP pending, 3 finished
+	int32_t aw0, aw1, sc0, seed;
+	DReg a;                     // region under construction
+};
+
+#define EXT_N_CLASS 8
+__device__ __constant__ int c_ext_class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
+
+__device__ __forceinline__ int ext_class_of(int qlen, int h0, int max_sc)
+{
+	if ((long long)h0 + (long long)qlen * max_sc >= 32768) return EXT_N_CLASS - 1;
+	int c = 0;
+	while (qlen > c_ext_class_cap[c]) ++c;
+	return c;
+}
+
+// ---------------------------------------------------------------- the state machine
+
+__device__ __forceinline__ void ext_emit_job(ExtJob *jb, const uint8_t *, int64_t l_pac, int64_t qaddr, int qstep, int64_t p0, int pstep,
+                                             int qlen, int tlen, int h0, int prev, int bonus)
+{
+	const bool fwd = p0 < l_pac;                  // p0: coordinate of target base 0 in [0, 2*l_pac); windows never bridge strands
+	jb->qaddr = qaddr; jb->qstep = qstep;
+	jb->f0 = fwd ? p0 : (l_pac << 1) - 1 - p0; jb->fstep = fwd ? pstep : -pstep; jb->comp = fwd ? 0 : 1;
+	jb->qlen = qlen; jb->tlen = tlen; jb->h0 = h0; jb->prev = prev; jb->bonus = bonus;
+}
+
+__global__ void __launch_bounds__(128) k_ext_advance(ExtOpt eo, int64_t l_pac, int n_active, const int32_t *__restrict__ active,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ chain_off,
+                                                     const DChain *__restrict__ chains, const DSeed *__restrict__ seeds, int32_t *srt,
+                                                     ExtState *state, ExtJob *jobs, DReg *regs, int32_t *n_regs,
+                                                     int32_t *next_active, uint32_t *next_key, int32_t *counters /* [0]=n_next, [1..]=class hist */)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_active) return;
+	const int r = active[t];
+	ExtState st = state[r];
+	ExtJob *jb = &jobs[r];
+	const int c0 = chain_off[r], nc = chain_off[r + 1] - c0;
+	const int l_query = (int)(off[r + 1] - off[r]);
+	const int64_t qbase = off[r];
+	DReg *out = regs + chains[c0].seed_beg;
+	bool emitted = false;
+	for (;;) {
+		const DChain &c = chains[c0 + st.ci];
+		const DSeed *cs = seeds + c.seed_beg;
+		if (st.phase == 1) {                          // left extension returned (reference src/bwamem.c:723-743)
+			const DSeed &s = cs[st.seed];
+			st.a.score = jb->score; st.aw0 = jb->aw;
+			if (jb->gscore <= 0 || jb->gscore <= st.a.score - eo.pen_clip5) {
+				st.a.qb = s.qbeg - jb->qle; st.a.rb = s.rbeg - jb->tle; st.a.truesc = st.a.score;
+			} else { st.a.qb = 0; st.a.rb = s.rbeg - jb->gtle; st.a.truesc = jb->gscore; }
+			st.phase = 4;                             // -> right side
+		} else if (st.phase == 2) {                   // right extension returned (src/bwamem.c:751-771)
+			const DSeed &s = cs[st.seed];
+			const int qe = s.qbeg + s.len;
+			const int64_t re = s.rbeg + s.len;
+			st.a.score = jb->score; st.aw1 = jb->aw;
+			if (jb->gscore <= 0 || jb->gscore <= st.a.score - eo.pen_clip3) {
+				st.a.qe = qe + jb->qle; st.a.re = re + jb->tle; st.a.truesc += st.a.score - st.sc0;
+			} else { st.a.qe = l_query; st.a.re = re + jb->gtle; st.a.truesc += jb->gscore - st.sc0; }
+			st.phase = 5;                             // -> finish the region
+		} else if (st.phase == 0) {                   // look for the next seed that needs extending
+			bool found = false;
+			while (st.ci < nc) {
+				const DChain &cc = chains[c0 + st.ci];
+				if (st.k < 0) { ++st.ci; if (st.ci < nc) st.k = chains[c0 + st.ci].n_seeds - 1; continue; }
+				if (cc.n_seeds > 0 && chain2aln_need_extension(eo, l_query, cc, seeds + cc.seed_beg, srt + cc.seed_beg, st.k, out, st.n_av)) { found = true; break; }
+				--st.k;
+			}
+			if (!found) { st.phase = 3; n_regs[r] = st.n_av; break; }
+			const DChain &cc = chains[c0 + st.ci];
+			st.seed = srt[cc.seed_beg + st.k];
+			const DSeed &s = seeds[cc.seed_beg + st.seed];
+			st.aw0 = st.aw1 = eo.w;
+			st.a.w = eo.w; st.a.score = st.a.truesc = -1; st.a.rid = cc.rid;
+			st.a.qb = st.a.qe = 0; st.a.rb = st.a.re = 0; st.a.seedcov = 0; st.a.seedlen0 = 0; st.a.pad = 0; st.a.frac_rep = 0;
+			if (s.qbeg) {
+				ext_emit_job(jb, nullptr, l_pac, qbase + s.qbeg - 1, -1, s.rbeg - 1, -1, s.qbeg, (int)(s.rbeg - cc.rmax0), s.len * eo.a, -1, eo.pen_clip5);
+				st.phase = 1; emitted = true; break;
+			}
+			st.a.score = st.a.truesc = s.len * eo.a; st.a.qb = 0; st.a.rb = s.rbeg;
+			st.phase = 4;
+		} else if (st.phase == 4) {                   // right side of the current seed
+			const DSeed &s = cs[st.seed];
+			if (s.qbeg + s.len != l_query) {
+				const int qe = s.qbeg + s.len;
+				const int64_t re = s.rbeg + s.len;
+				st.sc0 = st.a.score;
+				ext_emit_job(jb, nullptr, l_pac, qbase + qe, 1, re, 1, l_query - qe, (int)(c.rmax1 - re), st.sc0, st.a.score, eo.pen_clip3);
+				st.phase = 2; emitted = true; break;
+			}
+			st.a.qe = l_query; st.a.re = s.rbeg + s.len;
+			st.phase = 5;
+		} else {                                      // phase 5: seedcov, band, bookkeeping (src/bwamem.c:774-783)
+			const DSeed &s = cs[st.seed];
+			int cov = 0;
+			for (int i = 0; i < c.n_seeds; ++i) {
+				const DSeed &u = cs[i];
+				if (u.qbeg >= st.a.qb && u.qbeg + u.len <= st.a.qe && u.rbeg >= st.a.rb && u.rbeg + u.len <= st.a.re) cov += u.len;
+			}
+			st.a.seedcov = cov;
+			st.a.w = st.aw0 > st.aw1 ? st.aw0 : st.aw1;
+			st.a.seedlen0 = s.len;
+			st.a.frac_rep = c.frac_rep;
+			out[st.n_av++] = st.a;
+			--st.k;
+			st.phase = 0;
+		}
+	}
+	state[r] = st;
+	if (emitted) {
+		int pos = atomicAdd(&counters[0], 1);
+		int cls = ext_class_of(jb->qlen, jb->h0, eo.max_sc);
+		atomicAdd(&counters[1 + cls], 1);
+		next_active[pos] = r;
+		int tl = jb->tlen > 0xffff ? 0xffff : jb->tlen;
+		int ql = jb->qlen > 0x3fff ? 0x3fff : jb->qlen;
+		next_key[pos] = ((uint32_t)cls << 28) | ((uint32_t)(ql & 0xfff) << 16) | (uint32_t)tl;
+	}
+}
+
+__global__ void k_ext_init(int n_reads, const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains, ExtState *state,
+                           int32_t *n_regs, int32_t *active, int32_t *counters)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int c0 = chain_off[r], nc = chain_off[r + 1] - c0;
+	n_regs[r] = 0;
+	if (nc <= 0) return;
+	ExtState st;
+	st.ci = 0; st.k = chains[c0].n_seeds - 1; st.n_av = 0; st.phase = 0; st.aw0 = st.aw1 = st.sc0 = st.seed = 0;
+	st.a = DReg();
+	state[r] = st;
+	active[atomicAdd(&counters[0], 1)] = r;
+}
+
+// gather the regions of every read into one compact array (reg_off = exclusive scan of n_regs)
+__global__ void k_ext_gather(int n_reads, const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains,
+                             const int32_t *__restrict__ n_regs, const int64_t *__restrict__ reg_off, const DReg *__restrict__ regs, DReg *out)
+{
+	int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int n = n_regs[r];
+	if (n == 0) return;
+	const DReg *src = regs + chains[chain_off[r]].seed_beg;
+	DReg *dst = out + reg_off[r];
+	for (int i = 0; i < n; ++i) dst[i] = src[i];
+}
+
+// ---------------------------------------------------------------- the DP
+
+__device__ __forceinline__ int prmt_score(uint32_t lo, uint32_t hi, uint32_t sel)
+{
+	int s;
+	asm("prmt.b32 %0, %1, %2, %3;" : "=r"(s) : "r"(lo), "r"(hi), "r"(sel));
+	return s;
+}
+
+__device__ __forceinline__ int pac_fbase(const uint8_t *__restrict__ pac, int64_t f) { return pac[f >> 2] >> ((~f & 3) << 1) & 3; }
+
+// one ksw_extend2 call on the lane's job; S = packed state row (stride 32 words), Q = query bytes (stride 32 bytes)
+__device__ __forceinline__ void ext_dp_lane(const ExtOpt &o, const uint32_t *__restrict__ sc_lo, const uint32_t *__restrict__ sc_hi,
+                                            const uint8_t *__restrict__ pac, const ExtJob &jb, int w, volatile uint32_t *S,
+                                            const volatile uint8_t *Q, ExtOut *out, long long *cells)
+{
+	const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0;
+	const int e_del = o.e_del, e_ins = o.e_ins, oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
+	int i, j, beg = 0, end = qlen, max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+	{
+		int v = h0 > oe_ins ? h0 - oe_ins : 0;
+		S[0] = (uint32_t)h0;
+		for (j = 1; j <= qlen; ++j) { S[j * 32] = (uint32_t)v; v = v > e_ins ? v - e_ins : 0; }
+	}
+	{
+		int max_ins = (int)((double)(qlen * o.max_sc + jb.bonus - o.o_ins) / o.e_ins + 1.);
+		max_ins = max_ins > 1 ? max_ins : 1;
+		w = w < max_ins ? w : max_ins;
+		int max_del = (int)((double)(qlen * o.max_sc + jb.bonus - o.o_del) / o.e_del + 1.);
+		max_del = max_del > 1 ? max_del : 1;
+		w = w < max_del ? w : max_del;
+	}
+	long long ncell = 0;
+	int64_t f = jb.f0;
+	for (i = 0; i < tlen; ++i, f += jb.fstep) {
+		int t = pac_fbase(pac, f);
+		if (jb.comp) t = 3 - t;
+		const uint32_t lo = sc_lo[t], hi = sc_hi[t];
+		int fgap = 0, h1, hj = -1;
+		if (beg < i - w) beg = i - w;
+		if (end > i + w + 1) end = i + w + 1;
+		if (end > qlen) end = qlen;
+		if (beg == 0) { h1 = h0 - (o.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+		else h1 = 0;
+#pragma unroll 2
+		for (j = beg; j < end; ++j) {
+			const uint32_t wd = S[j * 32];
+			const int q = Q[j * 32];
+			const int s = prmt_score(lo, hi, (uint32_t)q * 0x1111u + 0x8880u);
+			const int hd = (int)(wd & 0xffffu);
+			int e = (int)(wd >> 16);
+			int M = hd + s;
+			M = hd ? M : 0;
+			int h = ::max(::max(M, e), fgap);
+			hj = ::max(hj, (h << 16) | j);
+			e = ::max(::max(e - e_del, M - oe_del), 0);
+			fgap = ::max(::max(fgap - e_ins, M - oe_ins), 0);
+			S[j * 32] = (uint32_t)h1 | ((uint32_t)e << 16);
+			h1 = h;
+		}
+		if (end > beg) ncell += end - beg;
+		S[end * 32] = (uint32_t)h1;
+		if (j == qlen) {
+			max_ie = gscore > h1 ? max_ie : i;
+			gscore = gscore > h1 ? gscore : h1;
+		}
+		const int m = hj < 0 ? 0 : hj >> 16, mj = hj < 0 ? -1 : hj & 0xffff;
+		if (m == 0) break;
+		if (m > max) {
+			max = m; max_i = i; max_j = mj;
+			int d = mj - i; d = d < 0 ? -d : d;
+			max_off = max_off > d ? max_off : d;
+		} else if (o.zdrop > 0) {
+			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > o.zdrop) break; }
+			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > o.zdrop) break; }
+		}
+		for (j = beg; j < end && S[j * 32] == 0; ++j) {}
+		beg = j;
+		for (j = end; j >= beg && S[j * 32] == 0; --j) {}
+		end = j + 2 < qlen ? j + 2 : qlen;
+	}
+	out->score = max; out->qle = max_j + 1; out->tle = max_i + 1; out->gtle = max_ie + 1; out->gscore = gscore; out->max_off = max_off;
+	*cells += ncell;
+}
+
+// fast path: one job per lane, warps built from the sorted order
+__global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
+                                               ExtJob *jobs, const int32_t *__restrict__ order, int n, int qcap, unsigned long long *cells_out,
+                                               unsigned long long *calls_out)
+{
+	extern __shared__ uint32_t smem[];
+	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int qpad = (qcap + 4) & ~3;
+	const int per_warp_words = (qcap + 1) * 32 + qpad * 8;
+	volatile uint32_t *S = smem + (size_t)wib * per_warp_words + lane;
+	volatile uint8_t *Q = (volatile uint8_t *)(smem + (size_t)wib * per_warp_words + (qcap + 1) * 32) + lane;
+	if (threadIdx.x < 4) {
+		const int8_t *m = eo.mat + threadIdx.x * 5;
+		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
+		sc_hi[threadIdx.x] = (uint32_t)(uint8_t)m[4];
+	}
+	__syncthreads();
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	long long cells = 0;
+	int calls = 0;
+	if (t < n) {
+		ExtJob *jp = &jobs[order[t]];
+		const ExtJob jb = *jp;
+		for (int j = 0; j < jb.qlen; ++j) Q[j * 32] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+		ExtOut x; x.score = -1; x.qle = x.tle = x.gtle = 0; x.gscore = -1; x.max_off = 0;
+		int score = jb.prev, aw = eo.w;
+		for (int it = 0; it < 2; ++it) {                      // MAX_BAND_TRY = 2 (src/bwamem.c:630,723-734)
+			const int prev = score;
+			aw = eo.w << it;
+			ext_dp_lane(eo, sc_lo, sc_hi, pac, jb, aw, S, Q, &x, &cells);
+			++calls;
+			score = x.score;
+			if (score == prev || x.max_off < (aw >> 1) + (aw >> 2)) break;
+		}
+		jp->score = score; jp->qle = x.qle; jp->tle = x.tle; jp->gtle = x.gtle; jp->gscore = x.gscore; jp->aw = aw;
+	}
+	for (int o = 16; o > 0; o >>= 1) { cells += __shfl_down_sync(0xffffffffu, cells, o); calls += __shfl_down_sync(0xffffffffu, calls, o); }
+	if (lane == 0) { if (cells) atomicAdd(cells_out, (unsigned long long)cells); if (calls) atomicAdd(calls_out, (unsigned long long)calls); }
+}
+
+// general path: any query length / score range, row state in global memory (int32, lane-interleaved)
+struct QStep { const uint8_t *p; int64_t step; __device__ __forceinline__ int operator()(int j) const { return p[step * j]; } };
+struct TStep { const uint8_t *pac; int64_t f0; int fstep, comp; __device__ __forceinline__ int operator()(int i) const { int b = pac_fbase(pac, f0 + (int64_t)fstep * i); return comp ? 3 - b : b; } };
+
+__global__ void __launch_bounds__(128) k_ext_dp_big(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
+                                                    ExtJob *jobs, const int32_t *__restrict__ order, int n, int32_t *eh, int64_t stride,
+                                                    unsigned long long *cells_out, unsigned long long *calls_out)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	int calls = 0;
+	if (t < n) {
+		ExtJob *jp = &jobs[order[t]];
+		const ExtJob jb = *jp;
+		EhStrided acc = { eh + t, stride };
+		QStep qa = { codes + jb.qaddr, jb.qstep };
+		TStep ta = { pac, jb.f0, jb.fstep, jb.comp };
+		ExtOut x; x.score = -1; x.qle = x.tle = x.gtle = 0; x.gscore = -1; x.max_off = 0;
+		int score = jb.prev, aw = eo.w;
+		for (int it = 0; it < 2; ++it) {
+			const int prev = score;
+			aw = eo.w << it;
+			extend_core(jb.qlen, qa, jb.tlen, ta, eo, aw, jb.bonus, jb.h0, acc, &x, &cells);
+			++calls;
+			score = x.score;
+			if (score == prev || x.max_off < (aw >> 1) + (aw >> 2)) break;
+		}
+		jp->score = score; jp->qle = x.qle; jp->tle = x.tle; jp->gtle = x.gtle; jp->gscore = x.gscore; jp->aw = aw;
+	}
+	long long c = cells;
+	for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); calls += __shfl_down_sync(0xffffffffu, calls, o); }
+	if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(cells_out, (unsigned long long)c); if (calls) atomicAdd(calls_out, (unsigned long long)calls); }
+}
+
+} // namespace b200

@@ -338,17 +338,17 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 
 	// ---- chain2aln / ksw_extend2 on the device
 	std::vector<DReg> dregs;
-	std::vector<int32_t> n_regs;
-	stage_extend(eng, make_ext_opt(opt), chain_off, dchains, dseeds, srt, dregs, n_regs);
+	std::vector<int64_t> reg_off;
+	stage_extend(eng, make_ext_opt(opt), chain_off, dchains, dseeds, srt, dregs, reg_off);
 	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
 
 	// ---- mem_sort_dedup_patch + ALT marking (reference src/bwamem.c:1073-1085)
 	std::vector<RegVec> regs(n);
 	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
-			int nr = n_regs[i];
+			int nr = (int)(reg_off[i + 1] - reg_off[i]);
 			if (nr == 0) continue;
-			int64_t base = chain_off[i] < chain_off[i + 1] ? dchains[chain_off[i]].seed_beg : 0;
+			int64_t base = reg_off[i];
 			RegVec &rv = regs[i];
 			rv.resize(nr);
 			for (int k = 0; k < nr; ++k) {

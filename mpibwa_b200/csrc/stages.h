@@ -48,11 +48,11 @@ void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_
 void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds,
                 std::vector<int32_t> &l_rep);
 
-// extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); regs of read r are written to
-// regs[first seed index of its first chain ...] and counted in n_regs[r].
+// extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r come back compacted
+// as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them.
 void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
                   const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs,
-                  std::vector<int32_t> &n_regs);
+                  std::vector<int64_t> &reg_off);
 
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);

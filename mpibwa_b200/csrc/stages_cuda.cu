@@ -12,6 +12,7 @@
 // mate rescue; the kernels in ksw_extend_kernel.cuh / ksw_align_kernel.cuh / smem_kernel.cuh do the work.
 #include "stages.h"
 #include "util.h"
+#include "ext_rounds.cuh"
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
@@ -63,6 +64,8 @@ public:
 	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
+	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
+	std::vector<cudaEvent_t> ev_pool;
 	Counters *d_cnt = nullptr;
 
 	void tic() { CK(cudaEventRecord(ev0, stream)); }
@@ -171,7 +174,7 @@ void engine_destroy(Engine *e)
 	cudaStreamSynchronize(e->stream);
 	DevBuf *bufs[] = { &e->d_off, &e->d_codes, &e->b_intv, &e->b_scr, &e->b_nintv, &e->b_ioff, &e->b_civ, &e->b_slots, &e->b_soff,
 		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
-		&e->b_nregs, &e->b_eh, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
+		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
 	for (DevBuf *b : bufs) b->release();
 	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -452,37 +455,15 @@ void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
 
 /* ------------------------------------------------------------------ extension */
 
-__global__ void __launch_bounds__(128) k_chain2aln(ExtOpt eo, const uint8_t *__restrict__ pac, int64_t l_pac, int n_reads,
-                                                   const int64_t *__restrict__ off, const uint8_t *__restrict__ codes,
-                                                   const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains,
-                                                   const DSeed *__restrict__ seeds, int32_t *srt, int32_t *eh, int64_t stride,
-                                                   DReg *regs, int32_t *n_regs, Counters *cnt)
-{
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t cells = 0;
-	int calls = 0;
-	if (r < n_reads) {
-		int c0 = chain_off[r], nc = chain_off[r + 1] - c0, n = 0;
-		if (nc > 0) {
-			int l_query = (int)(off[r + 1] - off[r]);
-			EhStrided acc = { eh + r, stride };
-			n = chain2aln_read(eo, pac, l_pac, l_query, codes + off[r], chains + c0, nc, seeds, srt, acc,
-			                   regs + chains[c0].seed_beg, &cells, &calls);
-		}
-		n_regs[r] = n;
-	}
-	warp_add(&cnt->ext_cells, cells);
-	warp_add(&cnt->ext_calls, calls);
-}
-
+// Rounds of (advance -> sort jobs by size -> batched DP) until every read has walked all its chains; see ext_rounds.cuh.
 void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
-                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int32_t> &n_regs)
+                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int64_t> &reg_off)
 {
 	CK(cudaSetDevice(e->device));
 	const int n = (int)chain_off.size() - 1;
 	if (n != e->n_reads) die("stage_extend: chain table does not match the uploaded reads");
-	regs.assign(seeds.size() + 1, DReg());
-	n_regs.assign(n, 0);
+	regs.clear();
+	reg_off.assign(n + 1, 0);
 	if (n == 0) return;
 	e->zero_counters();
 	int32_t *d_co = e->b_chain_off.as<int32_t>(n + 1);
@@ -490,21 +471,92 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	DSeed *d_se = e->b_dseeds.as<DSeed>(seeds.size() + 1);
 	int32_t *d_srt = e->b_srt.as<int32_t>(srt.size() + 1);
 	DReg *d_regs = e->b_regs.as<DReg>(seeds.size() + 1);
-	int32_t *d_nr = e->b_nregs.as<int32_t>(n);
+	int32_t *d_nr = e->b_nregs.as<int32_t>(n + 1);
+	ExtState *d_state = e->b_xstate.as<ExtState>(n);
+	ExtJob *d_jobs = e->b_xjobs.as<ExtJob>(n);
+	int32_t *d_act[2] = { e->b_xact0.as<int32_t>(n), e->b_xact1.as<int32_t>(n) };
+	uint32_t *d_key = e->b_xkey.as<uint32_t>(n), *d_key2 = e->b_xkey2.as<uint32_t>(n);
+	int32_t *d_ord = e->b_xord.as<int32_t>(n);
+	int32_t *d_ctr = e->b_xctr.as<int32_t>(16);
 	e->h2d(d_co, chain_off.data(), sizeof(int32_t) * (n + 1));
 	e->h2d(d_ch, chains.data(), sizeof(DChain) * chains.size());
 	e->h2d(d_se, seeds.data(), sizeof(DSeed) * seeds.size());
 	e->h2d(d_srt, srt.data(), sizeof(int32_t) * srt.size());
-	int64_t stride = ((int64_t)n + 31) & ~31ll;
-	int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
+	static bool attr_set = false;
+	if (!attr_set) { CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); attr_set = true; }
+	size_t sort_tmp = 0;
+	CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, d_key, d_key2, d_act[0], d_ord, n, 0, 31, e->stream));
+	void *d_sort_tmp = e->b_cub.need(sort_tmp);
+	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
+	int32_t ctr[16];
+	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
+	float ms_dp = 0;
 	e->tic();
-	k_chain2aln<<<grid_for(n, 128), 128, 0, e->stream>>>(eo, e->fm.pac, e->fm.l_pac, n, (const int64_t *)e->d_off.p,
-		(const uint8_t *)e->d_codes.p, d_co, d_ch, d_se, d_srt, d_eh, stride, d_regs, d_nr, e->d_cnt);
+	CK(cudaMemsetAsync(d_ctr, 0, 16 * sizeof(int32_t), e->stream));
+	k_ext_init<<<grid_for(n, 256), 256, 0, e->stream>>>(n, d_co, d_ch, d_state, d_nr, d_act[0], d_ctr);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	CK(cudaMemcpyAsync(ctr, d_ctr, sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+	e->sync();
+	int n_active = ctr[0], cur = 0, rounds = 0;
+	size_t ev_used = 0;
+	while (n_active > 0) {
+		CK(cudaMemsetAsync(d_ctr, 0, 16 * sizeof(int32_t), e->stream));
+		k_ext_advance<<<grid_for(n_active, 128), 128, 0, e->stream>>>(eo, e->fm.l_pac, n_active, d_act[cur], (const int64_t *)e->d_off.p, d_co, d_ch,
+			d_se, d_srt, d_state, d_jobs, d_regs, d_nr, d_act[cur ^ 1], d_key, d_ctr);
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+		CK(cudaMemcpyAsync(ctr, d_ctr, (1 + EXT_N_CLASS) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
+		e->sync();
+		const int n_jobs = ctr[0];
+		if (n_jobs == 0) break;
+		CK(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_tmp, d_key, d_key2, d_act[cur ^ 1], d_ord, n_jobs, 0, 31, e->stream));
+		e->stats.n_launches += 3;
+		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
+		CK(cudaEventRecord(e->ev_pool[ev_used], e->stream));
+		int pos = 0;
+		for (int c = 0; c < EXT_N_CLASS; ++c) {
+			const int cnt = ctr[1 + c];
+			if (cnt == 0) continue;
+			if (c < EXT_N_CLASS - 1) {
+				const int qcap = class_cap[c];
+				const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
+				const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+				k_ext_dp<<<grid_for(cnt, threads), threads, per_warp * (threads / 32), e->stream>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
+					d_jobs, d_ord + pos, cnt, qcap, d_cells, d_calls);
+			} else {
+				int64_t stride = ((int64_t)cnt + 31) & ~31ll;
+				int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
+				k_ext_dp_big<<<grid_for(cnt, 128), 128, 0, e->stream>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_jobs, d_ord + pos, cnt,
+					d_eh, stride, d_cells, d_calls);
+			}
+			CK(cudaGetLastError());
+			e->stats.n_launches += 1;
+			pos += cnt;
+		}
+		CK(cudaEventRecord(e->ev_pool[ev_used + 1], e->stream));
+		ev_used += 2;
+		cur ^= 1;
+		n_active = n_jobs;
+		++rounds;
+	}
+	// compact the regions: reg_off = exclusive scan of n_regs
+	CK(cudaMemsetAsync(d_nr + n, 0, sizeof(int32_t), e->stream));
+	int64_t *d_roff = e->b_soff.as<int64_t>(n + 2);
+	exclusive_scan(e, d_nr, d_roff, n + 1);
+	e->d2h(reg_off.data(), d_roff, sizeof(int64_t) * (n + 1));
+	e->sync();
+	const int64_t total = reg_off[n];
+	DReg *d_out = e->b_xout.as<DReg>(total + 1);
+	k_ext_gather<<<grid_for(n, 256), 256, 0, e->stream>>>(n, d_co, d_ch, d_nr, d_roff, d_regs, d_out);
 	CK(cudaGetLastError());
 	e->stats.n_launches += 1;
 	e->stats.ms_k_extend += e->toc();
-	e->d2h(regs.data(), d_regs, sizeof(DReg) * seeds.size());
-	e->d2h(n_regs.data(), d_nr, sizeof(int32_t) * n);
+	for (size_t i = 0; i < ev_used; i += 2) { float ms; CK(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1])); ms_dp += ms; }
+	e->stats.ms_k_extend_dp += ms_dp;
+	e->stats.n_extend_rounds += rounds;
+	regs.resize(total);
+	e->d2h(regs.data(), d_out, sizeof(DReg) * total);
 	Counters c = e->read_counters();
 	e->stats.extend_cells += (int64_t)c.ext_cells;
 	e->stats.n_extend_jobs += (int64_t)c.ext_calls;

@@ -110,25 +110,30 @@ void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, st
 }
 
 void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
-                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs,
-                  std::vector<int32_t> &n_regs)
+                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int64_t> &reg_off)
 {
 	int n = (int)chain_off.size() - 1;
-	regs.assign(seeds.size() + 1, DReg());
-	n_regs.assign(n, 0);
+	regs.clear();
+	reg_off.assign(n + 1, 0);
 	std::vector<int32_t> eh;
+	std::vector<DReg> tmp;
 	for (int r = 0; r < n; ++r) {
 		int nc = chain_off[r + 1] - chain_off[r];
+		reg_off[r] = (int64_t)regs.size();
 		if (nc == 0) continue;
 		int l_query = (int)(e->off[r + 1] - e->off[r]);
 		eh.resize(2 * (l_query + 2));
 		EhStrided acc = { eh.data(), 1 };
 		int calls = 0;
-		int64_t base = chains[chain_off[r]].seed_beg;
-		n_regs[r] = chain2aln_read(eo, e->fm.pac, e->fm.l_pac, l_query, e->codes.data() + e->off[r], &chains[chain_off[r]], nc,
-		                           seeds.data(), srt.data(), acc, &regs[base], &e->stats.extend_cells, &calls);
+		int n_seeds = 0;
+		for (int c = 0; c < nc; ++c) n_seeds += chains[chain_off[r] + c].n_seeds;
+		tmp.assign(n_seeds + 1, DReg());
+		int nr = chain2aln_read(eo, e->fm.pac, e->fm.l_pac, l_query, e->codes.data() + e->off[r], &chains[chain_off[r]], nc,
+		                        seeds.data(), srt.data(), acc, tmp.data(), &e->stats.extend_cells, &calls);
+		regs.insert(regs.end(), tmp.begin(), tmp.begin() + nr);
 		e->stats.n_extend_jobs += calls;
 	}
+	reg_off[n] = (int64_t)regs.size();
 }
 
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)

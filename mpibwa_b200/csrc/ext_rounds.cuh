@@ -194,81 +194,27 @@ __device__ __forceinline__ int prmt_score(uint32_t lo, uint32_t hi, uint32_t sel
 
 __device__ __forceinline__ int pac_fbase(const uint8_t *__restrict__ pac, int64_t f) { return pac[f >> 2] >> ((~f & 3) << 1) & 3; }
 
-// one ksw_extend2 call on the lane's job; S = packed state row (stride 32 words), Q = query bytes (stride 32 bytes)
-__device__ __forceinline__ void ext_dp_lane(const ExtOpt &o, const uint32_t *__restrict__ sc_lo, const uint32_t *__restrict__ sc_hi,
-                                            const uint8_t *__restrict__ pac, const ExtJob &jb, int w, volatile uint32_t *S,
-                                            const volatile uint8_t *Q, ExtOut *out, long long *cells)
+// Query bytes live in shared memory as [column/4][lane][column%4] (bank = lane for every lane/column combination).
+__device__ __forceinline__ int ext_qidx(int j) { return ((j >> 2) << 7) + (j & 3); }
+
+// row -1 of ksw_extend2 (src/ksw.c:395-397) and the band clamp (src/ksw.c:399-407)
+__device__ __forceinline__ int ext_init_row(const ExtOpt &o, const ExtJob &jb, int w, uint32_t *S)
 {
-	const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0;
-	const int e_del = o.e_del, e_ins = o.e_ins, oe_del = o.o_del + o.e_del, oe_ins = o.o_ins + o.e_ins;
-	int i, j, beg = 0, end = qlen, max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
-	{
-		int v = h0 > oe_ins ? h0 - oe_ins : 0;
-		S[0] = (uint32_t)h0;
-		for (j = 1; j <= qlen; ++j) { S[j * 32] = (uint32_t)v; v = v > e_ins ? v - e_ins : 0; }
-	}
-	{
-		int max_ins = (int)((double)(qlen * o.max_sc + jb.bonus - o.o_ins) / o.e_ins + 1.);
-		max_ins = max_ins > 1 ? max_ins : 1;
-		w = w < max_ins ? w : max_ins;
-		int max_del = (int)((double)(qlen * o.max_sc + jb.bonus - o.o_del) / o.e_del + 1.);
-		max_del = max_del > 1 ? max_del : 1;
-		w = w < max_del ? w : max_del;
-	}
-	long long ncell = 0;
-	int64_t f = jb.f0;
-	for (i = 0; i < tlen; ++i, f += jb.fstep) {
-		int t = pac_fbase(pac, f);
-		if (jb.comp) t = 3 - t;
-		const uint32_t lo = sc_lo[t], hi = sc_hi[t];
-		int fgap = 0, h1, hj = -1;
-		if (beg < i - w) beg = i - w;
-		if (end > i + w + 1) end = i + w + 1;
-		if (end > qlen) end = qlen;
-		if (beg == 0) { h1 = h0 - (o.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
-		else h1 = 0;
-#pragma unroll 2
-		for (j = beg; j < end; ++j) {
-			const uint32_t wd = S[j * 32];
-			const int q = Q[j * 32];
-			const int s = prmt_score(lo, hi, (uint32_t)q * 0x1111u + 0x8880u);
-			const int hd = (int)(wd & 0xffffu);
-			int e = (int)(wd >> 16);
-			int M = hd + s;
-			M = hd ? M : 0;
-			int h = ::max(::max(M, e), fgap);
-			hj = ::max(hj, (h << 16) | j);
-			e = ::max(::max(e - e_del, M - oe_del), 0);
-			fgap = ::max(::max(fgap - e_ins, M - oe_ins), 0);
-			S[j * 32] = (uint32_t)h1 | ((uint32_t)e << 16);
-			h1 = h;
-		}
-		if (end > beg) ncell += end - beg;
-		S[end * 32] = (uint32_t)h1;
-		if (j == qlen) {
-			max_ie = gscore > h1 ? max_ie : i;
-			gscore = gscore > h1 ? gscore : h1;
-		}
-		const int m = hj < 0 ? 0 : hj >> 16, mj = hj < 0 ? -1 : hj & 0xffff;
-		if (m == 0) break;
-		if (m > max) {
-			max = m; max_i = i; max_j = mj;
-			int d = mj - i; d = d < 0 ? -d : d;
-			max_off = max_off > d ? max_off : d;
-		} else if (o.zdrop > 0) {
-			if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > o.zdrop) break; }
-			else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > o.zdrop) break; }
-		}
-		for (j = beg; j < end && S[j * 32] == 0; ++j) {}
-		beg = j;
-		for (j = end; j >= beg && S[j * 32] == 0; --j) {}
-		end = j + 2 < qlen ? j + 2 : qlen;
-	}
-	out->score = max; out->qle = max_j + 1; out->tle = max_i + 1; out->gtle = max_ie + 1; out->gscore = gscore; out->max_off = max_off;
-	*cells += ncell;
+	const int oe_ins = o.o_ins + o.e_ins;
+	int v = jb.h0 > oe_ins ? jb.h0 - oe_ins : 0;
+	S[0] = (uint32_t)jb.h0;
+	for (int j = 1; j <= jb.qlen; ++j) { S[j * 32] = (uint32_t)v; v = v > o.e_ins ? v - o.e_ins : 0; }
+	int max_ins = (int)((double)(jb.qlen * o.max_sc + jb.bonus - o.o_ins) / o.e_ins + 1.);
+	max_ins = max_ins > 1 ? max_ins : 1;
+	w = w < max_ins ? w : max_ins;
+	int max_del = (int)((double)(jb.qlen * o.max_sc + jb.bonus - o.o_del) / o.e_del + 1.);
+	max_del = max_del > 1 ? max_del : 1;
+	return w < max_del ? w : max_del;
 }
 
-// fast path: one job per lane, warps built from the sorted order
+// Fast path: one job per lane, warps built from the size-sorted order.  The row loop is warp-synchronous: every
+// iteration each live lane computes one row of its own job, then the warp reconverges, so that the per-row
+// prologue/epilogue is issued once per warp-row and only the cell loop runs with per-lane trip counts.
 __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
                                                ExtJob *jobs, const int32_t *__restrict__ order, int n, int qcap, unsigned long long *cells_out,
                                                unsigned long long *calls_out)
@@ -278,8 +224,8 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int qpad = (qcap + 4) & ~3;
 	const int per_warp_words = (qcap + 1) * 32 + qpad * 8;
-	volatile uint32_t *S = smem + (size_t)wib * per_warp_words + lane;
-	volatile uint8_t *Q = (volatile uint8_t *)(smem + (size_t)wib * per_warp_words + (qcap + 1) * 32) + lane;
+	uint32_t *S = smem + (size_t)wib * per_warp_words + lane;
+	uint8_t *Q = (uint8_t *)(smem + (size_t)wib * per_warp_words + (qcap + 1) * 32) + lane * 4;
 	if (threadIdx.x < 4) {
 		const int8_t *m = eo.mat + threadIdx.x * 5;
 		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
@@ -287,23 +233,89 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 	}
 	__syncthreads();
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
 	long long cells = 0;
 	int calls = 0;
-	if (t < n) {
-		ExtJob *jp = &jobs[order[t]];
-		const ExtJob jb = *jp;
-		for (int j = 0; j < jb.qlen; ++j) Q[j * 32] = codes[jb.qaddr + (int64_t)jb.qstep * j];
-		ExtOut x; x.score = -1; x.qle = x.tle = x.gtle = 0; x.gscore = -1; x.max_off = 0;
-		int score = jb.prev, aw = eo.w;
-		for (int it = 0; it < 2; ++it) {                      // MAX_BAND_TRY = 2 (src/bwamem.c:630,723-734)
-			const int prev = score;
-			aw = eo.w << it;
-			ext_dp_lane(eo, sc_lo, sc_hi, pac, jb, aw, S, Q, &x, &cells);
-			++calls;
-			score = x.score;
-			if (score == prev || x.max_off < (aw >> 1) + (aw >> 2)) break;
+	ExtJob *jp = nullptr;
+	ExtJob jb;
+	jb.qlen = 0; jb.tlen = 0; jb.h0 = 1; jb.prev = -1; jb.bonus = 0; jb.f0 = 0; jb.fstep = 0; jb.comp = 0; jb.qaddr = 0; jb.qstep = 0;
+	bool alive = false;
+	if (t < n) { jp = &jobs[order[t]]; jb = *jp; alive = true; }
+	for (int j = 0; j < jb.qlen; ++j) Q[ext_qidx(j)] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+	// per-attempt DP state
+	int aw = eo.w, attempt = 0, prev_score = jb.prev;
+	int w = ext_init_row(eo, jb, aw, S);
+	int i = 0, beg = 0, end = jb.qlen, max = jb.h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+	int64_t f = jb.f0;
+	while (__any_sync(0xffffffffu, alive)) {
+		if (alive) {
+			bool done = i >= jb.tlen;
+			if (!done) {
+				int tb = pac_fbase(pac, f);
+				if (jb.comp) tb = 3 - tb;
+				const uint32_t lo = sc_lo[tb], hi = sc_hi[tb];
+				int fgap = 0, h1, hj = -1, j;
+				if (beg < i - w) beg = i - w;
+				if (end > i + w + 1) end = i + w + 1;
+				if (end > jb.qlen) end = jb.qlen;
+				if (beg == 0) { h1 = jb.h0 - (eo.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+				else h1 = 0;
+				for (j = beg; j < end; ++j) {
+					const uint32_t wd = S[j * 32];
+					const int q = Q[ext_qidx(j)];
+					const int sc = prmt_score(lo, hi, (uint32_t)q * 0x1111u + 0x8880u);
+					const int hd = (int)(wd & 0xffffu);
+					int e = (int)(wd >> 16);
+					int M = hd + sc;
+					M = hd ? M : 0;
+					const int h = ::max(::max(M, e), fgap);
+					hj = ::max(hj, h * 65536 + j);
+					e = ::max(::max(e - e_del, M - oe_del), 0);
+					fgap = ::max(::max(fgap - e_ins, M - oe_ins), 0);
+					S[j * 32] = (uint32_t)(e * 65536 + h1);
+					h1 = h;
+				}
+				if (end > beg) cells += end - beg;
+				S[end * 32] = (uint32_t)h1;
+				if (j == jb.qlen) {
+					max_ie = gscore > h1 ? max_ie : i;
+					gscore = gscore > h1 ? gscore : h1;
+				}
+				const int m = hj < 0 ? 0 : hj >> 16, mj = hj < 0 ? -1 : hj & 0xffff;
+				if (m == 0) done = true;
+				else {
+					if (m > max) {
+						max = m; max_i = i; max_j = mj;
+						int d = mj - i; d = d < 0 ? -d : d;
+						max_off = max_off > d ? max_off : d;
+					} else if (eo.zdrop > 0) {
+						if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > eo.zdrop) done = true; }
+						else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > eo.zdrop) done = true; }
+					}
+					if (!done) {
+						for (j = beg; j < end && S[j * 32] == 0; ++j) {}
+						beg = j;
+						for (j = end; j >= beg && S[j * 32] == 0; --j) {}
+						end = j + 2 < jb.qlen ? j + 2 : jb.qlen;
+						++i; f += jb.fstep;
+						if (i >= jb.tlen) done = true;
+					}
+				}
+			}
+			if (done) {                                     // this ksw_extend2 call is over (src/bwamem.c:723-734,751-762)
+				++calls;
+				const int score = max;
+				if (attempt == 0 && !(score == prev_score || max_off < (aw >> 1) + (aw >> 2))) {
+					attempt = 1; prev_score = score; aw = eo.w << 1;
+					w = ext_init_row(eo, jb, aw, S);
+					i = 0; beg = 0; end = jb.qlen; max = jb.h0; max_i = max_j = max_ie = -1; gscore = -1; max_off = 0; f = jb.f0;
+				} else {
+					jp->score = score; jp->qle = max_j + 1; jp->tle = max_i + 1; jp->gtle = max_ie + 1; jp->gscore = gscore; jp->aw = aw;
+					alive = false;
+				}
+			}
 		}
-		jp->score = score; jp->qle = x.qle; jp->tle = x.tle; jp->gtle = x.gtle; jp->gscore = x.gscore; jp->aw = aw;
+		__syncwarp();
 	}
 	for (int o = 16; o > 0; o >>= 1) { cells += __shfl_down_sync(0xffffffffu, cells, o); calls += __shfl_down_sync(0xffffffffu, calls, o); }
 	if (lane == 0) { if (cells) atomicAdd(cells_out, (unsigned long long)cells); if (calls) atomicAdd(calls_out, (unsigned long long)calls); }

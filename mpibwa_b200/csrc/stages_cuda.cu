@@ -66,6 +66,9 @@ public:
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
 	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
 	std::vector<cudaEvent_t> ev_pool;
+	static const int N_SIDE = 8;
+	cudaStream_t side[N_SIDE];
+	cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE];
 	Counters *d_cnt = nullptr;
 
 	void tic() { CK(cudaEventRecord(ev0, stream)); }
@@ -120,6 +123,8 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
 	CK(cudaEventCreate(&e->ev0));
 	CK(cudaEventCreate(&e->ev1));
+	CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+	for (int i = 0; i < Engine::N_SIDE; ++i) { CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming)); }
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	e->bwt_bytes = (size_t)bwt->bwt_size * 4;
 	size_t sa_bytes = (size_t)bwt->n_sa * 8, pac_bytes = (size_t)(bns->l_pac / 4 + 1);
@@ -485,7 +490,7 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	static bool attr_set = false;
 	if (!attr_set) { CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); attr_set = true; }
 	size_t sort_tmp = 0;
-	CK(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, d_key, d_key2, d_act[0], d_ord, n, 0, 31, e->stream));
+	CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp, d_key, d_key2, d_act[0], d_ord, n, 0, 31, e->stream));
 	void *d_sort_tmp = e->b_cub.need(sort_tmp);
 	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
 	int32_t ctr[16];
@@ -509,31 +514,41 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 		CK(cudaMemcpyAsync(ctr, d_ctr, (1 + EXT_N_CLASS) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
 		e->sync();
 		const int n_jobs = ctr[0];
+		if (getenv("B200_DEBUG"))
+			fprintf(stderr, "[ext] round %d active %d jobs %d classes %d %d %d %d %d %d %d %d\n", rounds, n_active, n_jobs, ctr[1], ctr[2], ctr[3],
+			        ctr[4], ctr[5], ctr[6], ctr[7], ctr[8]);
 		if (n_jobs == 0) break;
-		CK(cub::DeviceRadixSort::SortPairs(d_sort_tmp, sort_tmp, d_key, d_key2, d_act[cur ^ 1], d_ord, n_jobs, 0, 31, e->stream));
+		CK(cub::DeviceRadixSort::SortPairsDescending(d_sort_tmp, sort_tmp, d_key, d_key2, d_act[cur ^ 1], d_ord, n_jobs, 0, 31, e->stream));
 		e->stats.n_launches += 3;
 		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
 		CK(cudaEventRecord(e->ev_pool[ev_used], e->stream));
-		int pos = 0;
-		for (int c = 0; c < EXT_N_CLASS; ++c) {
+		// classes run concurrently on side streams (each launch has its own shared-memory footprint); largest jobs first
+		int pos = 0, k = 0;
+		CK(cudaEventRecord(e->ev_fork, e->stream));
+		for (int c = EXT_N_CLASS - 1; c >= 0; --c) {
 			const int cnt = ctr[1 + c];
 			if (cnt == 0) continue;
+			cudaStream_t st = e->side[k % Engine::N_SIDE];
+			CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
 			if (c < EXT_N_CLASS - 1) {
 				const int qcap = class_cap[c];
 				const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
 				const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-				k_ext_dp<<<grid_for(cnt, threads), threads, per_warp * (threads / 32), e->stream>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
+				k_ext_dp<<<grid_for(cnt, threads), threads, per_warp * (threads / 32), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
 					d_jobs, d_ord + pos, cnt, qcap, d_cells, d_calls);
 			} else {
 				int64_t stride = ((int64_t)cnt + 31) & ~31ll;
 				int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
-				k_ext_dp_big<<<grid_for(cnt, 128), 128, 0, e->stream>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_jobs, d_ord + pos, cnt,
+				k_ext_dp_big<<<grid_for(cnt, 128), 128, 0, st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_jobs, d_ord + pos, cnt,
 					d_eh, stride, d_cells, d_calls);
 			}
 			CK(cudaGetLastError());
+			CK(cudaEventRecord(e->ev_join[k % Engine::N_SIDE], st));
 			e->stats.n_launches += 1;
 			pos += cnt;
+			++k;
 		}
+		for (int q = 0; q < k && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
 		CK(cudaEventRecord(e->ev_pool[ev_used + 1], e->stream));
 		ev_used += 2;
 		cur ^= 1;

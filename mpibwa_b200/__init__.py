@@ -161,6 +161,8 @@ def load(path=None):
         raise RuntimeError("%s not found: run `make lib` (or __graft_entry__.build()); there is no Python/CPU fallback" % p)
     lib = C.CDLL(p)
     for name, (res, args) in _PROTOTYPES.items():
+        if path is not None and not hasattr(lib, name):
+            continue                      # test scaffolds (tests/hostemu) do not carry the device-only symbols
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1,0 +1,299 @@
+// smem_kernel.cuh - SMEM seeding (mem_collect_intv, reference src/bwamem.c:114-162 over bwt_smem1a / bwt_seed_strategy1,
+// src/bwt.c:289-379) as a per-lane state machine whose only expensive step is ONE bwt_extend per loop iteration.
+//
+// Why a state machine: the three seeding passes of a read are a few hundred *dependent* bi-directional extensions
+// (each = two 64-byte occ blocks of the FM-index, fetched with independent 128-bit loads) wrapped in irregular list
+// logic.  Running the reference's nested loops one read per thread leaves every lane of a warp in a different loop
+// nest (v1: 8.8 of 32 lanes active per instruction) and forces the per-read interval lists into thread-local arrays
+// in HBM (v1: 47.8 GB written per chunk).  Here
+//   * every lane owns one read and a small explicit state; each trip of the warp loop issues exactly one extension for
+//     every live lane (the block loads of all lanes are in flight together), then a short state transition;
+//   * the interval list of bwt_smem1a lives in shared memory.  ONE list suffices: the backward sweep compacts `prev`
+//     into `curr` in place (the write cursor never passes the read cursor) and the list is kept top-aligned and walked
+//     downwards so that the reference's "reverse curr" step disappears; entries are packed to 16 bytes (three 33-bit
+//     interval words + the end position) and laid out [entry][word][thread] (bank = lane).  Entries beyond the shared
+//     quota spill to a per-thread global strip (only very repetitive reads get there);
+//   * finished lanes fetch the next read from a global counter (persistent grid, no tail of idle lanes);
+//   * SMEMs are appended to the read's output strip as they are found; the sort by (start,end) that closes
+//     mem_collect_intv is done by rank in k_compact_intv (equal keys are identical intervals).
+//
+// The code is host/device so that tests/hostemu can run the very same state machine on the CPU against the
+// straightforward restatement in fm_kernels.h (and through it against the oracle).
+#pragma once
+#include "fm_kernels.h"
+
+namespace b200 {
+
+struct alignas(16) Q4 { uint32_t x, y, z, w; };
+
+B200_HD Q4 ld_q4(const uint32_t *p)
+{
+#if defined(__CUDA_ARCH__)
+	const uint4 v = __ldg(reinterpret_cast<const uint4 *>(p));
+	Q4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w;
+	return r;
+#else
+	return *reinterpret_cast<const Q4 *>(p);
+#endif
+}
+
+// fm.L2[i] without a dynamically indexed kernel parameter (which would be copied to local memory)
+B200_HD uint64_t l2_at(const FmView &fm, int i)
+{
+	return i == 0 ? fm.L2[0] : i == 1 ? fm.L2[1] : i == 2 ? fm.L2[2] : i == 3 ? fm.L2[3] : fm.L2[4];
+}
+
+// Occ(., k) for the four symbols from one loaded block; kin = (adjusted k) & 127
+B200_HD void occ4_block(const Q4 &c0, const Q4 &c1, const Q4 &s0, const Q4 &s1, uint32_t kin, uint64_t cnt[4])
+{
+	const uint32_t w[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
+	const uint32_t full = kin >> 4;
+	const uint32_t pm = ~((1u << ((~kin & 15u) << 1)) - 1u);
+	uint32_t slo = 0, shi = 0, s3 = 0;
+#pragma unroll
+	for (uint32_t i = 0; i < 8; ++i) {
+		const uint32_t m = i < full ? 0xffffffffu : (i == full ? pm : 0u);
+		const uint32_t v = w[i] & m;
+		const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+		slo += (uint32_t)popc32(lo); shi += (uint32_t)popc32(hi); s3 += (uint32_t)popc32(lo & hi);
+	}
+	const uint32_t n1 = slo - s3, n2 = shi - s3;
+	cnt[0] = ((uint64_t)c0.y << 32 | c0.x) + (kin + 1u - n1 - n2 - s3);
+	cnt[1] = ((uint64_t)c0.w << 32 | c0.z) + n1;
+	cnt[2] = ((uint64_t)c1.y << 32 | c1.x) + n2;
+	cnt[3] = ((uint64_t)c1.w << 32 | c1.z) + s3;
+}
+
+// bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c
+B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c,
+                           uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
+{
+	const uint64_t base = is_back ? x0 : x1, other = is_back ? x1 : x0;
+	const uint64_t k = base - 1, l = base - 1 + x2;
+	const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
+	const uint64_t ka = kz ? 0 : k - (k >= fm.primary), la = lz ? 0 : l - (l >= fm.primary);
+	const uint32_t *pk = fm.bwt + ((ka >> 7) << 4), *pl = fm.bwt + ((la >> 7) << 4);
+	const Q4 kc0 = ld_q4(pk), kc1 = ld_q4(pk + 4), ks0 = ld_q4(pk + 8), ks1 = ld_q4(pk + 12);
+	const Q4 lc0 = ld_q4(pl), lc1 = ld_q4(pl + 4), ls0 = ld_q4(pl + 8), ls1 = ld_q4(pl + 12);
+	uint64_t tk[4], tl[4];
+	occ4_block(kc0, kc1, ks0, ks1, (uint32_t)ka & 127u, tk);
+	occ4_block(lc0, lc1, ls0, ls1, (uint32_t)la & 127u, tl);
+	if (kz) tk[0] = tk[1] = tk[2] = tk[3] = 0;
+	if (lz) tl[0] = tl[1] = tl[2] = tl[3] = 0;
+	n_blocks += (kz ? 0 : 1) + ((!lz && (kz || (la >> 7) != (ka >> 7))) ? 1 : 0);
+	const uint64_t s1 = tl[1] - tk[1], s2 = tl[2] - tk[2], s3 = tl[3] - tk[3];
+	const uint64_t tkc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
+	const uint64_t tlc = c == 0 ? tl[0] : c == 1 ? tl[1] : c == 2 ? tl[2] : tl[3];
+	const uint64_t nb = l2_at(fm, c) + 1 + tkc;
+	uint64_t oth = other + ((base <= fm.primary && base + x2 - 1 >= fm.primary) ? 1 : 0);
+	oth += (c < 3 ? s3 : 0) + (c < 2 ? s2 : 0) + (c < 1 ? s1 : 0);
+	o2 = tlc - tkc;
+	if (is_back) { o0 = nb; o1 = oth; } else { o1 = nb; o0 = oth; }
+}
+
+// The interval list of one lane.  Entry k < quota lives in shared memory (sh[(k*4 + word) * stride]), the rest in the
+// lane's global strip (spill[(k - quota) * sstride]).  Values up to 2^33-1, end positions up to 2^29-1.
+struct SeedList {
+	uint32_t *sh; int stride, quota;
+	Q4 *spill; int64_t sstride;
+	B200_HD void set(int k, uint64_t x0, uint64_t x1, uint64_t x2, int end) const
+	{
+		Q4 v;
+		v.x = (uint32_t)x0; v.y = (uint32_t)x1; v.z = (uint32_t)x2;
+		v.w = (uint32_t)end | (uint32_t)(x0 >> 32) << 29 | (uint32_t)(x1 >> 32) << 30 | (uint32_t)(x2 >> 32) << 31;
+		if (k < quota) {
+			uint32_t *p = sh + (size_t)(k * 4) * stride;
+			p[0] = v.x; p[stride] = v.y; p[2 * stride] = v.z; p[3 * stride] = v.w;
+		} else spill[(int64_t)(k - quota) * sstride] = v;
+	}
+	B200_HD void get(int k, uint64_t &x0, uint64_t &x1, uint64_t &x2, int &end) const
+	{
+		Q4 v;
+		if (k < quota) {
+			const uint32_t *p = sh + (size_t)(k * 4) * stride;
+			v.x = p[0]; v.y = p[stride]; v.z = p[2 * stride]; v.w = p[3 * stride];
+		} else v = spill[(int64_t)(k - quota) * sstride];
+		x0 = (uint64_t)(v.w >> 29 & 1u) << 32 | v.x;
+		x1 = (uint64_t)(v.w >> 30 & 1u) << 32 | v.y;
+		x2 = (uint64_t)(v.w >> 31) << 32 | v.z;
+		end = (int)(v.w & 0x1fffffffu);
+	}
+};
+
+struct SeedLane {
+	enum { P1_NEXT, FWD, BWD_ROW, BWD, SMEM_END, P2_NEXT, P3_NEXT, P3, FINISH };
+	// the read
+	int len; const uint8_t *q; Intv *outp;
+	// machine
+	int st, pass, x, sx, i, c, is_back;
+	uint64_t k0, k1, k2; int kend;        // interval to extend next (forward: ik; backward: the entry being extended)
+	uint64_t min_intv, last_x2;
+	int n_list, n_prev, j, n_curr;
+	int nm, last_start, ret;
+	int n_out, old_n, k2i;
+
+	B200_HD void begin(const SeedOpt &so, int len_, const uint8_t *q_, Intv *outp_)
+	{
+		len = len_; q = q_; outp = outp_;
+		n_out = 0; x = 0; pass = 1;
+		st = len >= so.min_seed_len ? P1_NEXT : FINISH;
+	}
+	B200_HD void set_intv(const FmView &fm, int b)
+	{
+		k0 = l2_at(fm, b) + 1; k2 = l2_at(fm, b + 1) - l2_at(fm, b); k1 = l2_at(fm, 3 - b) + 1;
+	}
+	B200_HD void start_smem(const FmView &fm, int x_, uint64_t mi)
+	{
+		set_intv(fm, q[x_]);
+		kend = x_ + 1; min_intv = mi < 1 ? 1 : mi;
+		n_list = 0; nm = 0; last_start = 0; sx = x_; i = x_ + 1; st = FWD;
+	}
+	B200_HD void emit(const SeedOpt &so, int cap, uint64_t p0, uint64_t p1, uint64_t p2, int start, int end, bool filter)
+	{
+		if (filter && end - start < so.min_seed_len) return;
+		if (n_out < cap) { Intv v; v.x0 = p0; v.x1 = p1; v.x2 = p2; v.info = (uint64_t)start << 32 | (uint32_t)end; outp[n_out] = v; }
+		++n_out;
+	}
+	B200_HD void fwd_done(const SeedList &L)
+	{
+		L.set(n_list++, k0, k1, k2, kend);        // the interval that could not be extended any further
+		ret = kend; n_prev = n_list; i = sx - 1; st = BWD_ROW;
+	}
+
+	// run the cheap transitions until the lane needs an extension (true; inputs in k0,k1,k2,is_back,c) or its read is done
+	B200_HD bool advance(const FmView &fm, const SeedOpt &so, int cap, const SeedList &L)
+	{
+		for (;;) {
+			switch (st) {
+			case P1_NEXT:
+				if (x >= len) { pass = 2; old_n = n_out <= cap ? n_out : 0; k2i = 0; st = P2_NEXT; break; }
+				if (q[x] > 3) { ++x; break; }
+				start_smem(fm, x, 1);
+				break;
+			case FWD:
+				if (i < len && q[i] < 4) { c = 3 - q[i]; is_back = 0; return true; }
+				fwd_done(L);                          // end of the read or an ambiguous base
+				break;
+			case BWD_ROW: {
+				const int cc = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+				if (cc < 0) {                         // nothing can be extended: only the longest entry may be reported
+					if (nm == 0 || i + 1 < last_start) {
+						L.get(n_list - 1, k0, k1, k2, kend);
+						emit(so, cap, k0, k1, k2, i + 1, kend, true);
+						last_start = i + 1; ++nm;
+					}
+					st = SMEM_END;
+					break;
+				}
+				c = cc; j = 0; n_curr = 0; st = BWD;
+				break;
+			}
+			case BWD:
+				L.get(n_list - 1 - j, k0, k1, k2, kend);
+				is_back = 1;
+				return true;
+			case SMEM_END:
+				if (pass == 1) { x = ret; st = P1_NEXT; }
+				else { ++k2i; st = P2_NEXT; }
+				break;
+			case P2_NEXT: {
+				if (k2i >= old_n) { pass = 3; x = 0; st = so.max_mem_intv > 0 ? P3_NEXT : FINISH; break; }
+				const Intv p = outp[k2i];
+				const int start = (int)(p.info >> 32), end = (int)(int32_t)p.info;
+				if (end - start < so.split_len || p.x2 > (uint64_t)so.split_width) { ++k2i; break; }
+				const int mid = (start + end) >> 1;
+				if (q[mid] > 3) { ++k2i; break; }
+				start_smem(fm, mid, p.x2 + 1);
+				break;
+			}
+			case P3_NEXT:
+				if (x >= len) { st = FINISH; break; }
+				if (q[x] > 3) { ++x; break; }
+				set_intv(fm, q[x]);
+				sx = x; i = x + 1; st = P3;
+				break;
+			case P3:
+				if (i >= len) { x = len; st = P3_NEXT; break; }
+				if (q[i] > 3) { x = i + 1; st = P3_NEXT; break; }
+				c = 3 - q[i]; is_back = 0;
+				return true;
+			default:
+				return false;
+			}
+		}
+	}
+
+	// digest the result of the extension requested by advance()
+	B200_HD void consume(const SeedOpt &so, int cap, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
+	{
+		if (st == FWD) {
+			if (o2 != k2) {
+				if (o2 < min_intv) { fwd_done(L); return; }
+				L.set(n_list++, k0, k1, k2, kend);
+			}
+			k0 = o0; k1 = o1; k2 = o2; kend = i + 1; ++i;
+		} else if (st == BWD) {
+			if (o2 < min_intv) {
+				if (n_curr == 0 && (nm == 0 || i + 1 < last_start)) {
+					emit(so, cap, k0, k1, k2, i + 1, kend, true);
+					last_start = i + 1; ++nm;
+				}
+			} else if (n_curr == 0 || o2 != last_x2) {
+				L.set(n_list - 1 - n_curr, o0, o1, o2, kend);
+				++n_curr; last_x2 = o2;
+			}
+			if (++j == n_prev) {
+				if (n_curr == 0) st = SMEM_END;
+				else { n_prev = n_curr; --i; st = BWD_ROW; }
+			}
+		} else {                                      // P3 (reference src/bwt.c:367-376)
+			if (o2 < (uint64_t)so.max_mem_intv && i - sx >= so.min_seed_len) {
+				if (o2 > 0) emit(so, cap, o0, o1, o2, sx, i + 1, false);
+				x = i + 1; st = P3_NEXT;
+			} else { k0 = o0; k1 = o1; k2 = o2; ++i; }
+		}
+	}
+};
+
+#if defined(__CUDACC__)
+// Persistent kernel: every lane pulls reads from *next_read until none are left.
+// n_intv[r] = number of intervals of read r (unsorted, in out[r*cap ..]), or -(needed) when cap was too small.
+__global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n_reads, const int64_t *__restrict__ off,
+                                                    const uint8_t *__restrict__ codes, Intv *out, int cap, int quota, Q4 *spill,
+                                                    int32_t *n_intv, int *next_read, int *worst, unsigned long long *occ_blocks)
+{
+	extern __shared__ uint32_t seed_sh[];
+	SeedList L;
+	L.sh = seed_sh + threadIdx.x; L.stride = blockDim.x; L.quota = quota;
+	L.sstride = (int64_t)gridDim.x * blockDim.x;
+	L.spill = spill + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	SeedLane ln;
+	ln.st = SeedLane::FINISH; ln.n_out = 0;
+	int r = -1;
+	bool need = false, drained = false;
+	int64_t blocks = 0;
+	for (;;) {
+		while (!need && !drained) {
+			if (r >= 0) {
+				n_intv[r] = ln.n_out > cap ? -ln.n_out : ln.n_out;
+				if (ln.n_out > cap) atomicMax(worst, ln.n_out);
+			}
+			r = atomicAdd(next_read, 1);
+			if (r >= n_reads) { r = -1; drained = true; break; }
+			ln.begin(so, (int)(off[r + 1] - off[r]), codes + off[r], out + (int64_t)r * cap);
+			need = ln.advance(fm, so, cap, L);
+		}
+		if (!__any_sync(0xffffffffu, need)) break;
+		if (need) {
+			uint64_t o0, o1, o2;
+			fm_extend_sel(fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
+			ln.consume(so, cap, L, o0, o1, o2);
+			need = ln.advance(fm, so, cap, L);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);
+	if ((threadIdx.x & 31) == 0 && blocks) atomicAdd(occ_blocks, (unsigned long long)blocks);
+}
+#endif
+
+} // namespace b200

@@ -13,6 +13,7 @@
 #include "stages.h"
 #include "util.h"
 #include "ext_rounds.cuh"
+#include "smem_kernel.cuh"
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
@@ -152,6 +153,7 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.pac = (const uint8_t *)e->d_pac; fm.l_pac = bns->l_pac;
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
+	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
 
 	// L2 persistence window over the occ/BWT blocks (north star: "L2-persistence windows for the hot Occ blocks")
 	cudaDeviceProp prop;
@@ -199,43 +201,38 @@ static inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) 
 
 /* ------------------------------------------------------------------ seeding */
 
-__global__ void __launch_bounds__(128) k_collect_intv(FmView fm, SeedOpt so, int n_reads, const int64_t *__restrict__ off,
-                                                      const uint8_t *__restrict__ codes, Intv *out, int cap, Intv *scratch,
-                                                      int scr_per_read, int32_t *n_intv, Counters *cnt)
-{
-	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t blocks = 0;
-	if (r < n_reads) {
-		int len = (int)(off[r + 1] - off[r]);
-		int n = 0;
-		if (len >= so.min_seed_len)
-			n = fm_collect_intv(fm, so, len, codes + off[r], out + (int64_t)r * cap, cap, scratch + (int64_t)r * scr_per_read, &blocks);
-		n_intv[r] = n;
-	}
-	warp_add(&cnt->occ_blocks, blocks);
-}
-
-// per read: l_rep (reference src/bwamem.c:261-269) and compaction of the interval list with per-interval slot counts
-__global__ void k_compact_intv(SeedOpt so, int n_reads, const Intv *__restrict__ in, int cap, const int32_t *__restrict__ n_intv,
-                               const int64_t *__restrict__ ioff, Intv *civ, int32_t *slots, int32_t *l_rep)
+// per read: order the interval list by (start,end) (the ks_introsort that closes mem_collect_intv, reference
+// src/bwamem.c:160; equal keys are identical intervals, so a rank is enough), compact it, count the SA slots of every
+// interval and compute l_rep (reference src/bwamem.c:261-269)
+__global__ void __launch_bounds__(128) k_compact_intv(SeedOpt so, int n_reads, const Intv *__restrict__ in, int cap, const int32_t *__restrict__ n_intv,
+                                                      const int64_t *__restrict__ ioff, Intv *civ, int32_t *slots, int32_t *l_rep)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= n_reads) return;
-	int n = n_intv[r];
+	const int n = n_intv[r];
 	const Intv *p = in + (int64_t)r * cap;
-	int64_t o = ioff[r];
+	const int64_t o = ioff[r];
+	for (int i = 0; i < n; ++i) {
+		const Intv v = p[i];
+		int rank = 0;
+		for (int j = 0; j < n; ++j) {
+			const uint64_t u = p[j].info;
+			rank += (u < v.info) || (u == v.info && j < i);
+		}
+		civ[o + rank] = v;
+		slots[o + rank] = seed_slots(v.x2, so.max_occ);
+	}
+	if (!l_rep) return;
 	int b = 0, e = 0, rep = 0;
 	for (int i = 0; i < n; ++i) {
-		Intv v = p[i];
-		int sb = (int)(v.info >> 32), se = (int)(uint32_t)v.info;
-		civ[o + i] = v;
-		slots[o + i] = seed_slots(v.x2, so.max_occ);
+		const Intv v = civ[o + i];
 		if (v.x2 <= (uint64_t)so.max_occ) continue;
+		const int sb = (int)(v.info >> 32), se = (int)(uint32_t)v.info;
 		if (sb > e) { rep += e - b; b = sb; e = se; }
 		else e = e > se ? e : se;
 	}
 	rep += e - b;
-	if (l_rep) l_rep[r] = rep;
+	l_rep[r] = rep;
 }
 
 // one thread per suffix-array look-up
@@ -318,23 +315,35 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
                            bool want_lrep)
 {
 	const int n = r1 - r0;
-	int cap = max_len + 32;
-	const int scr = 3 * (max_len + 1);
+	static int blocks_per_sm = 0, n_sm = 0;
+	const int threads = 128, quota = 16;
+	const size_t sh_bytes = (size_t)threads * quota * 16;
+	if (!blocks_per_sm) {
+		cudaDeviceProp prop;
+		CK(cudaGetDeviceProperties(&prop, e->device));
+		n_sm = prop.multiProcessorCount;
+		CK(cudaFuncSetAttribute(k_seed_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_seed_lanes, threads, sh_bytes));
+		if (blocks_per_sm < 1) die("k_seed_lanes does not fit an SM");
+	}
+	const int grid = std::min(n_sm * blocks_per_sm, grid_for(n, threads));
+	int cap = std::min(max_len + 32, 64);
 	int32_t *n_intv = e->b_nintv.as<int32_t>(n + 1);
+	int *ctr = e->b_xctr.as<int>(16);
+	const int spill_per = std::max(0, max_len + 2 - quota);
+	Q4 *spill = e->b_scr.as<Q4>((size_t)grid * threads * spill_per + 1);
 	for (;;) {
 		Intv *out = e->b_intv.as<Intv>((size_t)n * cap);
-		Intv *scratch = e->b_scr.as<Intv>((size_t)n * scr);
-		k_collect_intv<<<grid_for(n, 128), 128, 0, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, scratch, scr, n_intv, e->d_cnt);
+		CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), e->stream));
+		k_seed_lanes<<<grid, threads, sh_bytes, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, quota, spill, n_intv, ctr, ctr + 1,
+			&e->d_cnt->occ_blocks);
 		CK(cudaGetLastError());
 		e->stats.n_launches += 1;
-		// overflow check (rare: more intervals than len+32)
-		std::vector<int32_t> h(n);
-		e->d2h(h.data(), n_intv, sizeof(int32_t) * n);
+		int h[2];
+		CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
 		e->sync();
-		int worst = 0;
-		for (int v : h) worst = std::min(worst, v);
-		if (worst >= 0) break;
-		cap = -worst + 32;
+		if (h[1] <= cap) break;                 // no read needed more than cap intervals
+		cap = h[1] + 8;                         // rare (very repetitive reads): run the sub-batch again with room for the worst
 	}
 	CK(cudaMemsetAsync(n_intv + n, 0, sizeof(int32_t), e->stream));
 	int64_t *ioff = e->b_ioff.as<int64_t>(n + 1);
@@ -353,8 +362,8 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 
 static int seed_sub_batch(int max_len)
 {
-	// scratch per read: (3*(len+1) + len+32) intervals of 32 bytes; keep one sub-batch under ~12 GB
-	size_t per = (size_t)(4 * max_len + 40) * sizeof(Intv);
+	// output strip per read: up to len+32 intervals of 32 bytes (64 in the common case); keep one sub-batch under ~12 GB
+	size_t per = (size_t)(max_len + 40) * sizeof(Intv);
 	size_t n = ((size_t)12 << 30) / per;
 	return (int)std::max<size_t>(1024, std::min<size_t>(n, 1 << 20));
 }

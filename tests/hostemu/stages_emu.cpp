@@ -4,6 +4,9 @@
 // libmpibwa_b200.so links stages_cuda.cu and has no CPU execution path.
 #include "../../mpibwa_b200/csrc/stages.h"
 #include "../../mpibwa_b200/csrc/util.h"
+#include "../../mpibwa_b200/csrc/smem_kernel.cuh"
+#include <cstdio>
+#include <algorithm>
 #include <cstring>
 #include <cstdlib>
 
@@ -63,6 +66,32 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 				if (n >= 0) break;
 				cap = -n * 2;
 			}
+		}
+		{	// cross-check: the lane state machine of the CUDA seeding kernel (smem_kernel.cuh), run here on the CPU with
+			// a tiny shared quota so that the spill path is exercised too, must give the same interval set
+			const int quota = 1 + r % 5, cap2 = std::max(len + 32, n + 1);
+			std::vector<uint32_t> sh(4 * quota);
+			std::vector<Q4> spill(len + 2);
+			std::vector<Intv> out2(cap2);
+			SeedList L; L.sh = sh.data(); L.stride = 1; L.quota = quota; L.spill = spill.data(); L.sstride = 1;
+			SeedLane ln;
+			int64_t blocks = 0;
+			ln.begin(so, len, codes + off[r], out2.data());
+			while (ln.advance(e->fm, so, cap2, L)) {
+				uint64_t o0, o1, o2;
+				fm_extend_sel(e->fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
+				ln.consume(so, cap2, L, o0, o1, o2);
+			}
+			bool same = ln.n_out == n;
+			if (same) {
+				std::sort(out2.begin(), out2.begin() + n, [](const Intv &a, const Intv &b) { return a.info < b.info; });
+				for (int i = 0; i < n && same; ++i)
+					same = out2[i].x0 == out[i].x0 && out2[i].x1 == out[i].x1 && out2[i].x2 == out[i].x2 && out2[i].info == out[i].info;
+			}
+			if (!same && getenv("B200_EMU_DEBUG")) for (int i = 0; i < n; ++i) fprintf(stderr, "%d: v1 %llu %llu %llu %d-%d | v2 %llu %llu %llu %d-%d\n", i,
+				(unsigned long long)out[i].x0, (unsigned long long)out[i].x1, (unsigned long long)out[i].x2, (int)(out[i].info >> 32), (int)(uint32_t)out[i].info,
+				(unsigned long long)out2[i].x0, (unsigned long long)out2[i].x1, (unsigned long long)out2[i].x2, (int)(out2[i].info >> 32), (int)(uint32_t)out2[i].info);
+			if (!same) { fprintf(stderr, "[hostemu] seeding state machine disagrees with fm_collect_intv on read %d (%d vs %d intervals)\n", r, ln.n_out, n); abort(); }
 		}
 		intv.insert(intv.end(), out.begin(), out.begin() + n);
 		intv_off[r + 1] = (int64_t)intv.size();

@@ -244,6 +244,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		}
 	});
 	seed_recs.clear(); seed_recs.shrink_to_fit();
+	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] build+filter %.1f ms\n", now_ms() - t0);
 
 	// ---- mem_flt_chained_seeds (reference src/bwamem.c:571-615): only reads of >= ~730 bp get here
 	{
@@ -333,6 +334,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		chain_off[n] = (int32_t)dchains.size();
 		st.n_chains = (int64_t)dchains.size();
 	}
+	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] +flatten %.1f ms\n", now_ms() - t0);
 	chains.clear(); chains.shrink_to_fit();
 	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
 

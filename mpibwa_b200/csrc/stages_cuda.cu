@@ -14,6 +14,7 @@
 #include "util.h"
 #include "ext_rounds.cuh"
 #include "smem_kernel.cuh"
+#include "sw_warp_kernel.cuh"
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
@@ -632,25 +633,142 @@ void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend
 
 /* ------------------------------------------------------------------ local Smith-Waterman (mate rescue, seed filter) */
 
-__global__ void __launch_bounds__(128) k_sw_jobs(SwOpt so, const uint8_t *__restrict__ pac, int64_t l_pac, int64_t n_jobs,
-                                                 const SwJob *__restrict__ jobs, const int64_t *__restrict__ off,
-                                                 const uint8_t *__restrict__ codes, uint16_t *H, uint16_t *E, uint64_t *B,
-                                                 int64_t stride, SwRes *res, Counters *cnt)
+// query accessor with a run-time orientation (read only while a pass loads its strip of the query into registers)
+struct SQAny {
+	const uint8_t *p; int l, rev;
+	__device__ __forceinline__ int operator()(int j) const { if (!rev) return p[j]; int c = p[l - 1 - j]; return c < 4 ? 3 - c : 4; }
+};
+
+// job sources of the Smith-Waterman kernels: the rescue/seed-filter jobs of the pipeline (query = a resident read, target =
+// a window of the packed reference) and the flat byte buffers of b200_ksw_align2_batch
+struct SwSrcPipeline {
+	const SwJob *jobs; const int64_t *off; const uint8_t *codes; const uint8_t *pac; int64_t l_pac; SwRes *res;
+	typedef STPac Target;
+	__device__ __forceinline__ void load(int jx, int &qlen, int &tlen, int &xtra, SQAny &q, STPac &t) const
+	{
+		const SwJob j = jobs[jx];
+		qlen = j.q_len; tlen = j.tlen; xtra = j.xtra;
+		q.p = codes + off[j.read] + j.q_beg; q.l = j.q_len; q.rev = j.is_rev;
+		t.pac = pac; t.l_pac = l_pac; t.beg = j.rb;
+	}
+	__device__ __forceinline__ void store(int jx, const SwRes &r) const { res[jx] = r; }
+};
+struct SwSrcBytes {
+	b200_align_job_t *jobs; const uint8_t *query, *target;
+	typedef STBytes Target;
+	__device__ __forceinline__ void load(int jx, int &qlen, int &tlen, int &xtra, SQAny &q, STBytes &t) const
+	{
+		const b200_align_job_t &j = jobs[jx];
+		qlen = j.qlen; tlen = j.tlen; xtra = j.xtra;
+		q.p = query + j.q_off; q.l = j.qlen; q.rev = 0;
+		t.p = target + j.t_off;
+	}
+	__device__ __forceinline__ void store(int jx, const SwRes &r) const
+	{
+		kswr_t &o = jobs[jx].r;
+		o.score = r.score; o.te = r.te; o.qe = r.qe; o.score2 = r.score2; o.te2 = r.te2; o.tb = r.tb; o.qb = r.qb;
+	}
+};
+
+// one warp per job (sw_warp_kernel.cuh); order[w] = job of warp w, B = run-list scratch (bcap entries per warp)
+template <int C, class SRC>
+__global__ void __launch_bounds__(128) k_sw_warp(SwOpt so, SRC src, const int32_t *__restrict__ order, int n, uint64_t *B, int64_t bcap, Counters *cnt)
+{
+	__shared__ uint32_t lut[10];
+	sw_fill_lut(so, lut);
+	__syncthreads();
+	const int w = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+	long long cells = 0;
+	if (w < n) {
+		const int jx = order[w];
+		int qlen, tlen, xtra;
+		SQAny q;
+		typename SRC::Target t;
+		src.load(jx, qlen, tlen, xtra, q, t);
+		SwRes r;
+		sw_align_warp<C>(qlen, q, tlen, t, so, lut, xtra, B + (int64_t)w * bcap, &r, &cells);
+		if ((threadIdx.x & 31) == 0) src.store(jx, r);
+	}
+	if (cells) atomicAdd(&cnt->sw_cells, (unsigned long long)cells);
+}
+
+// general path (queries wider than 256 padded columns): one job per thread, rows in global memory
+template <class SRC>
+__global__ void __launch_bounds__(128) k_sw_thread(SwOpt so, SRC src, const int32_t *__restrict__ order, int n, uint16_t *H, uint16_t *E, uint64_t *B,
+                                                   int64_t stride, Counters *cnt)
 {
 	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t cells = 0;
-	if (t < n_jobs) {
-		SwJob j = jobs[t];
+	if (t < n) {
+		const int jx = order[t];
+		int qlen, tlen, xtra;
+		SQAny q;
+		typename SRC::Target ta;
+		src.load(jx, qlen, tlen, xtra, q, ta);
 		Row16 h = { H + t, stride }, ee = { E + t, stride };
 		List64 bl = { B + t, stride };
-		STPac ta = { pac, l_pac, j.rb };
-		const uint8_t *q = codes + off[j.read] + j.q_beg;
 		SwRes r;
-		if (j.is_rev) { SQRevComp qa = { q, j.q_len }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells); }
-		else { SQFwd qa = { q }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells); }
-		res[t] = r;
+		sw_align(qlen, q, tlen, ta, so, xtra, h, ee, bl, &r, &cells);
+		src.store(jx, r);
 	}
 	warp_add(&cnt->sw_cells, cells);
+}
+
+// Runs n jobs (lengths/xtra given on the host for classification) through the warp kernels, one launch per strip width on
+// concurrent streams, and the rest through the general kernel.  `src` holds device pointers.
+template <class SRC, class LEN>
+static void run_sw(Engine *e, const SwOpt &so, const SRC &src, int64_t n, LEN len_of /* (i, &qlen, &tlen, &xtra) */)
+{
+	static const int cls_c[5] = { 0, 2, 4, 5, 8 };
+	std::vector<int32_t> order(n);
+	int64_t cnt[5] = { 0, 0, 0, 0, 0 }, pos[5];
+	int max_q = 0, max_t = 0;
+	std::vector<uint8_t> cls(n);
+	for (int64_t i = 0; i < n; ++i) {
+		int ql, tl, xt;
+		len_of(i, ql, tl, xt);
+		const int c = sw_warp_class(ql, xt);
+		const int k = c == 0 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 5 ? 3 : 4;
+		cls[i] = (uint8_t)k; ++cnt[k];
+		max_t = std::max(max_t, tl);
+		if (k == 0) max_q = std::max(max_q, ql);
+	}
+	pos[0] = 0;
+	for (int k = 1; k < 5; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
+	{ int64_t w[5]; for (int k = 0; k < 5; ++k) w[k] = pos[k]; for (int64_t i = 0; i < n; ++i) order[w[cls[i]]++] = (int32_t)i; }
+	int32_t *d_ord = e->b_xord.as<int32_t>(n);
+	e->h2d(d_ord, order.data(), sizeof(int32_t) * n);
+	const int64_t bcap = max_t / 2 + 2;
+	uint64_t *B = e->b_b.as<uint64_t>((size_t)(n + 32) * bcap);
+	e->tic();
+	CK(cudaEventRecord(e->ev_fork, e->stream));
+	int used = 0;
+	for (int k = 4; k >= 0; --k) {
+		if (cnt[k] == 0) continue;
+		cudaStream_t st = e->side[used % Engine::N_SIDE];
+		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+		const int nk = (int)cnt[k];
+		const int32_t *ord = d_ord + pos[k];
+		uint64_t *Bk = B + pos[k] * bcap;
+		const int grid = grid_for((int64_t)nk * 32, 128);
+		if (k == 4) k_sw_warp<8, SRC><<<grid, 128, 0, st>>>(so, src, ord, nk, Bk, bcap, e->d_cnt);
+		else if (k == 3) k_sw_warp<5, SRC><<<grid, 128, 0, st>>>(so, src, ord, nk, Bk, bcap, e->d_cnt);
+		else if (k == 2) k_sw_warp<4, SRC><<<grid, 128, 0, st>>>(so, src, ord, nk, Bk, bcap, e->d_cnt);
+		else if (k == 1) k_sw_warp<2, SRC><<<grid, 128, 0, st>>>(so, src, ord, nk, Bk, bcap, e->d_cnt);
+		else {
+			const int64_t stride = ((int64_t)nk + 31) & ~31ll;
+			uint16_t *H = e->b_h.as<uint16_t>((size_t)stride * (max_q + 16));
+			uint16_t *E = e->b_e.as<uint16_t>((size_t)stride * (max_q + 16));
+			uint64_t *B0 = e->b_eh.as<uint64_t>((size_t)stride * bcap);
+			k_sw_thread<SRC><<<grid_for(nk, 128), 128, 0, st>>>(so, src, ord, nk, H, E, B0, stride, e->d_cnt);
+		}
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
+		e->stats.n_launches += 1;
+		++used;
+	}
+	for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
+	e->stats.ms_k_sw += e->toc();
 }
 
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)
@@ -659,50 +777,16 @@ void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::v
 	out.resize(jobs.size());
 	if (jobs.empty()) return;
 	e->zero_counters();
-	const int64_t sub = 1 << 18;
-	for (int64_t j0 = 0; j0 < (int64_t)jobs.size(); j0 += sub) {
-		int64_t n = std::min<int64_t>(sub, (int64_t)jobs.size() - j0);
-		int max_q = 0, max_t = 0;
-		for (int64_t i = 0; i < n; ++i) { max_q = std::max(max_q, jobs[j0 + i].q_len); max_t = std::max(max_t, jobs[j0 + i].tlen); }
-		SwJob *dj = e->b_jobs.as<SwJob>(n);
-		SwRes *dr = e->b_res.as<SwRes>(n);
-		int64_t stride = (n + 31) & ~31ll;
-		uint16_t *H = e->b_h.as<uint16_t>((size_t)stride * (max_q + 16));
-		uint16_t *E = e->b_e.as<uint16_t>((size_t)stride * (max_q + 16));
-		uint64_t *B = e->b_b.as<uint64_t>((size_t)stride * (max_t / 2 + 2));
-		e->h2d(dj, jobs.data() + j0, sizeof(SwJob) * n);
-		e->tic();
-		k_sw_jobs<<<grid_for(n, 128), 128, 0, e->stream>>>(so, e->fm.pac, e->fm.l_pac, n, dj, (const int64_t *)e->d_off.p,
-			(const uint8_t *)e->d_codes.p, H, E, B, stride, dr, e->d_cnt);
-		CK(cudaGetLastError());
-		e->stats.n_launches += 1;
-		e->stats.ms_k_sw += e->toc();
-		e->d2h(out.data() + j0, dr, sizeof(SwRes) * n);
-		e->sync();
-	}
+	const int64_t n = (int64_t)jobs.size();
+	SwJob *dj = e->b_jobs.as<SwJob>(n);
+	SwRes *dr = e->b_res.as<SwRes>(n);
+	e->h2d(dj, jobs.data(), sizeof(SwJob) * n);
+	SwSrcPipeline src = { dj, (const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, e->fm.pac, e->fm.l_pac, dr };
+	run_sw(e, so, src, n, [&](int64_t i, int &ql, int &tl, int &xt) { ql = jobs[i].q_len; tl = jobs[i].tlen; xt = jobs[i].xtra; });
+	e->d2h(out.data(), dr, sizeof(SwRes) * n);
 	Counters c = e->read_counters();
 	e->stats.sw_cells += (int64_t)c.sw_cells;
-	e->stats.n_sw_jobs += (int64_t)jobs.size();
-}
-
-__global__ void __launch_bounds__(128) k_sw_bytes(SwOpt so, int64_t n_jobs, b200_align_job_t *jobs, const uint8_t *__restrict__ query,
-                                                  const uint8_t *__restrict__ target, uint16_t *H, uint16_t *E, uint64_t *B,
-                                                  int64_t stride, Counters *cnt)
-{
-	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t cells = 0;
-	if (t < n_jobs) {
-		b200_align_job_t j = jobs[t];
-		Row16 h = { H + t, stride }, ee = { E + t, stride };
-		List64 bl = { B + t, stride };
-		SQFwd qa = { query + j.q_off };
-		STBytes ta = { target + j.t_off };
-		SwRes r;
-		sw_align(j.qlen, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &r, &cells);
-		j.r.score = r.score; j.r.te = r.te; j.r.qe = r.qe; j.r.score2 = r.score2; j.r.te2 = r.te2; j.r.tb = r.tb; j.r.qb = r.qb;
-		jobs[t] = j;
-	}
-	warp_add(&cnt->sw_cells, cells);
+	e->stats.n_sw_jobs += n;
 }
 
 void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t *jobs,
@@ -710,23 +794,14 @@ void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t
 {
 	CK(cudaSetDevice(e->device));
 	if (n_jobs <= 0) return;
-	int max_q = 0, max_t = 0;
-	for (int64_t i = 0; i < n_jobs; ++i) { max_q = std::max(max_q, jobs[i].qlen); max_t = std::max(max_t, jobs[i].tlen); }
 	e->zero_counters();
 	b200_align_job_t *dj = e->b_jobs.as<b200_align_job_t>(n_jobs);
 	uint8_t *dq = e->b_q.as<uint8_t>(qbytes + 16), *dt = e->b_t.as<uint8_t>(tbytes + 16);
 	e->h2d(dj, jobs, sizeof(b200_align_job_t) * n_jobs);
 	e->h2d(dq, query, qbytes);
 	e->h2d(dt, target, tbytes);
-	int64_t stride = (n_jobs + 31) & ~31ll;
-	uint16_t *H = e->b_h.as<uint16_t>((size_t)stride * (max_q + 16));
-	uint16_t *E = e->b_e.as<uint16_t>((size_t)stride * (max_q + 16));
-	uint64_t *B = e->b_b.as<uint64_t>((size_t)stride * (max_t / 2 + 2));
-	e->tic();
-	k_sw_bytes<<<grid_for(n_jobs, 128), 128, 0, e->stream>>>(so, n_jobs, dj, dq, dt, H, E, B, stride, e->d_cnt);
-	CK(cudaGetLastError());
-	e->stats.n_launches += 1;
-	e->stats.ms_k_sw += e->toc();
+	SwSrcBytes src = { dj, dq, dt };
+	run_sw(e, so, src, n_jobs, [&](int64_t i, int &ql, int &tl, int &xt) { ql = jobs[i].qlen; tl = jobs[i].tlen; xt = jobs[i].xtra; });
 	e->d2h(jobs, dj, sizeof(b200_align_job_t) * n_jobs);
 	Counters c = e->read_counters();
 	e->stats.sw_cells += (int64_t)c.sw_cells;

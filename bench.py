@@ -43,7 +43,8 @@ def parse_args():
     p.add_argument("--pairs", type=int, default=1_000_000, help="simulated pairs per rank")
     p.add_argument("--read-len", type=int, default=150)
     p.add_argument("-K", type=int, default=100_000_000, dest="K")
-    p.add_argument("--ref-sample-pairs", type=int, default=60_000, help="pairs per step of the CPU reference arm")
+    p.add_argument("--ref-sample-pairs", type=int, default=333_334, help="pairs per step of the CPU reference arm (one chunk)")
+    p.add_argument("--cpu-baseline-pairs", type=int, default=1_000_000, help="pairs of the cpu_baseline sample of the b200 arm")
     p.add_argument("--no-cpu-baseline", action="store_true")
     return p.parse_args()
 
@@ -159,7 +160,7 @@ def reference_arm(args, prefix):
     cores = os.cpu_count() or 1
     f1, f2 = ensure_reads(args, 0, args.pairs)
     rb = record_bytes(f1)
-    n = args.ref_sample_pairs
+    n = min(args.ref_sample_pairs, args.pairs)
     d = workload_dir(args)
     total_pairs, total_s = 0, 0.0
     for step in range(args.warmup + args.steps):
@@ -252,8 +253,16 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def chunk_bytes(c):
+        """private, writable copy of the chunk's fastq bytes (what the MPI host gets from its file read); the parse is in place"""
         b, e = chunks[c % len(chunks)]
-        return fq1[b * rb1:e * rb1], fq2[b * rb2:e * rb2], e - b
+        out = []
+        for fq, rb in ((fq1, rb1), (fq2, rb2)):
+            nb = (e - b) * rb
+            a = np.empty(nb + 1, dtype=np.uint8)
+            a[:nb] = np.frombuffer(fq, dtype=np.uint8, count=nb, offset=b * rb)
+            a[nb] = 0
+            out.append((a, nb))
+        return out[0], out[1], e - b
 
     STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
@@ -262,8 +271,8 @@ def main():
     def e2e_step(c):
         """raw fastq bytes -> SAM bytes, everything inside"""
         a1, a2, n = chunk_bytes(c)
-        k1, p1, m1 = al.parse(a1)
-        k2, p2, m2 = al.parse(a2)
+        k1, p1, m1 = al.parse_array(*a1)
+        k2, p2, m2 = al.parse_array(*a2)
         sam = C.c_void_p()
         sam_len = C.c_int64()
         lib.b200_align_chunk(al.opt, al.idx, 0, m1, p1, p2, C.byref(sam), C.byref(sam_len))
@@ -274,8 +283,8 @@ def main():
     def resident_step(c, ev0, ev1):
         """reads parsed, encoded and resident in HBM before the timed region; SAM left in seqs[i].sam"""
         a1, a2, n = chunk_bytes(c)
-        k1, p1, m1 = al.parse(a1)
-        k2, p2, m2 = al.parse(a2)
+        k1, p1, m1 = al.parse_array(*a1)
+        k2, p2, m2 = al.parse_array(*a2)
         seqs = lib.b200_chunk_seqs(m1, p1, p2)
         lib.b200_stage_reads(al.opt, al.idx, 2 * m1, seqs)
         flush_buf.add_(1)
@@ -387,14 +396,14 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
         cores = os.cpu_count() or 1
-        n = min(args.ref_sample_pairs, args.pairs)
+        n = min(args.cpu_baseline_pairs, args.pairs)
         d = workload_dir(args)
         s1, s2 = os.path.join(d, "cpusample_1.fq"), os.path.join(d, "cpusample_2.fq")
         slice_fastq(f1, s1, 0, n, rb1)
         slice_fastq(f2, s2, 0, n, rb2)
         reads, sec = run_ref_driver(prefix, s1, s2, args.K, cores)
         line["cpu_baseline"] = {"value": (reads // 2) / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",
-                                "sample": "first %d pairs of the workload, one mem_process_seqs call, -t %d (%.2f s)" % (n, cores, sec)}
+                                "sample": "first %d pairs of the workload, chunked at -K %d, -t %d (%.2f s in mem_process_seqs)" % (n, args.K, cores, sec)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

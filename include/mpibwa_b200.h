@@ -277,6 +277,7 @@ int b200_bwt_sa_batch(int64_t n, const bwtint_t *k, bwtint_t *sa);
  * concatenate seqs[i].sam" (reference src/mainParallel.c:1271-1314, 103-127).  Buffers come from malloc();
  * release them with b200_free(). */
 int64_t b200_fastq_parse(char *buf, int64_t len, bseq1_t **seqs);
+void    b200_set_host_threads(int n);   /* threads used by the parse / concatenation helpers (0 = all hardware threads) */
 int64_t b200_plan_chunks(int64_t n, const bseq1_t *s1, const bseq1_t *s2, int64_t K, int trimmed, int64_t **ends);
 bseq1_t *b200_chunk_seqs(int64_t n, const bseq1_t *s1, const bseq1_t *s2);      /* interleaved mates 2i, 2i+1 */
 int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam);            /* concatenates and frees seqs[i].sam */

@@ -124,6 +124,7 @@ _PROTOTYPES = {
                                           C.POINTER(C.POINTER(bwtintv_t)), C.POINTER(C.POINTER(C.c_int64))]),
     "b200_bwt_sa_batch": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p]),
     "b200_fastq_parse": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(C.POINTER(bseq1_t))]),
+    "b200_set_host_threads": (None, [C.c_int]),
     "b200_plan_chunks": (C.c_int64, [C.c_int64, C.POINTER(bseq1_t), C.POINTER(bseq1_t), C.c_int64, C.c_int,
                                      C.POINTER(C.POINTER(C.c_int64))]),
     "b200_chunk_seqs": (C.POINTER(bseq1_t), [C.c_int64, C.POINTER(bseq1_t), C.POINTER(bseq1_t)]),
@@ -194,6 +195,12 @@ class Aligner:
         seqs = C.POINTER(bseq1_t)()
         n = self.lib.b200_fastq_parse(C.cast(buf, C.c_void_p), len(fastq_bytes), C.byref(seqs))
         return buf, seqs, n
+
+    def parse_array(self, arr, n_bytes):
+        """Same on a caller-owned writable uint8 numpy array (one byte of slack after n_bytes): no extra copy."""
+        seqs = C.POINTER(bseq1_t)()
+        n = self.lib.b200_fastq_parse(C.c_void_p(arr.ctypes.data), n_bytes, C.byref(seqs))
+        return arr, seqs, n
 
     def plan(self, n, s1, s2, K, trimmed=False):
         ends = C.POINTER(C.c_int64)()

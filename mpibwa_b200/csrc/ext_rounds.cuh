@@ -60,17 +60,12 @@ __device__ __forceinline__ void ext_emit_job(ExtJob *jb, const uint8_t *, int64_
 	jb->qlen = qlen; jb->tlen = tlen; jb->h0 = h0; jb->prev = prev; jb->bonus = bonus;
 }
 
-__global__ void __launch_bounds__(128) k_ext_advance(ExtOpt eo, int64_t l_pac, int n_active, const int32_t *__restrict__ active,
-                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ chain_off,
-                                                     const DChain *__restrict__ chains, const DSeed *__restrict__ seeds, int32_t *srt,
-                                                     ExtState *state, ExtJob *jobs, DReg *regs, int32_t *n_regs,
-                                                     int32_t *next_active, uint32_t *next_key, int32_t *counters /* [0]=n_next, [1..]=class hist */)
+// Advances the chain2aln walk of read r until it needs a DP (returns true; the job is in *jb) or is finished.
+__device__ __forceinline__ bool ext_advance_read(const ExtOpt &eo, int64_t l_pac, int r, const int64_t *__restrict__ off,
+                                                 const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains,
+                                                 const DSeed *__restrict__ seeds, int32_t *srt, ExtState &st, ExtJob *jb, DReg *regs,
+                                                 int32_t *n_regs)
 {
-	int t = blockIdx.x * blockDim.x + threadIdx.x;
-	if (t >= n_active) return;
-	const int r = active[t];
-	ExtState st = state[r];
-	ExtJob *jb = &jobs[r];
 	const int c0 = chain_off[r], nc = chain_off[r + 1] - c0;
 	const int l_query = (int)(off[r + 1] - off[r]);
 	const int64_t qbase = off[r];
@@ -143,6 +138,21 @@ __global__ void __launch_bounds__(128) k_ext_advance(ExtOpt eo, int64_t l_pac, i
 			st.phase = 0;
 		}
 	}
+	return emitted;
+}
+
+__global__ void __launch_bounds__(128) k_ext_advance(ExtOpt eo, int64_t l_pac, int n_active, const int32_t *__restrict__ active,
+                                                     const int64_t *__restrict__ off, const int32_t *__restrict__ chain_off,
+                                                     const DChain *__restrict__ chains, const DSeed *__restrict__ seeds, int32_t *srt,
+                                                     ExtState *state, ExtJob *jobs, DReg *regs, int32_t *n_regs,
+                                                     int32_t *next_active, uint32_t *next_key, int32_t *counters /* [0]=n_next, [1..]=class hist */)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_active) return;
+	const int r = active[t];
+	ExtState st = state[r];
+	ExtJob *jb = &jobs[r];
+	const bool emitted = ext_advance_read(eo, l_pac, r, off, chain_off, chains, seeds, srt, st, jb, regs, n_regs);
 	state[r] = st;
 	if (emitted) {
 		int pos = atomicAdd(&counters[0], 1);
@@ -353,6 +363,220 @@ __global__ void __launch_bounds__(128) k_ext_dp_big(ExtOpt eo, const uint8_t *__
 	long long c = cells;
 	for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); calls += __shfl_down_sync(0xffffffffu, calls, o); }
 	if ((threadIdx.x & 31) == 0) { if (c) atomicAdd(cells_out, (unsigned long long)c); if (calls) atomicAdd(calls_out, (unsigned long long)calls); }
+}
+
+// ---------------------------------------------------------------- warp-cooperative DP (latency path)
+//
+// One WARP per ksw_extend2 call: the 32 lanes take 32 adjacent columns of the band at a time.  Within a row the only
+// left-to-right dependency is F, and because BWA opens gaps from M (src/ksw.c:444-446: t = M - oe_ins) F is a pure
+// max-plus prefix over g_j = max(M_j - oe_ins, 0):  F_j = max_{k<j} (g_k - (j-1-k) e_ins)  - one 5-step shuffle scan of
+// a_j = g_j + j e_ins per 32 columns.  H(i,j-1) reaches column j by one shuffle, the row maximum (ties to the larger j)
+// by one max-reduction of (h << 32 | j), and the band shrink (first / last non-zero entry of the finished row,
+// src/ksw.c:466-469) by ballots.  H and E rows live in shared memory as int32 (no 15-bit limit).  Per row this costs
+// ~100-150 issue slots per warp instead of ~30 per CELL per lane in k_ext_dp, i.e. ~8x less latency per job at ~3x the
+// instruction count: it is used where a round has too few jobs to fill the chip (the long-query classes and the tail of
+// the round sequence), where the latency of the longest job, not throughput, sets the time.
+struct ExtWarpScratch { int32_t *H, *E; uint8_t *Q; };
+
+__device__ __forceinline__ ExtWarpScratch ext_warp_scratch(uint32_t *smem, int wib, int qcap)
+{
+	const int words = 2 * (qcap + 2) + ((qcap + 4) >> 2);
+	ExtWarpScratch s;
+	s.H = (int32_t *)(smem + (size_t)wib * words);
+	s.E = s.H + (qcap + 2);
+	s.Q = (uint8_t *)(s.E + (qcap + 2));
+	return s;
+}
+static inline size_t ext_warp_smem_bytes(int warps, int qcap) { return (size_t)warps * (2 * (qcap + 2) + ((qcap + 4) >> 2)) * 4; }
+
+// runs the job (both band attempts of the caller, src/bwamem.c:723-734,751-762) and leaves the results in jb
+__device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo, const uint32_t *__restrict__ sc_hi,
+                            const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes, ExtJob &jb, const ExtWarpScratch &S,
+                            long long &cells, int &calls)
+{
+	const unsigned FULL = 0xffffffffu;
+	const int lane = threadIdx.x & 31;
+	const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0;
+	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
+	for (int j = lane; j < qlen; j += 32) S.Q[j] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+	int prev_score = jb.prev, aw = eo.w, score = 0;
+	int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		aw = eo.w << attempt;
+		__syncwarp();
+		for (int j = lane; j <= qlen; j += 32) {           // row -1 (src/ksw.c:395-397)
+			int v = j == 0 ? h0 : h0 - oe_ins - (j - 1) * e_ins;
+			S.H[j] = v > 0 ? v : 0; S.E[j] = 0;
+		}
+		int w = aw;                                        // band clamp (src/ksw.c:399-407)
+		{
+			int max_ins = (int)((double)(qlen * eo.max_sc + jb.bonus - eo.o_ins) / eo.e_ins + 1.);
+			max_ins = max_ins > 1 ? max_ins : 1;
+			w = w < max_ins ? w : max_ins;
+			int max_del = (int)((double)(qlen * eo.max_sc + jb.bonus - eo.o_del) / eo.e_del + 1.);
+			max_del = max_del > 1 ? max_del : 1;
+			w = w < max_del ? w : max_del;
+		}
+		__syncwarp();
+		max = h0; max_i = -1; max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+		int beg = 0, end = qlen;
+		int64_t f = jb.f0;
+		int tb_next = tlen > 0 ? pac_fbase(pac, f) : 0;
+		for (int i = 0; i < tlen; ++i) {
+			int tb = tb_next;
+			f += jb.fstep;
+			if (i + 1 < tlen) tb_next = pac_fbase(pac, f);
+			if (jb.comp) tb = 3 - tb;
+			const uint32_t lo = sc_lo[tb], hi = sc_hi[tb];
+			if (beg < i - w) beg = i - w;
+			if (end > i + w + 1) end = i + w + 1;
+			if (end > qlen) end = qlen;
+			int h1 = 0;
+			if (beg == 0) { h1 = h0 - (eo.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
+			int fcar = 0, hcar = h1;                       // F entering / H left of the first column of the chunk
+			long long best = -1;
+			int first_nz = 0x7fffffff, last_nz = -1, hlast = h1;
+			for (int cb = beg; cb < end; cb += 32) {
+				const int j = cb + lane;
+				const bool act = j < end;
+				const int hd = act ? S.H[j] : 0;
+				int e = act ? S.E[j] : 0;
+				const int q = act ? S.Q[j] : 4;
+				int M = hd + prmt_score(lo, hi, (uint32_t)q * 0x1111u + 0x8880u);
+				M = hd ? M : 0;
+				// F by max-plus scan; the carry enters as a virtual column cb-1
+				int a = act ? ::max(M - oe_ins, 0) + j * e_ins : (int)0x80000000;
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(FULL, a, o); if (lane >= o) a = ::max(a, v); }
+				const int acar = fcar + (cb - 1) * e_ins;
+				int x = __shfl_up_sync(FULL, a, 1);
+				x = lane == 0 ? acar : ::max(x, acar);
+				const int fj = x - (j - 1) * e_ins;
+				const int h = ::max(::max(M, e), fj);
+				e = ::max(::max(e - e_del, M - oe_del), 0);
+				int hl = __shfl_up_sync(FULL, h, 1);
+				if (lane == 0) hl = hcar;
+				if (act) {
+					S.H[j] = hl; S.E[j] = e;
+					const long long key = (long long)h << 32 | (unsigned)j;
+					best = key > best ? key : best;
+				}
+				const unsigned nz = __ballot_sync(FULL, act && (hl | e) != 0);
+				if (nz) {
+					if (first_nz == 0x7fffffff) first_nz = cb + __ffs(nz) - 1;
+					last_nz = cb + 31 - __clz(nz);
+				}
+				const int nlast = ::min(end - cb, 32) - 1;    // lane of the last active column of this chunk
+				hlast = __shfl_sync(FULL, h, nlast);
+				hcar = hlast;
+				fcar = ::max(__shfl_sync(FULL, a, 31), acar) - (cb + 31) * e_ins;   // only used when the chunk is full
+			}
+			if (end > beg) cells += lane == 0 ? end - beg : 0;
+			if (lane == 0) { S.H[end] = hlast; S.E[end] = 0; }
+			if (hlast != 0) last_nz = end;
+			if ((beg < end ? end : beg) == qlen) {
+				max_ie = gscore > hlast ? max_ie : i;
+				gscore = gscore > hlast ? gscore : hlast;
+			}
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { const long long v = __shfl_xor_sync(FULL, best, o); best = v > best ? v : best; }
+			const int m = best < 0 ? 0 : (int)(best >> 32), mj = best < 0 ? -1 : (int)(uint32_t)best;
+			if (m == 0) break;
+			if (m > max) {
+				max = m; max_i = i; max_j = mj;
+				int d = mj - i; d = d < 0 ? -d : d;
+				max_off = max_off > d ? max_off : d;
+			} else if (eo.zdrop > 0) {
+				if (i - max_i > mj - max_j) { if (max - m - ((i - max_i) - (mj - max_j)) * e_del > eo.zdrop) break; }
+				else { if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > eo.zdrop) break; }
+			}
+			// band for the next row: first / last non-zero entry of the finished row (src/ksw.c:466-469)
+			const int nbeg = first_nz != 0x7fffffff ? first_nz : end;
+			const int jl = last_nz >= nbeg ? last_nz : nbeg - 1;
+			beg = nbeg;
+			end = jl + 2 < qlen ? jl + 2 : qlen;
+			__syncwarp();
+		}
+		++calls;
+		score = max;
+		if (attempt == 0 && !(score == prev_score || max_off < (aw >> 1) + (aw >> 2))) { prev_score = score; continue; }
+		break;
+	}
+	jb.score = score; jb.qle = max_j + 1; jb.tle = max_i + 1; jb.gtle = max_ie + 1; jb.gscore = gscore; jb.aw = aw;
+}
+
+__device__ __forceinline__ void ext_fill_score_rows(const ExtOpt &eo, uint32_t *sc_lo, uint32_t *sc_hi)
+{
+	if (threadIdx.x < 4) {
+		const int8_t *m = eo.mat + threadIdx.x * 5;
+		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
+		sc_hi[threadIdx.x] = (uint32_t)(uint8_t)m[4];
+	}
+}
+
+// one warp per job of a round
+__global__ void __launch_bounds__(128) k_ext_dp_warp(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
+                                                     ExtJob *jobs, const int32_t *__restrict__ order, int n, int qcap,
+                                                     unsigned long long *cells_out, unsigned long long *calls_out)
+{
+	extern __shared__ uint32_t smem[];
+	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	ext_fill_score_rows(eo, sc_lo, sc_hi);
+	__syncthreads();
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wid = blockIdx.x * (blockDim.x >> 5) + wib;
+	if (wid >= n) return;
+	ExtJob *jp = &jobs[order[wid]];
+	ExtJob jb = *jp;
+	long long cells = 0;
+	int calls = 0;
+	ext_dp_warp(eo, sc_lo, sc_hi, pac, codes, jb, ext_warp_scratch(smem, wib, qcap), cells, calls);
+	if (lane == 0) {
+		jp->score = jb.score; jp->qle = jb.qle; jp->tle = jb.tle; jp->gtle = jb.gtle; jp->gscore = jb.gscore; jp->aw = jb.aw;
+		if (cells) atomicAdd(cells_out, (unsigned long long)cells);
+		atomicAdd(calls_out, (unsigned long long)calls);
+	}
+}
+
+// Tail of the round sequence: one warp per read that still has work walks the rest of its chains on its own -
+// lane 0 runs the chain2aln state machine, the warp runs every DP it asks for - so the few reads with many chains
+// no longer cost a launch + sort + host round trip per extension.
+__global__ void __launch_bounds__(128) k_ext_tail(ExtOpt eo, int64_t l_pac, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
+                                                  int n_active, const int32_t *__restrict__ active, const int64_t *__restrict__ off,
+                                                  const int32_t *__restrict__ chain_off, const DChain *__restrict__ chains,
+                                                  const DSeed *__restrict__ seeds, int32_t *srt, ExtState *state, ExtJob *jobs, DReg *regs,
+                                                  int32_t *n_regs, int qcap, unsigned long long *cells_out, unsigned long long *calls_out)
+{
+	extern __shared__ uint32_t smem[];
+	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	ext_fill_score_rows(eo, sc_lo, sc_hi);
+	__syncthreads();
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int wid = blockIdx.x * (blockDim.x >> 5) + wib;
+	if (wid >= n_active) return;
+	const int r = active[wid];
+	const ExtWarpScratch S = ext_warp_scratch(smem, wib, qcap);
+	ExtJob *jp = &jobs[r];
+	long long cells = 0;
+	int calls = 0;
+	ExtState st;
+	if (lane == 0) st = state[r];
+	for (;;) {
+		int emitted = 0;
+		if (lane == 0) emitted = ext_advance_read(eo, l_pac, r, off, chain_off, chains, seeds, srt, st, jp, regs, n_regs) ? 1 : 0;
+		emitted = __shfl_sync(0xffffffffu, emitted, 0);
+		if (!emitted) break;
+		__syncwarp();
+		ExtJob jb = *jp;                                   // written by lane 0 just above
+		ext_dp_warp(eo, sc_lo, sc_hi, pac, codes, jb, S, cells, calls);
+		if (lane == 0) { jp->score = jb.score; jp->qle = jb.qle; jp->tle = jb.tle; jp->gtle = jb.gtle; jp->gscore = jb.gscore; jp->aw = jb.aw; }
+		__syncwarp();
+	}
+	if (lane == 0) {
+		state[r] = st;
+		if (cells) atomicAdd(cells_out, (unsigned long long)cells);
+		if (calls) atomicAdd(calls_out, (unsigned long long)calls);
+	}
 }
 
 } // namespace b200

@@ -11,36 +11,77 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <thread>
+#include <algorithm>
+
+// number of host threads used by the shim's own loops (parse, SAM concatenation); 0 = all hardware threads
+static int g_shim_threads = 0;
+static int shim_threads()
+{
+	int n = g_shim_threads > 0 ? g_shim_threads : (int)std::thread::hardware_concurrency();
+	return n > 0 ? n : 1;
+}
+
+template <class F>
+static void shim_parallel(int nt, F body)      // body(t) for t in [0, nt)
+{
+	std::vector<std::thread> pool;
+	for (int t = 1; t < nt; ++t) pool.emplace_back(body, t);
+	body(0);
+	for (auto &th : pool) th.join();
+}
 
 extern "C" {
 
+void b200_set_host_threads(int n) { g_shim_threads = n; }
+
+// Same result as the hosts' serial loop (4 lines per record, '\n' -> NUL, name cut at the first blank and stripped of a
+// trailing "/[0-9]"), done in two parallel sweeps: count the line ends per segment, then every segment fills the
+// records whose lines END inside it.
 int64_t b200_fastq_parse(char *buf, int64_t len, bseq1_t **out)
 {
-	size_t n = 0, m = 0, line = 0;
-	bseq1_t *s = nullptr;
-	char *p = buf, *q = buf, *e = buf + len;
-	while (q < e) {
-		if (*q != '\n') { ++q; continue; }
-		*q = 0;
-		switch (line & 3) {
-		case 0: {
-			if (n == m) { m = m ? m << 1 : 1024; s = (bseq1_t *)realloc(s, m * sizeof(bseq1_t)); }
-			memset(&s[n], 0, sizeof(bseq1_t));
-			s[n].name = p + 1;
-			char *t = p;
-			while (*t && !isspace((unsigned char)*t)) ++t;
-			if (t - 2 > s[n].name && *(t - 2) == '/' && isdigit((unsigned char)*(t - 1))) *(t - 2) = 0;
-			if (*t) *t = 0;
-			break;
+	const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(shim_threads(), len >> 20));
+	std::vector<int64_t> seg(nt + 1), first_line(nt + 1, 0);
+	for (int t = 0; t <= nt; ++t) seg[t] = len * t / nt;
+	shim_parallel(nt, [&](int t) {
+		int64_t c = 0;
+		const char *p = buf + seg[t], *e = buf + seg[t + 1];
+		while (p < e && (p = (const char *)memchr(p, '\n', (size_t)(e - p))) != nullptr) { ++c; ++p; }
+		first_line[t + 1] = c;
+	});
+	for (int t = 0; t < nt; ++t) first_line[t + 1] += first_line[t];
+	const int64_t n = first_line[nt] >> 2;          // an unfinished record at the end is dropped, as the serial loop does
+	bseq1_t *s = (bseq1_t *)malloc((size_t)(n + 1) * sizeof(bseq1_t));
+	shim_parallel(nt, [&](int t) {
+		int64_t line = first_line[t];
+		char *q = buf + seg[t], *e = buf + seg[t + 1];
+		char *p = q;                                  // start of the line that contains q: just after the previous line end
+		while (p > buf && p[-1] != '\n' && p[-1] != 0) --p;
+		while (q < e && (q = (char *)memchr(q, '\n', (size_t)(e - q))) != nullptr) {
+			const int64_t rec = line >> 2;
+			if (rec < n) {
+				*q = 0;
+				bseq1_t &r = s[rec];
+				switch (line & 3) {
+				case 0: {
+					r.id = 0; r.comment = nullptr; r.sam = nullptr;        // seq/l_seq/qual come from the other lines
+					r.name = p + 1;
+					char *z = p;
+					while (*z && !isspace((unsigned char)*z)) ++z;
+					if (z - 2 > r.name && *(z - 2) == '/' && isdigit((unsigned char)*(z - 1))) *(z - 2) = 0;
+					if (*z) *z = 0;
+					break;
+				}
+				case 1: r.seq = p; r.l_seq = (int)(q - p); break;
+				case 2: break;
+				default: r.qual = p; break;
+				}
+			}
+			p = ++q; ++line;
 		}
-		case 1: s[n].seq = p; s[n].l_seq = (int)(q - p); break;
-		case 2: break;
-		case 3: s[n].qual = p; ++n; break;
-		}
-		p = ++q; ++line;
-	}
+	});
 	*out = s;
-	return (int64_t)n;
+	return n;
 }
 
 int64_t b200_plan_chunks(int64_t n, const bseq1_t *s1, const bseq1_t *s2, int64_t K, int trimmed, int64_t **ends)
@@ -71,16 +112,26 @@ bseq1_t *b200_chunk_seqs(int64_t n, const bseq1_t *s1, const bseq1_t *s2)
 
 int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam)
 {
-	size_t sum = 0;
+	const int nt = (int)std::max<int64_t>(1, std::min<int64_t>(shim_threads(), total >> 12));
 	std::vector<size_t> len((size_t)total);
-	for (int64_t i = 0; i < total; ++i) { len[i] = seqs[i].sam ? strlen(seqs[i].sam) : 0; sum += len[i]; }
-	char *buf = sam ? (char *)malloc(sum + 1) : nullptr, *w = buf;
-	for (int64_t i = 0; i < total; ++i) {
-		if (buf) { memcpy(w, seqs[i].sam, len[i]); w += len[i]; }
-		free(seqs[i].sam);
-		seqs[i].sam = nullptr;
-	}
-	if (buf) { *w = 0; *sam = buf; }
+	std::vector<size_t> part(nt + 1, 0);
+	shim_parallel(nt, [&](int t) {
+		size_t sum = 0;
+		for (int64_t i = total * t / nt; i < total * (t + 1) / nt; ++i) { len[i] = seqs[i].sam ? strlen(seqs[i].sam) : 0; sum += len[i]; }
+		part[t + 1] = sum;
+	});
+	for (int t = 0; t < nt; ++t) part[t + 1] += part[t];
+	const size_t sum = part[nt];
+	char *buf = sam ? (char *)malloc(sum + 1) : nullptr;
+	shim_parallel(nt, [&](int t) {
+		char *w = buf ? buf + part[t] : nullptr;
+		for (int64_t i = total * t / nt; i < total * (t + 1) / nt; ++i) {
+			if (buf) { memcpy(w, seqs[i].sam, len[i]); w += len[i]; }
+			free(seqs[i].sam);
+			seqs[i].sam = nullptr;
+		}
+	});
+	if (buf) { buf[sum] = 0; *sam = buf; }
 	return (int64_t)sum;
 }
 

@@ -195,7 +195,7 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 	std::vector<int64_t> off(n + 1);
 	off[0] = 0;
 	for (int i = 0; i < n; ++i) off[i + 1] = off[i] + seqs[i].l_seq;
-	std::vector<uint8_t> codes(off[n] + 8);
+	uint8_t *codes = stage_read_buffer(eng, off[n] + 16);
 	parallel_for(nt, n, 4096, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
 			char *s = seqs[i].seq;
@@ -206,7 +206,7 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 			}
 		}
 	});
-	stage_upload_reads(eng, n, off.data(), codes.data());
+	stage_upload_reads(eng, n, off.data(), codes);
 	g_staged_key = (const void *)seqs; g_staged_n = n; g_staged_bases = off[n];
 }
 
@@ -228,22 +228,19 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	st.n_reads = n; st.n_bases = g_staged_bases;
 
 	// ---- seeding on the device
-	std::vector<int64_t> seed_off;
-	std::vector<SeedRec> seed_recs;
-	std::vector<int32_t> l_rep;
-	stage_seed(eng, make_seed_opt(opt), seed_off, seed_recs, l_rep);
+	SeedOut sd;
+	stage_seed(eng, make_seed_opt(opt), sd);
 	t1 = now_ms(); st.ms_seed = t1 - t0; t0 = t1;
-	st.n_seeds = (int64_t)seed_recs.size();
+	st.n_seeds = sd.n_seeds;
 
 	// ---- chaining + chain filtering on host threads
 	std::vector<std::vector<HChain>> chains(n);
 	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
-			build_chains(opt, bns, seqs[i].l_seq, seed_recs.data() + seed_off[i], seed_off[i + 1] - seed_off[i], l_rep[i], chains[i]);
+			build_chains(opt, bns, seqs[i].l_seq, sd.seeds + sd.seed_off[i], sd.seed_off[i + 1] - sd.seed_off[i], sd.l_rep[i], chains[i]);
 			filter_chains(opt, chains[i]);
 		}
 	});
-	seed_recs.clear(); seed_recs.shrink_to_fit();
 	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] build+filter %.1f ms\n", now_ms() - t0);
 
 	// ---- mem_flt_chained_seeds (reference src/bwamem.c:571-615): only reads of >= ~730 bp get here
@@ -299,40 +296,50 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		}
 	}
 
-	// ---- flatten chains for the extension stage
+	// ---- flatten chains for the extension stage (two sweeps: sizes, then a parallel fill at the prefix offsets)
 	std::vector<int32_t> chain_off(n + 1);
 	std::vector<DChain> dchains;
 	std::vector<DSeed> dseeds;
 	std::vector<int32_t> srt;
 	{
+		std::vector<int64_t> seed_at(n + 1);
 		int64_t nc = 0, ns = 0;
-		for (int i = 0; i < n; ++i) { nc += chains[i].size(); for (auto &c : chains[i]) ns += c.seeds.size(); }
-		dchains.reserve(nc); dseeds.reserve(ns); srt.reserve(ns);
-		std::vector<uint64_t> key;
 		for (int i = 0; i < n; ++i) {
-			chain_off[i] = (int32_t)dchains.size();
-			for (auto &c : chains[i]) {
-				DChain d;
-				d.seed_beg = (int32_t)dseeds.size(); d.n_seeds = (int32_t)c.seeds.size();
-				d.rid = c.rid; d.frac_rep = c.frac_rep; d.rmax0 = d.rmax1 = 0;
-				if (!c.seeds.empty()) {
-					int64_t rmax[2];
-					chain_window(opt, bns, seqs[i].l_seq, c, rmax);
-					d.rmax0 = rmax[0]; d.rmax1 = rmax[1];
-				}
-				key.resize(c.seeds.size());
-				for (size_t k = 0; k < c.seeds.size(); ++k) {
-					const HSeed &s = c.seeds[k];
-					dseeds.push_back({s.rbeg, s.qbeg, s.len, s.score, 0});
-					key[k] = (uint64_t)s.score << 32 | k;
-				}
-				std::sort(key.begin(), key.end());
-				for (size_t k = 0; k < key.size(); ++k) srt.push_back((int32_t)(uint32_t)key[k]);
-				dchains.push_back(d);
-			}
+			chain_off[i] = (int32_t)nc; seed_at[i] = ns;
+			nc += (int64_t)chains[i].size();
+			for (auto &c : chains[i]) ns += (int64_t)c.seeds.size();
 		}
-		chain_off[n] = (int32_t)dchains.size();
-		st.n_chains = (int64_t)dchains.size();
+		chain_off[n] = (int32_t)nc; seed_at[n] = ns;
+		if (nc > 0x7fffffffLL || ns > 0x7fffffffLL) { fprintf(stderr, "[mpibwa_b200] too many chains/seeds in one chunk\n"); abort(); }
+		dchains.resize(nc); dseeds.resize(ns); srt.resize(ns);
+		parallel_for(nt, n, 2048, [&](int, int64_t b, int64_t e) {
+			std::vector<uint64_t> key;
+			for (int64_t i = b; i < e; ++i) {
+				int64_t ci = chain_off[i], si = seed_at[i];
+				for (auto &c : chains[i]) {
+					DChain d;
+					d.seed_beg = (int32_t)si; d.n_seeds = (int32_t)c.seeds.size();
+					d.rid = c.rid; d.frac_rep = c.frac_rep; d.rmax0 = d.rmax1 = 0;
+					if (!c.seeds.empty()) {
+						int64_t rmax[2];
+						chain_window(opt, bns, seqs[i].l_seq, c, rmax);
+						d.rmax0 = rmax[0]; d.rmax1 = rmax[1];
+					}
+					key.resize(c.seeds.size());
+					for (size_t k = 0; k < c.seeds.size(); ++k) {
+						const HSeed &s = c.seeds[k];
+						dseeds[si + k] = {s.rbeg, s.qbeg, s.len, s.score, 0};
+						key[k] = (uint64_t)s.score << 32 | k;
+					}
+					std::sort(key.begin(), key.end());
+					for (size_t k = 0; k < key.size(); ++k) srt[si + k] = (int32_t)(uint32_t)key[k];
+					dchains[ci++] = d;
+					si += (int64_t)c.seeds.size();
+				}
+				std::vector<HChain>().swap(chains[i]);      // release in parallel
+			}
+		});
+		st.n_chains = nc;
 	}
 	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] +flatten %.1f ms\n", now_ms() - t0);
 	chains.clear(); chains.shrink_to_fit();

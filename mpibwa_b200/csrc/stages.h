@@ -14,7 +14,10 @@
 
 namespace b200 {
 
-struct SeedRec { int64_t rbeg; int32_t qbeg, len; int32_t rid; int32_t pad; };
+struct SeedRec { int64_t rbeg; uint16_t qbeg, len; int32_t rid; };   // 16 bytes; reads are shorter than 65536 bases
+
+// result of stage_seed: arrays owned by the engine (page-locked on the CUDA engine), valid until the next stage_seed call
+struct SeedOut { const int64_t *seed_off; const SeedRec *seeds; const int32_t *l_rep; int64_t n_seeds; };
 
 struct SwJob {
 	int64_t rb;             // first reference position of the target window (forward+reverse coordinate)
@@ -40,13 +43,14 @@ Stats  &engine_stats(Engine *e);
 const char *engine_kind();                     // "cuda" or "hostemu"
 int     engine_device_count();
 
+// host staging area (page-locked on the CUDA engine) in which the caller may assemble the encoded reads before the upload
+uint8_t *stage_read_buffer(Engine *e, int64_t bytes);
 // upload the encoded reads of the batch (codes 0-4, read r at codes[off[r] .. off[r+1]))
 void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes);
 
 // seeding + SA look-up: per read the seed list in mem_chain() order (interval order x SA order), with the
 // contig id already resolved (rid < 0 = bridging, to be dropped by the caller), and l_rep per read.
-void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds,
-                std::vector<int32_t> &l_rep);
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out);
 
 // extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r come back compacted
 // as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them.

@@ -47,6 +47,23 @@ struct DevBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// growable page-locked host buffer (results that the host threads read right after a D2H copy)
+struct PinBuf {
+	void *p = nullptr; size_t cap = 0;
+	void *need(size_t bytes, size_t keep = 0)
+	{
+		if (bytes > cap) {
+			size_t n = bytes + (bytes >> 2) + 4096;
+			void *q = nullptr;
+			CK(cudaHostAlloc(&q, n, cudaHostAllocDefault));
+			if (p) { if (keep) memcpy(q, p, keep); CK(cudaFreeHost(p)); }
+			p = q; cap = n;
+		}
+		return p;
+	}
+	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct Counters { unsigned long long occ_blocks, sa_steps, ext_cells, ext_calls, sw_cells; };
 
 class Engine {
@@ -67,6 +84,7 @@ public:
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
 	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
+	PinBuf h_seeds, h_seed_off, h_lrep, h_codes;
 	std::vector<cudaEvent_t> ev_pool;
 	static const int N_SIDE = 8;
 	cudaStream_t side[N_SIDE];
@@ -184,6 +202,7 @@ void engine_destroy(Engine *e)
 		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
 		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
 	for (DevBuf *b : bufs) b->release();
+	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release();
 	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);
@@ -251,20 +270,19 @@ __global__ void __launch_bounds__(256) k_sa_seeds(FmView fm, SeedOpt so, int64_t
 		int steps;
 		SeedRec s;
 		s.rbeg = (int64_t)fm_sa(fm, p.x0 + (uint64_t)c * step, &steps);
-		s.qbeg = (int32_t)(p.info >> 32);
-		s.len = (int32_t)(uint32_t)p.info - s.qbeg;
+		s.qbeg = (uint16_t)(p.info >> 32);
+		s.len = (uint16_t)((uint32_t)p.info - (uint32_t)(p.info >> 32));
 		s.rid = fm_intv2rid(fm, s.rbeg, s.rbeg + s.len);
-		s.pad = 0;
 		seeds[t] = s;
 		steps_total = steps;
 	}
 	warp_add(&cnt->sa_steps, steps_total);
 }
 
-__global__ void k_gather_seed_off(int n_reads, const int64_t *__restrict__ ioff, const int64_t *__restrict__ soff, int64_t *seed_off)
+__global__ void k_gather_seed_off(int n_reads, const int64_t *__restrict__ ioff, const int64_t *__restrict__ soff, int64_t *seed_off, int64_t base)
 {
 	int r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r <= n_reads) seed_off[r] = soff[ioff[r]];
+	if (r <= n_reads) seed_off[r] = base + soff[ioff[r]];
 }
 
 __global__ void k_sa_plain(FmView fm, int64_t n, const uint64_t *__restrict__ k, uint64_t *sa)
@@ -297,6 +315,12 @@ static void exclusive_scan(Engine *e, const int32_t *in, int64_t *out, int64_t n
 	void *d = e->b_cub.need(tmp);
 	CK(cub::DeviceScan::ExclusiveSum(d, tmp, wide, out, n, e->stream));
 	e->stats.n_launches += 2;
+}
+
+uint8_t *stage_read_buffer(Engine *e, int64_t bytes)
+{
+	CK(cudaSetDevice(e->device));
+	return (uint8_t *)e->h_codes.need((size_t)bytes);
 }
 
 void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes)
@@ -393,13 +417,15 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 	e->stats.n_intv += (int64_t)intv.size();
 }
 
-void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds, std::vector<int32_t> &l_rep)
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out)
 {
 	CK(cudaSetDevice(e->device));
 	const int n_reads = e->n_reads;
-	seed_off.assign(n_reads + 1, 0);
-	l_rep.assign(n_reads, 0);
-	seeds.clear();
+	if (e->max_len > 0xffff) die("reads of 65536 bases or more are not supported by the seeding stage");
+	int64_t *seed_off = (int64_t *)e->h_seed_off.need(sizeof(int64_t) * (n_reads + 1));
+	int32_t *l_rep = (int32_t *)e->h_lrep.need(sizeof(int32_t) * (n_reads + 1));
+	seed_off[0] = 0;
+	int64_t n_seeds = 0;
 	e->zero_counters();
 	const int sub = seed_sub_batch(e->max_len);
 	double ms_smem = 0, ms_sa = 0;
@@ -423,18 +449,16 @@ void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, st
 			e->stats.n_launches += 1;
 		}
 		int64_t *d_seed_off = e->b_seedoff.as<int64_t>(n + 1);
-		k_gather_seed_off<<<grid_for(n + 1, 256), 256, 0, e->stream>>>(n, (const int64_t *)e->b_ioff.p, soff, d_seed_off);
+		k_gather_seed_off<<<grid_for(n + 1, 256), 256, 0, e->stream>>>(n, (const int64_t *)e->b_ioff.p, soff, d_seed_off, n_seeds);
 		CK(cudaGetLastError());
 		e->stats.n_launches += 1;
 		ms_sa += e->toc();
-		size_t base = seeds.size();
-		seeds.resize(base + n_slots);
-		std::vector<int64_t> so_h(n + 1);
-		e->d2h(seeds.data() + base, d_seeds, sizeof(SeedRec) * n_slots);
-		e->d2h(so_h.data(), d_seed_off, sizeof(int64_t) * (n + 1));
-		e->d2h(l_rep.data() + r0, e->b_lrep.p, sizeof(int32_t) * n);
+		SeedRec *seeds = (SeedRec *)e->h_seeds.need(sizeof(SeedRec) * (n_seeds + n_slots + 1), sizeof(SeedRec) * n_seeds);
+		e->d2h(seeds + n_seeds, d_seeds, sizeof(SeedRec) * n_slots);
+		e->d2h(seed_off + r0, d_seed_off, sizeof(int64_t) * (n + 1));
+		e->d2h(l_rep + r0, e->b_lrep.p, sizeof(int32_t) * n);
 		e->sync();
-		for (int i = 0; i <= n; ++i) seed_off[r0 + i] = (int64_t)base + so_h[i];
+		n_seeds += n_slots;
 		e->stats.fm_sa_lookups += n_slots;
 	}
 	Counters c = e->read_counters();
@@ -442,6 +466,7 @@ void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, st
 	e->stats.fm_sa_steps += (int64_t)c.sa_steps;
 	e->stats.ms_k_smem += ms_smem;
 	e->stats.ms_k_sa += ms_sa;
+	out.seed_off = seed_off; out.seeds = (const SeedRec *)e->h_seeds.p; out.l_rep = l_rep; out.n_seeds = n_seeds;
 }
 
 void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
@@ -498,11 +523,21 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	e->h2d(d_se, seeds.data(), sizeof(DSeed) * seeds.size());
 	e->h2d(d_srt, srt.data(), sizeof(int32_t) * srt.size());
 	static bool attr_set = false;
-	if (!attr_set) { CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024)); attr_set = true; }
+	if (!attr_set) {
+		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+		CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		CK(cudaFuncSetAttribute(k_ext_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		attr_set = true;
+	}
 	size_t sort_tmp = 0;
 	CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp, d_key, d_key2, d_act[0], d_ord, n, 0, 31, e->stream));
 	void *d_sort_tmp = e->b_cub.need(sort_tmp);
 	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
+	// warp-cooperative kernels (latency path): warps per block such that the rows of the longest query fit shared memory
+	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
+	const int WARP_JOBS_MAX = 8192;       // a class with fewer jobs than this cannot fill the chip with one job per lane
+	const int tail_warps = warps_for(e->max_len);
+	const char *dbg = getenv("B200_DEBUG");
 	int32_t ctr[16];
 	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
 	float ms_dp = 0;
@@ -515,7 +550,26 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	e->sync();
 	int n_active = ctr[0], cur = 0, rounds = 0;
 	size_t ev_used = 0;
+	auto ev_pair = [&]() {
+		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
+	};
 	while (n_active > 0) {
+		if (rounds > 0 && tail_warps && n_active <= WARP_JOBS_MAX) {
+			// few reads left: one warp per read finishes the walk on the device (advance + DP fused)
+			ev_pair();
+			CK(cudaEventRecord(e->ev_pool[ev_used], e->stream));
+			const int threads = 32 * tail_warps;
+			k_ext_tail<<<grid_for(n_active, tail_warps), threads, ext_warp_smem_bytes(tail_warps, e->max_len), e->stream>>>(eo, e->fm.l_pac, e->fm.pac,
+				(const uint8_t *)e->d_codes.p, n_active, d_act[cur], (const int64_t *)e->d_off.p, d_co, d_ch, d_se, d_srt, d_state, d_jobs, d_regs, d_nr,
+				e->max_len, d_cells, d_calls);
+			CK(cudaGetLastError());
+			CK(cudaEventRecord(e->ev_pool[ev_used + 1], e->stream));
+			ev_used += 2;
+			e->stats.n_launches += 1;
+			if (dbg) fprintf(stderr, "[ext] tail kernel over %d reads\n", n_active);
+			++rounds;
+			break;
+		}
 		CK(cudaMemsetAsync(d_ctr, 0, 16 * sizeof(int32_t), e->stream));
 		k_ext_advance<<<grid_for(n_active, 128), 128, 0, e->stream>>>(eo, e->fm.l_pac, n_active, d_act[cur], (const int64_t *)e->d_off.p, d_co, d_ch,
 			d_se, d_srt, d_state, d_jobs, d_regs, d_nr, d_act[cur ^ 1], d_key, d_ctr);
@@ -524,13 +578,13 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 		CK(cudaMemcpyAsync(ctr, d_ctr, (1 + EXT_N_CLASS) * sizeof(int32_t), cudaMemcpyDeviceToHost, e->stream));
 		e->sync();
 		const int n_jobs = ctr[0];
-		if (getenv("B200_DEBUG"))
+		if (dbg)
 			fprintf(stderr, "[ext] round %d active %d jobs %d classes %d %d %d %d %d %d %d %d\n", rounds, n_active, n_jobs, ctr[1], ctr[2], ctr[3],
 			        ctr[4], ctr[5], ctr[6], ctr[7], ctr[8]);
 		if (n_jobs == 0) break;
 		CK(cub::DeviceRadixSort::SortPairsDescending(d_sort_tmp, sort_tmp, d_key, d_key2, d_act[cur ^ 1], d_ord, n_jobs, 0, 31, e->stream));
 		e->stats.n_launches += 3;
-		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
+		ev_pair();
 		CK(cudaEventRecord(e->ev_pool[ev_used], e->stream));
 		// classes run concurrently on side streams (each launch has its own shared-memory footprint); largest jobs first
 		int pos = 0, k = 0;
@@ -540,8 +594,12 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 			if (cnt == 0) continue;
 			cudaStream_t st = e->side[k % Engine::N_SIDE];
 			CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-			if (c < EXT_N_CLASS - 1) {
-				const int qcap = class_cap[c];
+			const int qcap = c < EXT_N_CLASS - 1 ? class_cap[c] : e->max_len;
+			const int wpb = warps_for(qcap);
+			if (wpb && (cnt < WARP_JOBS_MAX || c >= EXT_N_CLASS - 3)) {
+				k_ext_dp_warp<<<grid_for(cnt, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
+					d_jobs, d_ord + pos, cnt, qcap, d_cells, d_calls);
+			} else if (c < EXT_N_CLASS - 1) {
 				const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
 				const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
 				k_ext_dp<<<grid_for(cnt, threads), threads, per_warp * (threads / 32), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,

@@ -21,6 +21,10 @@ public:
 	int n_reads = 0;
 	std::vector<int64_t> off;
 	std::vector<uint8_t> codes;
+	std::vector<uint8_t> staging;
+	std::vector<int64_t> seed_off;
+	std::vector<SeedRec> seeds;
+	std::vector<int32_t> l_rep;
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
@@ -39,6 +43,12 @@ void engine_destroy(Engine *e) { delete e; }
 Stats &engine_stats(Engine *e) { return e->stats; }
 const char *engine_kind() { return "hostemu"; }
 int engine_device_count() { return 1; }
+
+uint8_t *stage_read_buffer(Engine *e, int64_t bytes)
+{
+	e->staging.resize((size_t)bytes);
+	return e->staging.data();
+}
 
 void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_t *codes)
 {
@@ -98,9 +108,11 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 	}
 }
 
-void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, std::vector<SeedRec> &seeds,
-                std::vector<int32_t> &l_rep)
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &res)
 {
+	std::vector<int64_t> &seed_off = e->seed_off;
+	std::vector<SeedRec> &seeds = e->seeds;
+	std::vector<int32_t> &l_rep = e->l_rep;
 	std::vector<int64_t> io;
 	std::vector<Intv> iv;
 	stage_collect_intv(e, so, e->n_reads, e->off.data(), e->codes.data(), io, iv);
@@ -128,7 +140,7 @@ void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, st
 				int steps;
 				SeedRec s;
 				s.rbeg = (int64_t)fm_sa(e->fm, p.x0 + (uint64_t)c * step, &steps);
-				s.qbeg = (int32_t)(p.info >> 32); s.len = slen; s.pad = 0;
+				s.qbeg = (uint16_t)(p.info >> 32); s.len = (uint16_t)slen;
 				s.rid = fm_intv2rid(e->fm, s.rbeg, s.rbeg + s.len);
 				seeds.push_back(s);
 				e->stats.fm_sa_steps += steps; ++e->stats.fm_sa_lookups;
@@ -136,6 +148,7 @@ void stage_seed(Engine *e, const SeedOpt &so, std::vector<int64_t> &seed_off, st
 		}
 		seed_off[r + 1] = (int64_t)seeds.size();
 	}
+	res.seed_off = seed_off.data(); res.seeds = seeds.data(); res.l_rep = l_rep.data(); res.n_seeds = (int64_t)seeds.size();
 }
 
 void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,

@@ -266,7 +266,8 @@ def main():
 
     STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
-                 "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv", "n_seeds", "n_chains")
+                 "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv", "n_seeds", "n_chains",
+                 "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells")
 
     def e2e_step(c):
         """raw fastq bytes -> SAM bytes, everything inside"""
@@ -376,6 +377,11 @@ def main():
         gc = agg["sw_cells"] / agg["ms_k_sw"] / 1e6
         kern["ksw_align2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_sw"] / K, "cells_per_step": agg["sw_cells"] / K, "gcups": gc,
                               "achieved": gc * 11, "unit": "Gop/s (11 ops per cell)", "peak": i32_peak, "frac": (gc * 11 / i32_peak) if i32_peak else None}
+    if agg["ms_k_global"] > 0:
+        gc = agg["global_cells"] / agg["ms_k_global"] / 1e6
+        kern["ksw_global2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_global"] / K, "cells_per_step": agg["global_cells"] / K,
+                               "jobs_per_step": agg["n_global_jobs"] / K, "gcups": gc, "achieved": gc * 14,
+                               "unit": "Gop/s (14 int32 ops per cell, src/ksw.c:546-566)", "peak": i32_peak, "frac": (gc * 14 / i32_peak) if i32_peak else None}
     dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
     roof = None
     if dom:
@@ -391,7 +397,7 @@ def main():
                 "d2h_bytes_per_step": d2h // args.steps, "sam_bytes_per_step": sam_bytes // args.steps, "wall_ms_rank0": wall_ms},
         "gpu_launches": int(agg["n_launches"]), "clocks": clocks, "roofline": roof, "kernels": kern,
         "ksw_extend2_gcups": kern.get("ksw_extend2", {}).get("gcups"),
-        "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total")},
+        "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global", "ms_total")},
         "host_threads": n_threads,
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):

@@ -300,6 +300,7 @@ typedef struct {
 	int64_t h2d_bytes, d2h_bytes;
 	double ms_k_extend_dp;    /* CUDA-event time of the ksw_extend2 DP kernels alone (ms_k_extend = whole extension stage) */
 	int64_t n_extend_rounds;
+	double ms_sam_plan, ms_global;   /* inside ms_sam_host: the dry-run sweep that queues the CIGAR jobs; the device CIGAR stage (wall) */
 } b200_stats_t;
 void b200_get_stats(b200_stats_t *out);
 /* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP

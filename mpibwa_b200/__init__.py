@@ -82,7 +82,8 @@ class b200_stats_t(C.Structure):
                [(n, C.c_int64) for n in ("n_reads", "n_bases", "n_intv", "n_seeds", "n_chains", "n_extend_jobs",
                                          "extend_cells", "n_sw_jobs", "sw_cells", "n_global_jobs", "global_cells",
                                          "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes",
-                                         "d2h_bytes")] + [("ms_k_extend_dp", C.c_double), ("n_extend_rounds", C.c_int64)]
+                                         "d2h_bytes")] + [("ms_k_extend_dp", C.c_double), ("n_extend_rounds", C.c_int64),
+                                                          ("ms_sam_plan", C.c_double), ("ms_global", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -22,8 +22,15 @@ const unsigned char kNt4[256] = {
 	4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4, 4,4,4,4,4,4,4,4,4,4,4,4,4,4,4,4
 };
 
+AlignCtx &align_ctx()
+{
+	static thread_local AlignCtx ctx;
+	return ctx;
+}
+
 char *dup_cstr(const std::string &s)
 {
+	if (align_ctx().mode == AlignCtx::RECORD) return nullptr;     // dry run: nothing is formatted
 	char *p = (char *)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size());
 	p[s.size()] = 0;
@@ -349,7 +356,7 @@ static void put_int(std::string &s, long c)
 
 bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac,
                const uint8_t *pac, int l_query, uint8_t *query, int64_t rb, int64_t re, int *score,
-               std::vector<uint32_t> *cigar, int *NM, std::string *md)
+               std::vector<uint32_t> *cigar, int *NM, std::string *md, const GlobalRes *pre)
 {
 	if (cigar) cigar->clear();
 	if (NM) *NM = -1;
@@ -362,7 +369,10 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 		std::reverse(query, query + l_query);
 		std::reverse(rseq.begin(), rseq.end());
 	}
-	if (l_query == re - rb && w_ == 0) {
+	if (pre) {                                    // alignment already done by the CIGAR stage on the device
+		cigar->assign(pre->cigar, pre->cigar + pre->n_cigar);
+		*score = pre->score;
+	} else if (l_query == re - rb && w_ == 0) {
 		if (cigar) cigar->push_back((uint32_t)l_query << 4 | 0);
 		int sc = 0;
 		for (int i = 0; i < l_query; ++i) sc += mat[rseq[i] * 5 + query[i]];
@@ -794,11 +804,31 @@ void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int 
 	w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
 	w2 = w2 > tmp ? w2 : tmp;
 	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+	AlignCtx &cx = align_ctx();
+	bool done = false;
+	if (cx.mode != AlignCtx::DIRECT && qe > qb && rb >= 0 && re <= bns->l_pac << 1 && rb < re && !(rb < bns->l_pac && re > bns->l_pac) &&
+	    global_needs_dp(qe - qb, re - rb, w2 < opt->w << 2 ? w2 : opt->w << 2)) {
+		if (cx.mode == AlignCtx::RECORD) {            // queue the region for the device; the placeholder is never formatted
+			GlobalJob j;
+			j.rb = rb; j.re = re; j.zoff = 0; j.qb = qb; j.qe = qe; j.w2 = w2; j.truesc = ar->truesc; j.wmax = 0;
+			j.read = query_ == cx.seq_ptr[0] ? cx.read_idx[0] : cx.read_idx[1];
+			cx.rec->push_back(j);
+			NM = 0;
+			done = true;
+		} else {
+			const GlobalRes &g = cx.res[cx.cursor++];
+			if (g.n_cigar >= 0) {
+				gen_cigar(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, 0, bns->l_pac, pac, qe - qb,
+				          &query[qb], rb, re, &score, &a.cigar, &NM, &a.md, &g);
+				done = true;
+			}                                           // else: too many CIGAR operations for the result record - align here
+		}
+	}
 	i = 0;
-	do {
+	if (!done) do {
 		w2 = w2 < opt->w << 2 ? w2 : opt->w << 2;
 		gen_cigar(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w2, bns->l_pac, pac, qe - qb,
-		          &query[qb], rb, re, &score, &a.cigar, &NM, &a.md);
+		          &query[qb], rb, re, &score, &a.cigar, &NM, &a.md, nullptr);
 		if (score == last_sc || w2 == opt->w << 2) break;
 		last_sc = score;
 		w2 <<= 1;
@@ -895,6 +925,7 @@ static inline void put_cigar(const mem_opt_t *opt, const AlnView &p, std::string
 void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const bseq1_t *s, int n, const Aln *list,
              int which, const Aln *m_)
 {
+	if (align_ctx().mode == AlignCtx::RECORD) return;
 	AlnView p(list[which]);
 	AlnView mt(m_ ? *m_ : list[which]);
 	AlnView *m = m_ ? &mt : nullptr;

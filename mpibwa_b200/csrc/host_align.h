@@ -34,6 +34,20 @@ struct Aln {                    // counterpart of mem_aln_t
 
 typedef std::vector<mem_alnreg_t> RegVec;
 
+// Plumbing between mem_reg2aln's alignment step and the batched CIGAR stage on the device.  The SAM stage runs twice
+// per pair: once in RECORD mode (regions that need a DP are queued, nothing is formatted), then - after the device has
+// aligned every queued region - in REPLAY mode, which makes the same calls in the same order and picks the results up.
+struct AlignCtx {
+	enum { DIRECT = 0, RECORD = 1, REPLAY = 2 };
+	int mode = DIRECT;
+	std::vector<GlobalJob> *rec = nullptr;
+	const GlobalRes *res = nullptr;      // results of the current pair, in request order
+	int cursor = 0;
+	const char *seq_ptr[2] = { nullptr, nullptr };
+	int read_idx[2] = { 0, 0 };
+};
+AlignCtx &align_ctx();                   // thread-local
+
 // reference src/bntseq.c:349-375, src/bntseq.h:87
 int     bns_pos2rid_h(const bntseq_t *bns, int64_t pos_f);
 int     bns_intv2rid_h(const bntseq_t *bns, int64_t rb, int64_t re);
@@ -58,7 +72,7 @@ int  global_align(int qlen, const uint8_t *query, int tlen, const uint8_t *targe
 // bwa_gen_cigar2, reference src/bwa.c:121-207.  Returns false when the reference would return NULL.
 bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins, int w_, int64_t l_pac,
                const uint8_t *pac, int l_query, uint8_t *query, int64_t rb, int64_t re, int *score,
-               std::vector<uint32_t> *cigar, int *NM, std::string *md);
+               std::vector<uint32_t> *cigar, int *NM, std::string *md, const GlobalRes *pre = nullptr);
 
 // mem_sort_dedup_patch / mem_patch_reg, reference src/bwamem.c:406-489
 int  sort_dedup_patch(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, uint8_t *query, int n, mem_alnreg_t *a);

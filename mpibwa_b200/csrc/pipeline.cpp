@@ -21,6 +21,7 @@
 #include <mutex>
 #include <unordered_map>
 #include <algorithm>
+#include <atomic>
 
 namespace b200 {
 
@@ -475,27 +476,72 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	}
 	t1 = now_ms(); st.ms_rescue = t1 - t0; t0 = t1;
 
-	// ---- primary marking, pairing, mapQ, CIGAR and SAM text (reference worker2, src/bwamem.c:1187-1203)
-	if (!pe) {
-		parallel_for(nt, n, 256, [&](int, int64_t b, int64_t e) {
-			for (int64_t i = b; i < e; ++i) {
-				mark_primary_se(opt, (int)regs[i].size(), regs[i].data(), n_processed + i);
-				if (opt->flag & MEM_F_PRIMARY5) reorder_primary5(opt->T, regs[i]);
-				reg2sam(opt, bns, pac, &seqs[i], regs[i], 0, 0);
+	// ---- primary marking, pairing, mapQ, CIGAR and SAM text (reference worker2, src/bwamem.c:1187-1203).
+	// Two sweeps over the pairs: a dry run that only queues the regions whose CIGAR needs a banded global alignment,
+	// the CIGAR stage on the device for all of them at once, then the real sweep that picks the alignments up.
+	{
+		const int64_t n_units = pe ? n >> 1 : n;
+		const int per = pe ? 2 : 1;
+		auto run_unit = [&](int64_t u, RegVec *r) {
+			if (pe) sam_pe_finish(opt, bns, pac, pes, (uint64_t)((n_processed >> 1) + u), &seqs[u << 1], r);
+			else {
+				mark_primary_se(opt, (int)r[0].size(), r[0].data(), n_processed + u);
+				if (opt->flag & MEM_F_PRIMARY5) reorder_primary5(opt->T, r[0]);
+				reg2sam(opt, bns, pac, &seqs[u], r[0], 0, 0);
 			}
+		};
+		struct UnitJobs { int32_t tid, start, count; };
+		std::vector<UnitJobs> uj(n_units);
+		std::vector<std::vector<GlobalJob>> tjobs(nt);
+		parallel_for(nt, n_units, 256, [&](int tid, int64_t b, int64_t e) {
+			AlignCtx &cx = align_ctx();
+			cx.mode = AlignCtx::RECORD; cx.rec = &tjobs[tid];
+			for (int64_t u = b; u < e; ++u) {
+				RegVec copy[2];
+				for (int k = 0; k < per; ++k) { copy[k] = regs[u * per + k]; cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
+				const int32_t start = (int32_t)tjobs[tid].size();
+				run_unit(u, copy);
+				uj[u] = { tid, start, (int32_t)tjobs[tid].size() - start };
+			}
+			cx.mode = AlignCtx::DIRECT; cx.rec = nullptr;
 		});
-	} else {
-		parallel_for(nt, n >> 1, 256, [&](int, int64_t b, int64_t e) {
-			for (int64_t i = b; i < e; ++i)
-				sam_pe_finish(opt, bns, pac, pes, (uint64_t)((n_processed >> 1) + i), &seqs[i << 1], &regs[i << 1]);
+		std::vector<int64_t> tbase(nt + 1, 0);
+		for (int t = 0; t < nt; ++t) tbase[t + 1] = tbase[t] + (int64_t)tjobs[t].size();
+		std::vector<GlobalJob> gjobs(tbase[nt]);
+		GlobalOpt go;
+		go.o_del = opt->o_del; go.e_del = opt->e_del; go.o_ins = opt->o_ins; go.e_ins = opt->e_ins; go.a = opt->a; go.w_max = opt->w << 2;
+		memcpy(go.mat, opt->mat, 25);
+		int64_t zb = 0;
+		for (int t = 0; t < nt; ++t)
+			for (size_t k = 0; k < tjobs[t].size(); ++k) {
+				GlobalJob j = tjobs[t][k];
+				j.zoff = zb;
+				zb += (global_z_need(go, j.qe - j.qb, (int)(j.re - j.rb), j.w2, &j.wmax) + 15) & ~(int64_t)15;
+				gjobs[tbase[t] + (int64_t)k] = j;
+			}
+		tjobs.clear();
+		double tg = now_ms();
+		st.ms_sam_plan = tg - t0;
+		std::vector<GlobalRes> gres;
+		if (!gjobs.empty()) stage_global(eng, go, gjobs, zb, gres);
+		st.ms_global = now_ms() - tg;
+		parallel_for(nt, n_units, 256, [&](int, int64_t b, int64_t e) {
+			AlignCtx &cx = align_ctx();
+			cx.mode = AlignCtx::REPLAY;
+			for (int64_t u = b; u < e; ++u) {
+				cx.res = gres.data() + tbase[uj[u].tid] + uj[u].start; cx.cursor = 0;
+				run_unit(u, &regs[u * per]);
+				if (cx.cursor != uj[u].count) { fprintf(stderr, "[mpibwa_b200] CIGAR stage: request sequence changed between the sweeps\n"); abort(); }
+			}
+			cx.mode = AlignCtx::DIRECT; cx.res = nullptr;
 		});
 	}
 	t1 = now_ms(); st.ms_sam_host = t1 - t0;
 	st.ms_total = t1 - t_start;
 	if (bwa_verbose >= 3)
-		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f)\n",
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f [plan %.0f, cigar stage %.0f])\n",
 		        "mem_process_seqs", n, st.ms_total * 1e-3, engine_kind(), st.ms_seed, st.ms_chain_host, st.ms_extend,
-		        st.ms_regs_host, st.ms_rescue, st.ms_sam_host);
+		        st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
 }
 
 } // namespace b200

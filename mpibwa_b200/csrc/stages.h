@@ -11,6 +11,7 @@
 #include "fm_kernels.h"
 #include "ext_kernels.h"
 #include "sw_kernels.h"
+#include "global_kernels.h"
 
 namespace b200 {
 
@@ -26,11 +27,6 @@ struct SwJob {
 	int32_t is_rev;         // use the reverse complement of the read as the query
 	int32_t xtra;
 	int32_t q_beg, q_len;   // sub-range of the read used as query (whole read for mate rescue)
-};
-
-struct GlobalJob {          // banded global alignment + traceback (bwa_gen_cigar2 / ksw_global2)
-	int64_t rb, re;
-	int32_t read, q_beg, q_len, w;
 };
 
 struct Stats : b200_stats_t {};
@@ -60,6 +56,9 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);
+
+// CIGAR stage: banded global alignment + traceback of regions of the resident reads (jobs carry zoff/slot filled by the caller)
+void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out);
 
 // generic batches over caller-provided byte buffers (C-ABI b200_*_batch and the single-job wrappers)
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,

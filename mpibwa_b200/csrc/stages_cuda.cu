@@ -64,7 +64,7 @@ struct PinBuf {
 	void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
 };
 
-struct Counters { unsigned long long occ_blocks, sa_steps, ext_cells, ext_calls, sw_cells; };
+struct Counters { unsigned long long occ_blocks, sa_steps, ext_cells, ext_calls, sw_cells, global_cells; };
 
 class Engine {
 public:
@@ -84,7 +84,8 @@ public:
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
 	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
-	PinBuf h_seeds, h_seed_off, h_lrep, h_codes;
+	PinBuf h_seeds, h_seed_off, h_lrep, h_codes, h_gres;
+	DevBuf b_gjobs, b_gres, b_grow, b_gz;
 	std::vector<cudaEvent_t> ev_pool;
 	static const int N_SIDE = 8;
 	cudaStream_t side[N_SIDE];
@@ -202,7 +203,8 @@ void engine_destroy(Engine *e)
 		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
 		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
 	for (DevBuf *b : bufs) b->release();
-	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release();
+	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release(); e->h_gres.release();
+	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
 	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);
@@ -864,6 +866,146 @@ void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t
 	Counters c = e->read_counters();
 	e->stats.sw_cells += (int64_t)c.sw_cells;
 	e->stats.n_sw_jobs += n_jobs;
+}
+
+/* ------------------------------------------------------------------ CIGAR stage (banded global alignment + traceback) */
+
+// Fast path: one region per lane.  The H/E row of a lane is a band-wide circular window (S columns, S >= 2*band+2) in
+// shared memory laid out [column][lane] as {h,e} pairs, the oriented query sits in shared memory as bytes, substitution
+// scores come from one PRMT over the two-register score row of the target base.
+struct GlobalRowSh {
+	int2 *base; int mask;
+	__device__ __forceinline__ int32_t h(int j) const { return base[(j & mask) << 5].x; }
+	__device__ __forceinline__ int32_t e(int j) const { return base[(j & mask) << 5].y; }
+	__device__ __forceinline__ void set_h(int j, int32_t v) const { base[(j & mask) << 5].x = v; }
+	__device__ __forceinline__ void set_e(int j, int32_t v) const { base[(j & mask) << 5].y = v; }
+};
+struct GlobalSeqsSh {
+	const uint8_t *Q; int l_query;
+	const uint8_t *pac; int64_t l_pac, rb, re; int rev;
+	const uint32_t *lut;
+	__device__ __forceinline__ int qa(int j) const { return Q[ext_qidx(j)]; }
+	__device__ __forceinline__ int ta(int i) const { return fm_base(pac, l_pac, rev ? re - 1 - i : rb + i); }
+	__device__ __forceinline__ uint2 trow(const GlobalOpt &, int i) const { const int t = ta(i); return make_uint2(lut[t * 2], lut[t * 2 + 1]); }
+	__device__ __forceinline__ int sub(const uint2 &row, int j) const { return prmt_score(row.x, row.y, (uint32_t)qa(j) * 0x1111u + 0x8880u); }
+};
+
+__global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t *__restrict__ pac, int64_t l_pac, int n,
+                                                     const GlobalJob *__restrict__ jobs, const int32_t *__restrict__ order,
+                                                     const int64_t *__restrict__ off, const uint8_t *__restrict__ codes, uint8_t *z,
+                                                     GlobalRes *res, int S, int qcap, Counters *cnt)
+{
+	extern __shared__ uint32_t smem[];
+	__shared__ uint32_t lut[10];
+	if (threadIdx.x < 5) {
+		const int8_t *m = go.mat + threadIdx.x * 5;
+		lut[threadIdx.x * 2] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
+		lut[threadIdx.x * 2 + 1] = (uint32_t)(uint8_t)m[4];
+	}
+	__syncthreads();
+	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+	const int qpad = (qcap + 4) & ~3;
+	const size_t per_warp_words = (size_t)S * 64 + (size_t)qpad * 8;
+	int2 *rows = (int2 *)(smem + wib * per_warp_words) + lane;
+	uint8_t *Q = (uint8_t *)(smem + wib * per_warp_words + (size_t)S * 64) + lane * 4;
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	if (t < n) {
+		const int jx = order[t];
+		const GlobalJob j = jobs[jx];
+		GlobalSeqsSh s;
+		s.Q = Q; s.l_query = j.qe - j.qb; s.pac = pac; s.l_pac = l_pac; s.rb = j.rb; s.re = j.re; s.rev = j.rb >= l_pac; s.lut = lut;
+		const uint8_t *q = codes + off[j.read] + j.qb;
+		for (int x = 0; x < s.l_query; ++x) Q[ext_qidx(x)] = s.rev ? q[s.l_query - 1 - x] : q[x];
+		GlobalRowSh eh = { rows, S - 1 };
+		global_task(go, s, j, eh, z + j.zoff, &res[jx], &cells);
+	}
+	warp_add(&cnt->global_cells, cells);
+}
+
+// general path: one region per thread; H/E row interleaved over the threads of the launch in global memory
+__global__ void __launch_bounds__(128) k_global_jobs(GlobalOpt go, const uint8_t *__restrict__ pac, int64_t l_pac, int n,
+                                                     const GlobalJob *__restrict__ jobs, const int32_t *__restrict__ order,
+                                                     const int64_t *__restrict__ off, const uint8_t *__restrict__ codes, int32_t *rows,
+                                                     int64_t stride, uint8_t *z, GlobalRes *res, Counters *cnt)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	int64_t cells = 0;
+	if (t < n) {
+		const int jx = order[t];
+		const GlobalJob j = jobs[jx];
+		GlobalRow eh = { rows + t, stride };
+		global_task(go, global_seqs(pac, l_pac, codes + off[j.read] + j.qb, j), j, eh, z + j.zoff, &res[jx], &cells);
+	}
+	warp_add(&cnt->global_cells, cells);
+}
+
+void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out)
+{
+	CK(cudaSetDevice(e->device));
+	const int64_t n = (int64_t)jobs.size();
+	out.resize(n);
+	if (n == 0) return;
+	e->zero_counters();
+	// classes by the circular window a lane needs: 32, 64, 128, 256, 512 columns; wider bands or queries over 256 bases
+	// take the general kernel
+	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
+	int64_t cnt[6] = { 0, 0, 0, 0, 0, 0 }, pos[6];
+	int qmax[6] = { 0, 0, 0, 0, 0, 0 };
+	std::vector<uint8_t> cls(n);
+	for (int64_t i = 0; i < n; ++i) {
+		const GlobalJob &j = jobs[i];
+		const int need = 2 * j.wmax + 2, ql = j.qe - j.qb;
+		int k = 5;
+		if (ql <= 256) for (int c = 0; c < 5; ++c) if (need <= cls_S[c]) { k = c; break; }
+		cls[i] = (uint8_t)k; ++cnt[k];
+		qmax[k] = std::max(qmax[k], ql);
+	}
+	pos[0] = 0;
+	for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
+	std::vector<int32_t> order(n);
+	{ int64_t w[6]; for (int k = 0; k < 6; ++k) w[k] = pos[k]; for (int64_t i = 0; i < n; ++i) order[w[cls[i]]++] = (int32_t)i; }
+	GlobalJob *dj = e->b_gjobs.as<GlobalJob>(n);
+	GlobalRes *dr = e->b_gres.as<GlobalRes>(n);
+	int32_t *d_ord = e->b_xord.as<int32_t>(n);
+	uint8_t *z = e->b_gz.as<uint8_t>((size_t)z_bytes + 64);
+	e->h2d(dj, jobs.data(), sizeof(GlobalJob) * n);
+	e->h2d(d_ord, order.data(), sizeof(int32_t) * n);
+	static bool attr_set = false;
+	if (!attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+	e->tic();
+	CK(cudaEventRecord(e->ev_fork, e->stream));
+	int used = 0;
+	for (int k = 5; k >= 0; --k) {
+		if (cnt[k] == 0) continue;
+		cudaStream_t st = e->side[used % Engine::N_SIDE];
+		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+		const int nk = (int)cnt[k];
+		if (k < 5) {
+			const int S = cls_S[k], qcap = qmax[k];
+			const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+			const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
+			k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
+				(const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, z, dr, S, qcap, e->d_cnt);
+		} else {
+			const int64_t stride = ((int64_t)nk + 31) & ~31ll;
+			int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
+			k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], (const int64_t *)e->d_off.p,
+				(const uint8_t *)e->d_codes.p, rows, stride, z, dr, e->d_cnt);
+		}
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
+		e->stats.n_launches += 1;
+		++used;
+	}
+	for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
+	e->stats.ms_k_global += e->toc();
+	GlobalRes *hr = (GlobalRes *)e->h_gres.need(sizeof(GlobalRes) * n);
+	e->d2h(hr, dr, sizeof(GlobalRes) * n);
+	Counters c = e->read_counters();
+	memcpy(out.data(), hr, sizeof(GlobalRes) * n);
+	e->stats.global_cells += (int64_t)c.global_cells;
+	e->stats.n_global_jobs += n;
 }
 
 /* ------------------------------------------------------------------ int32 issue-rate micro-benchmark (roofline denominator)

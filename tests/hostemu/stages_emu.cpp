@@ -197,6 +197,20 @@ void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::v
 	}
 }
 
+void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out)
+{
+	out.resize(jobs.size());
+	std::vector<uint8_t> z((size_t)z_bytes + 16);
+	std::vector<int32_t> row;
+	for (size_t x = 0; x < jobs.size(); ++x) {
+		const GlobalJob &j = jobs[x];
+		row.resize(2 * (size_t)(j.qe - j.qb + 2));
+		GlobalRow eh = { row.data(), 1 };
+		global_task(go, global_seqs(e->fm.pac, e->fm.l_pac, e->codes.data() + e->off[j.read] + j.qb, j), j, eh, z.data() + j.zoff, &out[x], &e->stats.global_cells);
+		++e->stats.n_global_jobs;
+	}
+}
+
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
                         const uint8_t *query, int64_t, const uint8_t *target, int64_t)
 {

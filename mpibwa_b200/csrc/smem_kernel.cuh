@@ -43,18 +43,38 @@ B200_HD uint64_t l2_at(const FmView &fm, int i)
 	return i == 0 ? fm.L2[0] : i == 1 ? fm.L2[1] : i == 2 ? fm.L2[2] : i == 3 ? fm.L2[3] : fm.L2[4];
 }
 
-// Occ(., k) for the four symbols from one loaded block; kin = (adjusted k) & 127
-B200_HD void occ4_block(const Q4 &c0, const Q4 &c1, const Q4 &s0, const Q4 &s1, uint32_t kin, uint64_t cnt[4])
+// Mask that keeps the first kin+1 symbols of a block, for the word pair (2p, 2p+1) in the packed-plane layout below
+// (even bits <- word 2p, odd bits <- word 2p+1).
+B200_HD uint32_t occ_pair_mask(uint32_t kin, int p)
+{
+	const int na = (int)kin + 1 - 32 * p, nb = na - 16;          // symbols kept in word 2p / 2p+1
+	const uint32_t ma = na <= 0 ? 0u : na >= 16 ? 0xffffffffu : ~((1u << ((16 - na) << 1)) - 1u);
+	const uint32_t mb = nb <= 0 ? 0u : nb >= 16 ? 0xffffffffu : ~((1u << ((16 - nb) << 1)) - 1u);
+	return (ma & 0x55555555u) | (mb & 0xaaaaaaaau);
+}
+
+// Occ(., k) for the four symbols from one loaded block; kin = (adjusted k) & 127.
+// Two symbol words are merged into one "low-bit plane" word and one "high-bit plane" word (the planes of the first word
+// on the even bits, of the second on the odd bits), so a pair of words costs three POPCs: #lo, #hi, #(lo & hi).
+// mlut: 128 x 4 packed masks (shared memory on the device); nullptr = compute the masks here.
+B200_HD void occ4_block(const Q4 &c0, const Q4 &c1, const Q4 &s0, const Q4 &s1, uint32_t kin, const uint32_t *mlut, uint64_t cnt[4])
 {
 	const uint32_t w[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
-	const uint32_t full = kin >> 4;
-	const uint32_t pm = ~((1u << ((~kin & 15u) << 1)) - 1u);
+	uint32_t pm[4];
+	if (mlut) {
+#if defined(__CUDA_ARCH__)
+		const uint4 m = *reinterpret_cast<const uint4 *>(mlut + kin * 4);
+		pm[0] = m.x; pm[1] = m.y; pm[2] = m.z; pm[3] = m.w;
+#else
+		for (int p = 0; p < 4; ++p) pm[p] = mlut[kin * 4 + p];
+#endif
+	} else for (int p = 0; p < 4; ++p) pm[p] = occ_pair_mask(kin, p);
 	uint32_t slo = 0, shi = 0, s3 = 0;
 #pragma unroll
-	for (uint32_t i = 0; i < 8; ++i) {
-		const uint32_t m = i < full ? 0xffffffffu : (i == full ? pm : 0u);
-		const uint32_t v = w[i] & m;
-		const uint32_t lo = v & 0x55555555u, hi = (v >> 1) & 0x55555555u;
+	for (int p = 0; p < 4; ++p) {
+		const uint32_t a = w[2 * p], b = w[2 * p + 1];
+		const uint32_t lo = ((a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau)) & pm[p];
+		const uint32_t hi = (((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau)) & pm[p];
 		slo += (uint32_t)popc32(lo); shi += (uint32_t)popc32(hi); s3 += (uint32_t)popc32(lo & hi);
 	}
 	const uint32_t n1 = slo - s3, n2 = shi - s3;
@@ -65,7 +85,7 @@ B200_HD void occ4_block(const Q4 &c0, const Q4 &c1, const Q4 &s0, const Q4 &s1, 
 }
 
 // bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c
-B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c,
+B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c, const uint32_t *mlut,
                            uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
 {
 	const uint64_t base = is_back ? x0 : x1, other = is_back ? x1 : x0;
@@ -76,8 +96,8 @@ B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t 
 	const Q4 kc0 = ld_q4(pk), kc1 = ld_q4(pk + 4), ks0 = ld_q4(pk + 8), ks1 = ld_q4(pk + 12);
 	const Q4 lc0 = ld_q4(pl), lc1 = ld_q4(pl + 4), ls0 = ld_q4(pl + 8), ls1 = ld_q4(pl + 12);
 	uint64_t tk[4], tl[4];
-	occ4_block(kc0, kc1, ks0, ks1, (uint32_t)ka & 127u, tk);
-	occ4_block(lc0, lc1, ls0, ls1, (uint32_t)la & 127u, tl);
+	occ4_block(kc0, kc1, ks0, ks1, (uint32_t)ka & 127u, mlut, tk);
+	occ4_block(lc0, lc1, ls0, ls1, (uint32_t)la & 127u, mlut, tl);
 	if (kz) tk[0] = tk[1] = tk[2] = tk[3] = 0;
 	if (lz) tl[0] = tl[1] = tl[2] = tl[3] = 0;
 	n_blocks += (kz ? 0 : 1) + ((!lz && (kz || (la >> 7) != (ka >> 7))) ? 1 : 0);
@@ -223,6 +243,43 @@ struct SeedLane {
 		}
 	}
 
+	// Fast path for the three steady states (forward sweep, backward sweep incl. the change of row, greedy pass): digests
+	// the result of the extension and sets up the next one without leaving straight-line code.  Returns 0 when the next
+	// extension is ready, 1 when the rarer transition must go through consume() + advance() (state untouched), 2 when
+	// only advance() is needed (state already updated as consume() would have).
+	B200_HD int fast_step(const SeedOpt &so, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
+	{
+		if (st == BWD) {
+			const bool live = o2 >= min_intv;
+			if (!live && n_curr == 0 && (nm == 0 || i + 1 < last_start)) return 1;      // an SMEM is reported
+			if (live && (n_curr == 0 || o2 != last_x2)) {
+				L.set(n_list - 1 - n_curr, o0, o1, o2, kend);
+				++n_curr; last_x2 = o2;
+			}
+			if (++j == n_prev) {
+				if (n_curr == 0) { st = SMEM_END; return 2; }
+				n_prev = n_curr; --i;
+				if (i < 0 || q[i] > 3) { st = BWD_ROW; return 2; }
+				c = q[i]; j = 0; n_curr = 0;
+			}
+			L.get(n_list - 1 - j, k0, k1, k2, kend);
+			return 0;
+		}
+		const int ni = i + 1;
+		if (ni >= len) return 1;
+		const int qn = q[ni];
+		if (qn > 3) return 1;
+		if (st == FWD) {
+			if (o2 != k2) {
+				if (o2 < min_intv) return 1;
+				L.set(n_list++, k0, k1, k2, kend);
+			}
+			kend = ni;
+		} else if (o2 < (uint64_t)so.max_mem_intv && i - sx >= so.min_seed_len) return 1;   // P3: a seed is reported
+		k0 = o0; k1 = o1; k2 = o2; i = ni; c = 3 - qn;
+		return 0;
+	}
+
 	// digest the result of the extension requested by advance()
 	B200_HD void consume(const SeedOpt &so, int cap, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
 	{
@@ -263,8 +320,11 @@ __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n
                                                     int32_t *n_intv, int *next_read, int *worst, unsigned long long *occ_blocks)
 {
 	extern __shared__ uint32_t seed_sh[];
+	uint32_t *mlut = seed_sh;                          // 128 x 4 packed occ masks
+	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
+	__syncthreads();
 	SeedList L;
-	L.sh = seed_sh + threadIdx.x; L.stride = blockDim.x; L.quota = quota;
+	L.sh = seed_sh + 512 + threadIdx.x; L.stride = 128; L.quota = quota;
 	L.sstride = (int64_t)gridDim.x * blockDim.x;
 	L.spill = spill + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	SeedLane ln;
@@ -286,9 +346,12 @@ __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			uint64_t o0, o1, o2;
-			fm_extend_sel(fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
-			ln.consume(so, cap, L, o0, o1, o2);
-			need = ln.advance(fm, so, cap, L);
+			fm_extend_sel(fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, mlut, o0, o1, o2, blocks);
+			const int slow = ln.fast_step(so, L, o0, o1, o2);
+			if (slow) {
+				if (slow == 1) ln.consume(so, cap, L, o0, o1, o2);
+				need = ln.advance(fm, so, cap, L);
+			}
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);

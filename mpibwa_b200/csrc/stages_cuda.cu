@@ -344,7 +344,7 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	const int n = r1 - r0;
 	static int blocks_per_sm = 0, n_sm = 0;
 	const int threads = 128, quota = 16;
-	const size_t sh_bytes = (size_t)threads * quota * 16;
+	const size_t sh_bytes = 2048 + (size_t)threads * quota * 16;      // occ mask table + interval lists
 	if (!blocks_per_sm) {
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, e->device));

@@ -87,10 +87,15 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 			SeedLane ln;
 			int64_t blocks = 0;
 			ln.begin(so, len, codes + off[r], out2.data());
-			while (ln.advance(e->fm, so, cap2, L)) {
+			bool need = ln.advance(e->fm, so, cap2, L);
+			while (need) {
 				uint64_t o0, o1, o2;
-				fm_extend_sel(e->fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
-				ln.consume(so, cap2, L, o0, o1, o2);
+				fm_extend_sel(e->fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, nullptr, o0, o1, o2, blocks);
+				const int slow = (r & 1) ? ln.fast_step(so, L, o0, o1, o2) : 1;     // odd reads also exercise the fast path
+				if (slow) {
+					if (slow == 1) ln.consume(so, cap2, L, o0, o1, o2);
+					need = ln.advance(e->fm, so, cap2, L);
+				}
 			}
 			bool same = ln.n_out == n;
 			if (same) {

@@ -22,12 +22,15 @@
 
 namespace b200 {
 
-struct ExtJob {                 // one pending ksw_extend2 call (+ retry) of a read; 64 bytes
+struct ExtJob {                 // one pending ksw_extend2 call (+ retry) of a read
 	int64_t qaddr;              // index into the code buffer of query base 0
-	int64_t f0;                 // forward-strand coordinate of target base 0
-	int32_t qstep, fstep, comp; // +-1 walking directions; comp: complement the target bases (reverse strand)
+	int64_t f0;                 // forward-strand coordinate of target base 0 (comp 0/1) or offset into a byte buffer (comp 2)
+	int32_t qstep, fstep;       // +-1 walking directions
+	int32_t comp;               // 0: target from pac; 1: from pac, complemented (reverse strand); 2: target bytes (codes 0-4)
 	int32_t qlen, tlen, h0, prev, bonus;
-	int32_t score, qle, tle, gtle, gscore, aw;   // results
+	int32_t w0;                 // 0: mem_chain2aln's rule (band eo.w, one retry with 2*eo.w); > 0: exactly one call with band w0
+	int32_t score, qle, tle, gtle, gscore, aw, max_off;   // results
+	int32_t pad;
 };
 
 struct ExtState {               // per read
@@ -57,7 +60,7 @@ __device__ __forceinline__ void ext_emit_job(ExtJob *jb, const uint8_t *, int64_
 	const bool fwd = p0 < l_pac;                  // p0: coordinate of target base 0 in [0, 2*l_pac); windows never bridge strands
 	jb->qaddr = qaddr; jb->qstep = qstep;
 	jb->f0 = fwd ? p0 : (l_pac << 1) - 1 - p0; jb->fstep = fwd ? pstep : -pstep; jb->comp = fwd ? 0 : 1;
-	jb->qlen = qlen; jb->tlen = tlen; jb->h0 = h0; jb->prev = prev; jb->bonus = bonus;
+	jb->qlen = qlen; jb->tlen = tlen; jb->h0 = h0; jb->prev = prev; jb->bonus = bonus; jb->w0 = 0;
 }
 
 // Advances the chain2aln walk of read r until it needs a DP (returns true; the job is in *jb) or is finished.
@@ -204,6 +207,14 @@ __device__ __forceinline__ int prmt_score(uint32_t lo, uint32_t hi, uint32_t sel
 
 __device__ __forceinline__ int pac_fbase(const uint8_t *__restrict__ pac, int64_t f) { return pac[f >> 2] >> ((~f & 3) << 1) & 3; }
 
+// target base of a job: 2-bit reference (forward / complemented) or a byte buffer of codes 0-4
+__device__ __forceinline__ int ext_tbase(const uint8_t *__restrict__ src, int64_t f, int comp)
+{
+	if (comp == 2) return src[f];
+	const int b = pac_fbase(src, f);
+	return comp ? 3 - b : b;
+}
+
 // Query bytes live in shared memory as [column/4][lane][column%4] (bank = lane for every lane/column combination).
 __device__ __forceinline__ int ext_qidx(int j) { return ((j >> 2) << 7) + (j & 3); }
 
@@ -222,6 +233,15 @@ __device__ __forceinline__ int ext_init_row(const ExtOpt &o, const ExtJob &jb, i
 	return w < max_del ? w : max_del;
 }
 
+__device__ __forceinline__ void ext_fill_score_rows(const ExtOpt &eo, uint32_t *sc_lo, uint32_t *sc_hi)
+{
+	if (threadIdx.x < 5) {
+		const int8_t *m = eo.mat + threadIdx.x * 5;
+		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
+		sc_hi[threadIdx.x] = (uint32_t)(uint8_t)m[4];
+	}
+}
+
 // Fast path: one job per lane, warps built from the size-sorted order.  The row loop is warp-synchronous: every
 // iteration each live lane computes one row of its own job, then the warp reconverges, so that the per-row
 // prologue/epilogue is issued once per warp-row and only the cell loop runs with per-lane trip counts.
@@ -230,17 +250,13 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
                                                unsigned long long *calls_out)
 {
 	extern __shared__ uint32_t smem[];
-	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	__shared__ uint32_t sc_lo[5], sc_hi[5];
 	const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
 	const int qpad = (qcap + 4) & ~3;
 	const int per_warp_words = (qcap + 1) * 32 + qpad * 8;
 	uint32_t *S = smem + (size_t)wib * per_warp_words + lane;
 	uint8_t *Q = (uint8_t *)(smem + (size_t)wib * per_warp_words + (qcap + 1) * 32) + lane * 4;
-	if (threadIdx.x < 4) {
-		const int8_t *m = eo.mat + threadIdx.x * 5;
-		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
-		sc_hi[threadIdx.x] = (uint32_t)(uint8_t)m[4];
-	}
+	ext_fill_score_rows(eo, sc_lo, sc_hi);
 	__syncthreads();
 	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
@@ -248,12 +264,12 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 	int calls = 0;
 	ExtJob *jp = nullptr;
 	ExtJob jb;
-	jb.qlen = 0; jb.tlen = 0; jb.h0 = 1; jb.prev = -1; jb.bonus = 0; jb.f0 = 0; jb.fstep = 0; jb.comp = 0; jb.qaddr = 0; jb.qstep = 0;
+	jb.qlen = 0; jb.tlen = 0; jb.h0 = 1; jb.prev = -1; jb.bonus = 0; jb.f0 = 0; jb.fstep = 0; jb.comp = 0; jb.qaddr = 0; jb.qstep = 0; jb.w0 = 0;
 	bool alive = false;
 	if (t < n) { jp = &jobs[order[t]]; jb = *jp; alive = true; }
 	for (int j = 0; j < jb.qlen; ++j) Q[ext_qidx(j)] = codes[jb.qaddr + (int64_t)jb.qstep * j];
 	// per-attempt DP state
-	int aw = eo.w, attempt = 0, prev_score = jb.prev;
+	int aw = jb.w0 > 0 ? jb.w0 : eo.w, attempt = jb.w0 > 0 ? 1 : 0, prev_score = jb.prev;
 	int w = ext_init_row(eo, jb, aw, S);
 	int i = 0, beg = 0, end = jb.qlen, max = jb.h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
 	int64_t f = jb.f0;
@@ -261,8 +277,7 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 		if (alive) {
 			bool done = i >= jb.tlen;
 			if (!done) {
-				int tb = pac_fbase(pac, f);
-				if (jb.comp) tb = 3 - tb;
+				const int tb = ext_tbase(pac, f, jb.comp);
 				const uint32_t lo = sc_lo[tb], hi = sc_hi[tb];
 				int fgap = 0, h1, hj = -1, j;
 				if (beg < i - w) beg = i - w;
@@ -321,6 +336,7 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 					i = 0; beg = 0; end = jb.qlen; max = jb.h0; max_i = max_j = max_ie = -1; gscore = -1; max_off = 0; f = jb.f0;
 				} else {
 					jp->score = score; jp->qle = max_j + 1; jp->tle = max_i + 1; jp->gtle = max_ie + 1; jp->gscore = gscore; jp->aw = aw;
+					jp->max_off = max_off;
 					alive = false;
 				}
 			}
@@ -333,7 +349,7 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 
 // general path: any query length / score range, row state in global memory (int32, lane-interleaved)
 struct QStep { const uint8_t *p; int64_t step; __device__ __forceinline__ int operator()(int j) const { return p[step * j]; } };
-struct TStep { const uint8_t *pac; int64_t f0; int fstep, comp; __device__ __forceinline__ int operator()(int i) const { int b = pac_fbase(pac, f0 + (int64_t)fstep * i); return comp ? 3 - b : b; } };
+struct TStep { const uint8_t *pac; int64_t f0; int fstep, comp; __device__ __forceinline__ int operator()(int i) const { return ext_tbase(pac, f0 + (int64_t)fstep * i, comp); } };
 
 __global__ void __launch_bounds__(128) k_ext_dp_big(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
                                                     ExtJob *jobs, const int32_t *__restrict__ order, int n, int32_t *eh, int64_t stride,
@@ -352,13 +368,13 @@ __global__ void __launch_bounds__(128) k_ext_dp_big(ExtOpt eo, const uint8_t *__
 		int score = jb.prev, aw = eo.w;
 		for (int it = 0; it < 2; ++it) {
 			const int prev = score;
-			aw = eo.w << it;
+			aw = jb.w0 > 0 ? jb.w0 : eo.w << it;
 			extend_core(jb.qlen, qa, jb.tlen, ta, eo, aw, jb.bonus, jb.h0, acc, &x, &cells);
 			++calls;
 			score = x.score;
-			if (score == prev || x.max_off < (aw >> 1) + (aw >> 2)) break;
+			if (jb.w0 > 0 || score == prev || x.max_off < (aw >> 1) + (aw >> 2)) break;
 		}
-		jp->score = score; jp->qle = x.qle; jp->tle = x.tle; jp->gtle = x.gtle; jp->gscore = x.gscore; jp->aw = aw;
+		jp->score = score; jp->qle = x.qle; jp->tle = x.tle; jp->gtle = x.gtle; jp->gscore = x.gscore; jp->aw = aw; jp->max_off = x.max_off;
 	}
 	long long c = cells;
 	for (int o = 16; o > 0; o >>= 1) { c += __shfl_down_sync(0xffffffffu, c, o); calls += __shfl_down_sync(0xffffffffu, calls, o); }
@@ -402,7 +418,7 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 	int prev_score = jb.prev, aw = eo.w, score = 0;
 	int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
 	for (int attempt = 0; attempt < 2; ++attempt) {
-		aw = eo.w << attempt;
+		aw = jb.w0 > 0 ? jb.w0 : eo.w << attempt;
 		__syncwarp();
 		for (int j = lane; j <= qlen; j += 32) {           // row -1 (src/ksw.c:395-397)
 			int v = j == 0 ? h0 : h0 - oe_ins - (j - 1) * e_ins;
@@ -421,12 +437,11 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 		max = h0; max_i = -1; max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
 		int beg = 0, end = qlen;
 		int64_t f = jb.f0;
-		int tb_next = tlen > 0 ? pac_fbase(pac, f) : 0;
+		int tb_next = tlen > 0 ? ext_tbase(pac, f, jb.comp) : 0;
 		for (int i = 0; i < tlen; ++i) {
-			int tb = tb_next;
+			const int tb = tb_next;
 			f += jb.fstep;
-			if (i + 1 < tlen) tb_next = pac_fbase(pac, f);
-			if (jb.comp) tb = 3 - tb;
+			if (i + 1 < tlen) tb_next = ext_tbase(pac, f, jb.comp);
 			const uint32_t lo = sc_lo[tb], hi = sc_hi[tb];
 			if (beg < i - w) beg = i - w;
 			if (end > i + w + 1) end = i + w + 1;
@@ -499,19 +514,10 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 		}
 		++calls;
 		score = max;
-		if (attempt == 0 && !(score == prev_score || max_off < (aw >> 1) + (aw >> 2))) { prev_score = score; continue; }
+		if (jb.w0 == 0 && attempt == 0 && !(score == prev_score || max_off < (aw >> 1) + (aw >> 2))) { prev_score = score; continue; }
 		break;
 	}
-	jb.score = score; jb.qle = max_j + 1; jb.tle = max_i + 1; jb.gtle = max_ie + 1; jb.gscore = gscore; jb.aw = aw;
-}
-
-__device__ __forceinline__ void ext_fill_score_rows(const ExtOpt &eo, uint32_t *sc_lo, uint32_t *sc_hi)
-{
-	if (threadIdx.x < 4) {
-		const int8_t *m = eo.mat + threadIdx.x * 5;
-		sc_lo[threadIdx.x] = (uint32_t)(uint8_t)m[0] | (uint32_t)(uint8_t)m[1] << 8 | (uint32_t)(uint8_t)m[2] << 16 | (uint32_t)(uint8_t)m[3] << 24;
-		sc_hi[threadIdx.x] = (uint32_t)(uint8_t)m[4];
-	}
+	jb.score = score; jb.qle = max_j + 1; jb.tle = max_i + 1; jb.gtle = max_ie + 1; jb.gscore = gscore; jb.aw = aw; jb.max_off = max_off;
 }
 
 // one warp per job of a round
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(128) k_ext_dp_warp(ExtOpt eo, const uint8_t *_
                                                      unsigned long long *cells_out, unsigned long long *calls_out)
 {
 	extern __shared__ uint32_t smem[];
-	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	__shared__ uint32_t sc_lo[5], sc_hi[5];
 	ext_fill_score_rows(eo, sc_lo, sc_hi);
 	__syncthreads();
 	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -533,6 +539,7 @@ __global__ void __launch_bounds__(128) k_ext_dp_warp(ExtOpt eo, const uint8_t *_
 	ext_dp_warp(eo, sc_lo, sc_hi, pac, codes, jb, ext_warp_scratch(smem, wib, qcap), cells, calls);
 	if (lane == 0) {
 		jp->score = jb.score; jp->qle = jb.qle; jp->tle = jb.tle; jp->gtle = jb.gtle; jp->gscore = jb.gscore; jp->aw = jb.aw;
+		jp->max_off = jb.max_off;
 		if (cells) atomicAdd(cells_out, (unsigned long long)cells);
 		atomicAdd(calls_out, (unsigned long long)calls);
 	}
@@ -548,7 +555,7 @@ __global__ void __launch_bounds__(128) k_ext_tail(ExtOpt eo, int64_t l_pac, cons
                                                   int32_t *n_regs, int qcap, unsigned long long *cells_out, unsigned long long *calls_out)
 {
 	extern __shared__ uint32_t smem[];
-	__shared__ uint32_t sc_lo[4], sc_hi[4];
+	__shared__ uint32_t sc_lo[5], sc_hi[5];
 	ext_fill_score_rows(eo, sc_lo, sc_hi);
 	__syncthreads();
 	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -647,47 +647,85 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	e->stats.n_extend_jobs += (int64_t)c.ext_calls;
 }
 
-__global__ void __launch_bounds__(128) k_extend_bytes(ExtOpt eo, int64_t n_jobs, b200_extend_job_t *jobs, const uint8_t *__restrict__ query,
-                                                      const uint8_t *__restrict__ target, int32_t *eh, int64_t stride, Counters *cnt)
-{
-	int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	int64_t cells = 0;
-	if (t < n_jobs) {
-		b200_extend_job_t j = jobs[t];
-		EhStrided acc = { eh + t, stride };
-		QFwd qa = { query + j.q_off };
-		TBytes ta = { target + j.t_off };
-		ExtOut o;
-		extend_core(j.qlen, qa, j.tlen, ta, eo, j.w, j.end_bonus, j.h0, acc, &o, &cells);
-		j.score = o.score; j.qle = o.qle; j.tle = o.tle; j.gtle = o.gtle; j.gscore = o.gscore; j.max_off = o.max_off;
-		jobs[t] = j;
-	}
-	warp_add(&cnt->ext_cells, cells);
-}
-
+// b200_ksw_extend2_batch: the caller's jobs run through the same three DP kernels as the pipeline (one job per lane,
+// one warp per job, general int32 path), with the target read from the caller's byte buffer and exactly one call per
+// job with the caller's band.  B200_EXT_KERNEL=lane|warp|big forces one kernel (used by the parity tests to fuzz each).
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
                         const uint8_t *query, int64_t qbytes, const uint8_t *target, int64_t tbytes)
 {
 	CK(cudaSetDevice(e->device));
 	if (n_jobs <= 0) return;
+	const char *force = getenv("B200_EXT_KERNEL");
+	const int mode = !force ? 0 : !strcmp(force, "lane") ? 1 : !strcmp(force, "warp") ? 2 : !strcmp(force, "big") ? 3 : 0;
+	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
+	std::vector<ExtJob> hj(n_jobs);
+	std::vector<int32_t> order(n_jobs);
+	int64_t cnt[EXT_N_CLASS] = { 0 }, pos[EXT_N_CLASS];
+	std::vector<uint8_t> cls(n_jobs);
 	int max_q = 0;
-	for (int64_t i = 0; i < n_jobs; ++i) max_q = std::max(max_q, jobs[i].qlen);
+	for (int64_t i = 0; i < n_jobs; ++i) {
+		const b200_extend_job_t &j = jobs[i];
+		ExtJob &x = hj[i];
+		memset(&x, 0, sizeof x);
+		x.qaddr = j.q_off; x.qstep = 1; x.f0 = j.t_off; x.fstep = 1; x.comp = 2;
+		x.qlen = j.qlen; x.tlen = j.tlen; x.h0 = j.h0; x.prev = -1; x.bonus = j.end_bonus; x.w0 = j.w > 0 ? j.w : 1;
+		int c = 0;
+		if ((long long)j.h0 + (long long)j.qlen * eo.max_sc >= 32768) c = EXT_N_CLASS - 1;
+		else while (j.qlen > class_cap[c]) ++c;
+		if (mode == 3) c = EXT_N_CLASS - 1;
+		cls[i] = (uint8_t)c; ++cnt[c];
+		max_q = std::max(max_q, j.qlen);
+	}
+	pos[0] = 0;
+	for (int c = 1; c < EXT_N_CLASS; ++c) pos[c] = pos[c - 1] + cnt[c - 1];
+	{ int64_t w[EXT_N_CLASS]; for (int c = 0; c < EXT_N_CLASS; ++c) w[c] = pos[c]; for (int64_t i = 0; i < n_jobs; ++i) order[w[cls[i]]++] = (int32_t)i; }
 	e->zero_counters();
-	b200_extend_job_t *dj = e->b_jobs.as<b200_extend_job_t>(n_jobs);
+	ExtJob *dj = e->b_xjobs.as<ExtJob>(n_jobs);
+	int32_t *d_ord = e->b_xord.as<int32_t>(n_jobs);
 	uint8_t *dq = e->b_q.as<uint8_t>(qbytes + 16), *dt = e->b_t.as<uint8_t>(tbytes + 16);
-	e->h2d(dj, jobs, sizeof(b200_extend_job_t) * n_jobs);
+	e->h2d(dj, hj.data(), sizeof(ExtJob) * n_jobs);
+	e->h2d(d_ord, order.data(), sizeof(int32_t) * n_jobs);
 	e->h2d(dq, query, qbytes);
 	e->h2d(dt, target, tbytes);
-	int64_t stride = (n_jobs + 31) & ~31ll;
-	int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (max_q + 2));
+	static bool attr_set = false;
+	if (!attr_set) {
+		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+		CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+		attr_set = true;
+	}
+	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
+	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
 	e->tic();
-	k_extend_bytes<<<grid_for(n_jobs, 128), 128, 0, e->stream>>>(eo, n_jobs, dj, dq, dt, d_eh, stride, e->d_cnt);
-	CK(cudaGetLastError());
-	e->stats.n_launches += 1;
+	for (int c = 0; c < EXT_N_CLASS; ++c) {
+		const int n = (int)cnt[c];
+		if (n == 0) continue;
+		const int qcap = c < EXT_N_CLASS - 1 ? class_cap[c] : max_q;
+		const int wpb = warps_for(qcap);
+		const bool lane_ok = c < EXT_N_CLASS - 1;
+		const bool use_warp = wpb && mode != 3 && (mode == 2 || !lane_ok || (mode == 0 && n < 8192));
+		if (use_warp)
+			k_ext_dp_warp<<<grid_for(n, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), e->stream>>>(eo, dt, dq, dj, d_ord + pos[c], n, qcap, d_cells, d_calls);
+		else if (lane_ok) {
+			const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
+			const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+			k_ext_dp<<<grid_for(n, threads), threads, per_warp * (threads / 32), e->stream>>>(eo, dt, dq, dj, d_ord + pos[c], n, qcap, d_cells, d_calls);
+		} else {
+			const int64_t stride = ((int64_t)n + 31) & ~31ll;
+			int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (max_q + 2));
+			k_ext_dp_big<<<grid_for(n, 128), 128, 0, e->stream>>>(eo, dt, dq, dj, d_ord + pos[c], n, d_eh, stride, d_cells, d_calls);
+		}
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+	}
 	e->stats.ms_k_extend += e->toc();
-	e->d2h(jobs, dj, sizeof(b200_extend_job_t) * n_jobs);
-	Counters c = e->read_counters();
-	e->stats.extend_cells += (int64_t)c.ext_cells;
+	e->d2h(hj.data(), dj, sizeof(ExtJob) * n_jobs);
+	Counters cc = e->read_counters();
+	for (int64_t i = 0; i < n_jobs; ++i) {
+		const ExtJob &x = hj[i];
+		b200_extend_job_t &j = jobs[i];
+		j.score = x.score; j.qle = x.qle; j.tle = x.tle; j.gtle = x.gtle; j.gscore = x.gscore; j.max_off = x.max_off;
+	}
+	e->stats.extend_cells += (int64_t)cc.ext_cells;
 	e->stats.n_extend_jobs += n_jobs;
 }
 

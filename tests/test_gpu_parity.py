@@ -76,9 +76,19 @@ def _run_align_batch(lib, cases):
     return out
 
 
-def test_extend_batch_vs_oracle(aligner, orc):
-    cases = fuzzgen.extend_cases(31, 20000) + fuzzgen.extend_cases(32, 2000, max_q=250, max_t=1100)
-    got = _run_extend_batch(aligner.lib, cases)
+@pytest.mark.parametrize("kernel", ["auto", "lane", "warp", "big"])
+def test_extend_batch_vs_oracle(aligner, orc, kernel):
+    """ksw_extend2 fuzz through the C ABI; every DP kernel of the extension stage is forced in turn (one job per lane with
+    packed 16-bit rows in shared memory, one warp per job with the max-plus scan, general int32 rows in global memory)"""
+    cases = fuzzgen.extend_cases(31, 12000) + fuzzgen.extend_cases(32, 2000, max_q=250, max_t=1100) + \
+        fuzzgen.extend_cases(33, 300, max_q=900, max_t=1500)
+    os.environ.pop("B200_EXT_KERNEL", None)
+    if kernel != "auto":
+        os.environ["B200_EXT_KERNEL"] = kernel
+    try:
+        got = _run_extend_batch(aligner.lib, cases)
+    finally:
+        os.environ.pop("B200_EXT_KERNEL", None)
     for c, g in zip(cases, got):
         a, b, od, ed, oi, ei = c["params"]
         want = orc.extend(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"], c["end_bonus"], c["zdrop"], c["h0"])[0]

@@ -528,9 +528,11 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 	std::sort(key.begin(), key.end());
 	for (uint64_t k : key) srt.push_back((int32_t)(uint32_t)k);
 	if (av->n != 0) die("mem_chain2aln: a non-empty region list must go through mem_process_seqs", nullptr);
-	std::vector<DReg> regs;
-	std::vector<int64_t> reg_off;
-	stage_extend(eng, make_ext_opt(opt), chain_off, dc, ds, srt, regs, reg_off);
+	ExtIn xin = { 1, chain_off.data(), dc.data(), 1, ds.data(), (int64_t)ds.size(), srt.data() };
+	ExtRegs xr;
+	stage_extend(eng, make_ext_opt(opt), xin, xr);
+	const DReg *regs = xr.regs;
+	const int64_t *reg_off = xr.reg_off;
 	for (int i = 0; i < (int)reg_off[1]; ++i) {
 		if (av->n == av->m) { av->m = av->m ? av->m << 1 : 2; av->a = (mem_alnreg_t *)realloc(av->a, av->m * sizeof(mem_alnreg_t)); }
 		mem_alnreg_t *a = &av->a[av->n++];

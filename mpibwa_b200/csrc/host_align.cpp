@@ -647,19 +647,27 @@ static int unique_sub(const mem_opt_t *opt, const RegVec &r)
 
 void pestat(const mem_opt_t *opt, int64_t l_pac, int n, const RegVec *regs, mem_pestat_t pes[4])
 {
-	int i, d, max;
+	int d, max;
 	std::vector<uint64_t> isize[4];
 	memset(pes, 0, 4 * sizeof(mem_pestat_t));
-	for (i = 0; i < n >> 1; ++i) {
-		int dir;
-		int64_t is;
-		const RegVec &r0 = regs[i << 1 | 0], &r1 = regs[i << 1 | 1];
-		if (r0.empty() || r1.empty()) continue;
-		if (unique_sub(opt, r0) > 0.8 * r0[0].score) continue;
-		if (unique_sub(opt, r1) > 0.8 * r1[0].score) continue;
-		if (r0[0].rid != r1[0].rid) continue;
-		dir = infer_dir(l_pac, r0[0].rb, r1[0].rb, &is);
-		if (is && is <= opt->max_ins) isize[dir].push_back(is);
+	{	// candidate insert sizes, gathered by the worker threads; the order does not matter because every use below goes
+		// through the sorted array
+		const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
+		std::vector<std::vector<uint64_t>> part((size_t)nt * 4);
+		parallel_for(nt, n >> 1, 4096, [&](int tid, int64_t b, int64_t e) {
+			for (int64_t i = b; i < e; ++i) {
+				int64_t is;
+				const RegVec &r0 = regs[i << 1 | 0], &r1 = regs[i << 1 | 1];
+				if (r0.empty() || r1.empty()) continue;
+				if (unique_sub(opt, r0) > 0.8 * r0[0].score) continue;
+				if (unique_sub(opt, r1) > 0.8 * r1[0].score) continue;
+				if (r0[0].rid != r1[0].rid) continue;
+				const int dir = infer_dir(l_pac, r0[0].rb, r1[0].rb, &is);
+				if (is && is <= opt->max_ins) part[(size_t)tid * 4 + dir].push_back(is);
+			}
+		});
+		for (d = 0; d < 4; ++d)
+			for (int t = 0; t < nt; ++t) isize[d].insert(isize[d].end(), part[(size_t)t * 4 + d].begin(), part[(size_t)t * 4 + d].end());
 	}
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n", "mem_pestat",
@@ -779,6 +787,17 @@ static inline int infer_bw(int l1, int l2, int score, int a, int q, int r)
 	w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
 	if (w < abs(l1 - l2)) w = abs(l1 - l2);
 	return w;
+}
+
+// Would mem_reg2aln run a banded DP for this region (as opposed to the no-gap path)?  Conservative: true when unsure.
+bool reg_needs_dp(const mem_opt_t *opt, const mem_alnreg_t *ar)
+{
+	if (ar->rb < 0 || ar->re < 0) return false;
+	int tmp = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
+	int w2 = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
+	w2 = w2 > tmp ? w2 : tmp;
+	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+	return global_needs_dp(ar->qe - ar->qb, ar->re - ar->rb, w2 < opt->w << 2 ? w2 : opt->w << 2);
 }
 
 void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query_,

@@ -89,6 +89,7 @@ int  infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist);
 // mem_pair, reference src/bwamem_pair.c:182-243
 int  pair_ends(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], RegVec a[2], int id,
                int *sub, int *n_sub, int z[2], int n_pri[2]);
+bool reg_needs_dp(const mem_opt_t *opt, const mem_alnreg_t *ar);
 // mem_reg2aln, reference src/bwamem.c:1089-1159
 void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query,
              const mem_alnreg_t *ar, Aln *out);

@@ -236,10 +236,14 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 
 	// ---- chaining + chain filtering on host threads
 	std::vector<std::vector<HChain>> chains(n);
+	std::vector<int32_t> n_chain_of(n), n_seed_of(n);
 	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
 			build_chains(opt, bns, seqs[i].l_seq, sd.seeds + sd.seed_off[i], sd.seed_off[i + 1] - sd.seed_off[i], sd.l_rep[i], chains[i]);
 			filter_chains(opt, chains[i]);
+			int32_t ns = 0;
+			for (auto &c : chains[i]) ns += (int32_t)c.seeds.size();
+			n_chain_of[i] = (int32_t)chains[i].size(); n_seed_of[i] = ns;
 		}
 	});
 	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] build+filter %.1f ms\n", now_ms() - t0);
@@ -249,11 +253,17 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		std::vector<SwJob> jobs;
 		std::vector<HSeed *> owner;
 		std::vector<int> long_reads;
+		std::vector<int8_t> len_rule(4096, 0);                   // per read length: 1 = the filter does not apply, 2 = it does
 		for (int i = 0; i < n; ++i) {
 			int l_query = seqs[i].l_seq;
-			if (l_query <= 0 || chains[i].empty()) continue;
-			double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
-			if (min_l > 0.05f * l_query) continue;
+			if (l_query <= 0 || n_chain_of[i] == 0) continue;
+			int8_t rule = l_query < 4096 ? len_rule[l_query] : 0;
+			if (rule == 0) {
+				double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
+				rule = min_l > 0.05f * l_query ? 1 : 2;
+				if (l_query < 4096) len_rule[l_query] = rule;
+			}
+			if (rule == 1) continue;
 			long_reads.push_back(i);
 			for (auto &c : chains[i])
 				for (HSeed &s : c.seeds) {
@@ -294,25 +304,28 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 				}
 				c.seeds.resize(k);
 			}
+			int32_t ns = 0;
+			for (auto &c : chains[i]) ns += (int32_t)c.seeds.size();
+			n_seed_of[i] = ns;
 		}
 	}
 
 	// ---- flatten chains for the extension stage (two sweeps: sizes, then a parallel fill at the prefix offsets)
-	std::vector<int32_t> chain_off(n + 1);
-	std::vector<DChain> dchains;
-	std::vector<DSeed> dseeds;
-	std::vector<int32_t> srt;
+	int32_t *chain_off = (int32_t *)stage_pinned(eng, PIN_CHAIN_OFF, sizeof(int32_t) * (n + 1));
+	DChain *dchains = nullptr;
+	DSeed *dseeds = nullptr;
+	int32_t *srt = nullptr;
+	ExtIn xin;
 	{
 		std::vector<int64_t> seed_at(n + 1);
 		int64_t nc = 0, ns = 0;
-		for (int i = 0; i < n; ++i) {
-			chain_off[i] = (int32_t)nc; seed_at[i] = ns;
-			nc += (int64_t)chains[i].size();
-			for (auto &c : chains[i]) ns += (int64_t)c.seeds.size();
-		}
+		for (int i = 0; i < n; ++i) { chain_off[i] = (int32_t)nc; seed_at[i] = ns; nc += n_chain_of[i]; ns += n_seed_of[i]; }
 		chain_off[n] = (int32_t)nc; seed_at[n] = ns;
 		if (nc > 0x7fffffffLL || ns > 0x7fffffffLL) { fprintf(stderr, "[mpibwa_b200] too many chains/seeds in one chunk\n"); abort(); }
-		dchains.resize(nc); dseeds.resize(ns); srt.resize(ns);
+		dchains = (DChain *)stage_pinned(eng, PIN_CHAINS, sizeof(DChain) * (nc + 1));
+		dseeds = (DSeed *)stage_pinned(eng, PIN_DSEEDS, sizeof(DSeed) * (ns + 1));
+		srt = (int32_t *)stage_pinned(eng, PIN_SRT, sizeof(int32_t) * (ns + 1));
+		xin.n_reads = n; xin.chain_off = chain_off; xin.chains = dchains; xin.n_chains = nc; xin.seeds = dseeds; xin.n_seeds = ns; xin.srt = srt;
 		parallel_for(nt, n, 2048, [&](int, int64_t b, int64_t e) {
 			std::vector<uint64_t> key;
 			for (int64_t i = b; i < e; ++i) {
@@ -347,9 +360,10 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
 
 	// ---- chain2aln / ksw_extend2 on the device
-	std::vector<DReg> dregs;
-	std::vector<int64_t> reg_off;
-	stage_extend(eng, make_ext_opt(opt), chain_off, dchains, dseeds, srt, dregs, reg_off);
+	ExtRegs xr;
+	stage_extend(eng, make_ext_opt(opt), xin, xr);
+	const DReg *dregs = xr.regs;
+	const int64_t *reg_off = xr.reg_off;
 	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
 
 	// ---- mem_sort_dedup_patch + ALT marking (reference src/bwamem.c:1073-1085)
@@ -373,7 +387,6 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 				if (p.rid >= 0 && bns->anns[p.rid].is_alt) p.is_alt = 1;
 		}
 	});
-	dregs.clear(); dregs.shrink_to_fit();
 	t1 = now_ms(); st.ms_regs_host = t1 - t0; t0 = t1;
 
 	// ---- insert-size statistics: the one chunk-global reduction (reference src/bwamem.c:1226-1229)
@@ -388,8 +401,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		const int n_pairs = n >> 1;
 		const int xtra_base = KSW_XSUBO | KSW_XSTART | (opt->min_seed_len * opt->a);
 		SwOpt so = make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins);
-		std::vector<int> pending(n_pairs);
-		for (int i = 0; i < n_pairs; ++i) pending[i] = i;
+		std::vector<int> pending;
 		std::vector<std::vector<RescueKey>> want(n_pairs);           // jobs to run this round, by pair
 		std::unordered_map<int, std::vector<RescueRes>> known;       // results carried over by deferred pairs
 		// round 0: every (anchor, orientation) not ruled out by the mate's pre-rescue regions
@@ -413,6 +425,8 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 				}
 			}
 		});
+		// a pair none of whose anchors asks for an alignment cannot change in mem_matesw: only the others are replayed
+		for (int i = 0; i < n_pairs; ++i) if (!want[i].empty()) pending.push_back(i);
 		while (!pending.empty()) {
 			std::vector<SwJob> jobs;
 			std::vector<RescueKey> job_key;
@@ -497,6 +511,10 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 			AlignCtx &cx = align_ctx();
 			cx.mode = AlignCtx::RECORD; cx.rec = &tjobs[tid];
 			for (int64_t u = b; u < e; ++u) {
+				bool any = false;                          // no region of the pair can ask for a DP: nothing to queue
+				for (int k = 0; k < per && !any; ++k)
+					for (const mem_alnreg_t &a : regs[u * per + k]) if (reg_needs_dp(opt, &a)) { any = true; break; }
+				if (!any) { uj[u] = { tid, (int32_t)tjobs[tid].size(), 0 }; continue; }
 				RegVec copy[2];
 				for (int k = 0; k < per; ++k) { copy[k] = regs[u * per + k]; cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
 				const int32_t start = (int32_t)tjobs[tid].size();

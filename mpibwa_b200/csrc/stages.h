@@ -48,11 +48,16 @@ void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_
 // contig id already resolved (rid < 0 = bridging, to be dropped by the caller), and l_rep per read.
 void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out);
 
+// page-locked host scratch owned by the engine (a handful of numbered slots); a slot's contents stay valid until the
+// same slot is requested again.  The pipeline assembles stage inputs in place there and reads stage outputs from there.
+void *stage_pinned(Engine *e, int slot, size_t bytes);
+enum { PIN_CHAIN_OFF = 0, PIN_CHAINS = 1, PIN_DSEEDS = 2, PIN_SRT = 3, PIN_REGS = 4, PIN_REG_OFF = 5, PIN_N_SLOTS = 8 };
+
 // extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r come back compacted
-// as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them.
-void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
-                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs,
-                  std::vector<int64_t> &reg_off);
+// as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them (arrays in the PIN_REGS / PIN_REG_OFF slots).
+struct ExtIn { int n_reads; const int32_t *chain_off; const DChain *chains; int64_t n_chains; const DSeed *seeds; int64_t n_seeds; const int32_t *srt; };
+struct ExtRegs { const DReg *regs; const int64_t *reg_off; };
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out);
 
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);

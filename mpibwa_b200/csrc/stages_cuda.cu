@@ -84,7 +84,7 @@ public:
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
 	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
-	PinBuf h_seeds, h_seed_off, h_lrep, h_codes, h_gres;
+	PinBuf h_seeds, h_seed_off, h_lrep, h_codes, h_gres, h_slot[PIN_N_SLOTS];
 	DevBuf b_gjobs, b_gres, b_grow, b_gz;
 	std::vector<cudaEvent_t> ev_pool;
 	static const int N_SIDE = 8;
@@ -204,6 +204,7 @@ void engine_destroy(Engine *e)
 		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
 	for (DevBuf *b : bufs) b->release();
 	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release(); e->h_gres.release();
+	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
 	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
 	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -498,21 +499,26 @@ void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
 /* ------------------------------------------------------------------ extension */
 
 // Rounds of (advance -> sort jobs by size -> batched DP) until every read has walked all its chains; see ext_rounds.cuh.
-void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
-                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int64_t> &reg_off)
+void *stage_pinned(Engine *e, int slot, size_t bytes)
 {
 	CK(cudaSetDevice(e->device));
-	const int n = (int)chain_off.size() - 1;
+	return e->h_slot[slot].need(bytes);
+}
+
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
+{
+	CK(cudaSetDevice(e->device));
+	const int n = in.n_reads;
 	if (n != e->n_reads) die("stage_extend: chain table does not match the uploaded reads");
-	regs.clear();
-	reg_off.assign(n + 1, 0);
-	if (n == 0) return;
+	int64_t *reg_off = (int64_t *)e->h_slot[PIN_REG_OFF].need(sizeof(int64_t) * (n + 2));
+	out.regs = nullptr; out.reg_off = reg_off;
+	if (n == 0) { reg_off[0] = 0; return; }
 	e->zero_counters();
 	int32_t *d_co = e->b_chain_off.as<int32_t>(n + 1);
-	DChain *d_ch = e->b_chains.as<DChain>(chains.size() + 1);
-	DSeed *d_se = e->b_dseeds.as<DSeed>(seeds.size() + 1);
-	int32_t *d_srt = e->b_srt.as<int32_t>(srt.size() + 1);
-	DReg *d_regs = e->b_regs.as<DReg>(seeds.size() + 1);
+	DChain *d_ch = e->b_chains.as<DChain>(in.n_chains + 1);
+	DSeed *d_se = e->b_dseeds.as<DSeed>(in.n_seeds + 1);
+	int32_t *d_srt = e->b_srt.as<int32_t>(in.n_seeds + 1);
+	DReg *d_regs = e->b_regs.as<DReg>(in.n_seeds + 1);
 	int32_t *d_nr = e->b_nregs.as<int32_t>(n + 1);
 	ExtState *d_state = e->b_xstate.as<ExtState>(n);
 	ExtJob *d_jobs = e->b_xjobs.as<ExtJob>(n);
@@ -520,10 +526,10 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	uint32_t *d_key = e->b_xkey.as<uint32_t>(n), *d_key2 = e->b_xkey2.as<uint32_t>(n);
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);
 	int32_t *d_ctr = e->b_xctr.as<int32_t>(16);
-	e->h2d(d_co, chain_off.data(), sizeof(int32_t) * (n + 1));
-	e->h2d(d_ch, chains.data(), sizeof(DChain) * chains.size());
-	e->h2d(d_se, seeds.data(), sizeof(DSeed) * seeds.size());
-	e->h2d(d_srt, srt.data(), sizeof(int32_t) * srt.size());
+	e->h2d(d_co, in.chain_off, sizeof(int32_t) * (n + 1));
+	e->h2d(d_ch, in.chains, sizeof(DChain) * in.n_chains);
+	e->h2d(d_se, in.seeds, sizeof(DSeed) * in.n_seeds);
+	e->h2d(d_srt, in.srt, sizeof(int32_t) * in.n_seeds);
 	static bool attr_set = false;
 	if (!attr_set) {
 		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -629,7 +635,7 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	CK(cudaMemsetAsync(d_nr + n, 0, sizeof(int32_t), e->stream));
 	int64_t *d_roff = e->b_soff.as<int64_t>(n + 2);
 	exclusive_scan(e, d_nr, d_roff, n + 1);
-	e->d2h(reg_off.data(), d_roff, sizeof(int64_t) * (n + 1));
+	e->d2h(reg_off, d_roff, sizeof(int64_t) * (n + 1));
 	e->sync();
 	const int64_t total = reg_off[n];
 	DReg *d_out = e->b_xout.as<DReg>(total + 1);
@@ -640,8 +646,9 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 	for (size_t i = 0; i < ev_used; i += 2) { float ms; CK(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1])); ms_dp += ms; }
 	e->stats.ms_k_extend_dp += ms_dp;
 	e->stats.n_extend_rounds += rounds;
-	regs.resize(total);
-	e->d2h(regs.data(), d_out, sizeof(DReg) * total);
+	DReg *regs = (DReg *)e->h_slot[PIN_REGS].need(sizeof(DReg) * (total + 1));
+	e->d2h(regs, d_out, sizeof(DReg) * total);
+	out.regs = regs;
 	Counters c = e->read_counters();
 	e->stats.extend_cells += (int64_t)c.ext_cells;
 	e->stats.n_extend_jobs += (int64_t)c.ext_calls;

@@ -22,6 +22,7 @@ public:
 	std::vector<int64_t> off;
 	std::vector<uint8_t> codes;
 	std::vector<uint8_t> staging;
+	std::vector<char> pinned[PIN_N_SLOTS];
 	std::vector<int64_t> seed_off;
 	std::vector<SeedRec> seeds;
 	std::vector<int32_t> l_rep;
@@ -156,12 +157,19 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &res)
 	res.seed_off = seed_off.data(); res.seeds = seeds.data(); res.l_rep = l_rep.data(); res.n_seeds = (int64_t)seeds.size();
 }
 
-void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain_off, const std::vector<DChain> &chains,
-                  const std::vector<DSeed> &seeds, std::vector<int32_t> &srt, std::vector<DReg> &regs, std::vector<int64_t> &reg_off)
+void *stage_pinned(Engine *e, int slot, size_t bytes)
 {
-	int n = (int)chain_off.size() - 1;
-	regs.clear();
-	reg_off.assign(n + 1, 0);
+	if (e->pinned[slot].size() < bytes) e->pinned[slot].resize(bytes + bytes / 4 + 64);
+	return e->pinned[slot].data();
+}
+
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &res)
+{
+	const int n = in.n_reads;
+	const int32_t *chain_off = in.chain_off;
+	const DChain *chains = in.chains;
+	std::vector<DReg> regs;
+	std::vector<int64_t> reg_off(n + 1, 0);
 	std::vector<int32_t> eh;
 	std::vector<DReg> tmp;
 	for (int r = 0; r < n; ++r) {
@@ -176,11 +184,16 @@ void stage_extend(Engine *e, const ExtOpt &eo, const std::vector<int32_t> &chain
 		for (int c = 0; c < nc; ++c) n_seeds += chains[chain_off[r] + c].n_seeds;
 		tmp.assign(n_seeds + 1, DReg());
 		int nr = chain2aln_read(eo, e->fm.pac, e->fm.l_pac, l_query, e->codes.data() + e->off[r], &chains[chain_off[r]], nc,
-		                        seeds.data(), srt.data(), acc, tmp.data(), &e->stats.extend_cells, &calls);
+		                        in.seeds, const_cast<int32_t *>(in.srt), acc, tmp.data(), &e->stats.extend_cells, &calls);
 		regs.insert(regs.end(), tmp.begin(), tmp.begin() + nr);
 		e->stats.n_extend_jobs += calls;
 	}
 	reg_off[n] = (int64_t)regs.size();
+	DReg *pr = (DReg *)stage_pinned(e, PIN_REGS, sizeof(DReg) * (regs.size() + 1));
+	int64_t *po = (int64_t *)stage_pinned(e, PIN_REG_OFF, sizeof(int64_t) * (n + 1));
+	memcpy(pr, regs.data(), sizeof(DReg) * regs.size());
+	memcpy(po, reg_off.data(), sizeof(int64_t) * (n + 1));
+	res.regs = pr; res.reg_off = po;
 }
 
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)

@@ -387,8 +387,12 @@ def main():
     roof = None
     if dom:
         kd = kern[dom]
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
-                "traffic": None, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()"}
+                "traffic": traffic, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()"}
     line = {
         "metric": "aligned 2x150bp read pairs/sec", "value": res_pairs_all / (res_ms_max * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps,

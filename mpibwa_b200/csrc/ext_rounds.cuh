@@ -285,21 +285,30 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 				if (end > jb.qlen) end = jb.qlen;
 				if (beg == 0) { h1 = jb.h0 - (eo.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
 				else h1 = 0;
-				for (j = beg; j < end; ++j) {
-					const uint32_t wd = S[j * 32];
-					const int q = Q[ext_qidx(j)];
-					const int sc = prmt_score(lo, hi, (uint32_t)q * 0x1111u + 0x8880u);
-					const int hd = (int)(wd & 0xffffu);
-					int e = (int)(wd >> 16);
-					int M = hd + sc;
-					M = hd ? M : 0;
-					const int h = ::max(::max(M, e), fgap);
-					hj = ::max(hj, h * 65536 + j);
-					e = ::max(::max(e - e_del, M - oe_del), 0);
-					fgap = ::max(::max(fgap - e_ins, M - oe_ins), 0);
-					S[j * 32] = (uint32_t)(e * 65536 + h1);
-					h1 = h;
+#define B200_EXT_CELL(J_, Q_) do { \
+					const uint32_t wd = S[(J_) * 32]; \
+					const int sc = prmt_score(lo, hi, (uint32_t)(Q_) * 0x1111u + 0x8880u); \
+					const int hd = (int)(wd & 0xffffu); \
+					int e = (int)(wd >> 16); \
+					int M = hd + sc; \
+					M = hd ? M : 0; \
+					const int h = ::max(::max(M, e), fgap); \
+					hj = ::max(hj, h * 65536 + (J_)); \
+					e = ::max(::max(e - e_del, M - oe_del), 0); \
+					fgap = ::max(::max(fgap - e_ins, M - oe_ins), 0); \
+					S[(J_) * 32] = (uint32_t)(e * 65536 + h1); \
+					h1 = h; } while (0)
+				// columns up to the next multiple of four, whole groups of four (one 32-bit load brings their query codes), rest
+				for (j = beg; j < end && (j & 3); ++j) B200_EXT_CELL(j, Q[ext_qidx(j)]);
+				for (; j + 4 <= end; j += 4) {
+					const uint32_t qw = *reinterpret_cast<const uint32_t *>(Q + ((j >> 2) << 7));
+					B200_EXT_CELL(j, qw & 0xffu);
+					B200_EXT_CELL(j + 1, (qw >> 8) & 0xffu);
+					B200_EXT_CELL(j + 2, (qw >> 16) & 0xffu);
+					B200_EXT_CELL(j + 3, qw >> 24);
 				}
+				for (; j < end; ++j) B200_EXT_CELL(j, Q[ext_qidx(j)]);
+#undef B200_EXT_CELL
 				if (end > beg) cells += end - beg;
 				S[end * 32] = (uint32_t)h1;
 				if (j == jb.qlen) {
@@ -415,6 +424,7 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 	const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0;
 	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
 	for (int j = lane; j < qlen; j += 32) S.Q[j] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+	const bool small = (long long)h0 + (long long)qlen * eo.max_sc < 32768 && qlen < 65536;
 	int prev_score = jb.prev, aw = eo.w, score = 0;
 	int max = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
 	for (int attempt = 0; attempt < 2; ++attempt) {
@@ -450,6 +460,7 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 			if (beg == 0) { h1 = h0 - (eo.o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; }
 			int fcar = 0, hcar = h1;                       // F entering / H left of the first column of the chunk
 			long long best = -1;
+			int best32 = -1;
 			int first_nz = 0x7fffffff, last_nz = -1, hlast = h1;
 			for (int cb = beg; cb < end; cb += 32) {
 				const int j = cb + lane;
@@ -473,8 +484,8 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 				if (lane == 0) hl = hcar;
 				if (act) {
 					S.H[j] = hl; S.E[j] = e;
-					const long long key = (long long)h << 32 | (unsigned)j;
-					best = key > best ? key : best;
+					if (small) { const int key = h * 65536 + j; best32 = ::max(best32, key); }
+					else { const long long key = (long long)h << 32 | (unsigned)j; best = key > best ? key : best; }
 				}
 				const unsigned nz = __ballot_sync(FULL, act && (hl | e) != 0);
 				if (nz) {
@@ -493,9 +504,16 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 				max_ie = gscore > hlast ? max_ie : i;
 				gscore = gscore > hlast ? gscore : hlast;
 			}
+			int m, mj;
+			if (small) {                                   // scores below 2^15: (h << 16 | j) fits one register
 #pragma unroll
-			for (int o = 16; o > 0; o >>= 1) { const long long v = __shfl_xor_sync(FULL, best, o); best = v > best ? v : best; }
-			const int m = best < 0 ? 0 : (int)(best >> 32), mj = best < 0 ? -1 : (int)(uint32_t)best;
+				for (int o = 16; o > 0; o >>= 1) best32 = ::max(best32, __shfl_xor_sync(FULL, best32, o));
+				m = best32 < 0 ? 0 : best32 >> 16; mj = best32 < 0 ? -1 : best32 & 0xffff;
+			} else {
+#pragma unroll
+				for (int o = 16; o > 0; o >>= 1) { const long long v = __shfl_xor_sync(FULL, best, o); best = v > best ? v : best; }
+				m = best < 0 ? 0 : (int)(best >> 32); mj = best < 0 ? -1 : (int)(uint32_t)best;
+			}
 			if (m == 0) break;
 			if (m > max) {
 				max = m; max_i = i; max_j = mj;

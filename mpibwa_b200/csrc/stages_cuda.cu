@@ -643,7 +643,12 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	CK(cudaGetLastError());
 	e->stats.n_launches += 1;
 	e->stats.ms_k_extend += e->toc();
-	for (size_t i = 0; i < ev_used; i += 2) { float ms; CK(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1])); ms_dp += ms; }
+	for (size_t i = 0; i < ev_used; i += 2) {
+		float ms;
+		CK(cudaEventElapsedTime(&ms, e->ev_pool[i], e->ev_pool[i + 1]));
+		ms_dp += ms;
+		if (dbg) fprintf(stderr, "[ext] DP of round %d: %.3f ms\n", (int)(i / 2), ms);
+	}
 	e->stats.ms_k_extend_dp += ms_dp;
 	e->stats.n_extend_rounds += rounds;
 	DReg *regs = (DReg *)e->h_slot[PIN_REGS].need(sizeof(DReg) * (total + 1));
@@ -997,19 +1002,26 @@ void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &
 	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
 	int64_t cnt[6] = { 0, 0, 0, 0, 0, 0 }, pos[6];
 	int qmax[6] = { 0, 0, 0, 0, 0, 0 };
-	std::vector<uint8_t> cls(n);
+	// counting sort by (class, band, target length / 16): lanes of a warp get regions of similar cost
+	const int NB = 6 * 256 * 64;
+	std::vector<int32_t> bucket(NB + 1, 0);
+	std::vector<int32_t> key(n);
 	for (int64_t i = 0; i < n; ++i) {
 		const GlobalJob &j = jobs[i];
 		const int need = 2 * j.wmax + 2, ql = j.qe - j.qb;
 		int k = 5;
 		if (ql <= 256) for (int c = 0; c < 5; ++c) if (need <= cls_S[c]) { k = c; break; }
-		cls[i] = (uint8_t)k; ++cnt[k];
+		++cnt[k];
 		qmax[k] = std::max(qmax[k], ql);
+		const int rl = (int)std::min<int64_t>((j.re - j.rb) >> 4, 63);
+		key[i] = (k * 256 + std::min(j.wmax, 255)) * 64 + rl;
+		++bucket[key[i] + 1];
 	}
+	for (int b = 0; b < NB; ++b) bucket[b + 1] += bucket[b];
 	pos[0] = 0;
 	for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
 	std::vector<int32_t> order(n);
-	{ int64_t w[6]; for (int k = 0; k < 6; ++k) w[k] = pos[k]; for (int64_t i = 0; i < n; ++i) order[w[cls[i]]++] = (int32_t)i; }
+	for (int64_t i = 0; i < n; ++i) order[bucket[key[i]]++] = (int32_t)i;
 	GlobalJob *dj = e->b_gjobs.as<GlobalJob>(n);
 	GlobalRes *dr = e->b_gres.as<GlobalRes>(n);
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);

@@ -22,6 +22,7 @@
 #include <unordered_map>
 #include <algorithm>
 #include <atomic>
+#include <thread>
 
 namespace b200 {
 
@@ -34,15 +35,17 @@ static double now_ms()
 /* ------------------------------------------------------------------ engine registry */
 
 static std::mutex g_mu;
-static Engine *g_engine = nullptr;
+static std::vector<Engine *> g_engines;     // [0] owns the index in HBM; the others are clones that share it (one per sub-batch lane)
 static const void *g_engine_key = nullptr;
 static int g_device = -1;
+static std::mutex g_gpu_mu;                  // one lane at a time drives the GPU; the other lane's host stage overlaps it
 
 Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (g_engine && g_engine_key == (const void *)bwt->bwt) return g_engine;
-	if (g_engine) engine_destroy(g_engine);
+	if (!g_engines.empty() && g_engine_key == (const void *)bwt->bwt) return g_engines[0];
+	for (size_t k = g_engines.size(); k-- > 0;) engine_destroy(g_engines[k]);
+	g_engines.clear();
 	int dev = g_device;
 	if (dev < 0) {
 		const char *lr = getenv("LOCAL_RANK");
@@ -50,19 +53,27 @@ Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 		int nd = engine_device_count();
 		if (nd > 0) dev %= nd;
 	}
-	g_engine = engine_create(bwt, bns, pac, dev);
+	g_engines.push_back(engine_create(bwt, bns, pac, dev));
 	g_engine_key = (const void *)bwt->bwt;
-	return g_engine;
+	return g_engines[0];
+}
+
+// engine of lane k (k = 0 is the primary engine)
+static Engine *engine_lane(int k)
+{
+	std::lock_guard<std::mutex> lk(g_mu);
+	while ((int)g_engines.size() <= k) g_engines.push_back(engine_clone(g_engines[0]));
+	return g_engines[k];
 }
 
 void engine_select_device(int dev) { g_device = dev; }
 void engine_release()
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (g_engine) engine_destroy(g_engine);
-	g_engine = nullptr; g_engine_key = nullptr;
+	for (size_t k = g_engines.size(); k-- > 0;) engine_destroy(g_engines[k]);
+	g_engines.clear(); g_engine_key = nullptr;
 }
-Engine *engine_current() { return g_engine; }
+Engine *engine_current() { return g_engines.empty() ? nullptr : g_engines[0]; }
 
 /* ------------------------------------------------------------------ option packing */
 
@@ -188,15 +199,40 @@ static const void *g_staged_key = nullptr;
 static int g_staged_n = 0;
 static int64_t g_staged_bases = 0;
 
-// encode the reads in place, flatten them and make them resident in HBM for the coming mem_process_seqs call
-void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs)
+// A chunk is cut into two (optionally four) sub-batches ("lanes") of whole pairs.  Each lane has its own engine (stream, scratch,
+// resident reads; the index is shared) and runs seeding -> chaining -> extension -> regions, and later rescue -> SAM, on
+// its own; two driver threads walk the lanes so that one lane's host stage overlaps the other lane's device stage.
+struct Lane { Engine *eng; int r0, n; };
+
+static std::vector<Lane> make_lanes(int n)
 {
-	Engine *eng = engine_for(bwt, bns, pac);
+	// two lanes by default: enough to overlap one lane's host stage with the other's device stage, while the kernels
+	// still see half a chunk per launch (four lanes gave the host another ~6 % but cost the DP kernels a third of their
+	// efficiency: every extension round has a latency floor).  B200_LANES / B200_LANE_MIN (reads per lane) override.
+	const int want = getenv("B200_LANES") ? atoi(getenv("B200_LANES")) : 2;
+	const int lane_min = getenv("B200_LANE_MIN") ? atoi(getenv("B200_LANE_MIN")) : 65536;
+	int k = want >= 4 ? 4 : want >= 2 ? 2 : 1;
+	while (k > 1 && n < k * lane_min) k >>= 1;
+	std::vector<Lane> lanes;
+	int r0 = 0;
+	for (int i = 0; i < k; ++i) {
+		int r1 = i + 1 == k ? n : (int)(((int64_t)n * (i + 1) / k) & ~1ll);
+		lanes.push_back({ engine_lane(i), r0, r1 - r0 });
+		r0 = r1;
+	}
+	return lanes;
+}
+
+// encode the reads of one lane in place, flatten them and make them resident in HBM
+static int64_t stage_lane_reads(const mem_opt_t *opt, const Lane &L, bseq1_t *seqs_all)
+{
+	const int n = L.n;
+	bseq1_t *seqs = seqs_all + L.r0;
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
 	std::vector<int64_t> off(n + 1);
 	off[0] = 0;
 	for (int i = 0; i < n; ++i) off[i + 1] = off[i] + seqs[i].l_seq;
-	uint8_t *codes = stage_read_buffer(eng, off[n] + 16);
+	uint8_t *codes = stage_read_buffer(L.eng, off[n] + 16);
 	parallel_for(nt, n, 4096, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
 			char *s = seqs[i].seq;
@@ -207,30 +243,59 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 			}
 		}
 	});
-	stage_upload_reads(eng, n, off.data(), codes);
-	g_staged_key = (const void *)seqs; g_staged_n = n; g_staged_bases = off[n];
+	stage_upload_reads(L.eng, n, off.data(), codes);
+	return off[n];
 }
 
-void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
-                  int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+// b200_stage_reads(): make the reads of the coming mem_process_seqs call resident ahead of time
+void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs)
 {
-	Engine *eng = engine_for(bwt, bns, pac);
-	Stats &st = engine_stats(eng);
-	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
+	engine_for(bwt, bns, pac);
+	int64_t bases = 0;
+	for (const Lane &L : make_lanes(n)) bases += stage_lane_reads(opt, L, seqs);
+	g_staged_key = (const void *)seqs; g_staged_n = n; g_staged_bases = bases;
+}
+
+template <class F>
+static void drive_lanes(std::vector<Lane> &lanes, F body)
+{
+	std::atomic<int> next(0);
+	auto run = [&]() { for (;;) { int k = next.fetch_add(1); if (k >= (int)lanes.size()) break; body(lanes[k]); } };
+	if (lanes.size() > 1) { std::thread other(run); run(); other.join(); }
+	else run();
+}
+
+#define GPU_STAGE(call) do { std::lock_guard<std::mutex> gpu_lk(g_gpu_mu); call; } while (0)
+
+void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                  int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0)
+{
+	Engine *eng0 = engine_for(bwt, bns, pac);
+	std::vector<Lane> lanes = make_lanes(n_all);
+	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
 	const double t_start = now_ms();
-	double t0 = t_start, t1;
 	const bool pe = (opt->flag & MEM_F_PE) != 0;
 	const int64_t l_pac = bns->l_pac;
-
-	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload - unless b200_stage_reads() already did
-	if (!(g_staged_key == (const void *)seqs && g_staged_n == n)) stage_reads(opt, bwt, bns, pac, n, seqs);
+	const bool staged = g_staged_key == (const void *)seqs_all && g_staged_n == n_all;
 	g_staged_key = nullptr;
-	st.n_reads = n; st.n_bases = g_staged_bases;
+	std::vector<RegVec> regs_all(n_all);
+
+	// ================= phase 1, per lane: reads -> seeds -> chains -> regions
+	drive_lanes(lanes, [&](Lane &L) {
+	Engine *eng = L.eng;
+	Stats &st = engine_stats(eng);
+	const int n = L.n;
+	bseq1_t *seqs = seqs_all + L.r0;
+	RegVec *regs = regs_all.data() + L.r0;
+	double t0 = now_ms(), t1;
+	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload - unless b200_stage_reads() already did
+	if (!staged) GPU_STAGE(st.n_bases = stage_lane_reads(opt, L, seqs_all));
+	st.n_reads = n;
 
 	// ---- seeding on the device
 	SeedOut sd;
-	stage_seed(eng, make_seed_opt(opt), sd);
+	GPU_STAGE(stage_seed(eng, make_seed_opt(opt), sd));
 	t1 = now_ms(); st.ms_seed = t1 - t0; t0 = t1;
 	st.n_seeds = sd.n_seeds;
 
@@ -286,7 +351,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		}
 		if (!jobs.empty()) {
 			std::vector<SwRes> res;
-			stage_sw(eng, make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins), jobs, res);
+			GPU_STAGE(stage_sw(eng, make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins), jobs, res));
 			for (size_t x = 0; x < owner.size(); ++x) owner[x]->score = res[x].score;
 		}
 		for (int i : long_reads) {
@@ -361,13 +426,12 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 
 	// ---- chain2aln / ksw_extend2 on the device
 	ExtRegs xr;
-	stage_extend(eng, make_ext_opt(opt), xin, xr);
+	GPU_STAGE(stage_extend(eng, make_ext_opt(opt), xin, xr));
 	const DReg *dregs = xr.regs;
 	const int64_t *reg_off = xr.reg_off;
 	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
 
 	// ---- mem_sort_dedup_patch + ALT marking (reference src/bwamem.c:1073-1085)
-	std::vector<RegVec> regs(n);
 	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
 		for (int64_t i = b; i < e; ++i) {
 			int nr = (int)(reg_off[i + 1] - reg_off[i]);
@@ -388,13 +452,26 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		}
 	});
 	t1 = now_ms(); st.ms_regs_host = t1 - t0; t0 = t1;
+	});
 
-	// ---- insert-size statistics: the one chunk-global reduction (reference src/bwamem.c:1226-1229)
+	// ================= insert-size statistics: the one chunk-global reduction (reference src/bwamem.c:1226-1229)
 	mem_pestat_t pes[4];
+	const double t_pes = now_ms();
 	if (pe) {
 		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
-		else pestat(opt, l_pac, n, regs.data(), pes);
+		else pestat(opt, l_pac, n_all, regs_all.data(), pes);
 	}
+	const double ms_pestat = now_ms() - t_pes;
+
+	// ================= phase 2, per lane: mate rescue -> pairing, mapQ, CIGAR, SAM text
+	drive_lanes(lanes, [&](Lane &L) {
+	Engine *eng = L.eng;
+	Stats &st = engine_stats(eng);
+	const int n = L.n;
+	bseq1_t *seqs = seqs_all + L.r0;
+	RegVec *regs = regs_all.data() + L.r0;
+	const int64_t n_processed = n_processed_all + L.r0;
+	double t0 = now_ms(), t1;
 
 	// ---- mate rescue: SW jobs on the device, then the sequential insert/skip logic replayed per pair
 	if (pe && !(opt->flag & MEM_F_NO_RESCUE)) {
@@ -452,7 +529,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 				first[x + 1] = (int64_t)jobs.size();
 			}
 			std::vector<SwRes> res;
-			if (!jobs.empty()) stage_sw(eng, so, jobs, res);
+			if (!jobs.empty()) GPU_STAGE(stage_sw(eng, so, jobs, res));
 			std::vector<char> done(pending.size(), 0);
 			std::vector<RescueKey> miss(pending.size());
 			std::vector<std::vector<RescueRes>> carry(pending.size());
@@ -541,7 +618,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		double tg = now_ms();
 		st.ms_sam_plan = tg - t0;
 		std::vector<GlobalRes> gres;
-		if (!gjobs.empty()) stage_global(eng, go, gjobs, zb, gres);
+		if (!gjobs.empty()) GPU_STAGE(stage_global(eng, go, gjobs, zb, gres));
 		st.ms_global = now_ms() - tg;
 		parallel_for(nt, n_units, 256, [&](int, int64_t b, int64_t e) {
 			AlignCtx &cx = align_ctx();
@@ -555,11 +632,30 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		});
 	}
 	t1 = now_ms(); st.ms_sam_host = t1 - t0;
-	st.ms_total = t1 - t_start;
+	});
+
+	// ================= merge the per-lane counters into the primary engine's record (b200_get_stats reads it)
+	Stats &st = engine_stats(eng0);
+	for (size_t k = 1; k < lanes.size(); ++k) {
+		const b200_stats_t &o = engine_stats(lanes[k].eng);
+		st.ms_seed += o.ms_seed; st.ms_sa += o.ms_sa; st.ms_chain_host += o.ms_chain_host; st.ms_extend += o.ms_extend;
+		st.ms_regs_host += o.ms_regs_host; st.ms_rescue += o.ms_rescue; st.ms_sam_host += o.ms_sam_host;
+		st.ms_k_smem += o.ms_k_smem; st.ms_k_sa += o.ms_k_sa; st.ms_k_extend += o.ms_k_extend; st.ms_k_sw += o.ms_k_sw; st.ms_k_global += o.ms_k_global;
+		st.n_reads += o.n_reads; st.n_bases += o.n_bases; st.n_intv += o.n_intv; st.n_seeds += o.n_seeds; st.n_chains += o.n_chains;
+		st.n_extend_jobs += o.n_extend_jobs; st.extend_cells += o.extend_cells; st.n_sw_jobs += o.n_sw_jobs; st.sw_cells += o.sw_cells;
+		st.n_global_jobs += o.n_global_jobs; st.global_cells += o.global_cells;
+		st.fm_occ_blocks += o.fm_occ_blocks; st.fm_sa_steps += o.fm_sa_steps; st.fm_sa_lookups += o.fm_sa_lookups;
+		st.n_launches += o.n_launches; st.h2d_bytes += o.h2d_bytes; st.d2h_bytes += o.d2h_bytes;
+		st.ms_k_extend_dp += o.ms_k_extend_dp; st.n_extend_rounds += o.n_extend_rounds;
+		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global;
+	}
+	st.ms_rescue += ms_pestat;
+	if (staged) st.n_bases = g_staged_bases;
+	st.ms_total = now_ms() - t_start;
 	if (bwa_verbose >= 3)
-		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f [plan %.0f, cigar stage %.0f])\n",
-		        "mem_process_seqs", n, st.ms_total * 1e-3, engine_kind(), st.ms_seed, st.ms_chain_host, st.ms_extend,
-		        st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s, %d lane%s; stage walls summed over lanes: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f [plan %.0f, cigar stage %.0f])\n",
+		        "mem_process_seqs", n_all, st.ms_total * 1e-3, engine_kind(), (int)lanes.size(), lanes.size() > 1 ? "s" : "", st.ms_seed, st.ms_chain_host,
+		        st.ms_extend, st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
 }
 
 } // namespace b200

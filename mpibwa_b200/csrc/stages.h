@@ -34,6 +34,7 @@ struct Stats : b200_stats_t {};
 class Engine;               // owns the device index, streams and scratch
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device);
+Engine *engine_clone(Engine *base);           // own stream + scratch + resident reads, index shared with base (destroy clones first)
 void    engine_destroy(Engine *e);
 Stats  &engine_stats(Engine *e);
 const char *engine_kind();                     // "cuda" or "hostemu"

@@ -73,6 +73,7 @@ public:
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	FmView fm;                     // device pointers
 	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_ctg_off = nullptr, *d_ctg_len = nullptr;
+	bool owns_index = true;        // false for clones made by engine_clone()
 	size_t bwt_bytes = 0;
 	Stats stats;
 	// resident reads of the current chunk
@@ -133,6 +134,9 @@ int engine_device_count()
 const char *engine_kind() { return "cuda"; }
 Stats &engine_stats(Engine *e) { return e->stats; }
 
+static void engine_set_l2_window(Engine *e);
+static void engine_make_streams(Engine *e);
+
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
 {
 	int nd = engine_device_count();
@@ -141,12 +145,7 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	Engine *e = new Engine();
 	e->device = device;
 	CK(cudaSetDevice(device));
-	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-	CK(cudaEventCreate(&e->ev0));
-	CK(cudaEventCreate(&e->ev1));
-	CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
-	for (int i = 0; i < Engine::N_SIDE; ++i) { CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming)); }
-	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
+	engine_make_streams(e);
 	e->bwt_bytes = (size_t)bwt->bwt_size * 4;
 	size_t sa_bytes = (size_t)bwt->n_sa * 8, pac_bytes = (size_t)(bns->l_pac / 4 + 1);
 	CK(cudaMalloc(&e->d_bwt, e->bwt_bytes + 64));
@@ -154,7 +153,6 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	CK(cudaMalloc(&e->d_pac, pac_bytes + 16));
 	CK(cudaMalloc(&e->d_ctg_off, sizeof(int64_t) * bns->n_seqs));
 	CK(cudaMalloc(&e->d_ctg_len, sizeof(int32_t) * bns->n_seqs));
-	CK(cudaMalloc(&e->d_cnt, sizeof(Counters)));
 	CK(cudaMemcpy(e->d_bwt, bwt->bwt, e->bwt_bytes, cudaMemcpyHostToDevice));
 	CK(cudaMemset((char *)e->d_bwt + e->bwt_bytes, 0, 64));
 	CK(cudaMemcpy(e->d_sa, bwt->sa, sa_bytes, cudaMemcpyHostToDevice));
@@ -175,9 +173,15 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
 
-	// L2 persistence window over the occ/BWT blocks (north star: "L2-persistence windows for the hot Occ blocks")
+	engine_set_l2_window(e);
+	return e;
+}
+
+// L2 persistence window over the occ/BWT blocks (north star: "L2-persistence windows for the hot Occ blocks")
+static void engine_set_l2_window(Engine *e)
+{
 	cudaDeviceProp prop;
-	CK(cudaGetDeviceProperties(&prop, device));
+	CK(cudaGetDeviceProperties(&prop, e->device));
 	if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
 		size_t persist = (size_t)prop.persistingL2CacheMaxSize;
 		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
@@ -191,6 +195,30 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
 		CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
 	}
+}
+
+static void engine_make_streams(Engine *e)
+{
+	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	CK(cudaEventCreate(&e->ev0));
+	CK(cudaEventCreate(&e->ev1));
+	CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+	for (int i = 0; i < Engine::N_SIDE; ++i) { CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming)); }
+	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
+	CK(cudaMalloc(&e->d_cnt, sizeof(Counters)));
+}
+
+Engine *engine_clone(Engine *base)
+{
+	Engine *e = new Engine();
+	e->device = base->device;
+	CK(cudaSetDevice(e->device));
+	engine_make_streams(e);
+	e->owns_index = false;
+	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len;
+	e->bwt_bytes = base->bwt_bytes;
+	e->fm = base->fm;
+	engine_set_l2_window(e);
 	return e;
 }
 
@@ -206,7 +234,8 @@ void engine_destroy(Engine *e)
 	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release(); e->h_gres.release();
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
 	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
-	cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_cnt);
+	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); }
+	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);
 	delete e;

@@ -40,6 +40,15 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
 }
+Engine *engine_clone(Engine *base)
+{
+	Engine *e = new Engine();
+	e->fm = base->fm;
+	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len;
+	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
+	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
+	return e;
+}
 void engine_destroy(Engine *e) { delete e; }
 Stats &engine_stats(Engine *e) { return e->stats; }
 const char *engine_kind() { return "hostemu"; }

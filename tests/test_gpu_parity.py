@@ -252,6 +252,15 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
     K = int(args[args.index("-K") + 1])
     got = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
     assert got == want
+    # the same with every chunk cut into four concurrently driven sub-batch lanes (as full-size chunks are)
+    os.environ["B200_LANE_MIN"] = "1000"
+    os.environ["B200_LANES"] = "4"
+    try:
+        got4 = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
+    finally:
+        os.environ.pop("B200_LANE_MIN", None)
+        os.environ.pop("B200_LANES", None)
+    assert got4 == want
     # through the stand-alone driver binary as well (the C host path)
     got2 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
     assert got2 == want

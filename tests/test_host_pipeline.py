@@ -47,3 +47,18 @@ def test_shapes_match_reference(hostemu_built, examples, tmp_path, shape):
     want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
     got = subprocess.run([drv, "-t", "1" if shape == "threads" else "8"] + args, capture_output=True, check=True).stdout
     assert got == want and want.count(b"\n") > 1000
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("lanes", ["4", "2"])
+def test_sub_batch_lanes_do_not_change_the_sam(hostemu_built, examples, tmp_path, lanes):
+    """a chunk cut into 4 (or 2) concurrently driven sub-batches gives the SAM of the reference, which never splits a chunk:
+    insert-size statistics stay chunk-global, read ids keep their chunk-wide values"""
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = [examples["idx"], _head(examples["R1_10K"], 1500, str(tmp_path / "a.fq")), _head(examples["R2_10K"], 1500, str(tmp_path / "b.fq"))]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    env = dict(os.environ, B200_LANE_MIN="500", B200_LANES=lanes)
+    r = subprocess.run([drv, "-t", "4", "-v", "3"] + args, capture_output=True, check=True, env=env)
+    assert r.stdout == want
+    assert (lanes + " lanes").encode() in r.stderr

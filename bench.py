@@ -285,13 +285,16 @@ def main():
     log("[bench] rank %d: %d pairs in %d chunks, %d host threads" % (rank, n1, len(chunks), n_threads))
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
+    max_pairs = max(e - b for b, e in chunks)
+    read_buf = [np.empty(max_pairs * rb + 1, dtype=np.uint8) for rb in (rb1, rb2)]     # the host's two fastq read buffers, reused
+
     def chunk_bytes(c):
         """private, writable copy of the chunk's fastq bytes (what the MPI host gets from its file read); the parse is in place"""
         b, e = chunks[c % len(chunks)]
         out = []
-        for fq, rb in ((fq1, rb1), (fq2, rb2)):
+        for k, (fq, rb) in enumerate(((fq1, rb1), (fq2, rb2))):
             nb = (e - b) * rb
-            a = np.empty(nb + 1, dtype=np.uint8)
+            a = read_buf[k]
             a[:nb] = np.frombuffer(fq, dtype=np.uint8, count=nb, offset=b * rb)
             a[nb] = 0
             out.append((a, nb))

@@ -317,7 +317,8 @@ struct SeedLane {
 // n_intv[r] = number of intervals of read r (unsorted, in out[r*cap ..]), or -(needed) when cap was too small.
 __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n_reads, const int64_t *__restrict__ off,
                                                     const uint8_t *__restrict__ codes, Intv *out, int cap, int quota, Q4 *spill,
-                                                    int32_t *n_intv, int *next_read, int *worst, unsigned long long *occ_blocks)
+                                                    int32_t *n_intv, int *next_read, int *worst, unsigned long long *occ_blocks,
+                                                    const int32_t *__restrict__ only_neg)     // non-null: only reads r with only_neg[r] < 0
 {
 	extern __shared__ uint32_t seed_sh[];
 	uint32_t *mlut = seed_sh;                          // 128 x 4 packed occ masks
@@ -340,6 +341,7 @@ __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n
 			}
 			r = atomicAdd(next_read, 1);
 			if (r >= n_reads) { r = -1; drained = true; break; }
+			if (only_neg && only_neg[r] >= 0) { r = -1; continue; }
 			ln.begin(so, (int)(off[r + 1] - off[r]), codes + off[r], out + (int64_t)r * cap);
 			need = ln.advance(fm, so, cap, L);
 		}

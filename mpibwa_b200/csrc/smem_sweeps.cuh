@@ -1,0 +1,310 @@
+// smem_sweeps.cuh - SMEM seeding split into HOMOGENEOUS sweeps (the throughput path of the seeding stage).
+//
+// In the per-read state machine of smem_kernel.cuh the lanes of a warp sit in different states (forward sweep, backward
+// sweep, greedy pass, transitions) and a third of the issued instructions are register shuffles between those code
+// paths.  The dependencies of mem_collect_intv (reference src/bwamem.c:114-162) allow a coarser split:
+//   * the start of the next bwt_smem1a call is the END of the longest forward match (ret = curr[0].info after the
+//     reversal, src/bwt.c:319-322), i.e. it is known after the FORWARD sweep alone - so all forward sweeps of pass 1 of
+//     a read can run back to back, each leaving its interval list (src/bwt.c:304-318) in a per-read strip in HBM;
+//   * the greedy third pass (bwt_seed_strategy1) depends on nothing but the read;
+//   * every backward sweep (src/bwt.c:326-345) depends only on its own list;
+//   * pass 2 re-seeds inside the long, rare SMEMs that pass 1 reported: same two sweeps again.
+// So: k_sweep_fwd<1> (pass-1 forward sweeps + pass 3), k_sweep_bwd, k_sweep_fwd<2>, k_sweep_bwd.  Inside one kernel every
+// lane is in the same steady state; the only divergent code is the short hand-over from one sweep to the next.  Lanes are
+// persistent and pull reads from a counter.  A read whose strip would overflow (pathological repeats) is flagged and
+// redone by the general state-machine kernel (k_seed_lanes), which has no such limit.
+// Host/device code: tests/hostemu runs the same four sweeps on the CPU against the plain restatement in fm_kernels.h.
+#pragma once
+#include "smem_kernel.cuh"
+
+namespace b200 {
+
+// strip of one read: records of 16 bytes; a sweep is a header {n, x, min_intv lo, min_intv hi} followed by its n entries
+// (packed like SeedList entries) in push order
+struct SweepStrip {
+	Q4 *base; int cap;
+	B200_HD static Q4 pack(uint64_t x0, uint64_t x1, uint64_t x2, int end)
+	{
+		Q4 v;
+		v.x = (uint32_t)x0; v.y = (uint32_t)x1; v.z = (uint32_t)x2;
+		v.w = (uint32_t)end | (uint32_t)(x0 >> 32) << 29 | (uint32_t)(x1 >> 32) << 30 | (uint32_t)(x2 >> 32) << 31;
+		return v;
+	}
+};
+
+struct FwdLane {
+	enum { NEXT, FWD, P3_NEXT, P3, DONE };
+	int len; const uint8_t *q; Intv *outp; Q4 *strip; int strip_cap;
+	int mode;                   // 1: pass-1 sweeps then pass 3; 2: pass-2 sweeps
+	int st, x, sx, i, c;
+	uint64_t k0, k1, k2, min_intv; int kend;
+	int wpos, hdr_pos, n, n_sweeps, over;
+	int n_out, old_n, k2i;
+
+	// k_first: first interval of `outp` that pass 2 may re-seed (the greedy seeds of pass 3 come before it and are not candidates)
+	B200_HD void begin(const SeedOpt &so, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
+	{
+		mode = mode_; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
+		n_out = n_out_; old_n = n_out_; k2i = k_first;
+		x = 0; wpos = 0; n_sweeps = 0; over = 0;
+		st = len >= so.min_seed_len ? NEXT : DONE;
+	}
+	B200_HD void set_intv(const FmView &fm, int b) { k0 = l2_at(fm, b) + 1; k2 = l2_at(fm, b + 1) - l2_at(fm, b); k1 = l2_at(fm, 3 - b) + 1; }
+	B200_HD void push()
+	{
+		if (wpos < strip_cap) strip[wpos] = SweepStrip::pack(k0, k1, k2, kend); else over = 1;
+		++wpos; ++n;
+	}
+	B200_HD void start_sweep(const FmView &fm, int x_, uint64_t mi)
+	{
+		set_intv(fm, q[x_]);
+		kend = x_ + 1; min_intv = mi < 1 ? 1 : mi; sx = x_; i = x_ + 1; n = 0;
+		hdr_pos = wpos++;
+		st = FWD;
+	}
+	B200_HD void end_sweep()      // the interval that could not be extended further closes the list; its end is the next x
+	{
+		push();
+		if (hdr_pos < strip_cap) { Q4 h; h.x = (uint32_t)n; h.y = (uint32_t)sx; h.z = (uint32_t)min_intv; h.w = (uint32_t)(min_intv >> 32); strip[hdr_pos] = h; }
+		else over = 1;
+		++n_sweeps;
+		x = kend;
+		st = NEXT;
+	}
+	B200_HD void emit3(int cap, uint64_t p0, uint64_t p1, uint64_t p2, int start, int end)
+	{
+		if (n_out < cap) { Intv v; v.x0 = p0; v.x1 = p1; v.x2 = p2; v.info = (uint64_t)start << 32 | (uint32_t)end; outp[n_out] = v; }
+		++n_out;
+	}
+	// slow path: runs until the lane needs an extension (true) or has finished its read (false)
+	B200_HD bool advance(const FmView &fm, const SeedOpt &so)
+	{
+		for (;;) {
+			switch (st) {
+			case NEXT:
+				if (mode == 1) {
+					if (x >= len) { x = 0; st = so.max_mem_intv > 0 ? P3_NEXT : DONE; break; }
+					if (q[x] > 3) { ++x; break; }
+					start_sweep(fm, x, 1);
+				} else {
+					if (k2i >= old_n) { st = DONE; break; }
+					const Intv p = outp[k2i++];
+					const int start = (int)(p.info >> 32), end = (int)(int32_t)p.info;
+					if (end - start < so.split_len || p.x2 > (uint64_t)so.split_width) break;
+					const int mid = (start + end) >> 1;
+					if (q[mid] > 3) break;
+					start_sweep(fm, mid, p.x2 + 1);
+				}
+				break;
+			case FWD:
+				if (i < len && q[i] < 4) { c = 3 - q[i]; return true; }
+				end_sweep();
+				break;
+			case P3_NEXT:
+				if (x >= len) { st = DONE; break; }
+				if (q[x] > 3) { ++x; break; }
+				set_intv(fm, q[x]);
+				sx = x; i = x + 1; st = P3;
+				break;
+			case P3:
+				if (i >= len) { st = DONE; break; }
+				if (q[i] > 3) { x = i + 1; st = P3_NEXT; break; }
+				c = 3 - q[i];
+				return true;
+			default:
+				return false;
+			}
+		}
+	}
+	// digest one extension; true = the next extension is already set up, false = go through advance()
+	B200_HD bool step(const SeedOpt &so, int cap, uint64_t o0, uint64_t o1, uint64_t o2)
+	{
+		if (st == FWD) {
+			if (o2 != k2) {
+				if (o2 < min_intv) { end_sweep(); return false; }
+				push();
+			}
+			k0 = o0; k1 = o1; k2 = o2; kend = i + 1; ++i;
+		} else {                                              // P3 (reference src/bwt.c:367-376)
+			if (o2 < (uint64_t)so.max_mem_intv && i - sx >= so.min_seed_len) {
+				if (o2 > 0) emit3(cap, o0, o1, o2, sx, i + 1);
+				x = i + 1; st = P3_NEXT;
+				return false;
+			}
+			k0 = o0; k1 = o1; k2 = o2; ++i;
+		}
+		if (i < len) { const int qn = q[i]; if (qn < 4) { c = 3 - qn; return true; } }
+		return false;
+	}
+};
+
+struct BwdLane {
+	enum { NEXT, ROW, BWD, DONE };
+	int len; const uint8_t *q; Intv *outp; const Q4 *strip;
+	int st, i, c, rpos, sweeps_left;
+	uint64_t k0, k1, k2, min_intv, last_x2; int kend;
+	int n_list, n_prev, j, n_curr, nm, last_start, n_out;
+
+	B200_HD void begin(int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_)
+	{
+		len = len_; q = q_; outp = outp_; strip = strip_; rpos = 0; sweeps_left = n_sweeps; n_out = n_out_;
+		st = NEXT;
+	}
+	B200_HD void emit(const SeedOpt &so, int cap, int start)
+	{
+		if (kend - start >= so.min_seed_len) {
+			if (n_out < cap) { Intv v; v.x0 = k0; v.x1 = k1; v.x2 = k2; v.info = (uint64_t)start << 32 | (uint32_t)kend; outp[n_out] = v; }
+			++n_out;
+		}
+		last_start = start; ++nm;
+	}
+	// L must map entry k of the CURRENT sweep: shared for k < quota, the strip itself beyond (see bind())
+	B200_HD void bind(SeedList &L) const { L.spill = const_cast<Q4 *>(strip) + rpos + L.quota; L.sstride = 1; }
+	B200_HD bool advance(const SeedOpt &so, int cap, SeedList &L)
+	{
+		for (;;) {
+			switch (st) {
+			case NEXT: {
+				if (sweeps_left == 0) { st = DONE; return false; }
+				--sweeps_left;
+				const Q4 h = strip[rpos];
+				++rpos;                                           // rpos -> first entry of the sweep
+				n_list = n_prev = (int)h.x; i = (int)h.y - 1; min_intv = (uint64_t)h.w << 32 | h.z;
+				bind(L);
+				const int ns = n_list < L.quota ? n_list : L.quota;   // stage the head of the list in shared memory
+				for (int k = 0; k < ns; ++k) {
+					const Q4 v = strip[rpos + k];
+					uint32_t *p = L.sh + (size_t)(k * 4) * L.stride;
+					p[0] = v.x; p[L.stride] = v.y; p[2 * L.stride] = v.z; p[3 * L.stride] = v.w;
+				}
+				rpos += n_list;                                   // (entries beyond the quota are read in place through L.spill)
+				nm = 0; last_start = 0;
+				st = ROW;
+				break;
+			}
+			case ROW: {
+				const int cc = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
+				if (cc < 0) {
+					if (nm == 0 || i + 1 < last_start) { L.get(n_list - 1, k0, k1, k2, kend); emit(so, cap, i + 1); }
+					st = NEXT;
+					break;
+				}
+				c = cc; j = 0; n_curr = 0; st = BWD;
+				break;
+			}
+			case BWD:
+				L.get(n_list - 1 - j, k0, k1, k2, kend);
+				return true;
+			default:
+				return false;
+			}
+		}
+	}
+	// digest one backward extension; true = next extension ready, false = advance() needed
+	B200_HD bool step(const SeedOpt &so, int cap, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
+	{
+		if (o2 < min_intv) {
+			if (n_curr == 0 && (nm == 0 || i + 1 < last_start)) emit(so, cap, i + 1);
+		} else if (n_curr == 0 || o2 != last_x2) {
+			L.set(n_list - 1 - n_curr, o0, o1, o2, kend);
+			++n_curr; last_x2 = o2;
+		}
+		if (++j == n_prev) {
+			if (n_curr == 0) { st = NEXT; return false; }
+			n_prev = n_curr; --i;
+			if (i < 0 || q[i] > 3) { st = ROW; return false; }
+			c = q[i]; j = 0; n_curr = 0;
+		}
+		L.get(n_list - 1 - j, k0, k1, k2, kend);
+		return true;
+	}
+};
+
+#if defined(__CUDACC__)
+struct SweepArgs {
+	FmView fm; SeedOpt so;
+	int n_reads; const int64_t *off; const uint8_t *codes;
+	Intv *out; int cap;
+	Q4 *strips; int strip_cap;      // strip of read r at strips + r * strip_cap
+	int32_t *n_intv;                // running count of reported intervals per read (may exceed cap: overflow)
+	int32_t *n_first;               // number of pass-3 seeds at the head of a read's output (pass 2 skips them)
+	int32_t *n_sweeps;              // sweeps left in the strip by the forward kernel; -1 = strip overflow, read needs the general kernel
+	int *next_read;                 // one counter per kernel of the sequence (the kernel is told which)
+	int *worst;                     // largest interval count over the reads whose output overflowed cap
+	int *n_over;                    // number of reads handed to the general kernel
+	unsigned long long *occ_blocks;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
+{
+	__shared__ uint32_t mlut[512];
+	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
+	__syncthreads();
+	FwdLane ln;
+	ln.st = FwdLane::DONE; ln.n_out = 0; ln.n_sweeps = 0; ln.over = 0;
+	int r = -1;
+	bool need = false, drained = false;
+	int64_t blocks = 0;
+	for (;;) {
+		while (!need && !drained) {
+			if (r >= 0) {
+				a.n_intv[r] = ln.n_out; a.n_sweeps[r] = ln.over ? -1 : ln.n_sweeps; if (MODE == 1) a.n_first[r] = ln.n_out;
+				if (ln.over) atomicAdd(a.n_over, 1);
+				if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out);
+			}
+			r = atomicAdd(a.next_read, 1);
+			if (r >= a.n_reads) { r = -1; drained = true; break; }
+			if (MODE == 2 && a.n_sweeps[r] < 0) { r = -1; continue; }       // already handed to the general kernel
+			ln.begin(a.so, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
+			         a.strips + (int64_t)r * a.strip_cap, a.strip_cap, MODE == 1 ? 0 : a.n_intv[r], MODE == 1 ? 0 : a.n_first[r]);
+			if (MODE == 2 && ln.n_out > a.cap) ln.st = FwdLane::DONE;        // output overflow: the whole batch is rerun anyway
+			need = ln.advance(a.fm, a.so);
+		}
+		if (!__any_sync(0xffffffffu, need)) break;
+		if (need) {
+			uint64_t o0, o1, o2;
+			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 0, ln.c, mlut, o0, o1, o2, blocks);
+			if (!ln.step(a.so, a.cap, o0, o1, o2)) need = ln.advance(a.fm, a.so);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);
+	if ((threadIdx.x & 31) == 0 && blocks) atomicAdd(a.occ_blocks, (unsigned long long)blocks);
+}
+
+__global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
+{
+	extern __shared__ uint32_t sweep_sh[];
+	uint32_t *mlut = sweep_sh;
+	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
+	__syncthreads();
+	SeedList L;
+	L.sh = sweep_sh + 512 + threadIdx.x; L.stride = 128; L.quota = quota; L.spill = nullptr; L.sstride = 1;
+	BwdLane ln;
+	ln.st = BwdLane::DONE; ln.n_out = 0;
+	int r = -1;
+	bool need = false, drained = false;
+	int64_t blocks = 0;
+	for (;;) {
+		while (!need && !drained) {
+			if (r >= 0) { a.n_intv[r] = ln.n_out; if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out); }
+			r = atomicAdd(a.next_read, 1);
+			if (r >= a.n_reads) { r = -1; drained = true; break; }
+			const int ns = a.n_sweeps[r];
+			if (ns <= 0) { r = -1; continue; }
+			ln.begin((int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r]);
+			need = ln.advance(a.so, a.cap, L);
+		}
+		if (!__any_sync(0xffffffffu, need)) break;
+		if (need) {
+			uint64_t o0, o1, o2;
+			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, mlut, o0, o1, o2, blocks);
+			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) need = ln.advance(a.so, a.cap, L);
+		}
+	}
+	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);
+	if ((threadIdx.x & 31) == 0 && blocks) atomicAdd(a.occ_blocks, (unsigned long long)blocks);
+}
+#endif
+
+} // namespace b200

@@ -14,6 +14,7 @@
 #include "util.h"
 #include "ext_rounds.cuh"
 #include "smem_kernel.cuh"
+#include "smem_sweeps.cuh"
 #include "sw_warp_kernel.cuh"
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
@@ -81,6 +82,7 @@ public:
 	std::vector<int64_t> h_off;
 	DevBuf d_off, d_codes;
 	// scratch
+	DevBuf b_strips, b_nfirst, b_nsweeps;
 	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
@@ -234,6 +236,7 @@ void engine_destroy(Engine *e)
 	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release(); e->h_gres.release();
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
 	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
+	e->b_strips.release(); e->b_nfirst.release(); e->b_nsweeps.release();
 	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); }
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -389,16 +392,52 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	int *ctr = e->b_xctr.as<int>(16);
 	const int spill_per = std::max(0, max_len + 2 - quota);
 	Q4 *spill = e->b_scr.as<Q4>((size_t)grid * threads * spill_per + 1);
+	// throughput path: the four homogeneous sweeps of smem_sweeps.cuh; the general state machine redoes the (rare) reads
+	// whose sweep strip overflowed.  B200_SEED_KERNEL=lanes forces the general kernel for every read (parity tests).
+	const bool use_sweeps = !(getenv("B200_SEED_KERNEL") && !strcmp(getenv("B200_SEED_KERNEL"), "lanes"));
+	static int bwd_blocks_per_sm = 0, fwd_blocks_per_sm = 0;
+	if (use_sweeps && !bwd_blocks_per_sm) {
+		CK(cudaFuncSetAttribute(k_sweep_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, k_sweep_bwd, threads, sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_blocks_per_sm, k_sweep_fwd<1>, threads, 0));
+		if (bwd_blocks_per_sm < 1 || fwd_blocks_per_sm < 1) die("sweep kernels do not fit an SM");
+	}
+	const int strip_cap = getenv("B200_SEED_STRIP") ? atoi(getenv("B200_SEED_STRIP")) : 3 * max_len + 8;   // (override: tests force overflows)
 	for (;;) {
 		Intv *out = e->b_intv.as<Intv>((size_t)n * cap);
-		CK(cudaMemsetAsync(ctr, 0, 2 * sizeof(int), e->stream));
-		k_seed_lanes<<<grid, threads, sh_bytes, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, quota, spill, n_intv, ctr, ctr + 1,
-			&e->d_cnt->occ_blocks);
-		CK(cudaGetLastError());
-		e->stats.n_launches += 1;
-		int h[2];
-		CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
-		e->sync();
+		CK(cudaMemsetAsync(ctr, 0, 8 * sizeof(int), e->stream));
+		int h[8];
+		if (use_sweeps) {
+			SweepArgs a;
+			a.fm = e->fm; a.so = so; a.n_reads = n; a.off = d_off + r0; a.codes = d_codes; a.out = out; a.cap = cap;
+			a.strips = e->b_strips.as<Q4>((size_t)n * strip_cap + 1); a.strip_cap = strip_cap;
+			a.n_intv = n_intv; a.n_first = e->b_nfirst.as<int32_t>(n + 1); a.n_sweeps = e->b_nsweeps.as<int32_t>(n + 1);
+			a.worst = ctr + 1; a.n_over = ctr + 2; a.occ_blocks = &e->d_cnt->occ_blocks;
+			const int gf = std::min(n_sm * fwd_blocks_per_sm, grid_for(n, threads)), gb = std::min(n_sm * bwd_blocks_per_sm, grid_for(n, threads));
+			a.next_read = ctr + 3; k_sweep_fwd<1><<<gf, threads, 0, e->stream>>>(a);
+			a.next_read = ctr + 4; k_sweep_bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			a.next_read = ctr + 5; k_sweep_fwd<2><<<gf, threads, 0, e->stream>>>(a);
+			a.next_read = ctr + 6; k_sweep_bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			CK(cudaGetLastError());
+			e->stats.n_launches += 4;
+			CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+			e->sync();
+			if (h[2] > 0) {                     // strip overflow: those reads go through the general state machine
+				k_seed_lanes<<<grid, threads, sh_bytes, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, quota, spill, n_intv, ctr, ctr + 1,
+					&e->d_cnt->occ_blocks, a.n_sweeps);
+				CK(cudaGetLastError());
+				e->stats.n_launches += 1;
+				CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+				e->sync();
+			}
+		} else {
+			k_seed_lanes<<<grid, threads, sh_bytes, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, quota, spill, n_intv, ctr, ctr + 1,
+				&e->d_cnt->occ_blocks, nullptr);
+			CK(cudaGetLastError());
+			e->stats.n_launches += 1;
+			CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
+			e->sync();
+		}
 		if (h[1] <= cap) break;                 // no read needed more than cap intervals
 		cap = h[1] + 8;                         // rare (very repetitive reads): run the sub-batch again with room for the worst
 	}

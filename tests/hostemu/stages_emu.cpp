@@ -5,6 +5,7 @@
 #include "../../mpibwa_b200/csrc/stages.h"
 #include "../../mpibwa_b200/csrc/util.h"
 #include "../../mpibwa_b200/csrc/smem_kernel.cuh"
+#include "../../mpibwa_b200/csrc/smem_sweeps.cuh"
 #include <cstdio>
 #include <algorithm>
 #include <cstring>
@@ -116,6 +117,43 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 			if (!same && getenv("B200_EMU_DEBUG")) for (int i = 0; i < n; ++i) fprintf(stderr, "%d: v1 %llu %llu %llu %d-%d | v2 %llu %llu %llu %d-%d\n", i,
 				(unsigned long long)out[i].x0, (unsigned long long)out[i].x1, (unsigned long long)out[i].x2, (int)(out[i].info >> 32), (int)(uint32_t)out[i].info,
 				(unsigned long long)out2[i].x0, (unsigned long long)out2[i].x1, (unsigned long long)out2[i].x2, (int)(out2[i].info >> 32), (int)(uint32_t)out2[i].info);
+			if (same && len >= so.min_seed_len) {     // the four homogeneous sweeps of smem_sweeps.cuh (throughput path of the CUDA stage)
+				const int strip_cap = 3 * len + 8;
+				std::vector<Q4> strip(strip_cap);
+				std::vector<Intv> out3(cap2);
+				std::vector<uint32_t> sh2(4 * quota);
+				int n_out = 0, n_first = 0, n_sw = 0;
+				for (int pass = 1; pass <= 2 && n_sw >= 0; ++pass) {
+					FwdLane f;
+					f.begin(so, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
+					bool nd = f.advance(e->fm, so);
+					while (nd) {
+						uint64_t o0, o1, o2;
+						fm_extend_sel(e->fm, f.k0, f.k1, f.k2, 0, f.c, nullptr, o0, o1, o2, blocks);
+						if (!f.step(so, cap2, o0, o1, o2)) nd = f.advance(e->fm, so);
+					}
+					n_out = f.n_out; n_sw = f.over ? -1 : f.n_sweeps;
+					if (pass == 1) n_first = n_out;
+					if (n_sw <= 0) continue;
+					SeedList L2; L2.sh = sh2.data(); L2.stride = 1; L2.quota = quota; L2.spill = nullptr; L2.sstride = 1;
+					BwdLane b;
+					b.begin(len, codes + off[r], out3.data(), strip.data(), n_sw, n_out);
+					nd = b.advance(so, cap2, L2);
+					while (nd) {
+						uint64_t o0, o1, o2;
+						fm_extend_sel(e->fm, b.k0, b.k1, b.k2, 1, b.c, nullptr, o0, o1, o2, blocks);
+						if (!b.step(so, cap2, L2, o0, o1, o2)) nd = b.advance(so, cap2, L2);
+					}
+					n_out = b.n_out;
+				}
+				bool same3 = n_sw < 0 || n_out == n;      // n_sw < 0: strip overflow, the read goes to the general kernel instead
+				if (same3 && n_sw >= 0) {
+					std::sort(out3.begin(), out3.begin() + n, [](const Intv &a, const Intv &b) { return a.info < b.info; });
+					for (int i = 0; i < n && same3; ++i)
+						same3 = out3[i].x0 == out[i].x0 && out3[i].x1 == out[i].x1 && out3[i].x2 == out[i].x2 && out3[i].info == out[i].info;
+				}
+				if (!same3) { fprintf(stderr, "[hostemu] seeding sweeps disagree with fm_collect_intv on read %d (%d vs %d intervals, sweeps %d)\n", r, n_out, n, n_sw); abort(); }
+			}
 			if (!same) { fprintf(stderr, "[hostemu] seeding state machine disagrees with fm_collect_intv on read %d (%d vs %d intervals)\n", r, ln.n_out, n); abort(); }
 		}
 		intv.insert(intv.end(), out.begin(), out.begin() + n);

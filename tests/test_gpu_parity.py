@@ -163,7 +163,14 @@ def _reads_as_codes(path, n):
     return out
 
 
-def test_seeding_and_sa_vs_oracle(aligner, orc, examples):
+@pytest.mark.parametrize("kernel", ["sweeps", "lanes", "sweeps_overflow"])
+def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
+    # the homogeneous sweep kernels (default), the general per-lane state machine, and sweeps with strips so small that
+    # most reads overflow and are redone by the general kernel
+    if kernel == "lanes":
+        monkeypatch.setenv("B200_SEED_KERNEL", "lanes")
+    if kernel == "sweeps_overflow":
+        monkeypatch.setenv("B200_SEED_STRIP", "40")
     idxf = OL.IndexFiles(examples["idx"])
     rng = np.random.default_rng(9)
     reads = _reads_as_codes(examples["R1_10K"], 400)

@@ -228,7 +228,9 @@ def kernel_table(agg, K, i32_peak, hbm_peak):
         kern["ksw_global2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_global"] / K, "cells_per_step": agg["global_cells"] / K,
                                "jobs_per_step": agg["n_global_jobs"] / K, "gcups": gc, "achieved": gc * 14,
                                "unit": "Gop/s (14 int32 ops per cell, src/ksw.c:546-566)", "peak": i32_peak, "frac": (gc * 14 / i32_peak) if i32_peak else None}
-
+    if agg.get("ms_k_chain", 0) > 0:
+        kern["chaining"] = {"bound": "latency (one read per lane, pointer chasing)", "ms_per_step": agg["ms_k_chain"] / K,
+                            "seeds_per_step": agg["n_seeds"] / K, "chains_per_step": agg["n_chains"] / K}
     return kern
 
 
@@ -300,9 +302,9 @@ def main():
             out.append((a, nb))
         return out[0], out[1], e - b
 
-    STAT_KEYS = ("ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
+    STAT_KEYS = ("ms_k_chain", "n_seeds", "n_chains", "ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
-                 "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv", "n_seeds", "n_chains",
+                 "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv",
                  "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells")
 
     def e2e_step(c):

@@ -301,6 +301,7 @@ typedef struct {
 	double ms_k_extend_dp;    /* CUDA-event time of the ksw_extend2 DP kernels alone (ms_k_extend = whole extension stage) */
 	int64_t n_extend_rounds;
 	double ms_sam_plan, ms_global;   /* inside ms_sam_host: the dry-run sweep that queues the CIGAR jobs; the device CIGAR stage (wall) */
+	double ms_k_chain;        /* CUDA-event time of the chaining kernels (ms_chain_host is the wall of the whole chaining stage, host or device) */
 } b200_stats_t;
 void b200_get_stats(b200_stats_t *out);
 /* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP

@@ -97,6 +97,23 @@ SwOpt make_sw_opt(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_i
 	return s;
 }
 
+ChainOpt make_chain_opt(const mem_opt_t *opt)
+{
+	ChainOpt c;
+	c.a = opt->a; c.o_del = opt->o_del; c.e_del = opt->e_del; c.o_ins = opt->o_ins; c.e_ins = opt->e_ins; c.w = opt->w;
+	c.min_seed_len = opt->min_seed_len; c.max_chain_gap = opt->max_chain_gap; c.min_chain_weight = opt->min_chain_weight;
+	c.max_chain_extend = opt->max_chain_extend; c.mask_level = opt->mask_level; c.drop_ratio = opt->drop_ratio;
+	return c;
+}
+
+// mem_flt_chained_seeds (reference src/bwamem.c:598-615) returns at once when min_l > MEM_SHORT_EXT * l_query, i.e. for
+// every read shorter than ~730 bases with default options; batches with a read to which it applies take the host chaining
+static bool seed_sw_filter_applies(const mem_opt_t *opt, int l_query)
+{
+	double min_l = opt->min_chain_weight ? 1.1f * opt->min_chain_weight : 5.5f * log(l_query);
+	return !(min_l > 0.05f * l_query);
+}
+
 SeedOpt make_seed_opt(const mem_opt_t *opt)
 {
 	SeedOpt s;
@@ -293,12 +310,39 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	if (!staged) GPU_STAGE(st.n_bases = stage_lane_reads(opt, L, seqs_all));
 	st.n_reads = n;
 
+	// ---- chaining on the device unless a read is long enough for mem_flt_chained_seeds (B200_CHAIN=host forces the host path)
+	bool dev_chain = !(getenv("B200_CHAIN") && !strcmp(getenv("B200_CHAIN"), "host"));
+	{
+		std::vector<int8_t> len_rule(4096, 0);
+		for (int i = 0; i < n && dev_chain; ++i) {
+			const int l = seqs[i].l_seq;
+			if (l < opt->min_seed_len) continue;
+			int8_t rule = l < 4096 ? len_rule[l] : 0;
+			if (rule == 0) { rule = seed_sw_filter_applies(opt, l) ? 2 : 1; if (l < 4096) len_rule[l] = rule; }
+			if (rule == 2) dev_chain = false;
+		}
+	}
+
 	// ---- seeding on the device
 	SeedOut sd;
-	GPU_STAGE(stage_seed(eng, make_seed_opt(opt), sd));
+	const bool chain_check = dev_chain && getenv("B200_CHAIN") && !strcmp(getenv("B200_CHAIN"), "check");   // run both, compare, abort on a difference
+	GPU_STAGE(stage_seed(eng, make_seed_opt(opt), sd, dev_chain && !chain_check));
 	t1 = now_ms(); st.ms_seed = t1 - t0; t0 = t1;
 	st.n_seeds = sd.n_seeds;
 
+	ExtIn xin;
+	std::vector<int32_t> chk_co, chk_srt;
+	std::vector<DChain> chk_ch;
+	std::vector<DSeed> chk_se;
+	if (dev_chain) {
+		GPU_STAGE(stage_chain(eng, make_chain_opt(opt), xin, chain_check));
+		st.n_chains = xin.n_chains;
+		if (chain_check) {
+			chk_co.assign(xin.chain_off, xin.chain_off + n + 1); chk_ch.assign(xin.chains, xin.chains + xin.n_chains);
+			chk_se.assign(xin.seeds, xin.seeds + xin.n_seeds); chk_srt.assign(xin.srt, xin.srt + xin.n_seeds);
+		}
+	}
+	if (!dev_chain || chain_check) {
 	// ---- chaining + chain filtering on host threads
 	std::vector<std::vector<HChain>> chains(n);
 	std::vector<int32_t> n_chain_of(n), n_seed_of(n);
@@ -380,7 +424,6 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	DChain *dchains = nullptr;
 	DSeed *dseeds = nullptr;
 	int32_t *srt = nullptr;
-	ExtIn xin;
 	{
 		std::vector<int64_t> seed_at(n + 1);
 		int64_t nc = 0, ns = 0;
@@ -422,6 +465,21 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	}
 	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] +flatten %.1f ms\n", now_ms() - t0);
 	chains.clear(); chains.shrink_to_fit();
+	xin.on_device = false;
+	if (chain_check) {
+		bool same = (int64_t)chk_ch.size() == xin.n_chains && (int64_t)chk_se.size() == xin.n_seeds && !memcmp(chk_co.data(), chain_off, sizeof(int32_t) * (n + 1));
+		for (int64_t k = 0; same && k < xin.n_chains; ++k) {
+			const DChain &x = chk_ch[k], &y = dchains[k];
+			same = x.rmax0 == y.rmax0 && x.rmax1 == y.rmax1 && x.seed_beg == y.seed_beg && x.n_seeds == y.n_seeds && x.rid == y.rid && !memcmp(&x.frac_rep, &y.frac_rep, 4);
+		}
+		for (int64_t k = 0; same && k < xin.n_seeds; ++k) {
+			const DSeed &x = chk_se[k], &y = dseeds[k];
+			same = x.rbeg == y.rbeg && x.qbeg == y.qbeg && x.len == y.len && x.score == y.score && chk_srt[k] == srt[k];
+		}
+		if (!same) { fprintf(stderr, "[mpibwa_b200] B200_CHAIN=check: the chaining stage disagrees with the host chaining (%lld vs %lld chains, %lld vs %lld seeds)\n",
+			(long long)chk_ch.size(), (long long)xin.n_chains, (long long)chk_se.size(), (long long)xin.n_seeds); abort(); }
+	}
+	}
 	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
 
 	// ---- chain2aln / ksw_extend2 on the device
@@ -647,7 +705,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		st.fm_occ_blocks += o.fm_occ_blocks; st.fm_sa_steps += o.fm_sa_steps; st.fm_sa_lookups += o.fm_sa_lookups;
 		st.n_launches += o.n_launches; st.h2d_bytes += o.h2d_bytes; st.d2h_bytes += o.d2h_bytes;
 		st.ms_k_extend_dp += o.ms_k_extend_dp; st.n_extend_rounds += o.n_extend_rounds;
-		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global;
+		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global; st.ms_k_chain += o.ms_k_chain;
 	}
 	st.ms_rescue += ms_pestat;
 	if (staged) st.n_bases = g_staged_bases;

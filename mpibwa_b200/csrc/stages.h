@@ -12,10 +12,9 @@
 #include "ext_kernels.h"
 #include "sw_kernels.h"
 #include "global_kernels.h"
+#include "chain_kernels.h"
 
 namespace b200 {
-
-struct SeedRec { int64_t rbeg; uint16_t qbeg, len; int32_t rid; };   // 16 bytes; reads are shorter than 65536 bases
 
 // result of stage_seed: arrays owned by the engine (page-locked on the CUDA engine), valid until the next stage_seed call
 struct SeedOut { const int64_t *seed_off; const SeedRec *seeds; const int32_t *l_rep; int64_t n_seeds; };
@@ -47,7 +46,8 @@ void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_
 
 // seeding + SA look-up: per read the seed list in mem_chain() order (interval order x SA order), with the
 // contig id already resolved (rid < 0 = bridging, to be dropped by the caller), and l_rep per read.
-void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out);
+// With keep_on_device the seed list stays in HBM for stage_chain() and only out.n_seeds is filled in.
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out, bool keep_on_device = false);
 
 // page-locked host scratch owned by the engine (a handful of numbered slots); a slot's contents stay valid until the
 // same slot is requested again.  The pipeline assembles stage inputs in place there and reads stage outputs from there.
@@ -56,9 +56,15 @@ enum { PIN_CHAIN_OFF = 0, PIN_CHAINS = 1, PIN_DSEEDS = 2, PIN_SRT = 3, PIN_REGS 
 
 // extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r come back compacted
 // as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them (arrays in the PIN_REGS / PIN_REG_OFF slots).
-struct ExtIn { int n_reads; const int32_t *chain_off; const DChain *chains; int64_t n_chains; const DSeed *seeds; int64_t n_seeds; const int32_t *srt; };
+// (on_device: the four arrays were left in HBM by stage_chain(); the pointers are then unused)
+struct ExtIn { int n_reads; const int32_t *chain_off; const DChain *chains; int64_t n_chains; const DSeed *seeds; int64_t n_seeds; const int32_t *srt; bool on_device = false; };
 struct ExtRegs { const DReg *regs; const int64_t *reg_off; };
 void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out);
+
+// chaining stage (mem_chain + mem_chain_flt + flattening, chain_kernels.h) over the seeds of the last stage_seed(keep_on_device)
+// call; fills `in` for stage_extend.  Valid for reads to which mem_flt_chained_seeds does not apply (see pipeline.cpp).
+// With `download` the four arrays are also copied to the PIN_CHAIN_OFF.. slots and `in` points at them (checking mode).
+void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool download = false);
 
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);

@@ -73,7 +73,9 @@ public:
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 	FmView fm;                     // device pointers
-	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_ctg_off = nullptr, *d_ctg_len = nullptr;
+	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_ctg_off = nullptr, *d_ctg_len = nullptr, *d_ctg_alt = nullptr;
+	bool seeds_resident = false;   // the seed list of the whole batch is still in b_seeds / b_seedoff / b_lrep
+	int64_t n_seeds_resident = 0;
 	bool owns_index = true;        // false for clones made by engine_clone()
 	size_t bwt_bytes = 0;
 	Stats stats;
@@ -83,6 +85,7 @@ public:
 	DevBuf d_off, d_codes;
 	// scratch
 	DevBuf b_strips, b_nfirst, b_nsweeps;
+	DevBuf b_chscr, b_chnodes, b_chnc, b_chns, b_chcoff, b_chsoff;
 	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
@@ -165,6 +168,10 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < bns->n_seqs; ++i) { co[i] = bns->anns[i].offset; cl[i] = bns->anns[i].len; }
 	CK(cudaMemcpy(e->d_ctg_off, co.data(), co.size() * 8, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->d_ctg_len, cl.data(), cl.size() * 4, cudaMemcpyHostToDevice));
+	std::vector<uint8_t> alt(bns->n_seqs + 1, 0);
+	for (int i = 0; i < bns->n_seqs; ++i) alt[i] = bns->anns[i].is_alt ? 1 : 0;
+	CK(cudaMalloc(&e->d_ctg_alt, alt.size()));
+	CK(cudaMemcpy(e->d_ctg_alt, alt.data(), alt.size(), cudaMemcpyHostToDevice));
 	FmView &fm = e->fm;
 	fm.bwt = (const uint32_t *)e->d_bwt; fm.sa = (const uint64_t *)e->d_sa;
 	fm.primary = bwt->primary;
@@ -217,7 +224,7 @@ Engine *engine_clone(Engine *base)
 	CK(cudaSetDevice(e->device));
 	engine_make_streams(e);
 	e->owns_index = false;
-	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len;
+	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len; e->d_ctg_alt = base->d_ctg_alt;
 	e->bwt_bytes = base->bwt_bytes;
 	e->fm = base->fm;
 	engine_set_l2_window(e);
@@ -237,7 +244,8 @@ void engine_destroy(Engine *e)
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
 	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
 	e->b_strips.release(); e->b_nfirst.release(); e->b_nsweeps.release();
-	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); }
+	e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
+	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt); }
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
 	cudaStreamDestroy(e->stream);
@@ -488,7 +496,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 	e->stats.n_intv += (int64_t)intv.size();
 }
 
-void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out)
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out, bool keep_on_device)
 {
 	CK(cudaSetDevice(e->device));
 	const int n_reads = e->n_reads;
@@ -499,6 +507,7 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out)
 	int64_t n_seeds = 0;
 	e->zero_counters();
 	const int sub = seed_sub_batch(e->max_len);
+	const bool resident = keep_on_device && n_reads <= sub;     // one sub-batch: its seed list can stay where it is
 	double ms_smem = 0, ms_sa = 0;
 	for (int r0 = 0; r0 < n_reads; r0 += sub) {
 		int r1 = std::min(n_reads, r0 + sub), n = r1 - r0;
@@ -524,11 +533,13 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out)
 		CK(cudaGetLastError());
 		e->stats.n_launches += 1;
 		ms_sa += e->toc();
-		SeedRec *seeds = (SeedRec *)e->h_seeds.need(sizeof(SeedRec) * (n_seeds + n_slots + 1), sizeof(SeedRec) * n_seeds);
-		e->d2h(seeds + n_seeds, d_seeds, sizeof(SeedRec) * n_slots);
-		e->d2h(seed_off + r0, d_seed_off, sizeof(int64_t) * (n + 1));
-		e->d2h(l_rep + r0, e->b_lrep.p, sizeof(int32_t) * n);
-		e->sync();
+		if (!resident) {
+			SeedRec *seeds = (SeedRec *)e->h_seeds.need(sizeof(SeedRec) * (n_seeds + n_slots + 1), sizeof(SeedRec) * n_seeds);
+			e->d2h(seeds + n_seeds, d_seeds, sizeof(SeedRec) * n_slots);
+			e->d2h(seed_off + r0, d_seed_off, sizeof(int64_t) * (n + 1));
+			e->d2h(l_rep + r0, e->b_lrep.p, sizeof(int32_t) * n);
+			e->sync();
+		}
 		n_seeds += n_slots;
 		e->stats.fm_sa_lookups += n_slots;
 	}
@@ -538,6 +549,88 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out)
 	e->stats.ms_k_smem += ms_smem;
 	e->stats.ms_k_sa += ms_sa;
 	out.seed_off = seed_off; out.seeds = (const SeedRec *)e->h_seeds.p; out.l_rep = l_rep; out.n_seeds = n_seeds;
+	e->seeds_resident = resident; e->n_seeds_resident = n_seeds;
+	if (resident) { out.seed_off = nullptr; out.seeds = nullptr; out.l_rep = nullptr; }
+}
+
+/* ------------------------------------------------------------------ chaining (row f2) */
+
+__global__ void __launch_bounds__(128) k_chain_build(ChainOpt co, int64_t l_pac, ChainScratch S, int n_reads, const int64_t *__restrict__ off,
+                                                     const SeedRec *__restrict__ seeds, const int64_t *__restrict__ seed_off, int32_t *n_kc, int32_t *n_ks)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= n_reads) return;
+	const int64_t base = seed_off[r];
+	int ns = 0;
+	n_kc[r] = chain_build_filter(co, l_pac, S, r, (int)(off[r + 1] - off[r]), seeds, base, (int)(seed_off[r + 1] - base), &ns);
+	n_ks[r] = ns;
+}
+
+__global__ void __launch_bounds__(128) k_chain_emit(ChainOpt co, FmView fm, ChainScratch S, int n_reads, const int64_t *__restrict__ off,
+                                                    const SeedRec *__restrict__ seeds, const int64_t *__restrict__ seed_off, const int32_t *__restrict__ l_rep,
+                                                    const int32_t *__restrict__ n_kc, const int64_t *__restrict__ coff, const int64_t *__restrict__ soff,
+                                                    int32_t *chain_off, DChain *chains, DSeed *dseeds, int32_t *srt)
+{
+	const int r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r > n_reads) return;
+	chain_off[r] = (int32_t)coff[r];
+	if (r == n_reads || n_kc[r] == 0) return;
+	chain_emit(co, fm, S, (int)(off[r + 1] - off[r]), l_rep[r], seeds, seed_off[r], n_kc[r], coff[r], soff[r], chains, dseeds, srt);
+}
+
+void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool download)
+{
+	CK(cudaSetDevice(e->device));
+	const int n = e->n_reads;
+	const int64_t n_in = e->n_seeds_resident;
+	if (!e->seeds_resident) {                   // several seeding sub-batches: bring the concatenated host copy back
+		e->h2d(e->b_seeds.as<SeedRec>(n_in + 1), e->h_seeds.p, sizeof(SeedRec) * n_in);
+		e->h2d(e->b_seedoff.as<int64_t>(n + 1), e->h_seed_off.p, sizeof(int64_t) * (n + 1));
+		e->h2d(e->b_lrep.as<int32_t>(n + 1), e->h_lrep.p, sizeof(int32_t) * n);
+	}
+	e->tic();
+	ChainScratch S;
+	S.scr = e->b_chscr.as<int32_t>((size_t)CH_N_PLANES * (n_in + 1)); S.n_total = n_in + 1;
+	S.nodes = e->b_chnodes.as<BtNode>((size_t)(n_in >> 1) + 2 * (size_t)n + 4);
+	S.ctg_alt = (const uint8_t *)e->d_ctg_alt;
+	int32_t *n_kc = e->b_chnc.as<int32_t>(n + 1), *n_ks = e->b_chns.as<int32_t>(n + 1);
+	int64_t *coff = e->b_chcoff.as<int64_t>(n + 1), *soff = e->b_chsoff.as<int64_t>(n + 1);
+	const SeedRec *seeds = (const SeedRec *)e->b_seeds.p;
+	const int64_t *seed_off = (const int64_t *)e->b_seedoff.p;
+	CK(cudaMemsetAsync(n_kc + n, 0, sizeof(int32_t), e->stream));
+	CK(cudaMemsetAsync(n_ks + n, 0, sizeof(int32_t), e->stream));
+	k_chain_build<<<grid_for(n, 128), 128, 0, e->stream>>>(co, e->fm.l_pac, S, n, (const int64_t *)e->d_off.p, seeds, seed_off, n_kc, n_ks);
+	CK(cudaGetLastError());
+	exclusive_scan(e, n_kc, coff, n + 1);
+	exclusive_scan(e, n_ks, soff, n + 1);
+	int64_t tot[2] = { 0, 0 };
+	e->d2h(&tot[0], coff + n, sizeof(int64_t));
+	e->d2h(&tot[1], soff + n, sizeof(int64_t));
+	e->sync();
+	if (tot[0] > 0x7fffffffLL || tot[1] > 0x7fffffffLL) die("too many chains/seeds in one batch");
+	int32_t *d_co = e->b_chain_off.as<int32_t>(n + 1);
+	DChain *d_ch = e->b_chains.as<DChain>(tot[0] + 1);
+	DSeed *d_se = e->b_dseeds.as<DSeed>(tot[1] + 1);
+	int32_t *d_srt = e->b_srt.as<int32_t>(tot[1] + 1);
+	k_chain_emit<<<grid_for(n + 1, 128), 128, 0, e->stream>>>(co, e->fm, S, n, (const int64_t *)e->d_off.p, seeds, seed_off, (const int32_t *)e->b_lrep.p,
+		n_kc, coff, soff, d_co, d_ch, d_se, d_srt);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 2;
+	e->stats.ms_k_chain += e->toc();
+	in.n_reads = n; in.chain_off = nullptr; in.chains = nullptr; in.seeds = nullptr; in.srt = nullptr;
+	in.n_chains = tot[0]; in.n_seeds = tot[1]; in.on_device = true;
+	if (download) {
+		int32_t *h_co = (int32_t *)stage_pinned(e, PIN_CHAIN_OFF, sizeof(int32_t) * (n + 1));
+		DChain *h_ch = (DChain *)stage_pinned(e, PIN_CHAINS, sizeof(DChain) * (tot[0] + 1));
+		DSeed *h_se = (DSeed *)stage_pinned(e, PIN_DSEEDS, sizeof(DSeed) * (tot[1] + 1));
+		int32_t *h_srt = (int32_t *)stage_pinned(e, PIN_SRT, sizeof(int32_t) * (tot[1] + 1));
+		e->d2h(h_co, d_co, sizeof(int32_t) * (n + 1));
+		e->d2h(h_ch, d_ch, sizeof(DChain) * tot[0]);
+		e->d2h(h_se, d_se, sizeof(DSeed) * tot[1]);
+		e->d2h(h_srt, d_srt, sizeof(int32_t) * tot[1]);
+		e->sync();
+		in.chain_off = h_co; in.chains = h_ch; in.seeds = h_se; in.srt = h_srt;
+	}
 }
 
 void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
@@ -594,10 +687,12 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	uint32_t *d_key = e->b_xkey.as<uint32_t>(n), *d_key2 = e->b_xkey2.as<uint32_t>(n);
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);
 	int32_t *d_ctr = e->b_xctr.as<int32_t>(16);
-	e->h2d(d_co, in.chain_off, sizeof(int32_t) * (n + 1));
-	e->h2d(d_ch, in.chains, sizeof(DChain) * in.n_chains);
-	e->h2d(d_se, in.seeds, sizeof(DSeed) * in.n_seeds);
-	e->h2d(d_srt, in.srt, sizeof(int32_t) * in.n_seeds);
+	if (!in.on_device) {
+		e->h2d(d_co, in.chain_off, sizeof(int32_t) * (n + 1));
+		e->h2d(d_ch, in.chains, sizeof(DChain) * in.n_chains);
+		e->h2d(d_se, in.seeds, sizeof(DSeed) * in.n_seeds);
+		e->h2d(d_srt, in.srt, sizeof(int32_t) * in.n_seeds);
+	}
 	static bool attr_set = false;
 	if (!attr_set) {
 		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));

@@ -27,6 +27,7 @@ public:
 	std::vector<int64_t> seed_off;
 	std::vector<SeedRec> seeds;
 	std::vector<int32_t> l_rep;
+	std::vector<uint8_t> ctg_alt;
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
@@ -37,6 +38,8 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
 	for (int i = 0; i < bns->n_seqs; ++i) { e->ctg_off.push_back(bns->anns[i].offset); e->ctg_len.push_back(bns->anns[i].len); }
+	for (int i = 0; i < bns->n_seqs; ++i) e->ctg_alt.push_back(bns->anns[i].is_alt ? 1 : 0);
+	e->ctg_alt.push_back(0);
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data(); e->fm.n_ctg = bns->n_seqs;
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
@@ -45,7 +48,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len;
+	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
@@ -161,7 +164,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 	}
 }
 
-void stage_seed(Engine *e, const SeedOpt &so, SeedOut &res)
+void stage_seed(Engine *e, const SeedOpt &so, SeedOut &res, bool)
 {
 	std::vector<int64_t> &seed_off = e->seed_off;
 	std::vector<SeedRec> &seeds = e->seeds;
@@ -208,6 +211,34 @@ void *stage_pinned(Engine *e, int slot, size_t bytes)
 {
 	if (e->pinned[slot].size() < bytes) e->pinned[slot].resize(bytes + bytes / 4 + 64);
 	return e->pinned[slot].data();
+}
+
+// the two chaining kernels of stages_cuda.cu as loops over the reads
+void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool)
+{
+	const int n = e->n_reads;
+	const int64_t n_in = (int64_t)e->seeds.size();
+	std::vector<int32_t> scr((size_t)CH_N_PLANES * (n_in + 1));
+	std::vector<BtNode> nodes((size_t)(n_in >> 1) + 2 * (size_t)n + 4);
+	ChainScratch S;
+	S.scr = scr.data(); S.n_total = n_in + 1; S.nodes = nodes.data(); S.ctg_alt = e->ctg_alt.data();
+	std::vector<int32_t> n_kc(n + 1, 0), n_ks(n + 1, 0);
+	for (int r = 0; r < n; ++r) {
+		int ns = 0;
+		n_kc[r] = chain_build_filter(co, e->fm.l_pac, S, r, (int)(e->off[r + 1] - e->off[r]), e->seeds.data(), e->seed_off[r], (int)(e->seed_off[r + 1] - e->seed_off[r]), &ns);
+		n_ks[r] = ns;
+	}
+	std::vector<int64_t> coff(n + 1, 0), soff(n + 1, 0);
+	for (int r = 0; r < n; ++r) { coff[r + 1] = coff[r] + n_kc[r]; soff[r + 1] = soff[r] + n_ks[r]; }
+	int32_t *h_co = (int32_t *)stage_pinned(e, PIN_CHAIN_OFF, sizeof(int32_t) * (n + 1));
+	DChain *h_ch = (DChain *)stage_pinned(e, PIN_CHAINS, sizeof(DChain) * (coff[n] + 1));
+	DSeed *h_se = (DSeed *)stage_pinned(e, PIN_DSEEDS, sizeof(DSeed) * (soff[n] + 1));
+	int32_t *h_srt = (int32_t *)stage_pinned(e, PIN_SRT, sizeof(int32_t) * (soff[n] + 1));
+	for (int r = 0; r <= n; ++r) h_co[r] = (int32_t)coff[r];
+	for (int r = 0; r < n; ++r)
+		if (n_kc[r]) chain_emit(co, e->fm, S, (int)(e->off[r + 1] - e->off[r]), e->l_rep[r], e->seeds.data(), e->seed_off[r], n_kc[r], coff[r], soff[r], h_ch, h_se, h_srt);
+	in.n_reads = n; in.chain_off = h_co; in.chains = h_ch; in.seeds = h_se; in.srt = h_srt;
+	in.n_chains = coff[n]; in.n_seeds = soff[n]; in.on_device = false;
 }
 
 void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &res)

@@ -268,6 +268,15 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
         os.environ.pop("B200_LANE_MIN", None)
         os.environ.pop("B200_LANES", None)
     assert got4 == want
+    # chaining stage: B200_CHAIN=check runs the device chaining AND the host chaining and aborts on any difference in the
+    # chain/seed tables handed to chain2aln; B200_CHAIN=host is the host path alone (the one long reads take)
+    for mode in ("check", "host"):
+        os.environ["B200_CHAIN"] = mode
+        try:
+            got_m = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
+        finally:
+            os.environ.pop("B200_CHAIN", None)
+        assert got_m == want, mode
     # through the stand-alone driver binary as well (the C host path)
     got2 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
     assert got2 == want
@@ -285,7 +294,12 @@ def test_properties_at_scale(tmp_path):
     again = a.align(r1, r2, K=30_000_000)
     a.opt.contents.n_threads = 3
     s3 = a.align(r1, r2, K=30_000_000)
-    assert s16 == again == s3
+    os.environ["B200_CHAIN"] = "check"         # device chaining cross-checked against the host chaining on every read
+    try:
+        s_chk = a.align(r1, r2, K=30_000_000)
+    finally:
+        os.environ.pop("B200_CHAIN", None)
+    assert s16 == again == s3 == s_chk
     flags = np.array([int(l.split(b"\t", 2)[1]) for l in s16.split(b"\n") if l])
     assert int(((flags & 0x900) == 0).sum()) == 400000            # one primary record per read
     assert ((flags & 4) == 0).mean() > 0.98                        # simulated reads map

@@ -27,8 +27,15 @@ namespace b200 {
 
 struct Intv { uint64_t x0, x1, x2, info; };     // same 32-byte layout as bwtintv_t
 
+// FM-index in HBM: "occ sectors".  The reference interleaves, per 128 BWT symbols, four 64-bit counts with 32 bytes of
+// 2-bit symbols (64-byte blocks, reference src/bwt.h:72-78): one Occ() is two 32-byte sectors, 4-8 load instructions and a
+// popcount per 16-symbol word.  The device copy is re-blocked ONCE at upload (occ_convert_block) into 32-byte sectors of
+// 64 symbols so that one Occ() for all four bases is ONE 256-bit load (LDG.256, one sector) and six popcounts:
+//   w0,w1,w2  low 32 bits of #C, #G, #T before the block        w3  bits 32-39 of the three counts (8 bits each)
+//   w4,w5     low-bit plane of the 64 symbols (symbol i at bit 31-(i&31) of word i>>5)      w6,w7  high-bit plane
+// #A is implied: 64*block - #C - #G - #T.  Same footprint as the reference layout (0.5 byte per symbol).
 struct FmView {
-	const uint32_t *bwt;        // occ-interleaved BWT, 64-byte blocks
+	const uint32_t *occ;        // occ sectors, 8 words per 64 symbols
 	const uint64_t *sa;         // SA samples
 	uint64_t primary, L2[5], seq_len;
 	int sa_intv;
@@ -62,23 +69,86 @@ B200_HD uint32_t sym_counts16(uint32_t w)
 	return c0 | c1 << 8 | c2 << 16 | c3 << 24;
 }
 
-// Occ(c, k) for the four symbols; k == (uint64_t)-1 gives zeros.  *blk receives the 64-byte block index (or -1).
+// the even bits of w gathered into the low 16 bits (bit 2m -> bit m)
+B200_HD uint32_t even_bits16(uint32_t w)
+{
+	w &= 0x55555555u;
+	w = (w | w >> 1) & 0x33333333u;
+	w = (w | w >> 2) & 0x0f0f0f0fu;
+	w = (w | w >> 4) & 0x00ff00ffu;
+	w = (w | w >> 8) & 0x0000ffffu;
+	return w;
+}
+
+// occ sector `b` (64 symbols) from the reference's occ-interleaved BWT (reference src/bwt.h:72-78, src/bwt.c:169-186).
+// ref_bwt must be readable (zero-padded) up to the end of the 64-byte block that holds the sector.
+B200_HD void occ_convert_block(const uint32_t *ref_bwt, uint64_t b, uint32_t out[8])
+{
+	const uint32_t *p = ref_bwt + ((b >> 1) << 4);
+	uint64_t c[4];
+	for (int i = 0; i < 4; ++i) c[i] = (uint64_t)p[2 * i + 1] << 32 | p[2 * i];
+	const uint32_t *sy = p + 8;
+	if (b & 1) {
+		uint32_t x = 0;
+		for (int i = 0; i < 4; ++i) x += sym_counts16(sy[i]);
+		c[0] += x & 0xff; c[1] += x >> 8 & 0xff; c[2] += x >> 16 & 0xff; c[3] += x >> 24;
+		sy += 4;
+	}
+	out[0] = (uint32_t)c[1]; out[1] = (uint32_t)c[2]; out[2] = (uint32_t)c[3];
+	out[3] = (uint32_t)(c[1] >> 32 & 0xff) | (uint32_t)(c[2] >> 32 & 0xff) << 8 | (uint32_t)(c[3] >> 32 & 0xff) << 16;
+	out[4] = even_bits16(sy[0]) << 16 | even_bits16(sy[1]);
+	out[5] = even_bits16(sy[2]) << 16 | even_bits16(sy[3]);
+	out[6] = even_bits16(sy[0] >> 1) << 16 | even_bits16(sy[1] >> 1);
+	out[7] = even_bits16(sy[2] >> 1) << 16 | even_bits16(sy[3] >> 1);
+}
+
+struct OccRaw { uint32_t w[8]; };
+
+B200_HD OccRaw ld_occ(const FmView &fm, uint64_t blk)
+{
+	OccRaw r;
+#if defined(__CUDA_ARCH__)
+	const uint32_t *p = fm.occ + (blk << 3);
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+#else
+	const uint32_t *p = fm.occ + (blk << 3);
+	for (int i = 0; i < 8; ++i) r.w[i] = p[i];
+#endif
+	return r;
+}
+
+// #C, #G, #T among the first kin+1 symbols of the sector (kin in 0..63)
+B200_HD void occ_sector_counts(const OccRaw &r, uint32_t kin, uint32_t &n1, uint32_t &n2, uint32_t &n3)
+{
+	const uint32_t ma = kin >= 31u ? 0xffffffffu : 0xffffffffu << (31u - kin);
+	const uint32_t mb = kin < 32u ? 0u : 0xffffffffu << (63u - kin);
+	const uint32_t la = r.w[4] & ma, lb = r.w[5] & mb, ha = r.w[6] & ma, hb = r.w[7] & mb;
+	n3 = (uint32_t)popc32(la & ha) + (uint32_t)popc32(lb & hb);
+	n1 = (uint32_t)popc32(la & ~ha) + (uint32_t)popc32(lb & ~hb);
+	n2 = (uint32_t)popc32(~la & ha) + (uint32_t)popc32(~lb & hb);
+}
+
+// Occ(c, ka) for the four symbols from a loaded sector; ka = row index after the sentinel adjustment
+B200_HD void occ4_sector(const OccRaw &r, uint64_t ka, uint64_t cnt[4])
+{
+	const uint32_t kin = (uint32_t)ka & 63u;
+	uint32_t n1, n2, n3;
+	occ_sector_counts(r, kin, n1, n2, n3);
+	cnt[1] = ((uint64_t)(r.w[3] & 0xffu) << 32 | r.w[0]) + n1;
+	cnt[2] = ((uint64_t)(r.w[3] >> 8 & 0xffu) << 32 | r.w[1]) + n2;
+	cnt[3] = ((uint64_t)(r.w[3] >> 16 & 0xffu) << 32 | r.w[2]) + n3;
+	cnt[0] = ka + 1 - cnt[1] - cnt[2] - cnt[3];
+}
+
+// Occ(c, k) for the four symbols; k == (uint64_t)-1 gives zeros.  *blk receives the index of the reference's 64-byte block
+// (the unit of the algorithmic traffic count), or -1.
 B200_HD void fm_occ4(const FmView &fm, uint64_t k, uint64_t cnt[4], int64_t *blk)
 {
 	if (k == (uint64_t)-1) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; if (blk) *blk = -1; return; }
 	k -= (k >= fm.primary);
-	const uint32_t *p = fm.bwt + ((k >> 7) << 4);
 	if (blk) *blk = (int64_t)(k >> 7);
-	const uint64_t *c = (const uint64_t *)p;
-	cnt[0] = c[0]; cnt[1] = c[1]; cnt[2] = c[2]; cnt[3] = c[3];
-	p += 8;
-	int full = (int)((k & 127) >> 4);
-	uint32_t x = 0;
-	for (int i = 0; i < full; ++i) x += sym_counts16(p[i]);
-	uint32_t drop = (uint32_t)(~k & 15);
-	uint32_t last = p[full] & ~((1u << (drop << 1)) - 1u);
-	x += sym_counts16(last) - drop;
-	cnt[0] += x & 0xff; cnt[1] += x >> 8 & 0xff; cnt[2] += x >> 16 & 0xff; cnt[3] += x >> 24;
+	occ4_sector(ld_occ(fm, k >> 6), k, cnt);
 }
 
 // bi-directional extension of ik by each of the four bases
@@ -256,11 +326,14 @@ B200_HD int seed_slots(uint64_t x2, int max_occ)
 }
 B200_HD uint64_t seed_step(uint64_t x2, int max_occ) { return x2 > (uint64_t)max_occ ? x2 / (uint64_t)max_occ : 1; }
 
-B200_HD int fm_B0(const FmView &fm, uint64_t k)
+B200_HD int sector_symbol(const OccRaw &r, uint64_t ka)
 {
-	uint32_t w = fm.bwt[((k >> 7) << 4) + 8 + ((k & 0x7f) >> 4)];
-	return (int)(w >> ((~k & 0xf) << 1) & 3);
+	const uint32_t kin = (uint32_t)ka & 63u, sh = 31u - (kin & 31u);
+	const uint32_t lo = kin < 32u ? r.w[4] : r.w[5], hi = kin < 32u ? r.w[6] : r.w[7];
+	return (int)((lo >> sh & 1u) | (hi >> sh & 1u) << 1);
 }
+
+B200_HD int fm_B0(const FmView &fm, uint64_t k) { return sector_symbol(ld_occ(fm, k >> 6), k); }
 
 // Occ(c,k) for one symbol
 B200_HD uint64_t fm_occ1(const FmView &fm, uint64_t k, int c)
@@ -268,16 +341,9 @@ B200_HD uint64_t fm_occ1(const FmView &fm, uint64_t k, int c)
 	if (k == fm.seq_len) return fm.L2[c + 1] - fm.L2[c];
 	if (k == (uint64_t)-1) return 0;
 	k -= (k >= fm.primary);
-	const uint32_t *p = fm.bwt + ((k >> 7) << 4);
-	uint64_t n = ((const uint64_t *)p)[c];
-	p += 8;
-	int full = (int)((k & 127) >> 4);
-	uint32_t x = 0;
-	for (int i = 0; i < full; ++i) x += sym_counts16(p[i]);
-	uint32_t drop = (uint32_t)(~k & 15);
-	uint32_t last = p[full] & ~((1u << (drop << 1)) - 1u);
-	x += sym_counts16(last) - drop;
-	return n + (x >> (c << 3) & 0xff);
+	uint64_t cnt[4];
+	occ4_sector(ld_occ(fm, k >> 6), k, cnt);
+	return cnt[c];
 }
 
 // SA[k] by LF-walking to a sampled row
@@ -289,9 +355,14 @@ B200_HD uint64_t fm_sa(const FmView &fm, uint64_t k, int *steps)
 		++sa; ++n;
 		if (k == fm.primary) k = 0;
 		else {
-			uint64_t kk = k - (k > fm.primary);
-			int c = fm_B0(fm, kk);
-			k = fm.L2[c] + fm_occ1(fm, k, c);
+			// bwt_invPsi (reference src/bwt.c:53-59): for k != primary the symbol row k - (k > primary) and the row of
+			// bwt_occ's count k - (k >= primary) coincide, so one sector gives both
+			const uint64_t kk = k - (k > fm.primary);
+			const OccRaw r = ld_occ(fm, kk >> 6);
+			const int c = sector_symbol(r, kk);
+			uint64_t cnt[4];
+			occ4_sector(r, kk, cnt);
+			k = (c == 0 ? fm.L2[0] : c == 1 ? fm.L2[1] : c == 2 ? fm.L2[2] : fm.L2[3]) + (c == 0 ? cnt[0] : c == 1 ? cnt[1] : c == 2 ? cnt[2] : cnt[3]);
 		}
 	}
 	if (steps) *steps = n;

@@ -43,61 +43,18 @@ B200_HD uint64_t l2_at(const FmView &fm, int i)
 	return i == 0 ? fm.L2[0] : i == 1 ? fm.L2[1] : i == 2 ? fm.L2[2] : i == 3 ? fm.L2[3] : fm.L2[4];
 }
 
-// Mask that keeps the first kin+1 symbols of a block, for the word pair (2p, 2p+1) in the packed-plane layout below
-// (even bits <- word 2p, odd bits <- word 2p+1).
-B200_HD uint32_t occ_pair_mask(uint32_t kin, int p)
-{
-	const int na = (int)kin + 1 - 32 * p, nb = na - 16;          // symbols kept in word 2p / 2p+1
-	const uint32_t ma = na <= 0 ? 0u : na >= 16 ? 0xffffffffu : ~((1u << ((16 - na) << 1)) - 1u);
-	const uint32_t mb = nb <= 0 ? 0u : nb >= 16 ? 0xffffffffu : ~((1u << ((16 - nb) << 1)) - 1u);
-	return (ma & 0x55555555u) | (mb & 0xaaaaaaaau);
-}
-
-// Occ(., k) for the four symbols from one loaded block; kin = (adjusted k) & 127.
-// Two symbol words are merged into one "low-bit plane" word and one "high-bit plane" word (the planes of the first word
-// on the even bits, of the second on the odd bits), so a pair of words costs three POPCs: #lo, #hi, #(lo & hi).
-// mlut: 128 x 4 packed masks (shared memory on the device); nullptr = compute the masks here.
-B200_HD void occ4_block(const Q4 &c0, const Q4 &c1, const Q4 &s0, const Q4 &s1, uint32_t kin, const uint32_t *mlut, uint64_t cnt[4])
-{
-	const uint32_t w[8] = { s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w };
-	uint32_t pm[4];
-	if (mlut) {
-#if defined(__CUDA_ARCH__)
-		const uint4 m = *reinterpret_cast<const uint4 *>(mlut + kin * 4);
-		pm[0] = m.x; pm[1] = m.y; pm[2] = m.z; pm[3] = m.w;
-#else
-		for (int p = 0; p < 4; ++p) pm[p] = mlut[kin * 4 + p];
-#endif
-	} else for (int p = 0; p < 4; ++p) pm[p] = occ_pair_mask(kin, p);
-	uint32_t slo = 0, shi = 0, s3 = 0;
-#pragma unroll
-	for (int p = 0; p < 4; ++p) {
-		const uint32_t a = w[2 * p], b = w[2 * p + 1];
-		const uint32_t lo = ((a & 0x55555555u) | ((b << 1) & 0xaaaaaaaau)) & pm[p];
-		const uint32_t hi = (((a >> 1) & 0x55555555u) | (b & 0xaaaaaaaau)) & pm[p];
-		slo += (uint32_t)popc32(lo); shi += (uint32_t)popc32(hi); s3 += (uint32_t)popc32(lo & hi);
-	}
-	const uint32_t n1 = slo - s3, n2 = shi - s3;
-	cnt[0] = ((uint64_t)c0.y << 32 | c0.x) + (kin + 1u - n1 - n2 - s3);
-	cnt[1] = ((uint64_t)c0.w << 32 | c0.z) + n1;
-	cnt[2] = ((uint64_t)c1.y << 32 | c1.x) + n2;
-	cnt[3] = ((uint64_t)c1.w << 32 | c1.z) + s3;
-}
-
-// bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c
-B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c, const uint32_t *mlut,
+// bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c: two occ sectors, one 256-bit load each
+B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c,
                            uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
 {
 	const uint64_t base = is_back ? x0 : x1, other = is_back ? x1 : x0;
 	const uint64_t k = base - 1, l = base - 1 + x2;
 	const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
 	const uint64_t ka = kz ? 0 : k - (k >= fm.primary), la = lz ? 0 : l - (l >= fm.primary);
-	const uint32_t *pk = fm.bwt + ((ka >> 7) << 4), *pl = fm.bwt + ((la >> 7) << 4);
-	const Q4 kc0 = ld_q4(pk), kc1 = ld_q4(pk + 4), ks0 = ld_q4(pk + 8), ks1 = ld_q4(pk + 12);
-	const Q4 lc0 = ld_q4(pl), lc1 = ld_q4(pl + 4), ls0 = ld_q4(pl + 8), ls1 = ld_q4(pl + 12);
+	const OccRaw rk = ld_occ(fm, ka >> 6), rl = ld_occ(fm, la >> 6);
 	uint64_t tk[4], tl[4];
-	occ4_block(kc0, kc1, ks0, ks1, (uint32_t)ka & 127u, mlut, tk);
-	occ4_block(lc0, lc1, ls0, ls1, (uint32_t)la & 127u, mlut, tl);
+	occ4_sector(rk, ka, tk);
+	occ4_sector(rl, la, tl);
 	if (kz) tk[0] = tk[1] = tk[2] = tk[3] = 0;
 	if (lz) tl[0] = tl[1] = tl[2] = tl[3] = 0;
 	n_blocks += (kz ? 0 : 1) + ((!lz && (kz || (la >> 7) != (ka >> 7))) ? 1 : 0);
@@ -321,11 +278,8 @@ __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n
                                                     const int32_t *__restrict__ only_neg)     // non-null: only reads r with only_neg[r] < 0
 {
 	extern __shared__ uint32_t seed_sh[];
-	uint32_t *mlut = seed_sh;                          // 128 x 4 packed occ masks
-	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
-	__syncthreads();
 	SeedList L;
-	L.sh = seed_sh + 512 + threadIdx.x; L.stride = 128; L.quota = quota;
+	L.sh = seed_sh + threadIdx.x; L.stride = 128; L.quota = quota;
 	L.sstride = (int64_t)gridDim.x * blockDim.x;
 	L.spill = spill + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	SeedLane ln;
@@ -348,7 +302,7 @@ __global__ void __launch_bounds__(128) k_seed_lanes(FmView fm, SeedOpt so, int n
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			uint64_t o0, o1, o2;
-			fm_extend_sel(fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, mlut, o0, o1, o2, blocks);
+			fm_extend_sel(fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
 			const int slow = ln.fast_step(so, L, o0, o1, o2);
 			if (slow) {
 				if (slow == 1) ln.consume(so, cap, L, o0, o1, o2);

@@ -238,9 +238,6 @@ struct SweepArgs {
 template <int MODE>
 __global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
 {
-	__shared__ uint32_t mlut[512];
-	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
-	__syncthreads();
 	FwdLane ln;
 	ln.st = FwdLane::DONE; ln.n_out = 0; ln.n_sweeps = 0; ln.over = 0;
 	int r = -1;
@@ -264,7 +261,7 @@ __global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			uint64_t o0, o1, o2;
-			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 0, ln.c, mlut, o0, o1, o2, blocks);
+			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 0, ln.c, o0, o1, o2, blocks);
 			if (!ln.step(a.so, a.cap, o0, o1, o2)) need = ln.advance(a.fm, a.so);
 		}
 	}
@@ -275,11 +272,8 @@ __global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
 __global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
 {
 	extern __shared__ uint32_t sweep_sh[];
-	uint32_t *mlut = sweep_sh;
-	for (int p = 0; p < 4; ++p) mlut[threadIdx.x * 4 + p] = occ_pair_mask(threadIdx.x, p);
-	__syncthreads();
 	SeedList L;
-	L.sh = sweep_sh + 512 + threadIdx.x; L.stride = 128; L.quota = quota; L.spill = nullptr; L.sstride = 1;
+	L.sh = sweep_sh + threadIdx.x; L.stride = 128; L.quota = quota; L.spill = nullptr; L.sstride = 1;
 	BwdLane ln;
 	ln.st = BwdLane::DONE; ln.n_out = 0;
 	int r = -1;
@@ -298,7 +292,7 @@ __global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			uint64_t o0, o1, o2;
-			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, mlut, o0, o1, o2, blocks);
+			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, o0, o1, o2, blocks);
 			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) need = ln.advance(a.so, a.cap, L);
 		}
 	}

@@ -142,6 +142,18 @@ Stats &engine_stats(Engine *e) { return e->stats; }
 static void engine_set_l2_window(Engine *e);
 static void engine_make_streams(Engine *e);
 
+// re-blocks the reference's occ-interleaved BWT into occ sectors (fm_kernels.h), one sector per thread
+__global__ void k_occ_convert(const uint32_t *__restrict__ ref_bwt, uint64_t n_sec, uint32_t *occ)
+{
+	const uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (b >= n_sec) return;
+	uint32_t w[8];
+	occ_convert_block(ref_bwt, b, w);
+	uint4 *o = reinterpret_cast<uint4 *>(occ + (b << 3));
+	o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+	o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
 {
 	int nd = engine_device_count();
@@ -151,15 +163,26 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	e->device = device;
 	CK(cudaSetDevice(device));
 	engine_make_streams(e);
-	e->bwt_bytes = (size_t)bwt->bwt_size * 4;
+	const size_t ref_bytes = (size_t)bwt->bwt_size * 4;
+	const uint64_t n_sec = (bwt->seq_len >> 6) + 2;
+	e->bwt_bytes = (size_t)n_sec * 32;
 	size_t sa_bytes = (size_t)bwt->n_sa * 8, pac_bytes = (size_t)(bns->l_pac / 4 + 1);
-	CK(cudaMalloc(&e->d_bwt, e->bwt_bytes + 64));
+	CK(cudaMalloc(&e->d_bwt, e->bwt_bytes));
 	CK(cudaMalloc(&e->d_sa, sa_bytes));
 	CK(cudaMalloc(&e->d_pac, pac_bytes + 16));
 	CK(cudaMalloc(&e->d_ctg_off, sizeof(int64_t) * bns->n_seqs));
 	CK(cudaMalloc(&e->d_ctg_len, sizeof(int32_t) * bns->n_seqs));
-	CK(cudaMemcpy(e->d_bwt, bwt->bwt, e->bwt_bytes, cudaMemcpyHostToDevice));
-	CK(cudaMemset((char *)e->d_bwt + e->bwt_bytes, 0, 64));
+	{	// upload the reference layout to a temporary, re-block it into occ sectors on the device, drop the temporary
+		const size_t padded = ((n_sec >> 1) + 2) * 64;
+		void *d_ref = nullptr;
+		CK(cudaMalloc(&d_ref, padded));
+		CK(cudaMemset(d_ref, 0, padded));
+		CK(cudaMemcpy(d_ref, bwt->bwt, ref_bytes, cudaMemcpyHostToDevice));
+		k_occ_convert<<<(unsigned)((n_sec + 255) / 256), 256>>>((const uint32_t *)d_ref, n_sec, (uint32_t *)e->d_bwt);
+		CK(cudaGetLastError());
+		CK(cudaDeviceSynchronize());
+		CK(cudaFree(d_ref));
+	}
 	CK(cudaMemcpy(e->d_sa, bwt->sa, sa_bytes, cudaMemcpyHostToDevice));
 	CK(cudaMemcpy(e->d_pac, pac, pac_bytes, cudaMemcpyHostToDevice));
 	CK(cudaMemset((char *)e->d_pac + pac_bytes, 0, 16));
@@ -173,7 +196,7 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	CK(cudaMalloc(&e->d_ctg_alt, alt.size()));
 	CK(cudaMemcpy(e->d_ctg_alt, alt.data(), alt.size(), cudaMemcpyHostToDevice));
 	FmView &fm = e->fm;
-	fm.bwt = (const uint32_t *)e->d_bwt; fm.sa = (const uint64_t *)e->d_sa;
+	fm.occ = (const uint32_t *)e->d_bwt; fm.sa = (const uint64_t *)e->d_sa;
 	fm.primary = bwt->primary;
 	for (int i = 0; i < 5; ++i) fm.L2[i] = bwt->L2[i];
 	fm.seq_len = bwt->seq_len; fm.sa_intv = bwt->sa_intv;
@@ -385,7 +408,7 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	const int n = r1 - r0;
 	static int blocks_per_sm = 0, n_sm = 0;
 	const int threads = 128, quota = 16;
-	const size_t sh_bytes = 2048 + (size_t)threads * quota * 16;      // occ mask table + interval lists
+	const size_t sh_bytes = (size_t)threads * quota * 16;               // interval lists
 	if (!blocks_per_sm) {
 		cudaDeviceProp prop;
 		CK(cudaGetDeviceProperties(&prop, e->device));

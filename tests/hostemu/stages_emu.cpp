@@ -7,6 +7,7 @@
 #include "../../mpibwa_b200/csrc/smem_kernel.cuh"
 #include "../../mpibwa_b200/csrc/smem_sweeps.cuh"
 #include <cstdio>
+#include <memory>
 #include <algorithm>
 #include <cstring>
 #include <cstdlib>
@@ -28,12 +29,20 @@ public:
 	std::vector<SeedRec> seeds;
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
+	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
 {
 	Engine *e = new Engine();
-	e->fm.bwt = bwt->bwt; e->fm.sa = bwt->sa; e->fm.primary = bwt->primary;
+	{	// the device's occ-sector layout, built with the same per-sector routine the upload kernel runs
+		const uint64_t n_sec = (bwt->seq_len >> 6) + 2;
+		std::vector<uint32_t> ref(bwt->bwt, bwt->bwt + bwt->bwt_size);
+		ref.resize(((n_sec >> 1) + 2) * 16, 0);
+		e->occ = std::make_shared<std::vector<uint32_t>>(n_sec * 8);
+		for (uint64_t b = 0; b < n_sec; ++b) occ_convert_block(ref.data(), b, e->occ->data() + b * 8);
+	}
+	e->fm.occ = e->occ->data(); e->fm.sa = bwt->sa; e->fm.primary = bwt->primary;
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
@@ -48,6 +57,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
+	e->occ = base->occ;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
@@ -104,7 +114,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 			bool need = ln.advance(e->fm, so, cap2, L);
 			while (need) {
 				uint64_t o0, o1, o2;
-				fm_extend_sel(e->fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, nullptr, o0, o1, o2, blocks);
+				fm_extend_sel(e->fm, ln.k0, ln.k1, ln.k2, ln.is_back, ln.c, o0, o1, o2, blocks);
 				const int slow = (r & 1) ? ln.fast_step(so, L, o0, o1, o2) : 1;     // odd reads also exercise the fast path
 				if (slow) {
 					if (slow == 1) ln.consume(so, cap2, L, o0, o1, o2);
@@ -132,7 +142,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					bool nd = f.advance(e->fm, so);
 					while (nd) {
 						uint64_t o0, o1, o2;
-						fm_extend_sel(e->fm, f.k0, f.k1, f.k2, 0, f.c, nullptr, o0, o1, o2, blocks);
+						fm_extend_sel(e->fm, f.k0, f.k1, f.k2, 0, f.c, o0, o1, o2, blocks);
 						if (!f.step(so, cap2, o0, o1, o2)) nd = f.advance(e->fm, so);
 					}
 					n_out = f.n_out; n_sw = f.over ? -1 : f.n_sweeps;
@@ -144,7 +154,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					nd = b.advance(so, cap2, L2);
 					while (nd) {
 						uint64_t o0, o1, o2;
-						fm_extend_sel(e->fm, b.k0, b.k1, b.k2, 1, b.c, nullptr, o0, o1, o2, blocks);
+						fm_extend_sel(e->fm, b.k0, b.k1, b.k2, 1, b.c, o0, o1, o2, blocks);
 						if (!b.step(so, cap2, L2, o0, o1, o2)) nd = b.advance(so, cap2, L2);
 					}
 					n_out = b.n_out;

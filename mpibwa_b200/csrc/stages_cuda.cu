@@ -202,6 +202,7 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.seq_len = bwt->seq_len; fm.sa_intv = bwt->sa_intv;
 	fm.pac = (const uint8_t *)e->d_pac; fm.l_pac = bns->l_pac;
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
+	fm.xflags = 0;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
 
@@ -523,6 +524,7 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out, bool keep_on_device)
 {
 	CK(cudaSetDevice(e->device));
 	const int n_reads = e->n_reads;
+	e->fm.xflags = getenv("B200_X") ? atoi(getenv("B200_X")) : 0;
 	if (e->max_len > 0xffff) die("reads of 65536 bases or more are not supported by the seeding stage");
 	int64_t *seed_off = (int64_t *)e->h_seed_off.need(sizeof(int64_t) * (n_reads + 1));
 	int32_t *l_rep = (int32_t *)e->h_lrep.need(sizeof(int32_t) * (n_reads + 1));

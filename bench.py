@@ -3,7 +3,9 @@
 
 Workload (BASELINE.json configs[1]): synthetic 100 Mbp reference (4 contigs, i.i.d. ACGT + 5 % planted diverged
 repeats), wgsim-style 2x150 bp pairs (insert N(400,50), 1 % substitutions, 0.1 % indels, 0.1 % N), chunked with the
-reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call on one chunk.
+reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call on one chunk, made
+in its chunk-job form (b200_process_seqs_begin / _end, include/mpibwa_b200.h) so that two chunks are in flight: the device
+stages of chunk i+1 run under the host stages of chunk i.  The timed region covers exactly K chunks, first begin to last end.
 
   value  read pairs/s through mem_process_seqs with the chunk's encoded reads already resident in HBM
   e2e    read pairs/s from raw fastq bytes in host memory to SAM bytes in host memory (in-place parse, interleave,
@@ -186,7 +188,7 @@ def reference_arm(args, prefix):
 def workload_config(args, what):
     return {"workload": "configs[1]: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (4 contigs, 5%% planted repeats), -K %d"
                         % (args.pairs, args.read_len, args.ref_bp, args.K),
-            "step": "one mem_process_seqs call on one chunk (%d pairs at full size; inside the call the chunk runs as 2 sub-batch lanes)" % ((args.K // 2) // args.read_len + 1),
+            "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, two chunks in flight; inside a call the chunk runs as 2 sub-batch lanes" % ((args.K // 2) // args.read_len + 1),
             "path": what, "cache_policy": "every step aligns a different chunk; index (175 MB) + chunk buffers exceed the 126 MB L2; "
                                           "an L2-sized buffer is rewritten between steps"}
 
@@ -288,15 +290,21 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     max_pairs = max(e - b for b, e in chunks)
-    read_buf = [np.empty(max_pairs * rb + 1, dtype=np.uint8) for rb in (rb1, rb2)]     # the host's two fastq read buffers, reused
+    N_SLOTS = 4      # chunk slots of the library: that many chunks can be resident ahead of their call
+    # the in-flight chunks need their own fastq buffers (the parse is in place and the job reads the records later)
+    n_buf = N_SLOTS
+    read_bufs = [[np.empty(max_pairs * rb + 1, dtype=np.uint8) for rb in (rb1, rb2)] for _ in range(n_buf)]
+    buf_turn = [0]
 
     def chunk_bytes(c):
         """private, writable copy of the chunk's fastq bytes (what the MPI host gets from its file read); the parse is in place"""
         b, e = chunks[c % len(chunks)]
+        bufs = read_bufs[buf_turn[0] % n_buf]
+        buf_turn[0] += 1
         out = []
         for k, (fq, rb) in enumerate(((fq1, rb1), (fq2, rb2))):
             nb = (e - b) * rb
-            a = read_buf[k]
+            a = bufs[k]
             a[:nb] = np.frombuffer(fq, dtype=np.uint8, count=nb, offset=b * rb)
             a[nb] = 0
             out.append((a, nb))
@@ -307,79 +315,138 @@ def main():
                  "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv",
                  "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells")
 
-    def e2e_step(c):
-        """raw fastq bytes -> SAM bytes, everything inside"""
-        a1, a2, n = chunk_bytes(c)
+    def e2e_begin(c, raw=None):
+        """raw fastq bytes -> chunk job (parse in place on this thread, everything else on the library's job thread)"""
+        a1, a2, n = raw if raw is not None else chunk_bytes(c)
         k1, p1, m1 = al.parse_array(*a1)
         k2, p2, m2 = al.parse_array(*a2)
+        return (lib.b200_align_chunk_begin(al.opt, al.idx, 0, m1, p1, p2), p1, p2, n)
+
+    def e2e_end(h, st):
+        job, p1, p2, n = h
         sam = C.c_void_p()
         sam_len = C.c_int64()
-        lib.b200_align_chunk(al.opt, al.idx, 0, m1, p1, p2, C.byref(sam), C.byref(sam_len))
+        lib.b200_align_chunk_end(job, C.byref(sam), C.byref(sam_len), C.byref(st))
         out_len = sam_len.value
         lib.b200_free(sam); lib.b200_free(p1); lib.b200_free(p2)
         return n, out_len
 
-    def resident_step(c, ev0, ev1):
-        """reads parsed, encoded and resident in HBM before the timed region; SAM left in seqs[i].sam"""
-        a1, a2, n = chunk_bytes(c)
-        k1, p1, m1 = al.parse_array(*a1)
-        k2, p2, m2 = al.parse_array(*a2)
-        seqs = lib.b200_chunk_seqs(m1, p1, p2)
-        lib.b200_stage_reads(al.opt, al.idx, 2 * m1, seqs)
+    DEPTH = 3        # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
+
+    def e2e_run(first, count, on_stats=None, raw=None):
+        """`count` chunks from fastq bytes in host memory to SAM bytes in host memory as chunk jobs: parse(i), begin(i),
+        ... end(i - DEPTH + 1).  raw: the chunks' private fastq buffers when they were filled before the timed region."""
+        pairs = out_bytes = 0
+        pending = []
+        st = M.b200_stats_t()
+
+        def finish():
+            nonlocal pairs, out_bytes
+            n, ob = e2e_end(pending.pop(0), st)
+            pairs += n; out_bytes += ob
+            if on_stats:
+                on_stats(st.as_dict())
+
+        for s in range(count):
+            pending.append(e2e_begin(first + s, raw[s] if raw else None))
+            if len(pending) >= DEPTH:
+                finish()
+        while pending:
+            finish()
+        return pairs, out_bytes
+
+    def resident_group(first, count, ev0, ev1, on_stats=None):
+        """`count` (<= N_SLOTS) chunks parsed, encoded and resident in HBM before the timed region, then aligned as chunk
+        jobs (two in flight); SAM left in seqs[i].sam"""
+        held = []
+        for s in range(count):
+            a1, a2, n = chunk_bytes(first + s)
+            k1, p1, m1 = al.parse_array(*a1)
+            k2, p2, m2 = al.parse_array(*a2)
+            seqs = lib.b200_chunk_seqs(m1, p1, p2)
+            lib.b200_stage_reads(al.opt, al.idx, 2 * m1, seqs)
+            held.append((seqs, p1, p2, m1, n))
         flush_buf.add_(1)
         torch.cuda.synchronize()
         ev0.record()
-        lib.mem_process_seqs(al.opt, al.idx.contents.bwt, al.idx.contents.bns, al.idx.contents.pac, 0, 2 * m1, seqs, None)
+        jobs = [lib.b200_process_seqs_begin(al.opt, al.idx.contents.bwt, al.idx.contents.bns, al.idx.contents.pac, 0, 2 * m1, seqs, None)
+                for seqs, p1, p2, m1, n in held]
+        st = M.b200_stats_t()
+        for j in jobs:
+            lib.b200_process_seqs_end(j, C.byref(st))
+            if on_stats:
+                on_stats(st.as_dict())
         ev1.record()
         torch.cuda.synchronize()
-        lib.b200_collect_sam(2 * m1, seqs, None)
-        lib.b200_free(seqs); lib.b200_free(p1); lib.b200_free(p2)
-        return n, ev0.elapsed_time(ev1)
+        pairs = 0
+        for seqs, p1, p2, m1, n in held:
+            lib.b200_collect_sam(2 * m1, seqs, None)
+            lib.b200_free(seqs); lib.b200_free(p1); lib.b200_free(p2)
+            pairs += n
+        return pairs, ev0.elapsed_time(ev1)
 
-    # ---- warm-up
-    for w in range(args.warmup):
-        e2e_step(w)
+    # ---- warm-up: W steps end to end, then one untimed resident group so that every chunk slot has its device buffers
+    e2e_run(0, args.warmup)
+    resident_group(0, N_SLOTS, torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
     # ---- timed: device-resident inputs
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
     agg = {k: 0.0 for k in STAT_KEYS}
-    res_pairs, res_ms = 0, 0.0
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for s in range(args.steps):
-        n, ms = resident_step(args.warmup + s, ev0, ev1)
-        res_pairs += n
-        res_ms += ms
-        st = al.stats()
+
+    def add_stats(st):
         for k in STAT_KEYS:
             agg[k] += st[k]
+
+    res_pairs, res_ms = 0, 0.0
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    done = 0
+    while done < args.steps:
+        g = min(N_SLOTS, args.steps - done)
+        n, ms = resident_group(args.warmup + done, g, ev0, ev1, add_stats)
+        res_pairs += n
+        res_ms += ms
+        done += g
     barrier()
     # ---- timed: end to end from host fastq bytes to host SAM bytes
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h2d = d2h = 0
-    e2e_pairs = 0
-    sam_bytes = 0
+    io = {"h2d": 0, "d2h": 0}
+
+    def add_io(st):
+        io["h2d"] += st["h2d_bytes"]
+        io["d2h"] += st["d2h_bytes"]
+
+    # the K chunks' fastq bytes sit in private host buffers (what the host's file read leaves) when the timed region starts
+    raw = None
+    if args.steps <= 16:
+        raw = []
+        for s in range(args.steps):
+            b, e = chunks[(args.warmup + s) % len(chunks)]
+            pair = []
+            for fq, rb in ((fq1, rb1), (fq2, rb2)):
+                nb = (e - b) * rb
+                a = np.empty(nb + 1, dtype=np.uint8)
+                a[:nb] = np.frombuffer(fq, dtype=np.uint8, count=nb, offset=b * rb)
+                a[nb] = 0
+                pair.append((a, nb))
+            raw.append((pair[0], pair[1], e - b))
     barrier()
+    flush_buf.add_(1)
     e0.record()
     t0 = time.time()
-    for s in range(args.steps):
-        flush_buf.add_(1)
-        n, out_len = e2e_step(args.warmup + s)
-        e2e_pairs += n
-        sam_bytes += out_len
-        st = al.stats()
-        h2d += st["h2d_bytes"]
-        d2h += st["d2h_bytes"]
+    e2e_pairs, sam_bytes = e2e_run(args.warmup, args.steps, add_io, raw)
     e1.record()
     barrier()
+    h2d, d2h = io["h2d"], io["d2h"]
     e2e_ms = e0.elapsed_time(e1)
     wall_ms = 1e3 * (time.time() - t0)
     clocks = sampler.result()
     # ---- untimed extra pass with the whole chunk as ONE batch per kernel (no sub-batch lanes): kernel-isolated efficiency
     os.environ["B200_LANES"] = "1"
-    resident_step(args.warmup + args.steps, ev0, ev1)          # first one grows the device buffers to whole-chunk size
-    resident_step(args.warmup + args.steps + 1, ev0, ev1)
-    st_iso = al.stats()
+    resident_group(args.warmup + args.steps, 1, ev0, ev1)          # first one grows the device buffers to whole-chunk size
+    iso = []
+    resident_group(args.warmup + args.steps + 1, 1, ev0, ev1, iso.append)
+    st_iso = iso[0]
     os.environ.pop("B200_LANES", None)
 
     # ---- reduce over ranks: MAX of times, SUM of pairs

@@ -303,7 +303,22 @@ typedef struct {
 	double ms_sam_plan, ms_global;   /* inside ms_sam_host: the dry-run sweep that queues the CIGAR jobs; the device CIGAR stage (wall) */
 	double ms_k_chain;        /* CUDA-event time of the chaining kernels (ms_chain_host is the wall of the whole chaining stage, host or device) */
 } b200_stats_t;
-void b200_get_stats(b200_stats_t *out);
+void b200_get_stats(b200_stats_t *out);   /* counters of the call that finished last */
+
+/* Chunk jobs - mem_process_seqs (reference src/bwamem.h:134) split into begin / end so that the host can keep two chunks
+ * in flight: begin() returns at once and the chunk is aligned by a library thread; end() waits and leaves the result where
+ * mem_process_seqs leaves it (seqs[i].sam).  Jobs run in submission order, B200_INFLIGHT (default 3) at a time, each in its
+ * own set of device buffers: the device stages of chunk i+1 (seeding, chaining, extension) run under the host stages of chunk
+ * i (rescue replay, pairing, SAM text), which a single synchronous call cannot overlap because the insert-size statistics
+ * separate them.  The reference host loop (src/mainParallel.c:1271-1314) becomes: read chunk i+1; begin(i+1); end(i);
+ * hand chunk i to the writer thread.  mem_process_seqs() itself is begin() + end().
+ * b200_align_chunk_begin/_end is the same for b200_align_chunk (the SAM concatenation runs in the job thread). */
+typedef struct b200_job b200_job_t;
+b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                                    int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0);
+void b200_process_seqs_end(b200_job_t *job, b200_stats_t *stats /* may be NULL */);
+b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2);
+int64_t b200_align_chunk_end(b200_job_t *job, char **sam, int64_t *sam_len, b200_stats_t *stats /* may be NULL */);
 /* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP
  * roofline denominator) and with half of the work as IMAD on the FMA pipe (dual-pipe ceiling) */
 double b200_int32_peak(int device);

@@ -134,6 +134,12 @@ _PROTOTYPES = {
     "b200_stage_reads": (None, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int, C.POINTER(bseq1_t)]),
     "b200_align_chunk": (C.c_int64, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int64, C.POINTER(bseq1_t),
                                      C.POINTER(bseq1_t), C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "b200_process_seqs_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwt_t), C.POINTER(bntseq_t), C.POINTER(C.c_uint8),
+                                             C.c_int64, C.c_int, C.POINTER(bseq1_t), C.c_void_p]),
+    "b200_process_seqs_end": (None, [C.c_void_p, C.POINTER(b200_stats_t)]),
+    "b200_align_chunk_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int64, C.POINTER(bseq1_t),
+                                            C.POINTER(bseq1_t)]),
+    "b200_align_chunk_end": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(b200_stats_t)]),
     "b200_free": (None, [C.c_void_p]),
     "b200_get_stats": (None, [C.POINTER(b200_stats_t)]),
     "b200_int32_peak": (C.c_double, [C.c_int]),
@@ -236,6 +242,36 @@ class Aligner:
             n_proc += total
             out.append(sam)
             beg = end
+        self.lib.b200_free(s1)
+        if s2:
+            self.lib.b200_free(s2)
+        return b"".join(out)
+
+    def align_pipelined(self, fq1, fq2=None, K=None, trimmed=False):
+        """align() with two chunks in flight (b200_align_chunk_begin / _end): same SAM, chunk i+1's device stages run under
+        chunk i's host stages"""
+        b1, s1, n1 = self.parse(fq1)
+        b2, s2, n2 = (self.parse(fq2) if fq2 is not None else (None, None, n1))
+        assert n1 == n2
+        K = K or self.opt.contents.chunk_size * self.opt.contents.n_threads
+        out, beg, n_proc, prev = [], 0, 0, None
+
+        def finish(job):
+            sam, sam_len = C.c_void_p(), C.c_int64()
+            self.lib.b200_align_chunk_end(job, C.byref(sam), C.byref(sam_len), None)
+            out.append(C.string_at(sam, sam_len.value))
+            self.lib.b200_free(sam)
+
+        for end in self.plan(n1, s1, s2, K, trimmed):
+            p1 = C.cast(C.addressof(s1.contents) + beg * C.sizeof(bseq1_t), C.POINTER(bseq1_t))
+            p2 = C.cast(C.addressof(s2.contents) + beg * C.sizeof(bseq1_t), C.POINTER(bseq1_t)) if s2 else None
+            job = self.lib.b200_align_chunk_begin(self.opt, self.idx, n_proc if trimmed else 0, end - beg, p1, p2)
+            n_proc += (end - beg) * (2 if s2 else 1)
+            if prev is not None:
+                finish(prev)
+            prev, beg = job, end
+        if prev is not None:
+            finish(prev)
         self.lib.b200_free(s1)
         if s2:
             self.lib.b200_free(s2)

@@ -22,6 +22,11 @@ SeedOpt make_seed_opt(const mem_opt_t *opt);
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0);
 void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs);
+struct SeqJob;
+SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
+                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *), void *arg);
+void process_seqs_end(SeqJob *j, b200_stats_t *stats);
+void last_stats(b200_stats_t *out);
 
 static void die(const char *what, const char *arg)
 {
@@ -378,10 +383,52 @@ void b200_stage_reads(const mem_opt_t *opt, const bwaidx_t *idx, int n, bseq1_t 
 	stage_reads(opt, idx->bwt, idx->bns, idx->pac, n, seqs);
 }
 
+/* chunk jobs: the asynchronous form of mem_process_seqs / b200_align_chunk (see include/mpibwa_b200.h) */
+struct b200_job {
+	SeqJob *job;
+	bseq1_t *seqs; int64_t total;       // b200_align_chunk_begin: the interleaved mates and the SAM collected by the job thread
+	char *sam; int64_t sam_len;
+};
+
+b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                                    int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	b200_job *j = new b200_job();
+	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr);
+	return j;
+}
+
+void b200_process_seqs_end(b200_job_t *j, b200_stats_t *stats)
+{
+	process_seqs_end(j->job, stats);
+	delete j;
+}
+
+b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2)
+{
+	b200_job *j = new b200_job();
+	j->total = s2 ? 2 * n : n;
+	j->seqs = b200_chunk_seqs(n, s1, s2);
+	j->sam = nullptr; j->sam_len = 0;
+	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
+		[](void *p) { b200_job *x = (b200_job *)p; x->sam_len = b200_collect_sam(x->total, x->seqs, &x->sam); free(x->seqs); x->seqs = nullptr; }, j);
+	return j;
+}
+
+int64_t b200_align_chunk_end(b200_job_t *j, char **sam, int64_t *sam_len, b200_stats_t *stats)
+{
+	process_seqs_end(j->job, stats);
+	const int64_t total = j->total;
+	if (sam) *sam = j->sam; else free(j->sam);
+	if (sam_len) *sam_len = j->sam_len;
+	delete j;
+	return total;
+}
+
 void b200_get_stats(b200_stats_t *out)
 {
-	Engine *e = engine_current();
-	if (e) *out = engine_stats(e);
+	if (engine_current()) last_stats(out);
 	else memset(out, 0, sizeof *out);
 }
 

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <condition_variable>
 
 namespace b200 {
 
@@ -58,13 +59,26 @@ Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 	return g_engines[0];
 }
 
-// engine of lane k (k = 0 is the primary engine)
-static Engine *engine_lane(int k)
+// engine of lane k of chunk slot `slot` (slot 0, lane 0 is the primary engine; all others are clones sharing its index)
+static const int MAX_LANES = 4, N_SLOTS = 4;
+static Engine *engine_lane(int slot, int k)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	while ((int)g_engines.size() <= k) g_engines.push_back(engine_clone(g_engines[0]));
-	return g_engines[k];
+	const int idx = slot * MAX_LANES + k;
+	while ((int)g_engines.size() <= idx) g_engines.push_back(engine_clone(g_engines[0]));
+	return g_engines[idx];
 }
+
+// Chunk slots: a slot is a set of lane engines that one mem_process_seqs call occupies from start to end.  Several calls
+// may be in flight (process_seqs_begin / _end): up to B200_INFLIGHT (default 3) run at once, in submission order, so that
+// the device stages of chunk i+1 run under the host stages (rescue replay, pairing, SAM text) of chunk i.
+struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0; int64_t staged_bases = 0; };
+static Slot g_slots[N_SLOTS];
+static std::mutex g_slot_mu;
+static std::condition_variable g_slot_cv;
+static int g_running = 0;
+static uint64_t g_ticket_next = 0, g_ticket_serving = 0;
+static b200_stats_t g_last_stats;
 
 void engine_select_device(int dev) { g_device = dev; }
 void engine_release()
@@ -74,6 +88,7 @@ void engine_release()
 	g_engines.clear(); g_engine_key = nullptr;
 }
 Engine *engine_current() { return g_engines.empty() ? nullptr : g_engines[0]; }
+void last_stats(b200_stats_t *out) { std::lock_guard<std::mutex> lk(g_slot_mu); *out = g_last_stats; }
 
 /* ------------------------------------------------------------------ option packing */
 
@@ -212,16 +227,13 @@ static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, cons
 
 /* ------------------------------------------------------------------ the hot path */
 
-static const void *g_staged_key = nullptr;
-static int g_staged_n = 0;
-static int64_t g_staged_bases = 0;
 
 // A chunk is cut into two (optionally four) sub-batches ("lanes") of whole pairs.  Each lane has its own engine (stream, scratch,
 // resident reads; the index is shared) and runs seeding -> chaining -> extension -> regions, and later rescue -> SAM, on
 // its own; two driver threads walk the lanes so that one lane's host stage overlaps the other lane's device stage.
 struct Lane { Engine *eng; int r0, n; };
 
-static std::vector<Lane> make_lanes(int n)
+static std::vector<Lane> make_lanes(int n, int slot)
 {
 	// two lanes by default: enough to overlap one lane's host stage with the other's device stage, while the kernels
 	// still see half a chunk per launch (four lanes gave the host another ~6 % but cost the DP kernels a third of their
@@ -234,7 +246,7 @@ static std::vector<Lane> make_lanes(int n)
 	int r0 = 0;
 	for (int i = 0; i < k; ++i) {
 		int r1 = i + 1 == k ? n : (int)(((int64_t)n * (i + 1) / k) & ~1ll);
-		lanes.push_back({ engine_lane(i), r0, r1 - r0 });
+		lanes.push_back({ engine_lane(slot, i), r0, r1 - r0 });
 		r0 = r1;
 	}
 	return lanes;
@@ -264,13 +276,22 @@ static int64_t stage_lane_reads(const mem_opt_t *opt, const Lane &L, bseq1_t *se
 	return off[n];
 }
 
-// b200_stage_reads(): make the reads of the coming mem_process_seqs call resident ahead of time
+// b200_stage_reads(): make the reads of a coming mem_process_seqs call resident ahead of time (in a free chunk slot,
+// which the call for the same `seqs` then takes over)
 void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs)
 {
 	engine_for(bwt, bns, pac);
+	int slot = -1;
+	{
+		std::unique_lock<std::mutex> lk(g_slot_mu);
+		g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
+		g_slots[slot].busy = true;
+	}
 	int64_t bases = 0;
-	for (const Lane &L : make_lanes(n)) bases += stage_lane_reads(opt, L, seqs);
-	g_staged_key = (const void *)seqs; g_staged_n = n; g_staged_bases = bases;
+	for (const Lane &L : make_lanes(n, slot)) bases += stage_lane_reads(opt, L, seqs);
+	std::lock_guard<std::mutex> lk(g_slot_mu);
+	g_slots[slot].busy = false; g_slots[slot].staged_key = (const void *)seqs; g_slots[slot].staged_n = n; g_slots[slot].staged_bases = bases;
+	g_slot_cv.notify_all();
 }
 
 template <class F>
@@ -284,18 +305,17 @@ static void drive_lanes(std::vector<Lane> &lanes, F body)
 
 #define GPU_STAGE(call) do { std::lock_guard<std::mutex> gpu_lk(g_gpu_mu); call; } while (0)
 
-void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
-                  int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0)
+static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                              int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0,
+                              int slot, bool staged, int64_t staged_bases, b200_stats_t *stats_out)
 {
-	Engine *eng0 = engine_for(bwt, bns, pac);
-	std::vector<Lane> lanes = make_lanes(n_all);
+	engine_for(bwt, bns, pac);
+	std::vector<Lane> lanes = make_lanes(n_all, slot);
 	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
 	const double t_start = now_ms();
 	const bool pe = (opt->flag & MEM_F_PE) != 0;
 	const int64_t l_pac = bns->l_pac;
-	const bool staged = g_staged_key == (const void *)seqs_all && g_staged_n == n_all;
-	g_staged_key = nullptr;
 	std::vector<RegVec> regs_all(n_all);
 
 	// ================= phase 1, per lane: reads -> seeds -> chains -> regions
@@ -307,7 +327,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	RegVec *regs = regs_all.data() + L.r0;
 	double t0 = now_ms(), t1;
 	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload - unless b200_stage_reads() already did
-	if (!staged) GPU_STAGE(st.n_bases = stage_lane_reads(opt, L, seqs_all));
+	if (!staged) st.n_bases = stage_lane_reads(opt, L, seqs_all);       // (own stream and buffers: no need to hold the device)
 	st.n_reads = n;
 
 	// ---- chaining on the device unless a read is long enough for mem_flt_chained_seeds (B200_CHAIN=host forces the host path)
@@ -693,7 +713,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 	});
 
 	// ================= merge the per-lane counters into the primary engine's record (b200_get_stats reads it)
-	Stats &st = engine_stats(eng0);
+	Stats &st = engine_stats(lanes[0].eng);
 	for (size_t k = 1; k < lanes.size(); ++k) {
 		const b200_stats_t &o = engine_stats(lanes[k].eng);
 		st.ms_seed += o.ms_seed; st.ms_sa += o.ms_sa; st.ms_chain_host += o.ms_chain_host; st.ms_extend += o.ms_extend;
@@ -708,12 +728,75 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global; st.ms_k_chain += o.ms_k_chain;
 	}
 	st.ms_rescue += ms_pestat;
-	if (staged) st.n_bases = g_staged_bases;
+	if (staged) st.n_bases = staged_bases;
 	st.ms_total = now_ms() - t_start;
 	if (bwa_verbose >= 3)
 		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s, %d lane%s; stage walls summed over lanes: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f [plan %.0f, cigar stage %.0f])\n",
 		        "mem_process_seqs", n_all, st.ms_total * 1e-3, engine_kind(), (int)lanes.size(), lanes.size() > 1 ? "s" : "", st.ms_seed, st.ms_chain_host,
 		        st.ms_extend, st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
+	if (stats_out) *stats_out = st;
+	std::lock_guard<std::mutex> lk(g_slot_mu);
+	g_last_stats = st;
+}
+
+/* ------------------------------------------------------------------ chunk jobs */
+
+struct SeqJob {
+	std::thread th;
+	b200_stats_t stats;
+};
+
+SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                           int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
+                           void (*after)(void *), void *arg)
+{
+	engine_for(bwt, bns, pac);
+	SeqJob *j = new SeqJob();
+	memset(&j->stats, 0, sizeof j->stats);
+	int slot = -1;
+	bool staged = false;
+	int64_t staged_bases = 0;
+	uint64_t ticket;
+	{
+		std::unique_lock<std::mutex> lk(g_slot_mu);
+		for (int k = 0; k < N_SLOTS; ++k)
+			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; }
+		if (slot < 0)
+			g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
+		g_slots[slot].busy = true; g_slots[slot].staged_key = nullptr;
+		ticket = g_ticket_next++;
+	}
+	const mem_pestat_t *pes = pes0;
+	j->th = std::thread([=]() {
+		static const int limit = getenv("B200_INFLIGHT") ? std::max(1, atoi(getenv("B200_INFLIGHT"))) : 3;
+		{
+			std::unique_lock<std::mutex> lk(g_slot_mu);
+			g_slot_cv.wait(lk, [&] { return ticket == g_ticket_serving && g_running < limit; });
+			++g_running; ++g_ticket_serving;
+			g_slot_cv.notify_all();
+		}
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, staged, staged_bases, &j->stats);
+		{
+			std::lock_guard<std::mutex> lk(g_slot_mu);
+			--g_running; g_slots[slot].busy = false;
+			g_slot_cv.notify_all();
+		}
+		if (after) after(arg);                   // (SAM concatenation: host work that overlaps the next chunk)
+	});
+	return j;
+}
+
+void process_seqs_end(SeqJob *j, b200_stats_t *stats)
+{
+	j->th.join();
+	if (stats) *stats = j->stats;
+	delete j;
+}
+
+void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
+                  int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr), nullptr);
 }
 
 } // namespace b200

@@ -15,6 +15,10 @@
 #include <thread>
 #include <atomic>
 #include <utility>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <condition_variable>
 
 namespace b200 {
 
@@ -216,27 +220,81 @@ private:
 	}
 };
 
-// dynamic parallel loop over [0,n) in blocks of `grain`
+// Dynamic parallel loop over [0,n) in blocks of `grain`: body(tid, begin, end) with tid < n_threads, at most one block per
+// tid at a time.  All loops of the process - several sub-batch lanes and chunk jobs run their host stages concurrently -
+// share ONE pool of n_threads - 1 workers (the calling thread takes part as tid 0 of its own loop), so the number of
+// runnable host threads stays at the core count however many chunks are in flight; the threads that drive the device
+// stages are then not starved by an oversubscribed run queue.
+namespace detail {
+struct PoolLoop {
+	std::function<void(int, int64_t, int64_t)> body;
+	int64_t n, grain;
+	int nt;                                  // workers with index >= nt stay out (results never depend on it; tid-indexed scratch does)
+	std::atomic<int64_t> next{0}, done{0};
+	int64_t n_blocks;
+};
+class WorkerPool {
+public:
+	static WorkerPool &get() { static WorkerPool p; return p; }
+	void run(int n_threads, int64_t n, int64_t grain, std::function<void(int, int64_t, int64_t)> body)
+	{
+		auto loop = std::make_shared<PoolLoop>();
+		loop->body = std::move(body); loop->n = n; loop->grain = grain; loop->nt = n_threads;
+		loop->n_blocks = (n + grain - 1) / grain;
+		{
+			std::lock_guard<std::mutex> lk(mu_);
+			while ((int)workers_.size() < n_threads - 1) { const int id = (int)workers_.size() + 1; workers_.emplace_back([this, id] { work(id); }); }
+			loops_.push_back(loop);
+		}
+		cv_.notify_all();
+		drain(*loop, 0);
+		std::unique_lock<std::mutex> lk(mu_);
+		for (size_t k = 0; k < loops_.size(); ++k) if (loops_[k] == loop) { loops_.erase(loops_.begin() + k); break; }
+		done_cv_.wait(lk, [&] { return loop->done.load() == loop->n_blocks; });
+	}
+private:
+	std::mutex mu_;
+	std::condition_variable cv_, done_cv_;
+	std::vector<std::shared_ptr<PoolLoop>> loops_;      // loops that may still have unclaimed blocks
+	std::vector<std::thread> workers_;
+	bool stop_ = false;
+	~WorkerPool()
+	{
+		{ std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+		cv_.notify_all();
+		for (auto &t : workers_) t.join();
+	}
+	void drain(PoolLoop &L, int tid)
+	{
+		for (;;) {
+			const int64_t b = L.next.fetch_add(L.grain);
+			if (b >= L.n) return;
+			const int64_t e = b + L.grain < L.n ? b + L.grain : L.n;
+			L.body(tid, b, e);
+			if (L.done.fetch_add(1) + 1 == L.n_blocks) { std::lock_guard<std::mutex> lk(mu_); done_cv_.notify_all(); }
+		}
+	}
+	void work(int id)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		for (;;) {
+			std::shared_ptr<PoolLoop> pick;
+			for (auto &l : loops_) if (id < l->nt && l->next.load() < l->n) { pick = l; break; }
+			if (!pick) { if (stop_) return; cv_.wait(lk); continue; }
+			lk.unlock();
+			drain(*pick, id);
+			lk.lock();
+		}
+	}
+};
+} // namespace detail
+
 template <class F>
 void parallel_for(int n_threads, int64_t n, int64_t grain, F body)
 {
 	if (n <= 0) return;
 	if (n_threads <= 1 || n <= grain) { body(0, (int64_t)0, n); return; }
-	std::atomic<int64_t> next(0);
-	std::vector<std::thread> pool;
-	int nt = n_threads;
-	if ((int64_t)nt > (n + grain - 1) / grain) nt = (int)((n + grain - 1) / grain);
-	auto run = [&](int tid) {
-		for (;;) {
-			int64_t b = next.fetch_add(grain);
-			if (b >= n) break;
-			int64_t e = b + grain < n ? b + grain : n;
-			body(tid, b, e);
-		}
-	};
-	for (int t = 1; t < nt; ++t) pool.emplace_back(run, t);
-	run(0);
-	for (auto &th : pool) th.join();
+	detail::WorkerPool::get().run(n_threads, n, grain, std::function<void(int, int64_t, int64_t)>(std::ref(body)));
 }
 
 } // namespace b200

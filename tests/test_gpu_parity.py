@@ -277,9 +277,13 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
         finally:
             os.environ.pop("B200_CHAIN", None)
         assert got_m == want, mode
-    # through the stand-alone driver binary as well (the C host path)
+    # chunk jobs (b200_align_chunk_begin / _end): several chunks in flight, SAM unchanged and in input order
+    assert a.align_pipelined(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args) == want
+    # through the stand-alone driver binary as well (the C host path), synchronous and with chunk jobs (-P)
     got2 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
     assert got2 == want
+    got3 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-P", "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
+    assert got3 == want
 
 
 def test_properties_at_scale(tmp_path):

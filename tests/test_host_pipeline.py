@@ -62,3 +62,22 @@ def test_sub_batch_lanes_do_not_change_the_sam(hostemu_built, examples, tmp_path
     r = subprocess.run([drv, "-t", "4", "-v", "3"] + args, capture_output=True, check=True, env=env)
     assert r.stdout == want
     assert (lanes + " lanes").encode() in r.stderr
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("shape", ["pe", "trim"])
+def test_chunk_jobs_give_the_same_sam(hostemu_built, examples, tmp_path, shape):
+    """-P: the host loop keeps chunks in flight through b200_process_seqs_begin / _end (several chunks, two lanes each,
+    one shared worker pool); records come out in input order and byte-identical to the reference's"""
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if shape == "pe":
+        args = ["-K", "90000", examples["idx"], _head(examples["R1_10K"], 1500, str(tmp_path / "a.fq")),
+                _head(examples["R2_10K"], 1500, str(tmp_path / "b.fq"))]
+    else:
+        args = ["-T", "-K", "70000", examples["idx"], _head(examples["R1_10K_TRIM"], 1200, str(tmp_path / "a.fq")),
+                _head(examples["R2_10K_TRIM"], 1200, str(tmp_path / "b.fq"))]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    env = dict(os.environ, B200_LANE_MIN="100", B200_LANES="2")
+    r = subprocess.run([drv, "-P", "-t", "4"] + args, capture_output=True, check=True, env=env)
+    assert r.stdout == want and want.count(b"\n") > 2000

@@ -6,7 +6,10 @@
  * With -r RANK -n NRANKS chunk c is taken by rank c % NRANKS (the MPI hosts claim chunks from a shared counter;
  * a static round-robin keeps runs reproducible) and only that rank's records are written.
  *
- * usage: b200_driver [-K bases] [-t threads] [-T] [-H] [-r rank -n nranks] [-d device] <idxprefix|.map> <r1.fq> [r2.fq]
+ * With -P the loop keeps two chunks in flight through the chunk-job form of the call (b200_process_seqs_begin / _end):
+ * "read chunk i+1; begin(i+1); end(i); write chunk i" - the patched host loop of INTEGRATION.md.
+ *
+ * usage: b200_driver [-K bases] [-t threads] [-T] [-H] [-P] [-r rank -n nranks] [-d device] <idxprefix|.map> <r1.fq> [r2.fq]
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -60,14 +63,15 @@ static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
 
 int main(int argc, char **argv)
 {
-	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0;
+	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0, pipelined = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THv:r:n:d:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THPv:r:n:d:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
 		else if (c == 'H') header = 1;
+		else if (c == 'P') pipelined = 1;
 		else if (c == 'v') bwa_verbose = atoi(optarg);
 		else if (c == 'r') rank = atoi(optarg);
 		else if (c == 'n') nranks = atoi(optarg);
@@ -102,6 +106,9 @@ int main(int argc, char **argv)
 	int64_t n_processed = 0;
 	double t_mem = 0;
 	bseq1_t *seqs = malloc((paired ? 2 : 1) * n1 * sizeof(bseq1_t));
+	b200_job_t *prev_job = 0;                 /* -P: the chunk whose end() is still to come */
+	bseq1_t *prev_seqs = 0;
+	size_t prev_n = 0;
 	for (i = 0; i < n1; ++i) {
 		bases += s1[i].l_seq;
 		if (paired && trimmed) bases += s2[i].l_seq;
@@ -113,14 +120,34 @@ int main(int argc, char **argv)
 					if (paired) seqs[n++] = s2[k];
 				}
 				double t0 = now();
-				mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, 0);
+				if (pipelined) {
+					bseq1_t *cs = malloc(n * sizeof(bseq1_t));
+					memcpy(cs, seqs, n * sizeof(bseq1_t));
+					b200_job_t *job = b200_process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, cs, 0);
+					if (prev_job) {
+						b200_process_seqs_end(prev_job, 0);
+						for (k = 0; k < prev_n; ++k) { fputs(prev_seqs[k].sam, stdout); free(prev_seqs[k].sam); }
+						free(prev_seqs);
+					}
+					prev_job = job; prev_seqs = cs; prev_n = n;
+				} else {
+					mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, 0);
+					for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }
+				}
 				t_mem += now() - t0;
 				n_processed += n;
-				for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }
 				mine += n;
 			}
 			beg = i + 1; bases = 0; ++n_chunks;
 		}
+	}
+	if (prev_job) {
+		size_t k;
+		double t0 = now();
+		b200_process_seqs_end(prev_job, 0);
+		t_mem += now() - t0;
+		for (k = 0; k < prev_n; ++k) { fputs(prev_seqs[k].sam, stdout); free(prev_seqs[k].sam); }
+		free(prev_seqs);
 	}
 	fprintf(stderr, "[b200_driver] rank=%d reads=%zu chunks=%zu mem_process_seqs_sec=%.3f\n", rank, mine, n_chunks, t_mem);
 	b200_gpu_release();

@@ -4,7 +4,7 @@
 Workload (BASELINE.json configs[1]): synthetic 100 Mbp reference (4 contigs, i.i.d. ACGT + 5 % planted diverged
 repeats), wgsim-style 2x150 bp pairs (insert N(400,50), 1 % substitutions, 0.1 % indels, 0.1 % N), chunked with the
 reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call on one chunk, made
-in its chunk-job form (b200_process_seqs_begin / _end, include/mpibwa_b200.h) so that two chunks are in flight: the device
+in its chunk-job form (b200_process_seqs_begin / _end, include/mpibwa_b200.h) so that several chunks are in flight: the device
 stages of chunk i+1 run under the host stages of chunk i.  The timed region covers exactly K chunks, first begin to last end.
 
   value  read pairs/s through mem_process_seqs with the chunk's encoded reads already resident in HBM
@@ -188,7 +188,7 @@ def reference_arm(args, prefix):
 def workload_config(args, what):
     return {"workload": "configs[1]: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (4 contigs, 5%% planted repeats), -K %d"
                         % (args.pairs, args.read_len, args.ref_bp, args.K),
-            "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, two chunks in flight; inside a call the chunk runs as 2 sub-batch lanes" % ((args.K // 2) // args.read_len + 1),
+            "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, up to four chunks in flight, each as one batch per kernel" % ((args.K // 2) // args.read_len + 1),
             "path": what, "cache_policy": "every step aligns a different chunk; index (175 MB) + chunk buffers exceed the 126 MB L2; "
                                           "an L2-sized buffer is rewritten between steps"}
 
@@ -228,7 +228,8 @@ def kernel_table(agg, K, i32_peak, hbm_peak):
     if agg["ms_k_global"] > 0:
         gc = agg["global_cells"] / agg["ms_k_global"] / 1e6
         kern["ksw_global2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_global"] / K, "cells_per_step": agg["global_cells"] / K,
-                               "jobs_per_step": agg["n_global_jobs"] / K, "gcups": gc, "achieved": gc * 14,
+                               "jobs_per_step": agg["n_global_jobs"] / K, "host_fallbacks_per_step": agg.get("n_global_host", 0) / K,
+                               "gcups": gc, "achieved": gc * 14,
                                "unit": "Gop/s (14 int32 ops per cell, src/ksw.c:546-566)", "peak": i32_peak, "frac": (gc * 14 / i32_peak) if i32_peak else None}
     if agg.get("ms_k_chain", 0) > 0:
         kern["chaining"] = {"bound": "latency (one read per lane, pointer chasing)", "ms_per_step": agg["ms_k_chain"] / K,
@@ -292,7 +293,7 @@ def main():
     max_pairs = max(e - b for b, e in chunks)
     N_SLOTS = 4      # chunk slots of the library: that many chunks can be resident ahead of their call
     # the in-flight chunks need their own fastq buffers (the parse is in place and the job reads the records later)
-    n_buf = N_SLOTS
+    n_buf = N_SLOTS + 1
     read_bufs = [[np.empty(max_pairs * rb + 1, dtype=np.uint8) for rb in (rb1, rb2)] for _ in range(n_buf)]
     buf_turn = [0]
 
@@ -313,7 +314,7 @@ def main():
     STAT_KEYS = ("ms_k_chain", "n_seeds", "n_chains", "ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
                  "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv",
-                 "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells")
+                 "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells", "n_global_host")
 
     def e2e_begin(c, raw=None):
         """raw fastq bytes -> chunk job (parse in place on this thread, everything else on the library's job thread)"""
@@ -331,7 +332,7 @@ def main():
         lib.b200_free(sam); lib.b200_free(p1); lib.b200_free(p2)
         return n, out_len
 
-    DEPTH = 3        # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
+    DEPTH = 4        # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
 
     def e2e_run(first, count, on_stats=None, raw=None):
         """`count` chunks from fastq bytes in host memory to SAM bytes in host memory as chunk jobs: parse(i), begin(i),
@@ -487,9 +488,9 @@ def main():
                 "d2h_bytes_per_step": d2h // args.steps, "sam_bytes_per_step": sam_bytes // args.steps, "wall_ms_rank0": wall_ms},
         "gpu_launches": int(agg["n_launches"]), "clocks": clocks, "roofline": roof, "kernels": kern,
         "kernels_isolated": kernel_table(st_iso, 1, i32_peak, hbm_peak),
-        "kernels_note": "roofline/kernels: CUDA-event kernel times inside the timed region (the chunk runs as 2 sub-batch lanes, so every kernel sees half "
-                        "a chunk per launch); kernels_isolated: one extra untimed pass with whole-chunk batches (B200_LANES=1), the kernel-isolated "
-                        "figures of BASELINE configs[1]; ksw_extend2_gcups is the isolated one",
+        "kernels_note": "roofline/kernels: CUDA-event kernel times inside the timed region (chunk jobs: one whole-chunk batch per kernel, up to four chunks "
+                        "in flight, device stages serialised); kernels_isolated: one extra untimed chunk run alone, the kernel-isolated figures of "
+                        "BASELINE configs[1]; ksw_extend2_gcups is the isolated one",
         "ksw_extend2_gcups": kernel_table(st_iso, 1, i32_peak, hbm_peak).get("ksw_extend2", {}).get("gcups"),
         "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global", "ms_total")},
         "host_threads": n_threads,

@@ -301,13 +301,14 @@ typedef struct {
 	double ms_k_extend_dp;    /* CUDA-event time of the ksw_extend2 DP kernels alone (ms_k_extend = whole extension stage) */
 	int64_t n_extend_rounds;
 	double ms_sam_plan, ms_global;   /* inside ms_sam_host: the dry-run sweep that queues the CIGAR jobs; the device CIGAR stage (wall) */
+	int64_t n_global_host;    /* regions whose CIGAR the SAM sweep computed with the host routine (not queued for the device stage) */
 	double ms_k_chain;        /* CUDA-event time of the chaining kernels (ms_chain_host is the wall of the whole chaining stage, host or device) */
 } b200_stats_t;
 void b200_get_stats(b200_stats_t *out);   /* counters of the call that finished last */
 
 /* Chunk jobs - mem_process_seqs (reference src/bwamem.h:134) split into begin / end so that the host can keep two chunks
  * in flight: begin() returns at once and the chunk is aligned by a library thread; end() waits and leaves the result where
- * mem_process_seqs leaves it (seqs[i].sam).  Jobs run in submission order, B200_INFLIGHT (default 3) at a time, each in its
+ * mem_process_seqs leaves it (seqs[i].sam).  Jobs run in submission order, B200_INFLIGHT (default 4) at a time, each in its
  * own set of device buffers: the device stages of chunk i+1 (seeding, chaining, extension) run under the host stages of chunk
  * i (rescue replay, pairing, SAM text), which a single synchronous call cannot overlap because the insert-size statistics
  * separate them.  The reference host loop (src/mainParallel.c:1271-1314) becomes: read chunk i+1; begin(i+1); end(i);

@@ -84,7 +84,7 @@ class b200_stats_t(C.Structure):
                                          "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes",
                                          "d2h_bytes")] + [("ms_k_extend_dp", C.c_double), ("n_extend_rounds", C.c_int64),
                                                           ("ms_sam_plan", C.c_double), ("ms_global", C.c_double),
-                                                          ("ms_k_chain", C.c_double)]
+                                                          ("n_global_host", C.c_int64), ("ms_k_chain", C.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -24,7 +24,7 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs);
 struct SeqJob;
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
-                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *), void *arg);
+                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *), void *arg, int want_lanes);
 void process_seqs_end(SeqJob *j, b200_stats_t *stats);
 void last_stats(b200_stats_t *out);
 
@@ -395,7 +395,7 @@ b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, cons
 {
 	b200_job *j = new b200_job();
 	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
-	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr);
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 1);
 	return j;
 }
 
@@ -412,7 +412,7 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->seqs = b200_chunk_seqs(n, s1, s2);
 	j->sam = nullptr; j->sam_len = 0;
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
-		[](void *p) { b200_job *x = (b200_job *)p; x->sam_len = b200_collect_sam(x->total, x->seqs, &x->sam); free(x->seqs); x->seqs = nullptr; }, j);
+		[](void *p) { b200_job *x = (b200_job *)p; x->sam_len = b200_collect_sam(x->total, x->seqs, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, 1);
 	return j;
 }
 

@@ -30,7 +30,6 @@ AlignCtx &align_ctx()
 
 char *dup_cstr(const std::string &s)
 {
-	if (align_ctx().mode == AlignCtx::RECORD) return nullptr;     // dry run: nothing is formatted
 	char *p = (char *)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size());
 	p[s.size()] = 0;
@@ -789,15 +788,24 @@ static inline int infer_bw(int l1, int l2, int score, int a, int q, int r)
 	return w;
 }
 
-// Would mem_reg2aln run a banded DP for this region (as opposed to the no-gap path)?  Conservative: true when unsure.
-bool reg_needs_dp(const mem_opt_t *opt, const mem_alnreg_t *ar)
+static int reg_first_band(const mem_opt_t *opt, const mem_alnreg_t *ar)       // reference src/bwamem.c:1107-1111
 {
-	if (ar->rb < 0 || ar->re < 0) return false;
 	int tmp = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
 	int w2 = infer_bw(ar->qe - ar->qb, (int)(ar->re - ar->rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
 	w2 = w2 > tmp ? w2 : tmp;
 	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
-	return global_needs_dp(ar->qe - ar->qb, ar->re - ar->rb, w2 < opt->w << 2 ? w2 : opt->w << 2);
+	return w2;
+}
+
+bool reg_global_job(const mem_opt_t *opt, const bntseq_t *bns, const mem_alnreg_t *ar, int read, GlobalJob *j)
+{
+	if (ar->rb < 0 || ar->re < 0) return false;
+	const int w2 = reg_first_band(opt, ar);
+	if (!(ar->qe > ar->qb && ar->re <= bns->l_pac << 1 && ar->rb < ar->re && !(ar->rb < bns->l_pac && ar->re > bns->l_pac) &&
+	      global_needs_dp(ar->qe - ar->qb, ar->re - ar->rb, w2 < opt->w << 2 ? w2 : opt->w << 2))) return false;
+	j->rb = ar->rb; j->re = ar->re; j->zoff = 0; j->qb = ar->qb; j->qe = ar->qe; j->w2 = w2; j->truesc = ar->truesc; j->wmax = 0;
+	j->read = read;
+	return true;
 }
 
 void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query_,
@@ -810,7 +818,7 @@ void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int 
 		a.rid = -1; a.pos = -1; a.flag |= 0x4;
 		return;
 	}
-	int i, w2, tmp, qb, qe, NM = -1, score = 0, is_rev, last_sc = -(1 << 30);
+	int i, w2, qb, qe, NM = -1, score = 0, is_rev, last_sc = -(1 << 30);
 	int64_t pos, rb, re;
 	qb = ar->qb; qe = ar->qe;
 	rb = ar->rb; re = ar->re;
@@ -819,31 +827,25 @@ void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int 
 		query[i] = query_[i] < 5 ? query_[i] : kNt4[(uint8_t)query_[i]];
 	a.mapq = ar->secondary < 0 ? (approx_mapq_se(opt, ar) & 0xff) : 0;
 	if (ar->secondary >= 0) a.flag |= 0x100;
-	tmp = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt->a, opt->o_del, opt->e_del);
-	w2 = infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt->a, opt->o_ins, opt->e_ins);
-	w2 = w2 > tmp ? w2 : tmp;
-	if (w2 > opt->w) w2 = w2 < ar->w ? w2 : ar->w;
+	w2 = reg_first_band(opt, ar);
 	AlignCtx &cx = align_ctx();
 	bool done = false;
-	if (cx.mode != AlignCtx::DIRECT && qe > qb && rb >= 0 && re <= bns->l_pac << 1 && rb < re && !(rb < bns->l_pac && re > bns->l_pac) &&
-	    global_needs_dp(qe - qb, re - rb, w2 < opt->w << 2 ? w2 : opt->w << 2)) {
-		if (cx.mode == AlignCtx::RECORD) {            // queue the region for the device; the placeholder is never formatted
-			GlobalJob j;
-			j.rb = rb; j.re = re; j.zoff = 0; j.qb = qb; j.qe = qe; j.w2 = w2; j.truesc = ar->truesc; j.wmax = 0;
-			j.read = query_ == cx.seq_ptr[0] ? cx.read_idx[0] : cx.read_idx[1];
-			cx.rec->push_back(j);
-			NM = 0;
-			done = true;
-		} else {
-			const GlobalRes &g = cx.res[cx.cursor++];
+	GlobalJob want;
+	if (cx.mode == AlignCtx::LOOKUP && reg_global_job(opt, bns, ar, query_ == cx.seq_ptr[0] ? cx.read_idx[0] : cx.read_idx[1], &want)) {
+		for (int k = 0; k < cx.n_jobs; ++k) {
+			const GlobalJob &j = cx.jobs[k];
+			if (j.read != want.read || j.rb != want.rb || j.re != want.re || j.qb != want.qb || j.qe != want.qe || j.w2 != want.w2 || j.truesc != want.truesc) continue;
+			const GlobalRes &g = cx.res[k];
 			if (g.n_cigar >= 0) {
 				gen_cigar(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, 0, bns->l_pac, pac, qe - qb,
 				          &query[qb], rb, re, &score, &a.cigar, &NM, &a.md, &g);
 				done = true;
 			}                                           // else: too many CIGAR operations for the result record - align here
+			break;
 		}
 	}
 	i = 0;
+	if (!done && cx.mode == AlignCtx::LOOKUP && global_needs_dp(qe - qb, re - rb, w2 < opt->w << 2 ? w2 : opt->w << 2)) ++cx.n_host_dp;
 	if (!done) do {
 		w2 = w2 < opt->w << 2 ? w2 : opt->w << 2;
 		gen_cigar(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins, w2, bns->l_pac, pac, qe - qb,
@@ -944,7 +946,6 @@ static inline void put_cigar(const mem_opt_t *opt, const AlnView &p, std::string
 void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const bseq1_t *s, int n, const Aln *list,
              int which, const Aln *m_)
 {
-	if (align_ctx().mode == AlignCtx::RECORD) return;
 	AlnView p(list[which]);
 	AlnView mt(m_ ? *m_ : list[which]);
 	AlnView *m = m_ ? &mt : nullptr;

@@ -34,17 +34,21 @@ struct Aln {                    // counterpart of mem_aln_t
 
 typedef std::vector<mem_alnreg_t> RegVec;
 
-// Plumbing between mem_reg2aln's alignment step and the batched CIGAR stage on the device.  The SAM stage runs twice
-// per pair: once in RECORD mode (regions that need a DP are queued, nothing is formatted), then - after the device has
-// aligned every queued region - in REPLAY mode, which makes the same calls in the same order and picks the results up.
+// Plumbing between mem_reg2aln's alignment step and the batched CIGAR stage on the device.  Before the SAM sweep the
+// pipeline queues a banded global alignment for every region that mem_reg2aln may be asked about (plan_global_jobs: a
+// function of the region and the read alone, so no dry run of the pairing logic is needed); the device aligns them all at
+// once; the sweep then runs in LOOKUP mode, where reg2aln finds the alignment of its region among the pair's jobs by
+// (read, interval, band, score).  A region that was not queued, or whose CIGAR did not fit the result record, is aligned
+// on the spot by the host routine - same arithmetic, same result.
 struct AlignCtx {
-	enum { DIRECT = 0, RECORD = 1, REPLAY = 2 };
+	enum { DIRECT = 0, LOOKUP = 2 };
 	int mode = DIRECT;
-	std::vector<GlobalJob> *rec = nullptr;
-	const GlobalRes *res = nullptr;      // results of the current pair, in request order
-	int cursor = 0;
+	const GlobalJob *jobs = nullptr;     // jobs / results of the current pair
+	const GlobalRes *res = nullptr;
+	int n_jobs = 0;
 	const char *seq_ptr[2] = { nullptr, nullptr };
 	int read_idx[2] = { 0, 0 };
+	int64_t n_host_dp = 0;               // regions the sweep had to align itself (not queued, or CIGAR too long for the record)
 };
 AlignCtx &align_ctx();                   // thread-local
 
@@ -89,7 +93,8 @@ int  infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t *dist);
 // mem_pair, reference src/bwamem_pair.c:182-243
 int  pair_ends(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], RegVec a[2], int id,
                int *sub, int *n_sub, int z[2], int n_pri[2]);
-bool reg_needs_dp(const mem_opt_t *opt, const mem_alnreg_t *ar);
+// the CIGAR-stage job mem_reg2aln would need for this region (false: no banded DP - gap-free path or degenerate interval)
+bool reg_global_job(const mem_opt_t *opt, const bntseq_t *bns, const mem_alnreg_t *ar, int read, GlobalJob *job);
 // mem_reg2aln, reference src/bwamem.c:1089-1159
 void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query,
              const mem_alnreg_t *ar, Aln *out);

@@ -70,9 +70,9 @@ static Engine *engine_lane(int slot, int k)
 }
 
 // Chunk slots: a slot is a set of lane engines that one mem_process_seqs call occupies from start to end.  Several calls
-// may be in flight (process_seqs_begin / _end): up to B200_INFLIGHT (default 3) run at once, in submission order, so that
+// may be in flight (process_seqs_begin / _end): up to B200_INFLIGHT (default 4) run at once, in submission order, so that
 // the device stages of chunk i+1 run under the host stages (rescue replay, pairing, SAM text) of chunk i.
-struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0; int64_t staged_bases = 0; };
+struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0, staged_lanes = 0; int64_t staged_bases = 0; };
 static Slot g_slots[N_SLOTS];
 static std::mutex g_slot_mu;
 static std::condition_variable g_slot_cv;
@@ -233,12 +233,13 @@ static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, cons
 // its own; two driver threads walk the lanes so that one lane's host stage overlaps the other lane's device stage.
 struct Lane { Engine *eng; int r0, n; };
 
-static std::vector<Lane> make_lanes(int n, int slot)
+static std::vector<Lane> make_lanes(int n, int slot, int want_default)
 {
-	// two lanes by default: enough to overlap one lane's host stage with the other's device stage, while the kernels
-	// still see half a chunk per launch (four lanes gave the host another ~6 % but cost the DP kernels a third of their
-	// efficiency: every extension round has a latency floor).  B200_LANES / B200_LANE_MIN (reads per lane) override.
-	const int want = getenv("B200_LANES") ? atoi(getenv("B200_LANES")) : 2;
+	// A synchronous mem_process_seqs call runs its chunk as two lanes: enough to overlap one lane's host stage with the
+	// other's device stage while the kernels still see half a chunk per launch.  Chunk jobs (process_seqs_begin) overlap
+	// whole chunks instead and run ONE lane, so every kernel sees the whole chunk (the DP rounds have a latency floor: half
+	// batches cost the extension kernels a third of their efficiency).  B200_LANES / B200_LANE_MIN (reads per lane) override.
+	const int want = getenv("B200_LANES") ? atoi(getenv("B200_LANES")) : want_default;
 	const int lane_min = getenv("B200_LANE_MIN") ? atoi(getenv("B200_LANE_MIN")) : 65536;
 	int k = want >= 4 ? 4 : want >= 2 ? 2 : 1;
 	while (k > 1 && n < k * lane_min) k >>= 1;
@@ -288,9 +289,11 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 		g_slots[slot].busy = true;
 	}
 	int64_t bases = 0;
-	for (const Lane &L : make_lanes(n, slot)) bases += stage_lane_reads(opt, L, seqs);
+	std::vector<Lane> lanes = make_lanes(n, slot, 1);
+	for (const Lane &L : lanes) bases += stage_lane_reads(opt, L, seqs);
 	std::lock_guard<std::mutex> lk(g_slot_mu);
 	g_slots[slot].busy = false; g_slots[slot].staged_key = (const void *)seqs; g_slots[slot].staged_n = n; g_slots[slot].staged_bases = bases;
+	g_slots[slot].staged_lanes = (int)lanes.size();
 	g_slot_cv.notify_all();
 }
 
@@ -307,10 +310,11 @@ static void drive_lanes(std::vector<Lane> &lanes, F body)
 
 static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                               int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0,
-                              int slot, bool staged, int64_t staged_bases, b200_stats_t *stats_out)
+                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out)
 {
 	engine_for(bwt, bns, pac);
-	std::vector<Lane> lanes = make_lanes(n_all, slot);
+	std::vector<Lane> lanes = make_lanes(n_all, slot, want_lanes);
+	if (staged && (int)lanes.size() != want_lanes) { fprintf(stderr, "[mpibwa_b200] staged reads do not match the lane split of the call\n"); abort(); }
 	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
 	const double t_start = now_ms();
@@ -646,8 +650,8 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	t1 = now_ms(); st.ms_rescue = t1 - t0; t0 = t1;
 
 	// ---- primary marking, pairing, mapQ, CIGAR and SAM text (reference worker2, src/bwamem.c:1187-1203).
-	// Two sweeps over the pairs: a dry run that only queues the regions whose CIGAR needs a banded global alignment,
-	// the CIGAR stage on the device for all of them at once, then the real sweep that picks the alignments up.
+	// First every region that mem_reg2aln may be asked about is queued for the CIGAR stage on the device (a function of
+	// the region alone: no dry run of the pairing logic), then the sweep over the pairs looks its alignments up.
 	{
 		const int64_t n_units = pe ? n >> 1 : n;
 		const int per = pe ? 2 : 1;
@@ -662,21 +666,24 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		struct UnitJobs { int32_t tid, start, count; };
 		std::vector<UnitJobs> uj(n_units);
 		std::vector<std::vector<GlobalJob>> tjobs(nt);
-		parallel_for(nt, n_units, 256, [&](int tid, int64_t b, int64_t e) {
-			AlignCtx &cx = align_ctx();
-			cx.mode = AlignCtx::RECORD; cx.rec = &tjobs[tid];
+		parallel_for(nt, n_units, 1024, [&](int tid, int64_t b, int64_t e) {
+			std::vector<GlobalJob> &out = tjobs[tid];
 			for (int64_t u = b; u < e; ++u) {
-				bool any = false;                          // no region of the pair can ask for a DP: nothing to queue
-				for (int k = 0; k < per && !any; ++k)
-					for (const mem_alnreg_t &a : regs[u * per + k]) if (reg_needs_dp(opt, &a)) { any = true; break; }
-				if (!any) { uj[u] = { tid, (int32_t)tjobs[tid].size(), 0 }; continue; }
-				RegVec copy[2];
-				for (int k = 0; k < per; ++k) { copy[k] = regs[u * per + k]; cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
-				const int32_t start = (int32_t)tjobs[tid].size();
-				run_unit(u, copy);
-				uj[u] = { tid, start, (int32_t)tjobs[tid].size() - start };
+				const int32_t start = (int32_t)out.size();
+				for (int k = 0; k < per; ++k) {
+					const RegVec &rv = regs[u * per + k];
+					// a region below the output threshold, or far below the read's best hit (never a primary, never in XA), is
+					// not worth a device job; should the sweep ask for it after all, reg2aln aligns it itself
+					int best = 0;
+					for (const mem_alnreg_t &a : rv) best = a.score > best ? a.score : best;
+					for (const mem_alnreg_t &a : rv) {
+						if (a.score < opt->T || a.score < best * opt->XA_drop_ratio - opt->pen_unpaired) continue;
+						GlobalJob j;
+						if (reg_global_job(opt, bns, &a, (int)(u * per + k), &j)) out.push_back(j);
+					}
+				}
+				uj[u] = { tid, start, (int32_t)out.size() - start };
 			}
-			cx.mode = AlignCtx::DIRECT; cx.rec = nullptr;
 		});
 		std::vector<int64_t> tbase(nt + 1, 0);
 		for (int t = 0; t < nt; ++t) tbase[t + 1] = tbase[t] + (int64_t)tjobs[t].size();
@@ -698,16 +705,20 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		std::vector<GlobalRes> gres;
 		if (!gjobs.empty()) GPU_STAGE(stage_global(eng, go, gjobs, zb, gres));
 		st.ms_global = now_ms() - tg;
+		std::atomic<int64_t> n_host_dp(0);
 		parallel_for(nt, n_units, 256, [&](int, int64_t b, int64_t e) {
 			AlignCtx &cx = align_ctx();
-			cx.mode = AlignCtx::REPLAY;
+			cx.mode = AlignCtx::LOOKUP; cx.n_host_dp = 0;
 			for (int64_t u = b; u < e; ++u) {
-				cx.res = gres.data() + tbase[uj[u].tid] + uj[u].start; cx.cursor = 0;
+				const int64_t first = tbase[uj[u].tid] + uj[u].start;
+				cx.jobs = gjobs.data() + first; cx.res = gres.data() + first; cx.n_jobs = uj[u].count;
+				for (int k = 0; k < per; ++k) { cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
 				run_unit(u, &regs[u * per]);
-				if (cx.cursor != uj[u].count) { fprintf(stderr, "[mpibwa_b200] CIGAR stage: request sequence changed between the sweeps\n"); abort(); }
 			}
-			cx.mode = AlignCtx::DIRECT; cx.res = nullptr;
+			cx.mode = AlignCtx::DIRECT; cx.jobs = nullptr; cx.res = nullptr; cx.n_jobs = 0;
+			n_host_dp += cx.n_host_dp;
 		});
+		st.n_global_host = n_host_dp;
 	}
 	t1 = now_ms(); st.ms_sam_host = t1 - t0;
 	});
@@ -725,7 +736,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		st.fm_occ_blocks += o.fm_occ_blocks; st.fm_sa_steps += o.fm_sa_steps; st.fm_sa_lookups += o.fm_sa_lookups;
 		st.n_launches += o.n_launches; st.h2d_bytes += o.h2d_bytes; st.d2h_bytes += o.d2h_bytes;
 		st.ms_k_extend_dp += o.ms_k_extend_dp; st.n_extend_rounds += o.n_extend_rounds;
-		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global; st.ms_k_chain += o.ms_k_chain;
+		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global; st.ms_k_chain += o.ms_k_chain; st.n_global_host += o.n_global_host;
 	}
 	st.ms_rescue += ms_pestat;
 	if (staged) st.n_bases = staged_bases;
@@ -748,7 +759,7 @@ struct SeqJob {
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
-                           void (*after)(void *), void *arg)
+                           void (*after)(void *), void *arg, int want_lanes)
 {
 	engine_for(bwt, bns, pac);
 	SeqJob *j = new SeqJob();
@@ -760,7 +771,7 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	{
 		std::unique_lock<std::mutex> lk(g_slot_mu);
 		for (int k = 0; k < N_SLOTS; ++k)
-			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; }
+			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; want_lanes = g_slots[k].staged_lanes; }
 		if (slot < 0)
 			g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
 		g_slots[slot].busy = true; g_slots[slot].staged_key = nullptr;
@@ -768,14 +779,14 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	}
 	const mem_pestat_t *pes = pes0;
 	j->th = std::thread([=]() {
-		static const int limit = getenv("B200_INFLIGHT") ? std::max(1, atoi(getenv("B200_INFLIGHT"))) : 3;
+		static const int limit = getenv("B200_INFLIGHT") ? std::max(1, atoi(getenv("B200_INFLIGHT"))) : 4;
 		{
 			std::unique_lock<std::mutex> lk(g_slot_mu);
 			g_slot_cv.wait(lk, [&] { return ticket == g_ticket_serving && g_running < limit; });
 			++g_running; ++g_ticket_serving;
 			g_slot_cv.notify_all();
 		}
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, staged, staged_bases, &j->stats);
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats);
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
 			--g_running; g_slots[slot].busy = false;
@@ -796,7 +807,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2), nullptr);
 }
 
 } // namespace b200

@@ -362,3 +362,40 @@ void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
 }
 
 } // namespace b200
+
+// ---- test-only entry points (tests/test_host_pipeline.py) ----------------------------------------------------------------
+// occ sectors with counts beyond 2^32 (human-sized references: 2 x 3.1 Gbp of BWT rows need 33 bits): a synthetic stretch of
+// the reference layout placed at row k0 is re-blocked with occ_convert_block and every Occ() is compared with a direct count.
+extern "C" int64_t b200_emu_occ_selftest(uint64_t k0, uint32_t seed)
+{
+	using namespace b200;
+	const int n_blk = 6;                                      // reference blocks of 128 symbols
+	std::vector<uint32_t> ref((n_blk + 1) * 16, 0);
+	std::vector<uint8_t> sym(n_blk * 128);
+	uint64_t x = seed * 2654435761u + 12345;
+	for (auto &s : sym) { x = x * 6364136223846793005ull + 1442695040888963407ull; s = (uint8_t)(x >> 61 & 3); }
+	k0 &= ~(uint64_t)127;
+	uint64_t c[4] = { k0 / 8, k0 / 2, k0 / 8, 0 };    // one count beyond 2^32 when k0 is
+	c[3] = k0 - c[0] - c[1] - c[2];
+	for (int j = 0; j < n_blk; ++j) {
+		for (int t = 0; t < 4; ++t) { ref[j * 16 + 2 * t] = (uint32_t)c[t]; ref[j * 16 + 2 * t + 1] = (uint32_t)(c[t] >> 32); }
+		for (int i = 0; i < 128; ++i) {
+			const int s = sym[j * 128 + i];
+			ref[j * 16 + 8 + (i >> 4)] |= (uint32_t)s << ((~i & 15) << 1);
+			++c[s];
+		}
+	}
+	int64_t bad = 0;
+	uint64_t run[4] = { k0 / 8, k0 / 2, k0 / 8, 0 };
+	run[3] = k0 - run[0] - run[1] - run[2];
+	for (int i = 0; i < n_blk * 128; ++i) {
+		++run[sym[i]];                                        // Occ(., k) counts rows 0..k inclusive
+		OccRaw r;
+		occ_convert_block(ref.data(), (uint64_t)(i >> 6), r.w);
+		uint64_t cnt[4];
+		occ4_sector(r, k0 + i, cnt);
+		for (int t = 0; t < 4; ++t) bad += cnt[t] != run[t];
+		bad += sector_symbol(r, k0 + i) != sym[i];
+	}
+	return bad;
+}

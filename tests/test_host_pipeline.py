@@ -81,3 +81,15 @@ def test_chunk_jobs_give_the_same_sam(hostemu_built, examples, tmp_path, shape):
     env = dict(os.environ, B200_LANE_MIN="100", B200_LANES="2")
     r = subprocess.run([drv, "-P", "-t", "4"] + args, capture_output=True, check=True, env=env)
     assert r.stdout == want and want.count(b"\n") > 2000
+
+
+def test_occ_sectors_beyond_32_bits(hostemu_built):
+    """the device's FM-index layout (32-byte occ sectors with 40-bit counts) against a direct count, at BWT rows of a
+    human-sized reference (> 2^32) as well as small ones"""
+    import ctypes as C
+    lib = C.CDLL(os.path.join(hostemu_built, "libmpibwa_b200_hostemu.so"))
+    lib.b200_emu_occ_selftest.restype = C.c_int64
+    lib.b200_emu_occ_selftest.argtypes = [C.c_uint64, C.c_uint32]
+    for k0 in (0, 128, 1 << 31, (1 << 32) - 128, 1 << 32, 6_200_000_000, (1 << 33) - 1024):
+        for seed in (1, 2, 3):
+            assert lib.b200_emu_occ_selftest(k0, seed) == 0, (k0, seed)

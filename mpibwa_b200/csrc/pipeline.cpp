@@ -702,8 +702,8 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		tjobs.clear();
 		double tg = now_ms();
 		st.ms_sam_plan = tg - t0;
-		std::vector<GlobalRes> gres;
-		if (!gjobs.empty()) GPU_STAGE(stage_global(eng, go, gjobs, zb, gres));
+		const GlobalRes *gres = nullptr;
+		if (!gjobs.empty()) GPU_STAGE(gres = stage_global(eng, go, gjobs, zb));
 		st.ms_global = now_ms() - tg;
 		std::atomic<int64_t> n_host_dp(0);
 		parallel_for(nt, n_units, 256, [&](int, int64_t b, int64_t e) {
@@ -711,7 +711,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 			cx.mode = AlignCtx::LOOKUP; cx.n_host_dp = 0;
 			for (int64_t u = b; u < e; ++u) {
 				const int64_t first = tbase[uj[u].tid] + uj[u].start;
-				cx.jobs = gjobs.data() + first; cx.res = gres.data() + first; cx.n_jobs = uj[u].count;
+				cx.jobs = gjobs.data() + first; cx.res = gres ? gres + first : nullptr; cx.n_jobs = uj[u].count;
 				for (int k = 0; k < per; ++k) { cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
 				run_unit(u, &regs[u * per]);
 			}

@@ -70,7 +70,9 @@ void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool download = false
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);
 
 // CIGAR stage: banded global alignment + traceback of regions of the resident reads (jobs carry zoff/slot filled by the caller)
-void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out);
+// Returns the results in job order, in memory owned by the engine (page-locked on the CUDA engine) that stays valid until
+// the next stage_global call on the same engine.
+const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes);
 
 // generic batches over caller-provided byte buffers (C-ABI b200_*_batch and the single-job wrappers)
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,

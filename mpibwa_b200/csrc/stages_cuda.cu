@@ -731,7 +731,10 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
 	// warp-cooperative kernels (latency path): warps per block such that the rows of the longest query fit shared memory
 	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
-	const int WARP_JOBS_MAX = 8192;       // a class with fewer jobs than this cannot fill the chip with one job per lane
+	// measured on the bench workload (tools/tune_env.py): a class is better off with one warp per job below ~2 k jobs;
+	// the fused tail kernel takes over once fewer than TAIL_READS_MAX reads still walk their chains
+	const int WARP_JOBS_MAX = getenv("B200_EXT_WARP_MAX") ? atoi(getenv("B200_EXT_WARP_MAX")) : 2048;
+	const int TAIL_READS_MAX = getenv("B200_EXT_TAIL_MAX") ? atoi(getenv("B200_EXT_TAIL_MAX")) : 50000;
 	const int tail_warps = warps_for(e->max_len);
 	const char *dbg = getenv("B200_DEBUG");
 	int32_t ctr[16];
@@ -750,7 +753,7 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
 	};
 	while (n_active > 0) {
-		if (rounds > 0 && tail_warps && n_active <= WARP_JOBS_MAX) {
+		if (rounds > 0 && tail_warps && n_active <= TAIL_READS_MAX) {
 			// few reads left: one warp per read finishes the walk on the device (advance + DP fused)
 			ev_pair();
 			CK(cudaEventRecord(e->ev_pool[ev_used], e->stream));
@@ -1178,12 +1181,11 @@ __global__ void __launch_bounds__(128) k_global_jobs(GlobalOpt go, const uint8_t
 	warp_add(&cnt->global_cells, cells);
 }
 
-void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out)
+const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes)
 {
 	CK(cudaSetDevice(e->device));
 	const int64_t n = (int64_t)jobs.size();
-	out.resize(n);
-	if (n == 0) return;
+	if (n == 0) return nullptr;
 	e->zero_counters();
 	// classes by the circular window a lane needs: 32, 64, 128, 256, 512 columns; wider bands or queries over 256 bases
 	// take the general kernel
@@ -1248,9 +1250,9 @@ void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &
 	GlobalRes *hr = (GlobalRes *)e->h_gres.need(sizeof(GlobalRes) * n);
 	e->d2h(hr, dr, sizeof(GlobalRes) * n);
 	Counters c = e->read_counters();
-	memcpy(out.data(), hr, sizeof(GlobalRes) * n);
 	e->stats.global_cells += (int64_t)c.global_cells;
 	e->stats.n_global_jobs += n;
+	return hr;
 }
 
 /* ------------------------------------------------------------------ int32 issue-rate micro-benchmark (roofline denominator)

@@ -29,6 +29,7 @@ public:
 	std::vector<SeedRec> seeds;
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
+	std::vector<GlobalRes> gres;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
 };
 
@@ -303,8 +304,9 @@ void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::v
 	}
 }
 
-void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes, std::vector<GlobalRes> &out)
+const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes)
 {
+	std::vector<GlobalRes> &out = e->gres;
 	out.resize(jobs.size());
 	std::vector<uint8_t> z((size_t)z_bytes + 16);
 	std::vector<int32_t> row;
@@ -315,6 +317,7 @@ void stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &
 		global_task(go, global_seqs(e->fm.pac, e->fm.l_pac, e->codes.data() + e->off[j.read] + j.qb, j), j, eh, z.data() + j.zoff, &out[x], &e->stats.global_cells);
 		++e->stats.n_global_jobs;
 	}
+	return out.data();
 }
 
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,

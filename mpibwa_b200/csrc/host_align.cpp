@@ -1,6 +1,7 @@
 // host_align.cpp - host-resident BWA-MEM logic (see host_align.h).  All arithmetic that decides output bytes
 // (float/double compares, (int)(x+.499) roundings, unstable sort ties) is kept in the reference's types and order.
 #include "host_align.h"
+#include <atomic>
 #include "util.h"
 #include <cmath>
 #include <cstdio>
@@ -28,8 +29,34 @@ AlignCtx &align_ctx()
 	return ctx;
 }
 
+/* ------------------------------------------------------------------ cycle accounting (B200_HOST_PROF) */
+static const bool g_prof_on = getenv("B200_HOST_PROF") != nullptr;
+static std::atomic<uint64_t> g_prof_cyc[HP_N], g_prof_cnt[HP_N];
+struct ProfTls { uint64_t cyc[HP_N], cnt[HP_N]; };
+static thread_local ProfTls t_prof;
+struct ProfScope {
+	int k; uint64_t t0;
+	explicit ProfScope(int k_) : k(k_), t0(g_prof_on ? __builtin_ia32_rdtsc() : 0) {}
+	~ProfScope() { if (g_prof_on) { ProfTls &p = t_prof; p.cyc[k] += __builtin_ia32_rdtsc() - t0; ++p.cnt[k]; } }
+};
+void host_prof_flush()
+{
+	if (!g_prof_on) return;
+	ProfTls &p = t_prof;
+	for (int k = 0; k < HP_N; ++k) { g_prof_cyc[k] += p.cyc[k]; g_prof_cnt[k] += p.cnt[k]; p.cyc[k] = p.cnt[k] = 0; }
+}
+void host_prof_report(const char *what)
+{
+	if (!g_prof_on) return;
+	static const char *name[HP_N] = { "sam_pe_finish", "mark_primary", "pair_ends", "gen_alt", "reg2aln", "gen_cigar", "aln2sam", "dup_cstr", "reg2sam" };
+	fprintf(stderr, "[host_prof] %s:", what);
+	for (int k = 0; k < HP_N; ++k) fprintf(stderr, " %s %.1f Mcyc/%lluk", name[k], g_prof_cyc[k].exchange(0) * 1e-6, (unsigned long long)(g_prof_cnt[k].exchange(0) / 1000));
+	fprintf(stderr, "\n");
+}
+
 char *dup_cstr(const std::string &s)
 {
+	ProfScope ps(HP_DUP);
 	char *p = (char *)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size());
 	p[s.size()] = 0;
@@ -80,6 +107,19 @@ void bns_clip_window(const bntseq_t *bns, int64_t *beg, int64_t mid, int64_t *en
 
 static inline int pac_base(const uint8_t *pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
 
+// four base codes per pac byte, first base in the low byte of the word (forward) / complemented and reversed (reverse strand)
+static const struct PacLut {
+	uint32_t fwd[256], rev[256];
+	PacLut()
+	{
+		for (int b = 0; b < 256; ++b) {
+			const uint32_t c0 = b >> 6 & 3, c1 = b >> 4 & 3, c2 = b >> 2 & 3, c3 = b & 3;
+			fwd[b] = c0 | c1 << 8 | c2 << 16 | c3 << 24;
+			rev[b] = (3 - c3) | (3 - c2) << 8 | (3 - c1) << 16 | (3 - c0) << 24;
+		}
+	}
+} kPacLut;
+
 void bns_get_seq_h(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, std::vector<uint8_t> &seq)
 {
 	seq.clear();
@@ -88,12 +128,19 @@ void bns_get_seq_h(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, 
 	if (beg < 0) beg = 0;
 	if (beg >= l_pac || end <= l_pac) {
 		seq.resize(end - beg);
+		uint8_t *d = seq.data();
 		int64_t l = 0;
-		if (beg >= l_pac) {
+		if (beg >= l_pac) {                        // reverse strand: complement of forward [beg_f+1, end_f], last base first
 			int64_t beg_f = (l_pac << 1) - 1 - end, end_f = (l_pac << 1) - 1 - beg;
-			for (int64_t k = end_f; k > beg_f; --k) seq[l++] = 3 - pac_base(pac, k);
+			int64_t k = end_f;
+			for (; k > beg_f && (k & 3) != 3; --k) d[l++] = 3 - pac_base(pac, k);
+			for (; k - 3 > beg_f; k -= 4) { const uint32_t w = kPacLut.rev[pac[k >> 2]]; memcpy(d + l, &w, 4); l += 4; }
+			for (; k > beg_f; --k) d[l++] = 3 - pac_base(pac, k);
 		} else {
-			for (int64_t k = beg; k < end; ++k) seq[l++] = pac_base(pac, k);
+			int64_t k = beg;
+			for (; k < end && (k & 3); ++k) d[l++] = pac_base(pac, k);
+			for (; k + 4 <= end; k += 4) { const uint32_t w = kPacLut.fwd[pac[k >> 2]]; memcpy(d + l, &w, 4); l += 4; }
+			for (; k < end; ++k) d[l++] = pac_base(pac, k);
 		}
 	}
 }
@@ -357,6 +404,7 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
                const uint8_t *pac, int l_query, uint8_t *query, int64_t rb, int64_t re, int *score,
                std::vector<uint32_t> *cigar, int *NM, std::string *md, const GlobalRes *pre)
 {
+	ProfScope ps(HP_GEN_CIGAR);
 	if (cigar) cigar->clear();
 	if (NM) *NM = -1;
 	if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
@@ -811,6 +859,7 @@ bool reg_global_job(const mem_opt_t *opt, const bntseq_t *bns, const mem_alnreg_
 void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int l_query, const char *query_,
              const mem_alnreg_t *ar, Aln *out)
 {
+	ProfScope ps(HP_REG2ALN);
 	Aln &a = *out;
 	a = Aln();
 	a.pos = 0; a.rid = 0;
@@ -822,7 +871,10 @@ void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int 
 	int64_t pos, rb, re;
 	qb = ar->qb; qe = ar->qe;
 	rb = ar->rb; re = ar->re;
-	std::vector<uint8_t> query(l_query);
+	uint8_t query_stack[512];                      // (gen_cigar reverses its query in place and restores it: work on a copy)
+	std::vector<uint8_t> query_heap;
+	uint8_t *query = query_stack;
+	if (l_query > (int)sizeof query_stack) { query_heap.resize(l_query); query = query_heap.data(); }
 	for (i = 0; i < l_query; ++i)
 		query[i] = query_[i] < 5 ? query_[i] : kNt4[(uint8_t)query_[i]];
 	a.mapq = ar->secondary < 0 ? (approx_mapq_se(opt, ar) & 0xff) : 0;
@@ -887,6 +939,7 @@ static inline int pri_idx(double XA_drop_ratio, const mem_alnreg_t *a, int i)
 bool gen_alt(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const RegVec &a, int l_query,
              const char *query, std::vector<std::string> &XA)
 {
+	ProfScope ps(HP_GEN_ALT);
 	const int n = (int)a.size();
 	std::vector<int> cnt(n, 0);
 	std::vector<char> has_alt(n, 0);
@@ -946,6 +999,7 @@ static inline void put_cigar(const mem_opt_t *opt, const AlnView &p, std::string
 void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const bseq1_t *s, int n, const Aln *list,
              int which, const Aln *m_)
 {
+	ProfScope ps(HP_ALN2SAM);
 	AlnView p(list[which]);
 	AlnView mt(m_ ? *m_ : list[which]);
 	AlnView *m = m_ ? &mt : nullptr;
@@ -1054,6 +1108,7 @@ void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const 
 void reg2sam(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq1_t *s, RegVec &a, int extra_flag,
              const Aln *m)
 {
+	ProfScope ps(HP_REG2SAM);
 	std::string str;
 	std::vector<Aln> aa;
 	std::vector<std::string> XA;
@@ -1096,18 +1151,23 @@ void reg2sam(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq
 void sam_pe_finish(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4],
                    uint64_t id, bseq1_t s[2], RegVec a[2])
 {
+	ProfScope ps(HP_SAM_PE);
 	int i, j, z[2], o, subo, n_sub, extra_flag = 1, n_pri[2];
 	Aln h[2], g[2];
 	std::vector<Aln> aa[2];
-	n_pri[0] = mark_primary_se(opt, (int)a[0].size(), a[0].data(), id << 1 | 0);
-	n_pri[1] = mark_primary_se(opt, (int)a[1].size(), a[1].data(), id << 1 | 1);
+	{
+		ProfScope pm(HP_MARK_PRIMARY);
+		n_pri[0] = mark_primary_se(opt, (int)a[0].size(), a[0].data(), id << 1 | 0);
+		n_pri[1] = mark_primary_se(opt, (int)a[1].size(), a[1].data(), id << 1 | 1);
+	}
 	if (opt->flag & MEM_F_PRIMARY5) {
 		reorder_primary5(opt->T, a[0]);
 		reorder_primary5(opt->T, a[1]);
 	}
 	bool paired_out = false;
-	if (!(opt->flag & MEM_F_NOPAIRING) && n_pri[0] && n_pri[1] &&
-	    (o = pair_ends(opt, bns, pes, a, (int)id, &subo, &n_sub, z, n_pri)) > 0) {
+	o = 0;
+	if (!(opt->flag & MEM_F_NOPAIRING) && n_pri[0] && n_pri[1]) { ProfScope pp(HP_PAIR); o = pair_ends(opt, bns, pes, a, (int)id, &subo, &n_sub, z, n_pri); }
+	if (o > 0) {
 		int is_multi[2], q_pe, score_un, q_se[2];
 		for (i = 0; i < 2; ++i) {
 			for (j = 1; j < n_pri[i]; ++j)

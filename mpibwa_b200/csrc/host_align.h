@@ -111,6 +111,12 @@ void reg2sam(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq
 void sam_pe_finish(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, const mem_pestat_t pes[4],
                    uint64_t id, bseq1_t s[2], RegVec a[2]);
 
+// Cycle accounting of the SAM sweep (B200_HOST_PROF=1; printed per call at verbosity >= 3): where the host threads spend
+// their time.  Thread-local accumulators, flushed by host_prof_flush() at the end of a block of pairs.
+enum { HP_SAM_PE = 0, HP_MARK_PRIMARY, HP_PAIR, HP_GEN_ALT, HP_REG2ALN, HP_GEN_CIGAR, HP_ALN2SAM, HP_DUP, HP_REG2SAM, HP_N };
+void host_prof_flush();
+void host_prof_report(const char *what);      // prints and resets
+
 char *dup_cstr(const std::string &s);   // malloc()ed copy (the host free()s seqs[i].sam)
 
 } // namespace b200

@@ -717,6 +717,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 			}
 			cx.mode = AlignCtx::DIRECT; cx.jobs = nullptr; cx.res = nullptr; cx.n_jobs = 0;
 			n_host_dp += cx.n_host_dp;
+			host_prof_flush();
 		});
 		st.n_global_host = n_host_dp;
 	}
@@ -746,6 +747,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		        "mem_process_seqs", n_all, st.ms_total * 1e-3, engine_kind(), (int)lanes.size(), lanes.size() > 1 ? "s" : "", st.ms_seed, st.ms_chain_host,
 		        st.ms_extend, st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
 	if (stats_out) *stats_out = st;
+	host_prof_report("SAM sweep");
 	std::lock_guard<std::mutex> lk(g_slot_mu);
 	g_last_stats = st;
 }

@@ -1045,7 +1045,12 @@ void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const 
 			if ((cig[0] & 0xf) == 4 || (cig[0] & 0xf) == 3) qb += cig[0] >> 4;
 			if ((cig[p.n_cigar - 1] & 0xf) == 4 || (cig[p.n_cigar - 1] & 0xf) == 3) qe -= cig[p.n_cigar - 1] >> 4;
 		}
-		for (int i = qb; i < qe; ++i) str.push_back("ACGTN"[(int)s->seq[i]]);
+		if (qe > qb) {
+			const size_t at = str.size();
+			str.resize(at + (size_t)(qe - qb));
+			char *d = &str[at];
+			for (int i = qb; i < qe; ++i) *d++ = "ACGTN"[(int)s->seq[i]];
+		}
 		str.push_back('\t');
 		if (s->qual) str.append(s->qual + qb, qe > qb ? qe - qb : 0);
 		else str.push_back('*');
@@ -1055,10 +1060,18 @@ void aln2sam(const mem_opt_t *opt, const bntseq_t *bns, std::string &str, const 
 			if ((cig[0] & 0xf) == 4 || (cig[0] & 0xf) == 3) qe -= cig[0] >> 4;
 			if ((cig[p.n_cigar - 1] & 0xf) == 4 || (cig[p.n_cigar - 1] & 0xf) == 3) qb += cig[p.n_cigar - 1] >> 4;
 		}
-		for (int i = qe - 1; i >= qb; --i) str.push_back("TGCAN"[(int)s->seq[i]]);
+		const size_t nq = qe > qb ? (size_t)(qe - qb) : 0;
+		size_t at = str.size();
+		str.resize(at + nq);
+		char *d = &str[at];
+		for (int i = qe - 1; i >= qb; --i) *d++ = "TGCAN"[(int)s->seq[i]];
 		str.push_back('\t');
-		if (s->qual) { for (int i = qe - 1; i >= qb; --i) str.push_back(s->qual[i]); }
-		else str.push_back('*');
+		if (s->qual) {
+			at = str.size();
+			str.resize(at + nq);
+			d = &str[at];
+			for (int i = qe - 1; i >= qb; --i) *d++ = s->qual[i];
+		} else str.push_back('*');
 	}
 
 	if (p.n_cigar) {
@@ -1230,6 +1243,7 @@ void sam_pe_finish(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 				}
 			}
 			std::string str;
+			str.reserve(640);
 			for (i = 0; i < (int)aa[0].size(); ++i)
 				aln2sam(opt, bns, str, &s[0], (int)aa[0].size(), aa[0].data(), i, &h[1]);
 			s[0].sam = dup_cstr(str); str.clear();

@@ -120,16 +120,11 @@ static const struct PacLut {
 	}
 } kPacLut;
 
-void bns_get_seq_h(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, std::vector<uint8_t> &seq)
+// bns_get_seq into a caller buffer of end - beg bytes (0 <= beg <= end <= 2 l_pac); returns the number of bases written
+static int64_t bns_get_seq_raw(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, uint8_t *d)
 {
-	seq.clear();
-	if (end < beg) std::swap(beg, end);
-	if (end > l_pac << 1) end = l_pac << 1;
-	if (beg < 0) beg = 0;
+	int64_t l = 0;
 	if (beg >= l_pac || end <= l_pac) {
-		seq.resize(end - beg);
-		uint8_t *d = seq.data();
-		int64_t l = 0;
 		if (beg >= l_pac) {                        // reverse strand: complement of forward [beg_f+1, end_f], last base first
 			int64_t beg_f = (l_pac << 1) - 1 - end, end_f = (l_pac << 1) - 1 - beg;
 			int64_t k = end_f;
@@ -142,6 +137,19 @@ void bns_get_seq_h(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, 
 			for (; k + 4 <= end; k += 4) { const uint32_t w = kPacLut.fwd[pac[k >> 2]]; memcpy(d + l, &w, 4); l += 4; }
 			for (; k < end; ++k) d[l++] = pac_base(pac, k);
 		}
+	}
+	return l;
+}
+
+void bns_get_seq_h(int64_t l_pac, const uint8_t *pac, int64_t beg, int64_t end, std::vector<uint8_t> &seq)
+{
+	seq.clear();
+	if (end < beg) std::swap(beg, end);
+	if (end > l_pac << 1) end = l_pac << 1;
+	if (beg < 0) beg = 0;
+	if (beg >= l_pac || end <= l_pac) {
+		seq.resize(end - beg);
+		bns_get_seq_raw(l_pac, pac, beg, end, seq.data());
 	}
 }
 
@@ -408,13 +416,22 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 	if (cigar) cigar->clear();
 	if (NM) *NM = -1;
 	if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return false;
-	std::vector<uint8_t> rseq;
-	bns_get_seq_h(l_pac, pac, rb, re, rseq);
-	int64_t rlen = (int64_t)rseq.size();
+	std::vector<uint8_t> rseq_heap;
+	uint8_t rseq_stack[1024 + 8];
+	uint8_t *rseq = rseq_stack;
+	int64_t rlen;
+	if (re - rb <= 1024 && rb >= 0 && re <= l_pac << 1) {      // the common case: no heap traffic for the window
+		rlen = bns_get_seq_raw(l_pac, pac, rb, re, rseq_stack);
+	} else {
+		bns_get_seq_h(l_pac, pac, rb, re, rseq_heap);
+		rseq_heap.resize(rseq_heap.size() + 8);
+		rseq = rseq_heap.data();
+		rlen = (int64_t)rseq_heap.size() - 8;
+	}
 	if (re - rb != rlen) return false;
 	if (rb >= l_pac) {
 		std::reverse(query, query + l_query);
-		std::reverse(rseq.begin(), rseq.end());
+		std::reverse(rseq, rseq + rlen);
 	}
 	if (pre) {                                    // alignment already done by the CIGAR stage on the device
 		cigar->assign(pre->cigar, pre->cigar + pre->n_cigar);
@@ -434,7 +451,7 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 		w = w < w_ ? w : w_;
 		min_w = abs((int)rlen - l_query) + 3;
 		w = w > min_w ? w : min_w;
-		*score = global_align(l_query, query, (int)rlen, rseq.data(), mat, o_del, e_del, o_ins, e_ins, w, cigar);
+		*score = global_align(l_query, query, (int)rlen, rseq, mat, o_del, e_del, o_ins, e_ins, w, cigar);
 	}
 	if (NM && cigar) {
 		int x = 0, y = 0, u = 0, n_mm = 0, n_gap = 0;
@@ -445,6 +462,11 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 			int op = (*cigar)[k] & 0xf, len = (*cigar)[k] >> 4;
 			if (op == 0) {
 				for (int i = 0; i < len; ++i) {
+					if (i + 8 <= len) {                   // eight equal bases at a time (most of a read matches)
+						uint64_t qa, ra;
+						memcpy(&qa, query + x + i, 8); memcpy(&ra, rseq + y + i, 8);
+						if (qa == ra) { u += 8; i += 7; continue; }
+					}
 					if (query[x + i] != rseq[y + i]) {
 						put_int(*md, u);
 						md->push_back(int2base[rseq[y + i]]);
@@ -871,12 +893,17 @@ void reg2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, int 
 	int64_t pos, rb, re;
 	qb = ar->qb; qe = ar->qe;
 	rb = ar->rb; re = ar->re;
-	uint8_t query_stack[512];                      // (gen_cigar reverses its query in place and restores it: work on a copy)
+	// gen_cigar reverses the query of a reverse-strand region in place (and restores it), so those work on a copy; an
+	// already encoded read (first byte a code: all are) with a forward-strand region is used where it lies
+	uint8_t query_stack[512];
 	std::vector<uint8_t> query_heap;
 	uint8_t *query = query_stack;
-	if (l_query > (int)sizeof query_stack) { query_heap.resize(l_query); query = query_heap.data(); }
-	for (i = 0; i < l_query; ++i)
-		query[i] = query_[i] < 5 ? query_[i] : kNt4[(uint8_t)query_[i]];
+	if (l_query > 0 && (uint8_t)query_[0] < 5 && rb < bns->l_pac) query = (uint8_t *)const_cast<char *>(query_);
+	else {
+		if (l_query > (int)sizeof query_stack) { query_heap.resize(l_query); query = query_heap.data(); }
+		for (i = 0; i < l_query; ++i)
+			query[i] = query_[i] < 5 ? query_[i] : kNt4[(uint8_t)query_[i]];
+	}
 	a.mapq = ar->secondary < 0 ? (approx_mapq_se(opt, ar) & 0xff) : 0;
 	if (ar->secondary >= 0) a.flag |= 0x100;
 	w2 = reg_first_band(opt, ar);

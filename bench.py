@@ -238,6 +238,14 @@ def kernel_table(agg, K, i32_peak, hbm_peak):
 
 
 def main():
+    # rank 0 prints exactly ONE line on stdout: everything libraries write there meanwhile (NCCL's version banner ...) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     args = parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,7 +255,7 @@ def main():
         if rank != 0:
             return 0
         prefix = ensure_index(args)
-        print(json.dumps(reference_arm(args, prefix)), flush=True)
+        emit(reference_arm(args, prefix))
         return 0
 
     import numpy as np
@@ -258,7 +266,6 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -505,7 +512,7 @@ def main():
         reads, sec = run_ref_driver(prefix, s1, s2, args.K, cores)
         line["cpu_baseline"] = {"value": (reads // 2) / sec, "unit": "pairs/s", "cores": cores, "kind": "reference",
                                 "sample": "first %d pairs of the workload, chunked at -K %d, -t %d (%.2f s in mem_process_seqs)" % (n, args.K, cores, sec)}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -420,8 +420,19 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 	uint8_t rseq_stack[1024 + 8];
 	uint8_t *rseq = rseq_stack;
 	int64_t rlen;
+	bool rseq_reversed = false;
 	if (re - rb <= 1024 && rb >= 0 && re <= l_pac << 1) {      // the common case: no heap traffic for the window
-		rlen = bns_get_seq_raw(l_pac, pac, rb, re, rseq_stack);
+		if (rb >= l_pac) {
+			// the reverse-strand window is needed back to front (below): that is the complement of the forward strand read
+			// in ascending order, fetched directly instead of fetching and reversing
+			const int64_t beg_f = (l_pac << 1) - 1 - re, end_f = (l_pac << 1) - 1 - rb;
+			int64_t l = 0, k = beg_f + 1;
+			for (; k <= end_f && (k & 3); ++k) rseq_stack[l++] = 3 - pac_base(pac, k);
+			for (; k + 4 <= end_f + 1; k += 4) { const uint32_t w = 0x03030303u - kPacLut.fwd[pac[k >> 2]]; memcpy(rseq_stack + l, &w, 4); l += 4; }
+			for (; k <= end_f; ++k) rseq_stack[l++] = 3 - pac_base(pac, k);
+			rlen = l;
+			rseq_reversed = true;
+		} else rlen = bns_get_seq_raw(l_pac, pac, rb, re, rseq_stack);
 	} else {
 		bns_get_seq_h(l_pac, pac, rb, re, rseq_heap);
 		rseq_heap.resize(rseq_heap.size() + 8);
@@ -431,15 +442,22 @@ bool gen_cigar(const int8_t mat[25], int o_del, int e_del, int o_ins, int e_ins,
 	if (re - rb != rlen) return false;
 	if (rb >= l_pac) {
 		std::reverse(query, query + l_query);
-		std::reverse(rseq, rseq + rlen);
+		if (!rseq_reversed) std::reverse(rseq, rseq + rlen);
 	}
 	if (pre) {                                    // alignment already done by the CIGAR stage on the device
 		cigar->assign(pre->cigar, pre->cigar + pre->n_cigar);
 		*score = pre->score;
 	} else if (l_query == re - rb && w_ == 0) {
 		if (cigar) cigar->push_back((uint32_t)l_query << 4 | 0);
-		int sc = 0;
-		for (int i = 0; i < l_query; ++i) sc += mat[rseq[i] * 5 + query[i]];
+		int sc = 0, i = 0;
+		if (mat[0] == mat[6] && mat[0] == mat[12] && mat[0] == mat[18])      // eight equal non-N bases at a time
+			for (; i + 8 <= l_query; i += 8) {
+				uint64_t qa, ra;
+				memcpy(&qa, query + i, 8); memcpy(&ra, rseq + i, 8);
+				if (qa == ra && !(qa & 0x0404040404040404ull)) sc += 8 * mat[0];
+				else for (int k = i; k < i + 8; ++k) sc += mat[rseq[k] * 5 + query[k]];
+			}
+		for (; i < l_query; ++i) sc += mat[rseq[i] * 5 + query[i]];
 		*score = sc;
 	} else {
 		int w, max_gap, max_ins, max_del, min_w;

@@ -286,6 +286,50 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
     assert got3 == want
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+def test_odd_reads_vs_compiled_reference(tmp_path):
+    """reads the simulator never makes - shorter than a seed, all N, homopolymers, exact copies of the reference, mates
+    of very different lengths, reads long enough for mem_flt_chained_seeds (which moves the batch to the host chaining) -
+    mixed into ordinary pairs: SAM == the compiled reference's, with blocking calls and with chunk jobs"""
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(1_500_000, 3, seed=71)
+    prefix = str(tmp_path / "ref.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+    rng = np.random.default_rng(5)
+    B = np.frombuffer(b"ACGTN", np.uint8)
+
+    def ref_piece(L, rc=False):
+        s0 = int(rng.integers(1000, int(lengths[0]) - L - 1000))
+        c = codes[s0:s0 + L]
+        return B[(3 - c[::-1]) if rc else c].tobytes()
+
+    odd = [(b"A", b"C"), (b"ACGTA", ref_piece(150)), (ref_piece(18), ref_piece(19)), (ref_piece(20, True), ref_piece(21)),
+           (b"N" * 150, ref_piece(150)), (b"A" * 150, b"T" * 150), (ref_piece(150), ref_piece(150, True)),
+           (ref_piece(75) + b"NNNNN" + ref_piece(70), ref_piece(150)), (ref_piece(150), ref_piece(35)),
+           (ref_piece(260), ref_piece(300, True)), (b"ACGT" * 40, b"AC" * 75), (ref_piece(100) + ref_piece(100, True), ref_piece(150))]
+
+    def block(pairs, tag):
+        a, b = [], []
+        for k, (x, y) in enumerate(pairs):
+            a.append(b"@%s%04d/1\n%s\n+\n%s\n" % (tag, k, x, b"F" * len(x)))
+            b.append(b"@%s%04d/2\n%s\n+\n%s\n" % (tag, k, y, b"F" * len(y)))
+        return b"".join(a), b"".join(b)
+
+    n1, n2 = simulate.simulate_pairs(codes, lengths, 3000, seed=9)
+    o1, o2 = block(odd, b"odd")
+    l1, l2 = simulate.simulate_pairs(codes, lengths, 24, read_len=800, ins_mean=1500, ins_sd=100, seed=10, prefix="long")
+    m1, m2 = simulate.simulate_pairs(codes, lengths, 1000, seed=11, prefix="tail")
+    for name, (r1, r2) in {"short": (n1 + o1 + m1, n2 + o2 + m2), "long": (n1 + l1 + o1 + m1, n2 + l2 + o2 + m2)}.items():
+        f1, f2 = str(tmp_path / (name + "_1.fq")), str(tmp_path / (name + "_2.fq"))
+        open(f1, "wb").write(r1); open(f2, "wb").write(r2)
+        want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16", "-T", "-K", "400000", prefix, f1, f2],
+                              capture_output=True, check=True).stdout
+        a = M.Aligner(prefix, device=0, n_threads=16, verbose=1)
+        assert a.align(r1, r2, K=400000, trimmed=True) == want, name
+        assert a.align_pipelined(r1, r2, K=400000, trimmed=True) == want, name
+        assert want.count(b"\n") >= 2 * (4000 + len(odd))
+
+
 def test_properties_at_scale(tmp_path):
     """size-independent properties on a larger run: thread-count invariance, idempotence, record accounting"""
     from mpibwa_b200 import simulate, index_build

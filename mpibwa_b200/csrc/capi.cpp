@@ -24,7 +24,8 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs);
 struct SeqJob;
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
-                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *), void *arg, int want_lanes);
+                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks);
+int64_t job_take_sam(SeqJob *j, int n_threads, char **out);
 void process_seqs_end(SeqJob *j, b200_stats_t *stats);
 void last_stats(b200_stats_t *out);
 
@@ -388,6 +389,7 @@ struct b200_job {
 	SeqJob *job;
 	bseq1_t *seqs; int64_t total;       // b200_align_chunk_begin: the interleaved mates and the SAM collected by the job thread
 	char *sam; int64_t sam_len;
+	int n_threads;
 };
 
 b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
@@ -395,7 +397,7 @@ b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, cons
 {
 	b200_job *j = new b200_job();
 	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
-	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 1);
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 1, false);
 	return j;
 }
 
@@ -411,8 +413,10 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->total = s2 ? 2 * n : n;
 	j->seqs = b200_chunk_seqs(n, s1, s2);
 	j->sam = nullptr; j->sam_len = 0;
+	j->n_threads = opt->n_threads;
+	// the records are written block-wise by the SAM sweep (no malloc per read) and concatenated by the job thread
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
-		[](void *p) { b200_job *x = (b200_job *)p; x->sam_len = b200_collect_sam(x->total, x->seqs, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, 1);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, x->n_threads, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, 1, true);
 	return j;
 }
 
@@ -424,6 +428,12 @@ int64_t b200_align_chunk_end(b200_job_t *j, char **sam, int64_t *sam_len, b200_s
 	if (sam_len) *sam_len = j->sam_len;
 	delete j;
 	return total;
+}
+
+int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2,
+                         char **sam, int64_t *sam_len)
+{
+	return b200_align_chunk_end(b200_align_chunk_begin(opt, idx, n_processed, n, s1, s2), sam, sam_len, nullptr);
 }
 
 void b200_get_stats(b200_stats_t *out)

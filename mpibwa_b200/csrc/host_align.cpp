@@ -57,6 +57,7 @@ void host_prof_report(const char *what)
 char *dup_cstr(const std::string &s)
 {
 	ProfScope ps(HP_DUP);
+	if (std::string *sink = align_ctx().sink) { sink->append(s); return nullptr; }
 	char *p = (char *)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size());
 	p[s.size()] = 0;

@@ -49,6 +49,7 @@ struct AlignCtx {
 	const char *seq_ptr[2] = { nullptr, nullptr };
 	int read_idx[2] = { 0, 0 };
 	int64_t n_host_dp = 0;               // regions the sweep had to align itself (not queued, or CIGAR too long for the record)
+	std::string *sink = nullptr;         // when set, SAM records are appended here (input order within a block of pairs) instead of malloc()ed per read
 };
 AlignCtx &align_ctx();                   // thread-local
 

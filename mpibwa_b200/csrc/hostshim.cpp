@@ -4,8 +4,8 @@
 //   b200_fastq_parse    in-place fastq parse into bseq1_t      reference src/mainParallel.c:1257-1304
 //   b200_plan_chunks    "close the chunk when bases > maxsiz"  reference src/parallel_aux.c:1532-1549 (same-size
 //                       pairs: R1 bases vs K/2), :1068-1082 (trimmed pairs: R1+R2 vs K), src/mainParallel.c:2773 (SE)
-//   b200_align_chunk    interleave mates, mem_process_seqs, concatenate seqs[i].sam in input order
-//                       reference src/mainParallel.c:1271-1314 and copy_buffer_thr :103-127
+//   b200_chunk_seqs / b200_collect_sam   interleave mates; concatenate seqs[i].sam in input order
+//                       reference src/mainParallel.c:1271-1314 and copy_buffer_thr :103-127 (b200_align_chunk itself: capi.cpp)
 #include "../../include/mpibwa_b200.h"
 #include <cctype>
 #include <cstdlib>
@@ -133,18 +133,6 @@ int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam)
 	});
 	if (buf) { buf[sum] = 0; *sam = buf; }
 	return (int64_t)sum;
-}
-
-int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2,
-                         char **sam, int64_t *sam_len)
-{
-	const int64_t total = s2 ? 2 * n : n;
-	bseq1_t *seqs = b200_chunk_seqs(n, s1, s2);
-	mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)total, seqs, nullptr);
-	int64_t l = b200_collect_sam(total, seqs, sam);
-	if (sam_len) *sam_len = l;
-	free(seqs);
-	return total;
 }
 
 void b200_free(void *p) { free(p); }

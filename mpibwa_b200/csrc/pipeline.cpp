@@ -233,6 +233,10 @@ static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, cons
 // its own; two driver threads walk the lanes so that one lane's host stage overlaps the other lane's device stage.
 struct Lane { Engine *eng; int r0, n; };
 
+// SAM text of a chunk as blocks of consecutive records (b200_align_chunk: the caller wants one buffer, so the sweep appends
+// the records of a block of pairs to one string instead of malloc()ing seqs[i].sam per read and concatenating afterwards)
+struct SamBlocks { std::vector<std::vector<std::string>> lane; };      // [lane][block], in input order
+
 static std::vector<Lane> make_lanes(int n, int slot, int want_default)
 {
 	// A synchronous mem_process_seqs call runs its chunk as two lanes: enough to overlap one lane's host stage with the
@@ -310,10 +314,11 @@ static void drive_lanes(std::vector<Lane> &lanes, F body)
 
 static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                               int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0,
-                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out)
+                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamBlocks *sam_blocks)
 {
 	engine_for(bwt, bns, pac);
 	std::vector<Lane> lanes = make_lanes(n_all, slot, want_lanes);
+	if (sam_blocks) sam_blocks->lane.assign(lanes.size(), std::vector<std::string>());
 	if (staged && (int)lanes.size() != want_lanes) { fprintf(stderr, "[mpibwa_b200] staged reads do not match the lane split of the call\n"); abort(); }
 	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
@@ -706,16 +711,23 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		if (!gjobs.empty()) GPU_STAGE(gres = stage_global(eng, go, gjobs, zb));
 		st.ms_global = now_ms() - tg;
 		std::atomic<int64_t> n_host_dp(0);
-		parallel_for(nt, n_units, 256, [&](int, int64_t b, int64_t e) {
+		const int64_t sweep_grain = 256;
+		std::vector<std::string> *blocks = nullptr;
+		if (sam_blocks) {
+			blocks = &sam_blocks->lane[&L - lanes.data()];
+			blocks->assign((size_t)((n_units + sweep_grain - 1) / sweep_grain), std::string());
+		}
+		parallel_for(nt, n_units, sweep_grain, [&](int, int64_t b, int64_t e) {
 			AlignCtx &cx = align_ctx();
 			cx.mode = AlignCtx::LOOKUP; cx.n_host_dp = 0;
+			if (blocks) { cx.sink = &(*blocks)[(size_t)(b / sweep_grain)]; cx.sink->reserve((size_t)(e - b) * per * 448); }
 			for (int64_t u = b; u < e; ++u) {
 				const int64_t first = tbase[uj[u].tid] + uj[u].start;
 				cx.jobs = gjobs.data() + first; cx.res = gres ? gres + first : nullptr; cx.n_jobs = uj[u].count;
 				for (int k = 0; k < per; ++k) { cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
 				run_unit(u, &regs[u * per]);
 			}
-			cx.mode = AlignCtx::DIRECT; cx.jobs = nullptr; cx.res = nullptr; cx.n_jobs = 0;
+			cx.mode = AlignCtx::DIRECT; cx.jobs = nullptr; cx.res = nullptr; cx.n_jobs = 0; cx.sink = nullptr;
 			n_host_dp += cx.n_host_dp;
 			host_prof_flush();
 		});
@@ -757,11 +769,30 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 struct SeqJob {
 	std::thread th;
 	b200_stats_t stats;
+	SamBlocks sam;
 };
+
+// concatenates the SAM blocks of a finished job into one malloc()ed, NUL-terminated buffer (parallel copy); returns its length
+int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
+{
+	std::vector<const std::string *> parts;
+	for (auto &ln : j->sam.lane) for (auto &b : ln) parts.push_back(&b);
+	std::vector<size_t> at(parts.size() + 1, 0);
+	for (size_t k = 0; k < parts.size(); ++k) at[k + 1] = at[k] + parts[k]->size();
+	char *buf = (char *)malloc(at.back() + 1);
+	parallel_for(n_threads, (int64_t)parts.size(), 16, [&](int, int64_t b, int64_t e) {
+		for (int64_t k = b; k < e; ++k) memcpy(buf + at[k], parts[k]->data(), parts[k]->size());
+	});
+	buf[at.back()] = 0;
+	*out = buf;
+	const int64_t len = (int64_t)at.back();
+	j->sam.lane.clear();
+	return len;
+}
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
-                           void (*after)(void *), void *arg, int want_lanes)
+                           void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks)
 {
 	engine_for(bwt, bns, pac);
 	SeqJob *j = new SeqJob();
@@ -788,13 +819,13 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 			++g_running; ++g_ticket_serving;
 			g_slot_cv.notify_all();
 		}
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats);
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats, sam_as_blocks ? &j->sam : nullptr);
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
 			--g_running; g_slots[slot].busy = false;
 			g_slot_cv.notify_all();
 		}
-		if (after) after(arg);                   // (SAM concatenation: host work that overlaps the next chunk)
+		if (after) after(arg, j);                // (SAM concatenation: host work that overlaps the next chunk)
 	});
 	return j;
 }
@@ -809,7 +840,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2, false), nullptr);
 }
 
 } // namespace b200

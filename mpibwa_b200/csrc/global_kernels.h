@@ -33,7 +33,8 @@ struct GlobalJob {
 
 struct GlobalRes {
 	int32_t score;
-	int32_t n_cigar;        // < 0: more than B200_GLOBAL_MAX_CIGAR operations - the caller redoes this region itself
+	int32_t n_cigar;        // -1: more than B200_GLOBAL_MAX_CIGAR operations - the caller redoes this region itself;
+	                        // -2 (device-internal): a retry needed a wider row window than the launch had - rerun in a wider class
 	int32_t n_tries, pad;
 	uint32_t cigar[B200_GLOBAL_MAX_CIGAR];
 };
@@ -168,8 +169,10 @@ B200_HDN int global_dp(const GlobalOpt &o, const SEQ &s, int tlen, int w, ROW eh
 }
 
 // the band-doubling loop of mem_reg2aln around bwa_gen_cigar2 (reference src/bwamem.c:1112-1122)
+// max_band: widest band the row accessor can hold (0x7fffffff: any)
 template <class ROW, class SEQ>
-B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb, ROW eh, uint8_t *z, GlobalRes *out, int64_t *cells)
+B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb, ROW eh, uint8_t *z, GlobalRes *out, int64_t *cells,
+                          int max_band = 0x7fffffff)
 {
 	const int l_query = s.l_query, rlen = (int)(jb.re - jb.rb);
 	int w2 = jb.w2, last_sc = -(1 << 30), score = 0, n_cigar = 0, i = 0;
@@ -182,6 +185,7 @@ B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb,
 			for (int x = 0; x < l_query; ++x) score += s.sub(s.trow(o, x), x);
 		} else {
 			const int w = global_band(o, l_query, rlen, w2);
+			if (w > max_band) { out->score = 0; out->n_cigar = -2; out->n_tries = i; out->pad = 0; return; }
 			score = global_dp(o, s, rlen, w, eh, z, out->cigar, &n_cigar, cells);
 		}
 		if (score == last_sc || w2 == o.w_max) { ++i; break; }

@@ -987,10 +987,13 @@ bool gen_alt(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, cons
 {
 	ProfScope ps(HP_GEN_ALT);
 	const int n = (int)a.size();
-	std::vector<int> cnt(n, 0);
-	std::vector<char> has_alt(n, 0);
 	int i, r, tot = 0;
 	XA.clear();
+	// most reads have no secondary hit within XA_drop_ratio of its primary: find that out before allocating anything
+	for (i = 0; i < n; ++i) if (pri_idx(opt->XA_drop_ratio, a.data(), i) >= 0) break;
+	if (i == n) return false;
+	std::vector<int> cnt(n, 0);
+	std::vector<char> has_alt(n, 0);
 	for (i = 0; i < n; ++i) {
 		r = pri_idx(opt->XA_drop_ratio, a.data(), i);
 		if (r >= 0) {

@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t
 		const uint8_t *q = codes + off[j.read] + j.qb;
 		for (int x = 0; x < s.l_query; ++x) Q[ext_qidx(x)] = s.rev ? q[s.l_query - 1 - x] : q[x];
 		GlobalRowSh eh = { rows, S - 1 };
-		global_task(go, s, j, eh, z + j.zoff, &res[jx], &cells);
+		global_task(go, s, j, eh, z + j.zoff, &res[jx], &cells, (S - 2) >> 1);
 	}
 	warp_add(&cnt->global_cells, cells);
 }
@@ -1188,67 +1188,82 @@ const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<
 	if (n == 0) return nullptr;
 	e->zero_counters();
 	// classes by the circular window a lane needs: 32, 64, 128, 256, 512 columns; wider bands or queries over 256 bases
-	// take the general kernel
+	// take the general kernel.  The FIRST pass sizes the window for the first band mem_reg2aln tries (the band-doubling
+	// retries are rare, and sizing every lane for the widest of three tries put nearly all regions into the 128-column class
+	// at 6 warps per SM); a region whose retry outgrows its window comes back flagged and is rerun in a second pass sized for
+	// its widest try.
 	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
-	int64_t cnt[6] = { 0, 0, 0, 0, 0, 0 }, pos[6];
-	int qmax[6] = { 0, 0, 0, 0, 0, 0 };
-	// counting sort by (class, band, target length / 16): lanes of a warp get regions of similar cost
-	const int NB = 6 * 256 * 64;
-	std::vector<int32_t> bucket(NB + 1, 0);
-	std::vector<int32_t> key(n);
-	for (int64_t i = 0; i < n; ++i) {
-		const GlobalJob &j = jobs[i];
-		const int need = 2 * j.wmax + 2, ql = j.qe - j.qb;
-		int k = 5;
-		if (ql <= 256) for (int c = 0; c < 5; ++c) if (need <= cls_S[c]) { k = c; break; }
-		++cnt[k];
-		qmax[k] = std::max(qmax[k], ql);
-		const int rl = (int)std::min<int64_t>((j.re - j.rb) >> 4, 63);
-		key[i] = (k * 256 + std::min(j.wmax, 255)) * 64 + rl;
-		++bucket[key[i] + 1];
-	}
-	for (int b = 0; b < NB; ++b) bucket[b + 1] += bucket[b];
-	pos[0] = 0;
-	for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
-	std::vector<int32_t> order(n);
-	for (int64_t i = 0; i < n; ++i) order[bucket[key[i]]++] = (int32_t)i;
 	GlobalJob *dj = e->b_gjobs.as<GlobalJob>(n);
 	GlobalRes *dr = e->b_gres.as<GlobalRes>(n);
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);
 	uint8_t *z = e->b_gz.as<uint8_t>((size_t)z_bytes + 64);
 	e->h2d(dj, jobs.data(), sizeof(GlobalJob) * n);
-	e->h2d(d_ord, order.data(), sizeof(int32_t) * n);
 	static bool attr_set = false;
 	if (!attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
-	e->tic();
-	CK(cudaEventRecord(e->ev_fork, e->stream));
-	int used = 0;
-	for (int k = 5; k >= 0; --k) {
-		if (cnt[k] == 0) continue;
-		cudaStream_t st = e->side[used % Engine::N_SIDE];
-		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-		const int nk = (int)cnt[k];
-		if (k < 5) {
-			const int S = cls_S[k], qcap = qmax[k];
-			const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-			const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
-			k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
-				(const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, z, dr, S, qcap, e->d_cnt);
-		} else {
-			const int64_t stride = ((int64_t)nk + 31) & ~31ll;
-			int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
-			k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], (const int64_t *)e->d_off.p,
-				(const uint8_t *)e->d_codes.p, rows, stride, z, dr, e->d_cnt);
-		}
-		CK(cudaGetLastError());
-		CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
-		e->stats.n_launches += 1;
-		++used;
-	}
-	for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
-	e->stats.ms_k_global += e->toc();
 	GlobalRes *hr = (GlobalRes *)e->h_gres.need(sizeof(GlobalRes) * n);
-	e->d2h(hr, dr, sizeof(GlobalRes) * n);
+	std::vector<int32_t> sel(n), order, key;
+	const bool squeeze = getenv("B200_GLOBAL_SQUEEZE") != nullptr;
+	for (int64_t i = 0; i < n; ++i) sel[i] = (int32_t)i;
+	for (int pass = 0; pass < 2 && !sel.empty(); ++pass) {
+		const int64_t m = (int64_t)sel.size();
+		int64_t cnt[6] = { 0, 0, 0, 0, 0, 0 }, pos[6];
+		int qmax[6] = { 0, 0, 0, 0, 0, 0 };
+		// counting sort by (class, band, target length / 16): lanes of a warp get regions of similar cost
+		const int NB = 6 * 256 * 64;
+		std::vector<int32_t> bucket(NB + 1, 0);
+		key.resize(m); order.resize(m);
+		for (int64_t x = 0; x < m; ++x) {
+			const GlobalJob &j = jobs[sel[x]];
+			const int ql = j.qe - j.qb, rl = (int)(j.re - j.rb);
+			int band = pass == 0 ? global_band(go, ql, rl, j.w2 < go.w_max ? j.w2 : go.w_max) : j.wmax;
+			if (pass == 0 && squeeze) band >>= 2;          // (tests: windows too small even for the first try - everything takes the rerun path)
+			const int need = 2 * band + 2;
+			int k = 5;
+			if (ql <= 256) for (int c = 0; c < 5; ++c) if (need <= cls_S[c]) { k = c; break; }
+			++cnt[k];
+			qmax[k] = std::max(qmax[k], ql);
+			key[x] = (k * 256 + std::min(band, 255)) * 64 + std::min(rl >> 4, 63);
+			++bucket[key[x] + 1];
+		}
+		for (int b = 0; b < NB; ++b) bucket[b + 1] += bucket[b];
+		pos[0] = 0;
+		for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
+		for (int64_t x = 0; x < m; ++x) order[bucket[key[x]]++] = sel[x];
+		e->h2d(d_ord, order.data(), sizeof(int32_t) * m);
+		e->tic();
+		CK(cudaEventRecord(e->ev_fork, e->stream));
+		int used = 0;
+		for (int k = 5; k >= 0; --k) {
+			if (cnt[k] == 0) continue;
+			cudaStream_t st = e->side[used % Engine::N_SIDE];
+			CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+			const int nk = (int)cnt[k];
+			if (k < 5) {
+				const int S = cls_S[k], qcap = qmax[k];
+				const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+				const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
+				k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
+					(const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, z, dr, S, qcap, e->d_cnt);
+			} else {
+				const int64_t stride = ((int64_t)nk + 31) & ~31ll;
+				int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
+				k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], (const int64_t *)e->d_off.p,
+					(const uint8_t *)e->d_codes.p, rows, stride, z, dr, e->d_cnt);
+			}
+			CK(cudaGetLastError());
+			CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
+			e->stats.n_launches += 1;
+			++used;
+		}
+		for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
+		e->stats.ms_k_global += e->toc();
+		e->d2h(hr, dr, sizeof(GlobalRes) * n);
+		e->sync();
+		sel.clear();
+		if (pass == 0) for (int64_t i = 0; i < n; ++i) if (hr[i].n_cigar == -2) sel.push_back((int32_t)i);
+		if (pass == 0 && getenv("B200_DEBUG")) fprintf(stderr, "[global] %lld regions, classes %lld %lld %lld %lld %lld %lld, %lld rerun with a wider window\n",
+			(long long)n, (long long)cnt[0], (long long)cnt[1], (long long)cnt[2], (long long)cnt[3], (long long)cnt[4], (long long)cnt[5], (long long)sel.size());
+	}
 	Counters c = e->read_counters();
 	e->stats.global_cells += (int64_t)c.global_cells;
 	e->stats.n_global_jobs += n;

@@ -277,6 +277,13 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
         finally:
             os.environ.pop("B200_CHAIN", None)
         assert got_m == want, mode
+    # CIGAR stage: row windows sized too small on purpose, so that every region comes back flagged and takes the rerun pass
+    os.environ["B200_GLOBAL_SQUEEZE"] = "1"
+    try:
+        got_sq = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
+    finally:
+        os.environ.pop("B200_GLOBAL_SQUEEZE", None)
+    assert got_sq == want
     # chunk jobs (b200_align_chunk_begin / _end): several chunks in flight, SAM unchanged and in input order
     assert a.align_pipelined(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args) == want
     # through the stand-alone driver binary as well (the C host path), synchronous and with chunk jobs (-P)

@@ -27,6 +27,8 @@ def main():
             os.environ[name] = v
         al.align(fq1, fq2, K=args.K)
         st = al.stats()
+        print("   stage walls (one chunk alone): seed %.1f chain %.1f extend %.1f regs %.1f rescue %.1f sam %.1f [plan %.1f cigar %.1f]" % (
+            st["ms_seed"], st["ms_chain_host"], st["ms_extend"], st["ms_regs_host"], st["ms_rescue"], st["ms_sam_host"], st["ms_sam_plan"], st["ms_global"]), flush=True)
         print("%s=%s  smem %.2f ms  sa %.2f  chain %.2f  ext_dp %.2f  ext_stage %.2f  sw %.2f  global %.2f  total %.1f" % (
             name, v, st["ms_k_smem"], st["ms_k_sa"], st["ms_k_chain"], st["ms_k_extend_dp"], st["ms_k_extend"], st["ms_k_sw"], st["ms_k_global"], st["ms_total"]), flush=True)
 

@@ -408,7 +408,8 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 {
 	const int n = r1 - r0;
 	static int blocks_per_sm = 0, n_sm = 0;
-	const int threads = 128, quota = 16;
+	static int bwd_blocks_per_sm = 0, fwd_blocks_per_sm = 0;
+	const int threads = 128, quota = 16;                                // (fewer entries in shared memory: measured slower - the spill strip is in HBM)
 	const size_t sh_bytes = (size_t)threads * quota * 16;               // interval lists
 	if (!blocks_per_sm) {
 		cudaDeviceProp prop;
@@ -427,7 +428,6 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	// throughput path: the four homogeneous sweeps of smem_sweeps.cuh; the general state machine redoes the (rare) reads
 	// whose sweep strip overflowed.  B200_SEED_KERNEL=lanes forces the general kernel for every read (parity tests).
 	const bool use_sweeps = !(getenv("B200_SEED_KERNEL") && !strcmp(getenv("B200_SEED_KERNEL"), "lanes"));
-	static int bwd_blocks_per_sm = 0, fwd_blocks_per_sm = 0;
 	if (use_sweeps && !bwd_blocks_per_sm) {
 		CK(cudaFuncSetAttribute(k_sweep_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, k_sweep_bwd, threads, sh_bytes));

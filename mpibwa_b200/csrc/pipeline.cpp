@@ -721,7 +721,20 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 			AlignCtx &cx = align_ctx();
 			cx.mode = AlignCtx::LOOKUP; cx.n_host_dp = 0;
 			if (blocks) { cx.sink = &(*blocks)[(size_t)(b / sweep_grain)]; cx.sink->reserve((size_t)(e - b) * per * 448); }
+			// a region's reference window is a random 40-byte read of the 2-bit reference (a DRAM miss per region, the largest
+			// single cost of the sweep once the arithmetic was trimmed): touch the windows of a pair a few pairs ahead
+			auto prefetch_unit = [&](int64_t v) {
+				for (int k = 0; k < per; ++k) {
+					const RegVec &rv = regs[v * per + k];
+					for (size_t x = 0; x < rv.size() && x < 3; ++x) {
+						const int64_t p = rv[x].rb < l_pac ? rv[x].rb : (l_pac << 1) - rv[x].re;
+						if (p >= 0 && p < l_pac) { __builtin_prefetch(pac + (p >> 2)); __builtin_prefetch(pac + (p >> 2) + 64); }
+					}
+				}
+			};
+			for (int64_t v = b; v < e && v < b + 4; ++v) prefetch_unit(v);
 			for (int64_t u = b; u < e; ++u) {
+				if (u + 4 < e) prefetch_unit(u + 4);
 				const int64_t first = tbase[uj[u].tid] + uj[u].start;
 				cx.jobs = gjobs.data() + first; cx.res = gres ? gres + first : nullptr; cx.n_jobs = uj[u].count;
 				for (int k = 0; k < per; ++k) { cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }

@@ -13,6 +13,8 @@ def main():
     sys.argv = sys.argv[:1]
     args = bench.parse_args()
     args.pairs = 333_334
+    if os.environ.get("B200_TUNE_REF_BP"):
+        args.ref_bp = int(os.environ["B200_TUNE_REF_BP"])
     prefix = bench.ensure_index(args)
     f1, f2 = bench.ensure_reads(args, 0, args.pairs)
     import mpibwa_b200 as M

@@ -66,6 +66,32 @@ static size_t parse_fastq(char *buf, size_t len, bseq1_t **out)
 	return n;
 }
 
+
+/* -o name=value[,name=value...]: set mem_opt_t fields by name (the scoring matrix is refilled afterwards) */
+static void set_opts(mem_opt_t *opt, const char *spec)
+{
+	char *dup = strdup(spec), *tok, *save = 0;
+	for (tok = strtok_r(dup, ",", &save); tok; tok = strtok_r(0, ",", &save)) {
+		char *eq = strchr(tok, '=');
+		if (!eq) { fprintf(stderr, "bad -o item %s\n", tok); exit(1); }
+		*eq = 0;
+		const char *v = eq + 1;
+#define OPT_I(f) else if (strcmp(tok, #f) == 0) opt->f = atoi(v)
+#define OPT_F(f) else if (strcmp(tok, #f) == 0) opt->f = (float)atof(v)
+		if (0) {}
+		OPT_I(a); OPT_I(b); OPT_I(o_del); OPT_I(e_del); OPT_I(o_ins); OPT_I(e_ins); OPT_I(pen_unpaired); OPT_I(pen_clip5); OPT_I(pen_clip3);
+		OPT_I(w); OPT_I(zdrop); OPT_I(T); OPT_I(min_seed_len); OPT_I(min_chain_weight); OPT_I(max_chain_extend); OPT_I(split_width);
+		OPT_I(max_occ); OPT_I(max_chain_gap); OPT_I(max_ins); OPT_I(max_matesw); OPT_I(max_XA_hits); OPT_I(max_XA_hits_alt);
+		OPT_F(split_factor); OPT_F(mask_level); OPT_F(drop_ratio); OPT_F(XA_drop_ratio);
+		else if (strcmp(tok, "flag") == 0) opt->flag |= atoi(v);
+		else { fprintf(stderr, "unknown -o field %s\n", tok); exit(1); }
+#undef OPT_I
+#undef OPT_F
+	}
+	free(dup);
+	bwa_fill_scmat(opt->a, opt->b, opt->mat);
+}
+
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 int main(int argc, char **argv)
@@ -73,12 +99,13 @@ int main(int argc, char **argv)
 	int c, trimmed = 0, header = 0, n_threads = 1;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THv:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THv:o:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
 		else if (c == 'H') header = 1;
 		else if (c == 'v') bwa_verbose = atoi(optarg);
+		else if (c == 'o') set_opts(opt, optarg);
 	}
 	if (argc - optind < 2) { fprintf(stderr, "usage: ref_driver [-K n] [-t n] [-T] [-H] idx r1.fq [r2.fq]\n"); return 1; }
 	opt->n_threads = n_threads;

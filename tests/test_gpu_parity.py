@@ -337,6 +337,21 @@ def test_odd_reads_vs_compiled_reference(tmp_path):
         assert want.count(b"\n") >= 2 * (4000 + len(odd))
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+@pytest.mark.parametrize("opts", range(6))
+def test_non_default_options_vs_compiled_reference(tmp_path, opts):
+    """the option sets of tests/test_host_pipeline.py::OPTION_SETS through the real kernels (stand-alone driver, blocking and
+    chunk jobs), indel-heavy reads, device chaining cross-checked against the host chaining"""
+    from test_host_pipeline import OPTION_SETS, synthetic_case
+    prefix, f1, f2 = synthetic_case(tmp_path, 12000, seed=13)
+    args = ["-K", "1500000", "-o", OPTION_SETS[opts], prefix, f1, f2]
+    want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16"] + args, capture_output=True, check=True).stdout
+    drv = os.path.join(ROOT, "tools", "b200_driver")
+    got = subprocess.run([drv, "-t", "16"] + args, capture_output=True, check=True, env=dict(os.environ, B200_CHAIN="check")).stdout
+    assert got == want and want.count(b"\n") >= 24000
+    assert subprocess.run([drv, "-P", "-t", "16"] + args, capture_output=True, check=True).stdout == want
+
+
 def test_properties_at_scale(tmp_path):
     """size-independent properties on a larger run: thread-count invariance, idempotence, record accounting"""
     from mpibwa_b200 import simulate, index_build

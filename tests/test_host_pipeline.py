@@ -93,3 +93,39 @@ def test_occ_sectors_beyond_32_bits(hostemu_built):
     for k0 in (0, 128, 1 << 31, (1 << 32) - 128, 1 << 32, 6_200_000_000, (1 << 33) - 1024):
         for seed in (1, 2, 3):
             assert lib.b200_emu_occ_selftest(k0, seed) == 0, (k0, seed)
+
+
+OPTION_SETS = ["w=200,zdrop=200",
+               "a=2,b=5,o_del=7,e_del=2,o_ins=8,e_ins=1,pen_clip5=3,pen_clip3=7,pen_unpaired=10,T=40",
+               "min_seed_len=15,min_chain_weight=10,max_occ=50,max_chain_extend=2,split_factor=1.2,split_width=5",
+               "mask_level=0.3,drop_ratio=0.7,XA_drop_ratio=0.6,max_XA_hits=2,max_matesw=3,w=30,zdrop=50",
+               "flag=32", "flag=128,max_chain_gap=100"]
+
+
+def synthetic_case(tmp_path, n_pairs, seed=3):
+    """small synthetic reference + indel-heavy pairs (band, z-drop and rescue paths fire); returns (prefix, r1 path, r2 path)"""
+    import sys
+    sys.path.insert(0, ROOT)
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(1_200_000, 3, seed=seed)
+    prefix = str(tmp_path / "ref.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+    r1, r2 = simulate.simulate_pairs(codes, lengths, n_pairs, sub=0.02, indel=0.006, max_indel=12, unmappable_frac=0.1, seed=seed + 1)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1); open(f2, "wb").write(r2)
+    return prefix, f1, f2
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("opts", OPTION_SETS[:4])
+def test_non_default_options_match_reference(hostemu_built, tmp_path, opts):
+    """alignment options away from their defaults (wide band / z-drop as in BASELINE configs[3], another scoring scheme with
+    unequal gap costs, seeding and chaining thresholds, filter ratios): SAM == the compiled reference's with the same options;
+    B200_CHAIN=check also compares the device chaining tables with the host chaining on the way"""
+    prefix, f1, f2 = synthetic_case(tmp_path, 1200)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-K", "200000", "-o", opts, prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    got = subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True, env=dict(os.environ, B200_CHAIN="check")).stdout
+    assert got == want and want.count(b"\n") >= 2400

@@ -352,6 +352,36 @@ def test_non_default_options_vs_compiled_reference(tmp_path, opts):
     assert subprocess.run([drv, "-P", "-t", "16"] + args, capture_output=True, check=True).stdout == want
 
 
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+def test_alt_contigs_vs_compiled_reference(tmp_path):
+    """ALT-aware mapping (reference with a contig listed in <prefix>.alt) through the real kernels, blocking and chunk jobs"""
+    from test_host_pipeline import alt_case
+    prefix, f1, f2 = alt_case(tmp_path, 8000)
+    args = ["-K", "1500000", prefix, f1, f2]
+    want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16"] + args, capture_output=True, check=True).stdout
+    drv = os.path.join(ROOT, "tools", "b200_driver")
+    got = subprocess.run([drv, "-t", "16"] + args, capture_output=True, check=True, env=dict(os.environ, B200_CHAIN="check")).stdout
+    assert got == want and want.count(b"pa:f:") > 2000
+    assert subprocess.run([drv, "-P", "-t", "16"] + args, capture_output=True, check=True).stdout == want
+    a = M.Aligner(prefix, device=0, n_threads=16, verbose=1)
+    assert a.align(open(f1, "rb").read(), open(f2, "rb").read(), K=1500000) == want
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
+def test_split_alignments_and_flags_vs_compiled_reference(tmp_path):
+    """reads glued from two loci under every output flag (supplementary records, SA tags, NO_MULTI, PRIMARY5, KEEP_SUPP_MAPQ, ALL,
+    SOFTCLIP, NOPAIRING) through the real kernels"""
+    from test_host_pipeline import chimeric_case, FLAG_SETS
+    prefix, f1, f2 = chimeric_case(tmp_path, 4000)
+    drv = os.path.join(ROOT, "tools", "b200_driver")
+    for flag in [0] + FLAG_SETS:
+        args = ["-K", "900000", "-o", "flag=%d" % flag, prefix, f1, f2]
+        want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16"] + args, capture_output=True, check=True).stdout
+        got = subprocess.run([drv, "-P", "-t", "16"] + args, capture_output=True, check=True).stdout
+        assert got == want, flag
+        assert want.count(b"SA:Z:") > 5000 or flag == 0x4
+
+
 def test_properties_at_scale(tmp_path):
     """size-independent properties on a larger run: thread-count invariance, idempotence, record accounting"""
     from mpibwa_b200 import simulate, index_build

@@ -129,3 +129,83 @@ def test_non_default_options_match_reference(hostemu_built, tmp_path, opts):
     want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
     got = subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True, env=dict(os.environ, B200_CHAIN="check")).stdout
     assert got == want and want.count(b"\n") >= 2400
+
+
+def alt_case(tmp_path, n_pairs):
+    """reference with an ALT contig (a 2 % diverged copy of 60 kb of chr1, listed in <prefix>.alt) and reads drawn from both:
+    ALT-aware chain filtering, primary marking, pa:f / XA / supplementary (SA) records"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(1_000_000, 3, seed=31)
+    rng = np.random.default_rng(7)
+    seg = codes[100000:160000].copy()
+    mut = rng.random(len(seg)) < 0.02
+    seg[mut] = (seg[mut] + rng.integers(1, 4, size=int(mut.sum()), dtype=np.uint8)) & 3
+    codes2 = np.concatenate([codes, seg])
+    lengths2 = np.concatenate([lengths, [len(seg)]])
+    prefix = str(tmp_path / "ref.fa")
+    index_build.build_index_from_codes(prefix, names + ["chr1_alt1"], lengths2, codes2)
+    open(prefix + ".alt", "w").write("@HD\tVN:1.0\nchr1_alt1\t0\tchr1\t100001\t60\t60000M\t*\t0\t0\t*\t*\n")
+    r1, r2 = simulate.simulate_pairs(codes2, lengths2, n_pairs, seed=33)
+    a1, a2 = simulate.simulate_pairs(np.concatenate([codes[90000:170000], seg]), np.array([80000, 60000]), n_pairs, seed=35, prefix="alt")
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1 + a1); open(f2, "wb").write(r2 + a2)
+    return prefix, f1, f2
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+def test_alt_contigs_match_reference(hostemu_built, tmp_path):
+    prefix, f1, f2 = alt_case(tmp_path, 1000)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-K", "400000", prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    got = subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True, env=dict(os.environ, B200_CHAIN="check")).stdout
+    assert got == want and want.count(b"pa:f:") > 300 and want.count(b"SA:Z:") > 300
+
+
+def chimeric_case(tmp_path, n):
+    """ordinary pairs + reads glued from two loci (split alignments: supplementary records, SA tags, the flags that govern them)"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(800_000, 3, seed=41)
+    prefix = str(tmp_path / "ref.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+    rng = np.random.default_rng(3)
+    B = np.frombuffer(b"ACGTN", np.uint8)
+
+    def piece(L, rc=False):
+        s0 = int(rng.integers(1000, len(codes) - L - 1000))
+        c = codes[s0:s0 + L]
+        return B[(3 - c[::-1]) if rc else c].tobytes()
+
+    a, b = [], []
+    for k in range(n):
+        l1 = int(rng.integers(40, 110))
+        x = piece(l1, rng.random() < 0.5) + piece(150 - l1, rng.random() < 0.5)
+        y = piece(150, rng.random() < 0.5) if rng.random() < 0.5 else piece(70) + piece(80, True)
+        a.append(b"@chim%05d/1\n%s\n+\n%s\n" % (k, x, b"F" * 150))
+        b.append(b"@chim%05d/2\n%s\n+\n%s\n" % (k, y, b"F" * 150))
+    r1, r2 = simulate.simulate_pairs(codes, lengths, n, seed=43)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1 + b"".join(a)); open(f2, "wb").write(r2 + b"".join(b))
+    return prefix, f1, f2
+
+
+FLAG_SETS = [0x10, 0x800, 0x1000, 0x810, 0x8, 0xA00, 0x4]   # NO_MULTI, PRIMARY5, KEEP_SUPP_MAPQ, both, ALL, SOFTCLIP|PRIMARY5, NOPAIRING
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("flag", FLAG_SETS[:4])
+def test_split_alignments_and_flags_match_reference(hostemu_built, tmp_path, flag):
+    prefix, f1, f2 = chimeric_case(tmp_path, 600)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-K", "300000", "-o", "flag=%d" % flag, prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    got = subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True).stdout
+    assert got == want and want.count(b"SA:Z:") > 1000

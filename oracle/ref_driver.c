@@ -92,20 +92,33 @@ static void set_opts(mem_opt_t *opt, const char *spec)
 	bwa_fill_scmat(opt->a, opt->b, opt->mat);
 }
 
+/* -I avg,std,high,low: fixed insert-size distribution for the FR orientation, the others marked failed (bwa mem -I) */
+static mem_pestat_t *parse_pes(const char *spec, mem_pestat_t pes[4])
+{
+	double avg, std; int high, low;
+	if (sscanf(spec, "%lf,%lf,%d,%d", &avg, &std, &high, &low) != 4) { fprintf(stderr, "bad -I %s\n", spec); exit(1); }
+	memset(pes, 0, 4 * sizeof(mem_pestat_t));
+	pes[0].failed = pes[2].failed = pes[3].failed = 1;
+	pes[1].avg = avg; pes[1].std = std; pes[1].high = high; pes[1].low = low;
+	return pes;
+}
+
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 int main(int argc, char **argv)
 {
 	int c, trimmed = 0, header = 0, n_threads = 1;
+	mem_pestat_t pes_fixed[4], *pes0 = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THv:o:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THv:o:I:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
 		else if (c == 'H') header = 1;
 		else if (c == 'v') bwa_verbose = atoi(optarg);
 		else if (c == 'o') set_opts(opt, optarg);
+		else if (c == 'I') pes0 = parse_pes(optarg, pes_fixed);
 	}
 	if (argc - optind < 2) { fprintf(stderr, "usage: ref_driver [-K n] [-t n] [-T] [-H] idx r1.fq [r2.fq]\n"); return 1; }
 	opt->n_threads = n_threads;
@@ -138,7 +151,7 @@ int main(int argc, char **argv)
 				if (paired) seqs[n++] = s2[k];
 			}
 			double t0 = now();
-			mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, 0);
+			mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, pes0);
 			t_mem += now() - t0;
 			n_processed += n;
 			for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }

@@ -380,6 +380,10 @@ def test_split_alignments_and_flags_vs_compiled_reference(tmp_path):
         got = subprocess.run([drv, "-P", "-t", "16"] + args, capture_output=True, check=True).stdout
         assert got == want, flag
         assert want.count(b"SA:Z:") > 5000 or flag == 0x4
+    for pes in ("300,10,330,270", "450,30,520,380"):          # caller-given insert-size distribution (pes0 != NULL)
+        args = ["-K", "900000", "-I", pes, prefix, f1, f2]
+        want = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16"] + args, capture_output=True, check=True).stdout
+        assert subprocess.run([drv, "-t", "16"] + args, capture_output=True, check=True).stdout == want, pes
 
 
 def test_properties_at_scale(tmp_path):

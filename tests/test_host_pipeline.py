@@ -209,3 +209,17 @@ def test_split_alignments_and_flags_match_reference(hostemu_built, tmp_path, fla
     want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
     got = subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True).stdout
     assert got == want and want.count(b"SA:Z:") > 1000
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("pes", ["300,10,330,270", "450,30,520,380"])
+def test_given_insert_size_distribution(hostemu_built, tmp_path, pes):
+    """mem_process_seqs with pes0 != NULL (bwa mem -I): the chunk-global statistics are taken from the caller, rescue windows
+    and pairing follow them"""
+    prefix, f1, f2 = chimeric_case(tmp_path, 500)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-K", "300000", "-I", pes, prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    assert subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True).stdout == want
+    assert subprocess.run([drv, "-P", "-t", "4"] + args, capture_output=True, check=True).stdout == want

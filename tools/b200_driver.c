@@ -85,14 +85,26 @@ static void set_opts(mem_opt_t *opt, const char *spec)
 	bwa_fill_scmat(opt->a, opt->b, opt->mat);
 }
 
+/* -I avg,std,high,low: fixed insert-size distribution for the FR orientation, the others marked failed (bwa mem -I) */
+static mem_pestat_t *parse_pes(const char *spec, mem_pestat_t pes[4])
+{
+	double avg, std; int high, low;
+	if (sscanf(spec, "%lf,%lf,%d,%d", &avg, &std, &high, &low) != 4) { fprintf(stderr, "bad -I %s\n", spec); exit(1); }
+	memset(pes, 0, 4 * sizeof(mem_pestat_t));
+	pes[0].failed = pes[2].failed = pes[3].failed = 1;
+	pes[1].avg = avg; pes[1].std = std; pes[1].high = high; pes[1].low = low;
+	return pes;
+}
+
 static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 int main(int argc, char **argv)
 {
 	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0, pipelined = 0;
+	mem_pestat_t pes_fixed[4], *pes0 = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THPv:r:n:d:o:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THPv:r:n:d:o:I:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
@@ -103,6 +115,7 @@ int main(int argc, char **argv)
 		else if (c == 'n') nranks = atoi(optarg);
 		else if (c == 'd') device = atoi(optarg);
 		else if (c == 'o') set_opts(opt, optarg);
+		else if (c == 'I') pes0 = parse_pes(optarg, pes_fixed);
 	}
 	if (argc - optind < 2) { fprintf(stderr, "usage: b200_driver [-K n] [-t n] [-T] [-H] [-r rank -n nranks] [-d dev] idx r1.fq [r2.fq]\n"); return 1; }
 	opt->n_threads = n_threads;
@@ -150,7 +163,7 @@ int main(int argc, char **argv)
 				if (pipelined) {
 					bseq1_t *cs = malloc(n * sizeof(bseq1_t));
 					memcpy(cs, seqs, n * sizeof(bseq1_t));
-					b200_job_t *job = b200_process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, cs, 0);
+					b200_job_t *job = b200_process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, cs, pes0);
 					if (prev_job) {
 						b200_process_seqs_end(prev_job, 0);
 						for (k = 0; k < prev_n; ++k) { fputs(prev_seqs[k].sam, stdout); free(prev_seqs[k].sam); }
@@ -158,7 +171,7 @@ int main(int argc, char **argv)
 					}
 					prev_job = job; prev_seqs = cs; prev_n = n;
 				} else {
-					mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, 0);
+					mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, pes0);
 					for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }
 				}
 				t_mem += now() - t0;

@@ -57,7 +57,6 @@ void host_prof_report(const char *what)
 char *dup_cstr(const std::string &s)
 {
 	ProfScope ps(HP_DUP);
-	if (std::string *sink = align_ctx().sink) { sink->append(s); return nullptr; }
 	char *p = (char *)malloc(s.size() + 1);
 	memcpy(p, s.data(), s.size());
 	p[s.size()] = 0;
@@ -1171,7 +1170,8 @@ void reg2sam(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq
              const Aln *m)
 {
 	ProfScope ps(HP_REG2SAM);
-	std::string str;
+	std::string local, *sink = align_ctx().sink;
+	std::string &str = sink ? *sink : local;
 	std::vector<Aln> aa;
 	std::vector<std::string> XA;
 	bool has_xa = false;
@@ -1205,7 +1205,7 @@ void reg2sam(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac, bseq
 		for (size_t k = 0; k < aa.size(); ++k)
 			aln2sam(opt, bns, str, s, (int)aa.size(), aa.data(), (int)k, m);
 	}
-	s->sam = dup_cstr(str);
+	s->sam = sink ? nullptr : dup_cstr(str);
 }
 
 #define RAW_MAPQ(diff, a) ((int)(6.02 * (diff) / (a) + .499))
@@ -1281,24 +1281,25 @@ void sam_pe_finish(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 				h[i].mapq = (uint32_t)q_se[i] & 0xff;
 				h[i].flag |= 0x40 << i | extra_flag;
 				h[i].XA = has_xa[i] ? &XA[i][z[i]] : nullptr;
-				aa[i].push_back(h[i]);
 				if (n_pri[i] < (int)a[i].size()) {
 					mem_alnreg_t *p = &a[i][n_pri[i]];
 					if (p->score < opt->T || p->secondary >= 0 || !p->is_alt) continue;
 					reg2aln(opt, bns, pac, s[i].l_seq, s[i].seq, p, &g[i]);
 					g[i].flag |= 0x800 | 0x40 << i | extra_flag;
 					g[i].XA = has_xa[i] ? &XA[i][n_pri[i]] : nullptr;
-					aa[i].push_back(g[i]);
+					aa[i].push_back(h[i]);                  // (only an ALT supplementary record needs the two-entry list)
+					aa[i].push_back(std::move(g[i]));
 				}
 			}
-			std::string str;
-			str.reserve(640);
-			for (i = 0; i < (int)aa[0].size(); ++i)
-				aln2sam(opt, bns, str, &s[0], (int)aa[0].size(), aa[0].data(), i, &h[1]);
-			s[0].sam = dup_cstr(str); str.clear();
-			for (i = 0; i < (int)aa[1].size(); ++i)
-				aln2sam(opt, bns, str, &s[1], (int)aa[1].size(), aa[1].data(), i, &h[0]);
-			s[1].sam = dup_cstr(str);
+			// records go straight into the block buffer of the sweep when there is one, else into seqs[i].sam
+			std::string local, *sink = align_ctx().sink;
+			std::string &str = sink ? *sink : local;
+			if (!sink) str.reserve(640);
+			for (i = 0; i < 2; ++i) {
+				if (aa[i].empty()) aln2sam(opt, bns, str, &s[i], 1, &h[i], 0, &h[!i]);
+				else for (j = 0; j < (int)aa[i].size(); ++j) aln2sam(opt, bns, str, &s[i], (int)aa[i].size(), aa[i].data(), j, &h[!i]);
+				if (!sink) { s[i].sam = dup_cstr(str); str.clear(); } else s[i].sam = nullptr;
+			}
 			if (strcmp(s[0].name, s[1].name) != 0) {
 				fprintf(stderr, "[mem_sam_pe] paired reads have different names: \"%s\", \"%s\"\n", s[0].name, s[1].name);
 				abort();

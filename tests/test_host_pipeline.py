@@ -81,6 +81,8 @@ def test_chunk_jobs_give_the_same_sam(hostemu_built, examples, tmp_path, shape):
     env = dict(os.environ, B200_LANE_MIN="100", B200_LANES="2")
     r = subprocess.run([drv, "-P", "-t", "4"] + args, capture_output=True, check=True, env=env)
     assert r.stdout == want and want.count(b"\n") > 2000
+    # -C: b200_align_chunk (the SAM sweep writes block buffers instead of seqs[i].sam)
+    assert subprocess.run([drv, "-C", "-t", "4"] + args, capture_output=True, check=True, env=env).stdout == want
 
 
 def test_occ_sectors_beyond_32_bits(hostemu_built):

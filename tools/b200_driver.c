@@ -9,7 +9,9 @@
  * With -P the loop keeps two chunks in flight through the chunk-job form of the call (b200_process_seqs_begin / _end):
  * "read chunk i+1; begin(i+1); end(i); write chunk i" - the patched host loop of INTEGRATION.md.
  *
- * usage: b200_driver [-K bases] [-t threads] [-T] [-H] [-P] [-r rank -n nranks] [-d device] <idxprefix|.map> <r1.fq> [r2.fq]
+ * With -C each chunk goes through b200_align_chunk (mates interleaved by the library, SAM returned as one buffer).
+ *
+ * usage: b200_driver [-K bases] [-t threads] [-T] [-H] [-P|-C] [-r rank -n nranks] [-d device] <idxprefix|.map> <r1.fq> [r2.fq]
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -104,12 +106,13 @@ int main(int argc, char **argv)
 	mem_pestat_t pes_fixed[4], *pes0 = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THPv:r:n:d:o:I:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THPCv:r:n:d:o:I:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
 		else if (c == 'H') header = 1;
 		else if (c == 'P') pipelined = 1;
+		else if (c == 'C') pipelined = 2;     /* b200_align_chunk: the library interleaves the mates and returns one SAM buffer */
 		else if (c == 'v') bwa_verbose = atoi(optarg);
 		else if (c == 'r') rank = atoi(optarg);
 		else if (c == 'n') nranks = atoi(optarg);
@@ -160,7 +163,12 @@ int main(int argc, char **argv)
 					if (paired) seqs[n++] = s2[k];
 				}
 				double t0 = now();
-				if (pipelined) {
+				if (pipelined == 2) {
+					char *sam = 0; int64_t sam_len = 0;
+					n = (size_t)b200_align_chunk(opt, idx, trimmed ? n_processed : 0, (int64_t)(i - beg + 1), s1 + beg, paired ? s2 + beg : 0, &sam, &sam_len);
+					fwrite(sam, 1, (size_t)sam_len, stdout);
+					b200_free(sam);
+				} else if (pipelined) {
 					bseq1_t *cs = malloc(n * sizeof(bseq1_t));
 					memcpy(cs, seqs, n * sizeof(bseq1_t));
 					b200_job_t *job = b200_process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, cs, pes0);

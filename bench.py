@@ -355,12 +355,21 @@ def main():
             if on_stats:
                 on_stats(st.as_dict())
 
+        tb = te = 0.0
         for s in range(count):
+            t_ = time.time()
             pending.append(e2e_begin(first + s, raw[s] if raw else None))
+            tb += time.time() - t_
             if len(pending) >= DEPTH:
+                t_ = time.time()
                 finish()
+                te += time.time() - t_
         while pending:
+            t_ = time.time()
             finish()
+            te += time.time() - t_
+        if os.environ.get("B200_BENCH_DEBUG"):
+            log("[bench] e2e_run: %d chunks, parse+begin %.1f ms, end (wait + free) %.1f ms" % (count, 1e3 * tb, 1e3 * te))
         return pairs, out_bytes
 
     def resident_group(first, count, ev0, ev1, on_stats=None):
@@ -423,6 +432,8 @@ def main():
     def add_io(st):
         io["h2d"] += st["h2d_bytes"]
         io["d2h"] += st["d2h_bytes"]
+        if os.environ.get("B200_BENCH_DEBUG"):
+            log("[bench] e2e job: " + " ".join("%s %.1f" % (k[3:], st[k]) for k in ("ms_total", "ms_seed", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global")))
 
     # the K chunks' fastq bytes sit in private host buffers (what the host's file read leaves) when the timed region starts
     raw = None

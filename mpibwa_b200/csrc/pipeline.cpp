@@ -24,6 +24,8 @@
 #include <atomic>
 #include <thread>
 #include <condition_variable>
+#include <set>
+#include <sys/mman.h>
 
 namespace b200 {
 
@@ -39,7 +41,32 @@ static std::mutex g_mu;
 static std::vector<Engine *> g_engines;     // [0] owns the index in HBM; the others are clones that share it (one per sub-batch lane)
 static const void *g_engine_key = nullptr;
 static int g_device = -1;
-static std::mutex g_gpu_mu;                  // one lane at a time drives the GPU; the other lane's host stage overlaps it
+// One lane at a time drives the GPU (the host stages of the other lanes and jobs overlap it).  The lock is handed to the waiter
+// of the OLDEST chunk job: a chunk that has reached its last device stage does not queue behind the seeding of three
+// younger chunks, which keeps the latency of a job - and the ramp of a short run - down.
+class DeviceTurn {
+public:
+	void lock(uint64_t ticket)
+	{
+		std::unique_lock<std::mutex> lk(mu_);
+		auto it = waiting_.insert(ticket);
+		cv_.wait(lk, [&] { return !held_ && *waiting_.begin() == ticket; });
+		waiting_.erase(it);
+		held_ = true;
+	}
+	void unlock()
+	{
+		{ std::lock_guard<std::mutex> lk(mu_); held_ = false; }
+		cv_.notify_all();
+	}
+private:
+	std::mutex mu_;
+	std::condition_variable cv_;
+	std::multiset<uint64_t> waiting_;
+	bool held_ = false;
+};
+static DeviceTurn g_gpu_turn;
+struct DeviceTurnGuard { uint64_t t; explicit DeviceTurnGuard(uint64_t t_) : t(t_) { g_gpu_turn.lock(t); } ~DeviceTurnGuard() { g_gpu_turn.unlock(); } };
 
 Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 {
@@ -310,15 +337,16 @@ static void drive_lanes(std::vector<Lane> &lanes, F body)
 	else run();
 }
 
-#define GPU_STAGE(call) do { std::lock_guard<std::mutex> gpu_lk(g_gpu_mu); call; } while (0)
+#define GPU_STAGE(call) do { DeviceTurnGuard gpu_lk(ticket); call; } while (0)
 
 static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                               int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0,
-                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamBlocks *sam_blocks)
+                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamBlocks *sam_blocks,
+                              uint64_t ticket)
 {
 	engine_for(bwt, bns, pac);
 	std::vector<Lane> lanes = make_lanes(n_all, slot, want_lanes);
-	if (sam_blocks) sam_blocks->lane.assign(lanes.size(), std::vector<std::string>());
+	if (sam_blocks) sam_blocks->lane.resize(lanes.size());
 	if (staged && (int)lanes.size() != want_lanes) { fprintf(stderr, "[mpibwa_b200] staged reads do not match the lane split of the call\n"); abort(); }
 	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
@@ -715,7 +743,8 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		std::vector<std::string> *blocks = nullptr;
 		if (sam_blocks) {
 			blocks = &sam_blocks->lane[&L - lanes.data()];
-			blocks->assign((size_t)((n_units + sweep_grain - 1) / sweep_grain), std::string());
+			blocks->resize((size_t)((n_units + sweep_grain - 1) / sweep_grain));
+			for (std::string &b : *blocks) b.clear();                          // (keeps the capacity)
 		}
 		parallel_for(nt, n_units, sweep_grain, [&](int, int64_t b, int64_t e) {
 			AlignCtx &cx = align_ctx();
@@ -782,25 +811,32 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 struct SeqJob {
 	std::thread th;
 	b200_stats_t stats;
-	SamBlocks sam;
+	SamBlocks *sam = nullptr;        // the slot's block buffers while the job holds the slot
 };
+
+// block buffers live with the slot and keep their capacity from chunk to chunk (no 200 KB allocations per block per chunk)
+static SamBlocks g_slot_sam[N_SLOTS];
 
 // concatenates the SAM blocks of a finished job into one malloc()ed, NUL-terminated buffer (parallel copy); returns its length
 int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
 {
 	std::vector<const std::string *> parts;
-	for (auto &ln : j->sam.lane) for (auto &b : ln) parts.push_back(&b);
+	for (auto &ln : j->sam->lane) for (auto &b : ln) parts.push_back(&b);
 	std::vector<size_t> at(parts.size() + 1, 0);
 	for (size_t k = 0; k < parts.size(); ++k) at[k + 1] = at[k] + parts[k]->size();
 	char *buf = (char *)malloc(at.back() + 1);
+#if defined(MADV_HUGEPAGE)
+	if (at.back() >= ((size_t)8 << 20)) {       // hundreds of MB touched once: ask for huge pages instead of 65 k page faults
+		const uintptr_t lo = ((uintptr_t)buf + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)buf + at.back()) & ~(((uintptr_t)2 << 20) - 1);
+		if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+	}
+#endif
 	parallel_for(n_threads, (int64_t)parts.size(), 16, [&](int, int64_t b, int64_t e) {
 		for (int64_t k = b; k < e; ++k) memcpy(buf + at[k], parts[k]->data(), parts[k]->size());
 	});
 	buf[at.back()] = 0;
 	*out = buf;
-	const int64_t len = (int64_t)at.back();
-	j->sam.lane.clear();
-	return len;
+	return (int64_t)at.back();
 }
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
@@ -832,13 +868,14 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 			++g_running; ++g_ticket_serving;
 			g_slot_cv.notify_all();
 		}
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats, sam_as_blocks ? &j->sam : nullptr);
+		j->sam = sam_as_blocks ? &g_slot_sam[slot] : nullptr;
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats, j->sam, ticket);
+		if (after) after(arg, j);                // (SAM concatenation out of the slot's block buffers: host work that overlaps the next chunk)
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
 			--g_running; g_slots[slot].busy = false;
 			g_slot_cv.notify_all();
 		}
-		if (after) after(arg, j);                // (SAM concatenation: host work that overlaps the next chunk)
 	});
 	return j;
 }

@@ -13,7 +13,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libmpibwa_b200.so")
+LIB_PATH = os.environ.get("B200_LIB") or os.path.join(_HERE, "libmpibwa_b200.so")     # (B200_LIB: A/B runs of two builds in one process environment)
 
 
 class bwt_t(C.Structure):                     # reference src/bwt.h:46-58

@@ -768,7 +768,15 @@ void pestat(const mem_opt_t *opt, int64_t l_pac, int n, const RegVec *regs, mem_
 			r->failed = 1;
 			continue;
 		} else fprintf(stderr, "[M::%s] analyzing insert size distribution for orientation %c%c...\n", "mem_pestat", "FR"[d >> 1 & 1], "FR"[d & 1]);
-		std::sort(q.begin(), q.end());
+		// ascending order (the sums below are taken in it).  Every value is in [1, max_ins]: a counting sort does in a
+		// millisecond what a comparison sort of a third of a million values does in twenty, on the critical path of the call
+		if (opt->max_ins > 0 && opt->max_ins <= 1 << 22) {
+			std::vector<uint32_t> cnt((size_t)opt->max_ins + 2, 0);
+			for (uint64_t v : q) ++cnt[v];
+			size_t at = 0;
+			for (size_t v = 0; v < cnt.size(); ++v)
+				for (uint32_t c = cnt[v]; c > 0; --c) q[at++] = v;
+		} else std::sort(q.begin(), q.end());
 		p25 = (int)q[(int)(.25 * q.size() + .499)];
 		p50 = (int)q[(int)(.50 * q.size() + .499)];
 		p75 = (int)q[(int)(.75 * q.size() + .499)];

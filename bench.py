@@ -324,26 +324,24 @@ def main():
                  "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells", "n_global_host")
 
     def e2e_begin(c, raw=None):
-        """raw fastq bytes -> chunk job (parse in place on this thread, everything else on the library's job thread)"""
+        """raw fastq bytes -> chunk job (b200_align_fastq_begin: parse in place, interleave, align, concatenate - all on the library's job thread)"""
         a1, a2, n = raw if raw is not None else chunk_bytes(c)
-        k1, p1, m1 = al.parse_array(*a1)
-        k2, p2, m2 = al.parse_array(*a2)
-        return (lib.b200_align_chunk_begin(al.opt, al.idx, 0, m1, p1, p2), p1, p2, n)
+        job = lib.b200_align_fastq_begin(al.opt, al.idx, 0, C.c_void_p(a1[0].ctypes.data), a1[1], C.c_void_p(a2[0].ctypes.data), a2[1])
+        return (job, a1, a2, n)
 
     def e2e_end(h, st):
-        job, p1, p2, n = h
+        job, a1, a2, n = h
         sam = C.c_void_p()
         sam_len = C.c_int64()
         lib.b200_align_chunk_end(job, C.byref(sam), C.byref(sam_len), C.byref(st))
         out_len = sam_len.value
-        lib.b200_free(sam); lib.b200_free(p1); lib.b200_free(p2)
+        lib.b200_free(sam)
         return n, out_len
 
     DEPTH = 4        # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
 
     def e2e_run(first, count, on_stats=None, raw=None):
-        """`count` chunks from fastq bytes in host memory to SAM bytes in host memory as chunk jobs: parse(i), begin(i),
-        ... end(i - DEPTH + 1).  raw: the chunks' private fastq buffers when they were filled before the timed region."""
+        """`count` chunks from fastq bytes in host memory to SAM bytes in host memory as chunk jobs: begin(i), ... end(i - DEPTH + 1).  raw: the chunks' private fastq buffers when they were filled before the timed region."""
         pairs = out_bytes = 0
         pending = []
         st = M.b200_stats_t()

@@ -139,6 +139,7 @@ _PROTOTYPES = {
     "b200_process_seqs_end": (None, [C.c_void_p, C.POINTER(b200_stats_t)]),
     "b200_align_chunk_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int64, C.POINTER(bseq1_t),
                                             C.POINTER(bseq1_t)]),
+    "b200_align_fastq_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "b200_align_chunk_end": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(b200_stats_t)]),
     "b200_free": (None, [C.c_void_p]),
     "b200_get_stats": (None, [C.POINTER(b200_stats_t)]),
@@ -276,6 +277,18 @@ class Aligner:
         if s2:
             self.lib.b200_free(s2)
         return b"".join(out)
+
+    def align_fastq(self, fq1, fq2=None):
+        """the whole input as ONE chunk from its raw fastq bytes (b200_align_fastq_begin: parsed by the job thread)"""
+        b1 = C.create_string_buffer(fq1, len(fq1) + 1)
+        b2 = C.create_string_buffer(fq2, len(fq2) + 1) if fq2 is not None else None
+        job = self.lib.b200_align_fastq_begin(self.opt, self.idx, 0, C.cast(b1, C.c_void_p), len(fq1),
+                                              C.cast(b2, C.c_void_p) if b2 is not None else None, len(fq2) if fq2 is not None else 0)
+        sam, sam_len = C.c_void_p(), C.c_int64()
+        self.lib.b200_align_chunk_end(job, C.byref(sam), C.byref(sam_len), None)
+        out = C.string_at(sam, sam_len.value)
+        self.lib.b200_free(sam)
+        return out
 
     def stats(self):
         st = b200_stats_t()

@@ -24,6 +24,9 @@
 #include <atomic>
 #include <thread>
 #include <condition_variable>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <set>
 #include <sys/mman.h>
 
@@ -298,7 +301,23 @@ static int64_t stage_lane_reads(const mem_opt_t *opt, const Lane &L, bseq1_t *se
 		for (int64_t i = b; i < e; ++i) {
 			char *s = seqs[i].seq;
 			uint8_t *d = &codes[off[i]];
-			for (int j = 0; j < seqs[i].l_seq; ++j) {
+			const int l = seqs[i].l_seq;
+			int j = 0;
+#if defined(__SSE2__) && !defined(B200_NO_SSE_ENCODE)
+			// sixteen bases at a time while they are all A/C/G/T in either case: code = ((c >> 1) ^ (c >> 2)) & 3;
+			// anything else (N, IUPAC codes, bytes that are already codes) goes through the table below
+			const __m128i lower = _mm_set1_epi8(0x20), three = _mm_set1_epi8(3);
+			for (; j + 16 <= l; j += 16) {
+				const __m128i c = _mm_loadu_si128((const __m128i *)(s + j)), u = _mm_or_si128(c, lower);
+				const __m128i ok = _mm_or_si128(_mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('a')), _mm_cmpeq_epi8(u, _mm_set1_epi8('c'))),
+				                                _mm_or_si128(_mm_cmpeq_epi8(u, _mm_set1_epi8('g')), _mm_cmpeq_epi8(u, _mm_set1_epi8('t'))));
+				if (_mm_movemask_epi8(ok) != 0xffff) break;
+				const __m128i code = _mm_and_si128(_mm_xor_si128(_mm_srli_epi16(c, 1), _mm_srli_epi16(c, 2)), three);
+				_mm_storeu_si128((__m128i *)(s + j), code);
+				_mm_storeu_si128((__m128i *)(d + j), code);
+			}
+#endif
+			for (; j < l; ++j) {
 				s[j] = s[j] < 4 ? s[j] : (char)kNt4[(uint8_t)s[j]];
 				d[j] = (uint8_t)s[j];
 			}
@@ -841,7 +860,8 @@ int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
-                           void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks)
+                           void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks,
+                           void (*before)(void *, bseq1_t **, int *))
 {
 	engine_for(bwt, bns, pac);
 	SeqJob *j = new SeqJob();
@@ -852,7 +872,7 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	uint64_t ticket;
 	{
 		std::unique_lock<std::mutex> lk(g_slot_mu);
-		for (int k = 0; k < N_SLOTS; ++k)
+		for (int k = 0; k < N_SLOTS && seqs; ++k)
 			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; want_lanes = g_slots[k].staged_lanes; }
 		if (slot < 0)
 			g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
@@ -862,6 +882,9 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	const mem_pestat_t *pes = pes0;
 	j->th = std::thread([=]() {
 		static const int limit = getenv("B200_INFLIGHT") ? std::max(1, atoi(getenv("B200_INFLIGHT"))) : 4;
+		bseq1_t *seqs_ = seqs;
+		int n_ = n;
+		if (before) before(arg, &seqs_, &n_);     // (b200_align_fastq_begin: parse + interleave on the job thread, before the job's turn)
 		{
 			std::unique_lock<std::mutex> lk(g_slot_mu);
 			g_slot_cv.wait(lk, [&] { return ticket == g_ticket_serving && g_running < limit; });
@@ -869,7 +892,7 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 			g_slot_cv.notify_all();
 		}
 		j->sam = sam_as_blocks ? &g_slot_sam[slot] : nullptr;
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, want_lanes, staged, staged_bases, &j->stats, j->sam, ticket);
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n_, seqs_, pes, slot, want_lanes, staged, staged_bases, &j->stats, j->sam, ticket);
 		if (after) after(arg, j);                // (SAM concatenation out of the slot's block buffers: host work that overlaps the next chunk)
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
@@ -890,7 +913,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2, false), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2, false, nullptr), nullptr);
 }
 
 } // namespace b200

@@ -286,6 +286,11 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
     assert got_sq == want
     # chunk jobs (b200_align_chunk_begin / _end): several chunks in flight, SAM unchanged and in input order
     assert a.align_pipelined(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args) == want
+    # from the raw fastq bytes, parsed by the job thread (one chunk: compare with a -K that does not split the input)
+    if "-T" not in args:
+        big = 1 << 40
+        want1 = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_driver"), "-t", "16", "-K", str(big), prefix] + fq, capture_output=True, check=True).stdout
+        assert a.align_fastq(r1, None if name == "se100" else r2) == want1
     # through the stand-alone driver binary as well (the C host path), synchronous and with chunk jobs (-P)
     got2 = subprocess.run([os.path.join(ROOT, "tools", "b200_driver"), "-t", "16"] + args + [prefix] + fq, capture_output=True, check=True).stdout
     assert got2 == want

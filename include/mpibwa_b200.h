@@ -283,7 +283,8 @@ bseq1_t *b200_chunk_seqs(int64_t n, const bseq1_t *s1, const bseq1_t *s2);      
 int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam);            /* concatenates and frees seqs[i].sam */
 int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2,
                          char **sam, int64_t *sam_len);
-void b200_free(void *p);
+void b200_free(void *p);            /* releases any buffer the b200_* calls return (large SAM buffers are parked for reuse, the rest is free()d) */
+void *b200_big_alloc(size_t bytes); /* a buffer from the same recycling pool (release with b200_free) */
 
 /* counters filled by the last mem_process_seqs call on this thread's context; used by bench.py */
 typedef struct {

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <mutex>
 #include <thread>
 #include <algorithm>
 
@@ -135,6 +136,31 @@ int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam)
 	return (int64_t)sum;
 }
 
-void b200_free(void *p) { free(p); }
+// Large result buffers (the concatenated SAM of a chunk: hundreds of MB) are recycled instead of returned to the system:
+// an mmap/munmap pair per chunk costs tens of thousands of page faults and a TLB shoot-down on every core of a busy host.
+// b200_big_alloc() hands out a buffer of at least `bytes`; b200_free() recognises such a buffer and parks it for the next call.
+static struct BigPool { std::mutex mu; struct Ent { void *p; size_t cap; bool busy; }; std::vector<Ent> ents; } g_big;
+
+void *b200_big_alloc(size_t bytes)
+{
+	std::lock_guard<std::mutex> lk(g_big.mu);
+	for (auto &e : g_big.ents) if (!e.busy && e.cap >= bytes) { e.busy = true; return e.p; }
+	for (size_t k = 0; k < g_big.ents.size(); ++k)
+		if (!g_big.ents[k].busy && g_big.ents.size() >= 8) { free(g_big.ents[k].p); g_big.ents.erase(g_big.ents.begin() + k); break; }   // too small and the pool is full
+	const size_t cap = bytes + (bytes >> 3) + 4096;
+	void *p = malloc(cap);
+	if (p && g_big.ents.size() < 8) g_big.ents.push_back({ p, cap, true });
+	return p;
+}
+
+void b200_free(void *p)
+{
+	if (!p) return;
+	{
+		std::lock_guard<std::mutex> lk(g_big.mu);
+		for (auto &e : g_big.ents) if (e.p == p) { e.busy = false; return; }
+	}
+	free(p);
+}
 
 } // extern "C"

@@ -836,6 +836,8 @@ struct SeqJob {
 // block buffers live with the slot and keep their capacity from chunk to chunk (no 200 KB allocations per block per chunk)
 static SamBlocks g_slot_sam[N_SLOTS];
 
+extern "C" void *b200_big_alloc(size_t bytes);
+
 // concatenates the SAM blocks of a finished job into one malloc()ed, NUL-terminated buffer (parallel copy); returns its length
 int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
 {
@@ -843,7 +845,7 @@ int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
 	for (auto &ln : j->sam->lane) for (auto &b : ln) parts.push_back(&b);
 	std::vector<size_t> at(parts.size() + 1, 0);
 	for (size_t k = 0; k < parts.size(); ++k) at[k + 1] = at[k] + parts[k]->size();
-	char *buf = (char *)malloc(at.back() + 1);
+	char *buf = (char *)b200_big_alloc(at.back() + 1);      // recycled through b200_free()
 #if defined(MADV_HUGEPAGE)
 	if (at.back() >= ((size_t)8 << 20)) {       // hundreds of MB touched once: ask for huge pages instead of 65 k page faults
 		const uintptr_t lo = ((uintptr_t)buf + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)buf + at.back()) & ~(((uintptr_t)2 << 20) - 1);

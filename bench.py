@@ -462,9 +462,15 @@ def main():
     os.environ["B200_LANES"] = "1"
     resident_group(args.warmup + args.steps, 1, ev0, ev1)          # first one grows the device buffers to whole-chunk size
     iso = []
+    os.environ["B200_EXT_RECORD"] = "1"            # keep this chunk's ksw_extend2 job list for the one-batch replay below
     resident_group(args.warmup + args.steps + 1, 1, ev0, ev1, iso.append)
+    os.environ.pop("B200_EXT_RECORD", None)
     st_iso = iso[0]
     os.environ.pop("B200_LANES", None)
+    # kernel-isolated ksw_extend2 as BASELINE configs[1] words it: the exact job list of the chunk, replayed as one batch
+    rp_cells, rp_jobs = C.c_int64(), C.c_int64()
+    lib.b200_ext_replay(al.opt, C.byref(rp_cells), C.byref(rp_jobs))          # (warm-up)
+    rp_ms = lib.b200_ext_replay(al.opt, C.byref(rp_cells), C.byref(rp_jobs))
 
     # ---- reduce over ranks: MAX of times, SUM of pairs
     t = torch.tensor([res_ms, e2e_ms], dtype=torch.float64, device="cuda")
@@ -506,8 +512,15 @@ def main():
         "kernels_isolated": kernel_table(st_iso, 1, i32_peak, hbm_peak),
         "kernels_note": "roofline/kernels: CUDA-event kernel times inside the timed region (chunk jobs: one whole-chunk batch per kernel, up to four chunks "
                         "in flight, device stages serialised); kernels_isolated: one extra untimed chunk run alone, the kernel-isolated figures of "
-                        "BASELINE configs[1]; ksw_extend2_gcups is the isolated one",
+                        "BASELINE configs[1]; ksw_extend2_gcups is the isolated one (DP kernels of all chain2aln rounds of the chunk), "
+                        "ksw_extend2_gcups_one_batch / ksw_extend2_replay the same job list replayed as one batch",
         "ksw_extend2_gcups": kernel_table(st_iso, 1, i32_peak, hbm_peak).get("ksw_extend2", {}).get("gcups"),
+        "ksw_extend2_gcups_one_batch": (rp_cells.value / rp_ms / 1e6) if rp_ms > 0 else None,
+        "ksw_extend2_replay": {"what": "every ksw_extend2 job of one chunk (recorded from the pipeline) as ONE batch through the DP kernels: no chain2aln rounds "
+                                       "in between, so no launch with too few jobs to fill the chip",
+                               "jobs": rp_jobs.value, "cells": rp_cells.value, "ms": rp_ms,
+                               "gcups": (rp_cells.value / rp_ms / 1e6) if rp_ms > 0 else None,
+                               "frac": (rp_cells.value / rp_ms / 1e6 * 14 / i32_peak) if rp_ms > 0 and i32_peak else None},
         "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global", "ms_total")},
         "host_threads": n_threads,
     }

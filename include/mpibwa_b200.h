@@ -305,6 +305,9 @@ typedef struct {
 	int64_t n_global_host;    /* regions whose CIGAR the SAM sweep computed with the host routine (not queued for the device stage) */
 	double ms_k_chain;        /* CUDA-event time of the chaining kernels (ms_chain_host is the wall of the whole chaining stage, host or device) */
 } b200_stats_t;
+/* kernel-isolated ksw_extend2: with B200_EXT_RECORD set in the environment the extension stage keeps every job of the call; this
+ * replays them as ONE batch through the DP kernels on the primary engine and returns the time in ms (bench.py; run one chunk alone first) */
+double b200_ext_replay(const mem_opt_t *opt, int64_t *cells, int64_t *n_jobs);
 void b200_get_stats(b200_stats_t *out);   /* counters of the call that finished last */
 
 /* Chunk jobs - mem_process_seqs (reference src/bwamem.h:134) split into begin / end so that the host can keep two chunks

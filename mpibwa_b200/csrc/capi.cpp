@@ -459,6 +459,11 @@ int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_pr
 	return b200_align_chunk_end(b200_align_chunk_begin(opt, idx, n_processed, n, s1, s2), sam, sam_len, nullptr);
 }
 
+double b200_ext_replay(const mem_opt_t *opt, int64_t *cells, int64_t *n_jobs)
+{
+	return stage_extend_replay(need_engine(), make_ext_opt(opt), cells, n_jobs);
+}
+
 void b200_get_stats(b200_stats_t *out)
 {
 	if (engine_current()) last_stats(out);

@@ -61,6 +61,9 @@ struct ExtIn { int n_reads; const int32_t *chain_off; const DChain *chains; int6
 struct ExtRegs { const DReg *regs; const int64_t *reg_off; };
 void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out);
 
+// kernel-isolated replay of every ksw_extend2 job the last stage_extend call recorded (B200_EXT_RECORD set): one batch, DP kernels only
+double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t *n_jobs);
+
 // chaining stage (mem_chain + mem_chain_flt + flattening, chain_kernels.h) over the seeds of the last stage_seed(keep_on_device)
 // call; fills `in` for stage_extend.  Valid for reads to which mem_flt_chained_seeds does not apply (see pipeline.cpp).
 // With `download` the four arrays are also copied to the PIN_CHAIN_OFF.. slots and `in` points at them (checking mode).

@@ -86,6 +86,7 @@ public:
 	// scratch
 	DevBuf b_strips, b_nfirst, b_nsweeps;
 	DevBuf b_chscr, b_chnodes, b_chnc, b_chns, b_chcoff, b_chsoff;
+	DevBuf b_xrec; int64_t n_rec = 0;      // B200_EXT_RECORD: every ksw_extend2 job of the last stage_extend call (for the one-batch replay)
 	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
@@ -268,7 +269,7 @@ void engine_destroy(Engine *e)
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
 	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
 	e->b_strips.release(); e->b_nfirst.release(); e->b_nsweeps.release();
-	e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
+	e->b_xrec.release(); e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
 	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt); }
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
@@ -691,6 +692,12 @@ void *stage_pinned(Engine *e, int slot, size_t bytes)
 	return e->h_slot[slot].need(bytes);
 }
 
+__global__ void k_ext_record(int n, const int32_t *__restrict__ active, const ExtJob *__restrict__ jobs, ExtJob *rec)
+{
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t < n) rec[t] = jobs[active[t]];
+}
+
 void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 {
 	CK(cudaSetDevice(e->device));
@@ -737,6 +744,10 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	const int TAIL_READS_MAX = getenv("B200_EXT_TAIL_MAX") ? atoi(getenv("B200_EXT_TAIL_MAX")) : 50000;
 	const int tail_warps = warps_for(e->max_len);
 	const char *dbg = getenv("B200_DEBUG");
+	const bool record = getenv("B200_EXT_RECORD") != nullptr;
+	const int64_t rec_cap = record ? 2 * in.n_seeds + n : 0;
+	ExtJob *d_rec = record ? e->b_xrec.as<ExtJob>((size_t)rec_cap + 1) : nullptr;
+	if (record) e->n_rec = 0;
 	int32_t ctr[16];
 	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
 	float ms_dp = 0;
@@ -781,6 +792,10 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 			fprintf(stderr, "[ext] round %d active %d jobs %d classes %d %d %d %d %d %d %d %d\n", rounds, n_active, n_jobs, ctr[1], ctr[2], ctr[3],
 			        ctr[4], ctr[5], ctr[6], ctr[7], ctr[8]);
 		if (n_jobs == 0) break;
+		if (record) {
+			if (e->n_rec + n_jobs <= rec_cap) k_ext_record<<<grid_for(n_jobs, 256), 256, 0, e->stream>>>(n_jobs, d_act[cur ^ 1], d_jobs, d_rec + e->n_rec);
+			e->n_rec = std::min<int64_t>(e->n_rec + n_jobs, rec_cap);
+		}
 		CK(cub::DeviceRadixSort::SortPairsDescending(d_sort_tmp, sort_tmp, d_key, d_key2, d_act[cur ^ 1], d_ord, n_jobs, 0, 31, e->stream));
 		e->stats.n_launches += 3;
 		ev_pair();
@@ -848,6 +863,75 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	Counters c = e->read_counters();
 	e->stats.extend_cells += (int64_t)c.ext_cells;
 	e->stats.n_extend_jobs += (int64_t)c.ext_calls;
+}
+
+// Kernel-isolated ksw_extend2 (BASELINE configs[1]: "the exact ksw_extend2 job list ... dump once, replay on GPU"): all the jobs the
+// last stage_extend call recorded (B200_EXT_RECORD) as ONE batch through the same DP kernels - no chain2aln rounds in between, so
+// no round runs with too few jobs to fill the chip.  Returns the DP time in ms; *cells = reference cell count of the batch.
+double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t *n_jobs)
+{
+	CK(cudaSetDevice(e->device));
+	const int64_t n = e->n_rec;
+	*cells = 0; *n_jobs = n;
+	if (n == 0) return 0;
+	ExtJob *d_rec = (ExtJob *)e->b_xrec.p;
+	std::vector<ExtJob> hj(n);
+	CK(cudaMemcpy(hj.data(), d_rec, sizeof(ExtJob) * n, cudaMemcpyDeviceToHost));
+	const int class_cap[EXT_N_CLASS] = { 32, 64, 96, 128, 160, 256, 704, 0x7fffffff };
+	std::vector<uint64_t> key(n);
+	int64_t cnt[EXT_N_CLASS] = { 0 };
+	for (int64_t i = 0; i < n; ++i) {
+		const ExtJob &j = hj[i];
+		int c = 0;
+		if ((long long)j.h0 + (long long)j.qlen * eo.max_sc >= 32768) c = EXT_N_CLASS - 1;
+		else while (j.qlen > class_cap[c]) ++c;
+		++cnt[c];
+		const uint64_t k32 = ((uint64_t)c << 28) | ((uint64_t)(std::min(j.qlen, 0x3fff) & 0xfff) << 16) | (uint64_t)std::min(j.tlen, 0xffff);
+		key[i] = k32 << 32 | (uint64_t)i;
+	}
+	std::sort(key.begin(), key.end(), std::greater<uint64_t>());          // like the pipeline: largest class, longest query first
+	std::vector<int32_t> order(n);
+	for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)(uint32_t)key[i];
+	int32_t *d_ord = e->b_xord.as<int32_t>(n);
+	CK(cudaMemcpy(d_ord, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
+	CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+	CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
+	e->zero_counters();
+	e->sync();
+	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
+	e->tic();
+	CK(cudaEventRecord(e->ev_fork, e->stream));
+	int64_t pos = 0;
+	int k = 0;
+	for (int c = EXT_N_CLASS - 1; c >= 0; --c) {
+		const int n_c = (int)cnt[c];
+		if (n_c == 0) continue;
+		cudaStream_t st = e->side[k % Engine::N_SIDE];
+		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+		const int qcap = c < EXT_N_CLASS - 1 ? class_cap[c] : e->max_len;
+		const int wpb = warps_for(qcap);
+		if (wpb && (n_c < 2048 || c >= EXT_N_CLASS - 3))
+			k_ext_dp_warp<<<grid_for(n_c, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, qcap, d_cells, d_calls);
+		else if (c < EXT_N_CLASS - 1) {
+			const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
+			const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+			k_ext_dp<<<grid_for(n_c, threads), threads, per_warp * (threads / 32), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, qcap, d_cells, d_calls);
+		} else {
+			const int64_t stride = ((int64_t)n_c + 31) & ~31ll;
+			int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
+			k_ext_dp_big<<<grid_for(n_c, 128), 128, 0, st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, d_eh, stride, d_cells, d_calls);
+		}
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(e->ev_join[k % Engine::N_SIDE], st));
+		pos += n_c;
+		++k;
+	}
+	for (int q = 0; q < k && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
+	const double ms = e->toc();
+	Counters cc = e->read_counters();
+	*cells = (int64_t)cc.ext_cells;
+	return ms;
 }
 
 // b200_ksw_extend2_batch: the caller's jobs run through the same three DP kernels as the pipeline (one job per lane,

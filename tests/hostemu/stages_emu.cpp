@@ -224,6 +224,8 @@ void *stage_pinned(Engine *e, int slot, size_t bytes)
 	return e->pinned[slot].data();
 }
 
+double stage_extend_replay(Engine *, const ExtOpt &, int64_t *cells, int64_t *n_jobs) { *cells = 0; *n_jobs = 0; return 0; }
+
 // the two chaining kernels of stages_cuda.cu as loops over the reads
 void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool)
 {

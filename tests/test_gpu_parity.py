@@ -409,6 +409,19 @@ def test_properties_at_scale(tmp_path):
     finally:
         os.environ.pop("B200_CHAIN", None)
     assert s16 == again == s3 == s_chk
+    # kernel-isolated replay of the chunk's ksw_extend2 job list (bench.py's one-batch figure): same cell count per job as the rounds
+    os.environ["B200_EXT_RECORD"] = "1"
+    os.environ["B200_LANES"] = "1"
+    try:
+        assert a.align(r1, r2, K=1 << 40) == a.align_fastq(r1, r2)
+        st = a.stats()
+    finally:
+        os.environ.pop("B200_EXT_RECORD", None)
+        os.environ.pop("B200_LANES", None)
+    cells, jobs = C.c_int64(), C.c_int64()
+    ms = a.lib.b200_ext_replay(a.opt, C.byref(cells), C.byref(jobs))
+    assert ms > 0 and 0.9 * st["n_extend_jobs"] <= jobs.value <= st["n_extend_jobs"]
+    assert 0.9 * st["extend_cells"] <= cells.value <= st["extend_cells"]
     flags = np.array([int(l.split(b"\t", 2)[1]) for l in s16.split(b"\n") if l])
     assert int(((flags & 0x900) == 0).sum()) == 400000            # one primary record per read
     assert ((flags & 4) == 0).mean() > 0.98                        # simulated reads map

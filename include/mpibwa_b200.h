@@ -238,6 +238,8 @@ int  b200_gpu_init(const bwaidx_t *idx, int device);
 /* Optional: encode the reads of the coming mem_process_seqs(…, n, seqs, …) call in place and make them resident in HBM
  * ahead of time (the call then skips its own encode + upload).  Used to time the path with device-resident inputs. */
 void b200_stage_reads(const mem_opt_t *opt, const bwaidx_t *idx, int n, bseq1_t *seqs);
+/* (a staged chunk occupies one of the library's four chunk slots until the call for the same `seqs` takes it over: stage at most
+ *  four chunks ahead, or the next stage / begin call waits for a slot) */
 void b200_gpu_release(void);
 int  b200_device_count(void);
 

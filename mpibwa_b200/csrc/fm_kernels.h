@@ -44,7 +44,6 @@ struct FmView {
 	const int64_t *ctg_off;     // contig offsets (forward strand)
 	const int32_t *ctg_len;
 	int n_ctg;
-	int xflags;                 // experiment switches (B200_X)
 };
 
 struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads

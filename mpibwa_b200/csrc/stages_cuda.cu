@@ -2,14 +2,15 @@
 // linked into libmpibwa_b200.so; there is no CPU execution path (every entry aborts when CUDA is unusable).
 //
 // Data resident in HBM for the life of the engine (uploaded once from the .map image / bwa_idx_load result):
-//   bwt   occ-interleaved BWT, 64-byte blocks (uint64 occ[4] | 128 two-bit symbols)   reference src/bwt.h:72-78
+//   occ   the reference's occ-interleaved BWT (src/bwt.h:72-78) re-blocked at upload into 32-byte occ sectors (fm_kernels.h)
 //   sa    suffix-array samples (every sa_intv-th row)                                 reference src/bwt.c:86-96
 //   pac   2-bit forward strand                                                         reference src/bntseq.c:224-225
-//   contig offset/length tables                                                        reference src/bntseq.h:44-51
-// An L2 access-policy window (persisting) is laid over the BWT for the seeding kernels.
+//   contig offset/length/ALT tables                                                    reference src/bntseq.h:44-51
+// An L2 access-policy window (persisting) is laid over the occ sectors for the seeding kernels.
 //
-// Per chunk: encoded reads are uploaded once (stage_upload_reads) and stay resident for seeding, extension and
-// mate rescue; the kernels in ksw_extend_kernel.cuh / ksw_align_kernel.cuh / smem_kernel.cuh do the work.
+// Per chunk: encoded reads are uploaded once (stage_upload_reads) and stay resident for seeding, chaining, extension, mate
+// rescue and the CIGAR stage; the kernels live in smem_sweeps.cuh / smem_kernel.cuh (seeding), chain_kernels.h (chaining),
+// ext_rounds.cuh (ksw_extend2), sw_warp_kernel.cuh (ksw_align2) and global_kernels.h (ksw_global2 + traceback).
 #include "stages.h"
 #include "util.h"
 #include "ext_rounds.cuh"
@@ -203,7 +204,6 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.seq_len = bwt->seq_len; fm.sa_intv = bwt->sa_intv;
 	fm.pac = (const uint8_t *)e->d_pac; fm.l_pac = bns->l_pac;
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
-	fm.xflags = 0;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
 
@@ -525,7 +525,6 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out, bool keep_on_device)
 {
 	CK(cudaSetDevice(e->device));
 	const int n_reads = e->n_reads;
-	e->fm.xflags = getenv("B200_X") ? atoi(getenv("B200_X")) : 0;
 	if (e->max_len > 0xffff) die("reads of 65536 bases or more are not supported by the seeding stage");
 	int64_t *seed_off = (int64_t *)e->h_seed_off.need(sizeof(int64_t) * (n_reads + 1));
 	int32_t *l_rep = (int32_t *)e->h_lrep.need(sizeof(int32_t) * (n_reads + 1));

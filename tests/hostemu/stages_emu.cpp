@@ -46,7 +46,7 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	e->fm.occ = e->occ->data(); e->fm.sa = bwt->sa; e->fm.primary = bwt->primary;
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
-	e->fm.pac = pac; e->fm.l_pac = bns->l_pac; e->fm.xflags = 0;
+	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
 	for (int i = 0; i < bns->n_seqs; ++i) { e->ctg_off.push_back(bns->anns[i].offset); e->ctg_len.push_back(bns->anns[i].len); }
 	for (int i = 0; i < bns->n_seqs; ++i) e->ctg_alt.push_back(bns->anns[i].is_alt ? 1 : 0);
 	e->ctg_alt.push_back(0);

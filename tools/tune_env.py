@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sweep an environment knob of the device stages over the bench workload and print the CUDA-event kernel times.
-usage: tune_env.py NAME v1 v2 ...   (e.g. B200_SEED_SERVICE 1 4 8 12 16); one whole chunk per setting, B200_LANES=1"""
+usage: tune_env.py NAME v1 v2 ...   (e.g. B200_EXT_WARP_MAX 1024 2048 4096; B200_TUNE_REF_BP picks the reference size); one whole chunk per setting, B200_LANES=1"""
 import os
 import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -48,6 +48,7 @@ def parse_args():
     p.add_argument("--ref-sample-pairs", type=int, default=333_334, help="pairs per step of the CPU reference arm (one chunk)")
     p.add_argument("--cpu-baseline-pairs", type=int, default=1_000_000, help="pairs of the cpu_baseline sample of the b200 arm")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--parity-chunks", type=int, default=1, help="chunks per rank whose SAM is compared (md5) with the compiled reference's, untimed")
     return p.parse_args()
 
 
@@ -133,15 +134,46 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ reference arm
 
-def run_ref_driver(prefix, f1, f2, K, threads):
+def run_ref_driver(prefix, f1, f2, K, threads, digest=None):
+    """runs oracle/_ref/ref_driver; digest: a hashlib object that is fed the SAM records it prints (else they are dropped)"""
     drv = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
-    r = subprocess.run([drv, "-t", str(threads), "-K", str(K), "-v", "1", prefix, f1, f2], stdout=subprocess.DEVNULL,
-                       stderr=subprocess.PIPE, text=True, check=True)
-    for line in r.stderr.splitlines():
+    cmd = [drv, "-t", str(threads), "-K", str(K), "-v", "1", prefix, f1, f2]
+    if digest is None:
+        r = subprocess.run(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, check=True)
+        err = r.stderr
+    else:
+        with subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE) as pr:
+            t = threading.Thread(target=lambda: errbuf.append(pr.stderr.read()))
+            errbuf = []
+            t.start()
+            n = 0
+            for blk in iter(lambda: pr.stdout.read(1 << 22), b""):
+                digest.update(blk)
+                n += len(blk)
+            t.join()
+            if pr.wait() != 0:
+                raise RuntimeError("ref_driver failed:\n" + errbuf[0].decode()[-2000:])
+        err = errbuf[0].decode()
+        digest.n_bytes = n
+    for line in err.splitlines():
         if line.startswith("[ref_driver]"):
             kv = dict(x.split("=") for x in line.split()[1:])
             return int(kv["reads"]), float(kv["mem_process_seqs_sec"])
-    raise RuntimeError("ref_driver printed no timing line:\n" + r.stderr[-2000:])
+    raise RuntimeError("ref_driver printed no timing line:\n" + err[-2000:])
+
+
+class Digest:
+    """md5 + byte count of a SAM stream"""
+
+    def __init__(self):
+        import hashlib
+        self.h, self.n_bytes = hashlib.md5(), 0
+
+    def update(self, b):
+        self.h.update(b)
+
+    def hexdigest(self):
+        return self.h.hexdigest()
 
 
 def slice_fastq(src, dst, first_read, n_reads, rec_bytes):
@@ -189,8 +221,9 @@ def workload_config(args, what):
     return {"workload": "configs[1]: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (4 contigs, 5%% planted repeats), -K %d"
                         % (args.pairs, args.read_len, args.ref_bp, args.K),
             "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, up to four chunks in flight, each as one batch per kernel" % ((args.K // 2) // args.read_len + 1),
-            "path": what, "cache_policy": "every step aligns a different chunk; index (175 MB) + chunk buffers exceed the 126 MB L2; "
-                                          "an L2-sized buffer is rewritten between steps"}
+            "path": what, "cache_policy": "steps cycle over the rank's %d chunks (consecutive steps never align the same chunk; with up to four chunks in "
+                                          "flight a chunk may be in flight twice); index (%d MB) + per-chunk buffers exceed the 126 MB L2; an L2-sized buffer "
+                                          "is rewritten before each timed region" % (max(1, -(-args.pairs // ((args.K // 2) // args.read_len + 1))), int(args.ref_bp * 1.75e-6))}
 
 
 # ------------------------------------------------------------------------------------------------ b200 arm
@@ -329,12 +362,15 @@ def main():
         job = lib.b200_align_fastq_begin(al.opt, al.idx, 0, C.c_void_p(a1[0].ctypes.data), a1[1], C.c_void_p(a2[0].ctypes.data), a2[1])
         return (job, a1, a2, n)
 
-    def e2e_end(h, st):
+    def e2e_end(h, st, digest=None):
         job, a1, a2, n = h
         sam = C.c_void_p()
         sam_len = C.c_int64()
         lib.b200_align_chunk_end(job, C.byref(sam), C.byref(sam_len), C.byref(st))
         out_len = sam_len.value
+        if digest is not None:
+            digest.update(C.string_at(sam, out_len))
+            digest.n_bytes += out_len
         lib.b200_free(sam)
         return n, out_len
 
@@ -458,6 +494,31 @@ def main():
     e2e_ms = e0.elapsed_time(e1)
     wall_ms = 1e3 * (time.time() - t0)
     clocks = sampler.result()
+    # ---- untimed parity leg: the SAM of the first timed chunk(s) of this rank, end to end through the same call, against the
+    # compiled reference's (oracle/_ref/ref_driver) on the same fastq slice - md5 of the record bytes
+    parity = {"chunks": 0, "identical": None, "checked_against": None}
+    ref_drv_path = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    if args.parity_chunks > 0 and os.path.exists(ref_drv_path):
+        ident, nb = True, 0
+        for pc in range(args.parity_chunks):
+            c = args.warmup + pc
+            b, e = chunks[c % len(chunks)]
+            mine = Digest()
+            st_ = M.b200_stats_t()
+            e2e_end(e2e_begin(c), st_, mine)
+            d = workload_dir(args)
+            s1, s2 = os.path.join(d, "parity%d_1.fq" % rank), os.path.join(d, "parity%d_2.fq" % rank)
+            slice_fastq(f1, s1, b, e - b, rb1)
+            slice_fastq(f2, s2, b, e - b, rb2)
+            theirs = Digest()
+            run_ref_driver(prefix, s1, s2, args.K, n_threads, theirs)
+            same = mine.hexdigest() == theirs.hexdigest() and mine.n_bytes == theirs.n_bytes
+            log("[bench] rank %d parity chunk %d: %d pairs, %d SAM bytes, md5 %s vs reference %s -> %s"
+                % (rank, c, e - b, mine.n_bytes, mine.hexdigest(), theirs.hexdigest(), "identical" if same else "DIFFERENT"))
+            ident = ident and same
+            nb += mine.n_bytes
+        parity = {"chunks": args.parity_chunks, "identical": ident, "sam_bytes": nb,
+                  "checked_against": "oracle/_ref/ref_driver (unmodified reference sources) on the same fastq slice, md5 of the SAM records"}
     # ---- untimed extra pass with the whole chunk as ONE batch per kernel (no sub-batch lanes): kernel-isolated efficiency
     os.environ["B200_LANES"] = "1"
     resident_group(args.warmup + args.steps, 1, ev0, ev1)          # first one grows the device buffers to whole-chunk size
@@ -473,13 +534,17 @@ def main():
     rp_ms = lib.b200_ext_replay(al.opt, C.byref(rp_cells), C.byref(rp_jobs))
 
     # ---- reduce over ranks: MAX of times, SUM of pairs
-    t = torch.tensor([res_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([res_pairs, e2e_pairs], dtype=torch.float64, device="cuda")
+    bad = 0.0 if parity["identical"] in (True, None) else 1.0
+    t = torch.tensor([res_ms, e2e_ms, bad], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([res_pairs, e2e_pairs, parity["chunks"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    res_ms_max, e2e_ms_max = t.tolist()
-    res_pairs_all, e2e_pairs_all = cnt.tolist()
+    res_ms_max, e2e_ms_max, any_bad = t.tolist()
+    res_pairs_all, e2e_pairs_all, parity_chunks_all = cnt.tolist()
+    if parity["identical"] is not None:
+        parity["identical"] = any_bad == 0.0
+        parity["chunks"] = int(parity_chunks_all)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -522,7 +587,7 @@ def main():
                                "gcups": (rp_cells.value / rp_ms / 1e6) if rp_ms > 0 else None,
                                "frac": (rp_cells.value / rp_ms / 1e6 * 14 / i32_peak) if rp_ms > 0 and i32_peak else None},
         "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global", "ms_total")},
-        "host_threads": n_threads,
+        "host_threads": n_threads, "parity": parity,
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
         cores = os.cpu_count() or 1
@@ -537,6 +602,9 @@ def main():
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if parity["identical"] is False:
+        log("[bench] FAILED: the SAM of the benchmarked workload differs from the compiled reference's")
+        return 1
     return 0
 
 

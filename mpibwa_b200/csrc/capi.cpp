@@ -14,6 +14,8 @@
 namespace b200 {
 Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac);
 Engine *engine_current();
+Engine *aux_acquire();
+void aux_release();
 void engine_select_device(int dev);
 void engine_release();
 ExtOpt make_ext_opt(const mem_opt_t *opt);
@@ -36,12 +38,15 @@ static void die(const char *what, const char *arg)
 	abort();
 }
 
-static Engine *need_engine()
-{
-	Engine *e = engine_current();
-	if (!e) die("no index on the device: call b200_gpu_init() or mem_process_seqs() first", nullptr);
-	return e;
-}
+// The single-job / caller-batch entry points run on an engine of their own, one call at a time, and take the device turn like a
+// chunk job's stage does: they are safe to call from several threads and while b200_process_seqs_begin jobs are in flight.
+struct AuxGuard {
+	Engine *e;
+	AuxGuard() : e(aux_acquire()) { if (!e) die("no index on the device: call b200_gpu_init() or mem_process_seqs() first", nullptr); }
+	~AuxGuard() { aux_release(); }
+	AuxGuard(const AuxGuard &) = delete;
+	operator Engine *() const { return e; }
+};
 } // namespace b200
 
 using namespace b200;
@@ -447,7 +452,7 @@ int64_t b200_align_chunk_end(b200_job_t *j, char **sam, int64_t *sam_len, b200_s
 {
 	process_seqs_end(j->job, stats);
 	const int64_t total = j->total;
-	if (sam) *sam = j->sam; else free(j->sam);
+	if (sam) *sam = j->sam; else b200_free(j->sam);      // (pool buffer: never free())
 	if (sam_len) *sam_len = j->sam_len;
 	delete j;
 	return total;
@@ -461,7 +466,7 @@ int64_t b200_align_chunk(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_pr
 
 double b200_ext_replay(const mem_opt_t *opt, int64_t *cells, int64_t *n_jobs)
 {
-	return stage_extend_replay(need_engine(), make_ext_opt(opt), cells, n_jobs);
+	return stage_extend_replay(engine_current(), make_ext_opt(opt), cells, n_jobs);    // (bench tool: replays what the primary engine recorded; no job may be in flight)
 }
 
 void b200_get_stats(b200_stats_t *out)
@@ -485,7 +490,7 @@ int b200_ksw_extend2_batch(int64_t n_jobs, b200_extend_job_t *jobs, const uint8_
                            const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
                            int o_del, int e_del, int o_ins, int e_ins, int zdrop)
 {
-	Engine *eng = need_engine();
+	AuxGuard eng;
 	stage_extend_bytes(eng, ext_opt_from(mat, o_del, e_del, o_ins, e_ins, zdrop), n_jobs, jobs,
 	                   query, query_bytes, target, target_bytes);
 	return 0;
@@ -495,7 +500,7 @@ int b200_ksw_align2_batch(int64_t n_jobs, b200_align_job_t *jobs, const uint8_t 
                           const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
                           int o_del, int e_del, int o_ins, int e_ins)
 {
-	Engine *eng = need_engine();
+	AuxGuard eng;
 	stage_sw_bytes(eng, make_sw_opt(mat, o_del, e_del, o_ins, e_ins), n_jobs, jobs, query, query_bytes, target, target_bytes);
 	return 0;
 }
@@ -505,7 +510,7 @@ int b200_collect_intv_batch(const mem_opt_t *opt, int n_reads, const int64_t *of
 {
 	std::vector<int64_t> io;
 	std::vector<Intv> iv;
-	stage_collect_intv(need_engine(), make_seed_opt(opt), n_reads, off, seq, io, iv);
+	{ AuxGuard eng; stage_collect_intv(eng, make_seed_opt(opt), n_reads, off, seq, io, iv); }
 	*intv_off = (int64_t *)malloc(io.size() * sizeof(int64_t));
 	memcpy(*intv_off, io.data(), io.size() * sizeof(int64_t));
 	*intv = (bwtintv_t *)malloc((iv.size() + 1) * sizeof(bwtintv_t));
@@ -515,7 +520,8 @@ int b200_collect_intv_batch(const mem_opt_t *opt, int n_reads, const int64_t *of
 
 int b200_bwt_sa_batch(int64_t n, const bwtint_t *k, bwtint_t *sa)
 {
-	stage_sa(need_engine(), n, k, sa);
+	AuxGuard eng;
+	stage_sa(eng, n, k, sa);
 	return 0;
 }
 
@@ -570,7 +576,7 @@ void bwt_extend(const bwt_t *bwt, const bwtintv_t *ik, bwtintv_t ok[4], int is_b
 {
 	(void)bwt;
 	Intv in = { ik->x[0], ik->x[1], ik->x[2], ik->info }, out[4];
-	stage_fm_extend(need_engine(), in, out, is_back);
+	{ AuxGuard eng; stage_fm_extend(eng, in, out, is_back); }
 	for (int i = 0; i < 4; ++i) { ok[i].x[0] = out[i].x0; ok[i].x[1] = out[i].x1; ok[i].x[2] = out[i].x2; }
 }
 
@@ -578,7 +584,8 @@ bwtint_t bwt_sa(const bwt_t *bwt, bwtint_t k)
 {
 	(void)bwt;
 	bwtint_t r;
-	stage_sa(need_engine(), 1, &k, &r);
+	AuxGuard eng;
+	stage_sa(eng, 1, &k, &r);
 	return r;
 }
 
@@ -587,7 +594,7 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 {
 	(void)pac;
 	if (c->n == 0) return;
-	Engine *eng = need_engine();
+	AuxGuard eng;
 	// one read, one chain; regions already in av take part in the containment test, so they are passed along
 	HChain hc;
 	hc.rid = c->rid; hc.frac_rep = c->frac_rep; hc.pos = c->pos;

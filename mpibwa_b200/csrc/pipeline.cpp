@@ -43,7 +43,7 @@ static double now_ms()
 static std::mutex g_mu;
 static std::vector<Engine *> g_engines;     // [0] owns the index in HBM; the others are clones that share it (one per sub-batch lane)
 static const void *g_engine_key = nullptr;
-static int g_device = -1;
+static int g_device = -1, g_engine_dev = -1;     // requested device (-1: from the launcher's local rank), device of g_engines
 // One lane at a time drives the GPU (the host stages of the other lanes and jobs overlap it).  The lock is handed to the waiter
 // of the OLDEST chunk job: a chunk that has reached its last device stage does not queue behind the seeding of three
 // younger chunks, which keeps the latency of a job - and the ramp of a short run - down.
@@ -71,21 +71,47 @@ private:
 static DeviceTurn g_gpu_turn;
 struct DeviceTurnGuard { uint64_t t; explicit DeviceTurnGuard(uint64_t t_) : t(t_) { g_gpu_turn.lock(t); } ~DeviceTurnGuard() { g_gpu_turn.unlock(); } };
 
+// engine of the single-job C wrappers (ksw_extend2, bwt_sa, ... in capi.cpp): a clone of its own, so that those calls never
+// touch the resident reads, scratch buffers or counters of a chunk job; serialised by g_aux_mu and the device turn (AuxGuard)
+static Engine *g_aux = nullptr;
+static std::mutex g_aux_mu;
+static int g_running = 0;                    // chunk jobs past their turn gate (guarded by g_slot_mu)
+static std::mutex g_slot_mu;
+
+static void destroy_engines_locked()
+{
+	if (g_aux) { engine_destroy(g_aux); g_aux = nullptr; }
+	for (size_t k = g_engines.size(); k-- > 0;) engine_destroy(g_engines[k]);
+	g_engines.clear(); g_engine_key = nullptr;
+}
+
+// local rank of this process: torchrun, Open MPI, MVAPICH2, Intel MPI / MPICH (hydra), Slurm - the reference hosts are
+// launched with mpirun or srun, not torchrun
+static int local_rank_from_env()
+{
+	static const char *names[] = { "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK", "MPI_LOCALRANKID", "SLURM_LOCALID" };
+	for (const char *n : names) { const char *v = getenv(n); if (v && *v) return atoi(v); }
+	return 0;
+}
+
 Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (!g_engines.empty() && g_engine_key == (const void *)bwt->bwt) return g_engines[0];
-	for (size_t k = g_engines.size(); k-- > 0;) engine_destroy(g_engines[k]);
-	g_engines.clear();
 	int dev = g_device;
 	if (dev < 0) {
-		const char *lr = getenv("LOCAL_RANK");
-		dev = lr ? atoi(lr) : 0;
+		dev = local_rank_from_env();
 		int nd = engine_device_count();
 		if (nd > 0) dev %= nd;
 	}
+	if (!g_engines.empty() && g_engine_key == (const void *)bwt->bwt && g_engine_dev == dev) return g_engines[0];
+	if (!g_engines.empty()) {
+		std::lock_guard<std::mutex> sl(g_slot_mu);
+		if (g_running > 0) { fprintf(stderr, "[mpibwa_b200] the index or device was changed while chunk jobs are in flight\n"); abort(); }
+	}
+	destroy_engines_locked();
 	g_engines.push_back(engine_create(bwt, bns, pac, dev));
 	g_engine_key = (const void *)bwt->bwt;
+	g_engine_dev = dev;
 	return g_engines[0];
 }
 
@@ -104,9 +130,7 @@ static Engine *engine_lane(int slot, int k)
 // the device stages of chunk i+1 run under the host stages (rescue replay, pairing, SAM text) of chunk i.
 struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0, staged_lanes = 0; int64_t staged_bases = 0; };
 static Slot g_slots[N_SLOTS];
-static std::mutex g_slot_mu;
 static std::condition_variable g_slot_cv;
-static int g_running = 0;
 static uint64_t g_ticket_next = 0, g_ticket_serving = 0;
 static b200_stats_t g_last_stats;
 
@@ -114,10 +138,28 @@ void engine_select_device(int dev) { g_device = dev; }
 void engine_release()
 {
 	std::lock_guard<std::mutex> lk(g_mu);
-	for (size_t k = g_engines.size(); k-- > 0;) engine_destroy(g_engines[k]);
-	g_engines.clear(); g_engine_key = nullptr;
+	{
+		std::lock_guard<std::mutex> sl(g_slot_mu);
+		if (g_running > 0) { fprintf(stderr, "[mpibwa_b200] b200_gpu_release() while chunk jobs are in flight\n"); abort(); }
+	}
+	destroy_engines_locked();
 }
 Engine *engine_current() { return g_engines.empty() ? nullptr : g_engines[0]; }
+
+// AuxGuard: exclusive use of the wrappers' engine and of the device for the lifetime of the guard.  The wrappers queue behind
+// every waiting chunk job (ticket = max).
+Engine *aux_acquire()
+{
+	g_aux_mu.lock();
+	{
+		std::lock_guard<std::mutex> lk(g_mu);
+		if (g_engines.empty()) { g_aux_mu.unlock(); return nullptr; }
+		if (!g_aux) g_aux = engine_clone(g_engines[0]);
+	}
+	g_gpu_turn.lock(~(uint64_t)0);
+	return g_aux;
+}
+void aux_release() { g_gpu_turn.unlock(); g_aux_mu.unlock(); }
 void last_stats(b200_stats_t *out) { std::lock_guard<std::mutex> lk(g_slot_mu); *out = g_last_stats; }
 
 /* ------------------------------------------------------------------ option packing */

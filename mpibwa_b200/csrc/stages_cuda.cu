@@ -99,6 +99,9 @@ public:
 	cudaStream_t side[N_SIDE];
 	cudaEvent_t ev_fork = nullptr, ev_join[N_SIDE];
 	Counters *d_cnt = nullptr;
+	// per-device launch configuration, set up once per engine (kernel attributes and occupancy belong to the device)
+	int n_sm = 0, seed_blocks_per_sm = 0, bwd_blocks_per_sm = 0, fwd_blocks_per_sm = 0;
+	bool ext_attr_set = false, global_attr_set = false;
 
 	void tic() { CK(cudaEventRecord(ev0, stream)); }
 	double toc()
@@ -272,7 +275,9 @@ void engine_destroy(Engine *e)
 	e->b_xrec.release(); e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
 	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt); }
 	cudaFree(e->d_cnt);
-	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1);
+	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork);
+	for (int i = 0; i < Engine::N_SIDE; ++i) { cudaStreamDestroy(e->side[i]); cudaEventDestroy(e->ev_join[i]); }
+	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	cudaStreamDestroy(e->stream);
 	delete e;
 }
@@ -408,8 +413,8 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
                            bool want_lrep)
 {
 	const int n = r1 - r0;
-	static int blocks_per_sm = 0, n_sm = 0;
-	static int bwd_blocks_per_sm = 0, fwd_blocks_per_sm = 0;
+	int &blocks_per_sm = e->seed_blocks_per_sm, &n_sm = e->n_sm;
+	int &bwd_blocks_per_sm = e->bwd_blocks_per_sm, &fwd_blocks_per_sm = e->fwd_blocks_per_sm;
 	const int threads = 128, quota = 16;                                // (fewer entries in shared memory: measured slower - the spill strip is in HBM)
 	const size_t sh_bytes = (size_t)threads * quota * 16;               // interval lists
 	if (!blocks_per_sm) {
@@ -697,6 +702,15 @@ __global__ void k_ext_record(int n, const int32_t *__restrict__ active, const Ex
 	if (t < n) rec[t] = jobs[active[t]];
 }
 
+static void ext_set_attrs(Engine *e)
+{
+	if (e->ext_attr_set) return;
+	CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+	CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	CK(cudaFuncSetAttribute(k_ext_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	e->ext_attr_set = true;
+}
+
 void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 {
 	CK(cudaSetDevice(e->device));
@@ -724,13 +738,7 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 		e->h2d(d_se, in.seeds, sizeof(DSeed) * in.n_seeds);
 		e->h2d(d_srt, in.srt, sizeof(int32_t) * in.n_seeds);
 	}
-	static bool attr_set = false;
-	if (!attr_set) {
-		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-		CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		CK(cudaFuncSetAttribute(k_ext_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		attr_set = true;
-	}
+	ext_set_attrs(e);
 	size_t sort_tmp = 0;
 	CK(cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_tmp, d_key, d_key2, d_act[0], d_ord, n, 0, 31, e->stream));
 	void *d_sort_tmp = e->b_cub.need(sort_tmp);
@@ -893,8 +901,7 @@ double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t 
 	for (int64_t i = 0; i < n; ++i) order[i] = (int32_t)(uint32_t)key[i];
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);
 	CK(cudaMemcpy(d_ord, order.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice));
-	CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-	CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+	ext_set_attrs(e);
 	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
 	e->zero_counters();
 	e->sync();
@@ -973,12 +980,7 @@ void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend
 	e->h2d(d_ord, order.data(), sizeof(int32_t) * n_jobs);
 	e->h2d(dq, query, qbytes);
 	e->h2d(dt, target, tbytes);
-	static bool attr_set = false;
-	if (!attr_set) {
-		CK(cudaFuncSetAttribute(k_ext_dp, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-		CK(cudaFuncSetAttribute(k_ext_dp_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-		attr_set = true;
-	}
+	ext_set_attrs(e);
 	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
 	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
 	e->tic();
@@ -1281,8 +1283,7 @@ const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<
 	int32_t *d_ord = e->b_xord.as<int32_t>(n);
 	uint8_t *z = e->b_gz.as<uint8_t>((size_t)z_bytes + 64);
 	e->h2d(dj, jobs.data(), sizeof(GlobalJob) * n);
-	static bool attr_set = false;
-	if (!attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+	if (!e->global_attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); e->global_attr_set = true; }
 	GlobalRes *hr = (GlobalRes *)e->h_gres.need(sizeof(GlobalRes) * n);
 	std::vector<int32_t> sel(n), order, key;
 	const bool squeeze = getenv("B200_GLOBAL_SQUEEZE") != nullptr;

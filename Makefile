@@ -7,7 +7,8 @@ NVCC     ?= /usr/local/cuda/bin/nvcc
 CXX      ?= g++
 CC       ?= gcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC,-O3,-pthread -Xptxas -v --expt-relaxed-constexpr
+# -fmad=false: the finish stages reproduce the reference's double/float decisions; a*b+c must stay two IEEE operations
+NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -fmad=false -Xcompiler -fPIC,-O3,-pthread -Xptxas -v --expt-relaxed-constexpr
 CXXFLAGS := -O3 -std=c++17 -fPIC -pthread -Wall -Wno-unused-function
 CSRC     := mpibwa_b200/csrc
 HOSTSRC  := $(CSRC)/capi.cpp $(CSRC)/host_align.cpp $(CSRC)/pipeline.cpp $(CSRC)/hostshim.cpp

@@ -306,6 +306,13 @@ typedef struct {
 	double ms_sam_plan, ms_global;   /* inside ms_sam_host: the dry-run sweep that queues the CIGAR jobs; the device CIGAR stage (wall) */
 	int64_t n_global_host;    /* regions whose CIGAR the SAM sweep computed with the host routine (not queued for the device stage) */
 	double ms_k_chain;        /* CUDA-event time of the chaining kernels (ms_chain_host is the wall of the whole chaining stage, host or device) */
+	/* finish stages (everything after seed extension runs on the device): ms_regs_host / ms_rescue / ms_sam_plan / ms_global /
+	 * ms_sam_host above are now the WALLS of region de-duplication, mate rescue, pairing + record plan, the CIGAR stage and
+	 * NM/MD + SAM text; the names are kept for the bench records of earlier rounds */
+	double ms_k_finish;       /* CUDA-event time of all finish-stage kernels but ksw_align2 and ksw_global2 */
+	double ms_k_samtext;      /* of which: NM/MD + SAM text kernels */
+	double ms_upload, ms_deliver; /* host walls: read text staging + H2D; SAM D2H + hand-over (per-read malloc for mem_process_seqs) */
+	int64_t n_patch_reads, n_rescue_rounds, n_global_rerun, n_aln_slots, sam_bytes;
 } b200_stats_t;
 /* kernel-isolated ksw_extend2: with B200_EXT_RECORD set in the environment the extension stage keeps every job of the call; this
  * replays them as ONE batch through the DP kernels on the primary engine and returns the time in ms (bench.py; run one chunk alone first) */

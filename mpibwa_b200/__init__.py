@@ -84,7 +84,10 @@ class b200_stats_t(C.Structure):
                                          "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes",
                                          "d2h_bytes")] + [("ms_k_extend_dp", C.c_double), ("n_extend_rounds", C.c_int64),
                                                           ("ms_sam_plan", C.c_double), ("ms_global", C.c_double),
-                                                          ("n_global_host", C.c_int64), ("ms_k_chain", C.c_double)]
+                                                          ("n_global_host", C.c_int64), ("ms_k_chain", C.c_double),
+                                                          ("ms_k_finish", C.c_double), ("ms_k_samtext", C.c_double),
+                                                          ("ms_upload", C.c_double), ("ms_deliver", C.c_double)] + \
+               [(n, C.c_int64) for n in ("n_patch_reads", "n_rescue_rounds", "n_global_rerun", "n_aln_slots", "sam_bytes")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

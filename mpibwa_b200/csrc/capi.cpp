@@ -26,9 +26,9 @@ void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, c
 void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int n, bseq1_t *seqs);
 struct SeqJob;
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
-                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks,
+                           bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
                            void (*before)(void *, bseq1_t **, int *));
-int64_t job_take_sam(SeqJob *j, int n_threads, char **out);
+int64_t job_take_sam(SeqJob *j, char **out);
 void process_seqs_end(SeqJob *j, b200_stats_t *stats);
 void last_stats(b200_stats_t *out);
 
@@ -405,7 +405,7 @@ b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, cons
 {
 	b200_job *j = new b200_job();
 	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
-	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 1, false, nullptr);
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr);
 	return j;
 }
 
@@ -422,9 +422,9 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->seqs = b200_chunk_seqs(n, s1, s2);
 	j->sam = nullptr; j->sam_len = 0;
 	j->n_threads = opt->n_threads;
-	// the records are written block-wise by the SAM sweep (no malloc per read) and concatenated by the job thread
+	// the chunk's text comes back from the device as one buffer (no malloc per read)
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, x->n_threads, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, 1, true, nullptr);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true, nullptr);
 	return j;
 }
 
@@ -434,7 +434,7 @@ b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->total = 0; j->seqs = nullptr; j->sam = nullptr; j->sam_len = 0; j->n_threads = opt->n_threads;
 	j->fq[0] = fq1; j->fq[1] = fq2; j->fq_len[0] = len1; j->fq_len[1] = len2; j->mate[0] = j->mate[1] = nullptr;
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, 0, nullptr, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, x->n_threads, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, 1, true,
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true,
 		[](void *p, bseq1_t **seqs, int *n) {
 			b200_job *x = (b200_job *)p;
 			const int64_t n1 = b200_fastq_parse(x->fq[0], x->fq_len[0], &x->mate[0]);
@@ -561,8 +561,12 @@ int ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target,
                 int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t **cigar)
 {
 	if (m != 5) die("ksw_global2: only the 5-letter nucleotide alphabet is supported", nullptr);
+	GlobalOpt go;
+	go.o_del = o_del; go.e_del = e_del; go.o_ins = o_ins; go.e_ins = e_ins; go.a = mat[0]; go.w_max = 0x3fffffff;
+	memcpy(go.mat, mat, 25);
 	std::vector<uint32_t> cg;
-	int score = global_align(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, (n_cigar && cigar) ? &cg : nullptr);
+	int score;
+	{ AuxGuard eng; score = stage_global_bytes(eng, go, qlen, query, tlen, target, w, (n_cigar && cigar) ? &cg : nullptr); }
 	if (n_cigar) *n_cigar = 0;
 	if (n_cigar && cigar) {
 		*n_cigar = (int)cg.size();
@@ -622,7 +626,8 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 	if (av->n != 0) die("mem_chain2aln: a non-empty region list must go through mem_process_seqs", nullptr);
 	ExtIn xin = { 1, chain_off.data(), dc.data(), 1, ds.data(), (int64_t)ds.size(), srt.data() };
 	ExtRegs xr;
-	stage_extend(eng, make_ext_opt(opt), xin, xr);
+	stage_extend(eng, make_ext_opt(opt), xin);
+	stage_extend_download(eng, xr);
 	const DReg *regs = xr.regs;
 	const int64_t *reg_off = xr.reg_off;
 	for (int i = 0; i < (int)reg_off[1]; ++i) {

@@ -13,7 +13,6 @@
 
 namespace b200 {
 
-#define B200_GLOBAL_MAX_CIGAR 28
 
 struct GlobalOpt {
 	int o_del, e_del, o_ins, e_ins;
@@ -29,14 +28,13 @@ struct GlobalJob {
 	int32_t w2;             // first band width to try (inferred from the region's score, src/bwamem.c:1107-1111)
 	int32_t truesc;
 	int32_t wmax;           // widest band any of the (up to three) tries can use - sizes the row buffer
+	int64_t cig_off;        // where the CIGAR goes in the arena (room for qlen + tlen operations)
 };
 
 struct GlobalRes {
 	int32_t score;
-	int32_t n_cigar;        // -1: more than B200_GLOBAL_MAX_CIGAR operations - the caller redoes this region itself;
-	                        // -2 (device-internal): a retry needed a wider row window than the launch had - rerun in a wider class
+	int32_t n_cigar;        // -2 (device-internal): a retry needed a wider row window than the launch had - rerun in a wider class
 	int32_t n_tries, pad;
-	uint32_t cigar[B200_GLOBAL_MAX_CIGAR];
 };
 
 #define B200_GLOBAL_MINUS_INF (-0x40000000)
@@ -93,7 +91,7 @@ struct GlobalSeqs {         // oriented views of query and target
 	B200_HD int sub(const int8_t *row, int j) const { return row[qa(j)]; }
 };
 
-// ksw_global2 with traceback.  Returns the score; cigar/n_cigar as described in GlobalRes.
+// ksw_global2 with traceback.  Returns the score; the CIGAR goes to cigar[] (room for qlen + tlen operations), its length to *n_cigar_.
 // ROW: H/E row accessor; SEQ: oriented query/target accessor (qa, ta, l_query).  z must be 4-byte aligned.
 template <class ROW, class SEQ>
 B200_HDN int global_dp(const GlobalOpt &o, const SEQ &s, int tlen, int w, ROW eh, uint8_t *z, uint32_t *cigar, int *n_cigar_,
@@ -148,21 +146,21 @@ B200_HDN int global_dp(const GlobalOpt &o, const SEQ &s, int tlen, int w, ROW eh
 	const int score = eh.h(qlen);
 	// traceback (operations come out last to first)
 	int n = 0, which = 0, i = tlen - 1, k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
-	bool over = false;
 	int last_op = -1;
+	uint32_t cur = 0;                              // the operation being grown lives in a register
 #define B200_PUSH(op_, len_) do { \
-		if (last_op != (op_)) { if (n == B200_GLOBAL_MAX_CIGAR) over = true; else { cigar[n++] = (uint32_t)(len_) << 4 | (uint32_t)(op_); last_op = (op_); } } \
-		else cigar[n - 1] += (uint32_t)(len_) << 4; } while (0)
-	while (i >= 0 && k >= 0 && !over) {
+		if (last_op != (op_)) { if (last_op >= 0) cigar[n++] = cur; cur = (uint32_t)(len_) << 4 | (uint32_t)(op_); last_op = (op_); } \
+		else cur += (uint32_t)(len_) << 4; } while (0)
+	while (i >= 0 && k >= 0) {
 		which = z[(int64_t)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
 		if (which == 0) { B200_PUSH(0, 1); --i; --k; }
 		else if (which == 1) { B200_PUSH(2, 1); --i; }
 		else { B200_PUSH(1, 1); --k; }
 	}
-	if (!over && i >= 0) B200_PUSH(2, i + 1);
-	if (!over && k >= 0) B200_PUSH(1, k + 1);
+	if (i >= 0) B200_PUSH(2, i + 1);
+	if (k >= 0) B200_PUSH(1, k + 1);
 #undef B200_PUSH
-	if (over) { *n_cigar_ = -1; return score; }
+	if (last_op >= 0) cigar[n++] = cur;
 	for (int x = 0; x < n >> 1; ++x) { const uint32_t tmp = cigar[x]; cigar[x] = cigar[n - 1 - x]; cigar[n - 1 - x] = tmp; }
 	*n_cigar_ = n;
 	return score;
@@ -171,7 +169,7 @@ B200_HDN int global_dp(const GlobalOpt &o, const SEQ &s, int tlen, int w, ROW eh
 // the band-doubling loop of mem_reg2aln around bwa_gen_cigar2 (reference src/bwamem.c:1112-1122)
 // max_band: widest band the row accessor can hold (0x7fffffff: any)
 template <class ROW, class SEQ>
-B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb, ROW eh, uint8_t *z, GlobalRes *out, int64_t *cells,
+B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb, ROW eh, uint8_t *z, uint32_t *cigar, GlobalRes *out, int64_t *cells,
                           int max_band = 0x7fffffff)
 {
 	const int l_query = s.l_query, rlen = (int)(jb.re - jb.rb);
@@ -179,14 +177,14 @@ B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb,
 	do {
 		w2 = w2 < o.w_max ? w2 : o.w_max;
 		if (l_query == rlen && w2 == 0) {
-			out->cigar[0] = (uint32_t)l_query << 4;
+			cigar[0] = (uint32_t)l_query << 4;
 			n_cigar = 1;
 			score = 0;
 			for (int x = 0; x < l_query; ++x) score += s.sub(s.trow(o, x), x);
 		} else {
 			const int w = global_band(o, l_query, rlen, w2);
 			if (w > max_band) { out->score = 0; out->n_cigar = -2; out->n_tries = i; out->pad = 0; return; }
-			score = global_dp(o, s, rlen, w, eh, z, out->cigar, &n_cigar, cells);
+			score = global_dp(o, s, rlen, w, eh, z, cigar, &n_cigar, cells);
 		}
 		if (score == last_sc || w2 == o.w_max) { ++i; break; }
 		last_sc = score;

@@ -15,6 +15,8 @@
 #include <thread>
 #include <algorithm>
 
+namespace b200 { void *stage_host_alloc(size_t bytes); void stage_host_free(void *p); }      // stages.h: page-locked on the CUDA engine
+
 // number of host threads used by the shim's own loops (parse, SAM concatenation); 0 = all hardware threads
 static int g_shim_threads = 0;
 static int shim_threads()
@@ -136,20 +138,24 @@ int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam)
 	return (int64_t)sum;
 }
 
-// Large result buffers (the concatenated SAM of a chunk: hundreds of MB) are recycled instead of returned to the system:
-// an mmap/munmap pair per chunk costs tens of thousands of page faults and a TLB shoot-down on every core of a busy host.
-// b200_big_alloc() hands out a buffer of at least `bytes`; b200_free() recognises such a buffer and parks it for the next call.
+// Large result buffers (the SAM text of a chunk: hundreds of MB) are page-locked - the device copies the text straight into them -
+// and recycled instead of returned to the system: pinning and unpinning that much memory per chunk costs milliseconds and a TLB
+// shoot-down on every core of a busy host.  b200_big_alloc() hands out a buffer of at least `bytes`; b200_free() recognises such a
+// buffer and parks it for the next call (at most eight stay parked).
 static struct BigPool { std::mutex mu; struct Ent { void *p; size_t cap; bool busy; }; std::vector<Ent> ents; } g_big;
 
 void *b200_big_alloc(size_t bytes)
 {
-	std::lock_guard<std::mutex> lk(g_big.mu);
-	for (auto &e : g_big.ents) if (!e.busy && e.cap >= bytes) { e.busy = true; return e.p; }
-	for (size_t k = 0; k < g_big.ents.size(); ++k)
-		if (!g_big.ents[k].busy && g_big.ents.size() >= 8) { free(g_big.ents[k].p); g_big.ents.erase(g_big.ents.begin() + k); break; }   // too small and the pool is full
+	{
+		std::lock_guard<std::mutex> lk(g_big.mu);
+		for (auto &e : g_big.ents) if (!e.busy && e.cap >= bytes) { e.busy = true; return e.p; }
+		for (size_t k = 0; k < g_big.ents.size(); ++k)          // a parked buffer that is too small makes room
+			if (!g_big.ents[k].busy) { b200::stage_host_free(g_big.ents[k].p); g_big.ents.erase(g_big.ents.begin() + k); break; }
+	}
 	const size_t cap = bytes + (bytes >> 3) + 4096;
-	void *p = malloc(cap);
-	if (p && g_big.ents.size() < 8) g_big.ents.push_back({ p, cap, true });
+	void *p = b200::stage_host_alloc(cap);
+	std::lock_guard<std::mutex> lk(g_big.mu);
+	g_big.ents.push_back({ p, cap, true });
 	return p;
 }
 
@@ -158,7 +164,14 @@ void b200_free(void *p)
 	if (!p) return;
 	{
 		std::lock_guard<std::mutex> lk(g_big.mu);
-		for (auto &e : g_big.ents) if (e.p == p) { e.busy = false; return; }
+		size_t parked = 0;
+		for (auto &e : g_big.ents) parked += !e.busy;
+		for (size_t k = 0; k < g_big.ents.size(); ++k)
+			if (g_big.ents[k].p == p) {
+				if (parked >= 8) { b200::stage_host_free(p); g_big.ents.erase(g_big.ents.begin() + k); }
+				else g_big.ents[k].busy = false;
+				return;
+			}
 	}
 	free(p);
 }

@@ -116,7 +116,7 @@ Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 }
 
 // engine of lane k of chunk slot `slot` (slot 0, lane 0 is the primary engine; all others are clones sharing its index)
-static const int MAX_LANES = 4, N_SLOTS = 4;
+static const int MAX_LANES = 1, N_SLOTS = 4;
 static Engine *engine_lane(int slot, int k)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
@@ -128,7 +128,7 @@ static Engine *engine_lane(int slot, int k)
 // Chunk slots: a slot is a set of lane engines that one mem_process_seqs call occupies from start to end.  Several calls
 // may be in flight (process_seqs_begin / _end): up to B200_INFLIGHT (default 4) run at once, in submission order, so that
 // the device stages of chunk i+1 run under the host stages (rescue replay, pairing, SAM text) of chunk i.
-struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0, staged_lanes = 0; int64_t staged_bases = 0; };
+struct Slot { bool busy = false; const void *staged_key = nullptr; int staged_n = 0; int64_t staged_bases = 0; };
 static Slot g_slots[N_SLOTS];
 static std::condition_variable g_slot_cv;
 static uint64_t g_ticket_next = 0, g_ticket_serving = 0;
@@ -212,122 +212,10 @@ SeedOpt make_seed_opt(const mem_opt_t *opt)
 	return s;
 }
 
-/* ------------------------------------------------------------------ mate rescue (reference src/bwamem_pair.c:111-180) */
-
-struct RescueKey { int end, anchor, r; };
-struct RescueRes { RescueKey key; int64_t rb; SwRes res; };
-
-// window of mem_matesw for orientation r; returns false when the reference would not run SW
-static bool rescue_window(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4], const mem_alnreg_t *a,
-                          int l_ms, int r, int64_t *rb_, int64_t *re_, int *is_rev_)
-{
-	const int64_t l_pac = bns->l_pac;
-	int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1), rid = -1;
-	int64_t rb, re;
-	if (!is_rev) {
-		rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
-		re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
-	} else {
-		rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
-		re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
-	}
-	if (rb < 0) rb = 0;
-	if (re > l_pac << 1) re = l_pac << 1;
-	if (rb >= re) return false;
-	bns_clip_window(bns, &rb, (rb + re) >> 1, &re, &rid);
-	*rb_ = rb; *re_ = re; *is_rev_ = is_rev;
-	return a->rid == rid && re - rb >= opt->min_seed_len;
-}
-
-static void rescue_skip_mask(const mem_pestat_t pes[4], int64_t l_pac, const mem_alnreg_t *a, const RegVec &ma, int skip[4])
-{
-	for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
-	for (size_t i = 0; i < ma.size(); ++i) {
-		int64_t dist;
-		int r = infer_dir(l_pac, a->rb, ma[i].rb, &dist);
-		if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
-	}
-}
-
-// Replays mem_matesw for one anchor with precomputed SW results.  Returns false (and reports the missing job)
-// when a result that the reference would compute here is not in `have`.
-static bool rescue_replay_anchor(const mem_opt_t *opt, const bntseq_t *bns, const mem_pestat_t pes[4],
-                                 const mem_alnreg_t *a, int l_ms, RegVec &ma, int end, int anchor,
-                                 const std::vector<RescueRes> &have, RescueKey *missing)
-{
-	const int64_t l_pac = bns->l_pac;
-	int skip[4], n = 0;
-	rescue_skip_mask(pes, l_pac, a, ma, skip);
-	if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return true;
-	for (int r = 0; r < 4; ++r) {
-		if (skip[r]) continue;
-		int64_t rb, re;
-		int is_rev;
-		if (rescue_window(opt, bns, pes, a, l_ms, r, &rb, &re, &is_rev)) {
-			const RescueRes *res = nullptr;
-			for (const RescueRes &h : have)
-				if (h.key.end == end && h.key.anchor == anchor && h.key.r == r) { res = &h; break; }
-			if (!res) { missing->end = end; missing->anchor = anchor; missing->r = r; return false; }
-			const SwRes &aln = res->res;
-			if (aln.score >= opt->min_seed_len && aln.qb >= 0) {
-				mem_alnreg_t b;
-				memset(&b, 0, sizeof b);
-				b.rid = a->rid;
-				b.is_alt = a->is_alt;
-				b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
-				b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
-				b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
-				b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
-				b.score = aln.score;
-				b.csub = aln.score2;
-				b.secondary = -1;
-				b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
-				ma.push_back(b);
-				size_t i, tmp;
-				for (i = 0; i < ma.size() - 1; ++i)
-					if (ma[i].score < b.score) break;
-				tmp = i;
-				for (i = ma.size() - 1; i > tmp; --i) ma[i] = ma[i - 1];
-				ma[i] = b;
-			}
-			++n;
-		}
-		if (n) ma.resize(sort_dedup_patch(opt, 0, 0, 0, (int)ma.size(), ma.data()));
-	}
-	return true;
-}
-
 /* ------------------------------------------------------------------ the hot path */
 
-
-// A chunk is cut into two (optionally four) sub-batches ("lanes") of whole pairs.  Each lane has its own engine (stream, scratch,
-// resident reads; the index is shared) and runs seeding -> chaining -> extension -> regions, and later rescue -> SAM, on
-// its own; two driver threads walk the lanes so that one lane's host stage overlaps the other lane's device stage.
+// One chunk = one engine (stream, scratch, resident reads; the index is shared): every kernel sees the whole chunk.
 struct Lane { Engine *eng; int r0, n; };
-
-// SAM text of a chunk as blocks of consecutive records (b200_align_chunk: the caller wants one buffer, so the sweep appends
-// the records of a block of pairs to one string instead of malloc()ing seqs[i].sam per read and concatenating afterwards)
-struct SamBlocks { std::vector<std::vector<std::string>> lane; };      // [lane][block], in input order
-
-static std::vector<Lane> make_lanes(int n, int slot, int want_default)
-{
-	// A synchronous mem_process_seqs call runs its chunk as two lanes: enough to overlap one lane's host stage with the
-	// other's device stage while the kernels still see half a chunk per launch.  Chunk jobs (process_seqs_begin) overlap
-	// whole chunks instead and run ONE lane, so every kernel sees the whole chunk (the DP rounds have a latency floor: half
-	// batches cost the extension kernels a third of their efficiency).  B200_LANES / B200_LANE_MIN (reads per lane) override.
-	const int want = getenv("B200_LANES") ? atoi(getenv("B200_LANES")) : want_default;
-	const int lane_min = getenv("B200_LANE_MIN") ? atoi(getenv("B200_LANE_MIN")) : 65536;
-	int k = want >= 4 ? 4 : want >= 2 ? 2 : 1;
-	while (k > 1 && n < k * lane_min) k >>= 1;
-	std::vector<Lane> lanes;
-	int r0 = 0;
-	for (int i = 0; i < k; ++i) {
-		int r1 = i + 1 == k ? n : (int)(((int64_t)n * (i + 1) / k) & ~1ll);
-		lanes.push_back({ engine_lane(slot, i), r0, r1 - r0 });
-		r0 = r1;
-	}
-	return lanes;
-}
 
 // encode the reads of one lane in place, flatten them and make them resident in HBM
 static int64_t stage_lane_reads(const mem_opt_t *opt, const Lane &L, bseq1_t *seqs_all)
@@ -366,6 +254,28 @@ static int64_t stage_lane_reads(const mem_opt_t *opt, const Lane &L, bseq1_t *se
 		}
 	});
 	stage_upload_reads(L.eng, n, off.data(), codes);
+	// names, qualities and comments for the SAM text: gathered into one page-locked buffer at prefix offsets
+	ReadText *rt = (ReadText *)stage_pinned(L.eng, PIN_RTEXT, sizeof(ReadText) * (n + 1));
+	std::vector<int64_t> toff(n + 1);
+	toff[0] = 0;
+	for (int i = 0; i < n; ++i) {
+		const bseq1_t &q = seqs[i];
+		const int64_t nl = q.name ? (int64_t)strlen(q.name) : 0, cl = q.comment ? (int64_t)strlen(q.comment) : 0, ql = q.qual ? q.l_seq : 0;
+		rt[i].name_len = (int32_t)nl; rt[i].comment_len = (int32_t)cl;
+		rt[i].name_off = toff[i]; rt[i].qual_off = q.qual ? toff[i] + nl : -1; rt[i].comment_off = q.comment ? toff[i] + nl + ql : -1;
+		toff[i + 1] = toff[i] + nl + ql + cl;
+	}
+	char *text = (char *)stage_pinned(L.eng, PIN_TEXT, (size_t)toff[n] + 16);
+	parallel_for(nt, n, 4096, [&](int, int64_t b, int64_t e) {
+		for (int64_t i = b; i < e; ++i) {
+			const bseq1_t &q = seqs[i];
+			char *d = text + toff[i];
+			if (rt[i].name_len) memcpy(d, q.name, rt[i].name_len);
+			if (q.qual) memcpy(d + rt[i].name_len, q.qual, q.l_seq);
+			if (rt[i].comment_len) memcpy(d + rt[i].name_len + (q.qual ? q.l_seq : 0), q.comment, rt[i].comment_len);
+		}
+	});
+	stage_upload_text(L.eng, n, rt, text, toff[n]);
 	return off[n];
 }
 
@@ -380,53 +290,40 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 		g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
 		g_slots[slot].busy = true;
 	}
-	int64_t bases = 0;
-	std::vector<Lane> lanes = make_lanes(n, slot, 1);
-	for (const Lane &L : lanes) bases += stage_lane_reads(opt, L, seqs);
+	const Lane L = { engine_lane(slot, 0), 0, n };
+	const int64_t bases = stage_lane_reads(opt, L, seqs);
 	std::lock_guard<std::mutex> lk(g_slot_mu);
 	g_slots[slot].busy = false; g_slots[slot].staged_key = (const void *)seqs; g_slots[slot].staged_n = n; g_slots[slot].staged_bases = bases;
-	g_slots[slot].staged_lanes = (int)lanes.size();
 	g_slot_cv.notify_all();
-}
-
-template <class F>
-static void drive_lanes(std::vector<Lane> &lanes, F body)
-{
-	std::atomic<int> next(0);
-	auto run = [&]() { for (;;) { int k = next.fetch_add(1); if (k >= (int)lanes.size()) break; body(lanes[k]); } };
-	if (lanes.size() > 1) { std::thread other(run); run(); other.join(); }
-	else run();
 }
 
 #define GPU_STAGE(call) do { DeviceTurnGuard gpu_lk(ticket); call; } while (0)
 
+// where the SAM text of the chunk goes: seqs[i].sam (mem_process_seqs' contract: one malloc()ed string per read) or ONE buffer
+// from the recycling pool of b200_big_alloc (b200_align_chunk / _fastq: the caller wants the chunk's text, not 667 k strings)
+struct SamDest { bool one_buffer = false; char *sam = nullptr; int64_t sam_len = 0; };
+
+extern "C" void *b200_big_alloc(size_t bytes);
+
 static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
-                              int64_t n_processed_all, int n_all, bseq1_t *seqs_all, const mem_pestat_t *pes0,
-                              int slot, int want_lanes, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamBlocks *sam_blocks,
-                              uint64_t ticket)
+                              int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
+                              int slot, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamDest *dest, uint64_t ticket)
 {
 	engine_for(bwt, bns, pac);
-	std::vector<Lane> lanes = make_lanes(n_all, slot, want_lanes);
-	if (sam_blocks) sam_blocks->lane.resize(lanes.size());
-	if (staged && (int)lanes.size() != want_lanes) { fprintf(stderr, "[mpibwa_b200] staged reads do not match the lane split of the call\n"); abort(); }
-	for (const Lane &L : lanes) memset(static_cast<b200_stats_t *>(&engine_stats(L.eng)), 0, sizeof(b200_stats_t));
-	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
-	const double t_start = now_ms();
-	const bool pe = (opt->flag & MEM_F_PE) != 0;
-	const int64_t l_pac = bns->l_pac;
-	std::vector<RegVec> regs_all(n_all);
-
-	// ================= phase 1, per lane: reads -> seeds -> chains -> regions
-	drive_lanes(lanes, [&](Lane &L) {
+	const Lane L = { engine_lane(slot, 0), 0, n };
 	Engine *eng = L.eng;
 	Stats &st = engine_stats(eng);
-	const int n = L.n;
-	bseq1_t *seqs = seqs_all + L.r0;
-	RegVec *regs = regs_all.data() + L.r0;
+	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
+	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
+	const double t_start = now_ms();
+	const int64_t l_pac = bns->l_pac;
 	double t0 = now_ms(), t1;
-	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload - unless b200_stage_reads() already did
-	if (!staged) st.n_bases = stage_lane_reads(opt, L, seqs_all);       // (own stream and buffers: no need to hold the device)
+
+	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload reads and their text - unless b200_stage_reads() already did
+	if (!staged) st.n_bases = stage_lane_reads(opt, L, seqs);            // (own stream and buffers: no need to hold the device)
+	else st.n_bases = staged_bases;
 	st.n_reads = n;
+	t1 = now_ms(); st.ms_upload = t1 - t0; t0 = t1;
 
 	// ---- chaining on the device unless a read is long enough for mem_flt_chained_seeds (B200_CHAIN=host forces the host path)
 	bool dev_chain = !(getenv("B200_CHAIN") && !strcmp(getenv("B200_CHAIN"), "host"));
@@ -461,7 +358,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		}
 	}
 	if (!dev_chain || chain_check) {
-	// ---- chaining + chain filtering on host threads
+	// ---- chaining + chain filtering on host threads (reads of >= ~730 bases: mem_flt_chained_seeds applies; and the checking mode)
 	std::vector<std::vector<HChain>> chains(n);
 	std::vector<int32_t> n_chain_of(n), n_seed_of(n);
 	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
@@ -473,7 +370,6 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 			n_chain_of[i] = (int32_t)chains[i].size(); n_seed_of[i] = ns;
 		}
 	});
-	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] build+filter %.1f ms\n", now_ms() - t0);
 
 	// ---- mem_flt_chained_seeds (reference src/bwamem.c:571-615): only reads of >= ~730 bp get here
 	{
@@ -581,7 +477,6 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		});
 		st.n_chains = nc;
 	}
-	if (getenv("B200_DEBUG")) fprintf(stderr, "[chain] +flatten %.1f ms\n", now_ms() - t0);
 	chains.clear(); chains.shrink_to_fit();
 	xin.on_device = false;
 	if (chain_check) {
@@ -600,269 +495,41 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	}
 	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
 
-	// ---- chain2aln / ksw_extend2 on the device
-	ExtRegs xr;
-	GPU_STAGE(stage_extend(eng, make_ext_opt(opt), xin, xr));
-	const DReg *dregs = xr.regs;
-	const int64_t *reg_off = xr.reg_off;
+	// ---- chain2aln / ksw_extend2 on the device; the regions stay there
+	GPU_STAGE(stage_extend(eng, make_ext_opt(opt), xin));
 	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
 
-	// ---- mem_sort_dedup_patch + ALT marking (reference src/bwamem.c:1073-1085)
-	parallel_for(nt, n, 512, [&](int, int64_t b, int64_t e) {
-		for (int64_t i = b; i < e; ++i) {
-			int nr = (int)(reg_off[i + 1] - reg_off[i]);
-			if (nr == 0) continue;
-			int64_t base = reg_off[i];
-			RegVec &rv = regs[i];
-			rv.resize(nr);
-			for (int k = 0; k < nr; ++k) {
-				const DReg &d = dregs[base + k];
-				mem_alnreg_t &a = rv[k];
-				memset(&a, 0, sizeof a);
-				a.rb = d.rb; a.re = d.re; a.qb = d.qb; a.qe = d.qe; a.rid = d.rid; a.score = d.score; a.truesc = d.truesc;
-				a.w = d.w; a.seedcov = d.seedcov; a.seedlen0 = d.seedlen0; a.frac_rep = d.frac_rep;
-			}
-			rv.resize(sort_dedup_patch(opt, bns, pac, (uint8_t *)seqs[i].seq, nr, rv.data()));
-			for (auto &p : rv)
-				if (p.rid >= 0 && bns->anns[p.rid].is_alt) p.is_alt = 1;
-		}
-	});
-	t1 = now_ms(); st.ms_regs_host = t1 - t0; t0 = t1;
-	});
-
-	// ================= insert-size statistics: the one chunk-global reduction (reference src/bwamem.c:1226-1229)
-	mem_pestat_t pes[4];
-	const double t_pes = now_ms();
-	if (pe) {
-		if (pes0) memcpy(pes, pes0, 4 * sizeof(mem_pestat_t));
-		else pestat(opt, l_pac, n_all, regs_all.data(), pes);
-	}
-	const double ms_pestat = now_ms() - t_pes;
-
-	// ================= phase 2, per lane: mate rescue -> pairing, mapQ, CIGAR, SAM text
-	drive_lanes(lanes, [&](Lane &L) {
-	Engine *eng = L.eng;
-	Stats &st = engine_stats(eng);
-	const int n = L.n;
-	bseq1_t *seqs = seqs_all + L.r0;
-	RegVec *regs = regs_all.data() + L.r0;
-	const int64_t n_processed = n_processed_all + L.r0;
-	double t0 = now_ms(), t1;
-
-	// ---- mate rescue: SW jobs on the device, then the sequential insert/skip logic replayed per pair
-	if (pe && !(opt->flag & MEM_F_NO_RESCUE)) {
-		const int n_pairs = n >> 1;
-		const int xtra_base = KSW_XSUBO | KSW_XSTART | (opt->min_seed_len * opt->a);
-		SwOpt so = make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins);
-		std::vector<int> pending;
-		std::vector<std::vector<RescueKey>> want(n_pairs);           // jobs to run this round, by pair
-		std::unordered_map<int, std::vector<RescueRes>> known;       // results carried over by deferred pairs
-		// round 0: every (anchor, orientation) not ruled out by the mate's pre-rescue regions
-		parallel_for(nt, n_pairs, 1024, [&](int, int64_t b, int64_t e) {
-			for (int64_t p = b; p < e; ++p) {
-				for (int i = 0; i < 2; ++i) {
-					const RegVec &ai = regs[p << 1 | i], &ma = regs[p << 1 | !i];
-					int l_ms = seqs[p << 1 | !i].l_seq;
-					int nb = 0;
-					for (size_t j = 0; j < ai.size() && nb < opt->max_matesw; ++j) {
-						if (ai[j].score < ai[0].score - opt->pen_unpaired) continue;
-						int skip[4];
-						rescue_skip_mask(pes, l_pac, &ai[j], ma, skip);
-						for (int r = 0; r < 4; ++r) {
-							int64_t rb, re; int is_rev;
-							if (!skip[r] && rescue_window(opt, bns, pes, &ai[j], l_ms, r, &rb, &re, &is_rev))
-								want[p].push_back({i, nb, r});
-						}
-						++nb;
-					}
-				}
+	// ---- everything else of mem_process_seqs (reference src/bwamem.c:1073-1085, 1187-1203, 1226-1229): de-duplication,
+	// insert-size statistics, mate rescue, primary marking, pairing, mapQ, CIGARs, NM/MD and the SAM text - finish_stage.h
+	FinishArgs fa;
+	fa.opt = opt; fa.pes0 = (opt->flag & MEM_F_PE) ? pes0 : nullptr; fa.n_processed = n_processed; fa.rg_id = bwa_rg_id;
+	fa.want_offsets = !dest->one_buffer;
+	fa.alloc = dest->one_buffer ? b200_big_alloc : nullptr;
+	GPU_STAGE(stage_finish(eng, fa));
+	SamChunk sc;
+	stage_fetch_sam(eng, fa, sc);           // (D2H on the engine's own stream: the next chunk's kernels run meanwhile)
+	t0 = now_ms();
+	if (dest->one_buffer) { dest->sam = sc.sam; dest->sam_len = sc.bytes; }
+	else {
+		// mem_process_seqs' contract: one malloc()ed, NUL-terminated string per read (the host free()s them)
+		parallel_for(nt, n, 2048, [&](int, int64_t b, int64_t e) {
+			for (int64_t i = b; i < e; ++i) {
+				const int64_t l = sc.sam_off[i + 1] - sc.sam_off[i];
+				char *p = (char *)malloc((size_t)l + 1);
+				memcpy(p, sc.sam + sc.sam_off[i], (size_t)l);
+				p[l] = 0;
+				seqs[i].sam = p;
 			}
 		});
-		// a pair none of whose anchors asks for an alignment cannot change in mem_matesw: only the others are replayed
-		for (int i = 0; i < n_pairs; ++i) if (!want[i].empty()) pending.push_back(i);
-		while (!pending.empty()) {
-			std::vector<SwJob> jobs;
-			std::vector<RescueKey> job_key;
-			std::vector<int64_t> first(pending.size() + 1, 0);
-			for (size_t x = 0; x < pending.size(); ++x) {
-				int p = pending[x];
-				for (const RescueKey &k : want[p]) {
-					const RegVec &ai = regs[p << 1 | k.end];
-					int nb = -1; const mem_alnreg_t *a = nullptr;
-					for (size_t j = 0; j < ai.size(); ++j) {
-						if (ai[j].score < ai[0].score - opt->pen_unpaired) continue;
-						if (++nb == k.anchor) { a = &ai[j]; break; }
-					}
-					int l_ms = seqs[p << 1 | !k.end].l_seq;
-					int64_t rb, re; int is_rev;
-					rescue_window(opt, bns, pes, a, l_ms, k.r, &rb, &re, &is_rev);
-					SwJob j;
-					j.rb = rb; j.tlen = (int)(re - rb); j.read = p << 1 | !k.end; j.is_rev = is_rev;
-					j.xtra = xtra_base | (l_ms * opt->a < 250 ? KSW_XBYTE : 0);
-					j.q_beg = 0; j.q_len = l_ms;
-					jobs.push_back(j); job_key.push_back(k);
-				}
-				first[x + 1] = (int64_t)jobs.size();
-			}
-			std::vector<SwRes> res;
-			if (!jobs.empty()) GPU_STAGE(stage_sw(eng, so, jobs, res));
-			std::vector<char> done(pending.size(), 0);
-			std::vector<RescueKey> miss(pending.size());
-			std::vector<std::vector<RescueRes>> carry(pending.size());
-			parallel_for(nt, (int64_t)pending.size(), 1024, [&](int, int64_t b, int64_t e) {
-				std::vector<RescueRes> have;
-				for (int64_t x = b; x < e; ++x) {
-					int p = pending[x];
-					have.clear();
-					auto it = known.find(p);            // read-only during this loop
-					if (it != known.end()) have = it->second;
-					for (int64_t y = first[x]; y < first[x + 1]; ++y) have.push_back({job_key[y], jobs[y].rb, res[y]});
-					RegVec a[2] = { regs[p << 1], regs[p << 1 | 1] };
-					RegVec anchors[2];
-					for (int i = 0; i < 2; ++i)
-						for (size_t j = 0; j < a[i].size(); ++j)
-							if (a[i][j].score >= a[i][0].score - opt->pen_unpaired) anchors[i].push_back(a[i][j]);
-					bool ok = true;
-					for (int i = 0; i < 2 && ok; ++i)
-						for (size_t j = 0; j < anchors[i].size() && (int)j < opt->max_matesw && ok; ++j)
-							ok = rescue_replay_anchor(opt, bns, pes, &anchors[i][j], seqs[p << 1 | !i].l_seq, a[!i], i, (int)j, have, &miss[x]);
-					if (ok) { regs[p << 1].swap(a[0]); regs[p << 1 | 1].swap(a[1]); done[x] = 1; }
-					else carry[x].swap(have);
-				}
-			});
-			std::vector<int> again;
-			for (size_t x = 0; x < pending.size(); ++x) {
-				if (done[x]) continue;
-				int p = pending[x];
-				known[p].swap(carry[x]);
-				want[p].assign(1, miss[x]);
-				again.push_back(p);
-			}
-			pending.swap(again);
-		}
 	}
-	t1 = now_ms(); st.ms_rescue = t1 - t0; t0 = t1;
-
-	// ---- primary marking, pairing, mapQ, CIGAR and SAM text (reference worker2, src/bwamem.c:1187-1203).
-	// First every region that mem_reg2aln may be asked about is queued for the CIGAR stage on the device (a function of
-	// the region alone: no dry run of the pairing logic), then the sweep over the pairs looks its alignments up.
-	{
-		const int64_t n_units = pe ? n >> 1 : n;
-		const int per = pe ? 2 : 1;
-		auto run_unit = [&](int64_t u, RegVec *r) {
-			if (pe) sam_pe_finish(opt, bns, pac, pes, (uint64_t)((n_processed >> 1) + u), &seqs[u << 1], r);
-			else {
-				mark_primary_se(opt, (int)r[0].size(), r[0].data(), n_processed + u);
-				if (opt->flag & MEM_F_PRIMARY5) reorder_primary5(opt->T, r[0]);
-				reg2sam(opt, bns, pac, &seqs[u], r[0], 0, 0);
-			}
-		};
-		struct UnitJobs { int32_t tid, start, count; };
-		std::vector<UnitJobs> uj(n_units);
-		std::vector<std::vector<GlobalJob>> tjobs(nt);
-		parallel_for(nt, n_units, 1024, [&](int tid, int64_t b, int64_t e) {
-			std::vector<GlobalJob> &out = tjobs[tid];
-			for (int64_t u = b; u < e; ++u) {
-				const int32_t start = (int32_t)out.size();
-				for (int k = 0; k < per; ++k) {
-					const RegVec &rv = regs[u * per + k];
-					// a region below the output threshold, or far below the read's best hit (never a primary, never in XA), is
-					// not worth a device job; should the sweep ask for it after all, reg2aln aligns it itself
-					int best = 0;
-					for (const mem_alnreg_t &a : rv) best = a.score > best ? a.score : best;
-					for (const mem_alnreg_t &a : rv) {
-						if (a.score < opt->T || a.score < best * opt->XA_drop_ratio - opt->pen_unpaired) continue;
-						GlobalJob j;
-						if (reg_global_job(opt, bns, &a, (int)(u * per + k), &j)) out.push_back(j);
-					}
-				}
-				uj[u] = { tid, start, (int32_t)out.size() - start };
-			}
-		});
-		std::vector<int64_t> tbase(nt + 1, 0);
-		for (int t = 0; t < nt; ++t) tbase[t + 1] = tbase[t] + (int64_t)tjobs[t].size();
-		std::vector<GlobalJob> gjobs(tbase[nt]);
-		GlobalOpt go;
-		go.o_del = opt->o_del; go.e_del = opt->e_del; go.o_ins = opt->o_ins; go.e_ins = opt->e_ins; go.a = opt->a; go.w_max = opt->w << 2;
-		memcpy(go.mat, opt->mat, 25);
-		int64_t zb = 0;
-		for (int t = 0; t < nt; ++t)
-			for (size_t k = 0; k < tjobs[t].size(); ++k) {
-				GlobalJob j = tjobs[t][k];
-				j.zoff = zb;
-				zb += (global_z_need(go, j.qe - j.qb, (int)(j.re - j.rb), j.w2, &j.wmax) + 15) & ~(int64_t)15;
-				gjobs[tbase[t] + (int64_t)k] = j;
-			}
-		tjobs.clear();
-		double tg = now_ms();
-		st.ms_sam_plan = tg - t0;
-		const GlobalRes *gres = nullptr;
-		if (!gjobs.empty()) GPU_STAGE(gres = stage_global(eng, go, gjobs, zb));
-		st.ms_global = now_ms() - tg;
-		std::atomic<int64_t> n_host_dp(0);
-		const int64_t sweep_grain = 256;
-		std::vector<std::string> *blocks = nullptr;
-		if (sam_blocks) {
-			blocks = &sam_blocks->lane[&L - lanes.data()];
-			blocks->resize((size_t)((n_units + sweep_grain - 1) / sweep_grain));
-			for (std::string &b : *blocks) b.clear();                          // (keeps the capacity)
-		}
-		parallel_for(nt, n_units, sweep_grain, [&](int, int64_t b, int64_t e) {
-			AlignCtx &cx = align_ctx();
-			cx.mode = AlignCtx::LOOKUP; cx.n_host_dp = 0;
-			if (blocks) { cx.sink = &(*blocks)[(size_t)(b / sweep_grain)]; cx.sink->reserve((size_t)(e - b) * per * 448); }
-			// a region's reference window is a random 40-byte read of the 2-bit reference (a DRAM miss per region, the largest
-			// single cost of the sweep once the arithmetic was trimmed): touch the windows of a pair a few pairs ahead
-			auto prefetch_unit = [&](int64_t v) {
-				for (int k = 0; k < per; ++k) {
-					const RegVec &rv = regs[v * per + k];
-					for (size_t x = 0; x < rv.size() && x < 3; ++x) {
-						const int64_t p = rv[x].rb < l_pac ? rv[x].rb : (l_pac << 1) - rv[x].re;
-						if (p >= 0 && p < l_pac) { __builtin_prefetch(pac + (p >> 2)); __builtin_prefetch(pac + (p >> 2) + 64); }
-					}
-				}
-			};
-			for (int64_t v = b; v < e && v < b + 4; ++v) prefetch_unit(v);
-			for (int64_t u = b; u < e; ++u) {
-				if (u + 4 < e) prefetch_unit(u + 4);
-				const int64_t first = tbase[uj[u].tid] + uj[u].start;
-				cx.jobs = gjobs.data() + first; cx.res = gres ? gres + first : nullptr; cx.n_jobs = uj[u].count;
-				for (int k = 0; k < per; ++k) { cx.seq_ptr[k] = seqs[u * per + k].seq; cx.read_idx[k] = (int)(u * per + k); }
-				run_unit(u, &regs[u * per]);
-			}
-			cx.mode = AlignCtx::DIRECT; cx.jobs = nullptr; cx.res = nullptr; cx.n_jobs = 0; cx.sink = nullptr;
-			n_host_dp += cx.n_host_dp;
-			host_prof_flush();
-		});
-		st.n_global_host = n_host_dp;
-	}
-	t1 = now_ms(); st.ms_sam_host = t1 - t0;
-	});
-
-	// ================= merge the per-lane counters into the primary engine's record (b200_get_stats reads it)
-	Stats &st = engine_stats(lanes[0].eng);
-	for (size_t k = 1; k < lanes.size(); ++k) {
-		const b200_stats_t &o = engine_stats(lanes[k].eng);
-		st.ms_seed += o.ms_seed; st.ms_sa += o.ms_sa; st.ms_chain_host += o.ms_chain_host; st.ms_extend += o.ms_extend;
-		st.ms_regs_host += o.ms_regs_host; st.ms_rescue += o.ms_rescue; st.ms_sam_host += o.ms_sam_host;
-		st.ms_k_smem += o.ms_k_smem; st.ms_k_sa += o.ms_k_sa; st.ms_k_extend += o.ms_k_extend; st.ms_k_sw += o.ms_k_sw; st.ms_k_global += o.ms_k_global;
-		st.n_reads += o.n_reads; st.n_bases += o.n_bases; st.n_intv += o.n_intv; st.n_seeds += o.n_seeds; st.n_chains += o.n_chains;
-		st.n_extend_jobs += o.n_extend_jobs; st.extend_cells += o.extend_cells; st.n_sw_jobs += o.n_sw_jobs; st.sw_cells += o.sw_cells;
-		st.n_global_jobs += o.n_global_jobs; st.global_cells += o.global_cells;
-		st.fm_occ_blocks += o.fm_occ_blocks; st.fm_sa_steps += o.fm_sa_steps; st.fm_sa_lookups += o.fm_sa_lookups;
-		st.n_launches += o.n_launches; st.h2d_bytes += o.h2d_bytes; st.d2h_bytes += o.d2h_bytes;
-		st.ms_k_extend_dp += o.ms_k_extend_dp; st.n_extend_rounds += o.n_extend_rounds;
-		st.ms_sam_plan += o.ms_sam_plan; st.ms_global += o.ms_global; st.ms_k_chain += o.ms_k_chain; st.n_global_host += o.n_global_host;
-	}
-	st.ms_rescue += ms_pestat;
-	if (staged) st.n_bases = staged_bases;
+	st.ms_deliver += now_ms() - t0;
 	st.ms_total = now_ms() - t_start;
 	if (bwa_verbose >= 3)
-		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s, %d lane%s; stage walls summed over lanes: seed %.0f ms, chain %.0f, extend %.0f, regs %.0f, rescue %.0f, sam %.0f [plan %.0f, cigar stage %.0f])\n",
-		        "mem_process_seqs", n_all, st.ms_total * 1e-3, engine_kind(), (int)lanes.size(), lanes.size() > 1 ? "s" : "", st.ms_seed, st.ms_chain_host,
-		        st.ms_extend, st.ms_regs_host, st.ms_rescue, st.ms_sam_host, st.ms_sam_plan, st.ms_global);
+		fprintf(stderr, "[M::%s] Processed %d reads in %.3f real sec (%s; stage walls: upload %.0f ms, seed %.0f, chain %.0f, extend %.0f, dedup %.0f, rescue %.0f, pairing %.0f, cigar %.0f, text %.0f, deliver %.0f; %lld reads re-patched with a DP, %lld extra rescue rounds, %lld of %lld CIGAR jobs rerun wider)\n",
+		        "mem_process_seqs", n, st.ms_total * 1e-3, engine_kind(), st.ms_upload, st.ms_seed, st.ms_chain_host,
+		        st.ms_extend, st.ms_regs_host, st.ms_rescue, st.ms_sam_plan, st.ms_global, st.ms_sam_host, st.ms_deliver,
+		        (long long)st.n_patch_reads, (long long)st.n_rescue_rounds, (long long)st.n_global_rerun, (long long)st.n_global_jobs);
 	if (stats_out) *stats_out = st;
-	host_prof_report("SAM sweep");
 	std::lock_guard<std::mutex> lk(g_slot_mu);
 	g_last_stats = st;
 }
@@ -872,39 +539,20 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 struct SeqJob {
 	std::thread th;
 	b200_stats_t stats;
-	SamBlocks *sam = nullptr;        // the slot's block buffers while the job holds the slot
+	SamDest dest;
 };
 
-// block buffers live with the slot and keep their capacity from chunk to chunk (no 200 KB allocations per block per chunk)
-static SamBlocks g_slot_sam[N_SLOTS];
-
-extern "C" void *b200_big_alloc(size_t bytes);
-
-// concatenates the SAM blocks of a finished job into one malloc()ed, NUL-terminated buffer (parallel copy); returns its length
-int64_t job_take_sam(SeqJob *j, int n_threads, char **out)
+// the chunk's SAM text of a finished one-buffer job (from b200_big_alloc: release with b200_free)
+int64_t job_take_sam(SeqJob *j, char **out)
 {
-	std::vector<const std::string *> parts;
-	for (auto &ln : j->sam->lane) for (auto &b : ln) parts.push_back(&b);
-	std::vector<size_t> at(parts.size() + 1, 0);
-	for (size_t k = 0; k < parts.size(); ++k) at[k + 1] = at[k] + parts[k]->size();
-	char *buf = (char *)b200_big_alloc(at.back() + 1);      // recycled through b200_free()
-#if defined(MADV_HUGEPAGE)
-	if (at.back() >= ((size_t)8 << 20)) {       // hundreds of MB touched once: ask for huge pages instead of 65 k page faults
-		const uintptr_t lo = ((uintptr_t)buf + ((size_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1), hi = ((uintptr_t)buf + at.back()) & ~(((uintptr_t)2 << 20) - 1);
-		if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
-	}
-#endif
-	parallel_for(n_threads, (int64_t)parts.size(), 16, [&](int, int64_t b, int64_t e) {
-		for (int64_t k = b; k < e; ++k) memcpy(buf + at[k], parts[k]->data(), parts[k]->size());
-	});
-	buf[at.back()] = 0;
-	*out = buf;
-	return (int64_t)at.back();
+	*out = j->dest.sam;
+	j->dest.sam = nullptr;
+	return j->dest.sam_len;
 }
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
-                           void (*after)(void *, SeqJob *), void *arg, int want_lanes, bool sam_as_blocks,
+                           void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
                            void (*before)(void *, bseq1_t **, int *))
 {
 	engine_for(bwt, bns, pac);
@@ -917,7 +565,7 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	{
 		std::unique_lock<std::mutex> lk(g_slot_mu);
 		for (int k = 0; k < N_SLOTS && seqs; ++k)
-			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; want_lanes = g_slots[k].staged_lanes; }
+			if (!g_slots[k].busy && g_slots[k].staged_key == (const void *)seqs && g_slots[k].staged_n == n) { slot = k; staged = true; staged_bases = g_slots[k].staged_bases; }
 		if (slot < 0)
 			g_slot_cv.wait(lk, [&] { for (int k = 0; k < N_SLOTS; ++k) if (!g_slots[k].busy && !g_slots[k].staged_key) { slot = k; return true; } return false; });
 		g_slots[slot].busy = true; g_slots[slot].staged_key = nullptr;
@@ -935,9 +583,9 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 			++g_running; ++g_ticket_serving;
 			g_slot_cv.notify_all();
 		}
-		j->sam = sam_as_blocks ? &g_slot_sam[slot] : nullptr;
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n_, seqs_, pes, slot, want_lanes, staged, staged_bases, &j->stats, j->sam, ticket);
-		if (after) after(arg, j);                // (SAM concatenation out of the slot's block buffers: host work that overlaps the next chunk)
+		j->dest.one_buffer = one_buffer;
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n_, seqs_, pes, slot, staged, staged_bases, &j->stats, &j->dest, ticket);
+		if (after) after(arg, j);
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
 			--g_running; g_slots[slot].busy = false;
@@ -957,7 +605,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, 2, false, nullptr), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr), nullptr);
 }
 
 } // namespace b200

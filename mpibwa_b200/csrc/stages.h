@@ -13,20 +13,12 @@
 #include "sw_kernels.h"
 #include "global_kernels.h"
 #include "chain_kernels.h"
+#include "finish_kernels.h"
 
 namespace b200 {
 
 // result of stage_seed: arrays owned by the engine (page-locked on the CUDA engine), valid until the next stage_seed call
 struct SeedOut { const int64_t *seed_off; const SeedRec *seeds; const int32_t *l_rep; int64_t n_seeds; };
-
-struct SwJob {
-	int64_t rb;             // first reference position of the target window (forward+reverse coordinate)
-	int32_t tlen;
-	int32_t read;           // index of the query read in the current batch
-	int32_t is_rev;         // use the reverse complement of the read as the query
-	int32_t xtra;
-	int32_t q_beg, q_len;   // sub-range of the read used as query (whole read for mate rescue)
-};
 
 struct Stats : b200_stats_t {};
 
@@ -52,14 +44,35 @@ void stage_seed(Engine *e, const SeedOpt &so, SeedOut &out, bool keep_on_device 
 // page-locked host scratch owned by the engine (a handful of numbered slots); a slot's contents stay valid until the
 // same slot is requested again.  The pipeline assembles stage inputs in place there and reads stage outputs from there.
 void *stage_pinned(Engine *e, int slot, size_t bytes);
-enum { PIN_CHAIN_OFF = 0, PIN_CHAINS = 1, PIN_DSEEDS = 2, PIN_SRT = 3, PIN_REGS = 4, PIN_REG_OFF = 5, PIN_N_SLOTS = 8 };
+enum { PIN_CHAIN_OFF = 0, PIN_CHAINS = 1, PIN_DSEEDS = 2, PIN_SRT = 3, PIN_REGS = 4, PIN_REG_OFF = 5, PIN_RTEXT = 6, PIN_TEXT = 7, PIN_N_SLOTS = 8 };
 
-// extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r come back compacted
-// as regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them (arrays in the PIN_REGS / PIN_REG_OFF slots).
-// (on_device: the four arrays were left in HBM by stage_chain(); the pointers are then unused)
+// extension: chains of read r are chains[chain_off[r] .. chain_off[r+1]); the regions of read r are left in HBM, compacted as
+// regs[reg_off[r] .. reg_off[r+1]) in the order mem_chain2aln appends them, for stage_finish().
+// (on_device: the four input arrays were left in HBM by stage_chain(); the pointers are then unused)
 struct ExtIn { int n_reads; const int32_t *chain_off; const DChain *chains; int64_t n_chains; const DSeed *seeds; int64_t n_seeds; const int32_t *srt; bool on_device = false; };
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in);
+// host copy of the regions of the last stage_extend call (the single-job mem_chain2aln wrapper; PIN_REGS / PIN_REG_OFF slots)
 struct ExtRegs { const DReg *regs; const int64_t *reg_off; };
-void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out);
+void stage_extend_download(Engine *e, ExtRegs &out);
+
+// names, qualities and comments of the batch's reads (for the SAM text): rtext[r] holds offsets into text[0..bytes)
+void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes);
+
+// Everything after extension (finish_stage.h): de-duplication, insert-size statistics, mate rescue, pairing, CIGARs, SAM text.
+// The text comes back NUL-terminated in page-locked host memory owned by the engine (valid until the next call on the same
+// engine), or in the buffer a.alloc returns; sam_off[r] .. sam_off[r+1] are the records of read r.
+struct FinishArgs {
+	const mem_opt_t *opt; const mem_pestat_t *pes0; int64_t n_processed; const char *rg_id;
+	bool want_offsets;              // also bring the per-read offsets back
+	void *(*alloc)(size_t bytes);   // when set: called once with the size of the text (+1); the text is copied there instead
+};
+struct SamChunk { char *sam; const int64_t *sam_off; int64_t bytes; };
+void stage_finish(Engine *e, const FinishArgs &a);                        // the kernels; leaves the text in HBM
+void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out);      // brings it to the host (copy engine only)
+
+// page-locked host memory for buffers the library hands to its caller (b200_big_alloc)
+void *stage_host_alloc(size_t bytes);
+void  stage_host_free(void *p);
 
 // kernel-isolated replay of every ksw_extend2 job the last stage_extend call recorded (B200_EXT_RECORD set): one batch, DP kernels only
 double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t *n_jobs);
@@ -72,10 +85,9 @@ void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool download = false
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);
 
-// CIGAR stage: banded global alignment + traceback of regions of the resident reads (jobs carry zoff/slot filled by the caller)
-// Returns the results in job order, in memory owned by the engine (page-locked on the CUDA engine) that stays valid until
-// the next stage_global call on the same engine.
-const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes);
+// ksw_global2 for caller-provided byte buffers (the single-job C wrapper): score and CIGAR of one banded global alignment
+int stage_global_bytes(Engine *e, const GlobalOpt &go, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int w,
+                       std::vector<uint32_t> *cigar);
 
 // generic batches over caller-provided byte buffers (C-ABI b200_*_batch and the single-job wrappers)
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,

@@ -17,11 +17,15 @@
 #include "smem_kernel.cuh"
 #include "smem_sweeps.cuh"
 #include "sw_warp_kernel.cuh"
+#include "finish_stage.h"
 #include <cuda_runtime.h>
 #include <cub/cub.cuh>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <cmath>
+#include <chrono>
 #include <algorithm>
 
 namespace b200 {
@@ -92,8 +96,15 @@ public:
 	DevBuf b_chain_off, b_chains, b_dseeds, b_srt, b_regs, b_nregs, b_eh;
 	DevBuf b_jobs, b_res, b_h, b_e, b_b, b_q, b_t;
 	DevBuf b_xstate, b_xjobs, b_xact0, b_xact1, b_xkey, b_xkey2, b_xord, b_xctr, b_xout;
-	PinBuf h_seeds, h_seed_off, h_lrep, h_codes, h_gres, h_slot[PIN_N_SLOTS];
-	DevBuf b_gjobs, b_gres, b_grow, b_gz;
+	PinBuf h_seeds, h_seed_off, h_lrep, h_codes, h_slot[PIN_N_SLOTS];
+	DevBuf b_grow;
+	// finish stages (finish_stage.h): scratch by FinBuf id, the read text, contig names, the log table, the SAM text on the host
+	DevBuf fb[FB_N], d_rtext, d_text;
+	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr;
+	int n_log = 0;
+	PinBuf h_sam, h_sam_off;
+	FinishOut fin_out;
+	double ms_task = 0, ms_task_text = 0;       // CUDA-event time of the finish-stage kernels of the current call
 	std::vector<cudaEvent_t> ev_pool;
 	static const int N_SIDE = 8;
 	cudaStream_t side[N_SIDE];
@@ -200,6 +211,28 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < bns->n_seqs; ++i) alt[i] = bns->anns[i].is_alt ? 1 : 0;
 	CK(cudaMalloc(&e->d_ctg_alt, alt.size()));
 	CK(cudaMemcpy(e->d_ctg_alt, alt.data(), alt.size(), cudaMemcpyHostToDevice));
+	{	// contig names and annotations (SAM text), back to back with offset tables
+		std::vector<int64_t> no(bns->n_seqs + 1, 0), ao(bns->n_seqs + 1, 0);
+		std::string names, annos;
+		for (int i = 0; i < bns->n_seqs; ++i) {
+			names += bns->anns[i].name; no[i + 1] = (int64_t)names.size();
+			if (bns->anns[i].anno) annos += bns->anns[i].anno;
+			ao[i + 1] = (int64_t)annos.size();
+		}
+		CK(cudaMalloc(&e->d_ctg_name_off, no.size() * 8)); CK(cudaMalloc(&e->d_ctg_names, names.size() + 8));
+		CK(cudaMalloc(&e->d_ctg_anno_off, ao.size() * 8)); CK(cudaMalloc(&e->d_ctg_annos, annos.size() + 8));
+		CK(cudaMemcpy(e->d_ctg_name_off, no.data(), no.size() * 8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(e->d_ctg_names, names.data(), names.size(), cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(e->d_ctg_anno_off, ao.data(), ao.size() * 8, cudaMemcpyHostToDevice));
+		CK(cudaMemcpy(e->d_ctg_annos, annos.data(), annos.size(), cudaMemcpyHostToDevice));
+	}
+	{	// log(i) by glibc for every integer the mapQ formulas can ask for (finish_kernels.h: bit-exactness)
+		e->n_log = 1 << 20;
+		std::vector<double> lt(e->n_log);
+		for (int i = 0; i < e->n_log; ++i) lt[i] = log((double)i);
+		CK(cudaMalloc(&e->d_logtab, sizeof(double) * e->n_log));
+		CK(cudaMemcpy(e->d_logtab, lt.data(), sizeof(double) * e->n_log, cudaMemcpyHostToDevice));
+	}
 	FmView &fm = e->fm;
 	fm.occ = (const uint32_t *)e->d_bwt; fm.sa = (const uint64_t *)e->d_sa;
 	fm.primary = bwt->primary;
@@ -253,6 +286,8 @@ Engine *engine_clone(Engine *base)
 	engine_make_streams(e);
 	e->owns_index = false;
 	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len; e->d_ctg_alt = base->d_ctg_alt;
+	e->d_ctg_name_off = base->d_ctg_name_off; e->d_ctg_names = base->d_ctg_names; e->d_ctg_anno_off = base->d_ctg_anno_off; e->d_ctg_annos = base->d_ctg_annos;
+	e->d_logtab = base->d_logtab; e->n_log = base->n_log;
 	e->bwt_bytes = base->bwt_bytes;
 	e->fm = base->fm;
 	engine_set_l2_window(e);
@@ -268,12 +303,17 @@ void engine_destroy(Engine *e)
 		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
 		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
 	for (DevBuf *b : bufs) b->release();
-	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release(); e->h_gres.release();
+	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release();
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
-	e->b_gjobs.release(); e->b_gres.release(); e->b_grow.release(); e->b_gz.release();
+	e->b_grow.release();
+	for (int i = 0; i < FB_N; ++i) e->fb[i].release();
+	e->d_rtext.release(); e->d_text.release(); e->h_sam.release(); e->h_sam_off.release();
 	e->b_strips.release(); e->b_nfirst.release(); e->b_nsweeps.release();
 	e->b_xrec.release(); e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
-	if (e->owns_index) { cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt); }
+	if (e->owns_index) {
+		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
+		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab);
+	}
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork);
 	for (int i = 0; i < Engine::N_SIDE; ++i) { cudaStreamDestroy(e->side[i]); cudaEventDestroy(e->ev_join[i]); }
@@ -711,14 +751,12 @@ static void ext_set_attrs(Engine *e)
 	e->ext_attr_set = true;
 }
 
-void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in)
 {
 	CK(cudaSetDevice(e->device));
 	const int n = in.n_reads;
 	if (n != e->n_reads) die("stage_extend: chain table does not match the uploaded reads");
-	int64_t *reg_off = (int64_t *)e->h_slot[PIN_REG_OFF].need(sizeof(int64_t) * (n + 2));
-	out.regs = nullptr; out.reg_off = reg_off;
-	if (n == 0) { reg_off[0] = 0; return; }
+	if (n == 0) { CK(cudaMemsetAsync(e->b_soff.as<int64_t>(2), 0, sizeof(int64_t) * 2, e->stream)); return; }
 	e->zero_counters();
 	int32_t *d_co = e->b_chain_off.as<int32_t>(n + 1);
 	DChain *d_ch = e->b_chains.as<DChain>(in.n_chains + 1);
@@ -848,9 +886,9 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	CK(cudaMemsetAsync(d_nr + n, 0, sizeof(int32_t), e->stream));
 	int64_t *d_roff = e->b_soff.as<int64_t>(n + 2);
 	exclusive_scan(e, d_nr, d_roff, n + 1);
-	e->d2h(reg_off, d_roff, sizeof(int64_t) * (n + 1));
+	int64_t total = 0;
+	e->d2h(&total, d_roff + n, sizeof(int64_t));
 	e->sync();
-	const int64_t total = reg_off[n];
 	DReg *d_out = e->b_xout.as<DReg>(total + 1);
 	k_ext_gather<<<grid_for(n, 256), 256, 0, e->stream>>>(n, d_co, d_ch, d_nr, d_roff, d_regs, d_out);
 	CK(cudaGetLastError());
@@ -864,12 +902,22 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &out)
 	}
 	e->stats.ms_k_extend_dp += ms_dp;
 	e->stats.n_extend_rounds += rounds;
-	DReg *regs = (DReg *)e->h_slot[PIN_REGS].need(sizeof(DReg) * (total + 1));
-	e->d2h(regs, d_out, sizeof(DReg) * total);
-	out.regs = regs;
 	Counters c = e->read_counters();
 	e->stats.extend_cells += (int64_t)c.ext_cells;
 	e->stats.n_extend_jobs += (int64_t)c.ext_calls;
+}
+
+void stage_extend_download(Engine *e, ExtRegs &out)
+{
+	CK(cudaSetDevice(e->device));
+	const int n = e->n_reads;
+	int64_t *reg_off = (int64_t *)e->h_slot[PIN_REG_OFF].need(sizeof(int64_t) * (n + 2));
+	e->d2h(reg_off, e->b_soff.p, sizeof(int64_t) * (n + 1));
+	e->sync();
+	DReg *regs = (DReg *)e->h_slot[PIN_REGS].need(sizeof(DReg) * (reg_off[n] + 1));
+	e->d2h(regs, e->b_xout.p, sizeof(DReg) * reg_off[n]);
+	e->sync();
+	out.regs = regs; out.reg_off = reg_off;
 }
 
 // Kernel-isolated ksw_extend2 (BASELINE configs[1]: "the exact ksw_extend2 job list ... dump once, replay on GPU"): all the jobs the
@@ -1100,30 +1148,15 @@ __global__ void __launch_bounds__(128) k_sw_thread(SwOpt so, SRC src, const int3
 	warp_add(&cnt->sw_cells, cells);
 }
 
-// Runs n jobs (lengths/xtra given on the host for classification) through the warp kernels, one launch per strip width on
-// concurrent streams, and the rest through the general kernel.  `src` holds device pointers.
-template <class SRC, class LEN>
-static void run_sw(Engine *e, const SwOpt &so, const SRC &src, int64_t n, LEN len_of /* (i, &qlen, &tlen, &xtra) */)
+// Launches the ksw_align2 kernels over classified jobs: d_ord lists the jobs class by class (general kernel first, then strip
+// widths 2, 4, 5, 8 query columns per lane), cnt[k] jobs in class k; one launch per class on concurrent streams.
+template <class SRC>
+static void sw_launch_classes(Engine *e, const SwOpt &so, const SRC &src, const int32_t *d_ord, const int32_t cnt[5], int max_t, int max_q)
 {
-	static const int cls_c[5] = { 0, 2, 4, 5, 8 };
-	std::vector<int32_t> order(n);
-	int64_t cnt[5] = { 0, 0, 0, 0, 0 }, pos[5];
-	int max_q = 0, max_t = 0;
-	std::vector<uint8_t> cls(n);
-	for (int64_t i = 0; i < n; ++i) {
-		int ql, tl, xt;
-		len_of(i, ql, tl, xt);
-		const int c = sw_warp_class(ql, xt);
-		const int k = c == 0 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 5 ? 3 : 4;
-		cls[i] = (uint8_t)k; ++cnt[k];
-		max_t = std::max(max_t, tl);
-		if (k == 0) max_q = std::max(max_q, ql);
-	}
+	int64_t pos[5], n = 0;
 	pos[0] = 0;
 	for (int k = 1; k < 5; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
-	{ int64_t w[5]; for (int k = 0; k < 5; ++k) w[k] = pos[k]; for (int64_t i = 0; i < n; ++i) order[w[cls[i]]++] = (int32_t)i; }
-	int32_t *d_ord = e->b_xord.as<int32_t>(n);
-	e->h2d(d_ord, order.data(), sizeof(int32_t) * n);
+	n = pos[4] + cnt[4];
 	const int64_t bcap = max_t / 2 + 2;
 	uint64_t *B = e->b_b.as<uint64_t>((size_t)(n + 32) * bcap);
 	e->tic();
@@ -1133,7 +1166,7 @@ static void run_sw(Engine *e, const SwOpt &so, const SRC &src, int64_t n, LEN le
 		if (cnt[k] == 0) continue;
 		cudaStream_t st = e->side[used % Engine::N_SIDE];
 		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-		const int nk = (int)cnt[k];
+		const int nk = cnt[k];
 		const int32_t *ord = d_ord + pos[k];
 		uint64_t *Bk = B + pos[k] * bcap;
 		const int grid = grid_for((int64_t)nk * 32, 128);
@@ -1155,6 +1188,32 @@ static void run_sw(Engine *e, const SwOpt &so, const SRC &src, int64_t n, LEN le
 	}
 	for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
 	e->stats.ms_k_sw += e->toc();
+}
+
+// caller-provided batches (stage_sw / stage_sw_bytes): lengths are on the host, so the classification is a host loop
+template <class SRC, class LEN>
+static void run_sw(Engine *e, const SwOpt &so, const SRC &src, int64_t n, LEN len_of /* (i, &qlen, &tlen, &xtra) */)
+{
+	std::vector<int32_t> order(n);
+	int32_t cnt[5] = { 0, 0, 0, 0, 0 };
+	int64_t pos[5];
+	int max_q = 0, max_t = 0;
+	std::vector<uint8_t> cls(n);
+	for (int64_t i = 0; i < n; ++i) {
+		int ql, tl, xt;
+		len_of(i, ql, tl, xt);
+		const int c = sw_warp_class(ql, xt);
+		const int k = c == 0 ? 0 : c == 2 ? 1 : c == 4 ? 2 : c == 5 ? 3 : 4;
+		cls[i] = (uint8_t)k; ++cnt[k];
+		max_t = std::max(max_t, tl);
+		if (k == 0) max_q = std::max(max_q, ql);
+	}
+	pos[0] = 0;
+	for (int k = 1; k < 5; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
+	{ int64_t w[5]; for (int k = 0; k < 5; ++k) w[k] = pos[k]; for (int64_t i = 0; i < n; ++i) order[w[cls[i]]++] = (int32_t)i; }
+	int32_t *d_ord = e->b_xord.as<int32_t>(n);
+	e->h2d(d_ord, order.data(), sizeof(int32_t) * n);
+	sw_launch_classes(e, so, src, d_ord, cnt, max_t, max_q);
 }
 
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)
@@ -1219,7 +1278,7 @@ struct GlobalSeqsSh {
 __global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t *__restrict__ pac, int64_t l_pac, int n,
                                                      const GlobalJob *__restrict__ jobs, const int32_t *__restrict__ order,
                                                      const int64_t *__restrict__ off, const uint8_t *__restrict__ codes, uint8_t *z,
-                                                     GlobalRes *res, int S, int qcap, Counters *cnt)
+                                                     uint32_t *cig, GlobalRes *res, int S, int qcap, Counters *cnt)
 {
 	extern __shared__ uint32_t smem[];
 	__shared__ uint32_t lut[10];
@@ -1244,7 +1303,7 @@ __global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t
 		const uint8_t *q = codes + off[j.read] + j.qb;
 		for (int x = 0; x < s.l_query; ++x) Q[ext_qidx(x)] = s.rev ? q[s.l_query - 1 - x] : q[x];
 		GlobalRowSh eh = { rows, S - 1 };
-		global_task(go, s, j, eh, z + j.zoff, &res[jx], &cells, (S - 2) >> 1);
+		global_task(go, s, j, eh, z + j.zoff, cig + j.cig_off, &res[jx], &cells, (S - 2) >> 1);
 	}
 	warp_add(&cnt->global_cells, cells);
 }
@@ -1253,7 +1312,7 @@ __global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t
 __global__ void __launch_bounds__(128) k_global_jobs(GlobalOpt go, const uint8_t *__restrict__ pac, int64_t l_pac, int n,
                                                      const GlobalJob *__restrict__ jobs, const int32_t *__restrict__ order,
                                                      const int64_t *__restrict__ off, const uint8_t *__restrict__ codes, int32_t *rows,
-                                                     int64_t stride, uint8_t *z, GlobalRes *res, Counters *cnt)
+                                                     int64_t stride, uint8_t *z, uint32_t *cig, GlobalRes *res, Counters *cnt)
 {
 	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	int64_t cells = 0;
@@ -1261,98 +1320,246 @@ __global__ void __launch_bounds__(128) k_global_jobs(GlobalOpt go, const uint8_t
 		const int jx = order[t];
 		const GlobalJob j = jobs[jx];
 		GlobalRow eh = { rows + t, stride };
-		global_task(go, global_seqs(pac, l_pac, codes + off[j.read] + j.qb, j), j, eh, z + j.zoff, &res[jx], &cells);
+		global_task(go, global_seqs(pac, l_pac, codes + off[j.read] + j.qb, j), j, eh, z + j.zoff, cig + j.cig_off, &res[jx], &cells);
 	}
 	warp_add(&cnt->global_cells, cells);
 }
 
-const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes)
+// Launches the CIGAR-stage kernels over classified jobs (finish_stage.h: GlobalClassTask): d_ord lists the jobs class by class
+// - row windows of 32, 64, 128, 256, 512 columns in shared memory, then the general kernel - and, within a class, by band and
+// target length, so that the lanes of a warp get regions of similar cost.  One launch per class on concurrent streams.
+static void global_launch_classes(Engine *e, const GlobalOpt &go, const GlobalJob *dj, const int32_t *d_ord, const int32_t cnt[6], const int32_t qmax[6],
+                                  const int64_t *d_off, const uint8_t *d_codes, uint8_t *z, uint32_t *cig, GlobalRes *dr)
+{
+	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
+	if (!e->global_attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); e->global_attr_set = true; }
+	int64_t pos[6];
+	pos[0] = 0;
+	for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
+	e->tic();
+	CK(cudaEventRecord(e->ev_fork, e->stream));
+	int used = 0;
+	for (int k = 5; k >= 0; --k) {
+		if (cnt[k] == 0) continue;
+		cudaStream_t st = e->side[used % Engine::N_SIDE];
+		CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
+		const int nk = cnt[k];
+		if (k < 5) {
+			const int S = cls_S[k], qcap = qmax[k];
+			const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+			const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
+			k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
+				d_off, d_codes, z, cig, dr, S, qcap, e->d_cnt);
+		} else {
+			const int64_t stride = ((int64_t)nk + 31) & ~31ll;
+			int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
+			k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], d_off, d_codes, rows, stride, z, cig, dr, e->d_cnt);
+		}
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
+		e->stats.n_launches += 1;
+		++used;
+	}
+	for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
+	e->stats.ms_k_global += e->toc();
+}
+
+// ksw_global2 for one caller-provided job (the C wrapper): the byte buffers stand in for read and reference
+__global__ void k_global_one(GlobalOpt go, int qlen, const uint8_t *q, int tlen, const uint8_t *t, int w, int32_t *rows, uint8_t *z, uint32_t *cig, int32_t *out)
+{
+	struct Seqs {
+		const uint8_t *q, *t; int l_query;
+		__device__ int qa(int j) const { return q[j]; }
+		__device__ int ta(int i) const { return t[i]; }
+		__device__ const int8_t *trow(const GlobalOpt &o, int i) const { return o.mat + t[i] * 5; }
+		__device__ int sub(const int8_t *row, int j) const { return row[q[j]]; }
+	} s = { q, t, qlen };
+	GlobalRow eh = { rows, 1 };
+	int n_cigar = 0;
+	out[0] = global_dp(go, s, tlen, w, eh, z, cig, &n_cigar, nullptr);
+	out[1] = n_cigar;
+}
+
+int stage_global_bytes(Engine *e, const GlobalOpt &go, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int w, std::vector<uint32_t> *cigar)
 {
 	CK(cudaSetDevice(e->device));
-	const int64_t n = (int64_t)jobs.size();
-	if (n == 0) return nullptr;
-	e->zero_counters();
-	// classes by the circular window a lane needs: 32, 64, 128, 256, 512 columns; wider bands or queries over 256 bases
-	// take the general kernel.  The FIRST pass sizes the window for the first band mem_reg2aln tries (the band-doubling
-	// retries are rare, and sizing every lane for the widest of three tries put nearly all regions into the 128-column class
-	// at 6 warps per SM); a region whose retry outgrows its window comes back flagged and is rerun in a second pass sized for
-	// its widest try.
-	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
-	GlobalJob *dj = e->b_gjobs.as<GlobalJob>(n);
-	GlobalRes *dr = e->b_gres.as<GlobalRes>(n);
-	int32_t *d_ord = e->b_xord.as<int32_t>(n);
-	uint8_t *z = e->b_gz.as<uint8_t>((size_t)z_bytes + 64);
-	e->h2d(dj, jobs.data(), sizeof(GlobalJob) * n);
-	if (!e->global_attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); e->global_attr_set = true; }
-	GlobalRes *hr = (GlobalRes *)e->h_gres.need(sizeof(GlobalRes) * n);
-	std::vector<int32_t> sel(n), order, key;
-	const bool squeeze = getenv("B200_GLOBAL_SQUEEZE") != nullptr;
-	for (int64_t i = 0; i < n; ++i) sel[i] = (int32_t)i;
-	for (int pass = 0; pass < 2 && !sel.empty(); ++pass) {
-		const int64_t m = (int64_t)sel.size();
-		int64_t cnt[6] = { 0, 0, 0, 0, 0, 0 }, pos[6];
-		int qmax[6] = { 0, 0, 0, 0, 0, 0 };
-		// counting sort by (class, band, target length / 16): lanes of a warp get regions of similar cost
-		const int NB = 6 * 256 * 64;
-		std::vector<int32_t> bucket(NB + 1, 0);
-		key.resize(m); order.resize(m);
-		for (int64_t x = 0; x < m; ++x) {
-			const GlobalJob &j = jobs[sel[x]];
-			const int ql = j.qe - j.qb, rl = (int)(j.re - j.rb);
-			int band = pass == 0 ? global_band(go, ql, rl, j.w2 < go.w_max ? j.w2 : go.w_max) : j.wmax;
-			if (pass == 0 && squeeze) band >>= 2;          // (tests: windows too small even for the first try - everything takes the rerun path)
-			const int need = 2 * band + 2;
-			int k = 5;
-			if (ql <= 256) for (int c = 0; c < 5; ++c) if (need <= cls_S[c]) { k = c; break; }
-			++cnt[k];
-			qmax[k] = std::max(qmax[k], ql);
-			key[x] = (k * 256 + std::min(band, 255)) * 64 + std::min(rl >> 4, 63);
-			++bucket[key[x] + 1];
-		}
-		for (int b = 0; b < NB; ++b) bucket[b + 1] += bucket[b];
-		pos[0] = 0;
-		for (int k = 1; k < 6; ++k) pos[k] = pos[k - 1] + cnt[k - 1];
-		for (int64_t x = 0; x < m; ++x) order[bucket[key[x]]++] = sel[x];
-		e->h2d(d_ord, order.data(), sizeof(int32_t) * m);
-		e->tic();
-		CK(cudaEventRecord(e->ev_fork, e->stream));
-		int used = 0;
-		for (int k = 5; k >= 0; --k) {
-			if (cnt[k] == 0) continue;
-			cudaStream_t st = e->side[used % Engine::N_SIDE];
-			CK(cudaStreamWaitEvent(st, e->ev_fork, 0));
-			const int nk = (int)cnt[k];
-			if (k < 5) {
-				const int S = cls_S[k], qcap = qmax[k];
-				const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-				const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
-				k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
-					(const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, z, dr, S, qcap, e->d_cnt);
-			} else {
-				const int64_t stride = ((int64_t)nk + 31) & ~31ll;
-				int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
-				k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], (const int64_t *)e->d_off.p,
-					(const uint8_t *)e->d_codes.p, rows, stride, z, dr, e->d_cnt);
-			}
-			CK(cudaGetLastError());
-			CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
-			e->stats.n_launches += 1;
-			++used;
-		}
-		for (int q = 0; q < used && q < Engine::N_SIDE; ++q) CK(cudaStreamWaitEvent(e->stream, e->ev_join[q], 0));
-		e->stats.ms_k_global += e->toc();
-		e->d2h(hr, dr, sizeof(GlobalRes) * n);
-		e->sync();
-		sel.clear();
-		if (pass == 0) for (int64_t i = 0; i < n; ++i) if (hr[i].n_cigar == -2) sel.push_back((int32_t)i);
-		if (pass == 0 && getenv("B200_DEBUG")) fprintf(stderr, "[global] %lld regions, classes %lld %lld %lld %lld %lld %lld, %lld rerun with a wider window\n",
-			(long long)n, (long long)cnt[0], (long long)cnt[1], (long long)cnt[2], (long long)cnt[3], (long long)cnt[4], (long long)cnt[5], (long long)sel.size());
+	uint8_t *dq = e->b_q.as<uint8_t>(qlen + 16), *dt = e->b_t.as<uint8_t>(tlen + 16);
+	const int n_col = ((qlen < 2 * w + 1 ? qlen : 2 * w + 1) + 3) & ~3;
+	int32_t *rows = e->b_grow.as<int32_t>((size_t)2 * (qlen + 2));
+	uint8_t *z = e->fb[FB_GZ].as<uint8_t>((size_t)n_col * (tlen + 1) + 64);
+	uint32_t *cig = e->fb[FB_CIG].as<uint32_t>((size_t)qlen + tlen + 8);
+	int32_t *d_out = e->fb[FB_CTR].as<int32_t>(64);
+	e->h2d(dq, query, qlen);
+	e->h2d(dt, target, tlen);
+	k_global_one<<<1, 1, 0, e->stream>>>(go, qlen, dq, tlen, dt, w, rows, z, cig, d_out);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	int32_t h[2];
+	e->d2h(h, d_out, sizeof h);
+	e->sync();
+	if (cigar) {
+		cigar->resize(h[1]);
+		if (h[1] > 0) { e->d2h(cigar->data(), cig, sizeof(uint32_t) * h[1]); e->sync(); }
 	}
-	Counters c = e->read_counters();
-	e->stats.global_cells += (int64_t)c.global_cells;
-	e->stats.n_global_jobs += n;
-	return hr;
+	return h[0];
 }
+
+/* ------------------------------------------------------------------ finish stages: the CUDA backend of finish_stage.h */
+
+template <class TASK>
+__global__ void __launch_bounds__(128) k_task(int64_t n, TASK task)
+{
+	const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) task(i);
+}
+
+struct CudaBK {
+	Engine *e;
+	bool text_phase = false;
+	template <class T> T *buf(int id, size_t n) { return e->fb[id].as<T>(n ? n : 1); }
+	template <class T> T *grow(int id, size_t n, size_t keep)
+	{
+		DevBuf &b = e->fb[id];
+		if (n * sizeof(T) <= b.cap) return (T *)b.p;
+		DevBuf nb;
+		nb.need(n * sizeof(T));
+		if (keep) CK(cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, e->stream));
+		e->sync();
+		b.release();
+		b = nb;
+		return (T *)b.p;
+	}
+	template <class TASK> void run(int64_t n, const TASK &t)
+	{
+		if (n <= 0) return;
+		static_assert(sizeof(TASK) <= 4000, "task does not fit the kernel parameter space");
+		cudaEvent_t a, b;
+		ev_pair(a, b);
+		CK(cudaEventRecord(a, e->stream));
+		k_task<TASK><<<grid_for(n, 128), 128, 0, e->stream>>>(n, t);
+		CK(cudaGetLastError());
+		CK(cudaEventRecord(b, e->stream));
+		e->stats.n_launches += 1;
+	}
+	void scan(const int32_t *in, int64_t *out, int64_t n) { exclusive_scan(e, in, out, n); }
+	void sort_pairs(uint32_t *key, int32_t *val, int64_t n)
+	{
+		uint32_t *key2 = e->b_xkey2.as<uint32_t>(n);
+		int32_t *val2 = e->b_xact1.as<int32_t>(n);
+		cub::DoubleBuffer<uint32_t> dk(key, key2);
+		cub::DoubleBuffer<int32_t> dv(val, val2);
+		size_t tmp = 0;
+		CK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dk, dv, (int)n, 0, 20, e->stream));
+		void *d = e->b_cub.need(tmp);
+		CK(cub::DeviceRadixSort::SortPairs(d, tmp, dk, dv, (int)n, 0, 20, e->stream));
+		if (dv.Current() != val) CK(cudaMemcpyAsync(val, dv.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+		e->stats.n_launches += 2;
+	}
+	void zero(void *p, size_t bytes) { CK(cudaMemsetAsync(p, 0, bytes, e->stream)); }
+	int64_t get64(const int64_t *p) { int64_t v = 0; e->d2h(&v, p, sizeof v); e->sync(); return v; }
+	int32_t get32(const int32_t *p) { int32_t v = 0; e->d2h(&v, p, sizeof v); e->sync(); return v; }
+	void upload(void *dst, const void *src, size_t bytes) { e->h2d(dst, src, bytes); e->sync(); }
+	void download(void *dst, const void *src, size_t bytes) { e->d2h(dst, src, bytes); e->sync(); }
+	void sw_launch(const SwOpt &so, const SwJob *jobs, SwRes *res, const int32_t *order, const int32_t cnt[5], int max_t, int max_q)
+	{
+		SwSrcPipeline src = { jobs, (const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, e->fm.pac, e->fm.l_pac, res };
+		sw_launch_classes(e, so, src, order, cnt, max_t, max_q);
+	}
+	void global_launch(const GlobalOpt &go, const GlobalJob *jobs, const int32_t *order, const int32_t cnt[6], const int32_t qmax[6], uint8_t *z,
+	                   uint32_t *cig, GlobalRes *res)
+	{
+		global_launch_classes(e, go, jobs, order, cnt, qmax, (const int64_t *)e->d_off.p, (const uint8_t *)e->d_codes.p, z, cig, res);
+	}
+	// CUDA-event pairs around every task launch: summed after the call (no synchronisation inside the sequence)
+	std::vector<size_t> text_from;
+	size_t ev_used = 0;
+	void ev_pair(cudaEvent_t &a, cudaEvent_t &b)
+	{
+		if (ev_used + 2 > e->ev_pool.size()) { e->ev_pool.resize(ev_used + 2); CK(cudaEventCreate(&e->ev_pool[ev_used])); CK(cudaEventCreate(&e->ev_pool[ev_used + 1])); }
+		a = e->ev_pool[ev_used]; b = e->ev_pool[ev_used + 1];
+		ev_used += 2;
+	}
+	double task_ms()
+	{
+		double ms = 0;
+		for (size_t i = 0; i < ev_used; i += 2) { float x; CK(cudaEventElapsedTime(&x, e->ev_pool[i], e->ev_pool[i + 1])); ms += x; }
+		return ms;
+	}
+};
+
+static double fin_clock_ms()
+{
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes)
+{
+	CK(cudaSetDevice(e->device));
+	if (n_reads != e->n_reads) die("stage_upload_text: does not match the uploaded reads");
+	e->h2d(e->d_rtext.as<ReadText>(n_reads + 1), rtext, sizeof(ReadText) * n_reads);
+	e->h2d(e->d_text.as<char>(bytes + 16), text, (size_t)bytes);
+	e->sync();
+}
+
+void stage_finish(Engine *e, const FinishArgs &a)
+{
+	CK(cudaSetDevice(e->device));
+	CudaBK bk = { e };
+	FinCtx cx;
+	memset(&cx, 0, sizeof cx);
+	cx.opt = *a.opt;
+	cx.fm = e->fm;
+	cx.ctg_alt = (const uint8_t *)e->d_ctg_alt;
+	cx.ctg_name_off = (const int64_t *)e->d_ctg_name_off; cx.ctg_names = (const char *)e->d_ctg_names;
+	cx.ctg_anno_off = (const int64_t *)e->d_ctg_anno_off; cx.ctg_annos = (const char *)e->d_ctg_annos;
+	cx.n_reads = e->n_reads; cx.pe = (a.opt->flag & MEM_F_PE) ? 1 : 0;
+	cx.n_processed = a.n_processed;
+	cx.off = (const int64_t *)e->d_off.p; cx.codes = (const uint8_t *)e->d_codes.p;
+	cx.rtext = (const ReadText *)e->d_rtext.p; cx.text = (const char *)e->d_text.p;
+	cx.rg_len = a.rg_id ? (int)strnlen(a.rg_id, 255) : 0;
+	if (cx.rg_len) memcpy(cx.rg_id, a.rg_id, cx.rg_len);
+	FinishIn in = { (const DReg *)e->b_xout.p, (const int64_t *)e->b_soff.p, a.pes0, e->max_len, (const double *)e->d_logtab, e->n_log };
+	FinishOut fo;
+	e->zero_counters();
+	const double k_sw0 = e->stats.ms_k_sw, k_gl0 = e->stats.ms_k_global;
+	finish_run(bk, cx, in, fo, e->stats, fin_clock_ms);
+	e->sync();
+	e->fin_out = fo;
+	e->stats.ms_k_finish += bk.task_ms();
+	(void)k_sw0; (void)k_gl0;
+	Counters c = e->read_counters();
+	e->stats.sw_cells += (int64_t)c.sw_cells;
+	e->stats.global_cells += (int64_t)c.global_cells;
+	e->stats.sam_bytes += fo.sam_bytes;
+}
+
+void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out)
+{
+	CK(cudaSetDevice(e->device));
+	const FinishOut fo = e->fin_out;
+	// the text and (on request) the per-read offsets come back in page-locked memory
+	const double t0 = fin_clock_ms();
+	char *h_sam = a.alloc ? (char *)a.alloc((size_t)fo.sam_bytes + 1) : (char *)e->h_sam.need((size_t)fo.sam_bytes + 16);
+	e->d2h(h_sam, fo.sam, (size_t)fo.sam_bytes);
+	int64_t *h_off = nullptr;
+	if (a.want_offsets) {
+		h_off = (int64_t *)e->h_sam_off.need(sizeof(int64_t) * (e->n_reads + 1));
+		e->d2h(h_off, fo.sam_off, sizeof(int64_t) * (e->n_reads + 1));
+	}
+	e->sync();
+	h_sam[fo.sam_bytes] = 0;
+	e->stats.ms_deliver += fin_clock_ms() - t0;
+	out.sam = h_sam; out.sam_off = h_off; out.bytes = fo.sam_bytes;
+}
+
+void *stage_host_alloc(size_t bytes)
+{
+	void *p = nullptr;
+	CK(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+	return p;
+}
+void stage_host_free(void *p) { if (p) cudaFreeHost(p); }
 
 /* ------------------------------------------------------------------ int32 issue-rate micro-benchmark (roofline denominator)
  * Measures the int32 instruction issue rate of this GPU ("measure it with a dependent-chain-free

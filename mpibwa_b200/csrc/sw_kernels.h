@@ -25,6 +25,15 @@ struct SwOpt {
 
 struct SwRes { int score, te, qe, score2, te2, tb, qb; };
 
+// smallest strip width (query columns per lane) of the one-warp-per-job kernel (sw_warp_kernel.cuh) that holds the job, or 0
+// when it must take the general (one thread per job) kernel
+B200_HD int sw_warp_class(int qlen, int xtra)
+{
+	const int p = (xtra & 0x10000) ? 16 : 8;
+	const int qpad = (qlen + p - 1) / p * p;
+	return qpad <= 64 ? 2 : qpad <= 128 ? 4 : qpad <= 160 ? 5 : qpad <= 256 ? 8 : 0;
+}
+
 struct Row16 {
 	uint16_t *base; int64_t stride;
 	B200_HD int get(int q) const { return base[(int64_t)q * stride]; }

@@ -161,12 +161,4 @@ __device__ void sw_align_warp(int qlen, QA query, int tlen, TA target, const SwO
 	if (r->score == rr.score) { r->tb = r->te - rr.te; r->qb = r->qe - rr.qe; }
 }
 
-// smallest supported strip width for a job, or 0 when the job must take the general (one thread per job) kernel
-static inline int sw_warp_class(int qlen, int xtra)
-{
-	const int p = (xtra & 0x10000) ? 16 : 8;
-	const int qpad = (qlen + p - 1) / p * p;
-	return qpad <= 64 ? 2 : qpad <= 128 ? 4 : qpad <= 160 ? 5 : qpad <= 256 ? 8 : 0;
-}
-
 } // namespace b200

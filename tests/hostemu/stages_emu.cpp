@@ -6,6 +6,10 @@
 #include "../../mpibwa_b200/csrc/util.h"
 #include "../../mpibwa_b200/csrc/smem_kernel.cuh"
 #include "../../mpibwa_b200/csrc/smem_sweeps.cuh"
+#include "../../mpibwa_b200/csrc/finish_stage.h"
+#include <chrono>
+#include <cmath>
+#include <string>
 #include <cstdio>
 #include <memory>
 #include <algorithm>
@@ -29,8 +33,18 @@ public:
 	std::vector<SeedRec> seeds;
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
-	std::vector<GlobalRes> gres;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
+	// finish stages
+	std::vector<DReg> xregs;
+	std::vector<int64_t> xoff;
+	std::vector<char> fb[FB_N];
+	std::vector<ReadText> rtext;
+	std::vector<char> text, sam;
+	std::vector<int64_t> sam_off, ctg_name_off, ctg_anno_off;
+	std::string ctg_names, ctg_annos;
+	std::shared_ptr<std::vector<double>> logtab;
+	int max_len = 0;
+	FinishOut fin_out;
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
@@ -51,6 +65,14 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < bns->n_seqs; ++i) e->ctg_alt.push_back(bns->anns[i].is_alt ? 1 : 0);
 	e->ctg_alt.push_back(0);
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data(); e->fm.n_ctg = bns->n_seqs;
+	e->ctg_name_off.assign(1, 0); e->ctg_anno_off.assign(1, 0);
+	for (int i = 0; i < bns->n_seqs; ++i) {
+		e->ctg_names += bns->anns[i].name; e->ctg_name_off.push_back((int64_t)e->ctg_names.size());
+		if (bns->anns[i].anno) e->ctg_annos += bns->anns[i].anno;
+		e->ctg_anno_off.push_back((int64_t)e->ctg_annos.size());
+	}
+	e->logtab = std::make_shared<std::vector<double>>(1 << 20);
+	for (size_t i = 0; i < e->logtab->size(); ++i) (*e->logtab)[i] = log((double)i);
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
 }
@@ -61,6 +83,8 @@ Engine *engine_clone(Engine *base)
 	e->occ = base->occ;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
+	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;
+	e->logtab = base->logtab;
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
 }
@@ -81,6 +105,14 @@ void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_
 	e->off.assign(off, off + n_reads + 1);
 	e->codes.assign(codes, codes + off[n_reads]);
 	e->codes.resize(off[n_reads] + 8);
+	e->max_len = 0;
+	for (int i = 0; i < n_reads; ++i) e->max_len = std::max(e->max_len, (int)(off[i + 1] - off[i]));
+}
+
+void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes)
+{
+	e->rtext.assign(rtext, rtext + n_reads);
+	e->text.assign(text, text + bytes);
 }
 
 void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t *off, const uint8_t *codes,
@@ -254,7 +286,7 @@ void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool)
 	in.n_chains = coff[n]; in.n_seeds = soff[n]; in.on_device = false;
 }
 
-void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &res)
+void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in)
 {
 	const int n = in.n_reads;
 	const int32_t *chain_off = in.chain_off;
@@ -280,12 +312,11 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in, ExtRegs &res)
 		e->stats.n_extend_jobs += calls;
 	}
 	reg_off[n] = (int64_t)regs.size();
-	DReg *pr = (DReg *)stage_pinned(e, PIN_REGS, sizeof(DReg) * (regs.size() + 1));
-	int64_t *po = (int64_t *)stage_pinned(e, PIN_REG_OFF, sizeof(int64_t) * (n + 1));
-	memcpy(pr, regs.data(), sizeof(DReg) * regs.size());
-	memcpy(po, reg_off.data(), sizeof(int64_t) * (n + 1));
-	res.regs = pr; res.reg_off = po;
+	regs.push_back(DReg());
+	e->xregs.swap(regs); e->xoff.swap(reg_off);
 }
+
+void stage_extend_download(Engine *e, ExtRegs &res) { res.regs = e->xregs.data(); res.reg_off = e->xoff.data(); }
 
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out)
 {
@@ -306,21 +337,122 @@ void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::v
 	}
 }
 
-const GlobalRes *stage_global(Engine *e, const GlobalOpt &go, const std::vector<GlobalJob> &jobs, int64_t z_bytes)
+int stage_global_bytes(Engine *, const GlobalOpt &go, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int w, std::vector<uint32_t> *cigar)
 {
-	std::vector<GlobalRes> &out = e->gres;
-	out.resize(jobs.size());
-	std::vector<uint8_t> z((size_t)z_bytes + 16);
-	std::vector<int32_t> row;
-	for (size_t x = 0; x < jobs.size(); ++x) {
-		const GlobalJob &j = jobs[x];
-		row.resize(2 * (size_t)(j.qe - j.qb + 2));
-		GlobalRow eh = { row.data(), 1 };
-		global_task(go, global_seqs(e->fm.pac, e->fm.l_pac, e->codes.data() + e->off[j.read] + j.qb, j), j, eh, z.data() + j.zoff, &out[x], &e->stats.global_cells);
-		++e->stats.n_global_jobs;
-	}
-	return out.data();
+	struct Seqs {
+		const uint8_t *q, *t; int l_query;
+		int qa(int j) const { return q[j]; }
+		int ta(int i) const { return t[i]; }
+		const int8_t *trow(const GlobalOpt &o, int i) const { return o.mat + t[i] * 5; }
+		int sub(const int8_t *row, int j) const { return row[q[j]]; }
+	} s = { query, target, qlen };
+	std::vector<int32_t> row(2 * (size_t)(qlen + 2));
+	const int n_col = ((qlen < 2 * w + 1 ? qlen : 2 * w + 1) + 3) & ~3;
+	std::vector<uint8_t> z((size_t)n_col * (tlen + 1) + 64);
+	std::vector<uint32_t> cig((size_t)qlen + tlen + 8);
+	GlobalRow eh = { row.data(), 1 };
+	int n_cigar = 0;
+	const int score = global_dp(go, s, tlen, w, eh, z.data(), cig.data(), &n_cigar, nullptr);
+	if (cigar) cigar->assign(cig.begin(), cig.begin() + n_cigar);
+	return score;
 }
+
+// finish_stage.h over plain loops
+struct HostBK {
+	Engine *e;
+	template <class T> T *buf(int id, size_t n) { e->fb[id].assign((n ? n : 1) * sizeof(T) + 64, (char)0x5a); return (T *)e->fb[id].data(); }   // (poisoned: nothing may rely on zeroed scratch)
+	template <class T> T *grow(int id, size_t n, size_t) { e->fb[id].resize(n * sizeof(T) + 64); return (T *)e->fb[id].data(); }
+	template <class TASK> void run(int64_t n, const TASK &t) { for (int64_t i = 0; i < n; ++i) t(i); }
+	void scan(const int32_t *in, int64_t *out, int64_t n) { int64_t s = 0; for (int64_t i = 0; i < n; ++i) { out[i] = s; s += in[i]; } }
+	void sort_pairs(uint32_t *key, int32_t *val, int64_t n)
+	{
+		std::vector<std::pair<uint32_t, int32_t>> v(n);
+		for (int64_t i = 0; i < n; ++i) v[i] = { key[i], val[i] };
+		std::stable_sort(v.begin(), v.end(), [](const std::pair<uint32_t, int32_t> &a, const std::pair<uint32_t, int32_t> &b) { return a.first < b.first; });
+		for (int64_t i = 0; i < n; ++i) { key[i] = v[i].first; val[i] = v[i].second; }
+	}
+	void zero(void *p, size_t bytes) { memset(p, 0, bytes); }
+	int64_t get64(const int64_t *p) { return *p; }
+	int32_t get32(const int32_t *p) { return *p; }
+	void upload(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+	void download(void *dst, const void *src, size_t bytes) { memcpy(dst, src, bytes); }
+	void sw_launch(const SwOpt &so, const SwJob *jobs, SwRes *res, const int32_t *order, const int32_t cnt[5], int, int)
+	{
+		const int64_t n = (int64_t)cnt[0] + cnt[1] + cnt[2] + cnt[3] + cnt[4];
+		std::vector<uint16_t> H, E;
+		std::vector<uint64_t> b;
+		for (int64_t x = 0; x < n; ++x) {
+			const SwJob &j = jobs[order[x]];
+			H.resize(j.q_len + 16); E.resize(j.q_len + 16); b.resize(j.tlen / 2 + 2);
+			Row16 h = { H.data(), 1 }, ee = { E.data(), 1 };
+			List64 bl = { b.data(), 1 };
+			STPac ta = { e->fm.pac, e->fm.l_pac, j.rb };
+			const uint8_t *q = e->codes.data() + e->off[j.read] + j.q_beg;
+			if (j.is_rev) { SQRevComp qa = { q, j.q_len }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &res[order[x]], &e->stats.sw_cells); }
+			else { SQFwd qa = { q }; sw_align(j.q_len, qa, j.tlen, ta, so, j.xtra, h, ee, bl, &res[order[x]], &e->stats.sw_cells); }
+		}
+	}
+	void global_launch(const GlobalOpt &go, const GlobalJob *jobs, const int32_t *order, const int32_t cnt[6], const int32_t *, uint8_t *z,
+	                   uint32_t *cig, GlobalRes *res)
+	{
+		static const int cls_S[5] = { 32, 64, 128, 256, 512 };
+		std::vector<int32_t> row;
+		int64_t x = 0;
+		for (int k = 0; k < 6; ++k)
+			for (int c = 0; c < cnt[k]; ++c, ++x) {
+				const GlobalJob &j = jobs[order[x]];
+				row.resize(2 * (size_t)(j.qe - j.qb + 2));
+				GlobalRow eh = { row.data(), 1 };
+				// (the shared-memory classes of the CUDA stage hold a window of S columns: a wider retry comes back flagged for the rerun pass)
+				global_task(go, global_seqs(e->fm.pac, e->fm.l_pac, e->codes.data() + e->off[j.read] + j.qb, j), j, eh, z + j.zoff, cig + j.cig_off,
+				            &res[order[x]], &e->stats.global_cells, k < 5 ? (cls_S[k] - 2) >> 1 : 0x7fffffff);
+			}
+	}
+};
+
+static double emu_clock_ms()
+{
+	using namespace std::chrono;
+	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+void stage_finish(Engine *e, const FinishArgs &a)
+{
+	HostBK bk = { e };
+	FinCtx cx;
+	memset(&cx, 0, sizeof cx);
+	cx.opt = *a.opt;
+	cx.fm = e->fm;
+	cx.ctg_alt = e->ctg_alt.data();
+	cx.ctg_name_off = e->ctg_name_off.data(); cx.ctg_names = e->ctg_names.data();
+	cx.ctg_anno_off = e->ctg_anno_off.data(); cx.ctg_annos = e->ctg_annos.data();
+	cx.n_reads = e->n_reads; cx.pe = (a.opt->flag & MEM_F_PE) ? 1 : 0;
+	cx.n_processed = a.n_processed;
+	cx.off = e->off.data(); cx.codes = e->codes.data();
+	cx.rtext = e->rtext.data(); cx.text = e->text.data();
+	cx.rg_len = a.rg_id ? (int)strnlen(a.rg_id, 255) : 0;
+	if (cx.rg_len) memcpy(cx.rg_id, a.rg_id, cx.rg_len);
+	FinishIn in = { e->xregs.data(), e->xoff.data(), a.pes0, e->max_len, e->logtab->data(), (int)e->logtab->size() };
+	FinishOut fo;
+	finish_run(bk, cx, in, fo, e->stats, emu_clock_ms);
+	e->fin_out = fo;
+	e->stats.sam_bytes += fo.sam_bytes;
+}
+
+void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out)
+{
+	const FinishOut fo = e->fin_out;
+	char *dst;
+	if (a.alloc) dst = (char *)a.alloc((size_t)fo.sam_bytes + 1);
+	else { e->sam.resize((size_t)fo.sam_bytes + 16); dst = e->sam.data(); }
+	memcpy(dst, fo.sam, (size_t)fo.sam_bytes);
+	dst[fo.sam_bytes] = 0;
+	e->sam_off.assign(fo.sam_off, fo.sam_off + e->n_reads + 1);
+	out.sam = dst; out.sam_off = e->sam_off.data(); out.bytes = fo.sam_bytes;
+}
+
+void *stage_host_alloc(size_t bytes) { return malloc(bytes); }
+void stage_host_free(void *p) { free(p); }
 
 void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend_job_t *jobs,
                         const uint8_t *query, int64_t, const uint8_t *target, int64_t)

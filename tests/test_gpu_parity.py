@@ -259,15 +259,8 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
     K = int(args[args.index("-K") + 1])
     got = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
     assert got == want
-    # the same with every chunk cut into four concurrently driven sub-batch lanes (as full-size chunks are)
-    os.environ["B200_LANE_MIN"] = "1000"
-    os.environ["B200_LANES"] = "4"
-    try:
-        got4 = a.align(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args)
-    finally:
-        os.environ.pop("B200_LANE_MIN", None)
-        os.environ.pop("B200_LANES", None)
-    assert got4 == want
+    # the same with two chunks in flight (chunk jobs) and the chunk's text as one buffer
+    assert a.align_pipelined(r1, None if name == "se100" else r2, K=K, trimmed="-T" in args) == want
     # chaining stage: B200_CHAIN=check runs the device chaining AND the host chaining and aborts on any difference in the
     # chain/seed tables handed to chain2aln; B200_CHAIN=host is the host path alone (the one long reads take)
     for mode in ("check", "host"):
@@ -411,13 +404,11 @@ def test_properties_at_scale(tmp_path):
     assert s16 == again == s3 == s_chk
     # kernel-isolated replay of the chunk's ksw_extend2 job list (bench.py's one-batch figure): same cell count per job as the rounds
     os.environ["B200_EXT_RECORD"] = "1"
-    os.environ["B200_LANES"] = "1"
     try:
         assert a.align(r1, r2, K=1 << 40) == a.align_fastq(r1, r2)
         st = a.stats()
     finally:
         os.environ.pop("B200_EXT_RECORD", None)
-        os.environ.pop("B200_LANES", None)
     cells, jobs = C.c_int64(), C.c_int64()
     ms = a.lib.b200_ext_replay(a.opt, C.byref(cells), C.byref(jobs))
     assert ms > 0 and 0.9 * st["n_extend_jobs"] <= jobs.value <= st["n_extend_jobs"]

@@ -8,8 +8,8 @@ in its chunk-job form (b200_process_seqs_begin / _end, include/mpibwa_b200.h) so
 stages of chunk i+1 run under the host stages of chunk i.  The timed region covers exactly K chunks, first begin to last end.
 
   value  read pairs/s through mem_process_seqs with the chunk's encoded reads already resident in HBM
-  e2e    read pairs/s from raw fastq bytes in host memory to SAM bytes in host memory (in-place parse, interleave,
-         mem_process_seqs incl. every H2D/D2H copy, SAM concatenation) - the reference-facing call with host buffers
+  e2e    read pairs/s from raw fastq bytes in (page-locked) host memory to SAM bytes in host memory: b200_align_fastq_begin /
+         b200_align_chunk_end, every H2D/D2H copy inside - the reference-facing call with host buffers
   roofline / kernels   per device stage: algorithmic work / CUDA-event kernel time vs the measured peak
   cpu_baseline         the compiled reference (oracle/_ref/ref_driver) on the box's host cores, bounded sample
 
@@ -312,6 +312,8 @@ def main():
     prefix = os.path.join(workload_dir(args), "ref.fa")
     f1, f2 = ensure_reads(args, rank, args.pairs)
     n_threads = max(1, (os.cpu_count() or 1) // world)
+    if os.environ.get("B200_BENCH_THREADS"):        # (experiments: the host-thread budget a rank gets at a larger N, on one GPU)
+        n_threads = int(os.environ["B200_BENCH_THREADS"])
     al = M.Aligner(prefix, device=local_rank, n_threads=n_threads, verbose=1)
     lib = al.lib
     fq1, fq2 = open(f1, "rb").read(), open(f2, "rb").read()
@@ -334,7 +336,13 @@ def main():
     N_SLOTS = 4      # chunk slots of the library: that many chunks can be resident ahead of their call
     # the in-flight chunks need their own fastq buffers (the parse is in place and the job reads the records later)
     n_buf = N_SLOTS + 1
-    read_bufs = [[np.empty(max_pairs * rb + 1, dtype=np.uint8) for rb in (rb1, rb2)] for _ in range(n_buf)]
+
+    def pinned_bytes(n):
+        """page-locked host buffer from the library's pool (what an MPI host would read its fastq chunk into), as a numpy view"""
+        ptr = lib.b200_big_alloc(n)
+        return np.ctypeslib.as_array((C.c_uint8 * n).from_address(ptr))
+
+    read_bufs = [[pinned_bytes(max_pairs * rb + 1) for rb in (rb1, rb2)] for _ in range(n_buf)]
     buf_turn = [0]
 
     def chunk_bytes(c):
@@ -354,7 +362,8 @@ def main():
     STAT_KEYS = ("ms_k_chain", "n_seeds", "n_chains", "ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_extend_dp", "n_extend_rounds", "ms_k_sw", "extend_cells", "n_extend_jobs", "sw_cells", "n_sw_jobs",
                  "fm_occ_blocks", "fm_sa_steps", "fm_sa_lookups", "n_launches", "h2d_bytes", "d2h_bytes", "ms_seed", "ms_chain_host",
                  "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_total", "n_intv",
-                 "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells", "n_global_host")
+                 "ms_sam_plan", "ms_global", "ms_k_global", "n_global_jobs", "global_cells", "n_global_host",
+                 "ms_k_finish", "ms_upload", "ms_deliver", "n_patch_reads", "n_rescue_rounds", "n_global_rerun", "n_aln_slots", "sam_bytes")
 
     def e2e_begin(c, raw=None):
         """raw fastq bytes -> chunk job (b200_align_fastq_begin: parse in place, interleave, align, concatenate - all on the library's job thread)"""
@@ -467,7 +476,7 @@ def main():
         io["h2d"] += st["h2d_bytes"]
         io["d2h"] += st["d2h_bytes"]
         if os.environ.get("B200_BENCH_DEBUG"):
-            log("[bench] e2e job: " + " ".join("%s %.1f" % (k[3:], st[k]) for k in ("ms_total", "ms_seed", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global")))
+            log("[bench] e2e job: " + " ".join("%s %.1f" % (k[3:], st[k]) for k in ("ms_total", "ms_upload", "ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_plan", "ms_global", "ms_sam_host", "ms_deliver", "ms_k_finish")))
 
     # the K chunks' fastq bytes sit in private host buffers (what the host's file read leaves) when the timed region starts
     raw = None
@@ -478,7 +487,7 @@ def main():
             pair = []
             for fq, rb in ((fq1, rb1), (fq2, rb2)):
                 nb = (e - b) * rb
-                a = np.empty(nb + 1, dtype=np.uint8)
+                a = pinned_bytes(nb + 1)
                 a[:nb] = np.frombuffer(fq, dtype=np.uint8, count=nb, offset=b * rb)
                 a[nb] = 0
                 pair.append((a, nb))
@@ -586,7 +595,9 @@ def main():
                                "jobs": rp_jobs.value, "cells": rp_cells.value, "ms": rp_ms,
                                "gcups": (rp_cells.value / rp_ms / 1e6) if rp_ms > 0 else None,
                                "frac": (rp_cells.value / rp_ms / 1e6 * 14 / i32_peak) if rp_ms > 0 and i32_peak else None},
-        "stage_ms_per_step": {k: agg[k] / K for k in ("ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_host", "ms_sam_plan", "ms_global", "ms_total")},
+        "stage_ms_per_step": {k: agg[k] / K for k in ("ms_upload", "ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_plan", "ms_global", "ms_sam_host", "ms_deliver", "ms_total")},
+        "stage_ms_note": "walls per chunk job incl. waiting for the device turn: upload = encode + read text staging + H2D; seed; chain; extend; regs_host = de-duplication; rescue = insert-size statistics + mate rescue; sam_plan = pairing + record plan; global = CIGAR stage; sam_host = NM/MD + SAM text; deliver = D2H + hand-over (all but upload/deliver are device stages; the names are those of round 1's records)",
+        "finish_kernels_ms_per_step": agg["ms_k_finish"] / K,
         "host_threads": n_threads, "parity": parity,
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):

@@ -27,7 +27,8 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 struct SeqJob;
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
                            bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
-                           void (*before)(void *, bseq1_t **, int *));
+                           char *fq1, int64_t len1, char *fq2, int64_t len2);
+int64_t job_n_reads(SeqJob *j);
 int64_t job_take_sam(SeqJob *j, char **out);
 void process_seqs_end(SeqJob *j, b200_stats_t *stats);
 void last_stats(b200_stats_t *out);
@@ -405,7 +406,7 @@ b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, cons
 {
 	b200_job *j = new b200_job();
 	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
-	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr);
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0);
 	return j;
 }
 
@@ -424,7 +425,7 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->n_threads = opt->n_threads;
 	// the chunk's text comes back from the device as one buffer (no malloc per read)
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true, nullptr);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true, nullptr, 0, nullptr, 0);
 	return j;
 }
 
@@ -433,18 +434,10 @@ b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	b200_job *j = new b200_job();
 	j->total = 0; j->seqs = nullptr; j->sam = nullptr; j->sam_len = 0; j->n_threads = opt->n_threads;
 	j->fq[0] = fq1; j->fq[1] = fq2; j->fq_len[0] = len1; j->fq_len[1] = len2; j->mate[0] = j->mate[1] = nullptr;
+	// the job thread uploads the raw bytes; the device parses, interleaves and encodes them (fastq_kernels.h)
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, 0, nullptr, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true,
-		[](void *p, bseq1_t **seqs, int *n) {
-			b200_job *x = (b200_job *)p;
-			const int64_t n1 = b200_fastq_parse(x->fq[0], x->fq_len[0], &x->mate[0]);
-			const int64_t n2 = x->fq[1] ? b200_fastq_parse(x->fq[1], x->fq_len[1], &x->mate[1]) : n1;
-			if (n1 != n2) { fprintf(stderr, "[mpibwa_b200] the two fastq buffers hold different numbers of reads\n"); abort(); }
-			x->total = x->fq[1] ? 2 * n1 : n1;
-			x->seqs = b200_chunk_seqs(n1, x->mate[0], x->mate[1]);
-			free(x->mate[0]); free(x->mate[1]); x->mate[0] = x->mate[1] = nullptr;
-			*seqs = x->seqs; *n = (int)x->total;
-		});
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); x->total = job_n_reads(self); }, j, true,
+		fq1, len1, fq2, fq2 ? len2 : 0);
 	return j;
 }
 

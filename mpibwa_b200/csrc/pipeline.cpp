@@ -69,7 +69,13 @@ private:
 	bool held_ = false;
 };
 static DeviceTurn g_gpu_turn;
-struct DeviceTurnGuard { uint64_t t; explicit DeviceTurnGuard(uint64_t t_) : t(t_) { g_gpu_turn.lock(t); } ~DeviceTurnGuard() { g_gpu_turn.unlock(); } };
+// B200_TURN=0: no serialisation - the stages of the chunks in flight share the device stream against stream
+static const bool g_turn_on = !(getenv("B200_TURN") && atoi(getenv("B200_TURN")) == 0);
+struct DeviceTurnGuard {
+	uint64_t t;
+	explicit DeviceTurnGuard(uint64_t t_) : t(t_) { if (g_turn_on) g_gpu_turn.lock(t); }
+	~DeviceTurnGuard() { if (g_turn_on) g_gpu_turn.unlock(); }
+};
 
 // engine of the single-job C wrappers (ksw_extend2, bwt_sa, ... in capi.cpp): a clone of its own, so that those calls never
 // touch the resident reads, scratch buffers or counters of a chunk job; serialised by g_aux_mu and the device turn (AuxGuard)
@@ -302,16 +308,20 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 // where the SAM text of the chunk goes: seqs[i].sam (mem_process_seqs' contract: one malloc()ed string per read) or ONE buffer
 // from the recycling pool of b200_big_alloc (b200_align_chunk / _fastq: the caller wants the chunk's text, not 667 k strings)
 struct SamDest { bool one_buffer = false; char *sam = nullptr; int64_t sam_len = 0; };
+// the chunk as raw fastq bytes (b200_align_fastq_begin): parsed on the device; seqs == null then
+struct FastqSrc { char *fq[2]; int64_t len[2]; };
+extern "C" int64_t b200_fastq_parse(char *buf, int64_t len, bseq1_t **out);
+extern "C" bseq1_t *b200_chunk_seqs(int64_t n, const bseq1_t *s1, const bseq1_t *s2);
 
 extern "C" void *b200_big_alloc(size_t bytes);
 
 static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                               int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
-                              int slot, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamDest *dest, uint64_t ticket)
+                              int slot, bool staged, int64_t staged_bases, b200_stats_t *stats_out, SamDest *dest, uint64_t ticket,
+                              const FastqSrc *fq = nullptr, int64_t *n_out = nullptr)
 {
 	engine_for(bwt, bns, pac);
-	const Lane L = { engine_lane(slot, 0), 0, n };
-	Engine *eng = L.eng;
+	Engine *eng = engine_lane(slot, 0);
 	Stats &st = engine_stats(eng);
 	memset(static_cast<b200_stats_t *>(&st), 0, sizeof(b200_stats_t));
 	const int nt = opt->n_threads > 0 ? opt->n_threads : 1;
@@ -319,9 +329,31 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	const int64_t l_pac = bns->l_pac;
 	double t0 = now_ms(), t1;
 
-	// ---- encode (reference src/bwamem.c:1057-1058), flatten and upload reads and their text - unless b200_stage_reads() already did
-	if (!staged) st.n_bases = stage_lane_reads(opt, L, seqs);            // (own stream and buffers: no need to hold the device)
-	else st.n_bases = staged_bases;
+	// ---- the reads: raw fastq bytes parsed, interleaved and encoded on the device, or bseq1_t records encoded here (reference
+	// src/bwamem.c:1057-1058) and uploaded with their text - unless b200_stage_reads() already did.  (Own stream and buffers: no
+	// need to hold the device.)
+	bseq1_t *own_seqs = nullptr;
+	int max_len = -1;
+	if (fq) {
+		FastqInfo fi;
+		stage_upload_fastq(eng, fq->fq[0], fq->len[0], fq->fq[1], fq->len[1], &fi);
+		n = fi.n_reads; st.n_bases = fi.n_bases; max_len = fi.max_len;
+		if (max_len >= opt->min_seed_len && seed_sw_filter_applies(opt, max_len)) {
+			// reads long enough for mem_flt_chained_seeds take the host chaining, which works on bseq1_t records: parse here after all
+			bseq1_t *m[2] = { nullptr, nullptr };
+			const int64_t n1 = b200_fastq_parse(fq->fq[0], fq->len[0], &m[0]);
+			if (fq->fq[1]) b200_fastq_parse(fq->fq[1], fq->len[1], &m[1]);
+			seqs = own_seqs = b200_chunk_seqs(n1, m[0], m[1]);
+			free(m[0]); free(m[1]);
+			fq = nullptr;
+		}
+		if (n_out) *n_out = n;
+	}
+	const Lane L = { eng, 0, n };
+	if (!fq) {
+		if (!staged) st.n_bases = stage_lane_reads(opt, L, seqs);
+		else st.n_bases = staged_bases;
+	}
 	st.n_reads = n;
 	t1 = now_ms(); st.ms_upload = t1 - t0; t0 = t1;
 
@@ -329,7 +361,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	bool dev_chain = !(getenv("B200_CHAIN") && !strcmp(getenv("B200_CHAIN"), "host"));
 	{
 		std::vector<int8_t> len_rule(4096, 0);
-		for (int i = 0; i < n && dev_chain; ++i) {
+		for (int i = 0; i < n && dev_chain && seqs; ++i) {
 			const int l = seqs[i].l_seq;
 			if (l < opt->min_seed_len) continue;
 			int8_t rule = l < 4096 ? len_rule[l] : 0;
@@ -522,6 +554,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 			}
 		});
 	}
+	free(own_seqs);
 	st.ms_deliver += now_ms() - t0;
 	st.ms_total = now_ms() - t_start;
 	if (bwa_verbose >= 3)
@@ -540,7 +573,9 @@ struct SeqJob {
 	std::thread th;
 	b200_stats_t stats;
 	SamDest dest;
+	int64_t n_reads = 0;       // (fastq jobs: known once the device has parsed the bytes)
 };
+int64_t job_n_reads(SeqJob *j) { return j->n_reads; }
 
 // the chunk's SAM text of a finished one-buffer job (from b200_big_alloc: release with b200_free)
 int64_t job_take_sam(SeqJob *j, char **out)
@@ -553,7 +588,7 @@ int64_t job_take_sam(SeqJob *j, char **out)
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
                            void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
-                           void (*before)(void *, bseq1_t **, int *))
+                           char *fq1, int64_t len1, char *fq2, int64_t len2)
 {
 	engine_for(bwt, bns, pac);
 	SeqJob *j = new SeqJob();
@@ -574,9 +609,7 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 	const mem_pestat_t *pes = pes0;
 	j->th = std::thread([=]() {
 		static const int limit = getenv("B200_INFLIGHT") ? std::max(1, atoi(getenv("B200_INFLIGHT"))) : 4;
-		bseq1_t *seqs_ = seqs;
-		int n_ = n;
-		if (before) before(arg, &seqs_, &n_);     // (b200_align_fastq_begin: parse + interleave on the job thread, before the job's turn)
+		const FastqSrc fqs = { { fq1, fq2 }, { len1, len2 } };
 		{
 			std::unique_lock<std::mutex> lk(g_slot_mu);
 			g_slot_cv.wait(lk, [&] { return ticket == g_ticket_serving && g_running < limit; });
@@ -584,7 +617,8 @@ SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_
 			g_slot_cv.notify_all();
 		}
 		j->dest.one_buffer = one_buffer;
-		process_seqs_slot(opt, bwt, bns, pac, n_processed, n_, seqs_, pes, slot, staged, staged_bases, &j->stats, &j->dest, ticket);
+		process_seqs_slot(opt, bwt, bns, pac, n_processed, n, seqs, pes, slot, staged, staged_bases, &j->stats, &j->dest, ticket,
+		                  fq1 ? &fqs : nullptr, &j->n_reads);
 		if (after) after(arg, j);
 		{
 			std::lock_guard<std::mutex> lk(g_slot_mu);
@@ -605,7 +639,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0), nullptr);
 }
 
 } // namespace b200

@@ -14,6 +14,7 @@
 #include "global_kernels.h"
 #include "chain_kernels.h"
 #include "finish_kernels.h"
+#include "fastq_kernels.h"
 
 namespace b200 {
 
@@ -54,6 +55,11 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in);
 // host copy of the regions of the last stage_extend call (the single-job mem_chain2aln wrapper; PIN_REGS / PIN_REG_OFF slots)
 struct ExtRegs { const DReg *regs; const int64_t *reg_off; };
 void stage_extend_download(Engine *e, ExtRegs &out);
+
+// the chunk straight from its raw fastq bytes (fastq_kernels.h): uploaded once, parsed, interleaved and encoded on the device;
+// replaces stage_upload_reads + stage_upload_text.  fq2 == null: single-end.  Aborts when the files hold different record counts.
+struct FastqInfo { int n_reads; int64_t n_bases; int max_len; };
+void stage_upload_fastq(Engine *e, const char *fq1, int64_t len1, const char *fq2, int64_t len2, FastqInfo *info);
 
 // names, qualities and comments of the batch's reads (for the SAM text): rtext[r] holds offsets into text[0..bytes)
 void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes);

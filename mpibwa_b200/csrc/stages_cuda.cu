@@ -1493,6 +1493,101 @@ static double fin_clock_ms()
 	return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
 }
 
+struct IsNewline { const char *t; __device__ bool operator()(int64_t i) const { return t[i] == '\n'; } };
+__global__ void __launch_bounds__(256) k_count_newlines(const char *__restrict__ t, int64_t n, unsigned long long *out)
+{
+	long long c = 0;
+	for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) c += t[i] == '\n';
+	warp_add(out, c);
+}
+struct FastqReadTask {
+	FastqView v; ReadText *rt; int64_t *seq_at; int32_t *len, *ctr;
+	B200_HD void operator()(int64_t r) const
+	{
+		int32_t l;
+		fastq_read(v, r, &rt[r], &seq_at[r], &l);
+		len[r] = l;
+		FIN_ATOMIC_MAX(ctr, l);
+	}
+};
+// one warp per read: the bases of its sequence line -> codes at the read's offset
+__global__ void __launch_bounds__(256) k_fastq_encode(int n, const char *__restrict__ text, const int64_t *__restrict__ seq_at, const int64_t *__restrict__ off, uint8_t *codes)
+{
+	const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (w >= n) return;
+	const int lane = threadIdx.x & 31;
+	const int64_t o = off[w], s = seq_at[w];
+	const int l = (int)(off[w + 1] - o);
+	for (int j = lane; j < l; j += 32) codes[o + j] = fq_code((uint8_t)text[s + j]);
+}
+
+void stage_upload_fastq(Engine *e, const char *fq1, int64_t len1, const char *fq2, int64_t len2, FastqInfo *info)
+{
+	CK(cudaSetDevice(e->device));
+	const int paired = fq2 != nullptr;
+	if (!paired) len2 = 0;
+	char *text = e->d_text.as<char>((size_t)(len1 + len2) + 16);
+	// page-locked buffers (b200_big_alloc, cudaHostRegister) go straight to the copy engine; pageable ones through the driver's staging
+	e->h2d(text, fq1, (size_t)len1);
+	if (paired) e->h2d(text + len1, fq2, (size_t)len2);
+	CudaBK bk = { e };
+	int32_t *ctr = e->fb[FB_CTR].as<int32_t>(64);
+	CK(cudaMemsetAsync(ctr, 0, 64 * sizeof(int32_t), e->stream));
+	int64_t *nl[2] = { nullptr, nullptr };
+	int64_t n_lines[2] = { 0, 0 };
+	const int64_t len[2] = { len1, len2 }, base[2] = { 0, len1 };
+	for (int f = 0; f < 1 + paired; ++f) {          // count the line ends first: the list is sized exactly, whatever the bytes are
+		k_count_newlines<<<148 * 8, 256, 0, e->stream>>>(text + base[f], len[f], (unsigned long long *)(ctr + 16 + 2 * f));
+		CK(cudaGetLastError());
+	}
+	int64_t h_cnt[2];
+	e->d2h(h_cnt, ctr + 16, sizeof h_cnt);
+	e->sync();
+	for (int f = 0; f < 1 + paired; ++f) {
+		nl[f] = e->fb[f ? FB_GSEL2 : FB_GSEL].as<int64_t>((size_t)h_cnt[f] + 16);
+		int64_t *d_n = (int64_t *)(ctr + 8 + 2 * f);
+		cub::CountingInputIterator<int64_t> it(0);
+		IsNewline pred = { text + base[f] };
+		size_t tmp = 0;
+		CK(cub::DeviceSelect::If(nullptr, tmp, it, nl[f], d_n, len[f], pred, e->stream));
+		void *d = e->b_cub.need(tmp);
+		CK(cub::DeviceSelect::If(d, tmp, it, nl[f], d_n, len[f], pred, e->stream));
+		e->stats.n_launches += 2;
+	}
+	int64_t h_n[2];
+	e->d2h(h_n, ctr + 8, sizeof h_n);
+	e->sync();
+	n_lines[0] = h_n[0]; n_lines[1] = h_n[1];
+	const int64_t n_rec = n_lines[0] >> 2;                    // an unfinished record at the end is dropped, as the hosts' loop does
+	if (paired && (n_lines[1] >> 2) != n_rec) die("the two fastq buffers hold different numbers of reads");
+	const int64_t n = paired ? 2 * n_rec : n_rec;
+	if (n > 0x7fffffff) die("too many reads in one chunk");
+	e->n_reads = (int)n;
+	ReadText *rt = e->d_rtext.as<ReadText>(n + 1);
+	int64_t *seq_at = e->fb[FB_O_Z].as<int64_t>(n + 1);
+	int32_t *l_seq = e->fb[FB_LEN].as<int32_t>(n + 1);
+	int64_t *off = e->d_off.as<int64_t>(n + 1);
+	FastqView v = { text, { nl[0], nl[1] }, { base[0], base[1] }, paired };
+	bk.run(n, FastqReadTask{ v, rt, seq_at, l_seq, ctr });
+	CK(cudaMemsetAsync(l_seq + n, 0, sizeof(int32_t), e->stream));
+	exclusive_scan(e, l_seq, off, n + 1);
+	int64_t total = 0;
+	int32_t max_len = 0;
+	e->d2h(&total, off + n, sizeof total);
+	e->d2h(&max_len, ctr, sizeof max_len);
+	e->sync();
+	uint8_t *codes = e->d_codes.as<uint8_t>((size_t)total + 16);
+	if (n > 0) {
+		k_fastq_encode<<<grid_for(n * 32, 256), 256, 0, e->stream>>>((int)n, text, seq_at, off, codes);
+		CK(cudaGetLastError());
+		e->stats.n_launches += 1;
+	}
+	e->sync();
+	e->max_len = max_len;
+	e->h_off.clear();
+	info->n_reads = (int)n; info->n_bases = total; info->max_len = max_len;
+}
+
 void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes)
 {
 	CK(cudaSetDevice(e->device));

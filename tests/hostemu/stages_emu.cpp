@@ -109,6 +109,37 @@ void stage_upload_reads(Engine *e, int n_reads, const int64_t *off, const uint8_
 	for (int i = 0; i < n_reads; ++i) e->max_len = std::max(e->max_len, (int)(off[i + 1] - off[i]));
 }
 
+void stage_upload_fastq(Engine *e, const char *fq1, int64_t len1, const char *fq2, int64_t len2, FastqInfo *info)
+{
+	const int paired = fq2 != nullptr;
+	if (!paired) len2 = 0;
+	e->text.assign(fq1, fq1 + len1);
+	if (paired) e->text.insert(e->text.end(), fq2, fq2 + len2);
+	std::vector<int64_t> nl[2];
+	const int64_t len[2] = { len1, len2 }, base[2] = { 0, len1 };
+	for (int f = 0; f < 1 + paired; ++f)
+		for (int64_t i = 0; i < len[f]; ++i) if (e->text[base[f] + i] == '\n') nl[f].push_back(i);
+	const int64_t n_rec = (int64_t)nl[0].size() >> 2;
+	if (paired && ((int64_t)nl[1].size() >> 2) != n_rec) { fprintf(stderr, "[mpibwa_b200] the two fastq buffers hold different numbers of reads\n"); abort(); }
+	const int64_t n = paired ? 2 * n_rec : n_rec;
+	e->n_reads = (int)n;
+	e->rtext.assign(n + 1, ReadText());
+	e->off.assign(n + 1, 0);
+	std::vector<int64_t> seq_at(n + 1);
+	FastqView v = { e->text.data(), { nl[0].data(), nl[1].data() }, { base[0], base[1] }, paired };
+	e->max_len = 0;
+	for (int64_t r = 0; r < n; ++r) {
+		int32_t l;
+		fastq_read(v, r, &e->rtext[r], &seq_at[r], &l);
+		e->off[r + 1] = e->off[r] + l;
+		e->max_len = std::max(e->max_len, (int)l);
+	}
+	e->codes.assign(e->off[n] + 8, 0);
+	for (int64_t r = 0; r < n; ++r)
+		for (int64_t j = 0; j < e->off[r + 1] - e->off[r]; ++j) e->codes[e->off[r] + j] = fq_code((uint8_t)e->text[seq_at[r] + j]);
+	info->n_reads = (int)n; info->n_bases = e->off[n]; info->max_len = e->max_len;
+}
+
 void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes)
 {
 	e->rtext.assign(rtext, rtext + n_reads);

@@ -67,6 +67,8 @@ def test_chunk_jobs_give_the_same_sam(hostemu_built, examples, tmp_path, shape):
     assert r.stdout == want and want.count(b"\n") > 2000
     # -C: b200_align_chunk (the chunk's text comes back as one buffer instead of seqs[i].sam)
     assert subprocess.run([drv, "-C", "-t", "4"] + args, capture_output=True, check=True).stdout == want
+    # -F: b200_align_fastq_begin (the chunk goes in as raw fastq bytes: parsed, interleaved and encoded by the fastq stage)
+    assert subprocess.run([drv, "-F", "-t", "4"] + args, capture_output=True, check=True).stdout == want
 
 
 def test_occ_sectors_beyond_32_bits(hostemu_built):

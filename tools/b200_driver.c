@@ -106,13 +106,14 @@ int main(int argc, char **argv)
 	mem_pestat_t pes_fixed[4], *pes0 = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THPCv:r:n:d:o:I:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THPCFv:r:n:d:o:I:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
 		else if (c == 'H') header = 1;
 		else if (c == 'P') pipelined = 1;
 		else if (c == 'C') pipelined = 2;     /* b200_align_chunk: the library interleaves the mates and returns one SAM buffer */
+		else if (c == 'F') pipelined = 3;     /* b200_align_fastq_begin: the chunk goes in as raw fastq bytes (parsed on the device) */
 		else if (c == 'v') bwa_verbose = atoi(optarg);
 		else if (c == 'r') rank = atoi(optarg);
 		else if (c == 'n') nranks = atoi(optarg);
@@ -136,10 +137,16 @@ int main(int argc, char **argv)
 	if (!idx) return 1;
 	b200_gpu_init(idx, device);
 	size_t l1, l2 = 0, n1, n2 = 0, i;
-	char *b1 = slurp(argv[optind+1], &l1), *b2 = 0;
+	char *b1 = slurp(argv[optind+1], &l1), *b2 = 0, *raw1 = 0, *raw2 = 0;
 	bseq1_t *s1, *s2 = 0;
+	if (pipelined == 3) { raw1 = malloc(l1 + 1); memcpy(raw1, b1, l1 + 1); }       /* the parse below is in place: keep the bytes */
 	n1 = parse_fastq(b1, l1, &s1);
-	if (paired) { b2 = slurp(argv[optind+2], &l2); n2 = parse_fastq(b2, l2, &s2); if (n1 != n2) { fprintf(stderr, "unequal read counts\n"); return 1; } }
+	if (paired) {
+		b2 = slurp(argv[optind+2], &l2);
+		if (pipelined == 3) { raw2 = malloc(l2 + 1); memcpy(raw2, b2, l2 + 1); }
+		n2 = parse_fastq(b2, l2, &s2);
+		if (n1 != n2) { fprintf(stderr, "unequal read counts\n"); return 1; }
+	}
 	if (header && rank == 0)
 		for (i = 0; i < (size_t)idx->bns->n_seqs; ++i)
 			printf("@SQ\tSN:%s\tLN:%d\n", idx->bns->anns[i].name, idx->bns->anns[i].len);
@@ -163,7 +170,16 @@ int main(int argc, char **argv)
 					if (paired) seqs[n++] = s2[k];
 				}
 				double t0 = now();
-				if (pipelined == 2) {
+				if (pipelined == 3) {
+					/* byte range of the chunk's records in either file: from the '@' of its first record to the '@' of the next chunk's */
+					size_t o1 = (size_t)(s1[beg].name - 1 - b1), e1 = i + 1 < n1 ? (size_t)(s1[i + 1].name - 1 - b1) : l1;
+					size_t o2 = paired ? (size_t)(s2[beg].name - 1 - b2) : 0, e2 = paired ? (i + 1 < n1 ? (size_t)(s2[i + 1].name - 1 - b2) : l2) : 0;
+					char *sam = 0; int64_t sam_len = 0;
+					b200_job_t *job = b200_align_fastq_begin(opt, idx, trimmed ? n_processed : 0, raw1 + o1, (int64_t)(e1 - o1), paired ? raw2 + o2 : 0, (int64_t)(e2 - o2));
+					n = (size_t)b200_align_chunk_end(job, &sam, &sam_len, 0);
+					fwrite(sam, 1, (size_t)sam_len, stdout);
+					b200_free(sam);
+				} else if (pipelined == 2) {
 					char *sam = 0; int64_t sam_len = 0;
 					n = (size_t)b200_align_chunk(opt, idx, trimmed ? n_processed : 0, (int64_t)(i - beg + 1), s1 + beg, paired ? s2 + beg : 0, &sam, &sam_len);
 					fwrite(sam, 1, (size_t)sam_len, stdout);

@@ -36,21 +36,36 @@ namespace b200 {
 
 static void die(const char *msg) { fprintf(stderr, "[mpibwa_b200] %s\n", msg); abort(); }
 
-// growable device buffer
+// Growable device buffer of an engine.  Growth is stream-ordered (cudaMallocAsync / cudaFreeAsync on the engine's stream, pool
+// memory kept cached): a chunk that needs a larger scratch buffer does not synchronise the device under the other chunks in flight,
+// which cudaFree would.  Every buffer registers with the engine under construction (EngineBufs), which binds the stream.
+struct DevBuf;
+static thread_local std::vector<DevBuf *> *tl_buf_registry = nullptr;
 struct DevBuf {
 	void *p = nullptr; size_t cap = 0;
+	cudaStream_t st = nullptr; bool bound = false;
+	DevBuf() { if (tl_buf_registry) tl_buf_registry->push_back(this); }
 	void *need(size_t bytes)
 	{
 		if (bytes > cap) {
-			if (p) CK(cudaFree(p));
 			size_t n = bytes + (bytes >> 2) + 256;
-			CK(cudaMalloc(&p, n));
+			if (bound) {
+				if (p) CK(cudaFreeAsync(p, st));
+				CK(cudaMallocAsync(&p, n, st));
+			} else {
+				if (p) CK(cudaFree(p));
+				CK(cudaMalloc(&p, n));
+			}
 			cap = n;
 		}
 		return p;
 	}
 	template <class T> T *as(size_t n) { return (T *)need(n * sizeof(T)); }
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (p) { if (bound) cudaFreeAsync(p, st); else cudaFree(p); } p = nullptr; cap = 0; }
+};
+struct EngineBufs {         // base of Engine: constructed before the members, so that their constructors find the registry
+	std::vector<DevBuf *> all_bufs;
+	EngineBufs() { tl_buf_registry = &all_bufs; }
 };
 
 // growable page-locked host buffer (results that the host threads read right after a D2H copy)
@@ -72,8 +87,9 @@ struct PinBuf {
 
 struct Counters { unsigned long long occ_blocks, sa_steps, ext_cells, ext_calls, sw_cells, global_cells; };
 
-class Engine {
+class Engine : public EngineBufs {
 public:
+	Engine() { tl_buf_registry = nullptr; }
 	int device = 0;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -270,6 +286,13 @@ static void engine_set_l2_window(Engine *e)
 static void engine_make_streams(Engine *e)
 {
 	CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+	{	// scratch comes from the device's default memory pool and stays cached there
+		cudaMemPool_t mp;
+		CK(cudaDeviceGetDefaultMemPool(&mp, e->device));
+		uint64_t keep = ~0ull;
+		CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
+		for (DevBuf *b : e->all_bufs) { b->st = e->stream; b->bound = true; }
+	}
 	CK(cudaEventCreate(&e->ev0));
 	CK(cudaEventCreate(&e->ev1));
 	CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
@@ -299,17 +322,11 @@ void engine_destroy(Engine *e)
 	if (!e) return;
 	cudaSetDevice(e->device);
 	cudaStreamSynchronize(e->stream);
-	DevBuf *bufs[] = { &e->d_off, &e->d_codes, &e->b_intv, &e->b_scr, &e->b_nintv, &e->b_ioff, &e->b_civ, &e->b_slots, &e->b_soff,
-		&e->b_seeds, &e->b_lrep, &e->b_seedoff, &e->b_cub, &e->b_wide, &e->b_chain_off, &e->b_chains, &e->b_dseeds, &e->b_srt, &e->b_regs,
-		&e->b_nregs, &e->b_eh, &e->b_xstate, &e->b_xjobs, &e->b_xact0, &e->b_xact1, &e->b_xkey, &e->b_xkey2, &e->b_xord, &e->b_xctr, &e->b_xout, &e->b_jobs, &e->b_res, &e->b_h, &e->b_e, &e->b_b, &e->b_q, &e->b_t };
-	for (DevBuf *b : bufs) b->release();
+	for (DevBuf *b : e->all_bufs) b->release();
+	cudaStreamSynchronize(e->stream);
 	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release();
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
-	e->b_grow.release();
-	for (int i = 0; i < FB_N; ++i) e->fb[i].release();
-	e->d_rtext.release(); e->d_text.release(); e->h_sam.release(); e->h_sam_off.release();
-	e->b_strips.release(); e->b_nfirst.release(); e->b_nsweeps.release();
-	e->b_xrec.release(); e->b_chscr.release(); e->b_chnodes.release(); e->b_chnc.release(); e->b_chns.release(); e->b_chcoff.release(); e->b_chsoff.release();
+	e->h_sam.release(); e->h_sam_off.release();
 	if (e->owns_index) {
 		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
 		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab);
@@ -1421,12 +1438,12 @@ struct CudaBK {
 	{
 		DevBuf &b = e->fb[id];
 		if (n * sizeof(T) <= b.cap) return (T *)b.p;
-		DevBuf nb;
-		nb.need(n * sizeof(T));
-		if (keep) CK(cudaMemcpyAsync(nb.p, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, e->stream));
-		e->sync();
-		b.release();
-		b = nb;
+		void *q = nullptr;
+		const size_t cap = n * sizeof(T) + (n * sizeof(T) >> 2) + 256;
+		CK(cudaMallocAsync(&q, cap, e->stream));
+		if (keep) CK(cudaMemcpyAsync(q, b.p, keep * sizeof(T), cudaMemcpyDeviceToDevice, e->stream));
+		if (b.p) CK(cudaFreeAsync(b.p, e->stream));
+		b.p = q; b.cap = cap;
 		return (T *)b.p;
 	}
 	template <class TASK> void run(int64_t n, const TASK &t)

@@ -417,7 +417,7 @@ def main():
 
     def resident_group(first, count, ev0, ev1, on_stats=None):
         """`count` (<= N_SLOTS) chunks parsed, encoded and resident in HBM before the timed region, then aligned as chunk
-        jobs (two in flight); SAM left in seqs[i].sam"""
+        jobs (b200_align_seqs_begin: mem_process_seqs with the chunk's SAM text as one buffer)"""
         held = []
         for s in range(count):
             a1, a2, n = chunk_bytes(first + s)
@@ -429,18 +429,21 @@ def main():
         flush_buf.add_(1)
         torch.cuda.synchronize()
         ev0.record()
-        jobs = [lib.b200_process_seqs_begin(al.opt, al.idx.contents.bwt, al.idx.contents.bns, al.idx.contents.pac, 0, 2 * m1, seqs, None)
-                for seqs, p1, p2, m1, n in held]
+        jobs = [lib.b200_align_seqs_begin(al.opt, al.idx, 0, 2 * m1, seqs, None) for seqs, p1, p2, m1, n in held]
         st = M.b200_stats_t()
+        sams = []
         for j in jobs:
-            lib.b200_process_seqs_end(j, C.byref(st))
+            sam, sam_len = C.c_void_p(), C.c_int64()
+            lib.b200_align_chunk_end(j, C.byref(sam), C.byref(sam_len), C.byref(st))
+            sams.append(sam)
             if on_stats:
                 on_stats(st.as_dict())
         ev1.record()
         torch.cuda.synchronize()
         pairs = 0
+        for sam in sams:
+            lib.b200_free(sam)
         for seqs, p1, p2, m1, n in held:
-            lib.b200_collect_sam(2 * m1, seqs, None)
             lib.b200_free(seqs); lib.b200_free(p1); lib.b200_free(p2)
             pairs += n
         return pairs, ev0.elapsed_time(ev1)
@@ -579,7 +582,7 @@ def main():
         "metric": "aligned 2x150bp read pairs/sec", "value": res_pairs_all / (res_ms_max * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": workload_config(args, "mem_process_seqs through the C ABI of libmpibwa_b200.so (ctypes), %d host threads per rank" % n_threads),
+        "config": workload_config(args, "mem_process_seqs in its chunk-job form (b200_align_seqs_begin / b200_align_fastq_begin + b200_align_chunk_end) through the C ABI of libmpibwa_b200.so (ctypes), %d host threads per rank" % n_threads),
         "e2e": {"value": e2e_pairs_all / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "sam_bytes_per_step": sam_bytes // args.steps, "wall_ms_rank0": wall_ms},
         "gpu_launches": int(agg["n_launches"]), "clocks": clocks, "roofline": roof, "kernels": kern,

@@ -333,6 +333,9 @@ b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, cons
 void b200_process_seqs_end(b200_job_t *job, b200_stats_t *stats /* may be NULL */);
 b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int64_t n, bseq1_t *s1, bseq1_t *s2);
 int64_t b200_align_chunk_end(b200_job_t *job, char **sam, int64_t *sam_len, b200_stats_t *stats /* may be NULL */);
+/* the same over an interleaved array (mates 2i, 2i+1; what mem_process_seqs takes - and what b200_stage_reads made resident):
+ * the chunk's SAM text comes back as ONE buffer from b200_align_chunk_end instead of one malloc()ed string per read */
+b200_job_t *b200_align_seqs_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0);
 /* the same from the raw fastq bytes of the chunk (one buffer per mate file, fq2 NULL for single-end; parsed IN PLACE by the job
  * thread, so begin() returns at once and the buffers must stay untouched until end()); finish with b200_align_chunk_end */
 b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, char *fq1, int64_t len1, char *fq2, int64_t len2);

@@ -142,6 +142,7 @@ _PROTOTYPES = {
     "b200_process_seqs_end": (None, [C.c_void_p, C.POINTER(b200_stats_t)]),
     "b200_align_chunk_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int64, C.POINTER(bseq1_t),
                                             C.POINTER(bseq1_t)]),
+    "b200_align_seqs_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int, C.POINTER(bseq1_t), C.c_void_p]),
     "b200_align_fastq_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "b200_align_chunk_end": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(b200_stats_t)]),
     "b200_free": (None, [C.c_void_p]),

@@ -429,6 +429,15 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	return j;
 }
 
+b200_job_t *b200_align_seqs_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
+{
+	b200_job *j = new b200_job();
+	j->total = n; j->seqs = nullptr; j->sam = nullptr; j->sam_len = 0; j->n_threads = opt->n_threads;
+	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, n, seqs, pes0,
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); }, j, true, nullptr, 0, nullptr, 0);
+	return j;
+}
+
 b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, char *fq1, int64_t len1, char *fq2, int64_t len2)
 {
 	b200_job *j = new b200_job();

@@ -92,7 +92,7 @@ public:
 	Engine() { tl_buf_registry = nullptr; }
 	int device = 0;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+	cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;   // ev_sync: blocking-sync event (host threads sleep instead of spinning)
 	FmView fm;                     // device pointers
 	void *d_bwt = nullptr, *d_sa = nullptr, *d_pac = nullptr, *d_ctg_off = nullptr, *d_ctg_len = nullptr, *d_ctg_alt = nullptr;
 	bool seeds_resident = false;   // the seed list of the whole batch is still in b_seeds / b_seedoff / b_lrep
@@ -151,7 +151,9 @@ public:
 		CK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, stream));
 		stats.d2h_bytes += (int64_t)n;
 	}
-	void sync() { CK(cudaStreamSynchronize(stream)); }
+	// waits for the stream without spinning: with several chunk jobs per process and one process per GPU the job threads outnumber
+	// the cores a rank has, and a spinning waiter takes the core the next chunk's launches need
+	void sync() { CK(cudaEventRecord(ev_sync, stream)); CK(cudaEventSynchronize(ev_sync)); }
 	void zero_counters() { CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), stream)); }
 	Counters read_counters()
 	{
@@ -293,8 +295,9 @@ static void engine_make_streams(Engine *e)
 		CK(cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &keep));
 		for (DevBuf *b : e->all_bufs) { b->st = e->stream; b->bound = true; }
 	}
-	CK(cudaEventCreate(&e->ev0));
-	CK(cudaEventCreate(&e->ev1));
+	CK(cudaEventCreateWithFlags(&e->ev0, cudaEventBlockingSync));
+	CK(cudaEventCreateWithFlags(&e->ev1, cudaEventBlockingSync));
+	CK(cudaEventCreateWithFlags(&e->ev_sync, cudaEventBlockingSync | cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
 	for (int i = 0; i < Engine::N_SIDE; ++i) { CK(cudaStreamCreateWithFlags(&e->side[i], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming)); }
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
@@ -332,7 +335,7 @@ void engine_destroy(Engine *e)
 		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab);
 	}
 	cudaFree(e->d_cnt);
-	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork);
+	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_sync);
 	for (int i = 0; i < Engine::N_SIDE; ++i) { cudaStreamDestroy(e->side[i]); cudaEventDestroy(e->ev_join[i]); }
 	for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
 	cudaStreamDestroy(e->stream);

@@ -333,7 +333,7 @@ def main():
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     max_pairs = max(e - b for b, e in chunks)
-    N_SLOTS = 4      # chunk slots of the library: that many chunks can be resident ahead of their call
+    N_SLOTS = int(os.environ.get("B200_INFLIGHT", "4"))      # chunks in flight (the library has eight chunk slots and runs B200_INFLIGHT jobs at a time)
     # the in-flight chunks need their own fastq buffers (the parse is in place and the job reads the records later)
     n_buf = N_SLOTS + 1
 
@@ -383,7 +383,7 @@ def main():
         lib.b200_free(sam)
         return n, out_len
 
-    DEPTH = 4        # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
+    DEPTH = N_SLOTS  # chunks the host loop keeps begun ahead of the one it waits for (the library runs B200_INFLIGHT at a time)
 
     def e2e_run(first, count, on_stats=None, raw=None):
         """`count` chunks from fastq bytes in host memory to SAM bytes in host memory as chunk jobs: begin(i), ... end(i - DEPTH + 1).  raw: the chunks' private fastq buffers when they were filled before the timed region."""
@@ -531,15 +531,13 @@ def main():
             nb += mine.n_bytes
         parity = {"chunks": args.parity_chunks, "identical": ident, "sam_bytes": nb,
                   "checked_against": "oracle/_ref/ref_driver (unmodified reference sources) on the same fastq slice, md5 of the SAM records"}
-    # ---- untimed extra pass with the whole chunk as ONE batch per kernel (no sub-batch lanes): kernel-isolated efficiency
-    os.environ["B200_LANES"] = "1"
+    # ---- untimed extra pass: ONE chunk alone on the device - kernel-isolated efficiency
     resident_group(args.warmup + args.steps, 1, ev0, ev1)          # first one grows the device buffers to whole-chunk size
     iso = []
     os.environ["B200_EXT_RECORD"] = "1"            # keep this chunk's ksw_extend2 job list for the one-batch replay below
     resident_group(args.warmup + args.steps + 1, 1, ev0, ev1, iso.append)
     os.environ.pop("B200_EXT_RECORD", None)
     st_iso = iso[0]
-    os.environ.pop("B200_LANES", None)
     # kernel-isolated ksw_extend2 as BASELINE configs[1] words it: the exact job list of the chunk, replayed as one batch
     rp_cells, rp_jobs = C.c_int64(), C.c_int64()
     lib.b200_ext_replay(al.opt, C.byref(rp_cells), C.byref(rp_jobs))          # (warm-up)
@@ -568,16 +566,25 @@ def main():
     i32_peak = int32_peak_gops(torch)
     K = args.steps
     kern = kernel_table(agg, K, i32_peak, hbm_peak)
-    dom = max(kern, key=lambda k: kern[k]["ms_per_step"]) if kern else None
+    kern_iso = kernel_table(st_iso, 1, i32_peak, hbm_peak)
+    # The chunks in flight share the SMs (B200_TURN=0, the default): the CUDA-event duration of a kernel in the timed region includes
+    # the time it spent sharing the device with the kernels of other chunks, so the roofline of the dominant kernel is taken from
+    # the pass that runs ONE chunk alone (same process, same inputs, CUDA events on the launching stream); `kernels` keeps the
+    # timed-region durations.
+    concurrent = os.environ.get("B200_TURN", "0") == "0"
+    src = kern_iso if concurrent else kern
+    dom = max(src, key=lambda k: src[k]["ms_per_step"]) if src else None
     roof = None
     if dom:
-        kd = kern[dom]
+        kd = src[dom]
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
-                "traffic": traffic, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()"}
+                "traffic": traffic, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()",
+                "measured": ("one chunk alone on the device (untimed extra pass of this run; in the timed region up to %d chunks share the SMs "
+                             "and the per-launch durations overlap)" % N_SLOTS) if concurrent else "timed region"}
     line = {
         "metric": "aligned 2x150bp read pairs/sec", "value": res_pairs_all / (res_ms_max * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res_ms_max / args.steps,
@@ -586,12 +593,12 @@ def main():
         "e2e": {"value": e2e_pairs_all / (e2e_ms_max * 1e-3), "unit": "pairs/s", "h2d_bytes_per_step": h2d // args.steps,
                 "d2h_bytes_per_step": d2h // args.steps, "sam_bytes_per_step": sam_bytes // args.steps, "wall_ms_rank0": wall_ms},
         "gpu_launches": int(agg["n_launches"]), "clocks": clocks, "roofline": roof, "kernels": kern,
-        "kernels_isolated": kernel_table(st_iso, 1, i32_peak, hbm_peak),
-        "kernels_note": "roofline/kernels: CUDA-event kernel times inside the timed region (chunk jobs: one whole-chunk batch per kernel, up to four chunks "
-                        "in flight, device stages serialised); kernels_isolated: one extra untimed chunk run alone, the kernel-isolated figures of "
+        "kernels_isolated": kern_iso,
+        "kernels_note": "kernels: CUDA-event kernel times inside the timed region (chunk jobs: one whole-chunk batch per kernel, several chunks "
+                        "in flight sharing the SMs); kernels_isolated / roofline: one extra untimed chunk run alone, the kernel-isolated figures of "
                         "BASELINE configs[1]; ksw_extend2_gcups is the isolated one (DP kernels of all chain2aln rounds of the chunk), "
                         "ksw_extend2_gcups_one_batch / ksw_extend2_replay the same job list replayed as one batch",
-        "ksw_extend2_gcups": kernel_table(st_iso, 1, i32_peak, hbm_peak).get("ksw_extend2", {}).get("gcups"),
+        "ksw_extend2_gcups": kern_iso.get("ksw_extend2", {}).get("gcups"),
         "ksw_extend2_gcups_one_batch": (rp_cells.value / rp_ms / 1e6) if rp_ms > 0 else None,
         "ksw_extend2_replay": {"what": "every ksw_extend2 job of one chunk (recorded from the pipeline) as ONE batch through the DP kernels: no chain2aln rounds "
                                        "in between, so no launch with too few jobs to fill the chip",

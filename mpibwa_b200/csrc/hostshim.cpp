@@ -141,16 +141,18 @@ int64_t b200_collect_sam(int64_t total, bseq1_t *seqs, char **sam)
 // Large result buffers (the SAM text of a chunk: hundreds of MB) are page-locked - the device copies the text straight into them -
 // and recycled instead of returned to the system: pinning and unpinning that much memory per chunk costs milliseconds and a TLB
 // shoot-down on every core of a busy host.  b200_big_alloc() hands out a buffer of at least `bytes`; b200_free() recognises such a
-// buffer and parks it for the next call (at most eight stay parked).
+// buffer and parks it for the next call (at most sixteen stay parked).
 static struct BigPool { std::mutex mu; struct Ent { void *p; size_t cap; bool busy; }; std::vector<Ent> ents; } g_big;
 
 void *b200_big_alloc(size_t bytes)
 {
 	{
 		std::lock_guard<std::mutex> lk(g_big.mu);
-		for (auto &e : g_big.ents) if (!e.busy && e.cap >= bytes) { e.busy = true; return e.p; }
-		for (size_t k = 0; k < g_big.ents.size(); ++k)          // a parked buffer that is too small makes room
-			if (!g_big.ents[k].busy) { b200::stage_host_free(g_big.ents[k].p); g_big.ents.erase(g_big.ents.begin() + k); break; }
+		// best fit among the parked buffers, and never a buffer more than twice the size asked for: the pool serves two very
+		// different sizes (fastq chunks, SAM chunks) and a small request must not walk away with a large buffer
+		BigPool::Ent *best = nullptr;
+		for (auto &e : g_big.ents) if (!e.busy && e.cap >= bytes && e.cap <= 2 * bytes + (1 << 20) && (!best || e.cap < best->cap)) best = &e;
+		if (best) { best->busy = true; return best->p; }
 	}
 	const size_t cap = bytes + (bytes >> 3) + 4096;
 	void *p = b200::stage_host_alloc(cap);
@@ -168,7 +170,7 @@ void b200_free(void *p)
 		for (auto &e : g_big.ents) parked += !e.busy;
 		for (size_t k = 0; k < g_big.ents.size(); ++k)
 			if (g_big.ents[k].p == p) {
-				if (parked >= 8) { b200::stage_host_free(p); g_big.ents.erase(g_big.ents.begin() + k); }
+				if (parked >= 16) { b200::stage_host_free(p); g_big.ents.erase(g_big.ents.begin() + k); }
 				else g_big.ents[k].busy = false;
 				return;
 			}

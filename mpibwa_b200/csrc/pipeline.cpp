@@ -68,13 +68,20 @@ private:
 	std::multiset<uint64_t> waiting_;
 	bool held_ = false;
 };
-static DeviceTurn g_gpu_turn;
-// B200_TURN=0: no serialisation - the stages of the chunks in flight share the device stream against stream
-static const bool g_turn_on = !(getenv("B200_TURN") && atoi(getenv("B200_TURN")) == 0);
+// How the device stages of the chunks in flight share the GPU (B200_TURN):
+//   0 (default)  no serialisation: every chunk job drives its own stream and the kernels of up to B200_INFLIGHT chunks share the
+//                SMs.  The stages are a mix of latency-bound kernels (seeding, SA look-up: half of the issue slots idle) and
+//                launches too small to fill 148 SMs (late extension rounds, rescue, CIGAR retries); interleaved, they fill each
+//                other's holes - measured 8.6 M pairs/s end to end against 7.7 M with one chunk on the device at a time.
+//   1            one turn for everything, handed to the oldest waiting chunk (round 1's behaviour: lowest latency per chunk)
+//   2            two turns: FM-index stages (seeding, SA, chaining) and DP / finish stages - measured 7.8 M
+static DeviceTurn g_gpu_turn[2];
+static const int g_turn_mode = getenv("B200_TURN") ? atoi(getenv("B200_TURN")) : 0;
+enum { TURN_FM = 0, TURN_DP = 1 };
 struct DeviceTurnGuard {
-	uint64_t t;
-	explicit DeviceTurnGuard(uint64_t t_) : t(t_) { if (g_turn_on) g_gpu_turn.lock(t); }
-	~DeviceTurnGuard() { if (g_turn_on) g_gpu_turn.unlock(); }
+	uint64_t t; int k;
+	DeviceTurnGuard(uint64_t t_, int kind) : t(t_), k(g_turn_mode == 2 ? kind : 0) { if (g_turn_mode) g_gpu_turn[k].lock(t); }
+	~DeviceTurnGuard() { if (g_turn_mode) g_gpu_turn[k].unlock(); }
 };
 
 // engine of the single-job C wrappers (ksw_extend2, bwt_sa, ... in capi.cpp): a clone of its own, so that those calls never
@@ -122,7 +129,7 @@ Engine *engine_for(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac)
 }
 
 // engine of lane k of chunk slot `slot` (slot 0, lane 0 is the primary engine; all others are clones sharing its index)
-static const int MAX_LANES = 1, N_SLOTS = 4;
+static const int MAX_LANES = 1, N_SLOTS = 8;
 static Engine *engine_lane(int slot, int k)
 {
 	std::lock_guard<std::mutex> lk(g_mu);
@@ -162,10 +169,14 @@ Engine *aux_acquire()
 		if (g_engines.empty()) { g_aux_mu.unlock(); return nullptr; }
 		if (!g_aux) g_aux = engine_clone(g_engines[0]);
 	}
-	g_gpu_turn.lock(~(uint64_t)0);
+	if (g_turn_mode) { g_gpu_turn[0].lock(~(uint64_t)0); if (g_turn_mode == 2) g_gpu_turn[1].lock(~(uint64_t)0); }
 	return g_aux;
 }
-void aux_release() { g_gpu_turn.unlock(); g_aux_mu.unlock(); }
+void aux_release()
+{
+	if (g_turn_mode) { if (g_turn_mode == 2) g_gpu_turn[1].unlock(); g_gpu_turn[0].unlock(); }
+	g_aux_mu.unlock();
+}
 void last_stats(b200_stats_t *out) { std::lock_guard<std::mutex> lk(g_slot_mu); *out = g_last_stats; }
 
 /* ------------------------------------------------------------------ option packing */
@@ -303,7 +314,7 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 	g_slot_cv.notify_all();
 }
 
-#define GPU_STAGE(call) do { DeviceTurnGuard gpu_lk(ticket); call; } while (0)
+#define GPU_STAGE(kind, call) do { DeviceTurnGuard gpu_lk(ticket, kind); call; } while (0)
 
 // where the SAM text of the chunk goes: seqs[i].sam (mem_process_seqs' contract: one malloc()ed string per read) or ONE buffer
 // from the recycling pool of b200_big_alloc (b200_align_chunk / _fastq: the caller wants the chunk's text, not 667 k strings)
@@ -373,7 +384,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	// ---- seeding on the device
 	SeedOut sd;
 	const bool chain_check = dev_chain && getenv("B200_CHAIN") && !strcmp(getenv("B200_CHAIN"), "check");   // run both, compare, abort on a difference
-	GPU_STAGE(stage_seed(eng, make_seed_opt(opt), sd, dev_chain && !chain_check));
+	GPU_STAGE(TURN_FM, stage_seed(eng, make_seed_opt(opt), sd, dev_chain && !chain_check));
 	t1 = now_ms(); st.ms_seed = t1 - t0; t0 = t1;
 	st.n_seeds = sd.n_seeds;
 
@@ -382,7 +393,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	std::vector<DChain> chk_ch;
 	std::vector<DSeed> chk_se;
 	if (dev_chain) {
-		GPU_STAGE(stage_chain(eng, make_chain_opt(opt), xin, chain_check));
+		GPU_STAGE(TURN_FM, stage_chain(eng, make_chain_opt(opt), xin, chain_check));
 		st.n_chains = xin.n_chains;
 		if (chain_check) {
 			chk_co.assign(xin.chain_off, xin.chain_off + n + 1); chk_ch.assign(xin.chains, xin.chains + xin.n_chains);
@@ -441,7 +452,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 		}
 		if (!jobs.empty()) {
 			std::vector<SwRes> res;
-			GPU_STAGE(stage_sw(eng, make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins), jobs, res));
+			GPU_STAGE(TURN_DP, stage_sw(eng, make_sw_opt(opt->mat, opt->o_del, opt->e_del, opt->o_ins, opt->e_ins), jobs, res));
 			for (size_t x = 0; x < owner.size(); ++x) owner[x]->score = res[x].score;
 		}
 		for (int i : long_reads) {
@@ -528,7 +539,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	t1 = now_ms(); st.ms_chain_host = t1 - t0; t0 = t1;
 
 	// ---- chain2aln / ksw_extend2 on the device; the regions stay there
-	GPU_STAGE(stage_extend(eng, make_ext_opt(opt), xin));
+	GPU_STAGE(TURN_DP, stage_extend(eng, make_ext_opt(opt), xin));
 	t1 = now_ms(); st.ms_extend = t1 - t0; t0 = t1;
 
 	// ---- everything else of mem_process_seqs (reference src/bwamem.c:1073-1085, 1187-1203, 1226-1229): de-duplication,
@@ -537,7 +548,7 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	fa.opt = opt; fa.pes0 = (opt->flag & MEM_F_PE) ? pes0 : nullptr; fa.n_processed = n_processed; fa.rg_id = bwa_rg_id;
 	fa.want_offsets = !dest->one_buffer;
 	fa.alloc = dest->one_buffer ? b200_big_alloc : nullptr;
-	GPU_STAGE(stage_finish(eng, fa));
+	GPU_STAGE(TURN_DP, stage_finish(eng, fa));
 	SamChunk sc;
 	stage_fetch_sam(eng, fa, sc);           // (D2H on the engine's own stream: the next chunk's kernels run meanwhile)
 	t0 = now_ms();

@@ -36,7 +36,7 @@ tools/b200_driver: tools/b200_driver.c $(LIB)
 	$(CC) -O2 -Wall -Iinclude tools/b200_driver.c -o $@ -Lmpibwa_b200 -lmpibwa_b200 -Wl,-rpath,'$$ORIGIN/../mpibwa_b200'
 
 hostemu: tests/_build/libmpibwa_b200_hostemu.so tests/_build/b200_driver_hostemu
-tests/_build/libmpibwa_b200_hostemu.so: $(HOSTSRC) tests/hostemu/stages_emu.cpp $(HDRS)
+tests/_build/libmpibwa_b200_hostemu.so: $(HOSTSRC) tests/hostemu/stages_emu.cpp tests/hostemu/emu_bodies.h $(HDRS)
 	@mkdir -p tests/_build
 	$(CXX) $(CXXFLAGS) -shared -o $@ $(HOSTSRC) tests/hostemu/stages_emu.cpp
 tests/_build/b200_driver_hostemu: tools/b200_driver.c tests/_build/libmpibwa_b200_hostemu.so

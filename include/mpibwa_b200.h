@@ -213,7 +213,10 @@ void mem_process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bn
                       int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0);
 
 /* ------------------------------------------------------------------ inner call surface (single-job wrappers)
- * Same signatures as the reference; each runs as a batch of one on the GPU. */
+ * Same signatures as the reference; each runs as a batch of one on the GPU, on an engine of its own (own stream, scratch and
+ * resident reads: a call never disturbs a chunk job in flight) and one call at a time (they serialise on a mutex), so they may be
+ * called from several threads.  ksw_extend2 requires h0 > 0 and mem_chain2aln an empty region list (both abort otherwise): the
+ * hot path never calls them any other way. */
 
 int ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, int m, const int8_t *mat,
                 int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
@@ -318,6 +321,7 @@ typedef struct {
  * replays them as ONE batch through the DP kernels on the primary engine and returns the time in ms (bench.py; run one chunk alone first) */
 double b200_ext_replay(const mem_opt_t *opt, int64_t *cells, int64_t *n_jobs);
 void b200_get_stats(b200_stats_t *out);   /* counters of the call that finished last */
+void b200_get_aux_stats(b200_stats_t *out); /* running counters of the single-job wrappers and the b200_*_batch calls (their own engine) */
 
 /* Chunk jobs - mem_process_seqs (reference src/bwamem.h:134) split into begin / end so that the host can keep two chunks
  * in flight: begin() returns at once and the chunk is aligned by a library thread; end() waits and leaves the result where

@@ -148,6 +148,7 @@ _PROTOTYPES = {
     "b200_free": (None, [C.c_void_p]),
     "b200_big_alloc": (C.c_void_p, [C.c_size_t]),
     "b200_get_stats": (None, [C.POINTER(b200_stats_t)]),
+    "b200_get_aux_stats": (None, [C.POINTER(b200_stats_t)]),
     "b200_ext_replay": (C.c_double, [C.POINTER(mem_opt_t), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200_int32_peak": (C.c_double, [C.c_int]),
     "b200_int32_peak_dual_pipe": (C.c_double, [C.c_int]),

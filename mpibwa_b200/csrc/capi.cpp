@@ -242,7 +242,7 @@ static bntseq_t *load_bns(const std::string &prefix)
 		p->name = strdup(buf);
 		std::string anno;
 		while ((c = fgetc(fp)) != '\n' && c != EOF) anno.push_back((char)c);
-		if (anno.size() > 1) p->anno = strdup(anno.c_str() + 1);   // skip the leading space
+		if (anno.size() > 1 && anno != " (null)") p->anno = strdup(anno.c_str() + 1);   // skip the leading space (reference src/bntseq.c:131-132)
 		else p->anno = strdup("");
 		n_read = fscanf(fp, "%lld%d%d", &xx, &p->len, &p->n_ambs);
 		if (n_read != 3) die("malformed record", fn.c_str());
@@ -644,9 +644,20 @@ void mem_chain2aln(const mem_opt_t *opt, const bntseq_t *bns, const uint8_t *pac
 
 int bwt_smem1(const bwt_t *bwt, int len, const uint8_t *q, int x, int min_intv, bwtintv_v *mem, bwtintv_v *tmpvec[2])
 {
-	(void)bwt; (void)tmpvec; (void)len; (void)q; (void)x; (void)min_intv; (void)mem;
-	die("bwt_smem1: single-position SMEM queries are served in batches; use b200_collect_intv_batch()", nullptr);
-	return 0;
+	(void)bwt; (void)tmpvec;                  // (the scratch vectors of the reference live on the device here)
+	std::vector<Intv> out;
+	int ret;
+	{ AuxGuard eng; ret = stage_smem1(eng, len, q, x, min_intv < 1 ? 1 : (uint64_t)min_intv, out); }
+	mem->n = 0;
+	if (out.size() > mem->m) { mem->m = out.size(); mem->a = (bwtintv_t *)realloc(mem->a, mem->m * sizeof(bwtintv_t)); }
+	for (const Intv &v : out) { bwtintv_t &o = mem->a[mem->n++]; o.x[0] = v.x0; o.x[1] = v.x1; o.x[2] = v.x2; o.info = v.info; }
+	return ret;
+}
+
+void b200_get_aux_stats(b200_stats_t *out)
+{
+	AuxGuard eng;
+	*out = engine_stats(eng);
 }
 
 } // extern "C"

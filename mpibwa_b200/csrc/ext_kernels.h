@@ -4,9 +4,9 @@
 //                   recurrences of reference src/ksw.c:380-479 (see SURVEY.md A.1 for the rules that bite:
 //                   a zero diagonal cannot restart, gaps open from M, ties in the row maximum go to the larger j,
 //                   stale cells outside the shrinking band keep their old values).
-//   chain2aln_*     the per-seed decision + left/right extension logic of reference src/bwamem.c:632-786,
-//                   restructured so that one device task owns one read and walks its chains and seeds in the
-//                   reference's order (the containment test of seed k needs the regions of the earlier seeds).
+//   chain2aln_need_extension   the per-seed containment test of reference src/bwamem.c:671-706 (the device walks a read's
+//                   chains and seeds in the reference's order in ext_rounds.cuh: the test of seed k needs the regions of
+//                   the earlier seeds).
 //
 // The DP state row is accessed through an accessor object so that the same code runs over shared memory,
 // interleaved global scratch or a plain host array.
@@ -179,94 +179,6 @@ B200_HDN int chain2aln_need_extension(const ExtOpt &o, int l_query, const DChain
 	}
 	if (i == c.n_seeds) { srt[k] = -1; return 0; }
 	return 1;
-}
-
-// Left + right extension of one seed with the band-doubling retry; fills *a.
-template <class EH>
-B200_HDN void chain2aln_extend_seed(const ExtOpt &o, const uint8_t *pac, int64_t l_pac, int l_query, const uint8_t *query,
-                                    const DChain &c, const DSeed *seeds, const DSeed &s, EH eh, DReg *a,
-                                    int64_t *cells, int *n_calls)
-{
-	int aw0 = o.w, aw1 = o.w;
-	a->w = o.w; a->score = a->truesc = -1; a->rid = c.rid;
-	a->qb = a->qe = 0; a->rb = a->re = 0; a->seedcov = 0; a->seedlen0 = 0; a->pad = 0;
-	if (s.qbeg) {
-		ExtOut x; x.score = -1; x.qle = x.tle = x.gtle = 0; x.gscore = -1; x.max_off = 0;
-		int tlen = (int)(s.rbeg - c.rmax0);
-		QRev qa = { query + s.qbeg - 1 };
-		TPacRev ta = { pac, l_pac, s.rbeg - 1 };
-		for (int i = 0; i < 2; ++i) {
-			int prev = a->score;
-			aw0 = o.w << i;
-			extend_core(s.qbeg, qa, tlen, ta, o, aw0, o.pen_clip5, s.len * o.a, eh, &x, cells);
-			if (n_calls) ++*n_calls;
-			a->score = x.score;
-			if (a->score == prev || x.max_off < (aw0 >> 1) + (aw0 >> 2)) break;
-		}
-		if (x.gscore <= 0 || x.gscore <= a->score - o.pen_clip5) {
-			a->qb = s.qbeg - x.qle; a->rb = s.rbeg - x.tle;
-			a->truesc = a->score;
-		} else {
-			a->qb = 0; a->rb = s.rbeg - x.gtle;
-			a->truesc = x.gscore;
-		}
-	} else { a->score = a->truesc = s.len * o.a; a->qb = 0; a->rb = s.rbeg; }
-
-	if (s.qbeg + s.len != l_query) {
-		ExtOut x; x.score = -1; x.qle = x.tle = x.gtle = 0; x.gscore = -1; x.max_off = 0;
-		int sc0 = a->score;
-		int qe = s.qbeg + s.len;
-		int64_t re = s.rbeg + s.len;
-		int tlen = (int)(c.rmax1 - re);
-		QFwd qa = { query + qe };
-		TPacFwd ta = { pac, l_pac, re };
-		for (int i = 0; i < 2; ++i) {
-			int prev = a->score;
-			aw1 = o.w << i;
-			extend_core(l_query - qe, qa, tlen, ta, o, aw1, o.pen_clip3, sc0, eh, &x, cells);
-			if (n_calls) ++*n_calls;
-			a->score = x.score;
-			if (a->score == prev || x.max_off < (aw1 >> 1) + (aw1 >> 2)) break;
-		}
-		if (x.gscore <= 0 || x.gscore <= a->score - o.pen_clip3) {
-			a->qe = qe + x.qle; a->re = re + x.tle;
-			a->truesc += a->score - sc0;
-		} else {
-			a->qe = l_query; a->re = re + x.gtle;
-			a->truesc += x.gscore - sc0;
-		}
-	} else { a->qe = l_query; a->re = s.rbeg + s.len; }
-
-	int cov = 0;
-	for (int i = 0; i < c.n_seeds; ++i) {
-		const DSeed &t = seeds[i];
-		if (t.qbeg >= a->qb && t.qbeg + t.len <= a->qe && t.rbeg >= a->rb && t.rbeg + t.len <= a->re) cov += t.len;
-	}
-	a->seedcov = cov;
-	a->w = aw0 > aw1 ? aw0 : aw1;
-	a->seedlen0 = s.len;
-	a->frac_rep = c.frac_rep;
-}
-
-// All chains of one read, in order.  seeds/srt are the chain-local arrays (indexing by c.seed_beg is done here).
-template <class EH>
-B200_HDN int chain2aln_read(const ExtOpt &o, const uint8_t *pac, int64_t l_pac, int l_query, const uint8_t *query,
-                            const DChain *chains, int n_chains, const DSeed *all_seeds, int32_t *all_srt,
-                            EH eh, DReg *regs, int64_t *cells, int *n_calls)
-{
-	int n_av = 0;
-	for (int ci = 0; ci < n_chains; ++ci) {
-		const DChain &c = chains[ci];
-		if (c.n_seeds == 0) continue;
-		const DSeed *seeds = all_seeds + c.seed_beg;
-		int32_t *srt = all_srt + c.seed_beg;
-		for (int k = c.n_seeds - 1; k >= 0; --k) {
-			if (!chain2aln_need_extension(o, l_query, c, seeds, srt, k, regs, n_av)) continue;
-			chain2aln_extend_seed(o, pac, l_pac, l_query, query, c, seeds, seeds[srt[k]], eh, &regs[n_av], cells, n_calls);
-			++n_av;
-		}
-	}
-	return n_av;
 }
 
 } // namespace b200

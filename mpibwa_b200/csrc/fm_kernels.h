@@ -7,9 +7,8 @@
 //
 // Semantics follow the reference line by line where the output depends on it:
 //   occ4 / extend            reference src/bwt.c:169-186, 262-275
-//   smem1a                   reference src/bwt.c:289-351   (max_intv is always 0 on the mem path)
-//   seed_strategy1           reference src/bwt.c:358-379
-//   collect_intv             reference src/bwamem.c:114-162
+//   smem1                    reference src/bwt.c:289-351   (max_intv is always 0 on the mem path; the single-call bwt_smem1 wrapper.
+//                            The seeding stage itself runs the sweeps of smem_sweeps.cuh / the lane state machine of smem_kernel.cuh.)
 //   sa_lookup                reference src/bwt.c:53-59, 86-96, 107-129
 //   pos2rid / intv2rid       reference src/bntseq.c:349-375
 #pragma once
@@ -245,77 +244,6 @@ B200_HDN int fm_smem1(const FmView &fm, int len, const uint8_t *q, int x, uint64
 	for (int j = 0; j < nm >> 1; ++j) { Intv t = mem[j]; mem[j] = mem[nm - 1 - j]; mem[nm - 1 - j] = t; }
 	*n_mem = nm;
 	return ret;
-}
-
-// forward-only greedy seed; m->x2 == 0 when nothing was found. Returns the next x.
-B200_HDN int fm_seed_strategy1(const FmView &fm, int len, const uint8_t *q, int x, int min_len, int max_intv,
-                               Intv *m, int64_t *n_blocks)
-{
-	Intv ik, ok[4];
-	m->x0 = m->x1 = m->x2 = m->info = 0;
-	if (q[x] > 3) return x + 1;
-	fm_set_intv(fm, q[x], ik);
-	for (int i = x + 1; i < len; ++i) {
-		if (q[i] < 4) {
-			int c = 3 - q[i];
-			fm_extend(fm, ik, ok, 0, n_blocks);
-			if (ok[c].x2 < (uint64_t)max_intv && i - x >= min_len) {
-				*m = ok[c];
-				m->info = (uint64_t)x << 32 | (uint32_t)(i + 1);
-				return i + 1;
-			}
-			ik = ok[c];
-		} else return i + 1;
-	}
-	return len;
-}
-
-// The three seeding passes of one read.  out[0..cap) receives the interval list sorted by info.
-// scratch = 3*(len+1) Intv.  Returns the number of intervals, or -(needed) when cap is too small.
-B200_HDN int fm_collect_intv(const FmView &fm, const SeedOpt &so, int len, const uint8_t *seq,
-                             Intv *out, int cap, Intv *scratch, int64_t *n_blocks)
-{
-	Intv *mem1 = scratch, *ta = scratch + (len + 1), *tb = scratch + 2 * (len + 1);
-	int n = 0, n1, x = 0;
-	while (x < len) {                             // pass 1: all SMEMs
-		if (seq[x] < 4) {
-			x = fm_smem1(fm, len, seq, x, 1, mem1, &n1, ta, tb, n_blocks);
-			for (int i = 0; i < n1; ++i) {
-				int slen = (int)(uint32_t)mem1[i].info - (int)(mem1[i].info >> 32);
-				if (slen >= so.min_seed_len) { if (n < cap) out[n] = mem1[i]; ++n; }
-			}
-		} else ++x;
-	}
-	int old_n = n < cap ? n : cap;                // pass 2: re-seed inside long, rare SMEMs
-	if (n <= cap)
-	for (int k = 0; k < old_n; ++k) {
-		const Intv p = out[k];
-		int start = (int)(p.info >> 32), end = (int)(int32_t)p.info;
-		if (end - start < so.split_len || p.x2 > (uint64_t)so.split_width) continue;
-		fm_smem1(fm, len, seq, (start + end) >> 1, p.x2 + 1, mem1, &n1, ta, tb, n_blocks);
-		for (int i = 0; i < n1; ++i) {
-			int slen = (int)(uint32_t)mem1[i].info - (int)(mem1[i].info >> 32);
-			if (slen >= so.min_seed_len) { if (n < cap) out[n] = mem1[i]; ++n; }
-		}
-	}
-	if (so.max_mem_intv > 0) {                    // pass 3: LAST-like greedy seeds
-		x = 0;
-		while (x < len) {
-			if (seq[x] < 4) {
-				Intv m;
-				x = fm_seed_strategy1(fm, len, seq, x, so.min_seed_len, so.max_mem_intv, &m, n_blocks);
-				if (m.x2 > 0) { if (n < cap) out[n] = m; ++n; }
-			} else ++x;
-		}
-	}
-	if (n > cap) return -n;
-	for (int i = 1; i < n; ++i) {                 // order by (start,end); equal keys are identical intervals
-		Intv v = out[i];
-		int j = i - 1;
-		while (j >= 0 && out[j].info > v.info) { out[j + 1] = out[j]; --j; }
-		out[j + 1] = v;
-	}
-	return n;
 }
 
 // number of suffix-array look-ups mem_chain() makes for one interval (reference src/bwamem.c:278-279)

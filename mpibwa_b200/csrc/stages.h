@@ -103,6 +103,8 @@ void stage_sw_bytes(Engine *e, const SwOpt &so, int64_t n_jobs, b200_align_job_t
 void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t *off, const uint8_t *codes,
                         std::vector<int64_t> &intv_off, std::vector<Intv> &intv);
 void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa);
+// bwt_smem1 (reference src/bwt.c:289-356) for one query position: all SMEMs through x with interval size >= min_intv; returns the next x
+int  stage_smem1(Engine *e, int len, const uint8_t *q, int x, uint64_t min_intv, std::vector<Intv> &mem);
 void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back);
 
 } // namespace b200

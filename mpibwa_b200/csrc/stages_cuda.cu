@@ -736,6 +736,31 @@ void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
 	e->sync();
 }
 
+__global__ void k_smem1_one(FmView fm, int len, const uint8_t *q, int x, uint64_t min_intv, Intv *mem, Intv *a, Intv *b, int32_t *out)
+{
+	int n = 0;
+	out[0] = fm_smem1(fm, len, q, x, min_intv, mem, &n, a, b, nullptr);
+	out[1] = n;
+}
+
+int stage_smem1(Engine *e, int len, const uint8_t *q, int x, uint64_t min_intv, std::vector<Intv> &mem)
+{
+	CK(cudaSetDevice(e->device));
+	uint8_t *dq = e->b_q.as<uint8_t>(len + 16);
+	Intv *d = e->b_t.as<Intv>((size_t)3 * (len + 1));
+	int32_t *d_out = e->b_xctr.as<int32_t>(16);
+	e->h2d(dq, q, len);
+	k_smem1_one<<<1, 1, 0, e->stream>>>(e->fm, len, dq, x, min_intv, d, d + (len + 1), d + 2 * (len + 1), d_out);
+	CK(cudaGetLastError());
+	e->stats.n_launches += 1;
+	int32_t h[2];
+	e->d2h(h, d_out, sizeof h);
+	e->sync();
+	mem.resize(h[1]);
+	if (h[1] > 0) { e->d2h(mem.data(), d, sizeof(Intv) * h[1]); e->sync(); }
+	return h[0];
+}
+
 void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
 {
 	CK(cudaSetDevice(e->device));

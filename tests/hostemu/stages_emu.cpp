@@ -7,6 +7,7 @@
 #include "../../mpibwa_b200/csrc/smem_kernel.cuh"
 #include "../../mpibwa_b200/csrc/smem_sweeps.cuh"
 #include "../../mpibwa_b200/csrc/finish_stage.h"
+#include "emu_bodies.h"
 #include <chrono>
 #include <cmath>
 #include <string>
@@ -524,6 +525,16 @@ void stage_sa(Engine *e, int64_t n, const uint64_t *k, uint64_t *sa)
 	for (int64_t i = 0; i < n; ++i) sa[i] = fm_sa(e->fm, k[i], nullptr);
 }
 
+int stage_smem1(Engine *e, int len, const uint8_t *q, int x, uint64_t min_intv, std::vector<Intv> &mem)
+{
+	std::vector<Intv> a(len + 1), b(len + 1);
+	mem.assign(len + 1, Intv());
+	int n = 0;
+	const int ret = fm_smem1(e->fm, len, q, x, min_intv, mem.data(), &n, a.data(), b.data(), nullptr);
+	mem.resize(n);
+	return ret;
+}
+
 void stage_fm_extend(Engine *e, const Intv &ik, Intv ok[4], int is_back)
 {
 	fm_extend(e->fm, ik, ok, is_back, nullptr);
@@ -564,6 +575,39 @@ extern "C" int64_t b200_emu_occ_selftest(uint64_t k0, uint32_t seed)
 		occ4_sector(r, k0 + i, cnt);
 		for (int t = 0; t < 4; ++t) bad += cnt[t] != run[t];
 		bad += sector_symbol(r, k0 + i) != sym[i];
+	}
+	return bad;
+}
+
+// the packed interval entries of the seeding kernels (smem_kernel.cuh SeedList, smem_sweeps.cuh SweepStrip: three 33-bit values and
+// a 29-bit end position in 16 bytes) round-trip values beyond 2^32, through the shared-memory slots and through the spill strip
+extern "C" int64_t b200_emu_pack_selftest(uint32_t seed)
+{
+	using namespace b200;
+	uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+	auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+	int64_t bad = 0;
+	const int quota = 3, n = 9;
+	std::vector<uint32_t> sh(4 * quota * 2);
+	std::vector<Q4> spill(n);
+	SeedList L; L.sh = sh.data(); L.stride = 2; L.quota = quota; L.spill = spill.data(); L.sstride = 1;
+	for (int rep = 0; rep < 2000; ++rep) {
+		uint64_t v[n][3]; int end[n];
+		for (int k = 0; k < n; ++k) {
+			for (int t = 0; t < 3; ++t) { v[k][t] = rnd() & ((1ull << 33) - 1); if (rep % 3 == 0) v[k][t] |= 1ull << 32; }
+			end[k] = (int)(rnd() & 0x1fffffff);
+			L.set(k, v[k][0], v[k][1], v[k][2], end[k]);
+		}
+		for (int k = 0; k < n; ++k) {
+			uint64_t a, b, c; int e;
+			L.get(k, a, b, c, e);
+			bad += a != v[k][0] || b != v[k][1] || c != v[k][2] || e != end[k];
+			const Q4 p = SweepStrip::pack(v[k][0], v[k][1], v[k][2], end[k]);
+			spill[0] = p;
+			SeedList S2 = L; S2.quota = 0;
+			S2.get(0, a, b, c, e);
+			bad += a != v[k][0] || b != v[k][1] || c != v[k][2] || e != end[k];
+		}
 	}
 	return bad;
 }

@@ -44,6 +44,56 @@ def test_struct_layouts_match_reference_abi():
     assert C.sizeof(M.mem_opt_t) == 168
 
 
+REF_SRC = "/root/reference/src"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference sources not present (they do not travel to the GPU box)")
+def test_c_header_layouts_equal_the_reference_headers(tmp_path):
+    """include/mpibwa_b200.h against the reference's OWN headers: one C translation unit compiled against each prints sizeof and
+    offsetof of every ABI type (and the flag constants); the outputs must be identical"""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "abi", "abi_probe.c")
+    cfg = tmp_path / "config.h"
+    cfg.write_text('#define VERSION "1.5.5"\n')
+    outs = []
+    for name, flags in (("ref", ["-DUSE_REF", "-I" + REF_SRC, "-I" + str(tmp_path)]), ("b200", ["-I" + os.path.join(ROOT, "include")])):
+        exe = str(tmp_path / ("probe_" + name))
+        subprocess.run(["gcc", "-w", "-o", exe, src] + flags, check=True)
+        outs.append(subprocess.run([exe], capture_output=True, check=True, text=True).stdout)
+    assert outs[0] == outs[1] and outs[0].count("\n") > 100
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference sources not present (they do not travel to the GPU box)")
+def test_reference_pidx_links_against_the_library(hostemu_built, examples, tmp_path):
+    """the reference's own src/pidx.c (the mpiBWAIdx host: needs no MPI) compiled unmodified against the library's symbols writes
+    the same .map image as the reference build of the same file (oracle/_ref/mpiBWAIdx)"""
+    import shutil
+    import subprocess
+    ref_tool = os.path.join(ROOT, "oracle", "_ref", "mpiBWAIdx")
+    if not os.path.exists(ref_tool):
+        pytest.skip("oracle/_ref/mpiBWAIdx not built")
+    cfg = tmp_path / "config.h"
+    cfg.write_text('#define VERSION "1.5.5"\n')
+    exe = str(tmp_path / "mpiBWAIdx_b200")
+    # (the CPU test scaffold carries the same capi.cpp as the product library; pidx.c touches only bwa_idx_load / bwa_idx2mem)
+    subprocess.run(["gcc", "-O2", "-w", "-I" + REF_SRC, "-I" + str(tmp_path), os.path.join(REF_SRC, "pidx.c"), "-o", exe,
+                    "-L" + hostemu_built, "-lmpibwa_b200_hostemu", "-Wl,-rpath," + hostemu_built], check=True)
+    maps = []
+    for tool, tag in ((exe, "b200"), (ref_tool, "ref")):
+        d = tmp_path / tag
+        d.mkdir()
+        for ext in (".bwt", ".sa", ".pac", ".ann", ".amb"):
+            shutil.copy(examples["idx"] + ext, str(d / ("x.fa" + ext)))
+        subprocess.run([tool, str(d / "x.fa")], check=True, capture_output=True)
+        maps.append(open(str(d / "x.fa.map"), "rb").read())
+    # the image holds raw pointers (bwt->bwt, bwt->sa, anns[].name ...) that differ from run to run: compare with them masked
+    import numpy as np
+    a, b = (np.frombuffer(m, np.uint8).copy() for m in maps)
+    assert len(a) == len(b) and len(a) > 1_000_000
+    diff = np.flatnonzero(a != b)
+    assert len(diff) < 64 * (2 + 8), len(diff)          # only the pointer fields of bwt_t, bntseq_t and the annotation records
+
+
 def test_no_cpu_fallback_without_device():
     """On a machine without CUDA the product aborts loudly instead of computing on the CPU."""
     import subprocess

@@ -76,6 +76,12 @@ def _run_align_batch(lib, cases):
     return out
 
 
+def _aux_stats(lib):
+    st = M.b200_stats_t()
+    lib.b200_get_aux_stats(C.byref(st))
+    return st.as_dict()
+
+
 @pytest.mark.parametrize("kernel", ["auto", "lane", "warp", "big"])
 def test_extend_batch_vs_oracle(aligner, orc, kernel):
     """ksw_extend2 fuzz through the C ABI; every DP kernel of the extension stage is forced in turn (one job per lane with
@@ -85,24 +91,35 @@ def test_extend_batch_vs_oracle(aligner, orc, kernel):
     os.environ.pop("B200_EXT_KERNEL", None)
     if kernel != "auto":
         os.environ["B200_EXT_KERNEL"] = kernel
+    st0 = _aux_stats(aligner.lib)
     try:
         got = _run_extend_batch(aligner.lib, cases)
     finally:
         os.environ.pop("B200_EXT_KERNEL", None)
+    st1 = _aux_stats(aligner.lib)
+    cells = 0
     for c, g in zip(cases, got):
         a, b, od, ed, oi, ei = c["params"]
-        want = orc.extend(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"], c["end_bonus"], c["zdrop"], c["h0"])[0]
+        want, n_cells = orc.extend(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"], c["end_bonus"], c["zdrop"], c["h0"])
         assert g == want, c
+        cells += n_cells
+    # the device's cell counter (the numerator of the ksw_extend2 roofline) counts what the reference executes: sum over rows of end - beg
+    assert st1["extend_cells"] - st0["extend_cells"] == cells
 
 
 @pytest.mark.parametrize("sixteen", [False, True])
 def test_align_batch_vs_oracle(aligner, orc, sixteen):
     cases = fuzzgen.align_cases(41 + sixteen, 6000, sixteen)
+    st0 = _aux_stats(aligner.lib)
     got = _run_align_batch(aligner.lib, cases)
+    st1 = _aux_stats(aligner.lib)
+    cells = 0
     for c, g in zip(cases, got):
         a, b, od, ed, oi, ei = c["params"]
-        want = orc.align(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["xtra"])[0]
+        want, n_cells = orc.align(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["xtra"])
         assert g == want, c
+        cells += n_cells
+    assert st1["sw_cells"] - st0["sw_cells"] == cells          # padded query length x rows executed, both passes
 
 
 def test_golden_vectors_through_cabi(aligner):
@@ -135,6 +152,35 @@ def test_single_job_wrappers(aligner, orc):
     ook = (OL.orc_intv_t * 4)()
     orc.lib.orc_extend(C.byref(idxf.fm), C.byref(oik), ook, 1)
     assert [(ok[i].x[0], ok[i].x[1], ok[i].x[2]) for i in range(4)] == [(ook[i].x0, ook[i].x1, ook[i].x2) for i in range(4)]
+    # bwt_smem1: all SMEMs through one query position (served by the device, reference src/bwt.c:353)
+    reads = _reads_as_codes(_PREFIX["R1"], 12)
+    for q in reads:
+        for x in (0, len(q) // 3, len(q) - 1):
+            for min_intv in (1, 3):
+                mem = M.bwtintv_v()
+                ret = lib.bwt_smem1(aligner.idx.contents.bwt, len(q), bytes(q), x, min_intv, C.byref(mem), None)
+                out = (OL.orc_intv_t * (len(q) + 1))()
+                n = C.c_int()
+                want_ret = orc.lib.orc_smem1(C.byref(idxf.fm), len(q), bytes(q), x, min_intv, out, C.byref(n))
+                assert ret == want_ret and mem.n == n.value
+                assert [(mem.a[i].x[0], mem.a[i].x[1], mem.a[i].x[2], mem.a[i].info) for i in range(mem.n)] == \
+                    [(out[i].x0, out[i].x1, out[i].x2, out[i].info) for i in range(n.value)]
+                lib.b200_free(mem.a)
+    # ksw_global2: score and CIGAR of a banded global alignment (served by the device, reference src/ksw.c:504)
+    if have_ref():
+        ref = OL.Reference()
+        ref.lib.ksw_global2.argtypes = lib.ksw_global2.argtypes
+        rng = np.random.default_rng(77)
+        for _ in range(60):
+            ql, w = int(rng.integers(1, 200)), int(rng.integers(1, 120))
+            t = rng.integers(0, 4, size=max(1, ql + int(rng.integers(-min(w, ql) + 1, w))), dtype=np.uint8)
+            q = fuzzgen.mutate(rng, t[:ql] if len(t) >= ql else np.resize(t, ql), 0.05, 0.03, 0.01)
+            outs = []
+            for L in (lib, ref.lib):
+                n_cigar, cigar = C.c_int(), C.POINTER(C.c_uint32)()
+                sc = L.ksw_global2(len(q), bytes(q), len(t), bytes(t), 5, OL.default_mat(1, 4), 6, 1, 5, 2, w, C.byref(n_cigar), C.byref(cigar))
+                outs.append((sc, [cigar[i] for i in range(n_cigar.value)]))
+            assert outs[0] == outs[1], (len(q), len(t), w)
 
 
 _PREFIX = {}
@@ -147,6 +193,7 @@ def aligner_idx_prefix(aligner):
 @pytest.fixture(autouse=True)
 def _remember_prefix(examples):
     _PREFIX["idx"] = examples["idx"]
+    _PREFIX["R1"] = examples["R1_10K"]
 
 
 def _reads_as_codes(path, n):
@@ -204,6 +251,41 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
     assert sa[:3000].tolist() == want
     # size-independent property: SA values of distinct rows are distinct text positions
     assert len(set(sa.tolist())) == len(set(ks.tolist()))
+
+
+@pytest.mark.parametrize("dom", [1, 3])
+def test_fm_index_beyond_2_32(tmp_path, orc, dom):
+    """occ sectors at BWT rows AND symbol counts beyond 2^32 (human-sized references: 2 x 3.1 Gbp rows), on the real device path:
+    a synthetic 4.4 G-row index in the reference's file formats (tests/bigfm.py) is loaded through bwa_idx_load, re-blocked into
+    occ sectors by the upload kernel like any index, and bwt_extend (ld_occ's 256-bit sector load + occ4_sector's 40-bit counts,
+    the primitive of every seeding and SA kernel) is compared with the oracle's orc_extend over the same files, for intervals
+    that start, end and straddle rows around 2^32 and hold up to 2^32 + 999 rows.  (The symbol array is not the transform of a
+    text, so only single steps are compared: a sweep over it would leave the range of valid rows.)"""
+    import bigfm
+    prefix = str(tmp_path / "big.fa")
+    info = bigfm.write_index(prefix, dom=dom, seed=5 + dom)
+    idxf = OL.IndexFiles(prefix)
+    a = M.Aligner(prefix, device=0, n_threads=4, verbose=1)
+    try:
+        lib = a.lib
+        rng = np.random.default_rng(13)
+        n_bad = 0
+        for t in range(400):
+            w0, w1 = info["windows"][t % len(info["windows"])]
+            k = int(rng.integers(w0 - 300, w1 + 300))
+            size = int(rng.choice([1, 2, 50, 4000, 1 << 20, 1 << 31, (1 << 32) + 999]))
+            size = min(size, info["seq_len"] - k)
+            ik = M.bwtintv_t((C.c_uint64 * 3)(k, int(rng.integers(1, info["seq_len"] - size)), size), 0)
+            for is_back in (0, 1):
+                ok = (M.bwtintv_t * 4)()
+                lib.bwt_extend(a.idx.contents.bwt, C.byref(ik), ok, is_back)
+                oik = OL.orc_intv_t(ik.x[0], ik.x[1], ik.x[2], 0)
+                ook = (OL.orc_intv_t * 4)()
+                orc.lib.orc_extend(C.byref(idxf.fm), C.byref(oik), ook, is_back)
+                n_bad += [(ok[i].x[0], ok[i].x[1], ok[i].x[2]) for i in range(4)] != [(ook[i].x0, ook[i].x1, ook[i].x2) for i in range(4)]
+        assert n_bad == 0
+    finally:
+        a.close()
 
 
 def _sq_header(aligner):

@@ -81,6 +81,10 @@ def test_occ_sectors_beyond_32_bits(hostemu_built):
     for k0 in (0, 128, 1 << 31, (1 << 32) - 128, 1 << 32, 6_200_000_000, (1 << 33) - 1024):
         for seed in (1, 2, 3):
             assert lib.b200_emu_occ_selftest(k0, seed) == 0, (k0, seed)
+    # the packed interval entries of the seeding kernels hold three 33-bit values each
+    lib.b200_emu_pack_selftest.restype = C.c_int64
+    lib.b200_emu_pack_selftest.argtypes = [C.c_uint32]
+    assert lib.b200_emu_pack_selftest(7) == 0
 
 
 OPTION_SETS = ["w=200,zdrop=200",

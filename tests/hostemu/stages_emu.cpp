@@ -602,9 +602,8 @@ extern "C" int64_t b200_emu_pack_selftest(uint32_t seed)
 			uint64_t a, b, c; int e;
 			L.get(k, a, b, c, e);
 			bad += a != v[k][0] || b != v[k][1] || c != v[k][2] || e != end[k];
-			const Q4 p = SweepStrip::pack(v[k][0], v[k][1], v[k][2], end[k]);
-			spill[0] = p;
-			SeedList S2 = L; S2.quota = 0;
+			Q4 p = SweepStrip::pack(v[k][0], v[k][1], v[k][2], end[k]);
+			SeedList S2 = L; S2.quota = 0; S2.spill = &p;
 			S2.get(0, a, b, c, e);
 			bad += a != v[k][0] || b != v[k][1] || c != v[k][2] || e != end[k];
 		}

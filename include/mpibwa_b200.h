@@ -268,6 +268,20 @@ int b200_ksw_align2_batch(int64_t n_jobs, b200_align_job_t *jobs, const uint8_t 
                           const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
                           int o_del, int e_del, int o_ins, int e_ins);
 
+/* batched banded global alignment with traceback (ksw_global2, reference src/ksw.c:504-606) through the kernels of the CIGAR stage.
+ * Queries hold codes 0-4, targets codes 0-3 (the stage reads its targets from the 2-bit reference).  *cigar is one malloc()ed
+ * array (release with b200_free): job j's operations are (*cigar)[cigar_off .. cigar_off + n_cigar), len << 4 | op. */
+typedef struct {
+	int32_t qlen, tlen;       /* in */
+	int64_t q_off, t_off;     /* in: offsets into the flat code buffers */
+	int32_t w;                /* in: band */
+	int32_t score, n_cigar;   /* out */
+	int64_t cigar_off;        /* out */
+} b200_global_job_t;
+int b200_ksw_global2_batch(int64_t n_jobs, b200_global_job_t *jobs, const uint8_t *query, int64_t query_bytes,
+                           const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
+                           int o_del, int e_del, int o_ins, int e_ins, uint32_t **cigar);
+
 /* batched seeding: for read r (codes 0-4 at seq[off[r] .. off[r+1])) the sorted interval list of
  * mem_collect_intv (reference src/bwamem.c:114-162) is returned in a malloc()ed array; *intv_off has n+1 entries. */
 int b200_collect_intv_batch(const mem_opt_t *opt, int n_reads, const int64_t *off, const uint8_t *seq,

@@ -75,6 +75,11 @@ class b200_align_job_t(C.Structure):
                 ("xtra", C.c_int32), ("r", kswr_t)]
 
 
+class b200_global_job_t(C.Structure):
+    _fields_ = [("qlen", C.c_int32), ("tlen", C.c_int32), ("q_off", C.c_int64), ("t_off", C.c_int64), ("w", C.c_int32),
+                ("score", C.c_int32), ("n_cigar", C.c_int32), ("cigar_off", C.c_int64)]
+
+
 class b200_stats_t(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("ms_total", "ms_seed", "ms_sa", "ms_chain_host", "ms_extend", "ms_regs_host",
                                           "ms_rescue", "ms_sam_host", "ms_k_smem", "ms_k_sa", "ms_k_extend", "ms_k_sw",
@@ -125,6 +130,8 @@ _PROTOTYPES = {
                                          C.POINTER(C.c_int8)] + [C.c_int] * 5),
     "b200_ksw_align2_batch": (C.c_int, [C.c_int64, C.POINTER(b200_align_job_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                         C.POINTER(C.c_int8)] + [C.c_int] * 4),
+    "b200_ksw_global2_batch": (C.c_int, [C.c_int64, C.POINTER(b200_global_job_t), C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.POINTER(C.c_int8)] + [C.c_int] * 4 + [C.POINTER(C.POINTER(C.c_uint32))]),
     "b200_collect_intv_batch": (C.c_int, [C.POINTER(mem_opt_t), C.c_int, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.POINTER(bwtintv_t)), C.POINTER(C.POINTER(C.c_int64))]),
     "b200_bwt_sa_batch": (C.c_int, [C.c_int64, C.c_void_p, C.c_void_p]),

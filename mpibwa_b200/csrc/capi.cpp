@@ -507,6 +507,20 @@ int b200_ksw_align2_batch(int64_t n_jobs, b200_align_job_t *jobs, const uint8_t 
 	return 0;
 }
 
+int b200_ksw_global2_batch(int64_t n_jobs, b200_global_job_t *jobs, const uint8_t *query, int64_t query_bytes,
+                           const uint8_t *target, int64_t target_bytes, const int8_t mat[25],
+                           int o_del, int e_del, int o_ins, int e_ins, uint32_t **cigar)
+{
+	GlobalOpt go;
+	go.o_del = o_del; go.e_del = e_del; go.o_ins = o_ins; go.e_ins = e_ins; go.a = mat[0]; go.w_max = 0x3fffffff;
+	memcpy(go.mat, mat, 25);
+	std::vector<uint32_t> cg;
+	{ AuxGuard eng; stage_global_batch(eng, go, n_jobs, jobs, query, query_bytes, target, target_bytes, cg); }
+	*cigar = (uint32_t *)malloc(cg.size() * 4 + 4);
+	memcpy(*cigar, cg.data(), cg.size() * 4);
+	return 0;
+}
+
 int b200_collect_intv_batch(const mem_opt_t *opt, int n_reads, const int64_t *off, const uint8_t *seq,
                             bwtintv_t **intv, int64_t **intv_off)
 {

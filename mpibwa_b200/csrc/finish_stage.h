@@ -252,7 +252,7 @@ struct GlobalClassTask {    // class (row window), band and length key of every 
 	{
 		const GlobalJob j = jobs[sel[x]];
 		const int ql = j.qe - j.qb, rl = (int)(j.re - j.rb);
-		int band = pass == 0 ? global_band(go, ql, rl, j.w2 < go.w_max ? j.w2 : go.w_max) : j.wmax;
+		int band = j.truesc == B200_GLOBAL_RAW ? j.w2 : pass == 0 ? global_band(go, ql, rl, j.w2 < go.w_max ? j.w2 : go.w_max) : j.wmax;
 		if (pass == 0 && squeeze) band >>= 2;
 		const int need = 2 * band + 2;
 		int k = 5;

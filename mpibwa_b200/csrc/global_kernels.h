@@ -38,6 +38,7 @@ struct GlobalRes {
 };
 
 #define B200_GLOBAL_MINUS_INF (-0x40000000)
+#define B200_GLOBAL_RAW ((int32_t)0x80000000)     // GlobalJob.truesc: w2 is the band itself, no bwa_gen_cigar2 clamp, no retries
 
 // band actually used by bwa_gen_cigar2 for a requested width w_ (reference src/bwa.c:151-160)
 B200_HD int global_band(const GlobalOpt &o, int l_query, int rlen, int w_)
@@ -174,6 +175,12 @@ B200_HDN void global_task(const GlobalOpt &o, const SEQ &s, const GlobalJob &jb,
 {
 	const int l_query = s.l_query, rlen = (int)(jb.re - jb.rb);
 	int w2 = jb.w2, last_sc = -(1 << 30), score = 0, n_cigar = 0, i = 0;
+	if (jb.truesc == B200_GLOBAL_RAW) {             // one plain ksw_global2 call with the caller's band (b200_ksw_global2_batch)
+		if (w2 > max_band) { out->score = 0; out->n_cigar = -2; out->n_tries = 0; out->pad = 0; return; }
+		out->score = global_dp(o, s, rlen, w2, eh, z, cigar, &n_cigar, cells);
+		out->n_cigar = n_cigar; out->n_tries = 1; out->pad = 0;
+		return;
+	}
 	do {
 		w2 = w2 < o.w_max ? w2 : o.w_max;
 		if (l_query == rlen && w2 == 0) {

@@ -91,6 +91,10 @@ void stage_chain(Engine *e, const ChainOpt &co, ExtIn &in, bool download = false
 // local SW batch against reference windows
 void stage_sw(Engine *e, const SwOpt &so, const std::vector<SwJob> &jobs, std::vector<SwRes> &out);
 
+// b200_ksw_global2_batch: the caller's jobs through the CIGAR-stage kernels (queries codes 0-4, targets codes 0-3); cigar receives
+// the operations of all jobs back to back, jobs[i].cigar_off / n_cigar say where
+void stage_global_batch(Engine *e, const GlobalOpt &go, int64_t n_jobs, b200_global_job_t *jobs, const uint8_t *query, int64_t qbytes,
+                        const uint8_t *target, int64_t tbytes, std::vector<uint32_t> &cigar);
 // ksw_global2 for caller-provided byte buffers (the single-job C wrapper): score and CIGAR of one banded global alignment
 int stage_global_bytes(Engine *e, const GlobalOpt &go, int qlen, const uint8_t *query, int tlen, const uint8_t *target, int w,
                        std::vector<uint32_t> *cigar);

@@ -1374,8 +1374,10 @@ __global__ void __launch_bounds__(128) k_global_jobs(GlobalOpt go, const uint8_t
 // - row windows of 32, 64, 128, 256, 512 columns in shared memory, then the general kernel - and, within a class, by band and
 // target length, so that the lanes of a warp get regions of similar cost.  One launch per class on concurrent streams.
 static void global_launch_classes(Engine *e, const GlobalOpt &go, const GlobalJob *dj, const int32_t *d_ord, const int32_t cnt[6], const int32_t qmax[6],
-                                  const int64_t *d_off, const uint8_t *d_codes, uint8_t *z, uint32_t *cig, GlobalRes *dr)
+                                  const int64_t *d_off, const uint8_t *d_codes, uint8_t *z, uint32_t *cig, GlobalRes *dr,
+                                  const uint8_t *pac = nullptr, int64_t l_pac = 0)
 {
+	if (!pac) { pac = e->fm.pac; l_pac = e->fm.l_pac; }
 	static const int cls_S[5] = { 32, 64, 128, 256, 512 };
 	if (!e->global_attr_set) { CK(cudaFuncSetAttribute(k_global_lanes, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); e->global_attr_set = true; }
 	int64_t pos[6];
@@ -1393,12 +1395,12 @@ static void global_launch_classes(Engine *e, const GlobalOpt &go, const GlobalJo
 			const int S = cls_S[k], qcap = qmax[k];
 			const size_t per_warp = ((size_t)S * 64 + (size_t)((qcap + 4) & ~3) * 8) * 4;
 			const int threads = per_warp * 2 <= 200 * 1024 ? 64 : 32;
-			k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k],
+			k_global_lanes<<<grid_for(nk, threads), threads, per_warp * (threads / 32), st>>>(go, pac, l_pac, nk, dj, d_ord + pos[k],
 				d_off, d_codes, z, cig, dr, S, qcap, e->d_cnt);
 		} else {
 			const int64_t stride = ((int64_t)nk + 31) & ~31ll;
 			int32_t *rows = e->b_grow.as<int32_t>((size_t)stride * 2 * (qmax[k] + 2));
-			k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, e->fm.pac, e->fm.l_pac, nk, dj, d_ord + pos[k], d_off, d_codes, rows, stride, z, cig, dr, e->d_cnt);
+			k_global_jobs<<<grid_for(nk, 128), 128, 0, st>>>(go, pac, l_pac, nk, dj, d_ord + pos[k], d_off, d_codes, rows, stride, z, cig, dr, e->d_cnt);
 		}
 		CK(cudaGetLastError());
 		CK(cudaEventRecord(e->ev_join[used % Engine::N_SIDE], st));
@@ -1631,6 +1633,76 @@ void stage_upload_fastq(Engine *e, const char *fq1, int64_t len1, const char *fq
 	e->max_len = max_len;
 	e->h_off.clear();
 	info->n_reads = (int)n; info->n_bases = total; info->max_len = max_len;
+}
+
+// the caller's jobs through the CIGAR-stage kernels: same classification (GlobalClassTask + radix sort), same launches, same rerun
+// pass for jobs whose band outgrows the row window of their class as finish_run() uses
+void stage_global_batch(Engine *e, const GlobalOpt &go, int64_t n, b200_global_job_t *jobs, const uint8_t *query, int64_t qbytes,
+                        const uint8_t *target, int64_t tbytes, std::vector<uint32_t> &cigar)
+{
+	CK(cudaSetDevice(e->device));
+	cigar.clear();
+	if (n <= 0) return;
+	CudaBK bk = { e };
+	std::vector<GlobalJob> hj(n);
+	std::vector<int64_t> off(n + 1);
+	int64_t zb = 0, cb = 0;
+	for (int64_t i = 0; i < n; ++i) {
+		const b200_global_job_t &j = jobs[i];
+		GlobalJob &g = hj[i];
+		g.rb = j.t_off; g.re = j.t_off + j.tlen; g.zoff = zb; g.read = (int32_t)i; g.qb = 0; g.qe = j.qlen; g.w2 = j.w; g.truesc = B200_GLOBAL_RAW;
+		g.wmax = j.w; g.cig_off = cb;
+		const int n_col = ((j.qlen < 2 * j.w + 1 ? j.qlen : 2 * j.w + 1) + 3) & ~3;
+		zb += ((int64_t)n_col * j.tlen + 15) & ~(int64_t)15;
+		cb += (int64_t)j.qlen + j.tlen + 4;
+		off[i] = j.q_off;
+	}
+	off[n] = qbytes;
+	std::vector<uint8_t> pac((size_t)tbytes / 4 + 2, 0);
+	for (int64_t l = 0; l < tbytes; ++l) pac[l >> 2] |= (uint8_t)((target[l] & 3) << ((~l & 3) << 1));
+	GlobalJob *dj = bk.buf<GlobalJob>(FB_GJOBS, n);
+	GlobalRes *dr = bk.buf<GlobalRes>(FB_GRES, n);
+	uint8_t *z = bk.buf<uint8_t>(FB_GZ, (size_t)zb + 64);
+	uint32_t *cig = bk.buf<uint32_t>(FB_CIG, (size_t)cb + 4);
+	uint32_t *key = bk.buf<uint32_t>(FB_GKEY, n);
+	int32_t *sel = bk.buf<int32_t>(FB_GSEL, n), *sel2 = bk.buf<int32_t>(FB_GSEL2, n);
+	int32_t *ctr = bk.buf<int32_t>(FB_CTR, 64);
+	int64_t *d_off = e->b_soff.as<int64_t>(n + 2);
+	uint8_t *d_q = e->b_q.as<uint8_t>((size_t)qbytes + 16), *d_pac = e->b_t.as<uint8_t>(pac.size() + 16);
+	e->h2d(dj, hj.data(), sizeof(GlobalJob) * n);
+	e->h2d(d_off, off.data(), sizeof(int64_t) * (n + 1));
+	e->h2d(d_q, query, (size_t)qbytes);
+	e->h2d(d_pac, pac.data(), pac.size());
+	bk.zero(ctr, 64 * sizeof(int32_t));
+	bk.run(n, IotaTask{ sel });
+	int64_t m = n;
+	const int squeeze = getenv("B200_GLOBAL_SQUEEZE") != nullptr;
+	e->zero_counters();
+	for (int pass = 0; pass < 2 && m > 0; ++pass) {
+		int32_t *sl = pass == 0 ? sel : sel2;
+		bk.zero(ctr + 8, 16 * sizeof(int32_t));
+		bk.run(m, GlobalClassTask{ go, dj, sl, key, ctr + 8, pass, squeeze });
+		bk.sort_pairs(key, sl, m);
+		int32_t h[12];
+		bk.download(h, ctr + 8, sizeof h);
+		global_launch_classes(e, go, dj, sl, h, h + 6, d_off, d_q, z, cig, dr, d_pac, tbytes);
+		if (pass == 0) {
+			bk.zero(ctr + 2, sizeof(int32_t));
+			bk.run(n, GlobalRerunTask{ dr, sel2, ctr + 2 });
+			m = bk.get32(ctr + 2);
+		}
+	}
+	std::vector<GlobalRes> hr(n);
+	std::vector<uint32_t> arena((size_t)cb);
+	e->d2h(hr.data(), dr, sizeof(GlobalRes) * n);
+	e->d2h(arena.data(), cig, sizeof(uint32_t) * cb);
+	Counters c = e->read_counters();
+	e->stats.global_cells += (int64_t)c.global_cells;
+	e->stats.n_global_jobs += n;
+	for (int64_t i = 0; i < n; ++i) {
+		jobs[i].score = hr[i].score; jobs[i].n_cigar = hr[i].n_cigar; jobs[i].cigar_off = (int64_t)cigar.size();
+		cigar.insert(cigar.end(), arena.begin() + hj[i].cig_off, arena.begin() + hj[i].cig_off + (hr[i].n_cigar > 0 ? hr[i].n_cigar : 0));
+	}
 }
 
 void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char *text, int64_t bytes)

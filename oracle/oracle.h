@@ -4,7 +4,7 @@
  *
  * Parity pinning: the reference has no golden vectors or tests for this path, so every function here
  * is pinned against the UNMODIFIED reference compiled into oracle/_ref/libbwa_ref.so (tests/test_oracle_pinned.py
- * fuzzes each one against ksw_extend2 / ksw_align2 / bwt_extend / bwt_smem1 / bwt_seed_strategy1 / bwt_sa /
+ * fuzzes each one against ksw_extend2 / ksw_align2 / ksw_global2 / bwt_extend / bwt_smem1 / bwt_seed_strategy1 / bwt_sa /
  * bns_fetch_seq of that library).  Without oracle/_ref the oracle is "parity unpinned".
  */
 #ifndef B200_ORACLE_H
@@ -27,6 +27,9 @@ void orc_ksw_extend2(int qlen, const uint8_t *query, int tlen, const uint8_t *ta
 /* reference src/ksw.c:63-365 (ksw_align2 with qry == NULL) */
 void orc_ksw_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t mat[25],
                     int o_del, int e_del, int o_ins, int e_ins, int xtra, orc_aln_t *out);
+/* reference src/ksw.c:504-606; *cigar is malloc()ed when asked for; *cells = band cells computed */
+int orc_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t mat[25],
+                    int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t **cigar, int64_t *cells);
 /* reference src/bwt.c:107-129,169-186 */
 void orc_occ4(const orc_fm_t *fm, uint64_t k, uint64_t cnt[4]);
 /* reference src/bwt.c:262-275 */

@@ -138,3 +138,76 @@ void orc_ksw_align2(int qlen, const uint8_t *query, int tlen, const uint8_t *tar
 		free(rq); free(rt);
 	}
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * ksw_global2, reference src/ksw.c:504-606: banded global alignment with affine gaps (separate deletion / insertion costs)
+ * and its traceback.  Restated over FULL matrices (the reference rolls one row): cell (i, j), i = target row, j = query
+ * column, both 0-based, lives inside the band when i - w <= j <= i + w.
+ *   M(i,j)   = H(i-1,j-1) + S(i,j)                      H(-1,-1) = 0, H(-1,j) = -(o_ins + e_ins (j+1)) for j < w,
+ *   H(i,j)   = max{M, E(i,j), F(i,j)}                   H(i,-1) = -(o_del + e_del (i+1)) while the band touches column 0
+ *   E(i+1,j) = max{M - o_del, E(i,j)} - e_del           ties: M before E before F for H; "continue the gap" only when strictly
+ *   F(i,j+1) = max{M - o_ins, F(i,j)} - e_ins           better than opening it (reference :546-566)
+ * The traceback state machine (which = 0 M, 1 E / deletion, 2 F / insertion) reads, per cell, where H came from and whether
+ * the E / F of the NEXT cell continues a gap (reference :586-599).  Returns the score; *n_cigar / cigar (caller frees) as
+ * the reference; *cells = band cells computed. */
+#define ORC_NEG (-0x40000000)
+int orc_ksw_global2(int qlen, const uint8_t *query, int tlen, const uint8_t *target, const int8_t mat[25],
+                    int o_del, int e_del, int o_ins, int e_ins, int w, int *n_cigar, uint32_t **cigar, int64_t *cells)
+{
+	const long W = qlen + 2, R = tlen + 3;
+	int32_t *H = malloc(sizeof(int32_t) * W * R), *E = malloc(sizeof(int32_t) * W * R);
+	uint8_t *src = malloc(W * R), *e_ext = malloc(W * R), *f_ext = malloc(W * R);
+	int i, j, score;
+	int64_t n_cells = 0;
+#define AT(a, i, j) a[((long)(i) + 1) * W + (j) + 1]          /* indices from -1 */
+	for (i = -1; i <= tlen; ++i) for (j = -1; j < qlen; ++j) { AT(H, i, j) = ORC_NEG; AT(E, i, j) = ORC_NEG; }
+	AT(H, -1, -1) = 0;
+	for (j = 0; j < qlen && j + 1 <= w; ++j) AT(H, -1, j) = -(o_ins + e_ins * (j + 1));
+	for (i = 0; i < tlen; ++i) {
+		const int beg = i > w ? i - w : 0, end = i + w + 1 < qlen ? i + w + 1 : qlen;
+		int32_t F = ORC_NEG;
+		if (beg == 0) AT(H, i, -1) = -(o_del + e_del * (i + 1));
+		for (j = beg; j < end; ++j) {
+			const int32_t M = AT(H, i - 1, j - 1) + mat[target[i] * 5 + query[j]];
+			const int32_t e = AT(E, i, j);
+			int32_t h = M, t;
+			uint8_t s = 0;
+			if (e > h) { h = e; s = 1; }
+			if (F > h) { h = F; s = 2; }
+			AT(H, i, j) = h; AT(src, i, j) = s;
+			t = M - (o_del + e_del);
+			AT(e_ext, i, j) = e - e_del > t;
+			AT(E, i + 1, j) = e - e_del > t ? e - e_del : t;
+			t = M - (o_ins + e_ins);
+			AT(f_ext, i, j) = F - e_ins > t;
+			F = F - e_ins > t ? F - e_ins : t;
+			++n_cells;
+		}
+	}
+	score = qlen > 0 ? (tlen > 0 ? AT(H, tlen - 1, qlen - 1) : AT(H, -1, qlen - 1)) : (tlen > 0 ? AT(H, tlen - 1, -1) : 0);
+	if (cells) *cells = n_cells;
+	if (n_cigar) *n_cigar = 0;
+	if (n_cigar && cigar) {
+		uint32_t *cg = malloc(sizeof(uint32_t) * (qlen + tlen + 2));
+		int n = 0, which = 0, k;
+		i = tlen - 1; k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+#define PUSH(op, len) do { if (n && (cg[n - 1] & 0xf) == (uint32_t)(op)) cg[n - 1] += (uint32_t)(len) << 4; else cg[n++] = (uint32_t)(len) << 4 | (op); } while (0)
+		while (i >= 0 && k >= 0) {
+			/* in state 0 the cell says where H came from; in state 1 (2) whether the gap that ENDS here was opened here or continues */
+			if (which == 0) which = AT(src, i, k);
+			else if (which == 1) which = AT(e_ext, i, k) ? 1 : 0;
+			else which = AT(f_ext, i, k) ? 2 : 0;
+			if (which == 0) { PUSH(0, 1); --i; --k; }
+			else if (which == 1) { PUSH(2, 1); --i; }
+			else { PUSH(1, 1); --k; }
+		}
+		if (i >= 0) PUSH(2, i + 1);
+		if (k >= 0) PUSH(1, k + 1);
+#undef PUSH
+		for (i = 0; i < n >> 1; ++i) { uint32_t t = cg[i]; cg[i] = cg[n - 1 - i]; cg[n - 1 - i] = t; }
+		*n_cigar = n; *cigar = cg;
+	}
+#undef AT
+	free(H); free(E); free(src); free(e_ext); free(f_ext);
+	return score;
+}

@@ -82,3 +82,35 @@ def align_cases(seed, n, sixteen=False, gap_open_min=1):
             xtra |= 0x10000
         cases.append(dict(q=q, t=t, params=(a, b, od, ed, oi, ei), xtra=xtra))
     return cases
+
+
+def global_cases(seed, n, max_q=260):
+    """banded global alignments: bands 1..200, tlen != qlen, gappy pairs whose CIGARs run to dozens of operations"""
+    rng = np.random.default_rng(seed)
+    out = []
+    for k in range(n):
+        ql = int(rng.integers(1, max_q))
+        t0 = rng.integers(0, 4, size=ql + 300, dtype=np.uint8)
+        style = k % 4
+        if style == 0:
+            q = mutate(rng, t0[:ql], 0.03, 0.003, 0.0)
+        elif style == 1:
+            q = mutate(rng, t0[:ql], 0.06, 0.08, 0.01)           # many short indels: long CIGARs
+        elif style == 2:
+            q = mutate(rng, t0[:ql], 0.01, 0.0, 0.02)
+            cut = int(rng.integers(0, len(q) + 1))
+            q = np.concatenate([q[:cut], rng.integers(0, 4, size=int(rng.integers(1, 40)), dtype=np.uint8), q[cut:]])   # one long insertion
+        else:
+            q = rng.integers(0, 5, size=ql, dtype=np.uint8)      # unrelated
+        q = q[:max_q]
+        if len(q) == 0:
+            q = np.zeros(1, np.uint8)
+        w = int(rng.choice([1, 2, 3, 5, 10, 30, 60, 100, 200]))
+        # (the band always reaches the last cell: |tlen - qlen| <= w, as bwa_gen_cigar2 guarantees - below that ksw_global2 tracks back
+        #  through cells it never wrote)
+        d = int(rng.integers(-min(w, len(q) - 1), w + 1)) if style != 3 else int(rng.integers(-min(3, w, len(q) - 1), min(3, w) + 1))
+        tl = max(1, len(q) + d)
+        t = t0[:tl]
+        params = [(1, 4, 6, 1, 6, 1), (1, 4, 6, 1, 6, 1), (2, 5, 7, 2, 8, 1), (1, 3, 4, 2, 5, 3)][int(rng.integers(0, 4))]
+        out.append(dict(q=q.astype(np.uint8), t=t.astype(np.uint8), w=w, params=params))
+    return out

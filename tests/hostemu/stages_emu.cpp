@@ -389,6 +389,28 @@ int stage_global_bytes(Engine *, const GlobalOpt &go, int qlen, const uint8_t *q
 	return score;
 }
 
+void stage_global_batch(Engine *e, const GlobalOpt &go, int64_t n, b200_global_job_t *jobs, const uint8_t *query, int64_t,
+                        const uint8_t *target, int64_t tbytes, std::vector<uint32_t> &cigar)
+{
+	cigar.clear();
+	std::vector<uint8_t> pac((size_t)tbytes / 4 + 2, 0);
+	for (int64_t l = 0; l < tbytes; ++l) pac[l >> 2] |= (uint8_t)((target[l] & 3) << ((~l & 3) << 1));
+	for (int64_t i = 0; i < n; ++i) {
+		b200_global_job_t &j = jobs[i];
+		GlobalJob g;
+		g.rb = j.t_off; g.re = j.t_off + j.tlen; g.zoff = 0; g.read = 0; g.qb = 0; g.qe = j.qlen; g.w2 = j.w; g.truesc = B200_GLOBAL_RAW; g.wmax = j.w; g.cig_off = 0;
+		std::vector<int32_t> row(2 * (size_t)(j.qlen + 2));
+		const int n_col = ((j.qlen < 2 * j.w + 1 ? j.qlen : 2 * j.w + 1) + 3) & ~3;
+		std::vector<uint8_t> z((size_t)n_col * (j.tlen + 1) + 64);
+		std::vector<uint32_t> cg((size_t)j.qlen + j.tlen + 8);
+		GlobalRow eh = { row.data(), 1 };
+		GlobalRes r;
+		global_task(go, global_seqs(pac.data(), tbytes, query + j.q_off, g), g, eh, z.data(), cg.data(), &r, &e->stats.global_cells);
+		j.score = r.score; j.n_cigar = r.n_cigar; j.cigar_off = (int64_t)cigar.size();
+		cigar.insert(cigar.end(), cg.begin(), cg.begin() + r.n_cigar);
+	}
+}
+
 // finish_stage.h over plain loops
 struct HostBK {
 	Engine *e;

@@ -41,6 +41,11 @@ class Oracle:
         L = self.lib
         L.orc_ksw_extend2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int8)] + [C.c_int] * 8 + [C.POINTER(orc_ext_t)]
         L.orc_ksw_align2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int8)] + [C.c_int] * 5 + [C.POINTER(orc_aln_t)]
+        L.orc_ksw_global2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.POINTER(C.c_int8)] + [C.c_int] * 5 + \
+            [C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32)), C.POINTER(C.c_int64)]
+        L.orc_ksw_global2.restype = C.c_int
+        self.libc = C.CDLL(None)
+        self.libc.free.argtypes = [C.c_void_p]
         L.orc_extend.argtypes = [C.POINTER(orc_fm_t), C.POINTER(orc_intv_t), C.POINTER(orc_intv_t), C.c_int]
         L.orc_smem1.argtypes = [C.POINTER(orc_fm_t), C.c_int, C.c_char_p, C.c_int, C.c_uint64, C.POINTER(orc_intv_t), C.POINTER(C.c_int)]
         L.orc_smem1.restype = C.c_int
@@ -60,6 +65,14 @@ class Oracle:
         r = orc_aln_t()
         self.lib.orc_ksw_align2(len(q), bytes(q), len(t), bytes(t), mat, o_del, e_del, o_ins, e_ins, xtra, C.byref(r))
         return (r.score, r.te, r.qe, r.score2, r.te2, r.tb, r.qb), r.cells
+
+    def global2(self, q, t, mat, o_del, e_del, o_ins, e_ins, w):
+        """-> (score, [cigar ops as len << 4 | op]), band cells"""
+        n, cg, cells = C.c_int(), C.POINTER(C.c_uint32)(), C.c_int64()
+        sc = self.lib.orc_ksw_global2(len(q), bytes(q), len(t), bytes(t), mat, o_del, e_del, o_ins, e_ins, w, C.byref(n), C.byref(cg), C.byref(cells))
+        ops = [cg[i] for i in range(n.value)]
+        self.libc.free(cg)
+        return (sc, ops), cells.value
 
     def collect_intv(self, fm, seq, min_seed_len=19, split_factor=1.5, split_width=10, max_mem_intv=20):
         out = (orc_intv_t * (3 * len(seq) + 8))()
@@ -109,6 +122,9 @@ class Reference:
         L.ksw_extend2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int8)] + [C.c_int] * 8 + [C.POINTER(C.c_int)] * 5
         L.ksw_align2.restype = kswr_t
         L.ksw_align2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int8)] + [C.c_int] * 5 + [C.c_void_p]
+        L.ksw_global2.restype = C.c_int
+        L.ksw_global2.argtypes = [C.c_int, C.c_char_p, C.c_int, C.c_char_p, C.c_int, C.POINTER(C.c_int8)] + [C.c_int] * 5 + \
+            [C.POINTER(C.c_int), C.POINTER(C.POINTER(C.c_uint32))]
         L.bwa_idx_load.restype = C.POINTER(M.bwaidx_t)
         L.bwa_idx_load.argtypes = [C.c_char_p, C.c_int]
         L.bwt_extend.argtypes = [C.POINTER(M.bwt_t), C.POINTER(ref_bwtintv_t), C.POINTER(ref_bwtintv_t), C.c_int]
@@ -131,6 +147,13 @@ class Reference:
         qb, tb = C.create_string_buffer(bytes(q), len(q) + 16), C.create_string_buffer(bytes(t), len(t) + 16)
         r = self.lib.ksw_align2(len(q), qb, len(t), tb, 5, mat, o_del, e_del, o_ins, e_ins, xtra, None)
         return (r.score, r.te, r.qe, r.score2, r.te2, r.tb, r.qb)
+
+    def global2(self, q, t, mat, o_del, e_del, o_ins, e_ins, w):
+        n, cg = C.c_int(), C.POINTER(C.c_uint32)()
+        sc = self.lib.ksw_global2(len(q), bytes(q), len(t), bytes(t), 5, mat, o_del, e_del, o_ins, e_ins, w, C.byref(n), C.byref(cg))
+        ops = [cg[i] for i in range(n.value)]
+        self.libc.free(cg)
+        return (sc, ops)
 
     def smem1(self, bwt, seq, x, min_intv):
         mem = ref_bwtintv_v()

@@ -122,6 +122,49 @@ def test_align_batch_vs_oracle(aligner, orc, sixteen):
     assert st1["sw_cells"] - st0["sw_cells"] == cells          # padded query length x rows executed, both passes
 
 
+@pytest.mark.parametrize("squeeze", [False, True])
+def test_global_batch_vs_oracle(aligner, orc, squeeze, monkeypatch):
+    """ksw_global2 fuzz through the kernels of the CIGAR stage (k_global_lanes: band-wide circular row window in shared memory,
+    classes by window width; k_global_jobs: general path): score, CIGAR and cell count against the oracle's orc_ksw_global2 for
+    bands 1..200, tlen != qlen and gappy pairs with dozens of operations; squeeze: windows too small for the band, every job takes
+    the rerun pass"""
+    if squeeze:
+        monkeypatch.setenv("B200_GLOBAL_SQUEEZE", "1")
+    cases = fuzzgen.global_cases(71, 6000) + fuzzgen.global_cases(72, 300, max_q=600)
+    for c in cases:
+        c["t"] = c["t"] & 3
+    groups = {}
+    for i, c in enumerate(cases):
+        groups.setdefault(c["params"], []).append(i)
+    st0 = _aux_stats(aligner.lib)
+    got, cells, max_ops = {}, 0, 0
+    for params, idxs in groups.items():
+        a, b, od, ed, oi, ei = params
+        jobs = (M.b200_global_job_t * len(idxs))()
+        qs, ts, qo, to = [], [], 0, 0
+        for k, i in enumerate(idxs):
+            c = cases[i]
+            jobs[k].qlen, jobs[k].tlen, jobs[k].q_off, jobs[k].t_off, jobs[k].w = len(c["q"]), len(c["t"]), qo, to, c["w"]
+            qs.append(bytes(c["q"])); ts.append(bytes(c["t"]))
+            qo += len(c["q"]); to += len(c["t"])
+        qb, tb = b"".join(qs), b"".join(ts)
+        cig = C.POINTER(C.c_uint32)()
+        aligner.lib.b200_ksw_global2_batch(len(idxs), jobs, qb, len(qb), tb, len(tb), OL.default_mat(a, b), od, ed, oi, ei, C.byref(cig))
+        for k, i in enumerate(idxs):
+            got[i] = (jobs[k].score, [cig[jobs[k].cigar_off + x] for x in range(jobs[k].n_cigar)])
+        aligner.lib.b200_free(cig)
+    st1 = _aux_stats(aligner.lib)
+    for i, c in enumerate(cases):
+        a, b, od, ed, oi, ei = c["params"]
+        want, n_cells = orc.global2(c["q"], c["t"], OL.default_mat(a, b), od, ed, oi, ei, c["w"])
+        assert got[i] == want, (i, len(c["q"]), len(c["t"]), c["w"])
+        cells += n_cells
+        max_ops = max(max_ops, len(want[1]))
+    assert max_ops > 28                                   # (round 1's result record held 28 operations)
+    if not squeeze:
+        assert st1["global_cells"] - st0["global_cells"] == cells
+
+
 def test_golden_vectors_through_cabi(aligner):
     g = json.load(open(os.path.join(GOLD, "ksw_vectors.json")))
     ext = [dict(q=np.array(v["q"], np.uint8), t=np.array(v["t"], np.uint8), params=(v["a"], v["b"], v["o_del"], v["e_del"], v["o_ins"], v["e_ins"]),

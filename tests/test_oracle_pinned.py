@@ -42,6 +42,14 @@ def test_align_matches_reference(orc, ref, sixteen):
         assert orc.align(*args)[0] == ref.align(*args), c
 
 
+def test_global_matches_reference(orc, ref):
+    """orc_ksw_global2 (full-matrix restatement) against the reference's ksw_global2: score and CIGAR"""
+    for c in fuzzgen.global_cases(61, 1500):
+        a, b, od, ed, oi, ei = c["params"]
+        mat = OL.default_mat(a, b)
+        assert orc.global2(c["q"], c["t"], mat, od, ed, oi, ei, c["w"])[0] == ref.global2(c["q"], c["t"], mat, od, ed, oi, ei, c["w"]), (len(c["q"]), len(c["t"]), c["w"])
+
+
 def test_golden_vectors(orc):
     """golden input/output vectors recorded from the reference (travel to machines without the reference)"""
     with open(os.path.join(ROOT, "tests", "golden", "ksw_vectors.json")) as fh:

@@ -200,7 +200,7 @@ def test_single_job_wrappers(aligner, orc):
     for q in reads:
         for x in (0, len(q) // 3, len(q) - 1):
             for min_intv in (1, 3):
-                mem = M.bwtintv_v()
+                mem = OL.ref_bwtintv_v()
                 ret = lib.bwt_smem1(aligner.idx.contents.bwt, len(q), bytes(q), x, min_intv, C.byref(mem), None)
                 out = (OL.orc_intv_t * (len(q) + 1))()
                 n = C.c_int()

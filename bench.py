@@ -41,7 +41,8 @@ def parse_args():
     p.add_argument("--steps", type=int, default=8)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--ref-bp", type=int, default=100_000_000)
+    p.add_argument("--ref-bp", type=int, default=1_000_000_000,
+                   help="synthetic reference size: 100000000 = BASELINE configs[1], 3100000000 = configs[2] (human-sized)")
     p.add_argument("--pairs", type=int, default=1_000_000, help="simulated pairs per rank")
     p.add_argument("--read-len", type=int, default=150)
     p.add_argument("-K", type=int, default=100_000_000, dest="K")
@@ -60,6 +61,10 @@ def workload_dir(args):
     return d
 
 
+def n_contigs(args):
+    return 24 if args.ref_bp >= 2_000_000_000 else 4          # (configs[2]: 24 contigs with human-like length ratios)
+
+
 def ensure_index(args):
     """synthetic reference + bwa-compatible index files, cached under CACHE"""
     import numpy as np
@@ -68,12 +73,21 @@ def ensure_index(args):
     prefix = os.path.join(d, "ref.fa")
     if not os.path.exists(prefix + ".done"):
         t = time.time()
-        names, lengths, codes = simulate.make_reference(args.ref_bp, 4, seed=1)
+        names, lengths, codes = simulate.make_reference(args.ref_bp, n_contigs(args), seed=1)
+        t1 = time.time()
         index_build.build_index_from_codes(prefix, names, lengths, codes)
+        t2 = time.time()
         np.save(os.path.join(d, "codes.npy"), codes)
         np.save(os.path.join(d, "lengths.npy"), lengths)
         open(prefix + ".done", "w").write("ok")
-        log("[bench] built %d bp reference + index in %.1f s" % (args.ref_bp, time.time() - t))
+        try:
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.empty_cache()          # the builder's scratch goes back to the device before the library allocates
+        except ImportError:
+            pass
+        log("[bench] %d bp reference simulated in %.1f s, index built in %.1f s, files written in %.1f s"
+            % (args.ref_bp, t1 - t, t2 - t1, time.time() - t2))
     return prefix
 
 
@@ -155,9 +169,14 @@ def run_ref_driver(prefix, f1, f2, K, threads, digest=None):
                 raise RuntimeError("ref_driver failed:\n" + errbuf[0].decode()[-2000:])
         err = errbuf[0].decode()
         digest.n_bytes = n
+    chunk_sec = []
     for line in err.splitlines():
-        if line.startswith("[ref_driver]"):
+        if line.startswith("[ref_driver] chunk="):
             kv = dict(x.split("=") for x in line.split()[1:])
+            chunk_sec.append((int(kv["reads"]), float(kv["sec"])))
+        elif line.startswith("[ref_driver]"):
+            kv = dict(x.split("=") for x in line.split()[1:])
+            run_ref_driver.chunks = chunk_sec
             return int(kv["reads"]), float(kv["mem_process_seqs_sec"])
     raise RuntimeError("ref_driver printed no timing line:\n" + err[-2000:])
 
@@ -190,23 +209,30 @@ def record_bytes(path):
 
 
 def reference_arm(args, prefix):
-    """the reference's own CPU implementation of the path, all host threads, bounded samples of the workload"""
+    """the reference's own CPU implementation of the path, all host threads, bounded samples of the workload: ONE run of
+    oracle/_ref/ref_driver (the index is loaded once) over W + K chunks of the rank-0 read set, chunked by the reference hosts' rule
+    at the same -K; the first W chunks are the warm-up, the time of the K others is what is reported"""
     cores = os.cpu_count() or 1
     f1, f2 = ensure_reads(args, 0, args.pairs)
     rb = record_bytes(f1)
     n = min(args.ref_sample_pairs, args.pairs)
     d = workload_dir(args)
-    total_pairs, total_s = 0, 0.0
-    for step in range(args.warmup + args.steps):
-        first = (step * n) % max(1, args.pairs - n)
-        s1, s2 = os.path.join(d, "refsample_1.fq"), os.path.join(d, "refsample_2.fq")
-        slice_fastq(f1, s1, first, n, rb)
-        slice_fastq(f2, s2, first, n, rb)
-        reads, sec = run_ref_driver(prefix, s1, s2, args.K, cores)
+    s1, s2 = os.path.join(d, "refsample_1.fq"), os.path.join(d, "refsample_2.fq")
+    total = args.warmup + args.steps
+    with open(s1, "wb") as o1, open(s2, "wb") as o2:
+        for step in range(total):
+            first = (step * n) % max(1, args.pairs - n)
+            for src, dst in ((f1, o1), (f2, o2)):
+                with open(src, "rb") as fi:
+                    fi.seek(first * rb)
+                    dst.write(fi.read(n * rb))
+    run_ref_driver(prefix, s1, s2, args.K, cores)
+    chunks = run_ref_driver.chunks
+    assert len(chunks) == total, (len(chunks), total)
+    for step, (reads, sec) in enumerate(chunks):
         log("[bench] reference step %d: %d reads in %.3f s" % (step, reads, sec))
-        if step >= args.warmup:
-            total_pairs += reads // 2
-            total_s += sec
+    total_pairs = sum(r for r, _ in chunks[args.warmup:]) // 2
+    total_s = sum(t for _, t in chunks[args.warmup:])
     v = total_pairs / total_s
     sample = "%d pairs per step (one mem_process_seqs call, -t %d) of the same simulated read set" % (n, cores)
     return {"metric": "aligned 2x150bp read pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -218,8 +244,10 @@ def reference_arm(args, prefix):
 
 
 def workload_config(args, what):
-    return {"workload": "configs[1]: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (4 contigs, 5%% planted repeats), -K %d"
-                        % (args.pairs, args.read_len, args.ref_bp, args.K),
+    which = ("configs[1]" if args.ref_bp == 100_000_000 else "configs[2] reference (human-sized), read set of configs[1]" if args.ref_bp >= 3_000_000_000
+             else "configs[1] read set against a reference %dx larger than configs[1]'s, beyond the 126 MB L2 (configs[2]'s 3.1 Gbp: --ref-bp 3100000000)" % (args.ref_bp // 100_000_000))
+    return {"workload": "%s: %d synthetic 2x%dbp pairs per GPU vs synthetic %d bp reference (%d contigs, 5%% planted repeats), -K %d"
+                        % (which, args.pairs, args.read_len, args.ref_bp, n_contigs(args), args.K),
             "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, up to four chunks in flight, each as one batch per kernel" % ((args.K // 2) // args.read_len + 1),
             "path": what, "cache_policy": "steps cycle over the rank's %d chunks (consecutive steps never align the same chunk; with up to four chunks in "
                                           "flight a chunk may be in flight twice); index (%d MB) + per-chunk buffers exceed the 126 MB L2; an L2-sized buffer "

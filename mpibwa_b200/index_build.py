@@ -10,9 +10,11 @@ reference *reads*:
   .bwt  primary, L2[1..4], occ-interleaved BWT of fwd+revcomp text (reader: reference src/bwt.c:443-462)
   .sa   primary, L2[1..4], sa_intv, seq_len, samples (reader: reference src/bwt.c:421-441)
 
-The suffix array is built by a radix-style sort of 31-mers (torch.sort; runs on the GPU when one is present)
-followed by rounds that refine the groups of still-equal suffixes by their next 31-mer.  This is tooling, not
-part of the alignment hot path.
+The suffix array is built bucket range by bucket range (12-base prefixes; a radix sort of the 31-base keys of one range -
+torch.sort, on the GPU when one is present - followed by rounds that refine the groups of still-equal suffixes by their next
+31 bases), so that memory stays a few arrays of one range whatever the reference size: a human-sized reference (2 x 3.1 G
+suffixes) is built on one B200.  BWT symbols and sampled rows are taken from each slice as it is produced and the
+occ-interleaved layout is packed on the device.  This is tooling, not part of the alignment hot path.
 """
 from __future__ import annotations
 
@@ -107,11 +109,13 @@ def encode_contigs(contigs):
 
 def write_pac_ann_amb(prefix, codes, anns, ambs):
     l_pac = len(codes)
-    pad = (-l_pac) % 4
-    c = np.concatenate([codes, np.zeros(pad, np.uint8)]).reshape(-1, 4)
-    pac = (c[:, 0] << 6 | c[:, 1] << 4 | c[:, 2] << 2 | c[:, 3]).astype(np.uint8)
     with open(prefix + ".pac", "wb") as fh:
-        fh.write(pac.tobytes())
+        step = 1 << 28                                       # (slices: a human-sized reference is 3.1 G codes)
+        for b0 in range(0, l_pac, step):
+            seg = codes[b0:min(l_pac, b0 + step)]
+            pad = (-len(seg)) % 4
+            c = (np.concatenate([seg, np.zeros(pad, np.uint8)]) if pad else seg).reshape(-1, 4)
+            fh.write((c[:, 0] << 6 | c[:, 1] << 4 | c[:, 2] << 2 | c[:, 3]).astype(np.uint8).tobytes())
         if l_pac % 4 == 0:
             fh.write(b"\0")
         fh.write(bytes([l_pac % 4]))
@@ -127,153 +131,247 @@ def write_pac_ann_amb(prefix, codes, anns, ambs):
             fh.write("%d %d %c\n" % (off, ln, ch))
 
 
-def _kmer31(text: torch.Tensor) -> torch.Tensor:
-    """int64 key of the 31 bases starting at every position (zero padded past the end)"""
-    n = text.numel()
-    k = text.to(torch.int64)
-
-    def shifted(x, d):
-        out = torch.zeros_like(x)
-        if d < n:
-            out[: n - d] = x[d:]
-        return out
-
-    k = (k << 2) | shifted(k, 1)            # 2 bases
-    k = (k << 4) | shifted(k, 2)            # 4
-    k = (k << 8) | shifted(k, 4)            # 8
-    k = (k << 16) | shifted(k, 8)           # 16 bases = 32 bits
-    k = (k << 30) | (shifted(k, 16) >> 2)   # 31 bases = 62 bits
-    return k
+K = 31                      # bases per sort key (62 bits of an int64)
+_PREFIX = 12                # bases of the bucket prefix (4^12 buckets)
 
 
-def suffix_array(codes: np.ndarray, device=None) -> np.ndarray:
-    """Suffix array (int64[n]) of the text with an implicit sentinel smaller than every base."""
+class _Text:
+    """2-bit text packed 32 bases per int64 word (first base in the top bits) with the key of any position two gathers away"""
+
+    def __init__(self, codes: np.ndarray, device):
+        self.n = n = len(codes)
+        self.device = device
+        nw = (n + 31) // 32 + 2
+        self.words = torch.zeros(nw, dtype=torch.int64, device=device)
+        self.text = torch.from_numpy(np.ascontiguousarray(codes)).to(device)
+        sh = (62 - 2 * torch.arange(32, device=device)).to(torch.int64)
+        step = 1 << 26                                       # bases per slice (32 x 8 bytes of scratch each)
+        for b0 in range(0, n, step):
+            b1 = min(n, b0 + step)
+            m = (b1 - b0 + 31) // 32
+            blk = torch.zeros(m * 32, dtype=torch.int64, device=device)
+            blk[: b1 - b0] = self.text[b0:b1]
+            self.words[b0 // 32: b0 // 32 + m] = (blk.view(m, 32) << sh).sum(dim=1)     # (disjoint bit fields: the sum is an OR)
+            del blk
+
+    def key(self, pos: torch.Tensor) -> torch.Tensor:
+        """the K = 31 bases starting at pos as a non-negative int64 (zero padded past the end)"""
+        pos = torch.clamp(pos, max=self.n)                   # (positions past the end read the zero padding)
+        q = pos >> 5
+        r = (pos & 31) << 1
+        hi = self.words[q]
+        lo = self.words[q + 1]
+        a = (torch.bitwise_left_shift(hi, r) >> 2) & 0x3FFFFFFFFFFFFFFF
+        sh = torch.clamp(66 - r, max=63)
+        b = torch.where(r >= 4, torch.bitwise_right_shift(lo, sh) & (torch.bitwise_left_shift(torch.ones_like(r), torch.clamp(r - 2, min=0)) - 1),
+                        torch.zeros_like(lo))
+        return a | b
+
+
+def _sa_batches(codes: np.ndarray, device=None, batch=None):
+    """Suffix array of the text (implicit sentinel smaller than every base), in order, as a stream of slices.
+
+    Bucketed: a histogram of the 12-base prefixes cuts the suffixes into ranges of at most `batch` suffixes; each range is
+    sorted by its 31-base key (one radix sort: torch.sort), then the groups of still-equal suffixes are refined by their next
+    31 bases until no group is left.  Peak memory is a few arrays of `batch` int64 beside the text, whatever the text size, so a
+    human-sized reference (2 x 3.1 G suffixes) fits one B200.  Yields (first_row, sa_slice int64 tensor on `device`)."""
     n = len(codes)
     if device is None:
         device = "cuda" if torch.cuda.is_available() else "cpu"
-    text = torch.from_numpy(np.ascontiguousarray(codes)).to(device)
-    K = 31
-    key = _kmer31(text)
-    ntr = min(K - 1, n)                      # suffixes shorter than K bases: positions n-ntr .. n-1
-    order0 = torch.cat([torch.arange(n - 1, n - 1 - ntr, -1, device=device), torch.arange(0, n - ntr, device=device)])
-    skey, perm = torch.sort(key[order0], stable=True)
-    sa = order0[perm]
-    del perm, order0
-    trunc = sa > n - K
-    same = torch.zeros(n, dtype=torch.bool, device=device)
-    same[1:] = (skey[1:] == skey[:-1]) & ~trunc[1:] & ~trunc[:-1]
-    del skey, trunc
-    # group id = index of the first element of the run of equal keys
-    idx = torch.arange(n, device=device)
-    start = torch.where(same, torch.zeros_like(idx), idx)
-    grp = torch.cummax(start, 0).values
-    del start
-    nxt = torch.zeros(n, dtype=torch.bool, device=device)
-    nxt[:-1] = same[1:]
-    active = torch.nonzero(same | nxt).flatten()
-    del same, nxt, idx
-    depth = K
-    while active.numel() > 0:
-        pos = sa[active]
-        g = grp[active]
-        p2 = pos + depth
-        inb = p2 < n
-        k2 = torch.where(inb, key[torch.clamp(p2, max=n - 1)], torch.zeros_like(p2))
-        vlen = torch.clamp(n - p2, min=0, max=K)
-        # order inside a group: by next 31-mer; among equal padded keys the shorter (truncated) suffix first
-        o = torch.sort(vlen, stable=True).indices
-        o = o[torch.sort(k2[o], stable=True).indices]
-        o = o[torch.sort(g[o], stable=True).indices]
-        pos, g, k2, vlen = pos[o], g[o], k2[o], vlen[o]
-        sa[active] = pos
-        m = active.numel()
+    if batch is None:
+        batch = 1 << 29 if str(device).startswith("cuda") else 1 << 24
+    T = _Text(codes, device)
+    if n == 0:
+        return
+    shift = 2 * (K - _PREFIX)
+    nb = 1 << (2 * _PREFIX)
+    step = 1 << 27
+    # ---- histogram of the bucket prefixes
+    hist = torch.zeros(nb, dtype=torch.int64, device=device)
+    for b0 in range(0, n, step):
+        pos = torch.arange(b0, min(n, b0 + step), device=device)
+        hist += torch.bincount(T.key(pos) >> shift, minlength=nb)
+        del pos
+    cum = torch.cumsum(hist, 0).cpu().numpy()
+    # ---- ranges of whole buckets of at most `batch` suffixes (a single bucket may exceed it: poly-A runs ...)
+    bounds = [0]
+    while bounds[-1] < nb:
+        lo = bounds[-1]
+        base = int(cum[lo - 1]) if lo else 0
+        hi = int(np.searchsorted(cum, base + batch, side="right"))
+        bounds.append(min(nb, max(hi, lo + 1)))
+    ntr = min(K - 1, n)                                      # suffixes shorter than K bases: positions n-ntr .. n-1
+    row = 0
+    for lo, hi in zip(bounds[:-1], bounds[1:]):
+        m_expect = int(cum[hi - 1]) - (int(cum[lo - 1]) if lo else 0)
+        if m_expect == 0:
+            continue
+        parts = []
+        for b0 in range(0, n, step):
+            pos = torch.arange(b0, min(n, b0 + step), device=device)
+            kb = T.key(pos) >> shift
+            parts.append(pos[(kb >= lo) & (kb < hi)])
+            del pos, kb
+        pos = torch.cat(parts)
+        del parts
+        # truncated suffixes first, shortest first: the stable sort keeps them in front of the full suffixes with the same padded key
+        tr = pos >= n - ntr
+        if bool(tr.any()):
+            pos = torch.cat([torch.flip(pos[tr], [0]), pos[~tr]])
+        del tr
+        key = T.key(pos)
+        skey, perm = torch.sort(key, stable=True)
+        sa = pos[perm]
+        del perm, key, pos
+        m = sa.numel()
+        trunc = sa > n - K
         same = torch.zeros(m, dtype=torch.bool, device=device)
-        same[1:] = (g[1:] == g[:-1]) & (k2[1:] == k2[:-1]) & (vlen[1:] == K) & (vlen[:-1] == K)
-        ar = torch.arange(m, device=device)
-        start = torch.where(same, torch.zeros_like(ar), ar)
-        first = torch.cummax(start, 0).values
-        grp[active] = active[first]
+        same[1:] = (skey[1:] == skey[:-1]) & ~trunc[1:] & ~trunc[:-1]
+        del skey, trunc
+        idx = torch.arange(m, device=device)
+        grp = torch.cummax(torch.where(same, torch.zeros_like(idx), idx), 0).values      # group id = index of its first element
         nxt = torch.zeros(m, dtype=torch.bool, device=device)
         nxt[:-1] = same[1:]
-        active = active[same | nxt]
-        depth += K
-    return sa.cpu().numpy()
+        active = torch.nonzero(same | nxt).flatten()
+        del same, nxt, idx
+        depth = K
+        while active.numel() > 0:
+            p = sa[active]
+            g = grp[active]
+            p2 = p + depth
+            k2 = T.key(p2)
+            vlen = torch.clamp(n - p2, min=0, max=K)
+            # order inside a group: by next 31 bases; among equal padded keys the shorter (truncated) suffix first
+            o = torch.sort(vlen, stable=True).indices
+            o = o[torch.sort(k2[o], stable=True).indices]
+            o = o[torch.sort(g[o], stable=True).indices]
+            p, g, k2, vlen = p[o], g[o], k2[o], vlen[o]
+            sa[active] = p
+            ma = active.numel()
+            same = torch.zeros(ma, dtype=torch.bool, device=device)
+            same[1:] = (g[1:] == g[:-1]) & (k2[1:] == k2[:-1]) & (vlen[1:] == K) & (vlen[:-1] == K)
+            ar = torch.arange(ma, device=device)
+            first = torch.cummax(torch.where(same, torch.zeros_like(ar), ar), 0).values
+            grp[active] = active[first]
+            nx = torch.zeros(ma, dtype=torch.bool, device=device)
+            nx[:-1] = same[1:]
+            active = active[same | nx]
+            depth += K
+        del grp
+        assert m == m_expect
+        yield row, sa
+        row += m
+        del sa
 
 
-def build_bwt_sa(codes_fwd: np.ndarray, sa_intv=32, device=None):
-    """-> dict(primary, L2[5], seq_len, bwt uint32[bwt_size] (occ-interleaved), sa uint64[n_sa])"""
+def suffix_array(codes: np.ndarray, device=None, batch=None) -> np.ndarray:
+    """Suffix array (int64[n]) of the text with an implicit sentinel smaller than every base."""
+    parts = [sa.cpu().numpy() for _, sa in _sa_batches(codes, device, batch)]
+    return np.concatenate(parts) if parts else np.zeros(0, np.int64)
+
+
+def build_bwt_sa(codes_fwd: np.ndarray, sa_intv=32, device=None, batch=None):
+    """-> dict(primary, L2[5], seq_len, bwt uint32[bwt_size] (occ-interleaved), sa uint64[n_sa]).  The suffix array is consumed
+    slice by slice (BWT symbols and the sampled rows are all that is kept), and the occ-interleaved layout is packed on the device."""
+    if device is None:
+        device = "cuda" if torch.cuda.is_available() else "cpu"
     l_pac = len(codes_fwd)
-    text = np.concatenate([codes_fwd, (3 - codes_fwd[::-1]).astype(np.uint8)])
-    n = len(text)
-    sa = suffix_array(text, device)
-    row0 = int(np.flatnonzero(sa == 0)[0])
-    primary = row0 + 1
+    text_np = np.concatenate([codes_fwd, (3 - codes_fwd[::-1]).astype(np.uint8)])
+    n = len(text_np)
+    text = torch.from_numpy(text_np).to(device)
+    # rows of the (n+1)-row matrix: row 0 is the sentinel suffix, row i+1 is suffix sa[i]; bw_full[row] = the base before the suffix
+    bw_full = torch.empty(n + 1, dtype=torch.uint8, device=device)
+    bw_full[0] = text[n - 1]
+    n_sa = (n + sa_intv) // sa_intv
+    sa_s = torch.zeros(n_sa, dtype=torch.int64, device=device)
+    primary = -1
+    for row, sa in _sa_batches(text_np, device, batch):
+        m = sa.numel()
+        z = torch.nonzero(sa == 0).flatten()
+        if z.numel():
+            primary = row + int(z[0]) + 1
+        bw_full[row + 1: row + 1 + m] = text[torch.clamp(sa - 1, min=0)]
+        # sampled rows: matrix row j * sa_intv holds suffix sa[j * sa_intv - 1]
+        j0 = (row + 1 + sa_intv - 1) // sa_intv
+        j1 = (row + m) // sa_intv
+        if j1 >= j0 and j1 >= 1:
+            j = torch.arange(max(j0, 1), j1 + 1, device=device)
+            sa_s[j] = sa[j * sa_intv - 1 - row]
+        del sa
+    assert primary > 0
     # BWT column without the sentinel row
-    prev = sa - 1
-    bw = np.empty(n, dtype=np.uint8)
-    bw[0] = text[n - 1]
-    keep = np.ones(n, dtype=bool)
-    keep[row0] = False
-    bw[1:] = text[prev[keep]]
-    cnt = np.bincount(text, minlength=4).astype(np.uint64)
+    bw = torch.cat([bw_full[:primary], bw_full[primary + 1:]])
+    del bw_full
+    cnt = torch.bincount(text.to(torch.int64) if n < (1 << 24) else text[: 1 << 24].to(torch.int64), minlength=4)
+    if n >= (1 << 24):
+        cnt = torch.zeros(4, dtype=torch.int64, device=device)
+        for b0 in range(0, n, 1 << 28):
+            cnt += torch.bincount(text[b0:b0 + (1 << 28)].to(torch.int64), minlength=4)
     L2 = np.zeros(5, dtype=np.uint64)
-    L2[1:] = np.cumsum(cnt)
-    # 2-bit pack, first symbol in the top bits of each word
+    L2[1:] = np.cumsum(cnt.cpu().numpy().astype(np.uint64))
+    del text
+    # occ interleave: per 128 symbols 4 x uint64 counts-before followed by the (up to) 8 words of 16 two-bit symbols (first
+    # symbol in the top bits of each word); one more count record closes the array
     n_words = (n + 15) >> 4
-    padded = np.zeros(n_words * 16, dtype=np.uint32)
-    padded[:n] = bw
-    shifts = (30 - 2 * np.arange(16)).astype(np.uint32)
-    words = np.bitwise_or.reduce(padded.reshape(-1, 16) << shifts, axis=1).astype(np.uint32)
-    # occ interleave: per 128 symbols 4 x uint64 counts-before followed by the (up to) 8 symbol words
     n_blk = (n + OCC_INTERVAL - 1) // OCC_INTERVAL
-    blk_pad = np.full(n_blk * OCC_INTERVAL, 4, dtype=np.uint8)
-    blk_pad[:n] = bw
-    blk = blk_pad.reshape(n_blk, OCC_INTERVAL)
-    per = np.stack([(blk == c).sum(axis=1) for c in range(4)], axis=1).astype(np.uint64)
-    before = np.zeros((n_blk + 1, 4), dtype=np.uint64)
-    before[1:] = np.cumsum(per, axis=0)
     bwt_size = n_words + (n_blk + 1) * 8
-    wpad = np.zeros(n_blk * 8, dtype=np.uint32)
-    wpad[:n_words] = words
-    rec = np.zeros((n_blk, 16), dtype=np.uint32)
-    rec[:, :8] = before[:n_blk].view(np.uint32).reshape(n_blk, 8)
-    rec[:, 8:] = wpad.reshape(n_blk, 8)
+    rec = np.zeros((n_blk + 1, 16), dtype=np.uint32)
+    sh16 = (30 - 2 * torch.arange(16, device=device)).to(torch.int64)
+    run = torch.zeros(4, dtype=torch.int64, device=device)
+    step = 1 << 20                                           # blocks per slice
+    for k0 in range(0, n_blk, step):
+        k1 = min(n_blk, k0 + step)
+        sl = torch.full(((k1 - k0) * OCC_INTERVAL,), 4, dtype=torch.uint8, device=device)
+        seg = bw[k0 * OCC_INTERVAL: min(n, k1 * OCC_INTERVAL)]
+        sl[: seg.numel()] = seg
+        blk = sl.view(k1 - k0, OCC_INTERVAL)
+        per = torch.stack([(blk == c).sum(dim=1) for c in range(4)], dim=1).to(torch.int64)
+        before = torch.cumsum(per, 0) - per + run
+        run = run + per.sum(dim=0)
+        sym = torch.where(sl < 4, sl, torch.zeros_like(sl)).to(torch.int64).view(-1, 16)
+        words = (sym << sh16).sum(dim=1).view(k1 - k0, 8)
+        out = torch.empty((k1 - k0, 16), dtype=torch.int64, device=device)
+        out[:, 0:8:2] = before & 0xFFFFFFFF
+        out[:, 1:8:2] = before >> 32
+        out[:, 8:] = words
+        rec[k0:k1] = out.cpu().numpy().astype(np.uint32)
+        del sl, blk, per, before, sym, words, out
+    rec[n_blk, 0:8:2] = (run & 0xFFFFFFFF).cpu().numpy().astype(np.uint32)
+    rec[n_blk, 1:8:2] = (run >> 32).cpu().numpy().astype(np.uint32)
     flat = rec.reshape(-1)
     tail_words = n_words - (n_blk - 1) * 8 if n_blk else 0
-    body = flat[: (n_blk - 1) * 16 + 8 + tail_words] if n_blk else flat[:0]
-    bwt = np.concatenate([body, before[n_blk].view(np.uint32)])
+    bwt = np.concatenate([flat[: (n_blk - 1) * 16 + 8 + tail_words] if n_blk else flat[:0], flat[n_blk * 16: n_blk * 16 + 8]])
     assert len(bwt) == bwt_size, (len(bwt), bwt_size)
-    # sampled suffix array in the (n+1)-row coordinate system; row 0 is the sentinel suffix
-    n_sa = (n + sa_intv) // sa_intv
-    rows = np.arange(1, n_sa, dtype=np.int64) * sa_intv
-    sa_s = np.empty(n_sa, dtype=np.uint64)
-    sa_s[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
-    sa_s[1:] = sa[rows - 1].astype(np.uint64)
-    return dict(primary=primary, L2=L2, seq_len=n, bwt=bwt, sa=sa_s, sa_intv=sa_intv, l_pac=l_pac)
+    sa_np = sa_s.cpu().numpy().astype(np.uint64)
+    sa_np[0] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    if str(device).startswith("cuda"):
+        del bw, sa_s
+        torch.cuda.empty_cache()
+    return dict(primary=primary, L2=L2, seq_len=n, bwt=bwt, sa=sa_np, sa_intv=sa_intv, l_pac=l_pac)
 
 
 def write_bwt_sa(prefix, idx):
     hdr = np.array([idx["primary"], *idx["L2"][1:5]], dtype=np.uint64)
     with open(prefix + ".bwt", "wb") as fh:
         fh.write(hdr.tobytes())
-        fh.write(idx["bwt"].tobytes())
+        idx["bwt"].tofile(fh)
     with open(prefix + ".sa", "wb") as fh:
         fh.write(hdr.tobytes())
         fh.write(np.array([idx["sa_intv"], idx["seq_len"]], dtype=np.uint64).tobytes())
-        fh.write(idx["sa"][1:].tobytes())
+        idx["sa"][1:].tofile(fh)
 
 
-def build_index(fasta_path, prefix=None, sa_intv=32, device=None):
+def build_index(fasta_path, prefix=None, sa_intv=32, device=None, batch=None):
     """`bwa index` equivalent: writes <prefix>.{pac,ann,amb,bwt,sa}; returns the prefix."""
     prefix = prefix or fasta_path
     contigs = read_fasta(fasta_path)
     codes, anns, ambs = encode_contigs(contigs)
     write_pac_ann_amb(prefix, codes, anns, ambs)
-    write_bwt_sa(prefix, build_bwt_sa(codes, sa_intv, device))
+    write_bwt_sa(prefix, build_bwt_sa(codes, sa_intv, device, batch))
     return prefix
 
 
-def build_index_from_codes(prefix, names, lengths, codes, sa_intv=32, device=None):
+def build_index_from_codes(prefix, names, lengths, codes, sa_intv=32, device=None, batch=None):
     """Index an N-free reference given directly as base codes (skips FASTA parsing); also writes <prefix> FASTA-less."""
     anns, off = [], 0
     for nm, ln in zip(names, lengths):
@@ -281,7 +379,7 @@ def build_index_from_codes(prefix, names, lengths, codes, sa_intv=32, device=Non
         off += int(ln)
     assert off == len(codes)
     write_pac_ann_amb(prefix, codes, anns, [])
-    write_bwt_sa(prefix, build_bwt_sa(codes, sa_intv, device))
+    write_bwt_sa(prefix, build_bwt_sa(codes, sa_intv, device, batch))
     return prefix
 
 

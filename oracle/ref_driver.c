@@ -13,7 +13,8 @@
  *   -T  use the trimmed-pairs rule (R1+R2 bases against K, running n_processed)
  *   -H  print @SQ header lines first
  * Output: SAM records on stdout (no @PG line: it embeds argv in the reference).
- * Timing of the mem_process_seqs calls alone is printed to stderr as
+ * Timing of the mem_process_seqs calls alone is printed to stderr, per chunk and in total, as
+ *   [ref_driver] chunk=<k> reads=<n> sec=<s>
  *   [ref_driver] reads=<n> chunks=<c> mem_process_seqs_sec=<s>
  */
 #include <stdio.h>
@@ -153,6 +154,7 @@ int main(int argc, char **argv)
 			double t0 = now();
 			mem_process_seqs(opt, idx->bwt, idx->bns, idx->pac, trimmed ? n_processed : 0, (int)n, seqs, pes0);
 			t_mem += now() - t0;
+			fprintf(stderr, "[ref_driver] chunk=%zu reads=%zu sec=%.4f\n", n_chunks, n, now() - t0);
 			n_processed += n;
 			for (k = 0; k < n; ++k) { fputs(seqs[k].sam, stdout); free(seqs[k].sam); }
 			beg = i + 1; bases = 0; ++n_chunks;

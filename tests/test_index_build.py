@@ -6,11 +6,13 @@ from mpibwa_b200 import index_build, simulate
 
 
 def test_rebuild_hg19_small(examples, tmp_path):
+    """one bucket range, and many small ones (the way a human-sized reference is built: memory bounded by the range size)"""
     fa = examples["idx"]
-    prefix = str(tmp_path / "rebuilt.fa")
-    index_build.build_index(fa, prefix, device="cpu")
-    for ext in (".pac", ".ann", ".amb", ".bwt", ".sa"):
-        assert open(prefix + ext, "rb").read() == open(fa + ext, "rb").read(), ext
+    for batch in (None, 300_000):
+        prefix = str(tmp_path / ("rebuilt%s.fa" % batch))
+        index_build.build_index(fa, prefix, device="cpu", batch=batch)
+        for ext in (".pac", ".ann", ".amb", ".bwt", ".sa"):
+            assert open(prefix + ext, "rb").read() == open(fa + ext, "rb").read(), (ext, batch)
 
 
 def test_suffix_array_small_texts():
@@ -19,10 +21,10 @@ def test_suffix_array_small_texts():
         t = rng.integers(0, alphabet, size=n).astype(np.uint8)
         if n == 300:
             t[100:200] = t[0:100]          # long exact repeat -> several refinement rounds
-        sa = index_build.suffix_array(t, device="cpu")
         s = bytes(t + 1)
         want = sorted(range(n), key=lambda i: s[i:])
-        assert sa.tolist() == want, n
+        for batch in (None, 7):
+            assert index_build.suffix_array(t, device="cpu", batch=batch).tolist() == want, (n, batch)
 
 
 def test_simulator_is_seeded():

@@ -41,7 +41,7 @@ def parse_args():
     p.add_argument("--steps", type=int, default=8)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--ref-bp", type=int, default=1_000_000_000,
+    p.add_argument("--ref-bp", type=int, default=3_100_000_000,
                    help="synthetic reference size: 100000000 = BASELINE configs[1], 3100000000 = configs[2] (human-sized)")
     p.add_argument("--pairs", type=int, default=1_000_000, help="simulated pairs per rank")
     p.add_argument("--read-len", type=int, default=150)

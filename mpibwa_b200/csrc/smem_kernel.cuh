@@ -68,6 +68,17 @@ B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t 
 	if (is_back) { o0 = nb; o1 = oth; } else { o1 = nb; o0 = oth; }
 }
 
+#if defined(__CUDACC__)
+// non-binding L2 prefetch of the two occ sectors a backward extension of the interval (x0, .., x2) will read
+__device__ __forceinline__ void fm_prefetch_back(const FmView &fm, uint64_t x0, uint64_t x2)
+{
+	const uint64_t k = x0 - 1, l = x0 - 1 + x2;
+	const uint64_t ka = k == (uint64_t)-1 ? 0 : k - (k >= fm.primary), la = l == (uint64_t)-1 ? 0 : l - (l >= fm.primary);
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(fm.occ + ((ka >> 6) << 3)));
+	asm volatile("prefetch.global.L2 [%0];" :: "l"(fm.occ + ((la >> 6) << 3)));
+}
+#endif
+
 // The interval list of one lane.  Entry k < quota lives in shared memory (sh[(k*4 + word) * stride]), the rest in the
 // lane's global strip (spill[(k - quota) * sstride]).  Values up to 2^33-1, end positions up to 2^29-1.
 struct SeedList {

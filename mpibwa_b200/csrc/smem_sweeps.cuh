@@ -200,6 +200,15 @@ struct BwdLane {
 			}
 		}
 	}
+	// the entry after the current one in the row being extended (its extension is independent of the current one: reference
+	// src/bwt.c:326-345 walks the row's entries with the same base); false at the end of the row
+	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p2) const
+	{
+		if (st != BWD || j + 1 >= n_prev) return false;
+		uint64_t p1; int pe;
+		L.get(n_list - 2 - j, p0, p1, p2, pe);
+		return true;
+	}
 	// digest one backward extension; true = next extension ready, false = advance() needed
 	B200_HD bool step(const SeedOpt &so, int cap, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
 	{
@@ -291,6 +300,10 @@ __global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
 		}
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
+			// the two occ sectors of the FOLLOWING entry of the row are on their way to L2 while this one is digested: the entries
+			// of a row are independent, so a lane keeps two extensions in flight instead of one dependent round trip per loop trip
+			uint64_t p0, p2;
+			if (ln.peek(L, p0, p2)) fm_prefetch_back(a.fm, p0, p2);
 			uint64_t o0, o1, o2;
 			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, o0, o1, o2, blocks);
 			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) need = ln.advance(a.so, a.cap, L);

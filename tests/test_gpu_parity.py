@@ -213,11 +213,8 @@ def test_single_job_wrappers(aligner, orc):
     if have_ref():
         ref = OL.Reference()
         ref.lib.ksw_global2.argtypes = lib.ksw_global2.argtypes
-        rng = np.random.default_rng(77)
-        for _ in range(60):
-            ql, w = int(rng.integers(1, 200)), int(rng.integers(1, 120))
-            t = rng.integers(0, 4, size=max(1, ql + int(rng.integers(-min(w, ql) + 1, w))), dtype=np.uint8)
-            q = fuzzgen.mutate(rng, t[:ql] if len(t) >= ql else np.resize(t, ql), 0.05, 0.03, 0.01)
+        for c in fuzzgen.global_cases(77, 60):            # (bands that reach the last cell: |tlen - qlen| <= w, as every caller guarantees)
+            q, t, w = c["q"], c["t"] & 3, c["w"]
             outs = []
             for L in (lib, ref.lib):
                 n_cigar, cigar = C.c_int(), C.POINTER(C.c_uint32)()

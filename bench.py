@@ -592,6 +592,9 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     hbm_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback"
     i32_peak = int32_peak_gops(torch)
+    # what the device delivers to random 32-byte sectors of a table of the index's size (the FM-index kernels' pattern)
+    occ_bytes = int(args.ref_bp)                           # occ sectors: 0.5 byte per BWT symbol, 2 symbols per base
+    rnd_peak = lib.b200_hbm_random_sector_peak(torch.cuda.current_device(), max(occ_bytes, 1 << 26))
     K = args.steps
     kern = kernel_table(agg, K, i32_peak, hbm_peak)
     kern_iso = kernel_table(st_iso, 1, i32_peak, hbm_peak)
@@ -611,6 +614,10 @@ def main():
             traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
                 "traffic": traffic, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()",
+                "random_sector_peak": {"value": rnd_peak, "unit": "GB/s", "table_bytes": occ_bytes,
+                                       "frac_of_it": (kd["achieved"] / rnd_peak) if kd["bound"] == "hbm" and rnd_peak else None,
+                                       "what": "measured live (b200_hbm_random_sector_peak): independent 256-bit loads of uniformly random 32-byte sectors of a table "
+                                               "the size of the occ table - the access pattern of the seeding / SA kernels; `peak` above stays the streaming copy bandwidth"},
                 "measured": ("one chunk alone on the device (untimed extra pass of this run; in the timed region up to %d chunks share the SMs "
                              "and the per-launch durations overlap)" % N_SLOTS) if concurrent else "timed region"}
     line = {

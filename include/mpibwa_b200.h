@@ -361,6 +361,9 @@ b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
  * roofline denominator) and with half of the work as IMAD on the FMA pipe (dual-pipe ceiling) */
 double b200_int32_peak(int device);
 double b200_int32_peak_dual_pipe(int device);
+/* measured bandwidth (GB/s) the device delivers to the FM-index kernels' access pattern: independent 256-bit loads of uniformly
+ * random 32-byte sectors of a table of table_bytes (the roofline of the seeding / SA kernels once the index outgrows L2) */
+double b200_hbm_random_sector_peak(int device, size_t table_bytes);
 const char *b200_version(void);
 
 #ifdef __cplusplus

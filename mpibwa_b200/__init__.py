@@ -157,6 +157,7 @@ _PROTOTYPES = {
     "b200_get_stats": (None, [C.POINTER(b200_stats_t)]),
     "b200_get_aux_stats": (None, [C.POINTER(b200_stats_t)]),
     "b200_ext_replay": (C.c_double, [C.POINTER(mem_opt_t), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "b200_hbm_random_sector_peak": (C.c_double, [C.c_int, C.c_size_t]),
     "b200_int32_peak": (C.c_double, [C.c_int]),
     "b200_int32_peak_dual_pipe": (C.c_double, [C.c_int]),
     "b200_version": (C.c_char_p, []),

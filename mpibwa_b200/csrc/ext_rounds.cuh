@@ -215,6 +215,19 @@ __device__ __forceinline__ int ext_tbase(const uint8_t *__restrict__ src, int64_
 	return comp ? 3 - b : b;
 }
 
+// The target of a job is a window of the 2-bit reference at a random place (775 MB for a human-sized reference: a DRAM miss per
+// 128-byte line), read one base per DP row.  Asking for its lines up front turns the serialised misses of the row loop - where the
+// whole warp waits for the lane that crossed into a new line - into one overlapped batch behind the query staging.
+// `first`, `step`: which of the window's lines this thread asks for (all of them: 0, 1; one warp per job: lane, 32).
+__device__ __forceinline__ void ext_prefetch_target(const uint8_t *__restrict__ pac, int64_t f0, int fstep, int tlen, int comp, int first, int step)
+{
+	if (comp == 2 || tlen <= 0) return;
+	const int64_t fe = f0 + (int64_t)fstep * (tlen - 1);
+	const int64_t lo = (f0 < fe ? f0 : fe) >> 2, hi = (f0 < fe ? fe : f0) >> 2;
+	for (int64_t a = (lo & ~(int64_t)127) + (int64_t)first * 128; a <= hi; a += (int64_t)step * 128)
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(pac + a));
+}
+
 // Query bytes live in shared memory as [column/4][lane][column%4] (bank = lane for every lane/column combination).
 __device__ __forceinline__ int ext_qidx(int j) { return ((j >> 2) << 7) + (j & 3); }
 
@@ -267,6 +280,7 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 	jb.qlen = 0; jb.tlen = 0; jb.h0 = 1; jb.prev = -1; jb.bonus = 0; jb.f0 = 0; jb.fstep = 0; jb.comp = 0; jb.qaddr = 0; jb.qstep = 0; jb.w0 = 0;
 	bool alive = false;
 	if (t < n) { jp = &jobs[order[t]]; jb = *jp; alive = true; }
+	ext_prefetch_target(pac, jb.f0, jb.fstep, jb.tlen, jb.comp, 0, 1);
 	for (int j = 0; j < jb.qlen; ++j) Q[ext_qidx(j)] = codes[jb.qaddr + (int64_t)jb.qstep * j];
 	// per-attempt DP state
 	int aw = jb.w0 > 0 ? jb.w0 : eo.w, attempt = jb.w0 > 0 ? 1 : 0, prev_score = jb.prev;
@@ -423,6 +437,7 @@ __device__ void ext_dp_warp(const ExtOpt &eo, const uint32_t *__restrict__ sc_lo
 	const int lane = threadIdx.x & 31;
 	const int qlen = jb.qlen, tlen = jb.tlen, h0 = jb.h0;
 	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
+	ext_prefetch_target(pac, jb.f0, jb.fstep, tlen, jb.comp, lane, 32);
 	for (int j = lane; j < qlen; j += 32) S.Q[j] = codes[jb.qaddr + (int64_t)jb.qstep * j];
 	const bool small = (long long)h0 + (long long)qlen * eo.max_sc < 32768 && qlen < 65536;
 	int prev_score = jb.prev, aw = eo.w, score = 0;

@@ -43,15 +43,23 @@ B200_HD uint64_t l2_at(const FmView &fm, int i)
 	return i == 0 ? fm.L2[0] : i == 1 ? fm.L2[1] : i == 2 ? fm.L2[2] : i == 3 ? fm.L2[3] : fm.L2[4];
 }
 
-// bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c: two occ sectors, one 256-bit load each
-B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c,
+// the two occ sectors a backward (is_back) or forward extension of the interval reads
+B200_HD void fm_extend_load(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, OccRaw &rk, OccRaw &rl)
+{
+	const uint64_t base = is_back ? x0 : x1;
+	const uint64_t k = base - 1, l = base - 1 + x2;
+	const uint64_t ka = k == (uint64_t)-1 ? 0 : k - (k >= fm.primary), la = l == (uint64_t)-1 ? 0 : l - (l >= fm.primary);
+	rk = ld_occ(fm, ka >> 6); rl = ld_occ(fm, la >> 6);
+}
+
+// bwt_extend (reference src/bwt.c:262-275) returning only the interval of base c, from the two occ sectors (one 256-bit load each)
+B200_HD void fm_extend_use(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c, const OccRaw &rk, const OccRaw &rl,
                            uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
 {
 	const uint64_t base = is_back ? x0 : x1, other = is_back ? x1 : x0;
 	const uint64_t k = base - 1, l = base - 1 + x2;
 	const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
 	const uint64_t ka = kz ? 0 : k - (k >= fm.primary), la = lz ? 0 : l - (l >= fm.primary);
-	const OccRaw rk = ld_occ(fm, ka >> 6), rl = ld_occ(fm, la >> 6);
 	uint64_t tk[4], tl[4];
 	occ4_sector(rk, ka, tk);
 	occ4_sector(rl, la, tl);
@@ -68,16 +76,13 @@ B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t 
 	if (is_back) { o0 = nb; o1 = oth; } else { o1 = nb; o0 = oth; }
 }
 
-#if defined(__CUDACC__)
-// non-binding L2 prefetch of the two occ sectors a backward extension of the interval (x0, .., x2) will read
-__device__ __forceinline__ void fm_prefetch_back(const FmView &fm, uint64_t x0, uint64_t x2)
+B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c,
+                           uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
 {
-	const uint64_t k = x0 - 1, l = x0 - 1 + x2;
-	const uint64_t ka = k == (uint64_t)-1 ? 0 : k - (k >= fm.primary), la = l == (uint64_t)-1 ? 0 : l - (l >= fm.primary);
-	asm volatile("prefetch.global.L2 [%0];" :: "l"(fm.occ + ((ka >> 6) << 3)));
-	asm volatile("prefetch.global.L2 [%0];" :: "l"(fm.occ + ((la >> 6) << 3)));
+	OccRaw rk, rl;
+	fm_extend_load(fm, x0, x1, x2, is_back, rk, rl);
+	fm_extend_use(fm, x0, x1, x2, is_back, c, rk, rl, o0, o1, o2, n_blocks);
 }
-#endif
 
 // The interval list of one lane.  Entry k < quota lives in shared memory (sh[(k*4 + word) * stride]), the rest in the
 // lane's global strip (spill[(k - quota) * sstride]).  Values up to 2^33-1, end positions up to 2^29-1.

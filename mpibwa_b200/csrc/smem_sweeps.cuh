@@ -202,10 +202,10 @@ struct BwdLane {
 	}
 	// the entry after the current one in the row being extended (its extension is independent of the current one: reference
 	// src/bwt.c:326-345 walks the row's entries with the same base); false at the end of the row
-	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p2) const
+	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p1, uint64_t &p2) const
 	{
 		if (st != BWD || j + 1 >= n_prev) return false;
-		uint64_t p1; int pe;
+		int pe;
 		L.get(n_list - 2 - j, p0, p1, p2, pe);
 		return true;
 	}
@@ -244,8 +244,10 @@ struct SweepArgs {
 	unsigned long long *occ_blocks;
 };
 
-template <int MODE>
-__global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
+// MINB: resident blocks per SM the kernel is compiled for (the register budget follows: 9 -> 56 registers, 12 -> 40, 16 -> 32; what
+// does not fit spills to thread-local memory - the cold part of the lane state - in exchange for more extensions in flight per SM)
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 {
 	FwdLane ln;
 	ln.st = FwdLane::DONE; ln.n_out = 0; ln.n_sweeps = 0; ln.over = 0;
@@ -278,7 +280,8 @@ __global__ void __launch_bounds__(128) k_sweep_fwd(SweepArgs a)
 	if ((threadIdx.x & 31) == 0 && blocks) atomicAdd(a.occ_blocks, (unsigned long long)blocks);
 }
 
-__global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a, int quota)
 {
 	extern __shared__ uint32_t sweep_sh[];
 	SeedList L;
@@ -288,6 +291,12 @@ __global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
 	int r = -1;
 	bool need = false, drained = false;
 	int64_t blocks = 0;
+	// The entries of a row are independent (reference src/bwt.c:326-345 extends each by the same base), so a lane keeps TWO
+	// extensions in flight: while the sectors of the current entry are digested, those of the following entry of the row are
+	// already being loaded into a second register pair (the kernel's occupancy is set by its shared-memory lists, not by
+	// registers).  ahead: the sectors in (nk, nl) belong to the entry that is now current.
+	OccRaw nk, nl;
+	bool ahead = false;
 	for (;;) {
 		while (!need && !drained) {
 			if (r >= 0) { a.n_intv[r] = ln.n_out; if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out); }
@@ -297,16 +306,19 @@ __global__ void __launch_bounds__(128) k_sweep_bwd(SweepArgs a, int quota)
 			if (ns <= 0) { r = -1; continue; }
 			ln.begin((int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r]);
 			need = ln.advance(a.so, a.cap, L);
+			ahead = false;
 		}
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
-			// the two occ sectors of the FOLLOWING entry of the row are on their way to L2 while this one is digested: the entries
-			// of a row are independent, so a lane keeps two extensions in flight instead of one dependent round trip per loop trip
-			uint64_t p0, p2;
-			if (ln.peek(L, p0, p2)) fm_prefetch_back(a.fm, p0, p2);
+			OccRaw rk, rl;
+			if (ahead) { rk = nk; rl = nl; }
+			else fm_extend_load(a.fm, ln.k0, ln.k1, ln.k2, 1, rk, rl);
+			uint64_t p0, p1, p2;
+			ahead = ln.peek(L, p0, p1, p2);
+			if (ahead) fm_extend_load(a.fm, p0, p1, p2, 1, nk, nl);
 			uint64_t o0, o1, o2;
-			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, o0, o1, o2, blocks);
-			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) need = ln.advance(a.so, a.cap, L);
+			fm_extend_use(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, rk, rl, o0, o1, o2, blocks);
+			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) { need = ln.advance(a.so, a.cap, L); ahead = false; }
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);

@@ -344,6 +344,16 @@ void engine_destroy(Engine *e)
 
 /* ------------------------------------------------------------------ small device helpers */
 
+// asks for the 128-byte lines of the 2-bit reference that hold the window [rb, re) of the forward+reverse coordinate (one strand),
+// ahead of a DP that reads one base per row: see ext_prefetch_target (ext_rounds.cuh).  first / step: this thread's share of the lines.
+__device__ __forceinline__ void prefetch_ref_window(const uint8_t *__restrict__ pac, int64_t l_pac, int64_t rb, int64_t re, int first, int step)
+{
+	if (re <= rb) return;
+	const int64_t fb = rb < l_pac ? rb : (l_pac << 1) - re, fe = rb < l_pac ? re - 1 : (l_pac << 1) - 1 - rb;
+	for (int64_t a = ((fb >> 2) & ~(int64_t)127) + (int64_t)first * 128; a <= (fe >> 2); a += (int64_t)step * 128)
+		asm volatile("prefetch.global.L1 [%0];" :: "l"(pac + a));
+}
+
 __device__ __forceinline__ void warp_add(unsigned long long *dst, long long v)
 {
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -475,7 +485,11 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	const int n = r1 - r0;
 	int &blocks_per_sm = e->seed_blocks_per_sm, &n_sm = e->n_sm;
 	int &bwd_blocks_per_sm = e->bwd_blocks_per_sm, &fwd_blocks_per_sm = e->fwd_blocks_per_sm;
-	const int threads = 128, quota = 16;                                // (fewer entries in shared memory: measured slower - the spill strip is in HBM)
+	// (tuning knobs, tools/tune_env.py: entries of an interval list kept in shared memory; resident blocks the sweeps are compiled for)
+	static const int quota_env = getenv("B200_SEED_QUOTA") ? atoi(getenv("B200_SEED_QUOTA")) : 16;
+	static const int fwd_minb = getenv("B200_FWD_MINB") ? atoi(getenv("B200_FWD_MINB")) : 9;
+	static const int bwd_minb = getenv("B200_BWD_MINB") ? atoi(getenv("B200_BWD_MINB")) : 6;
+	const int threads = 128, quota = quota_env;
 	const size_t sh_bytes = (size_t)threads * quota * 16;               // interval lists
 	if (!blocks_per_sm) {
 		cudaDeviceProp prop;
@@ -494,11 +508,17 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	// throughput path: the four homogeneous sweeps of smem_sweeps.cuh; the general state machine redoes the (rare) reads
 	// whose sweep strip overflowed.  B200_SEED_KERNEL=lanes forces the general kernel for every read (parity tests).
 	const bool use_sweeps = !(getenv("B200_SEED_KERNEL") && !strcmp(getenv("B200_SEED_KERNEL"), "lanes"));
+	typedef void (*FwdK)(SweepArgs);
+	typedef void (*BwdK)(SweepArgs, int);
+	const FwdK fwd1 = fwd_minb >= 16 ? k_sweep_fwd<1, 16> : fwd_minb >= 12 ? k_sweep_fwd<1, 12> : k_sweep_fwd<1, 9>;
+	const FwdK fwd2 = fwd_minb >= 16 ? k_sweep_fwd<2, 16> : fwd_minb >= 12 ? k_sweep_fwd<2, 12> : k_sweep_fwd<2, 9>;
+	const BwdK bwd = bwd_minb >= 12 ? k_sweep_bwd<12> : bwd_minb >= 9 ? k_sweep_bwd<9> : k_sweep_bwd<6>;
 	if (use_sweeps && !bwd_blocks_per_sm) {
-		CK(cudaFuncSetAttribute(k_sweep_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, k_sweep_bwd, threads, sh_bytes));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_blocks_per_sm, k_sweep_fwd<1>, threads, 0));
+		CK(cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, bwd, threads, sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_blocks_per_sm, fwd1, threads, 0));
 		if (bwd_blocks_per_sm < 1 || fwd_blocks_per_sm < 1) die("sweep kernels do not fit an SM");
+		if (getenv("B200_DEBUG")) fprintf(stderr, "[seed] sweeps: %d forward, %d backward blocks per SM (quota %d)\n", fwd_blocks_per_sm, bwd_blocks_per_sm, quota);
 	}
 	const int strip_cap = getenv("B200_SEED_STRIP") ? atoi(getenv("B200_SEED_STRIP")) : 3 * max_len + 8;   // (override: tests force overflows)
 	for (;;) {
@@ -511,11 +531,15 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 			a.strips = e->b_strips.as<Q4>((size_t)n * strip_cap + 1); a.strip_cap = strip_cap;
 			a.n_intv = n_intv; a.n_first = e->b_nfirst.as<int32_t>(n + 1); a.n_sweeps = e->b_nsweeps.as<int32_t>(n + 1);
 			a.worst = ctr + 1; a.n_over = ctr + 2; a.occ_blocks = &e->d_cnt->occ_blocks;
-			const int gf = std::min(n_sm * fwd_blocks_per_sm, grid_for(n, threads)), gb = std::min(n_sm * bwd_blocks_per_sm, grid_for(n, threads));
-			a.next_read = ctr + 3; k_sweep_fwd<1><<<gf, threads, 0, e->stream>>>(a);
-			a.next_read = ctr + 4; k_sweep_bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
-			a.next_read = ctr + 5; k_sweep_fwd<2><<<gf, threads, 0, e->stream>>>(a);
-			a.next_read = ctr + 6; k_sweep_bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			// B200_SEED_FILL < 1: the persistent sweeps take only that share of the blocks an SM could hold, leaving registers and
+			// shared memory for the kernels of the other chunks in flight (the sweeps are bound by random DRAM sectors, not by issue)
+			static const double fill = getenv("B200_SEED_FILL") ? atof(getenv("B200_SEED_FILL")) : 1.0;
+			const int fpb = std::max(1, (int)(fwd_blocks_per_sm * fill + .5)), bpb = std::max(1, (int)(bwd_blocks_per_sm * fill + .5));
+			const int gf = std::min(n_sm * fpb, grid_for(n, threads)), gb = std::min(n_sm * bpb, grid_for(n, threads));
+			a.next_read = ctr + 3; fwd1<<<gf, threads, 0, e->stream>>>(a);
+			a.next_read = ctr + 4; bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			a.next_read = ctr + 5; fwd2<<<gf, threads, 0, e->stream>>>(a);
+			a.next_read = ctr + 6; bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
 			CK(cudaGetLastError());
 			e->stats.n_launches += 4;
 			CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
@@ -1129,6 +1153,7 @@ struct SwSrcPipeline {
 		qlen = j.q_len; tlen = j.tlen; xtra = j.xtra;
 		q.p = codes + off[j.read] + j.q_beg; q.l = j.q_len; q.rev = j.is_rev;
 		t.pac = pac; t.l_pac = l_pac; t.beg = j.rb;
+		prefetch_ref_window(pac, l_pac, j.rb, j.rb + j.tlen, threadIdx.x & 31, 32);     // (one warp per job; harmless when one thread runs it)
 	}
 	__device__ __forceinline__ void store(int jx, const SwRes &r) const { res[jx] = r; }
 };
@@ -1346,6 +1371,7 @@ __global__ void __launch_bounds__(64) k_global_lanes(GlobalOpt go, const uint8_t
 		GlobalSeqsSh s;
 		s.Q = Q; s.l_query = j.qe - j.qb; s.pac = pac; s.l_pac = l_pac; s.rb = j.rb; s.re = j.re; s.rev = j.rb >= l_pac; s.lut = lut;
 		const uint8_t *q = codes + off[j.read] + j.qb;
+		prefetch_ref_window(pac, l_pac, j.rb, j.re, 0, 1);
 		for (int x = 0; x < s.l_query; ++x) Q[ext_qidx(x)] = s.rev ? q[s.l_query - 1 - x] : q[x];
 		GlobalRowSh eh = { rows, S - 1 };
 		global_task(go, s, j, eh, z + j.zoff, cig + j.cig_off, &res[jx], &cells, (S - 2) >> 1);
@@ -1829,7 +1855,62 @@ double int32_peak_gops(int device, int mode)
 	return ops / (best * 1e-3) / 1e9;
 }
 
+/* ------------------------------------------------------------------ random-sector bandwidth micro-benchmark
+ * The FM-index kernels read 32-byte occ sectors at random places of a table far larger than L2.  HBM delivers much less than its
+ * streaming (copy) bandwidth to such a pattern - every sector opens a DRAM page for 32 useful bytes - so the copy bandwidth of
+ * MEASURED_PEAKS.json is not what bounds them.  This measures what the device delivers to the access pattern itself: independent
+ * 256-bit loads (the seeding kernels' own instruction: ld.global.nc.L1::no_allocate.v8.u32) of uniformly random sectors of a
+ * table of `bytes`, four in flight per thread, 2048 threads per SM. */
+__global__ void __launch_bounds__(128) k_random_sectors(const uint32_t *__restrict__ tab, uint64_t n_sec, int iters, uint32_t *out)
+{
+	uint64_t x = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull + 12345;
+	uint32_t acc = 0;
+	for (int i = 0; i < iters; ++i) {
+		uint32_t w[4][8];
+#pragma unroll
+		for (int u = 0; u < 4; ++u) {
+			x = x * 6364136223846793005ull + 1442695040888963407ull;
+			const uint64_t sec = __umul64hi(x, n_sec);
+			const uint32_t *p = tab + (sec << 3);
+			asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+			    : "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7]) : "l"(p));
+		}
+#pragma unroll
+		for (int u = 0; u < 4; ++u) acc ^= w[u][0] ^ w[u][1] ^ w[u][2] ^ w[u][3] ^ w[u][4] ^ w[u][5] ^ w[u][6] ^ w[u][7];
+	}
+	out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+
+double random_sector_gbs(int device, size_t bytes)
+{
+	CK(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	const int blocks = prop.multiProcessorCount * 16, threads = 128, iters = 256;
+	const uint64_t n_sec = bytes / 32;
+	uint32_t *tab = nullptr, *out = nullptr;
+	CK(cudaMalloc(&tab, n_sec * 32));
+	CK(cudaMemset(tab, 1, n_sec * 32));
+	CK(cudaMalloc(&out, (size_t)blocks * threads * sizeof(uint32_t)));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+	float best = 1e30f;
+	for (int rep = 0; rep < 4; ++rep) {
+		CK(cudaEventRecord(e0));
+		k_random_sectors<<<blocks, threads>>>(tab, n_sec, iters, out);
+		CK(cudaEventRecord(e1));
+		CK(cudaEventSynchronize(e1));
+		float ms;
+		CK(cudaEventElapsedTime(&ms, e0, e1));
+		if (rep > 0 && ms < best) best = ms;
+	}
+	CK(cudaFree(tab)); CK(cudaFree(out));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	return (double)blocks * threads * iters * 4.0 * 32.0 / (best * 1e-3) / 1e9;
+}
+
 } // namespace b200
 
+extern "C" double b200_hbm_random_sector_peak(int device, size_t table_bytes) { return b200::random_sector_gbs(device, table_bytes); }
 extern "C" double b200_int32_peak(int device) { return b200::int32_peak_gops(device, 0); }
 extern "C" double b200_int32_peak_dual_pipe(int device) { return b200::int32_peak_gops(device, 1); }

@@ -270,7 +270,12 @@ static void engine_set_l2_window(Engine *e)
 {
 	cudaDeviceProp prop;
 	CK(cudaGetDeviceProperties(&prop, e->device));
-	if (prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+	// B200_L2_WINDOW: 0 = no access-policy window, 1 = persisting share + streaming misses, 2 = persisting share + normal misses
+	// Default 0: measured on 100 Mbp / 1 Gbp / 3.1 Gbp references the window COSTS 10-15 % of the end-to-end rate (seeding 16.6 -> 14.1,
+	// 26.1 -> 23.7, 31.4 -> 28.1 ms; CIGAR stage 4.4 -> 3.2 ms): a window over a multi-GB table marks a random few percent of its lines
+	// persisting, not the hot ones, and the persisting carve-out takes L2 away from everything else (profiles/r02_summary.md).
+	static const int mode = getenv("B200_L2_WINDOW") ? atoi(getenv("B200_L2_WINDOW")) : 0;
+	if (mode && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
 		size_t persist = (size_t)prop.persistingL2CacheMaxSize;
 		CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist));
 		cudaStreamAttrValue attr;
@@ -280,7 +285,7 @@ static void engine_set_l2_window(Engine *e)
 		attr.accessPolicyWindow.num_bytes = win;
 		attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)persist / (double)win);
 		attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-		attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+		attr.accessPolicyWindow.missProp = mode == 2 ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
 		CK(cudaStreamSetAttribute(e->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
 	}
 }

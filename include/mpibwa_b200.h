@@ -357,6 +357,23 @@ b200_job_t *b200_align_seqs_begin(const mem_opt_t *opt, const bwaidx_t *idx, int
 /* the same from the raw fastq bytes of the chunk (one buffer per mate file, fq2 NULL for single-end; parsed IN PLACE by the job
  * thread, so begin() returns at once and the buffers must stay untouched until end()); finish with b200_align_chunk_end */
 b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, int64_t n_processed, char *fq1, int64_t len1, char *fq2, int64_t len2);
+/* Per-chromosome routing (row f3; reference src/mainParallelByChromosome.c:1395-1457: the ByChr host parses RNAME and RNEXT back out
+ * of every SAM line and copies the line into the buffer of its contig, of "unmapped" or - without fixmate - also of "discordant").
+ * The device writes the lines, so it knows both contigs.  b200_set_routing(flags) applies to the one-buffer chunk jobs begun after it
+ * (b200_align_chunk_begin / _seqs_begin / _fastq_begin); finish those jobs with b200_align_chunk_end_routed:
+ *   B200_ROUTE_LINES      the text comes back in input order plus one b200_sam_line_t per line (malloc()ed; free() it)
+ *   B200_ROUTE_BY_CONTIG  the text comes back GROUPED BY DESTINATION - contig 0 .. n_seqs-1, then "discordant" (index n_seqs), then
+ *                         "unmapped" (n_seqs+1) - lines of a destination in input order; (*dest_off)[d] .. [d+1] is destination d's
+ *                         range (n_dest + 1 = n_seqs + 3 entries, malloc()ed): what the reference builds in buffer_out_vec[]
+ *   | B200_ROUTE_DISCORDANT  (with BY_CONTIG) a mapped line whose mate maps to another contig is ALSO copied into "discordant"
+ *                         (the branch without fixmate, src/mainParallelByChromosome.c:1440-1444; single-end data has none) */
+typedef struct { int64_t off; int32_t len, rid, mate_rid, read; } b200_sam_line_t;   /* rid / mate_rid: contig printed as RNAME / RNEXT, -1 for '*' */
+#define B200_ROUTE_LINES 1
+#define B200_ROUTE_BY_CONTIG 2
+#define B200_ROUTE_DISCORDANT 4
+void b200_set_routing(int flags);
+int64_t b200_align_chunk_end_routed(b200_job_t *job, char **sam, int64_t *sam_len, b200_sam_line_t **lines, int64_t *n_lines,
+                                    int64_t **dest_off, int *n_dest, b200_stats_t *stats /* may be NULL */);
 /* measured int32 instruction issue rate of the device in Gop/s: integer ALU pipe only (min/max/add/logic; the DP
  * roofline denominator) and with half of the work as IMAD on the FMA pipe (dual-pipe ceiling) */
 double b200_int32_peak(int device);

@@ -152,6 +152,9 @@ _PROTOTYPES = {
     "b200_align_seqs_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_int, C.POINTER(bseq1_t), C.c_void_p]),
     "b200_align_fastq_begin": (C.c_void_p, [C.POINTER(mem_opt_t), C.POINTER(bwaidx_t), C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "b200_align_chunk_end": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(b200_stats_t)]),
+    "b200_set_routing": (None, [C.c_int]),
+    "b200_align_chunk_end_routed": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64), C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                                C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(b200_stats_t)]),
     "b200_free": (None, [C.c_void_p]),
     "b200_big_alloc": (C.c_void_p, [C.c_size_t]),
     "b200_get_stats": (None, [C.POINTER(b200_stats_t)]),

@@ -4,6 +4,7 @@
 #include "host_align.h"
 #include "stages.h"
 #include "util.h"
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,8 +28,10 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 struct SeqJob;
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int64_t n_processed, int n,
                            bseq1_t *seqs, const mem_pestat_t *pes0, void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
-                           char *fq1, int64_t len1, char *fq2, int64_t len2);
+                           char *fq1, int64_t len1, char *fq2, int64_t len2, int route);
 int64_t job_n_reads(SeqJob *j);
+int64_t job_take_lines(SeqJob *j, b200_sam_line_t **out);
+int job_take_dest_off(SeqJob *j, int64_t **out);
 int64_t job_take_sam(SeqJob *j, char **out);
 void process_seqs_end(SeqJob *j, b200_stats_t *stats);
 void last_stats(b200_stats_t *out);
@@ -396,17 +399,26 @@ struct b200_job {
 	SeqJob *job;
 	bseq1_t *seqs; int64_t total;       // b200_align_chunk_begin: the interleaved mates and the SAM collected by the job thread
 	char *sam; int64_t sam_len;
+	b200_sam_line_t *lines = nullptr; int64_t n_lines = 0; int64_t *dest_off = nullptr; int n_dest = 0;   // b200_set_routing products
 	int n_threads;
 	char *fq[2]; int64_t fq_len[2];     // b200_align_fastq_begin: the raw fastq buffers, parsed in place by the job thread
 	bseq1_t *mate[2];
 };
+
+static std::atomic<int> g_route{0};
+void b200_set_routing(int flags) { g_route = flags; }
+static void take_routing(b200_job *x, SeqJob *self)
+{
+	x->n_lines = job_take_lines(self, &x->lines);
+	x->n_dest = job_take_dest_off(self, &x->dest_off);
+}
 
 b200_job_t *b200_process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                                     int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
 	b200_job *j = new b200_job();
 	j->seqs = nullptr; j->total = 0; j->sam = nullptr; j->sam_len = 0;
-	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0);
+	j->job = process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0, 0);
 	return j;
 }
 
@@ -425,7 +437,7 @@ b200_job_t *b200_align_chunk_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->n_threads = opt->n_threads;
 	// the chunk's text comes back from the device as one buffer (no malloc per read)
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, (int)j->total, j->seqs, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); free(x->seqs); x->seqs = nullptr; }, j, true, nullptr, 0, nullptr, 0);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); take_routing(x, self); free(x->seqs); x->seqs = nullptr; }, j, true, nullptr, 0, nullptr, 0, g_route);
 	return j;
 }
 
@@ -434,7 +446,7 @@ b200_job_t *b200_align_seqs_begin(const mem_opt_t *opt, const bwaidx_t *idx, int
 	b200_job *j = new b200_job();
 	j->total = n; j->seqs = nullptr; j->sam = nullptr; j->sam_len = 0; j->n_threads = opt->n_threads;
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, n, seqs, pes0,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); }, j, true, nullptr, 0, nullptr, 0);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); take_routing(x, self); }, j, true, nullptr, 0, nullptr, 0, g_route);
 	return j;
 }
 
@@ -445,8 +457,8 @@ b200_job_t *b200_align_fastq_begin(const mem_opt_t *opt, const bwaidx_t *idx, in
 	j->fq[0] = fq1; j->fq[1] = fq2; j->fq_len[0] = len1; j->fq_len[1] = len2; j->mate[0] = j->mate[1] = nullptr;
 	// the job thread uploads the raw bytes; the device parses, interleaves and encodes them (fastq_kernels.h)
 	j->job = process_seqs_begin(opt, idx->bwt, idx->bns, idx->pac, n_processed, 0, nullptr, nullptr,
-		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); x->total = job_n_reads(self); }, j, true,
-		fq1, len1, fq2, fq2 ? len2 : 0);
+		[](void *p, SeqJob *self) { b200_job *x = (b200_job *)p; x->sam_len = job_take_sam(self, &x->sam); take_routing(x, self); x->total = job_n_reads(self); }, j, true,
+		fq1, len1, fq2, fq2 ? len2 : 0, g_route);
 	return j;
 }
 
@@ -456,6 +468,24 @@ int64_t b200_align_chunk_end(b200_job_t *j, char **sam, int64_t *sam_len, b200_s
 	const int64_t total = j->total;
 	if (sam) *sam = j->sam; else b200_free(j->sam);      // (pool buffer: never free())
 	if (sam_len) *sam_len = j->sam_len;
+	free(j->lines); free(j->dest_off);
+	delete j;
+	return total;
+}
+
+int64_t b200_align_chunk_end_routed(b200_job_t *j, char **sam, int64_t *sam_len, b200_sam_line_t **lines, int64_t *n_lines,
+                                    int64_t **dest_off, int *n_dest, b200_stats_t *stats)
+{
+	process_seqs_end(j->job, stats);
+	j->job = nullptr;
+	if (lines) { *lines = j->lines; j->lines = nullptr; }
+	if (n_lines) *n_lines = j->n_lines;
+	if (dest_off) { *dest_off = j->dest_off; j->dest_off = nullptr; }
+	if (n_dest) *n_dest = j->n_dest;
+	const int64_t total = j->total;
+	if (sam) *sam = j->sam; else b200_free(j->sam);
+	if (sam_len) *sam_len = j->sam_len;
+	free(j->lines); free(j->dest_off);
 	delete j;
 	return total;
 }

@@ -1156,9 +1156,11 @@ B200_HD void fin_put_cigar(const FinCtx &cx, SINK &s, const SamView &V, const Al
 template <class SINK>
 B200_HD void fin_put_ctg(const FinCtx &cx, SINK &s, int rid) { s.puts(cx.ctg_names + cx.ctg_name_off[rid], cx.ctg_name_off[rid + 1] - cx.ctg_name_off[rid]); }
 
-// one SAM line: record `which` of read r (mem_aln2sam, reference src/bwamem.c:825-946)
+// one SAM line: record `which` of read r (mem_aln2sam, reference src/bwamem.c:825-946).  *rid_out / *mrid_out: the contigs printed
+// as RNAME and RNEXT (-1: '*') - the two fields the per-chromosome hosts parse back out of every line to route it
+// (reference src/mainParallelByChromosome.c:1395-1457).
 template <class SINK>
-B200_HDN void sam_format(const FinCtx &cx, const SamView &V, int64_t r, int which, SINK &s)
+B200_HDN void sam_format(const FinCtx &cx, const SamView &V, int64_t r, int which, SINK &s, int *rid_out = nullptr, int *mrid_out = nullptr)
 {
 	const mem_opt_t &opt = cx.opt;
 	const int64_t base = V.roff[r];
@@ -1187,6 +1189,7 @@ B200_HDN void sam_format(const FinCtx &cx, const SamView &V, int64_t r, int whic
 	flag |= p_rev ? 0x10 : 0;
 	flag |= has_mate && m_rev ? 0x20 : 0;
 
+	if (rid_out) { *rid_out = p_rid; *mrid_out = has_mate ? m_rid : -1; }
 	const ReadText rt = cx.rtext[r];
 	s.puts(cx.text + rt.name_off, rt.name_len); s.put('\t');
 	fin_put_int(s, (flag & 0xffff) | (flag & 0x10000 ? 0x100 : 0)); s.put('\t');
@@ -1305,6 +1308,9 @@ B200_HD void sam_format_read(const FinCtx &cx, const SamView &V, int64_t r, SINK
 	const int n = V.nrec[r];
 	for (int w = 0; w < n; ++w) sam_format(cx, V, r, w, s);
 }
+
+// one entry per SAM line of the chunk, in output order: where the line is in the text and which contigs it names
+struct SamLine { int64_t off; int32_t len, rid, mate_rid, read; };
 
 // mates must carry the same name (reference src/bwamem_pair.c:360)
 B200_HD bool fin_names_differ(const FinCtx &cx, int64_t r0)

@@ -41,7 +41,7 @@ enum FinBuf {
 	FB_JOBS, FB_KEYS, FB_RES, FB_NEXT, FB_HEAD, FB_PEND0, FB_PEND1, FB_MISS, FB_ORDER, FB_Z, FB_CNT, FB_HASALT, FB_V, FB_VTMP, FB_XAOF, FB_NEED,
 	FB_RECS, FB_NREC, FB_MATE, FB_CN_ALN, FB_CN_DP, FB_CN_CIG, FB_CN_MD, FB_CN_Z, FB_O_ALN, FB_O_DP, FB_O_CIG, FB_O_MD, FB_O_Z, FB_ALNSLOT,
 	FB_SLOTREG, FB_SLOTJOB, FB_SLOTCIG, FB_SLOTMD, FB_GJOBS, FB_GRES, FB_GKEY, FB_GSEL, FB_GSEL2, FB_GZ, FB_CIG, FB_MD, FB_ALN, FB_LEN, FB_SAMOFF, FB_SAM,
-	FB_PAIRTAB, FB_N
+	FB_PAIRTAB, FB_LINEOFF, FB_LINES, FB_RKEY, FB_RVAL, FB_RLEN, FB_RTOFF, FB_DESTOFF, FB_ROUTED, FB_N
 };
 
 inline SwOpt fin_sw_opt(const mem_opt_t &opt)
@@ -298,7 +298,68 @@ struct SamCountTask {
 };
 struct SamWriteTask {
 	FinCtx cx; SamView V; const int64_t *sam_off; char *sam;
-	B200_HD void operator()(int64_t r) const { WriteSink s(sam + sam_off[r]); sam_format_read(cx, V, r, s); s.flush(); }
+	const int64_t *line_off; SamLine *lines;      // (optional) routing table: lines of read r at lines[line_off[r] ..]
+	B200_HD void operator()(int64_t r) const
+	{
+		WriteSink s(sam + sam_off[r]);
+		if (!lines) { sam_format_read(cx, V, r, s); s.flush(); return; }
+		const int n = V.nrec[r];
+		int64_t at = sam_off[r];
+		for (int w = 0; w < n; ++w) {
+			int rid, mrid;
+			sam_format(cx, V, r, w, s, &rid, &mrid);
+			const int64_t end = (int64_t)(s.p - sam) + s.na;
+			SamLine L;
+			L.off = at; L.len = (int32_t)(end - at); L.rid = rid; L.mate_rid = mrid; L.read = (int32_t)r;
+			lines[line_off[r] + w] = L;
+			at = end;
+		}
+		s.flush();
+	}
+};
+
+/* ---------------------------------------------------------------- per-chromosome routing of the SAM lines
+ * (reference src/mainParallelByChromosome.c:1395-1457 parses RNAME / RNEXT back out of every line and copies the line into the buffer
+ * of its contig, or of "unmapped"; in the branch without fixmate a line whose mate sits on another contig goes into "discordant" AS
+ * WELL.  Here the writer of the line knows both contigs: a stable sort of (destination, line) pairs, a prefix sum of the line lengths
+ * in that order and one copy per pair build the same buffers - destinations 0 .. n_ctg-1, n_ctg = discordant, n_ctg+1 = unmapped -
+ * back to back, lines of a destination in output order.) */
+enum { ROUTE_LINES = 1, ROUTE_BY_CONTIG = 2, ROUTE_DISCORDANT = 4 };
+struct RouteKeyTask {
+	const SamLine *lines; int64_t n_lines; int n_ctg, with_disc; uint32_t *key; int32_t *val;
+	B200_HD void operator()(int64_t i) const
+	{
+		const SamLine L = lines[i];
+		key[i] = L.rid < 0 ? (uint32_t)n_ctg + 1 : (uint32_t)L.rid;
+		val[i] = (int32_t)i;
+		const bool disc = with_disc && L.rid >= 0 && L.mate_rid >= 0 && L.rid != L.mate_rid;
+		key[n_lines + i] = disc ? (uint32_t)n_ctg : (uint32_t)n_ctg + 2;      // (n_ctg + 2: not a destination, sorts last, length 0)
+		val[n_lines + i] = (int32_t)i;
+	}
+};
+struct RouteLenTask {
+	const SamLine *lines; const uint32_t *key; const int32_t *val; int n_dest; int32_t *len;
+	B200_HD void operator()(int64_t j) const { len[j] = key[j] < (uint32_t)n_dest ? lines[val[j]].len : 0; }
+};
+struct RouteBoundsTask {       // j in [0, m]: destinations in (key[j-1], key[j]] start at roff[j]
+	const uint32_t *key; const int64_t *roff; int64_t m; int n_dest; int64_t *dest_off;
+	B200_HD void operator()(int64_t j) const
+	{
+		const int64_t lo = j == 0 ? -1 : (key[j - 1] < (uint32_t)n_dest ? (int64_t)key[j - 1] : n_dest);
+		const int64_t hi = j == m ? n_dest : (key[j] < (uint32_t)n_dest ? (int64_t)key[j] : n_dest);
+		for (int64_t d = lo + 1; d <= hi; ++d) dest_off[d] = roff[j];
+	}
+};
+struct RouteCopyTask {
+	const SamLine *lines; const uint32_t *key; const int32_t *val; const int64_t *roff; int n_dest; const char *sam; char *routed;
+	B200_HD void operator()(int64_t j) const
+	{
+		if (key[j] >= (uint32_t)n_dest) return;
+		const SamLine L = lines[val[j]];
+		WriteSink s(routed + roff[j]);
+		s.puts(sam + L.off, L.len);
+		s.flush();
+	}
 };
 
 /* ---------------------------------------------------------------- host side of mem_pestat (reference src/bwamem_pair.c:67-109) */
@@ -328,11 +389,17 @@ struct FinishIn {
 	const mem_pestat_t *pes0;                   // caller-given insert-size statistics, or null
 	int max_len;
 	const double *logtab; int n_log;            // device memory
+	int route;                                  // ROUTE_* flags: also build the per-line routing table / the text grouped by contig
 };
 struct FinishOut {
 	const char *sam;            // device memory: the chunk's SAM text, records of read r at [sam_off[r], sam_off[r+1])
 	const int64_t *sam_off;     // device memory, n_reads + 1
 	int64_t sam_bytes;
+	const SamLine *lines;       // device memory (when asked for): one entry per SAM line, in output order
+	int64_t n_lines;
+	const char *routed;         // device memory (ROUTE_BY_CONTIG): the lines grouped by destination, destination d at [dest_off[d], dest_off[d+1])
+	const int64_t *dest_off;    // n_ctg + 3 entries
+	int64_t routed_bytes;
 };
 
 template <class BK>
@@ -545,14 +612,46 @@ void finish_run(BK &bk, FinCtx cx, const FinishIn &in, FinishOut &out, b200_stat
 	bk.scan(len, sam_off, n + 1);
 	const int64_t total = bk.get64(sam_off + n);
 	char *sam = bk.template buf<char>(FB_SAM, total + 16);
-	bk.run(n, SamWriteTask{ cx, V, sam_off, sam });
+	int64_t *line_off = nullptr;
+	SamLine *lines = nullptr;
+	int64_t n_lines = 0;
+	if (in.route) {
+		line_off = bk.template buf<int64_t>(FB_LINEOFF, n + 1);
+		bk.zero(nrec + n, sizeof(int32_t));
+		bk.scan(nrec, line_off, n + 1);
+		n_lines = bk.get64(line_off + n);
+		lines = bk.template buf<SamLine>(FB_LINES, n_lines + 1);
+	}
+	bk.run(n, SamWriteTask{ cx, V, sam_off, sam, line_off, lines });
 	int32_t err[2];
 	bk.download(err, ctr + 32, sizeof err);
 	if (err[0] == FIN_ERR_NAMES) { fprintf(stderr, "[mem_sam_pe] paired reads have different names (reads %d and %d of the chunk)\n", err[1], err[1] + 1); abort(); }
 	if (err[0]) { fprintf(stderr, "[mpibwa_b200] finish stage: table range exceeded (code %d, value %d)\n", err[0], err[1]); abort(); }
 	t1 = clock_ms(); st.ms_sam_host += t1 - t0; t0 = t1;
+	out.routed = nullptr; out.dest_off = nullptr; out.routed_bytes = 0;
+	if ((in.route & ROUTE_BY_CONTIG) && n_lines > 0) {
+		const int n_ctg = cx.fm.n_ctg, n_dest = n_ctg + 2;
+		if (n_dest + 1 >= (1 << 20)) { fprintf(stderr, "[mpibwa_b200] per-contig routing: too many contigs (%d)\n", n_ctg); abort(); }
+		const int64_t m = 2 * n_lines;
+		uint32_t *key = bk.template buf<uint32_t>(FB_RKEY, m);
+		int32_t *val = bk.template buf<int32_t>(FB_RVAL, m);
+		bk.run(n_lines, RouteKeyTask{ lines, n_lines, n_ctg, (in.route & ROUTE_DISCORDANT) ? 1 : 0, key, val });
+		bk.sort_pairs(key, val, m);
+		int32_t *rlen = bk.template buf<int32_t>(FB_RLEN, m + 1);
+		int64_t *roff = bk.template buf<int64_t>(FB_RTOFF, m + 1);
+		bk.run(m, RouteLenTask{ lines, key, val, n_dest, rlen });
+		bk.zero(rlen + m, sizeof(int32_t));
+		bk.scan(rlen, roff, m + 1);
+		const int64_t rtotal = bk.get64(roff + m);
+		int64_t *dest_off = bk.template buf<int64_t>(FB_DESTOFF, n_dest + 1);
+		bk.run(m + 1, RouteBoundsTask{ key, roff, m, n_dest, dest_off });
+		char *routed = bk.template buf<char>(FB_ROUTED, rtotal + 16);
+		bk.run(m, RouteCopyTask{ lines, key, val, roff, n_dest, sam, routed });
+		out.routed = routed; out.dest_off = dest_off; out.routed_bytes = rtotal;
+		t1 = clock_ms(); st.ms_sam_host += t1 - t0; t0 = t1;
+	}
 	st.n_aln_slots += n_aln;
-	out.sam = sam; out.sam_off = sam_off; out.sam_bytes = total;
+	out.sam = sam; out.sam_off = sam_off; out.sam_bytes = total; out.lines = lines; out.n_lines = n_lines;
 }
 
 } // namespace b200

@@ -318,7 +318,11 @@ void stage_reads(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, co
 
 // where the SAM text of the chunk goes: seqs[i].sam (mem_process_seqs' contract: one malloc()ed string per read) or ONE buffer
 // from the recycling pool of b200_big_alloc (b200_align_chunk / _fastq: the caller wants the chunk's text, not 667 k strings)
-struct SamDest { bool one_buffer = false; char *sam = nullptr; int64_t sam_len = 0; };
+struct SamDest {
+	bool one_buffer = false; char *sam = nullptr; int64_t sam_len = 0;
+	int route = 0; b200_sam_line_t *lines = nullptr; int64_t n_lines = 0;     // (one-buffer jobs, B200_ROUTE_*: the per-line table, malloc()ed)
+	int64_t *dest_off = nullptr; int n_dest = 0;                              // (B200_ROUTE_BY_CONTIG: sam is grouped by destination; n_dest + 1 offsets, malloc()ed)
+};
 // the chunk as raw fastq bytes (b200_align_fastq_begin): parsed on the device; seqs == null then
 struct FastqSrc { char *fq[2]; int64_t len[2]; };
 extern "C" int64_t b200_fastq_parse(char *buf, int64_t len, bseq1_t **out);
@@ -547,12 +551,26 @@ static void process_seqs_slot(const mem_opt_t *opt, const bwt_t *bwt, const bnts
 	FinishArgs fa;
 	fa.opt = opt; fa.pes0 = (opt->flag & MEM_F_PE) ? pes0 : nullptr; fa.n_processed = n_processed; fa.rg_id = bwa_rg_id;
 	fa.want_offsets = !dest->one_buffer;
+	fa.route = dest->one_buffer ? dest->route : 0;
 	fa.alloc = dest->one_buffer ? b200_big_alloc : nullptr;
 	GPU_STAGE(TURN_DP, stage_finish(eng, fa));
 	SamChunk sc;
 	stage_fetch_sam(eng, fa, sc);           // (D2H on the engine's own stream: the next chunk's kernels run meanwhile)
 	t0 = now_ms();
-	if (dest->one_buffer) { dest->sam = sc.sam; dest->sam_len = sc.bytes; }
+	if (dest->one_buffer) {
+		dest->sam = sc.sam; dest->sam_len = sc.bytes;
+		static_assert(sizeof(b200_sam_line_t) == sizeof(SamLine), "routing table entry layout");
+		if (fa.route & B200_ROUTE_BY_CONTIG) {
+			dest->n_dest = sc.n_dest;
+			dest->dest_off = (int64_t *)calloc((size_t)sc.n_dest + 1, sizeof(int64_t));
+			if (sc.dest_off) memcpy(dest->dest_off, sc.dest_off, sizeof(int64_t) * ((size_t)sc.n_dest + 1));
+		}
+		else if (fa.route) {
+			dest->n_lines = sc.n_lines;
+			dest->lines = (b200_sam_line_t *)malloc(sizeof(b200_sam_line_t) * (size_t)(sc.n_lines + 1));
+			if (sc.n_lines) memcpy(dest->lines, sc.lines, sizeof(SamLine) * (size_t)sc.n_lines);
+		}
+	}
 	else {
 		// mem_process_seqs' contract: one malloc()ed, NUL-terminated string per read (the host free()s them)
 		parallel_for(nt, n, 2048, [&](int, int64_t b, int64_t e) {
@@ -595,14 +613,27 @@ int64_t job_take_sam(SeqJob *j, char **out)
 	j->dest.sam = nullptr;
 	return j->dest.sam_len;
 }
+int64_t job_take_lines(SeqJob *j, b200_sam_line_t **out)
+{
+	*out = j->dest.lines;
+	j->dest.lines = nullptr;
+	return j->dest.n_lines;
+}
+int job_take_dest_off(SeqJob *j, int64_t **out)
+{
+	*out = j->dest.dest_off;
+	j->dest.dest_off = nullptr;
+	return j->dest.n_dest;
+}
 
 SeqJob *process_seqs_begin(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                            int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0,
                            void (*after)(void *, SeqJob *), void *arg, bool one_buffer,
-                           char *fq1, int64_t len1, char *fq2, int64_t len2)
+                           char *fq1, int64_t len1, char *fq2, int64_t len2, int route)
 {
 	engine_for(bwt, bns, pac);
 	SeqJob *j = new SeqJob();
+	j->dest.route = route;
 	memset(&j->stats, 0, sizeof j->stats);
 	int slot = -1;
 	bool staged = false;
@@ -650,7 +681,7 @@ void process_seqs_end(SeqJob *j, b200_stats_t *stats)
 void process_seqs(const mem_opt_t *opt, const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
                   int64_t n_processed, int n, bseq1_t *seqs, const mem_pestat_t *pes0)
 {
-	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0), nullptr);
+	process_seqs_end(process_seqs_begin(opt, bwt, bns, pac, n_processed, n, seqs, pes0, nullptr, nullptr, false, nullptr, 0, nullptr, 0, 0), nullptr);
 }
 
 } // namespace b200

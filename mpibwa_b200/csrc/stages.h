@@ -70,9 +70,10 @@ void stage_upload_text(Engine *e, int n_reads, const ReadText *rtext, const char
 struct FinishArgs {
 	const mem_opt_t *opt; const mem_pestat_t *pes0; int64_t n_processed; const char *rg_id;
 	bool want_offsets;              // also bring the per-read offsets back
+	int route;                      // B200_ROUTE_* (finish_stage.h ROUTE_*): bring back the per-line routing table, or the text grouped by contig
 	void *(*alloc)(size_t bytes);   // when set: called once with the size of the text (+1); the text is copied there instead
 };
-struct SamChunk { char *sam; const int64_t *sam_off; int64_t bytes; };
+struct SamChunk { char *sam; const int64_t *sam_off; int64_t bytes; const SamLine *lines; int64_t n_lines; const int64_t *dest_off; int n_dest; };
 void stage_finish(Engine *e, const FinishArgs &a);                        // the kernels; leaves the text in HBM
 void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out);      // brings it to the host (copy engine only)
 

@@ -118,7 +118,7 @@ public:
 	DevBuf fb[FB_N], d_rtext, d_text;
 	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr;
 	int n_log = 0;
-	PinBuf h_sam, h_sam_off;
+	PinBuf h_sam, h_sam_off, h_lines, h_dest_off;
 	FinishOut fin_out;
 	double ms_task = 0, ms_task_text = 0;       // CUDA-event time of the finish-stage kernels of the current call
 	std::vector<cudaEvent_t> ev_pool;
@@ -334,7 +334,7 @@ void engine_destroy(Engine *e)
 	cudaStreamSynchronize(e->stream);
 	e->h_seeds.release(); e->h_seed_off.release(); e->h_lrep.release(); e->h_codes.release();
 	for (int i = 0; i < PIN_N_SLOTS; ++i) e->h_slot[i].release();
-	e->h_sam.release(); e->h_sam_off.release();
+	e->h_sam.release(); e->h_sam_off.release(); e->h_lines.release(); e->h_dest_off.release();
 	if (e->owns_index) {
 		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
 		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab);
@@ -1531,6 +1531,7 @@ struct CudaBK {
 		void *d = e->b_cub.need(tmp);
 		CK(cub::DeviceRadixSort::SortPairs(d, tmp, dk, dv, (int)n, 0, 20, e->stream));
 		if (dv.Current() != val) CK(cudaMemcpyAsync(val, dv.Current(), sizeof(int32_t) * n, cudaMemcpyDeviceToDevice, e->stream));
+		if (dk.Current() != key) CK(cudaMemcpyAsync(key, dk.Current(), sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, e->stream));
 		e->stats.n_launches += 2;
 	}
 	void zero(void *p, size_t bytes) { CK(cudaMemsetAsync(p, 0, bytes, e->stream)); }
@@ -1762,7 +1763,7 @@ void stage_finish(Engine *e, const FinishArgs &a)
 	cx.rtext = (const ReadText *)e->d_rtext.p; cx.text = (const char *)e->d_text.p;
 	cx.rg_len = a.rg_id ? (int)strnlen(a.rg_id, 255) : 0;
 	if (cx.rg_len) memcpy(cx.rg_id, a.rg_id, cx.rg_len);
-	FinishIn in = { (const DReg *)e->b_xout.p, (const int64_t *)e->b_soff.p, a.pes0, e->max_len, (const double *)e->d_logtab, e->n_log };
+	FinishIn in = { (const DReg *)e->b_xout.p, (const int64_t *)e->b_soff.p, a.pes0, e->max_len, (const double *)e->d_logtab, e->n_log, a.route };
 	FinishOut fo;
 	e->zero_counters();
 	const double k_sw0 = e->stats.ms_k_sw, k_gl0 = e->stats.ms_k_global;
@@ -1783,17 +1784,32 @@ void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out)
 	const FinishOut fo = e->fin_out;
 	// the text and (on request) the per-read offsets come back in page-locked memory
 	const double t0 = fin_clock_ms();
-	char *h_sam = a.alloc ? (char *)a.alloc((size_t)fo.sam_bytes + 1) : (char *)e->h_sam.need((size_t)fo.sam_bytes + 16);
-	e->d2h(h_sam, fo.sam, (size_t)fo.sam_bytes);
+	const bool routed = fo.routed != nullptr;
+	const char *d_text = routed ? fo.routed : fo.sam;
+	const int64_t bytes = routed ? fo.routed_bytes : fo.sam_bytes;
+	char *h_sam = a.alloc ? (char *)a.alloc((size_t)bytes + 1) : (char *)e->h_sam.need((size_t)bytes + 16);
+	e->d2h(h_sam, d_text, (size_t)bytes);
 	int64_t *h_off = nullptr;
 	if (a.want_offsets) {
 		h_off = (int64_t *)e->h_sam_off.need(sizeof(int64_t) * (e->n_reads + 1));
 		e->d2h(h_off, fo.sam_off, sizeof(int64_t) * (e->n_reads + 1));
 	}
+	SamLine *h_lines = nullptr;
+	int64_t *h_dest = nullptr;
+	const int n_dest = e->fm.n_ctg + 2;
+	if (a.route && !routed && fo.lines) {
+		h_lines = (SamLine *)e->h_lines.need(sizeof(SamLine) * (fo.n_lines + 1));
+		e->d2h(h_lines, fo.lines, sizeof(SamLine) * fo.n_lines);
+	}
+	if (routed) {
+		h_dest = (int64_t *)e->h_dest_off.need(sizeof(int64_t) * (n_dest + 1));
+		e->d2h(h_dest, fo.dest_off, sizeof(int64_t) * (n_dest + 1));
+	}
 	e->sync();
-	h_sam[fo.sam_bytes] = 0;
+	h_sam[bytes] = 0;
 	e->stats.ms_deliver += fin_clock_ms() - t0;
-	out.sam = h_sam; out.sam_off = h_off; out.bytes = fo.sam_bytes;
+	out.sam = h_sam; out.sam_off = h_off; out.bytes = bytes; out.lines = h_lines; out.n_lines = h_lines ? fo.n_lines : 0;
+	out.dest_off = h_dest; out.n_dest = n_dest;
 }
 
 void *stage_host_alloc(size_t bytes)

@@ -46,6 +46,8 @@ public:
 	std::shared_ptr<std::vector<double>> logtab;
 	int max_len = 0;
 	FinishOut fin_out;
+	std::vector<SamLine> lines;
+	std::vector<int64_t> dest_off;
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
@@ -486,7 +488,7 @@ void stage_finish(Engine *e, const FinishArgs &a)
 	cx.rtext = e->rtext.data(); cx.text = e->text.data();
 	cx.rg_len = a.rg_id ? (int)strnlen(a.rg_id, 255) : 0;
 	if (cx.rg_len) memcpy(cx.rg_id, a.rg_id, cx.rg_len);
-	FinishIn in = { e->xregs.data(), e->xoff.data(), a.pes0, e->max_len, e->logtab->data(), (int)e->logtab->size() };
+	FinishIn in = { e->xregs.data(), e->xoff.data(), a.pes0, e->max_len, e->logtab->data(), (int)e->logtab->size(), a.route };
 	FinishOut fo;
 	finish_run(bk, cx, in, fo, e->stats, emu_clock_ms);
 	e->fin_out = fo;
@@ -496,13 +498,22 @@ void stage_finish(Engine *e, const FinishArgs &a)
 void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out)
 {
 	const FinishOut fo = e->fin_out;
+	const bool routed = fo.routed != nullptr;
+	const char *text = routed ? fo.routed : fo.sam;
+	const int64_t bytes = routed ? fo.routed_bytes : fo.sam_bytes;
 	char *dst;
-	if (a.alloc) dst = (char *)a.alloc((size_t)fo.sam_bytes + 1);
-	else { e->sam.resize((size_t)fo.sam_bytes + 16); dst = e->sam.data(); }
-	memcpy(dst, fo.sam, (size_t)fo.sam_bytes);
-	dst[fo.sam_bytes] = 0;
+	if (a.alloc) dst = (char *)a.alloc((size_t)bytes + 1);
+	else { e->sam.resize((size_t)bytes + 16); dst = e->sam.data(); }
+	memcpy(dst, text, (size_t)bytes);
+	dst[bytes] = 0;
 	e->sam_off.assign(fo.sam_off, fo.sam_off + e->n_reads + 1);
-	out.sam = dst; out.sam_off = e->sam_off.data(); out.bytes = fo.sam_bytes;
+	const int n_dest = e->fm.n_ctg + 2;
+	const bool lines = a.route && !routed && fo.lines;
+	if (lines) e->lines.assign(fo.lines, fo.lines + fo.n_lines);
+	if (routed) e->dest_off.assign(fo.dest_off, fo.dest_off + n_dest + 1);
+	out.lines = lines ? e->lines.data() : nullptr; out.n_lines = lines ? fo.n_lines : 0;
+	out.dest_off = routed ? e->dest_off.data() : nullptr; out.n_dest = n_dest;
+	out.sam = dst; out.sam_off = e->sam_off.data(); out.bytes = bytes;
 }
 
 void *stage_host_alloc(size_t bytes) { return malloc(bytes); }

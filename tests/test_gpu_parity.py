@@ -413,6 +413,24 @@ def test_synthetic_vs_compiled_reference(tmp_path, name):
     assert got3 == want
 
 
+def test_per_chromosome_routing(tmp_path):
+    """row f3: the line table and the per-destination text of b200_set_routing / b200_align_chunk_end_routed (the routing kernels of
+    finish_stage.h) against the ByChr host's rule applied to the plain SAM; chimeric pairs over five contigs fill 'discordant'"""
+    import routing_check
+    from mpibwa_b200 import simulate, index_build
+    names, lengths, codes = simulate.make_reference(2_000_000, 5, seed=23)
+    prefix = str(tmp_path / "ref.fa")
+    index_build.write_fasta(prefix, simulate.codes_to_fasta_contigs(names, lengths, codes, n_runs=2))
+    index_build.build_index(prefix)
+    r1, r2 = simulate.simulate_pairs(codes, lengths, n_pairs=12000, unmappable_frac=0.05, seed=24)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1); open(f2, "wb").write(r2)
+    routing_check.make_chimeric(f2)
+    drv = os.path.join(ROOT, "tools", "b200_driver")
+    assert routing_check.check_driver(drv, ["-t", "8", "-K", "1200000", prefix, f1, f2], prefix) > 1000
+    assert routing_check.check_driver(drv, ["-t", "8", "-K", "700000", prefix, f1], prefix) == 0      # single-end: no discordant
+
+
 @pytest.mark.skipif(not have_ref(), reason="oracle/_ref did not travel")
 def test_odd_reads_vs_compiled_reference(tmp_path):
     """reads the simulator never makes - shorter than a seed, all N, homopolymers, exact copies of the reference, mates

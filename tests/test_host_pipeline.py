@@ -231,3 +231,24 @@ def test_given_insert_size_distribution(hostemu_built, tmp_path, pes):
     want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
     assert subprocess.run([drv, "-t", "4"] + args, capture_output=True, check=True).stdout == want
     assert subprocess.run([drv, "-P", "-t", "4"] + args, capture_output=True, check=True).stdout == want
+
+
+
+@pytest.mark.parametrize("shape", ["pe", "se", "chimeric"])
+def test_per_chromosome_routing(hostemu_built, examples, tmp_path, shape):
+    """b200_set_routing + b200_align_chunk_end_routed: the line table and the text grouped by destination against the reference
+    host's own routing rule (tests/routing_check.py) applied to the plain SAM of the same chunks; 'chimeric': three contigs and
+    every fifth pair with its second mate taken from another place, so that the discordant group fills"""
+    import routing_check
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    if shape == "chimeric":
+        prefix, f1, f2 = synthetic_case(tmp_path, 1000, seed=21)
+        routing_check.make_chimeric(f2)
+        args = ["-K", "80000", prefix, f1, f2]
+    else:
+        prefix = examples["idx"]
+        args = ["-K", "90000", prefix, _head(examples["R1_10K"], 1200, str(tmp_path / "a.fq"))]
+        if shape == "pe":
+            args.append(_head(examples["R2_10K"], 1200, str(tmp_path / "b.fq")))
+    n_disc = routing_check.check_driver(drv, ["-t", "4"] + args, prefix)
+    assert (n_disc > 50) == (shape == "chimeric")

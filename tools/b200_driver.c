@@ -102,11 +102,11 @@ static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t);
 
 int main(int argc, char **argv)
 {
-	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0, pipelined = 0;
+	int c, trimmed = 0, header = 0, n_threads = 1, rank = 0, nranks = 1, device = 0, pipelined = 0, route = 0;
 	mem_pestat_t pes_fixed[4], *pes0 = 0;
 	long K = 0;
 	mem_opt_t *opt = mem_opt_init();
-	while ((c = getopt(argc, argv, "K:t:THPCFv:r:n:d:o:I:")) >= 0) {
+	while ((c = getopt(argc, argv, "K:t:THPCFv:r:n:d:o:I:R:")) >= 0) {
 		if (c == 'K') K = atol(optarg);
 		else if (c == 't') n_threads = atoi(optarg);
 		else if (c == 'T') trimmed = 1;
@@ -120,6 +120,7 @@ int main(int argc, char **argv)
 		else if (c == 'd') device = atoi(optarg);
 		else if (c == 'o') set_opts(opt, optarg);
 		else if (c == 'I') pes0 = parse_pes(optarg, pes_fixed);
+		else if (c == 'R') route = atoi(optarg);   /* with -F: B200_ROUTE_* flags (per-chromosome routing of the chunk's lines) */
 	}
 	if (argc - optind < 2) { fprintf(stderr, "usage: b200_driver [-K n] [-t n] [-T] [-H] [-r rank -n nranks] [-d dev] idx r1.fq [r2.fq]\n"); return 1; }
 	opt->n_threads = n_threads;
@@ -175,9 +176,31 @@ int main(int argc, char **argv)
 					size_t o1 = (size_t)(s1[beg].name - 1 - b1), e1 = i + 1 < n1 ? (size_t)(s1[i + 1].name - 1 - b1) : l1;
 					size_t o2 = paired ? (size_t)(s2[beg].name - 1 - b2) : 0, e2 = paired ? (i + 1 < n1 ? (size_t)(s2[i + 1].name - 1 - b2) : l2) : 0;
 					char *sam = 0; int64_t sam_len = 0;
+					b200_set_routing(route);
 					b200_job_t *job = b200_align_fastq_begin(opt, idx, trimmed ? n_processed : 0, raw1 + o1, (int64_t)(e1 - o1), paired ? raw2 + o2 : 0, (int64_t)(e2 - o2));
-					n = (size_t)b200_align_chunk_end(job, &sam, &sam_len, 0);
-					fwrite(sam, 1, (size_t)sam_len, stdout);
+					if (!route) {
+						n = (size_t)b200_align_chunk_end(job, &sam, &sam_len, 0);
+						fwrite(sam, 1, (size_t)sam_len, stdout);
+					} else {
+						/* routed chunk: "@@CHUNK", then either the destinations' ranges ("@@DEST d bytes" + the bytes) or the text in
+						 * input order followed by its line table ("@@LINE off len rid mate_rid read") */
+						b200_sam_line_t *lines = 0; int64_t n_lines = 0, *dest_off = 0; int n_dest = 0, d;
+						n = (size_t)b200_align_chunk_end_routed(job, &sam, &sam_len, &lines, &n_lines, &dest_off, &n_dest, 0);
+						printf("@@CHUNK\t%lld\n", (long long)sam_len);
+						if (route & B200_ROUTE_BY_CONTIG) {
+							for (d = 0; d < n_dest; ++d)
+								if (dest_off[d + 1] > dest_off[d]) {
+									printf("@@DEST\t%d\t%lld\n", d, (long long)(dest_off[d + 1] - dest_off[d]));
+									fwrite(sam + dest_off[d], 1, (size_t)(dest_off[d + 1] - dest_off[d]), stdout);
+								}
+						} else {
+							int64_t l;
+							fwrite(sam, 1, (size_t)sam_len, stdout);
+							for (l = 0; l < n_lines; ++l)
+								printf("@@LINE\t%lld\t%d\t%d\t%d\t%d\n", (long long)lines[l].off, lines[l].len, lines[l].rid, lines[l].mate_rid, lines[l].read);
+						}
+						free(lines); free(dest_off);
+					}
 					b200_free(sam);
 				} else if (pipelined == 2) {
 					char *sam = 0; int64_t sam_len = 0;

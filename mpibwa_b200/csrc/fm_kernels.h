@@ -43,6 +43,10 @@ struct FmView {
 	const int64_t *ctg_off;     // contig offsets (forward strand)
 	const int32_t *ctg_len;
 	int n_ctg;
+	// k-mer interval tables (smem_kernel.cuh, "k-mer tables"): the bi-interval of every pattern of 1 .. kmax bases, 16 bytes each,
+	// length L at entry ktab_off(L) + (pattern as a base-4 number, first base most significant); kmax == 0: none
+	const uint32_t *ktab;
+	int kmax;
 };
 
 struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads
@@ -102,6 +106,19 @@ B200_HD void occ_convert_block(const uint32_t *ref_bwt, uint64_t b, uint32_t out
 }
 
 struct OccRaw { uint32_t w[8]; };
+
+// one 32-byte sector (p is 32-byte aligned) of a table read at random
+B200_HD OccRaw ld_sector(const uint32_t *p)
+{
+	OccRaw r;
+#if defined(__CUDA_ARCH__)
+	asm("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+#else
+	for (int i = 0; i < 8; ++i) r.w[i] = p[i];
+#endif
+	return r;
+}
 
 B200_HD OccRaw ld_occ(const FmView &fm, uint64_t blk)
 {

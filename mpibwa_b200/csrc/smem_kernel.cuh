@@ -84,6 +84,93 @@ B200_HD void fm_extend_sel(const FmView &fm, uint64_t x0, uint64_t x1, uint64_t 
 	fm_extend_use(fm, x0, x1, x2, is_back, c, rk, rl, o0, o1, o2, n_blocks);
 }
 
+/* ---------------------------------------------------------------- k-mer tables
+ * The bi-interval of a pattern is a function of the pattern alone, whichever way bwt_extend (reference src/bwt.c:262-275) reached
+ * it (the reference's text is its own reverse complement, so the "other" coordinate it carries along is the interval of the reverse
+ * complement).  With 180 GB of HBM the intervals of EVERY pattern of up to kmax bases (15 for a human-sized reference: 22.9 GB) are
+ * tabulated once when the index is uploaded, by the same extension routine, level L from level L-1, so that the sweeps can replace
+ * an extension whose result is a pattern of at most kmax bases - two dependent random occ sectors - by ONE random sector that
+ * depends on nothing but the read.  Entries of absent patterns hold exactly what the reference's extensions of an empty interval
+ * produce (size 0 with real coordinates): the greedy pass keeps extending those (src/bwt.c:367-376).
+ * An entry also carries the number of reference-layout occ blocks (the unit of SURVEY.md 8d's algorithmic traffic) that the
+ * reference's forward extensions from the first base to this pattern touch, so that the traffic counter stays the reference's. */
+B200_HD uint64_t ktab_off(int L) { return (((uint64_t)1 << (2 * L)) - 4) / 3; }       // entries of lengths 1 .. L-1
+B200_HD uint64_t ktab_entries(int kmax) { return kmax > 0 ? ktab_off(kmax + 1) : 0; }
+// default depth: the longest patterns of which a text of seq_len bases still holds most (4^kmax <= 2 * seq_len), at most 15
+// (22.9 GB of table; 16 would be 91.6 GB)
+inline int ktab_default_kmax(uint64_t seq_len)
+{
+	int k = 0;
+	while (k < 15 && ((uint64_t)1 << (2 * (k + 1))) <= 2 * seq_len) ++k;
+	return k;
+}
+B200_HD Q4 ktab_pack(uint64_t x0, uint64_t x1, uint64_t x2, int blocks)
+{
+	Q4 v;
+	v.x = (uint32_t)x0; v.y = (uint32_t)x1; v.z = (uint32_t)x2;
+	v.w = (uint32_t)blocks | (uint32_t)(x0 >> 32) << 29 | (uint32_t)(x1 >> 32) << 30 | (uint32_t)(x2 >> 32) << 31;
+	return v;
+}
+// the sector that holds entry (L, idx) and which half of it
+B200_HD const uint32_t *ktab_sector(const FmView &fm, int L, uint32_t idx, int &half)
+{
+	const uint64_t e = ktab_off(L) + idx;
+	half = (int)(e & 1);
+	return fm.ktab + ((e >> 1) << 3);
+}
+B200_HD void ktab_unpack(const OccRaw &r, int half, uint64_t &x0, uint64_t &x1, uint64_t &x2, int &blocks)
+{
+	const uint32_t a = half ? r.w[4] : r.w[0], b = half ? r.w[5] : r.w[1], c = half ? r.w[6] : r.w[2], w = half ? r.w[7] : r.w[3];
+	x0 = (uint64_t)(w >> 29 & 1u) << 32 | a;
+	x1 = (uint64_t)(w >> 30 & 1u) << 32 | b;
+	x2 = (uint64_t)(w >> 31) << 32 | c;
+	blocks = (int)(w & 0xffu);
+}
+// reference-layout occ blocks one bwt_extend of the interval touches (base = the coordinate it extends on); see fm_extend_use
+B200_HD int fm_extend_blocks(const FmView &fm, uint64_t base, uint64_t x2)
+{
+	const uint64_t k = base - 1, l = base - 1 + x2;
+	const bool kz = k == (uint64_t)-1, lz = l == (uint64_t)-1;
+	const uint64_t ka = kz ? 0 : k - (k >= fm.primary), la = lz ? 0 : l - (l >= fm.primary);
+	return (kz ? 0 : 1) + ((!lz && (kz || (la >> 7) != (ka >> 7))) ? 1 : 0);
+}
+// entry `idx` of level L (L >= 1) of the table from level L-1: the forward extension of the parent pattern by the base idx & 3
+B200_HD Q4 ktab_make(const FmView &fm, int L, uint32_t idx)
+{
+	const int b = (int)(idx & 3u);
+	if (L == 1) return ktab_pack(l2_at(fm, b) + 1, l2_at(fm, 3 - b) + 1, l2_at(fm, b + 1) - l2_at(fm, b), 0);
+	int half, pb;
+	const uint32_t *ps = ktab_sector(fm, L - 1, idx >> 2, half);
+	OccRaw r;
+	for (int i = 0; i < 8; ++i) r.w[i] = ps[i];
+	uint64_t p0, p1, p2, o0, o1, o2;
+	ktab_unpack(r, half, p0, p1, p2, pb);
+	// (a symbol array that is not the transform of a text - a damaged index - can lead an interval outside the table: keep the loads inside)
+	if (p1 < 1 || p1 - 1 + p2 > fm.seq_len) return ktab_pack(1, 1, 0, pb);
+	int64_t nb = 0;
+	fm_extend_sel(fm, p0, p1, p2, 0, 3 - b, o0, o1, o2, nb);
+	return ktab_pack(o0, o1, o2, pb + (int)nb);
+}
+// a step of a sweep that is served by the table (tab) or by an extension: the loads ...
+B200_HD void fm_step_load(const FmView &fm, bool tab, int L, uint32_t idx, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, OccRaw &rk, OccRaw &rl, int &half)
+{
+	if (tab) { rk = ld_sector(ktab_sector(fm, L, idx, half)); return; }
+	half = 0;
+	fm_extend_load(fm, x0, x1, x2, is_back, rk, rl);
+}
+// ... and the result.  n_blocks counts what the reference's extension of (x0, x1, x2) touches either way.
+B200_HD void fm_step_use(const FmView &fm, bool tab, int half, uint64_t x0, uint64_t x1, uint64_t x2, int is_back, int c, const OccRaw &rk, const OccRaw &rl,
+                         uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &n_blocks)
+{
+	if (tab) {
+		int tb;
+		ktab_unpack(rk, half, o0, o1, o2, tb);
+		n_blocks += fm_extend_blocks(fm, is_back ? x0 : x1, x2);
+		return;
+	}
+	fm_extend_use(fm, x0, x1, x2, is_back, c, rk, rl, o0, o1, o2, n_blocks);
+}
+
 // The interval list of one lane.  Entry k < quota lives in shared memory (sh[(k*4 + word) * stride]), the rest in the
 // lane's global strip (spill[(k - quota) * sstride]).  Values up to 2^33-1, end positions up to 2^29-1.
 struct SeedList {

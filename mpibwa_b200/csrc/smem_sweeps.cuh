@@ -40,14 +40,25 @@ struct FwdLane {
 	uint64_t k0, k1, k2, min_intv; int kend;
 	int wpos, hdr_pos, n, n_sweeps, over;
 	int n_out, old_n, k2i;
+	// k-mer tables (smem_kernel.cuh): tab != 0 = the pending step is a table look-up of the klen bases packed in W instead of an
+	// extension; 1 = one step of a forward sweep (pattern q[sx .. i]), 2 = the first klen-1 steps of the greedy pass at once
+	int kmax, tab, klen; uint32_t W;
 
 	// k_first: first interval of `outp` that pass 2 may re-seed (the greedy seeds of pass 3 come before it and are not candidates)
-	B200_HD void begin(const SeedOpt &so, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
+	B200_HD void begin(const SeedOpt &so, int kmax_, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
 	{
-		mode = mode_; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
+		kmax = kmax_; mode = mode_; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
 		n_out = n_out_; old_n = n_out_; k2i = k_first;
 		x = 0; wpos = 0; n_sweeps = 0; over = 0;
+		tab = 0; klen = 0; W = 0;
 		st = len >= so.min_seed_len ? NEXT : DONE;
+	}
+	// the extension by base qn = q[i] of the sweep that began at sx is the next step: through the table while the pattern is short
+	B200_HD void want(int qn)
+	{
+		c = 3 - qn;
+		tab = 0;
+		if (st == FWD && i - sx < kmax) { W = W << 2 | (uint32_t)qn; klen = i - sx + 1; tab = 1; }
 	}
 	B200_HD void set_intv(const FmView &fm, int b) { k0 = l2_at(fm, b) + 1; k2 = l2_at(fm, b + 1) - l2_at(fm, b); k1 = l2_at(fm, 3 - b) + 1; }
 	B200_HD void push()
@@ -60,6 +71,7 @@ struct FwdLane {
 		set_intv(fm, q[x_]);
 		kend = x_ + 1; min_intv = mi < 1 ? 1 : mi; sx = x_; i = x_ + 1; n = 0;
 		hdr_pos = wpos++;
+		W = q[x_];
 		st = FWD;
 	}
 	B200_HD void end_sweep()      // the interval that could not be extended further closes the list; its end is the next x
@@ -97,19 +109,28 @@ struct FwdLane {
 				}
 				break;
 			case FWD:
-				if (i < len && q[i] < 4) { c = 3 - q[i]; return true; }
+				if (i < len && q[i] < 4) { want(q[i]); return true; }
 				end_sweep();
 				break;
-			case P3_NEXT:
+			case P3_NEXT: {
 				if (x >= len) { st = DONE; break; }
 				if (q[x] > 3) { ++x; break; }
 				set_intv(fm, q[x]);
 				sx = x; i = x + 1; st = P3;
+				// no seed can be reported before the pattern has min_seed_len + 1 bases (src/bwt.c:369): the run of plain bases at sx,
+				// up to min(kmax, min_seed_len) of them, is ONE table look-up instead of an extension per base
+				int run = kmax < so.min_seed_len ? kmax : so.min_seed_len;
+				if (run > len - sx) run = len - sx;
+				W = q[x];
+				int m = 1;
+				for (; m < run && q[sx + m] < 4; ++m) W = W << 2 | q[sx + m];
+				if (m >= 2) { klen = m; i = sx + m - 1; tab = 2; c = 3 - q[i]; return true; }
 				break;
+			}
 			case P3:
 				if (i >= len) { st = DONE; break; }
 				if (q[i] > 3) { x = i + 1; st = P3_NEXT; break; }
-				c = 3 - q[i];
+				want(q[i]);
 				return true;
 			default:
 				return false;
@@ -133,10 +154,20 @@ struct FwdLane {
 			}
 			k0 = o0; k1 = o1; k2 = o2; ++i;
 		}
-		if (i < len) { const int qn = q[i]; if (qn < 4) { c = 3 - qn; return true; } }
+		if (i < len) { const int qn = q[i]; if (qn < 4) { want(qn); return true; } }
 		return false;
 	}
 };
+
+// one trip of a forward lane: the pending step's result and the reference's occ-block count for it
+B200_HD void fwd_lane_fetch(const FmView &fm, const FwdLane &ln, uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &blocks)
+{
+	OccRaw rk, rl;
+	int half;
+	fm_step_load(fm, ln.tab != 0, ln.klen, ln.W, ln.k0, ln.k1, ln.k2, 0, rk, rl, half);
+	if (ln.tab == 2) { int tb; ktab_unpack(rk, half, o0, o1, o2, tb); blocks += tb; }
+	else fm_step_use(fm, ln.tab != 0, half, ln.k0, ln.k1, ln.k2, 0, ln.c, rk, rl, o0, o1, o2, blocks);
+}
 
 struct BwdLane {
 	enum { NEXT, ROW, BWD, DONE };
@@ -144,9 +175,16 @@ struct BwdLane {
 	int st, i, c, rpos, sweeps_left;
 	uint64_t k0, k1, k2, min_intv, last_x2; int kend;
 	int n_list, n_prev, j, n_curr, nm, last_start, n_out;
+	// k-mer tables: W = the kmax bases from the row's start i on, first base most significant; an entry of the row whose extended
+	// pattern q[i .. kend) has at most kmax bases is looked up (tab_len > 0 and tab_idx) instead of extended
+	int kmax; uint32_t W;
 
-	B200_HD void begin(int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_)
+	B200_HD int tab_len(int end) const { return end - i <= kmax ? end - i : 0; }
+	B200_HD uint32_t tab_idx(int L) const { return L ? W >> (2 * (kmax - L)) : 0u; }
+	B200_HD void row_base(int cc) { if (kmax) W = (uint32_t)cc << (2 * (kmax - 1)) | W >> 2; }
+	B200_HD void begin(int kmax_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_)
 	{
+		kmax = kmax_; W = 0;
 		len = len_; q = q_; outp = outp_; strip = strip_; rpos = 0; sweeps_left = n_sweeps; n_out = n_out_;
 		st = NEXT;
 	}
@@ -179,6 +217,8 @@ struct BwdLane {
 				}
 				rpos += n_list;                                   // (entries beyond the quota are read in place through L.spill)
 				nm = 0; last_start = 0;
+				W = 0;
+				for (int k = 0; k < kmax; ++k) W = W << 2 | (uint32_t)((int)h.y + k < len ? q[(int)h.y + k] & 3 : 0);
 				st = ROW;
 				break;
 			}
@@ -190,6 +230,7 @@ struct BwdLane {
 					break;
 				}
 				c = cc; j = 0; n_curr = 0; st = BWD;
+				row_base(cc);
 				break;
 			}
 			case BWD:
@@ -202,10 +243,9 @@ struct BwdLane {
 	}
 	// the entry after the current one in the row being extended (its extension is independent of the current one: reference
 	// src/bwt.c:326-345 walks the row's entries with the same base); false at the end of the row
-	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p1, uint64_t &p2) const
+	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p1, uint64_t &p2, int &pe) const
 	{
 		if (st != BWD || j + 1 >= n_prev) return false;
-		int pe;
 		L.get(n_list - 2 - j, p0, p1, p2, pe);
 		return true;
 	}
@@ -223,6 +263,7 @@ struct BwdLane {
 			n_prev = n_curr; --i;
 			if (i < 0 || q[i] > 3) { st = ROW; return false; }
 			c = q[i]; j = 0; n_curr = 0;
+			row_base(c);
 		}
 		L.get(n_list - 1 - j, k0, k1, k2, kend);
 		return true;
@@ -264,7 +305,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 			r = atomicAdd(a.next_read, 1);
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			if (MODE == 2 && a.n_sweeps[r] < 0) { r = -1; continue; }       // already handed to the general kernel
-			ln.begin(a.so, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
+			ln.begin(a.so, a.fm.kmax, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
 			         a.strips + (int64_t)r * a.strip_cap, a.strip_cap, MODE == 1 ? 0 : a.n_intv[r], MODE == 1 ? 0 : a.n_first[r]);
 			if (MODE == 2 && ln.n_out > a.cap) ln.st = FwdLane::DONE;        // output overflow: the whole batch is rerun anyway
 			need = ln.advance(a.fm, a.so);
@@ -272,7 +313,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			uint64_t o0, o1, o2;
-			fm_extend_sel(a.fm, ln.k0, ln.k1, ln.k2, 0, ln.c, o0, o1, o2, blocks);
+			fwd_lane_fetch(a.fm, ln, o0, o1, o2, blocks);
 			if (!ln.step(a.so, a.cap, o0, o1, o2)) need = ln.advance(a.fm, a.so);
 		}
 	}
@@ -297,6 +338,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a, int quota)
 	// registers).  ahead: the sectors in (nk, nl) belong to the entry that is now current.
 	OccRaw nk, nl;
 	bool ahead = false;
+	int nhalf = 0, ntl = 0;
 	for (;;) {
 		while (!need && !drained) {
 			if (r >= 0) { a.n_intv[r] = ln.n_out; if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out); }
@@ -304,20 +346,22 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a, int quota)
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			const int ns = a.n_sweeps[r];
 			if (ns <= 0) { r = -1; continue; }
-			ln.begin((int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r]);
+			ln.begin(a.fm.kmax, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r]);
 			need = ln.advance(a.so, a.cap, L);
 			ahead = false;
 		}
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
 			OccRaw rk, rl;
-			if (ahead) { rk = nk; rl = nl; }
-			else fm_extend_load(a.fm, ln.k0, ln.k1, ln.k2, 1, rk, rl);
+			int half, tl;
+			if (ahead) { rk = nk; rl = nl; half = nhalf; tl = ntl; }
+			else { tl = ln.tab_len(ln.kend); fm_step_load(a.fm, tl != 0, tl, ln.tab_idx(tl), ln.k0, ln.k1, ln.k2, 1, rk, rl, half); }
 			uint64_t p0, p1, p2;
-			ahead = ln.peek(L, p0, p1, p2);
-			if (ahead) fm_extend_load(a.fm, p0, p1, p2, 1, nk, nl);
+			int pe;
+			ahead = ln.peek(L, p0, p1, p2, pe);
+			if (ahead) { ntl = ln.tab_len(pe); fm_step_load(a.fm, ntl != 0, ntl, ln.tab_idx(ntl), p0, p1, p2, 1, nk, nl, nhalf); }
 			uint64_t o0, o1, o2;
-			fm_extend_use(a.fm, ln.k0, ln.k1, ln.k2, 1, ln.c, rk, rl, o0, o1, o2, blocks);
+			fm_step_use(a.fm, tl != 0, half, ln.k0, ln.k1, ln.k2, 1, ln.c, rk, rl, o0, o1, o2, blocks);
 			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) { need = ln.advance(a.so, a.cap, L); ahead = false; }
 		}
 	}

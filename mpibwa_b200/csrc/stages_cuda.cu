@@ -116,7 +116,7 @@ public:
 	DevBuf b_grow;
 	// finish stages (finish_stage.h): scratch by FinBuf id, the read text, contig names, the log table, the SAM text on the host
 	DevBuf fb[FB_N], d_rtext, d_text;
-	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr;
+	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr, *d_ktab = nullptr;
 	int n_log = 0;
 	PinBuf h_sam, h_sam_off, h_lines, h_dest_off;
 	FinishOut fin_out;
@@ -186,6 +186,14 @@ __global__ void k_occ_convert(const uint32_t *__restrict__ ref_bwt, uint64_t n_s
 	uint4 *o = reinterpret_cast<uint4 *>(occ + (b << 3));
 	o[0] = make_uint4(w[0], w[1], w[2], w[3]);
 	o[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
+// level L of the k-mer interval tables from level L-1 (smem_kernel.cuh), one entry per thread
+__global__ void k_ktab_level(FmView fm, int L, Q4 *tab)
+{
+	const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (idx >> (2 * L)) return;
+	tab[ktab_off(L) + idx] = ktab_make(fm, L, (uint32_t)idx);
 }
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
@@ -260,6 +268,30 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
+	{	// k-mer interval tables: every pattern of up to kmax bases, built level by level with the seeding kernels' own extension
+		// (B200_KMER_MAX: depth override, 0 = none; never more than half of the memory that is free now)
+		int kmax = ktab_default_kmax(fm.seq_len);
+		if (getenv("B200_KMER_MAX")) kmax = std::max(0, std::min(16, atoi(getenv("B200_KMER_MAX"))));
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		while (kmax > 0 && ktab_entries(kmax) * sizeof(Q4) > free_b / 2) --kmax;
+		fm.ktab = nullptr; fm.kmax = 0;
+		if (kmax > 0) {
+			const auto t0 = std::chrono::steady_clock::now();
+			CK(cudaMalloc(&e->d_ktab, ktab_entries(kmax) * sizeof(Q4) + 64));
+			fm.ktab = (const uint32_t *)e->d_ktab;
+			for (int L = 1; L <= kmax; ++L) {
+				const uint64_t n = (uint64_t)1 << (2 * L);
+				k_ktab_level<<<(unsigned)((n + 255) / 256), 256>>>(fm, L, (Q4 *)e->d_ktab);
+				CK(cudaGetLastError());
+			}
+			CK(cudaDeviceSynchronize());
+			fm.kmax = kmax;
+			if (getenv("B200_DEBUG"))
+				fprintf(stderr, "[mpibwa_b200] k-mer interval tables: patterns of up to %d bases, %.2f GB, built in %.0f ms\n", kmax,
+				        ktab_entries(kmax) * sizeof(Q4) / 1e9, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		}
+	}
 
 	engine_set_l2_window(e);
 	return e;
@@ -318,7 +350,7 @@ Engine *engine_clone(Engine *base)
 	e->owns_index = false;
 	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len; e->d_ctg_alt = base->d_ctg_alt;
 	e->d_ctg_name_off = base->d_ctg_name_off; e->d_ctg_names = base->d_ctg_names; e->d_ctg_anno_off = base->d_ctg_anno_off; e->d_ctg_annos = base->d_ctg_annos;
-	e->d_logtab = base->d_logtab; e->n_log = base->n_log;
+	e->d_logtab = base->d_logtab; e->n_log = base->n_log; e->d_ktab = base->d_ktab;
 	e->bwt_bytes = base->bwt_bytes;
 	e->fm = base->fm;
 	engine_set_l2_window(e);
@@ -337,7 +369,7 @@ void engine_destroy(Engine *e)
 	e->h_sam.release(); e->h_sam_off.release(); e->h_lines.release(); e->h_dest_off.release();
 	if (e->owns_index) {
 		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
-		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab);
+		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab); cudaFree(e->d_ktab);
 	}
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_sync);

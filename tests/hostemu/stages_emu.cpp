@@ -35,6 +35,7 @@ public:
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
+	std::shared_ptr<std::vector<Q4>> ktab;           // k-mer interval tables, built level by level with the routine the upload kernel runs
 	// finish stages
 	std::vector<DReg> xregs;
 	std::vector<int64_t> xoff;
@@ -64,6 +65,15 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
+	{
+		int kmax = ktab_default_kmax(bwt->seq_len);
+		if (getenv("B200_KMER_MAX")) kmax = std::max(0, std::min(16, atoi(getenv("B200_KMER_MAX"))));
+		e->ktab = std::make_shared<std::vector<Q4>>(ktab_entries(kmax) + 2);
+		e->fm.ktab = (const uint32_t *)e->ktab->data(); e->fm.kmax = kmax;
+		if (getenv("B200_DEBUG")) fprintf(stderr, "[hostemu] k-mer interval tables up to %d bases (%llu entries)\n", kmax, (unsigned long long)ktab_entries(kmax));
+		for (int L = 1; L <= kmax; ++L)
+			for (uint64_t idx = 0; idx < (uint64_t)1 << (2 * L); ++idx) (*e->ktab)[ktab_off(L) + idx] = ktab_make(e->fm, L, (uint32_t)idx);
+	}
 	for (int i = 0; i < bns->n_seqs; ++i) { e->ctg_off.push_back(bns->anns[i].offset); e->ctg_len.push_back(bns->anns[i].len); }
 	for (int i = 0; i < bns->n_seqs; ++i) e->ctg_alt.push_back(bns->anns[i].is_alt ? 1 : 0);
 	e->ctg_alt.push_back(0);
@@ -83,7 +93,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->occ = base->occ;
+	e->occ = base->occ; e->ktab = base->ktab;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;
@@ -158,6 +168,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 	for (int r = 0; r < n_reads; ++r) {
 		int len = (int)(off[r + 1] - off[r]);
 		int n = 0;
+		const int64_t blocks_before = e->stats.fm_occ_blocks;
 		if (len >= so.min_seed_len) {
 			scratch.resize(3 * (len + 1));
 			int cap = len + 32;
@@ -203,13 +214,14 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 				std::vector<Intv> out3(cap2);
 				std::vector<uint32_t> sh2(4 * quota);
 				int n_out = 0, n_first = 0, n_sw = 0;
+				int64_t blocks3 = 0;
 				for (int pass = 1; pass <= 2 && n_sw >= 0; ++pass) {
 					FwdLane f;
-					f.begin(so, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
+					f.begin(so, e->fm.kmax, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
 					bool nd = f.advance(e->fm, so);
 					while (nd) {
 						uint64_t o0, o1, o2;
-						fm_extend_sel(e->fm, f.k0, f.k1, f.k2, 0, f.c, o0, o1, o2, blocks);
+						fwd_lane_fetch(e->fm, f, o0, o1, o2, blocks3);
 						if (!f.step(so, cap2, o0, o1, o2)) nd = f.advance(e->fm, so);
 					}
 					n_out = f.n_out; n_sw = f.over ? -1 : f.n_sweeps;
@@ -217,11 +229,15 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					if (n_sw <= 0) continue;
 					SeedList L2; L2.sh = sh2.data(); L2.stride = 1; L2.quota = quota; L2.spill = nullptr; L2.sstride = 1;
 					BwdLane b;
-					b.begin(len, codes + off[r], out3.data(), strip.data(), n_sw, n_out);
+					b.begin(e->fm.kmax, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out);
 					nd = b.advance(so, cap2, L2);
 					while (nd) {
 						uint64_t o0, o1, o2;
-						fm_extend_sel(e->fm, b.k0, b.k1, b.k2, 1, b.c, o0, o1, o2, blocks);
+						OccRaw rk, rl;
+						int half;
+						const int tl = b.tab_len(b.kend);
+						fm_step_load(e->fm, tl != 0, tl, b.tab_idx(tl), b.k0, b.k1, b.k2, 1, rk, rl, half);
+						fm_step_use(e->fm, tl != 0, half, b.k0, b.k1, b.k2, 1, b.c, rk, rl, o0, o1, o2, blocks3);
 						if (!b.step(so, cap2, L2, o0, o1, o2)) nd = b.advance(so, cap2, L2);
 					}
 					n_out = b.n_out;
@@ -233,6 +249,8 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 						same3 = out3[i].x0 == out[i].x0 && out3[i].x1 == out[i].x1 && out3[i].x2 == out[i].x2 && out3[i].info == out[i].info;
 				}
 				if (!same3) { fprintf(stderr, "[hostemu] seeding sweeps disagree with fm_collect_intv on read %d (%d vs %d intervals, sweeps %d)\n", r, n_out, n, n_sw); abort(); }
+				// the traffic counter of the sweeps (extensions served by the k-mer tables included) is the plain routine's
+				if (n_sw >= 0 && blocks3 != e->stats.fm_occ_blocks - blocks_before) { fprintf(stderr, "[hostemu] seeding sweeps count %lld occ blocks on read %d, fm_collect_intv %lld\n", (long long)blocks3, r, (long long)(e->stats.fm_occ_blocks - blocks_before)); abort(); }
 			}
 			if (!same) { fprintf(stderr, "[hostemu] seeding state machine disagrees with fm_collect_intv on read %d (%d vs %d intervals)\n", r, ln.n_out, n); abort(); }
 		}

@@ -250,14 +250,22 @@ def _reads_as_codes(path, n):
     return out
 
 
-@pytest.mark.parametrize("kernel", ["sweeps", "lanes", "sweeps_overflow"])
+_occ_blocks = {}
+
+
+@pytest.mark.parametrize("kernel", ["sweeps", "lanes", "sweeps_overflow", "sweeps_no_tables", "sweeps_tables5"])
 def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
-    # the homogeneous sweep kernels (default), the general per-lane state machine, and sweeps with strips so small that
-    # most reads overflow and are redone by the general kernel
+    # the homogeneous sweep kernels (default: short patterns served by the k-mer interval tables), the general per-lane state
+    # machine (extensions only), sweeps with strips so small that most reads overflow and are redone by the general kernel, and the
+    # sweeps without tables / with tables of only five bases (an index uploaded anew with B200_KMER_MAX)
     if kernel == "lanes":
         monkeypatch.setenv("B200_SEED_KERNEL", "lanes")
     if kernel == "sweeps_overflow":
         monkeypatch.setenv("B200_SEED_STRIP", "40")
+    if kernel in ("sweeps_no_tables", "sweeps_tables5"):
+        monkeypatch.setenv("B200_KMER_MAX", "0" if kernel == "sweeps_no_tables" else "5")
+        aligner = M.Aligner(examples["idx"], device=0, n_threads=8, verbose=1)
+    blocks0 = _aux_stats(aligner.lib)["fm_occ_blocks"]
     idxf = OL.IndexFiles(examples["idx"])
     rng = np.random.default_rng(9)
     reads = _reads_as_codes(examples["R1_10K"], 400)
@@ -284,6 +292,12 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
         n_total += len(got)
     assert n_total > 1000
     aligner.lib.b200_free(intv); aligner.lib.b200_free(ioff)
+    # the algorithmic traffic counter (reference-layout occ blocks the REFERENCE's extensions touch) does not depend
+    # on how the kernels got the intervals: table look-ups count the blocks of the extension they stand for
+    # (strip overflows excepted: those reads are counted by the sweep that gave up and again by the general kernel)
+    if kernel != "sweeps_overflow":
+        _occ_blocks[kernel] = _aux_stats(aligner.lib)["fm_occ_blocks"] - blocks0
+        assert _occ_blocks[kernel] > 100000 and len(set(_occ_blocks.values())) == 1, _occ_blocks
     ks = np.concatenate([[1, idxf.primary, idxf.seq_len, 32], rng.integers(1, idxf.seq_len + 1, size=20000)]).astype(np.uint64)
     sa = np.zeros(len(ks), np.uint64)
     aligner.lib.b200_bwt_sa_batch(len(ks), ks.ctypes.data, sa.ctypes.data)

@@ -169,23 +169,59 @@ B200_HD void fwd_lane_fetch(const FmView &fm, const FwdLane &ln, uint64_t &o0, u
 	else fm_step_use(fm, ln.tab != 0, half, ln.k0, ln.k1, ln.k2, 0, ln.c, rk, rl, o0, o1, o2, blocks);
 }
 
+// Backward sweeps (reference src/bwt.c:326-345) WITHOUT the rows.  The reference extends every entry of the forward list one base
+// at a time, row by row, and reports an entry when it dies in a row in which no longer-forward entry survived before it.  An
+// entry's occurrences contain those of every entry that reaches further forward, so with
+//     b_k = the number of bases entry k can be extended backward by before its interval falls under min_intv
+//           (or the read's start / an ambiguous base stops it: b_lim),
+// b_k never decreases from the longest-forward entry to the shortest, and entry k is reported exactly when b_k is GREATER than the
+// b of the next-longer entry (equal b: the longer one was reported in that row first and `i + 1 < last_start` fails; entries the
+// reference merges because their sizes coincide have identical occurrences, hence equal b, and are never reported).  So the
+// entries are independent chains and nothing needs b_k but the report decision - and a report shorter than min_seed_len is dropped
+// (src/bwamem.c:130).  With the k-mer tables an entry of L0 < kj = min(kmax, min_seed_len) forward bases starts its chain with ONE
+// look-up of the kj-base pattern that ends where the entry ends: if that pattern is absent the entry dies short of kj bases - it
+// cannot be reported, and every shorter-forward entry that is still alive at its own kj-base pattern reaches further back than it
+// did (the report rule holds without knowing where it died); if present, the chain goes on from there by extensions.  Per sweep:
+// one look-up per entry plus the few extensions past kj bases, instead of the whole triangle of rows.
 struct BwdLane {
-	enum { NEXT, ROW, BWD, DONE };
+	enum { NEXT, ENTRY, STEP, DONE };
 	int len; const uint8_t *q; Intv *outp; const Q4 *strip;
-	int st, i, c, rpos, sweeps_left;
-	uint64_t k0, k1, k2, min_intv, last_x2; int kend;
-	int n_list, n_prev, j, n_curr, nm, last_start, n_out;
-	// k-mer tables: W = the kmax bases from the row's start i on, first base most significant; an entry of the row whose extended
-	// pattern q[i .. kend) has at most kmax bases is looked up (tab_len > 0 and tab_idx) instead of extended
-	int kmax; uint32_t W;
+	int st, c, rpos, sweeps_left;
+	uint64_t k0, k1, k2, min_intv; int kend;      // the entry's interval as extended so far
+	int n_list, j, x, b, b_lim, b_prev, n_out;
+	int kmax, kj, tab, klen; uint32_t W;          // tab: the pending step is a look-up of the klen bases in W
+	uint64_t P;                                   // bases q[x-16 .. x+16), two bits each, first base most significant
+	int scan, last_n;                             // ambiguous bases seen so far: last_n = the last one before `scan`
+	// The reference merges entries whose sizes coincide in a row; independent chains walk such entries separately.  That is a few
+	// steps per entry on ordinary reads, but entries that survive TOGETHER for many bases (a read whose flank matches another copy
+	// of a repeat) would multiply the reference's work: a read that needs more than `budget` extensions in one kernel is handed to
+	// the general state machine (k_seed_lanes: the reference's rows) like a read whose strip overflowed.
+	int steps, budget, over;
+	// What stands in for the merge: the sizes the last WALKED entry had at the first TRAJ offsets of its chain (tr[cur]).  A
+	// shorter-forward entry whose size at one of those offsets is the same has the same occurrences from there on (its set contains
+	// the walked entry's), so it ends where the walked entry ended and is not reported: its chain stops at once.
+	enum { TRAJ = 8 };
+	uint32_t *tr; int tr_stride;                  // tr[(buf * TRAJ + t) * tr_stride]: buf `cur` = last walked entry, the other = the chain being walked
+	int cur, tr_base, tr_n, tr_b, nw_base, nw_n;  // offsets tr_base .. tr_base + tr_n - 1 hold sizes; tr_b = where that entry ended
 
-	B200_HD int tab_len(int end) const { return end - i <= kmax ? end - i : 0; }
-	B200_HD uint32_t tab_idx(int L) const { return L ? W >> (2 * (kmax - L)) : 0u; }
-	B200_HD void row_base(int cc) { if (kmax) W = (uint32_t)cc << (2 * (kmax - 1)) | W >> 2; }
-	B200_HD void begin(int kmax_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_)
+	B200_HD bool same_as_walked(int off, uint64_t size) const
 	{
-		kmax = kmax_; W = 0;
+		const int t = off - tr_base;
+		return t >= 0 && t < tr_n && size < 0xffffffffu && tr[(cur * TRAJ + t) * tr_stride] == (uint32_t)size;
+	}
+	B200_HD void note(int off, uint64_t size)      // the chain being walked is at `off` with `size` occurrences
+	{
+		if (nw_n == 0) nw_base = off;
+		if (off - nw_base == nw_n && nw_n < TRAJ) { tr[((cur ^ 1) * TRAJ + nw_n) * tr_stride] = size < 0xffffffffu ? (uint32_t)size : 0xffffffffu; ++nw_n; }
+	}
+
+	B200_HD void begin(const SeedOpt &so, int kmax_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_, uint32_t *tr_, int tr_stride_)
+	{
+		tr = tr_; tr_stride = tr_stride_; cur = 0; tr_n = 0; tr_base = 0; tr_b = 0; nw_n = 0; nw_base = 0;
+		kmax = kmax_; kj = kmax_ < so.min_seed_len ? kmax_ : so.min_seed_len; tab = 0; klen = 0; W = 0; P = 0;
 		len = len_; q = q_; outp = outp_; strip = strip_; rpos = 0; sweeps_left = n_sweeps; n_out = n_out_;
+		scan = 0; last_n = -1;
+		steps = 0; budget = 4 * len_ + 64; over = 0;
 		st = NEXT;
 	}
 	B200_HD void emit(const SeedOpt &so, int cap, int start)
@@ -194,11 +230,17 @@ struct BwdLane {
 			if (n_out < cap) { Intv v; v.x0 = k0; v.x1 = k1; v.x2 = k2; v.info = (uint64_t)start << 32 | (uint32_t)kend; outp[n_out] = v; }
 			++n_out;
 		}
-		last_start = start; ++nm;
 	}
-	// L must map entry k of the CURRENT sweep: shared for k < quota, the strip itself beyond (see bind())
-	B200_HD void bind(SeedList &L) const { L.spill = const_cast<Q4 *>(strip) + rpos + L.quota; L.sstride = 1; }
-	B200_HD bool advance(const SeedOpt &so, int cap, SeedList &L)
+	// the entry's chain ended after b backward bases
+	B200_HD void finish(const SeedOpt &so, int cap)
+	{
+		if (b > b_prev) { emit(so, cap, x - b); b_prev = b; }
+		cur ^= 1; tr_base = nw_base; tr_n = nw_n; tr_b = b;       // its sizes are what the following entries are compared with
+		++j; st = ENTRY;
+	}
+	// the entry has the occurrences of the last walked entry: it ends where that one ended, unreported
+	B200_HD void merged() { b_prev = tr_b; ++j; st = ENTRY; }
+	B200_HD bool advance(const SeedOpt &so, int cap)
 	{
 		for (;;) {
 			switch (st) {
@@ -207,68 +249,73 @@ struct BwdLane {
 				--sweeps_left;
 				const Q4 h = strip[rpos];
 				++rpos;                                           // rpos -> first entry of the sweep
-				n_list = n_prev = (int)h.x; i = (int)h.y - 1; min_intv = (uint64_t)h.w << 32 | h.z;
-				bind(L);
-				const int ns = n_list < L.quota ? n_list : L.quota;   // stage the head of the list in shared memory
-				for (int k = 0; k < ns; ++k) {
-					const Q4 v = strip[rpos + k];
-					uint32_t *p = L.sh + (size_t)(k * 4) * L.stride;
-					p[0] = v.x; p[L.stride] = v.y; p[2 * L.stride] = v.z; p[3 * L.stride] = v.w;
-				}
-				rpos += n_list;                                   // (entries beyond the quota are read in place through L.spill)
-				nm = 0; last_start = 0;
-				W = 0;
-				for (int k = 0; k < kmax; ++k) W = W << 2 | (uint32_t)((int)h.y + k < len ? q[(int)h.y + k] & 3 : 0);
-				st = ROW;
+				n_list = (int)h.x; x = (int)h.y; min_intv = (uint64_t)h.w << 32 | h.z;
+				if (x < scan) { scan = 0; last_n = -1; }              // (pass 2 visits its starts in the order pass 1 reported the SMEMs)
+				for (; scan < x; ++scan) if (q[scan] > 3) last_n = scan;
+				b_lim = x - 1 - last_n;
+				P = 0;
+				if (kj) for (int t = x - 16; t < x + 16; ++t) P = P << 2 | (uint64_t)(t >= 0 && t < len ? q[t] & 3 : 0);
+				j = 0; b_prev = -1; tr_n = 0;
+				st = ENTRY;
 				break;
 			}
-			case ROW: {
-				const int cc = i < 0 ? -1 : (q[i] < 4 ? (int)q[i] : -1);
-				if (cc < 0) {
-					if (nm == 0 || i + 1 < last_start) { L.get(n_list - 1, k0, k1, k2, kend); emit(so, cap, i + 1); }
-					st = NEXT;
-					break;
+			case ENTRY: {
+				if (j == n_list) { rpos += n_list; st = NEXT; break; }
+				const Q4 v = strip[rpos + n_list - 1 - j];            // longest-forward entry first
+				k0 = (uint64_t)(v.w >> 29 & 1u) << 32 | v.x;
+				k1 = (uint64_t)(v.w >> 30 & 1u) << 32 | v.y;
+				k2 = (uint64_t)(v.w >> 31) << 32 | v.z;
+				kend = (int)(v.w & 0x1fffffffu);
+				b = 0; nw_n = 0;
+				if (b_lim == 0) { finish(so, cap); break; }
+				const int l0 = kend - x;
+				if (l0 < kj) {
+					b = kj - l0 < b_lim ? kj - l0 : b_lim;
+					klen = l0 + b;
+					W = (uint32_t)(P >> (2 * (x + 16 - kend))) & (uint32_t)(((uint64_t)1 << (2 * klen)) - 1);
+					tab = 1;
+				} else {
+					if (same_as_walked(0, k2)) { merged(); break; }
+					note(0, k2);
+					tab = 0; c = q[x - 1];
 				}
-				c = cc; j = 0; n_curr = 0; st = BWD;
-				row_base(cc);
-				break;
-			}
-			case BWD:
-				L.get(n_list - 1 - j, k0, k1, k2, kend);
+				st = STEP;
 				return true;
+			}
 			default:
 				return false;
 			}
 		}
 	}
-	// the entry after the current one in the row being extended (its extension is independent of the current one: reference
-	// src/bwt.c:326-345 walks the row's entries with the same base); false at the end of the row
-	B200_HD bool peek(const SeedList &L, uint64_t &p0, uint64_t &p1, uint64_t &p2, int &pe) const
+	// digest the look-up or the extension; true = the chain's next extension is set up, false = advance() needed
+	B200_HD bool step(const SeedOpt &so, int cap, uint64_t o0, uint64_t o1, uint64_t o2)
 	{
-		if (st != BWD || j + 1 >= n_prev) return false;
-		L.get(n_list - 2 - j, p0, p1, p2, pe);
-		return true;
-	}
-	// digest one backward extension; true = next extension ready, false = advance() needed
-	B200_HD bool step(const SeedOpt &so, int cap, const SeedList &L, uint64_t o0, uint64_t o1, uint64_t o2)
-	{
-		if (o2 < min_intv) {
-			if (n_curr == 0 && (nm == 0 || i + 1 < last_start)) emit(so, cap, i + 1);
-		} else if (n_curr == 0 || o2 != last_x2) {
-			L.set(n_list - 1 - n_curr, o0, o1, o2, kend);
-			++n_curr; last_x2 = o2;
+		if (tab) {
+			tab = 0;
+			if (o2 < min_intv) { b_prev = -1; ++j; st = ENTRY; return false; }     // dies short of kj bases: no report, see above
+			k0 = o0; k1 = o1; k2 = o2;
+		} else {
+			if (o2 < min_intv) { finish(so, cap); return false; }
+			k0 = o0; k1 = o1; k2 = o2; ++b;
+			if (++steps > budget) { over = 1; st = DONE; return false; }
 		}
-		if (++j == n_prev) {
-			if (n_curr == 0) { st = NEXT; return false; }
-			n_prev = n_curr; --i;
-			if (i < 0 || q[i] > 3) { st = ROW; return false; }
-			c = q[i]; j = 0; n_curr = 0;
-			row_base(c);
-		}
-		L.get(n_list - 1 - j, k0, k1, k2, kend);
+		if (same_as_walked(b, k2)) { merged(); return false; }
+		note(b, k2);
+		if (b == b_lim) { finish(so, cap); return false; }
+		c = q[x - b - 1];
 		return true;
 	}
 };
+
+// one trip of a backward lane
+B200_HD void bwd_lane_fetch(const FmView &fm, const BwdLane &ln, uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &blocks)
+{
+	OccRaw rk, rl;
+	int half;
+	fm_step_load(fm, ln.tab != 0, ln.klen, ln.W, ln.k0, ln.k1, ln.k2, 1, rk, rl, half);
+	if (ln.tab) { int tb; ktab_unpack(rk, half, o0, o1, o2, tb); blocks += 1; }
+	else fm_extend_use(fm, ln.k0, ln.k1, ln.k2, 1, ln.c, rk, rl, o0, o1, o2, blocks);
+}
 
 #if defined(__CUDACC__)
 struct SweepArgs {
@@ -322,47 +369,33 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 }
 
 template <int MINB>
-__global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a, int quota)
+__global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a)
 {
-	extern __shared__ uint32_t sweep_sh[];
-	SeedList L;
-	L.sh = sweep_sh + threadIdx.x; L.stride = 128; L.quota = quota; L.spill = nullptr; L.sstride = 1;
+	__shared__ uint32_t traj_sh[2 * BwdLane::TRAJ * 128];
 	BwdLane ln;
 	ln.st = BwdLane::DONE; ln.n_out = 0;
 	int r = -1;
 	bool need = false, drained = false;
 	int64_t blocks = 0;
-	// The entries of a row are independent (reference src/bwt.c:326-345 extends each by the same base), so a lane keeps TWO
-	// extensions in flight: while the sectors of the current entry are digested, those of the following entry of the row are
-	// already being loaded into a second register pair (the kernel's occupancy is set by its shared-memory lists, not by
-	// registers).  ahead: the sectors in (nk, nl) belong to the entry that is now current.
-	OccRaw nk, nl;
-	bool ahead = false;
-	int nhalf = 0, ntl = 0;
 	for (;;) {
 		while (!need && !drained) {
-			if (r >= 0) { a.n_intv[r] = ln.n_out; if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out); }
+			if (r >= 0) {
+				a.n_intv[r] = ln.n_out;
+				if (ln.over) { a.n_sweeps[r] = -1; atomicAdd(a.n_over, 1); }
+				else if (ln.n_out > a.cap) atomicMax(a.worst, ln.n_out);
+			}
 			r = atomicAdd(a.next_read, 1);
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			const int ns = a.n_sweeps[r];
 			if (ns <= 0) { r = -1; continue; }
-			ln.begin(a.fm.kmax, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r]);
-			need = ln.advance(a.so, a.cap, L);
-			ahead = false;
+			ln.begin(a.so, a.fm.kmax, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r], traj_sh + threadIdx.x, 128);
+			need = ln.advance(a.so, a.cap);
 		}
 		if (!__any_sync(0xffffffffu, need)) break;
 		if (need) {
-			OccRaw rk, rl;
-			int half, tl;
-			if (ahead) { rk = nk; rl = nl; half = nhalf; tl = ntl; }
-			else { tl = ln.tab_len(ln.kend); fm_step_load(a.fm, tl != 0, tl, ln.tab_idx(tl), ln.k0, ln.k1, ln.k2, 1, rk, rl, half); }
-			uint64_t p0, p1, p2;
-			int pe;
-			ahead = ln.peek(L, p0, p1, p2, pe);
-			if (ahead) { ntl = ln.tab_len(pe); fm_step_load(a.fm, ntl != 0, ntl, ln.tab_idx(ntl), p0, p1, p2, 1, nk, nl, nhalf); }
 			uint64_t o0, o1, o2;
-			fm_step_use(a.fm, tl != 0, half, ln.k0, ln.k1, ln.k2, 1, ln.c, rk, rl, o0, o1, o2, blocks);
-			if (!ln.step(a.so, a.cap, L, o0, o1, o2)) { need = ln.advance(a.so, a.cap, L); ahead = false; }
+			bwd_lane_fetch(a.fm, ln, o0, o1, o2, blocks);
+			if (!ln.step(a.so, a.cap, o0, o1, o2)) need = ln.advance(a.so, a.cap);
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);

@@ -546,13 +546,12 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	// whose sweep strip overflowed.  B200_SEED_KERNEL=lanes forces the general kernel for every read (parity tests).
 	const bool use_sweeps = !(getenv("B200_SEED_KERNEL") && !strcmp(getenv("B200_SEED_KERNEL"), "lanes"));
 	typedef void (*FwdK)(SweepArgs);
-	typedef void (*BwdK)(SweepArgs, int);
+	typedef void (*BwdK)(SweepArgs);
 	const FwdK fwd1 = fwd_minb >= 16 ? k_sweep_fwd<1, 16> : fwd_minb >= 12 ? k_sweep_fwd<1, 12> : k_sweep_fwd<1, 9>;
 	const FwdK fwd2 = fwd_minb >= 16 ? k_sweep_fwd<2, 16> : fwd_minb >= 12 ? k_sweep_fwd<2, 12> : k_sweep_fwd<2, 9>;
 	const BwdK bwd = bwd_minb >= 12 ? k_sweep_bwd<12> : bwd_minb >= 9 ? k_sweep_bwd<9> : k_sweep_bwd<6>;
 	if (use_sweeps && !bwd_blocks_per_sm) {
-		CK(cudaFuncSetAttribute(bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_bytes));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, bwd, threads, sh_bytes));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, bwd, threads, 0));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fwd_blocks_per_sm, fwd1, threads, 0));
 		if (bwd_blocks_per_sm < 1 || fwd_blocks_per_sm < 1) die("sweep kernels do not fit an SM");
 		if (getenv("B200_DEBUG")) fprintf(stderr, "[seed] sweeps: %d forward, %d backward blocks per SM (quota %d)\n", fwd_blocks_per_sm, bwd_blocks_per_sm, quota);
@@ -574,14 +573,15 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 			const int fpb = std::max(1, (int)(fwd_blocks_per_sm * fill + .5)), bpb = std::max(1, (int)(bwd_blocks_per_sm * fill + .5));
 			const int gf = std::min(n_sm * fpb, grid_for(n, threads)), gb = std::min(n_sm * bpb, grid_for(n, threads));
 			a.next_read = ctr + 3; fwd1<<<gf, threads, 0, e->stream>>>(a);
-			a.next_read = ctr + 4; bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			a.next_read = ctr + 4; bwd<<<gb, threads, 0, e->stream>>>(a);
 			a.next_read = ctr + 5; fwd2<<<gf, threads, 0, e->stream>>>(a);
-			a.next_read = ctr + 6; bwd<<<gb, threads, sh_bytes, e->stream>>>(a, quota);
+			a.next_read = ctr + 6; bwd<<<gb, threads, 0, e->stream>>>(a);
 			CK(cudaGetLastError());
 			e->stats.n_launches += 4;
 			CK(cudaMemcpyAsync(h, ctr, sizeof h, cudaMemcpyDeviceToHost, e->stream));
 			e->sync();
-			if (h[2] > 0) {                     // strip overflow: those reads go through the general state machine
+			if (h[2] > 0) {                     // strip overflow / chain budget: those reads go through the general state machine
+				if (getenv("B200_DEBUG")) fprintf(stderr, "[seed] %d of %d reads redone by the general kernel\n", h[2], n);
 				k_seed_lanes<<<grid, threads, sh_bytes, e->stream>>>(e->fm, so, n, d_off + r0, d_codes, out, cap, quota, spill, n_intv, ctr, ctr + 1,
 					&e->d_cnt->occ_blocks, a.n_sweeps);
 				CK(cudaGetLastError());

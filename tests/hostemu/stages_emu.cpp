@@ -49,6 +49,7 @@ public:
 	FinishOut fin_out;
 	std::vector<SamLine> lines;
 	std::vector<int64_t> dest_off;
+	int64_t plain_blocks = 0, sweep_blocks = 0;                        // occ blocks the sweeps touched or looked up (fm_occ_blocks counts the plain routine)
 };
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int)
@@ -101,7 +102,11 @@ Engine *engine_clone(Engine *base)
 	memset(static_cast<b200_stats_t *>(&e->stats), 0, sizeof(b200_stats_t));
 	return e;
 }
-void engine_destroy(Engine *e) { delete e; }
+void engine_destroy(Engine *e)
+{
+	if (getenv("B200_DEBUG") && e->plain_blocks) fprintf(stderr, "[hostemu] occ blocks: %lld by the reference's loops, %lld touched or looked up by the sweeps\n", (long long)e->plain_blocks, (long long)e->sweep_blocks);
+	delete e;
+}
 Stats &engine_stats(Engine *e) { return e->stats; }
 const char *engine_kind() { return "hostemu"; }
 int engine_device_count() { return 1; }
@@ -212,7 +217,6 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 				const int strip_cap = 3 * len + 8;
 				std::vector<Q4> strip(strip_cap);
 				std::vector<Intv> out3(cap2);
-				std::vector<uint32_t> sh2(4 * quota);
 				int n_out = 0, n_first = 0, n_sw = 0;
 				int64_t blocks3 = 0;
 				for (int pass = 1; pass <= 2 && n_sw >= 0; ++pass) {
@@ -227,20 +231,17 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					n_out = f.n_out; n_sw = f.over ? -1 : f.n_sweeps;
 					if (pass == 1) n_first = n_out;
 					if (n_sw <= 0) continue;
-					SeedList L2; L2.sh = sh2.data(); L2.stride = 1; L2.quota = quota; L2.spill = nullptr; L2.sstride = 1;
 					BwdLane b;
-					b.begin(e->fm.kmax, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out);
-					nd = b.advance(so, cap2, L2);
+					uint32_t traj[2 * BwdLane::TRAJ];
+					b.begin(so, e->fm.kmax, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out, traj, 1);
+					nd = b.advance(so, cap2);
 					while (nd) {
 						uint64_t o0, o1, o2;
-						OccRaw rk, rl;
-						int half;
-						const int tl = b.tab_len(b.kend);
-						fm_step_load(e->fm, tl != 0, tl, b.tab_idx(tl), b.k0, b.k1, b.k2, 1, rk, rl, half);
-						fm_step_use(e->fm, tl != 0, half, b.k0, b.k1, b.k2, 1, b.c, rk, rl, o0, o1, o2, blocks3);
-						if (!b.step(so, cap2, L2, o0, o1, o2)) nd = b.advance(so, cap2, L2);
+						bwd_lane_fetch(e->fm, b, o0, o1, o2, blocks3);
+						if (!b.step(so, cap2, o0, o1, o2)) nd = b.advance(so, cap2);
 					}
 					n_out = b.n_out;
+					if (b.over) n_sw = -1;                    // chain budget exceeded: the read goes to the general kernel instead
 				}
 				bool same3 = n_sw < 0 || n_out == n;      // n_sw < 0: strip overflow, the read goes to the general kernel instead
 				if (same3 && n_sw >= 0) {
@@ -249,8 +250,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 						same3 = out3[i].x0 == out[i].x0 && out3[i].x1 == out[i].x1 && out3[i].x2 == out[i].x2 && out3[i].info == out[i].info;
 				}
 				if (!same3) { fprintf(stderr, "[hostemu] seeding sweeps disagree with fm_collect_intv on read %d (%d vs %d intervals, sweeps %d)\n", r, n_out, n, n_sw); abort(); }
-				// the traffic counter of the sweeps (extensions served by the k-mer tables included) is the plain routine's
-				if (n_sw >= 0 && blocks3 != e->stats.fm_occ_blocks - blocks_before) { fprintf(stderr, "[hostemu] seeding sweeps count %lld occ blocks on read %d, fm_collect_intv %lld\n", (long long)blocks3, r, (long long)(e->stats.fm_occ_blocks - blocks_before)); abort(); }
+				e->sweep_blocks += blocks3; e->plain_blocks += e->stats.fm_occ_blocks - blocks_before;
 			}
 			if (!same) { fprintf(stderr, "[hostemu] seeding state machine disagrees with fm_collect_intv on read %d (%d vs %d intervals)\n", r, ln.n_out, n); abort(); }
 		}

@@ -292,12 +292,15 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
         n_total += len(got)
     assert n_total > 1000
     aligner.lib.b200_free(intv); aligner.lib.b200_free(ioff)
-    # the algorithmic traffic counter (reference-layout occ blocks the REFERENCE's extensions touch) does not depend
-    # on how the kernels got the intervals: table look-ups count the blocks of the extension they stand for
-    # (strip overflows excepted: those reads are counted by the sweep that gave up and again by the general kernel)
+    # occ blocks touched: the general kernel runs the reference's loops (its count is the algorithmic traffic of SURVEY.md 8d); the
+    # sweeps look short patterns up and walk the backward entries as independent chains, which must not cost more than the loops
     if kernel != "sweeps_overflow":
         _occ_blocks[kernel] = _aux_stats(aligner.lib)["fm_occ_blocks"] - blocks0
-        assert _occ_blocks[kernel] > 100000 and len(set(_occ_blocks.values())) == 1, _occ_blocks
+        assert _occ_blocks[kernel] > 100000
+        if "lanes" in _occ_blocks and "sweeps" in _occ_blocks:
+            assert _occ_blocks["sweeps"] < 0.7 * _occ_blocks["lanes"], _occ_blocks
+        if "lanes" in _occ_blocks and "sweeps_no_tables" in _occ_blocks:
+            assert _occ_blocks["sweeps_no_tables"] < 1.02 * _occ_blocks["lanes"], _occ_blocks
     ks = np.concatenate([[1, idxf.primary, idxf.seq_len, 32], rng.integers(1, idxf.seq_len + 1, size=20000)]).astype(np.uint64)
     sa = np.zeros(len(ks), np.uint64)
     aligner.lib.b200_bwt_sa_batch(len(ks), ks.ctypes.data, sa.ctypes.data)

@@ -47,6 +47,8 @@ struct FmView {
 	// length L at entry ktab_off(L) + (pattern as a base-4 number, first base most significant); kmax == 0: none
 	const uint32_t *ktab;
 	int kmax;
+	// the whole suffix array, five bytes per row (fm_sa below), or null: only the reference's samples
+	const uint8_t *sa5;
 };
 
 struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads
@@ -293,25 +295,58 @@ B200_HD uint64_t fm_occ1(const FmView &fm, uint64_t k, int c)
 	return cnt[c];
 }
 
-// SA[k] by LF-walking to a sampled row
+// bwt_invPsi (reference src/bwt.c:53-59): the row of the suffix that starts one base earlier
+B200_HD uint64_t fm_lf(const FmView &fm, uint64_t k)
+{
+	if (k == fm.primary) return 0;
+	// for k != primary the symbol row k - (k > primary) and the row of bwt_occ's count k - (k >= primary) coincide, so one sector gives both
+	const uint64_t kk = k - (k > fm.primary);
+	const OccRaw r = ld_occ(fm, kk >> 6);
+	const int c = sector_symbol(r, kk);
+	uint64_t cnt[4];
+	occ4_sector(r, kk, cnt);
+	return (c == 0 ? fm.L2[0] : c == 1 ? fm.L2[1] : c == 2 ? fm.L2[2] : fm.L2[3]) + (c == 0 ? cnt[0] : c == 1 ? cnt[1] : c == 2 ? cnt[2] : cnt[3]);
+}
+
+/* The whole suffix array in HBM.  bwt_sa (reference src/bwt.c:86-96) walks bwt_invPsi from row k to a sampled row - 31 dependent
+ * random sectors on average with the shipped sampling of 32 - because a host cannot afford 8 bytes per row.  A B200 can afford five
+ * (31 GB for a human-sized reference): the samples are expanded ONCE when the index is uploaded (sa5_expand: from every sampled
+ * row the walk of invPsi visits exactly the unsampled rows up to the next sampled one, each one base earlier in the text), and a
+ * look-up is one random access.  Row 0 keeps the reference's own sa[0]. */
+B200_HD uint64_t sa5_read(const uint8_t *sa5, uint64_t k)
+{
+	const uint64_t o = k * 5;
+	const uint32_t *w = reinterpret_cast<const uint32_t *>(sa5) + (o >> 2);
+	const uint64_t v = (uint64_t)w[1] << 32 | w[0];
+	return v >> ((o & 3) << 3) & 0xffffffffffull;
+}
+B200_HD void sa5_write(uint8_t *sa5, uint64_t k, uint64_t v)
+{
+	uint8_t *p = sa5 + k * 5;
+	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); p[4] = (uint8_t)(v >> 32);
+}
+// the rows between sampled row j * sa_intv and the next sampled row on the walk
+B200_HD void sa5_expand(const FmView &fm, uint64_t j, uint8_t *sa5)
+{
+	const uint64_t mask = (uint64_t)fm.sa_intv - 1;
+	uint64_t row = j * (uint64_t)fm.sa_intv;
+	uint64_t p = j == 0 ? fm.seq_len : fm.sa[j];          // (the reference stores -1 for the row of the empty suffix)
+	sa5_write(sa5, row, p);
+	for (int guard = 0; guard < (1 << 24); ++guard) {      // (the bound only matters for a damaged index whose walk never reaches a sample)
+		if (p == 0) break;                                 // the suffix at the start of the text: the walk is over
+		row = fm_lf(fm, row); --p;
+		if (!(row & mask)) break;
+		sa5_write(sa5, row, p);
+	}
+}
+
+// SA[k]: from the expanded array, else by walking to a sampled row
 B200_HD uint64_t fm_sa(const FmView &fm, uint64_t k, int *steps)
 {
+	if (fm.sa5 && k) { if (steps) *steps = 0; return sa5_read(fm.sa5, k); }
 	uint64_t sa = 0, mask = (uint64_t)fm.sa_intv - 1;
 	int n = 0;
-	while (k & mask) {
-		++sa; ++n;
-		if (k == fm.primary) k = 0;
-		else {
-			// bwt_invPsi (reference src/bwt.c:53-59): for k != primary the symbol row k - (k > primary) and the row of
-			// bwt_occ's count k - (k >= primary) coincide, so one sector gives both
-			const uint64_t kk = k - (k > fm.primary);
-			const OccRaw r = ld_occ(fm, kk >> 6);
-			const int c = sector_symbol(r, kk);
-			uint64_t cnt[4];
-			occ4_sector(r, kk, cnt);
-			k = (c == 0 ? fm.L2[0] : c == 1 ? fm.L2[1] : c == 2 ? fm.L2[2] : fm.L2[3]) + (c == 0 ? cnt[0] : c == 1 ? cnt[1] : c == 2 ? cnt[2] : cnt[3]);
-		}
-	}
+	while (k & mask) { ++sa; ++n; k = fm_lf(fm, k); }
 	if (steps) *steps = n;
 	return sa + fm.sa[k / (uint64_t)fm.sa_intv];
 }

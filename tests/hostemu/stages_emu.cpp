@@ -35,6 +35,7 @@ public:
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
+	std::shared_ptr<std::vector<uint8_t>> sa5;       // the whole suffix array, expanded from the samples like the upload kernel does
 	std::shared_ptr<std::vector<Q4>> ktab;           // k-mer interval tables, built level by level with the routine the upload kernel runs
 	// finish stages
 	std::vector<DReg> xregs;
@@ -66,6 +67,18 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
+	e->fm.sa5 = nullptr;
+	if (!(getenv("B200_SA_FULL") && atoi(getenv("B200_SA_FULL")) == 0)) {
+		e->sa5 = std::make_shared<std::vector<uint8_t>>((size_t)(bwt->seq_len + 1) * 5 + 16);
+		for (uint64_t j = 0; j < (uint64_t)bwt->n_sa; ++j) sa5_expand(e->fm, j, e->sa5->data());
+		// every 61st row (and the rows around the sentinel's) against the reference's walk to a sampled row
+		for (uint64_t k = 1; k <= bwt->seq_len; k += (k + 3 > bwt->primary && k < bwt->primary + 3) ? 1 : 61) {
+			int st;
+			const uint64_t want = fm_sa(e->fm, k, &st);       // (fm.sa5 is still null here: the walk)
+			if (sa5_read(e->sa5->data(), k) != want) { fprintf(stderr, "[hostemu] expanded suffix array differs at row %llu\n", (unsigned long long)k); abort(); }
+		}
+		e->fm.sa5 = e->sa5->data();
+	}
 	{
 		int kmax = ktab_default_kmax(bwt->seq_len);
 		if (getenv("B200_KMER_MAX")) kmax = std::max(0, std::min(16, atoi(getenv("B200_KMER_MAX"))));
@@ -94,7 +107,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->occ = base->occ; e->ktab = base->ktab;
+	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;

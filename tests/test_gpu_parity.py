@@ -264,6 +264,8 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
         monkeypatch.setenv("B200_SEED_STRIP", "40")
     if kernel in ("sweeps_no_tables", "sweeps_tables5"):
         monkeypatch.setenv("B200_KMER_MAX", "0" if kernel == "sweeps_no_tables" else "5")
+        if kernel == "sweeps_no_tables":
+            monkeypatch.setenv("B200_SA_FULL", "0")        # ... and bwt_sa by the walk to a sampled row instead of the expanded array
         aligner = M.Aligner(examples["idx"], device=0, n_threads=8, verbose=1)
     blocks0 = _aux_stats(aligner.lib)["fm_occ_blocks"]
     idxf = OL.IndexFiles(examples["idx"])
@@ -300,7 +302,7 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
         if "lanes" in _occ_blocks and "sweeps" in _occ_blocks:
             assert _occ_blocks["sweeps"] < 0.7 * _occ_blocks["lanes"], _occ_blocks
         if "lanes" in _occ_blocks and "sweeps_no_tables" in _occ_blocks:
-            assert _occ_blocks["sweeps_no_tables"] < 1.02 * _occ_blocks["lanes"], _occ_blocks
+            assert _occ_blocks["sweeps_no_tables"] < 1.1 * _occ_blocks["lanes"], _occ_blocks
     ks = np.concatenate([[1, idxf.primary, idxf.seq_len, 32], rng.integers(1, idxf.seq_len + 1, size=20000)]).astype(np.uint64)
     sa = np.zeros(len(ks), np.uint64)
     aligner.lib.b200_bwt_sa_batch(len(ks), ks.ctypes.data, sa.ctypes.data)

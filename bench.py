@@ -263,8 +263,9 @@ def int32_peak_gops(torch):
     return lib.b200_int32_peak(torch.cuda.current_device())
 
 
-def kernel_table(agg, K, i32_peak, hbm_peak):
-    """per device stage: algorithmic work / CUDA-event kernel time vs the measured peak"""
+def kernel_table(agg, K, i32_peak, hbm_peak, ref_ratio=1.0):
+    """per device stage: algorithmic work / CUDA-event kernel time vs the measured peak.  ref_ratio: occ blocks the REFERENCE's
+    seeding loops touch on these reads / occ blocks the sweep kernels touched or looked up (measured on the isolated chunk)"""
     kern = {}
     if agg["ms_k_extend_dp"] > 0:
         gcups = agg["extend_cells"] / agg["ms_k_extend_dp"] / 1e6
@@ -274,14 +275,21 @@ def kernel_table(agg, K, i32_peak, hbm_peak):
                                "achieved": gcups * 14, "unit": "Gop/s (14 int32 ops per cell)", "peak": i32_peak,
                                "frac": (gcups * 14 / i32_peak) if i32_peak else None}
     if agg["ms_k_smem"] > 0:
-        gbs = 64.0 * agg["fm_occ_blocks"] / agg["ms_k_smem"] / 1e6
-        kern["smem_seeding"] = {"bound": "hbm", "ms_per_step": agg["ms_k_smem"] / K, "bytes_per_step": 64.0 * agg["fm_occ_blocks"] / K,
-                                "achieved": gbs, "unit": "GB/s", "peak": hbm_peak, "frac": gbs / hbm_peak}
+        gbs = 64.0 * agg["fm_occ_blocks"] * ref_ratio / agg["ms_k_smem"] / 1e6
+        kern["smem_seeding"] = {"bound": "hbm", "ms_per_step": agg["ms_k_smem"] / K, "bytes_per_step": 64.0 * agg["fm_occ_blocks"] * ref_ratio / K,
+                                "touched_bytes_per_step": 64.0 * agg["fm_occ_blocks"] / K,
+                                "achieved": gbs, "unit": "GB/s", "peak": hbm_peak, "frac": gbs / hbm_peak,
+                                "bytes_note": "bytes_per_step = ALGORITHMIC traffic (SURVEY.md 8d): 64 B per distinct occ block of the reference layout per bwt_occ4 "
+                                              "of the reference's seeding loops on these reads, counted by running the general kernel (the reference's loops, "
+                                              "B200_SEED_KERNEL=lanes) over the isolated chunk; touched_bytes_per_step = the same unit over what the sweep kernels "
+                                              "actually extended or looked up in the k-mer tables (they skip most of the backward rows)"}
     if agg["ms_k_sa"] > 0:
         b = 64.0 * agg["fm_sa_steps"] + 8.0 * agg["fm_sa_lookups"]
         gbs = b / agg["ms_k_sa"] / 1e6
         kern["sa_lookup"] = {"bound": "hbm", "ms_per_step": agg["ms_k_sa"] / K, "bytes_per_step": b / K, "achieved": gbs, "unit": "GB/s",
-                             "peak": hbm_peak, "frac": gbs / hbm_peak}
+                             "peak": hbm_peak, "frac": gbs / hbm_peak, "lookups_per_step": agg["fm_sa_lookups"] / K,
+                             "bytes_note": "64 B per bwt_invPsi step the kernel walked + 8 B per look-up; with the whole suffix array in HBM "
+                                           "(the default) a look-up walks nothing: one 5-byte read"}
     if agg["ms_k_sw"] > 0:
         gc = agg["sw_cells"] / agg["ms_k_sw"] / 1e6
         kern["ksw_align2"] = {"bound": "int32_issue", "ms_per_step": agg["ms_k_sw"] / K, "cells_per_step": agg["sw_cells"] / K, "gcups": gc,
@@ -566,6 +574,12 @@ def main():
     resident_group(args.warmup + args.steps + 1, 1, ev0, ev1, iso.append)
     os.environ.pop("B200_EXT_RECORD", None)
     st_iso = iso[0]
+    # the algorithmic FM-index traffic of that chunk: the general seeding kernel runs the reference's loops extension for extension
+    iso_ref = []
+    os.environ["B200_SEED_KERNEL"] = "lanes"
+    resident_group(args.warmup + args.steps + 1, 1, ev0, ev1, iso_ref.append)
+    os.environ.pop("B200_SEED_KERNEL", None)
+    ref_ratio = iso_ref[0]["fm_occ_blocks"] / max(1, st_iso["fm_occ_blocks"])
     # kernel-isolated ksw_extend2 as BASELINE configs[1] words it: the exact job list of the chunk, replayed as one batch
     rp_cells, rp_jobs = C.c_int64(), C.c_int64()
     lib.b200_ext_replay(al.opt, C.byref(rp_cells), C.byref(rp_jobs))          # (warm-up)
@@ -596,8 +610,8 @@ def main():
     occ_bytes = int(args.ref_bp)                           # occ sectors: 0.5 byte per BWT symbol, 2 symbols per base
     rnd_peak = lib.b200_hbm_random_sector_peak(torch.cuda.current_device(), max(occ_bytes, 1 << 26))
     K = args.steps
-    kern = kernel_table(agg, K, i32_peak, hbm_peak)
-    kern_iso = kernel_table(st_iso, 1, i32_peak, hbm_peak)
+    kern = kernel_table(agg, K, i32_peak, hbm_peak, ref_ratio)
+    kern_iso = kernel_table(st_iso, 1, i32_peak, hbm_peak, ref_ratio)
     # The chunks in flight share the SMs (B200_TURN=0, the default): the CUDA-event duration of a kernel in the timed region includes
     # the time it spent sharing the device with the kernels of other chunks, so the roofline of the dominant kernel is taken from
     # the pass that runs ONE chunk alone (same process, same inputs, CUDA events on the launching stream); `kernels` keeps the
@@ -613,7 +627,8 @@ def main():
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
-                "traffic": traffic, "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()",
+                "traffic": traffic, "algorithmic_bytes_per_launch": kd.get("bytes_per_step"), "touched_bytes_per_launch": kd.get("touched_bytes_per_step"),
+                "bytes_note": kd.get("bytes_note"), "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()",
                 "random_sector_peak": {"value": rnd_peak, "unit": "GB/s", "table_bytes": occ_bytes,
                                        "frac_of_it": (kd["achieved"] / rnd_peak) if kd["bound"] == "hbm" and rnd_peak else None,
                                        "what": "measured live (b200_hbm_random_sector_peak): independent 256-bit loads of uniformly random 32-byte sectors of a table "

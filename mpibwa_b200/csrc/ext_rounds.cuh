@@ -255,12 +255,16 @@ __device__ __forceinline__ void ext_fill_score_rows(const ExtOpt &eo, uint32_t *
 	}
 }
 
-// Fast path: one job per lane, warps built from the size-sorted order.  The row loop is warp-synchronous: every
-// iteration each live lane computes one row of its own job, then the warp reconverges, so that the per-row
-// prologue/epilogue is issued once per warp-row and only the cell loop runs with per-lane trip counts.
+// Fast path: one job per lane.  The row loop is warp-synchronous: every iteration each live lane computes one row of its own
+// job, then the warp reconverges, so that the per-row prologue/epilogue is issued once per warp-row and only the cell loop runs
+// with per-lane trip counts.  Lanes are PERSISTENT: a job ends where z-drop, an all-zero row or the target's end stop it
+// (src/ksw.c:455-465) - a spurious 19-mer seed of a human-sized index dies after a handful of rows, a true flank runs all of them -
+// so no sort key keeps 32 lanes in step; a lane whose job is over takes the next one of its size class from a counter (the order
+// is largest first), staged and initialised while the others wait, once `refill` lanes of the warp are idle (16: measured best of 1 / 8 / 16 /
+// 32; the chunk's job list as one batch 6.35 -> 5.53 ms against lanes that keep their first job only).
 __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restrict__ pac, const uint8_t *__restrict__ codes,
                                                ExtJob *jobs, const int32_t *__restrict__ order, int n, int qcap, unsigned long long *cells_out,
-                                               unsigned long long *calls_out)
+                                               unsigned long long *calls_out, int *next, int refill)
 {
 	extern __shared__ uint32_t smem[];
 	__shared__ uint32_t sc_lo[5], sc_hi[5];
@@ -271,23 +275,35 @@ __global__ void __launch_bounds__(64) k_ext_dp(ExtOpt eo, const uint8_t *__restr
 	uint8_t *Q = (uint8_t *)(smem + (size_t)wib * per_warp_words + (qcap + 1) * 32) + lane * 4;
 	ext_fill_score_rows(eo, sc_lo, sc_hi);
 	__syncthreads();
-	const int t = blockIdx.x * blockDim.x + threadIdx.x;
 	const int e_del = eo.e_del, e_ins = eo.e_ins, oe_del = eo.o_del + eo.e_del, oe_ins = eo.o_ins + eo.e_ins;
 	long long cells = 0;
 	int calls = 0;
 	ExtJob *jp = nullptr;
 	ExtJob jb;
 	jb.qlen = 0; jb.tlen = 0; jb.h0 = 1; jb.prev = -1; jb.bonus = 0; jb.f0 = 0; jb.fstep = 0; jb.comp = 0; jb.qaddr = 0; jb.qstep = 0; jb.w0 = 0;
-	bool alive = false;
-	if (t < n) { jp = &jobs[order[t]]; jb = *jp; alive = true; }
-	ext_prefetch_target(pac, jb.f0, jb.fstep, jb.tlen, jb.comp, 0, 1);
-	for (int j = 0; j < jb.qlen; ++j) Q[ext_qidx(j)] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+	bool alive = false, drained = false;
 	// per-attempt DP state
-	int aw = jb.w0 > 0 ? jb.w0 : eo.w, attempt = jb.w0 > 0 ? 1 : 0, prev_score = jb.prev;
-	int w = ext_init_row(eo, jb, aw, S);
-	int i = 0, beg = 0, end = jb.qlen, max = jb.h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
-	int64_t f = jb.f0;
-	while (__any_sync(0xffffffffu, alive)) {
+	int aw = eo.w, attempt = 0, prev_score = -1, w = 0;
+	int i = 0, beg = 0, end = 0, max = 0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, max_off = 0;
+	int64_t f = 0;
+	for (;;) {
+		const unsigned idle = __ballot_sync(0xffffffffu, !alive && !drained);
+		if (idle && (__popc(idle) >= refill || !__any_sync(0xffffffffu, alive))) {
+			if (!alive && !drained) {
+				const int t = atomicAdd(next, 1);
+				if (t < n) {
+					jp = &jobs[order[t]]; jb = *jp; alive = true;
+					ext_prefetch_target(pac, jb.f0, jb.fstep, jb.tlen, jb.comp, 0, 1);
+					for (int j = 0; j < jb.qlen; ++j) Q[ext_qidx(j)] = codes[jb.qaddr + (int64_t)jb.qstep * j];
+					aw = jb.w0 > 0 ? jb.w0 : eo.w; attempt = jb.w0 > 0 ? 1 : 0; prev_score = jb.prev;
+					w = ext_init_row(eo, jb, aw, S);
+					i = 0; beg = 0; end = jb.qlen; max = jb.h0; max_i = -1; max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+					f = jb.f0;
+				} else drained = true;
+			}
+			__syncwarp();
+		}
+		if (!__any_sync(0xffffffffu, alive)) break;
 		if (alive) {
 			bool done = i >= jb.tlen;
 			if (!done) {

@@ -874,6 +874,22 @@ __global__ void k_ext_record(int n, const int32_t *__restrict__ active, const Ex
 	if (t < n) rec[t] = jobs[active[t]];
 }
 
+// k_ext_dp over the n jobs of size class c in order[]: a persistent grid (as many blocks as the device can hold at that class's
+// shared-memory footprint) whose lanes take jobs from *next (zeroed by the caller)
+static void launch_ext_dp(Engine *e, cudaStream_t st, const ExtOpt &eo, const uint8_t *pac, const uint8_t *codes, ExtJob *jobs, const int32_t *order,
+                          int n, int c, int qcap, unsigned long long *d_cells, unsigned long long *d_calls, int *next)
+{
+	static const int refill = getenv("B200_EXT_REFILL") ? std::max(1, std::min(32, atoi(getenv("B200_EXT_REFILL")))) : 16;
+	const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
+	const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
+	const size_t smem = per_warp * (threads / 32);
+	int n_sm = 0;
+	CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, e->device));
+	const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / threads, (size_t)(227 * 1024) / (smem + 1024)));
+	const int grid = std::min(grid_for(n, threads), n_sm * per_sm);
+	k_ext_dp<<<grid, threads, smem, st>>>(eo, pac, codes, jobs, order, n, qcap, d_cells, d_calls, next, refill);
+}
+
 static void ext_set_attrs(Engine *e)
 {
 	if (e->ext_attr_set) return;
@@ -991,10 +1007,7 @@ void stage_extend(Engine *e, const ExtOpt &eo, const ExtIn &in)
 				k_ext_dp_warp<<<grid_for(cnt, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
 					d_jobs, d_ord + pos, cnt, qcap, d_cells, d_calls);
 			} else if (c < EXT_N_CLASS - 1) {
-				const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
-				const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-				k_ext_dp<<<grid_for(cnt, threads), threads, per_warp * (threads / 32), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p,
-					d_jobs, d_ord + pos, cnt, qcap, d_cells, d_calls);
+				launch_ext_dp(e, st, eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_jobs, d_ord + pos, cnt, c, qcap, d_cells, d_calls, d_ctr + 9 + c);
 			} else {
 				int64_t stride = ((int64_t)cnt + 31) & ~31ll;
 				int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
@@ -1084,6 +1097,8 @@ double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t 
 	ext_set_attrs(e);
 	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
 	e->zero_counters();
+	int *d_next = e->b_xctr.as<int>(16);
+	CK(cudaMemsetAsync(d_next, 0, 16 * sizeof(int), e->stream));
 	e->sync();
 	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
 	e->tic();
@@ -1100,9 +1115,7 @@ double stage_extend_replay(Engine *e, const ExtOpt &eo, int64_t *cells, int64_t 
 		if (wpb && (n_c < 2048 || c >= EXT_N_CLASS - 3))
 			k_ext_dp_warp<<<grid_for(n_c, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, qcap, d_cells, d_calls);
 		else if (c < EXT_N_CLASS - 1) {
-			const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
-			const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-			k_ext_dp<<<grid_for(n_c, threads), threads, per_warp * (threads / 32), st>>>(eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, qcap, d_cells, d_calls);
+			launch_ext_dp(e, st, eo, e->fm.pac, (const uint8_t *)e->d_codes.p, d_rec, d_ord + pos, n_c, c, qcap, d_cells, d_calls, d_next + c);
 		} else {
 			const int64_t stride = ((int64_t)n_c + 31) & ~31ll;
 			int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (e->max_len + 2));
@@ -1163,6 +1176,8 @@ void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend
 	ext_set_attrs(e);
 	auto warps_for = [](int qcap) { return ext_warp_smem_bytes(4, qcap) <= 200 * 1024 ? 4 : ext_warp_smem_bytes(1, qcap) <= 200 * 1024 ? 1 : 0; };
 	unsigned long long *d_cells = &e->d_cnt->ext_cells, *d_calls = &e->d_cnt->ext_calls;
+	int *d_next = e->b_xctr.as<int>(16);
+	CK(cudaMemsetAsync(d_next, 0, 16 * sizeof(int), e->stream));
 	e->tic();
 	for (int c = 0; c < EXT_N_CLASS; ++c) {
 		const int n = (int)cnt[c];
@@ -1174,9 +1189,7 @@ void stage_extend_bytes(Engine *e, const ExtOpt &eo, int64_t n_jobs, b200_extend
 		if (use_warp)
 			k_ext_dp_warp<<<grid_for(n, wpb), 32 * wpb, ext_warp_smem_bytes(wpb, qcap), e->stream>>>(eo, dt, dq, dj, d_ord + pos[c], n, qcap, d_cells, d_calls);
 		else if (lane_ok) {
-			const int threads = c == EXT_N_CLASS - 2 ? 32 : 64;
-			const size_t per_warp = ((size_t)(qcap + 1) * 32 + (size_t)((qcap + 4) & ~3) * 8) * 4;
-			k_ext_dp<<<grid_for(n, threads), threads, per_warp * (threads / 32), e->stream>>>(eo, dt, dq, dj, d_ord + pos[c], n, qcap, d_cells, d_calls);
+			launch_ext_dp(e, e->stream, eo, dt, dq, dj, d_ord + pos[c], n, c, qcap, d_cells, d_calls, d_next + c);
 		} else {
 			const int64_t stride = ((int64_t)n + 31) & ~31ll;
 			int32_t *d_eh = e->b_eh.as<int32_t>((size_t)stride * 2 * (max_q + 2));

@@ -49,6 +49,8 @@ struct FmView {
 	int kmax;
 	// the whole suffix array, five bytes per row (fm_sa below), or null: only the reference's samples
 	const uint8_t *sa5;
+	// ... and its inverse (the row of the suffix that starts at a text position), same packing, or null
+	const uint8_t *isa5;
 };
 
 struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads
@@ -325,18 +327,20 @@ B200_HD void sa5_write(uint8_t *sa5, uint64_t k, uint64_t v)
 	uint8_t *p = sa5 + k * 5;
 	p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); p[4] = (uint8_t)(v >> 32);
 }
-// the rows between sampled row j * sa_intv and the next sampled row on the walk
-B200_HD void sa5_expand(const FmView &fm, uint64_t j, uint8_t *sa5)
+// the rows between sampled row j * sa_intv and the next sampled row on the walk (isa5: the inverse array as well, or null)
+B200_HD void sa5_expand(const FmView &fm, uint64_t j, uint8_t *sa5, uint8_t *isa5)
 {
 	const uint64_t mask = (uint64_t)fm.sa_intv - 1;
 	uint64_t row = j * (uint64_t)fm.sa_intv;
 	uint64_t p = j == 0 ? fm.seq_len : fm.sa[j];          // (the reference stores -1 for the row of the empty suffix)
 	sa5_write(sa5, row, p);
+	if (isa5 && p <= fm.seq_len) sa5_write(isa5, p, row);
 	for (int guard = 0; guard < (1 << 24); ++guard) {      // (the bound only matters for a damaged index whose walk never reaches a sample)
 		if (p == 0) break;                                 // the suffix at the start of the text: the walk is over
 		row = fm_lf(fm, row); --p;
 		if (!(row & mask)) break;
 		sa5_write(sa5, row, p);
+		if (isa5 && p <= fm.seq_len) sa5_write(isa5, p, row);
 	}
 }
 

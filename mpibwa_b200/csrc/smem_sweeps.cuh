@@ -33,7 +33,7 @@ struct SweepStrip {
 };
 
 struct FwdLane {
-	enum { NEXT, FWD, P3_NEXT, P3, DONE };
+	enum { NEXT, FWD, FWD_JUMP, P3_NEXT, P3, DONE };
 	int len; const uint8_t *q; Intv *outp; Q4 *strip; int strip_cap;
 	int mode;                   // 1: pass-1 sweeps then pass 3; 2: pass-2 sweeps
 	int st, x, sx, i, c;
@@ -42,12 +42,17 @@ struct FwdLane {
 	int n_out, old_n, k2i;
 	// k-mer tables (smem_kernel.cuh): tab != 0 = the pending step is a table look-up of the klen bases packed in W instead of an
 	// extension; 1 = one step of a forward sweep (pattern q[sx .. i]), 2 = the first klen-1 steps of the greedy pass at once
-	int kmax, tab, klen; uint32_t W;
+	//   3 = the first kj bases of a forward sweep at once (its shorter prefixes become IMPLICIT entries of the list: the backward
+	//       chains take them from the tables, see BwdLane); 4 / 5 = the suffix array / inverse suffix array read of a unique walk
+	int kmax, kj, tab, klen; uint32_t W;
+	int n_impl;                 // implicit entries of the current sweep: forward extents 1 .. n_impl
+	int uw_ok, uw_n; uint64_t t1;
 
 	// k_first: first interval of `outp` that pass 2 may re-seed (the greedy seeds of pass 3 come before it and are not candidates)
-	B200_HD void begin(const SeedOpt &so, int kmax_, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
+	B200_HD void begin(const SeedOpt &so, const FmView &fm, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
 	{
-		kmax = kmax_; mode = mode_; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
+		kmax = fm.kmax; kj = fm.kmax < so.min_seed_len ? fm.kmax : so.min_seed_len; mode = mode_;
+		uw_ok = fm.sa5 != nullptr && fm.isa5 != nullptr; uw_n = 0; t1 = 0; n_impl = 0; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
 		n_out = n_out_; old_n = n_out_; k2i = k_first;
 		x = 0; wpos = 0; n_sweeps = 0; over = 0;
 		tab = 0; klen = 0; W = 0;
@@ -72,12 +77,19 @@ struct FwdLane {
 		kend = x_ + 1; min_intv = mi < 1 ? 1 : mi; sx = x_; i = x_ + 1; n = 0;
 		hdr_pos = wpos++;
 		W = q[x_];
-		st = FWD;
+		st = FWD; n_impl = 0;
+		// the first kj bases at once when they are plain bases of the read: one look-up instead of kj - 1 steps
+		if (kj >= 2 && x_ + kj <= len) {
+			uint32_t w = W;
+			int m = 1;
+			for (; m < kj && q[x_ + m] < 4; ++m) w = w << 2 | q[x_ + m];
+			if (m == kj) { W = w; klen = kj; tab = 3; st = FWD_JUMP; }
+		}
 	}
 	B200_HD void end_sweep()      // the interval that could not be extended further closes the list; its end is the next x
 	{
 		push();
-		if (hdr_pos < strip_cap) { Q4 h; h.x = (uint32_t)n; h.y = (uint32_t)sx; h.z = (uint32_t)min_intv; h.w = (uint32_t)(min_intv >> 32); strip[hdr_pos] = h; }
+		if (hdr_pos < strip_cap) { Q4 h; h.x = (uint32_t)n | (uint32_t)n_impl << 16; h.y = (uint32_t)sx; h.z = (uint32_t)min_intv; h.w = (uint32_t)(min_intv >> 32); strip[hdr_pos] = h; }
 		else over = 1;
 		++n_sweeps;
 		x = kend;
@@ -112,6 +124,8 @@ struct FwdLane {
 				if (i < len && q[i] < 4) { want(q[i]); return true; }
 				end_sweep();
 				break;
+			case FWD_JUMP:
+				return true;                                  // (tab == 3: set up by start_sweep)
 			case P3_NEXT: {
 				if (x >= len) { st = DONE; break; }
 				if (q[x] > 3) { ++x; break; }
@@ -138,14 +152,32 @@ struct FwdLane {
 		}
 	}
 	// digest one extension; true = the next extension is already set up, false = go through advance()
-	B200_HD bool step(const SeedOpt &so, int cap, uint64_t o0, uint64_t o1, uint64_t o2)
+	B200_HD bool step(const FmView &fm, const SeedOpt &so, int cap, uint64_t o0, uint64_t o1, uint64_t o2)
 	{
-		if (st == FWD) {
+		if (st == FWD_JUMP) {
+			st = FWD; tab = 0;
+			if (o2 >= min_intv) { k0 = o0; k1 = o1; k2 = o2; i = sx + kj; kend = i; n_impl = kj - 1; }
+			else W = q[sx];                                  // the match ends inside the first kj bases: step through them (i, k* are still the first base's)
+		} else if (tab == 4) {
+			// unique walk: the pattern's single occurrence is at a known place of the text, so the rest of the forward sweep is a
+			// comparison of the read with the reference (its reverse-complement strand read downwards, see fwd_lane_fetch)
+			t1 = o0;
+			int m = 0;
+			while (i + m < len && q[i + m] < 4 && t1 >= (uint64_t)(1 + m) && fm_base(fm.pac, fm.l_pac, (int64_t)(t1 - 1 - m)) == 3 - q[i + m]) ++m;
+			if (m == 0) { tab = 0; end_sweep(); return false; }   // (q[i] is a plain base: the text differs there, or ends)
+			uw_n = m; t1 -= m; tab = 5;
+			return true;
+		} else if (tab == 5) {
+			k1 = o0; i += uw_n; kend = i; tab = 0;
+			end_sweep();                                      // whatever stopped the comparison stops the sweep (src/bwt.c:304-318)
+			return false;
+		} else if (st == FWD) {
 			if (o2 != k2) {
 				if (o2 < min_intv) { end_sweep(); return false; }
 				push();
 			}
 			k0 = o0; k1 = o1; k2 = o2; kend = i + 1; ++i;
+			if (k2 == 1 && min_intv == 1 && uw_ok && i < len && q[i] < 4) { tab = 4; return true; }
 		} else {                                              // P3 (reference src/bwt.c:367-376)
 			if (o2 < (uint64_t)so.max_mem_intv && i - sx >= so.min_seed_len) {
 				if (o2 > 0) emit3(cap, o0, o1, o2, sx, i + 1);
@@ -162,10 +194,20 @@ struct FwdLane {
 // one trip of a forward lane: the pending step's result and the reference's occ-block count for it
 B200_HD void fwd_lane_fetch(const FmView &fm, const FwdLane &ln, uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &blocks)
 {
+	if (ln.tab >= 4) {
+		// Unique walk (tab 4, 5).  Once the interval holds ONE row the rest of a forward sweep asks, base after base, whether the
+		// text goes on like the read; the reference answers each with an occ look-up of the reverse complement's row k1.  With
+		// the whole suffix array and its inverse in HBM the row is turned into its text position once (tab 4), the bases are
+		// compared in the 2-bit text itself (step()), and the position where the comparison stops is turned back into the row
+		// (tab 5) - the forward coordinate k0 does not move while the single occurrence goes on matching.
+		o0 = sa5_read(ln.tab == 4 ? fm.sa5 : fm.isa5, ln.tab == 4 ? ln.k1 : ln.t1); o1 = 0; o2 = 0;
+		blocks += 1;
+		return;
+	}
 	OccRaw rk, rl;
 	int half;
 	fm_step_load(fm, ln.tab != 0, ln.klen, ln.W, ln.k0, ln.k1, ln.k2, 0, rk, rl, half);
-	if (ln.tab == 2) { int tb; ktab_unpack(rk, half, o0, o1, o2, tb); blocks += tb; }
+	if (ln.tab >= 2) { int tb; ktab_unpack(rk, half, o0, o1, o2, tb); blocks += ln.tab == 2 ? tb : 1; }
 	else fm_step_use(fm, ln.tab != 0, half, ln.k0, ln.k1, ln.k2, 0, ln.c, rk, rl, o0, o1, o2, blocks);
 }
 
@@ -188,7 +230,7 @@ struct BwdLane {
 	int len; const uint8_t *q; Intv *outp; const Q4 *strip;
 	int st, c, rpos, sweeps_left;
 	uint64_t k0, k1, k2, min_intv; int kend;      // the entry's interval as extended so far
-	int n_list, j, x, b, b_lim, b_prev, n_out;
+	int n_list, n_impl, j, x, b, b_lim, b_prev, n_out;   // n_impl: implicit entries after the n_list stored ones (forward extents n_impl .. 1)
 	int kmax, kj, tab, klen; uint32_t W;          // tab: the pending step is a look-up of the klen bases in W
 	uint64_t P;                                   // bases q[x-16 .. x+16), two bits each, first base most significant
 	int scan, last_n;                             // ambiguous bases seen so far: last_n = the last one before `scan`
@@ -249,7 +291,7 @@ struct BwdLane {
 				--sweeps_left;
 				const Q4 h = strip[rpos];
 				++rpos;                                           // rpos -> first entry of the sweep
-				n_list = (int)h.x; x = (int)h.y; min_intv = (uint64_t)h.w << 32 | h.z;
+				n_list = (int)(h.x & 0xffffu); n_impl = (int)(h.x >> 16); x = (int)h.y; min_intv = (uint64_t)h.w << 32 | h.z;
 				if (x < scan) { scan = 0; last_n = -1; }              // (pass 2 visits its starts in the order pass 1 reported the SMEMs)
 				for (; scan < x; ++scan) if (q[scan] > 3) last_n = scan;
 				b_lim = x - 1 - last_n;
@@ -260,12 +302,14 @@ struct BwdLane {
 				break;
 			}
 			case ENTRY: {
-				if (j == n_list) { rpos += n_list; st = NEXT; break; }
-				const Q4 v = strip[rpos + n_list - 1 - j];            // longest-forward entry first
-				k0 = (uint64_t)(v.w >> 29 & 1u) << 32 | v.x;
-				k1 = (uint64_t)(v.w >> 30 & 1u) << 32 | v.y;
-				k2 = (uint64_t)(v.w >> 31) << 32 | v.z;
-				kend = (int)(v.w & 0x1fffffffu);
+				if (j == n_list + n_impl || (j >= n_list && b_lim == 0)) { rpos += n_list; st = NEXT; break; }
+				if (j < n_list) {
+					const Q4 v = strip[rpos + n_list - 1 - j];        // longest-forward entry first
+					k0 = (uint64_t)(v.w >> 29 & 1u) << 32 | v.x;
+					k1 = (uint64_t)(v.w >> 30 & 1u) << 32 | v.y;
+					k2 = (uint64_t)(v.w >> 31) << 32 | v.z;
+					kend = (int)(v.w & 0x1fffffffu);
+				} else kend = x + n_impl - (j - n_list);              // an implicit entry: a prefix shorter than kj bases, taken from the tables below
 				b = 0; nw_n = 0;
 				if (b_lim == 0) { finish(so, cap); break; }
 				const int l0 = kend - x;
@@ -352,7 +396,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 			r = atomicAdd(a.next_read, 1);
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			if (MODE == 2 && a.n_sweeps[r] < 0) { r = -1; continue; }       // already handed to the general kernel
-			ln.begin(a.so, a.fm.kmax, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
+			ln.begin(a.so, a.fm, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
 			         a.strips + (int64_t)r * a.strip_cap, a.strip_cap, MODE == 1 ? 0 : a.n_intv[r], MODE == 1 ? 0 : a.n_first[r]);
 			if (MODE == 2 && ln.n_out > a.cap) ln.st = FwdLane::DONE;        // output overflow: the whole batch is rerun anyway
 			need = ln.advance(a.fm, a.so);
@@ -361,7 +405,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 		if (need) {
 			uint64_t o0, o1, o2;
 			fwd_lane_fetch(a.fm, ln, o0, o1, o2, blocks);
-			if (!ln.step(a.so, a.cap, o0, o1, o2)) need = ln.advance(a.fm, a.so);
+			if (!ln.step(a.fm, a.so, a.cap, o0, o1, o2)) need = ln.advance(a.fm, a.so);
 		}
 	}
 	for (int o = 16; o > 0; o >>= 1) blocks += __shfl_down_sync(0xffffffffu, blocks, o);

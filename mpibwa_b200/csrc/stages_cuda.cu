@@ -116,7 +116,7 @@ public:
 	DevBuf b_grow;
 	// finish stages (finish_stage.h): scratch by FinBuf id, the read text, contig names, the log table, the SAM text on the host
 	DevBuf fb[FB_N], d_rtext, d_text;
-	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr, *d_ktab = nullptr, *d_sa5 = nullptr;
+	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr, *d_ktab = nullptr, *d_sa5 = nullptr, *d_isa5 = nullptr;
 	int n_log = 0;
 	PinBuf h_sam, h_sam_off, h_lines, h_dest_off;
 	FinishOut fin_out;
@@ -197,10 +197,10 @@ __global__ void k_ktab_level(FmView fm, int L, Q4 *tab)
 }
 
 // the whole suffix array from its samples (fm_kernels.h), one sampled row per thread
-__global__ void k_sa5_expand(FmView fm, uint64_t n_sa, uint8_t *sa5)
+__global__ void k_sa5_expand(FmView fm, uint64_t n_sa, uint8_t *sa5, uint8_t *isa5)
 {
 	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j < n_sa) sa5_expand(fm, j, sa5);
+	if (j < n_sa) sa5_expand(fm, j, sa5, isa5);
 }
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
@@ -275,23 +275,26 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
-	fm.sa5 = nullptr;
-	if (!(getenv("B200_SA_FULL") && atoi(getenv("B200_SA_FULL")) == 0)) {
-		// the whole suffix array, five bytes per row, expanded from the samples (B200_SA_FULL=0: keep the samples only); never more
-		// than a third of the memory that is free now
+	fm.sa5 = nullptr; fm.isa5 = nullptr;
+	const int sa_full = getenv("B200_SA_FULL") ? atoi(getenv("B200_SA_FULL")) : 2;
+	if (sa_full > 0) {
+		// the whole suffix array and its inverse, five bytes per row / position, expanded from the samples (B200_SA_FULL=0: keep the
+		// samples only, 1: no inverse); the pair never takes more than half of the memory that is free now, the array alone a third
 		size_t free_b = 0, total_b = 0;
 		CK(cudaMemGetInfo(&free_b, &total_b));
 		const size_t bytes = ((size_t)fm.seq_len + 1) * 5 + 16;
-		if (bytes <= free_b / 3 && (fm.seq_len >> 40) == 0 && (uint64_t)bwt->n_sa == (fm.seq_len + fm.sa_intv) / fm.sa_intv) {
+		const bool inverse = sa_full > 1 && 2 * bytes <= free_b / 2;
+		if ((inverse || bytes <= free_b / 3) && (fm.seq_len >> 40) == 0 && (uint64_t)bwt->n_sa == (fm.seq_len + fm.sa_intv) / fm.sa_intv) {
 			const auto t0 = std::chrono::steady_clock::now();
 			CK(cudaMalloc(&e->d_sa5, bytes));
-			k_sa5_expand<<<(unsigned)(((uint64_t)bwt->n_sa + 127) / 128), 128>>>(fm, (uint64_t)bwt->n_sa, (uint8_t *)e->d_sa5);
+			if (inverse) { CK(cudaMalloc(&e->d_isa5, bytes)); CK(cudaMemset(e->d_isa5, 0, bytes)); }
+			k_sa5_expand<<<(unsigned)(((uint64_t)bwt->n_sa + 127) / 128), 128>>>(fm, (uint64_t)bwt->n_sa, (uint8_t *)e->d_sa5, (uint8_t *)e->d_isa5);
 			CK(cudaGetLastError());
 			CK(cudaDeviceSynchronize());
-			fm.sa5 = (const uint8_t *)e->d_sa5;
+			fm.sa5 = (const uint8_t *)e->d_sa5; fm.isa5 = (const uint8_t *)e->d_isa5;
 			if (getenv("B200_DEBUG"))
-				fprintf(stderr, "[mpibwa_b200] whole suffix array: %.2f GB, expanded from the samples in %.0f ms\n", bytes / 1e9,
-				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+				fprintf(stderr, "[mpibwa_b200] whole suffix array%s: %.2f GB, expanded from the samples in %.0f ms\n", inverse ? " and its inverse" : "",
+				        (inverse ? 2 : 1) * bytes / 1e9, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 		}
 	}
 	{	// k-mer interval tables: every pattern of up to kmax bases, built level by level with the seeding kernels' own extension
@@ -376,7 +379,7 @@ Engine *engine_clone(Engine *base)
 	e->owns_index = false;
 	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len; e->d_ctg_alt = base->d_ctg_alt;
 	e->d_ctg_name_off = base->d_ctg_name_off; e->d_ctg_names = base->d_ctg_names; e->d_ctg_anno_off = base->d_ctg_anno_off; e->d_ctg_annos = base->d_ctg_annos;
-	e->d_logtab = base->d_logtab; e->n_log = base->n_log; e->d_ktab = base->d_ktab; e->d_sa5 = base->d_sa5;
+	e->d_logtab = base->d_logtab; e->n_log = base->n_log; e->d_ktab = base->d_ktab; e->d_sa5 = base->d_sa5; e->d_isa5 = base->d_isa5;
 	e->bwt_bytes = base->bwt_bytes;
 	e->fm = base->fm;
 	engine_set_l2_window(e);
@@ -395,7 +398,7 @@ void engine_destroy(Engine *e)
 	e->h_sam.release(); e->h_sam_off.release(); e->h_lines.release(); e->h_dest_off.release();
 	if (e->owns_index) {
 		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
-		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab); cudaFree(e->d_ktab); cudaFree(e->d_sa5);
+		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab); cudaFree(e->d_ktab); cudaFree(e->d_sa5); cudaFree(e->d_isa5);
 	}
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_sync);
@@ -573,8 +576,8 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 	const bool use_sweeps = !(getenv("B200_SEED_KERNEL") && !strcmp(getenv("B200_SEED_KERNEL"), "lanes"));
 	typedef void (*FwdK)(SweepArgs);
 	typedef void (*BwdK)(SweepArgs);
-	const FwdK fwd1 = fwd_minb >= 16 ? k_sweep_fwd<1, 16> : fwd_minb >= 12 ? k_sweep_fwd<1, 12> : k_sweep_fwd<1, 9>;
-	const FwdK fwd2 = fwd_minb >= 16 ? k_sweep_fwd<2, 16> : fwd_minb >= 12 ? k_sweep_fwd<2, 12> : k_sweep_fwd<2, 9>;
+	const FwdK fwd1 = fwd_minb >= 12 ? k_sweep_fwd<1, 12> : fwd_minb >= 9 ? k_sweep_fwd<1, 9> : fwd_minb >= 8 ? k_sweep_fwd<1, 8> : k_sweep_fwd<1, 6>;
+	const FwdK fwd2 = fwd_minb >= 12 ? k_sweep_fwd<2, 12> : fwd_minb >= 9 ? k_sweep_fwd<2, 9> : fwd_minb >= 8 ? k_sweep_fwd<2, 8> : k_sweep_fwd<2, 6>;
 	const BwdK bwd = bwd_minb >= 12 ? k_sweep_bwd<12> : bwd_minb >= 9 ? k_sweep_bwd<9> : k_sweep_bwd<6>;
 	if (use_sweeps && !bwd_blocks_per_sm) {
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bwd_blocks_per_sm, bwd, threads, 0));

@@ -35,6 +35,7 @@ public:
 	std::vector<int32_t> l_rep;
 	std::vector<uint8_t> ctg_alt;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
+	std::shared_ptr<std::vector<uint8_t>> isa5;
 	std::shared_ptr<std::vector<uint8_t>> sa5;       // the whole suffix array, expanded from the samples like the upload kernel does
 	std::shared_ptr<std::vector<Q4>> ktab;           // k-mer interval tables, built level by level with the routine the upload kernel runs
 	// finish stages
@@ -67,10 +68,12 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
-	e->fm.sa5 = nullptr;
-	if (!(getenv("B200_SA_FULL") && atoi(getenv("B200_SA_FULL")) == 0)) {
+	e->fm.sa5 = nullptr; e->fm.isa5 = nullptr;
+	const int sa_full = getenv("B200_SA_FULL") ? atoi(getenv("B200_SA_FULL")) : 2;
+	if (sa_full > 0) {
 		e->sa5 = std::make_shared<std::vector<uint8_t>>((size_t)(bwt->seq_len + 1) * 5 + 16);
-		for (uint64_t j = 0; j < (uint64_t)bwt->n_sa; ++j) sa5_expand(e->fm, j, e->sa5->data());
+		if (sa_full > 1) e->isa5 = std::make_shared<std::vector<uint8_t>>((size_t)(bwt->seq_len + 1) * 5 + 16);
+		for (uint64_t j = 0; j < (uint64_t)bwt->n_sa; ++j) sa5_expand(e->fm, j, e->sa5->data(), e->isa5 ? e->isa5->data() : nullptr);
 		// every 61st row (and the rows around the sentinel's) against the reference's walk to a sampled row
 		for (uint64_t k = 1; k <= bwt->seq_len; k += (k + 3 > bwt->primary && k < bwt->primary + 3) ? 1 : 61) {
 			int st;
@@ -78,6 +81,11 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 			if (sa5_read(e->sa5->data(), k) != want) { fprintf(stderr, "[hostemu] expanded suffix array differs at row %llu\n", (unsigned long long)k); abort(); }
 		}
 		e->fm.sa5 = e->sa5->data();
+		if (e->isa5) {
+			for (uint64_t k = 1; k <= bwt->seq_len; k += 61)
+				if (sa5_read(e->isa5->data(), sa5_read(e->sa5->data(), k)) != k) { fprintf(stderr, "[hostemu] inverse suffix array differs at row %llu\n", (unsigned long long)k); abort(); }
+			e->fm.isa5 = e->isa5->data();
+		}
 	}
 	{
 		int kmax = ktab_default_kmax(bwt->seq_len);
@@ -107,7 +115,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5;
+	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5; e->isa5 = base->isa5;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;
@@ -234,12 +242,12 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 				int64_t blocks3 = 0;
 				for (int pass = 1; pass <= 2 && n_sw >= 0; ++pass) {
 					FwdLane f;
-					f.begin(so, e->fm.kmax, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
+					f.begin(so, e->fm, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
 					bool nd = f.advance(e->fm, so);
 					while (nd) {
 						uint64_t o0, o1, o2;
 						fwd_lane_fetch(e->fm, f, o0, o1, o2, blocks3);
-						if (!f.step(so, cap2, o0, o1, o2)) nd = f.advance(e->fm, so);
+						if (!f.step(e->fm, so, cap2, o0, o1, o2)) nd = f.advance(e->fm, so);
 					}
 					n_out = f.n_out; n_sw = f.over ? -1 : f.n_sweeps;
 					if (pass == 1) n_first = n_out;

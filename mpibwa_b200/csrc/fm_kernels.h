@@ -51,6 +51,9 @@ struct FmView {
 	const uint8_t *sa5;
 	// ... and its inverse (the row of the suffix that starts at a text position), same packing, or null
 	const uint8_t *isa5;
+	// which patterns of bloom_k bases the text holds at all (word 2i) and which it holds more than once (word 2i + 1): two blocked
+	// Bloom filters (one 64-bit word per pattern, four bits) interleaved, or null
+	const uint64_t *bloom; uint64_t bloom_mask; int bloom_k;
 };
 
 struct SeedOpt {                // the subset of mem_opt_t the seeding stage reads
@@ -344,6 +347,35 @@ B200_HD void sa5_expand(const FmView &fm, uint64_t j, uint8_t *sa5, uint8_t *isa
 	}
 }
 
+/* A seed shorter than min_seed_len is never kept (reference src/bwamem.c:130), and most entries of a backward sweep end one or two
+ * bases short of it.  Whether the min_seed_len-base window that ends where an entry ends occurs in the text AT ALL is one random
+ * 8-byte read of a Bloom filter over the text's bloom_k-mers (11 bits per text position, four hash bits inside one word; built
+ * when the index is uploaded): "absent" is certain, so the entry can be dropped without walking it; "maybe" walks it as before.
+ * The re-seeding pass (src/bwamem.c:135-147) only keeps intervals of MORE occurrences than the SMEM it splits (min_intv >= 2), so
+ * it asks a second filter that holds the windows inserted more than once (bloom_insert: the word's previous value says whether all
+ * of the pattern's bits were there already - by an earlier occurrence or by chance, never the other way round). */
+B200_HD uint64_t bloom_mix(uint64_t v)
+{
+	v += 0x9e3779b97f4a7c15ull; v = (v ^ (v >> 30)) * 0xbf58476d1ce4e5b9ull; v = (v ^ (v >> 27)) * 0x94d049bb133111ebull;
+	return v ^ (v >> 31);
+}
+B200_HD uint64_t bloom_bits(uint64_t h) { return (uint64_t)1 << (h >> 40 & 63) | (uint64_t)1 << (h >> 46 & 63) | (uint64_t)1 << (h >> 52 & 63) | (uint64_t)1 << (h >> 58); }
+// the filter word and bits of the K bases that start at text position p (forward strand followed by its reverse complement)
+B200_HD void bloom_of_text(const uint8_t *pac, int64_t l_pac, int64_t p, int K, uint64_t mask, uint64_t &word, uint64_t &bits);
+// host-side insertion (tests/hostemu); the device does the same with atomicOr's return value
+inline void bloom_insert(uint64_t *bloom, uint64_t word, uint64_t bits)
+{
+	const uint64_t old = bloom[2 * word];
+	bloom[2 * word] = old | bits;
+	if ((old & bits) == bits) bloom[2 * word + 1] |= bits;
+}
+inline uint64_t bloom_words_for(uint64_t seq_len)
+{
+	uint64_t n = 1024;
+	while (n * 64 < seq_len * 11) n <<= 1;
+	return n;
+}
+
 // SA[k]: from the expanded array, else by walking to a sampled row
 B200_HD uint64_t fm_sa(const FmView &fm, uint64_t k, int *steps)
 {
@@ -368,6 +400,20 @@ B200_HD int fm_pos2rid(const FmView &fm, int64_t pos_f)
 		} else right = mid;
 	}
 	return mid;
+}
+
+B200_HD void bloom_of_text(const uint8_t *pac, int64_t l_pac, int64_t p, int K, uint64_t mask, uint64_t &word, uint64_t &bits)
+{
+	uint64_t v = 0;
+	for (int t = 0; t < K; ++t) {
+		const int64_t a = p + t;
+		int c;
+		if (a < l_pac) c = pac[a >> 2] >> ((~a & 3) << 1) & 3;
+		else { const int64_t f = (l_pac << 1) - 1 - a; c = 3 - (pac[f >> 2] >> ((~f & 3) << 1) & 3); }
+		v = v << 2 | (uint64_t)c;
+	}
+	const uint64_t h = bloom_mix(v);
+	word = h & mask; bits = bloom_bits(h);
 }
 
 B200_HD int64_t fm_depos(const FmView &fm, int64_t pos, int *is_rev)

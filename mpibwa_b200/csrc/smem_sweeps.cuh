@@ -231,8 +231,9 @@ struct BwdLane {
 	int st, c, rpos, sweeps_left;
 	uint64_t k0, k1, k2, min_intv; int kend;      // the entry's interval as extended so far
 	int n_list, n_impl, j, x, b, b_lim, b_prev, n_out;   // n_impl: implicit entries after the n_list stored ones (forward extents n_impl .. 1)
-	int kmax, kj, tab, klen; uint32_t W;          // tab: the pending step is a look-up of the klen bases in W
-	uint64_t P;                                   // bases q[x-16 .. x+16), two bits each, first base most significant
+	int kmax, kj, tab, klen; uint32_t W;          // tab == 1: the pending step is a look-up of the klen bases in W; 2: a Bloom filter word
+	uint64_t PH, PL;                              // bases q[x-32 .. x) and q[x .. x+32), two bits each, first base most significant
+	int bk; uint64_t bv;                          // Bloom filter over the text's bk-mers (0: none); bv = hash of the window being asked for
 	int scan, last_n;                             // ambiguous bases seen so far: last_n = the last one before `scan`
 	// The reference merges entries whose sizes coincide in a row; independent chains walk such entries separately.  That is a few
 	// steps per entry on ordinary reads, but entries that survive TOGETHER for many bases (a read whose flank matches another copy
@@ -257,10 +258,10 @@ struct BwdLane {
 		if (off - nw_base == nw_n && nw_n < TRAJ) { tr[((cur ^ 1) * TRAJ + nw_n) * tr_stride] = size < 0xffffffffu ? (uint32_t)size : 0xffffffffu; ++nw_n; }
 	}
 
-	B200_HD void begin(const SeedOpt &so, int kmax_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_, uint32_t *tr_, int tr_stride_)
+	B200_HD void begin(const SeedOpt &so, int kmax_, int bk_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_, uint32_t *tr_, int tr_stride_)
 	{
 		tr = tr_; tr_stride = tr_stride_; cur = 0; tr_n = 0; tr_base = 0; tr_b = 0; nw_n = 0; nw_base = 0;
-		kmax = kmax_; kj = kmax_ < so.min_seed_len ? kmax_ : so.min_seed_len; tab = 0; klen = 0; W = 0; P = 0;
+		kmax = kmax_; kj = kmax_ < so.min_seed_len ? kmax_ : so.min_seed_len; tab = 0; klen = 0; W = 0; PH = PL = 0; bk = bk_; bv = 0;
 		len = len_; q = q_; outp = outp_; strip = strip_; rpos = 0; sweeps_left = n_sweeps; n_out = n_out_;
 		scan = 0; last_n = -1;
 		steps = 0; budget = 4 * len_ + 64; over = 0;
@@ -295,8 +296,13 @@ struct BwdLane {
 				if (x < scan) { scan = 0; last_n = -1; }              // (pass 2 visits its starts in the order pass 1 reported the SMEMs)
 				for (; scan < x; ++scan) if (q[scan] > 3) last_n = scan;
 				b_lim = x - 1 - last_n;
-				P = 0;
-				if (kj) for (int t = x - 16; t < x + 16; ++t) P = P << 2 | (uint64_t)(t >= 0 && t < len ? q[t] & 3 : 0);
+				PH = PL = 0;
+				if (kj || bk) {
+					const int span = bk > kj ? bk : kj;               // (no window asked for below reaches further from x than this)
+					for (int t = x - span; t < x; ++t) PH = PH << 2 | (uint64_t)(t >= 0 ? q[t] & 3 : 0);
+					for (int t = x; t < x + span; ++t) PL = PL << 2 | (uint64_t)(t < len ? q[t] & 3 : 0);
+					PL <<= 2 * (32 - span);
+				}
 				j = 0; b_prev = -1; tr_n = 0;
 				st = ENTRY;
 				break;
@@ -313,17 +319,16 @@ struct BwdLane {
 				b = 0; nw_n = 0;
 				if (b_lim == 0) { finish(so, cap); break; }
 				const int l0 = kend - x;
-				if (l0 < kj) {
-					b = kj - l0 < b_lim ? kj - l0 : b_lim;
-					klen = l0 + b;
-					W = (uint32_t)(P >> (2 * (x + 16 - kend))) & (uint32_t)(((uint64_t)1 << (2 * klen)) - 1);
-					tab = 1;
-				} else {
-					if (same_as_walked(0, k2)) { merged(); break; }
-					note(0, k2);
-					tab = 0; c = q[x - 1];
+				if (bk && l0 < bk) {
+					// can the entry grow to bk (<= min_seed_len) bases at all?  Not if the read's start or an ambiguous base is nearer
+					// than that, and not if the text does not hold the bk-base window that ends where the entry ends (min_intv >= 2,
+					// the re-seeding pass: does not hold it more than once)
+					if (bk - l0 > b_lim) { b_prev = -1; ++j; break; }
+					bv = bloom_mix(window(kend, bk));
+					tab = 2; st = STEP;
+					return true;
 				}
-				st = STEP;
+				if (!start_chain()) break;
 				return true;
 			}
 			default:
@@ -331,9 +336,41 @@ struct BwdLane {
 			}
 		}
 	}
+	// the bases q[end - L .. end) as a number (first base most significant), end in (x, x + 32], L <= 32 bases of which at most 32 before x
+	B200_HD uint64_t window(int end, int L) const
+	{
+		const int l0 = end - x, nh = L - l0;
+		const uint64_t lo = PL >> (2 * (32 - l0));
+		const uint64_t hi = nh <= 0 ? 0 : nh >= 32 ? PH : PH & (((uint64_t)1 << (2 * nh)) - 1);
+		return (nh > 0 ? hi << (2 * l0) : 0) | (nh >= 0 ? lo : lo >> (2 * -nh));
+	}
+	// first step of the entry's chain: the kj-base look-up or, for an entry that is longer already, its first extension;
+	// false = the entry was merged into the last walked one
+	B200_HD bool start_chain()
+	{
+		const int l0 = kend - x;
+		if (l0 < kj) {
+			b = kj - l0 < b_lim ? kj - l0 : b_lim;
+			klen = l0 + b;
+			W = (uint32_t)window(kend, klen);
+			tab = 1;
+		} else {
+			if (same_as_walked(0, k2)) { merged(); return false; }
+			note(0, k2);
+			tab = 0; c = q[x - 1];
+		}
+		st = STEP;
+		return true;
+	}
 	// digest the look-up or the extension; true = the chain's next extension is set up, false = advance() needed
 	B200_HD bool step(const SeedOpt &so, int cap, uint64_t o0, uint64_t o1, uint64_t o2)
 	{
+		if (tab == 2) {
+			tab = 0;
+			const uint64_t m = bloom_bits(bv);
+			if ((o0 & m) != m) { b_prev = -1; ++j; st = ENTRY; return false; }     // certainly absent: cannot reach min_seed_len bases
+			return start_chain();
+		}
 		if (tab) {
 			tab = 0;
 			if (o2 < min_intv) { b_prev = -1; ++j; st = ENTRY; return false; }     // dies short of kj bases: no report, see above
@@ -354,6 +391,16 @@ struct BwdLane {
 // one trip of a backward lane
 B200_HD void bwd_lane_fetch(const FmView &fm, const BwdLane &ln, uint64_t &o0, uint64_t &o1, uint64_t &o2, int64_t &blocks)
 {
+	if (ln.tab == 2) {
+#if defined(__CUDA_ARCH__)
+		o0 = __ldg(fm.bloom + 2 * (ln.bv & fm.bloom_mask) + (ln.min_intv >= 2 ? 1 : 0));
+#else
+		o0 = fm.bloom[2 * (ln.bv & fm.bloom_mask) + (ln.min_intv >= 2 ? 1 : 0)];
+#endif
+		o1 = o2 = 0;
+		blocks += 1;
+		return;
+	}
 	OccRaw rk, rl;
 	int half;
 	fm_step_load(fm, ln.tab != 0, ln.klen, ln.W, ln.k0, ln.k1, ln.k2, 1, rk, rl, half);
@@ -432,7 +479,7 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a)
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			const int ns = a.n_sweeps[r];
 			if (ns <= 0) { r = -1; continue; }
-			ln.begin(a.so, a.fm.kmax, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r], traj_sh + threadIdx.x, 128);
+			ln.begin(a.so, a.fm.kmax, a.fm.bloom && a.so.min_seed_len >= a.fm.bloom_k ? a.fm.bloom_k : 0, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r], traj_sh + threadIdx.x, 128);
 			need = ln.advance(a.so, a.cap);
 		}
 		if (!__any_sync(0xffffffffu, need)) break;

@@ -116,7 +116,7 @@ public:
 	DevBuf b_grow;
 	// finish stages (finish_stage.h): scratch by FinBuf id, the read text, contig names, the log table, the SAM text on the host
 	DevBuf fb[FB_N], d_rtext, d_text;
-	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr, *d_ktab = nullptr, *d_sa5 = nullptr, *d_isa5 = nullptr;
+	void *d_ctg_name_off = nullptr, *d_ctg_names = nullptr, *d_ctg_anno_off = nullptr, *d_ctg_annos = nullptr, *d_logtab = nullptr, *d_ktab = nullptr, *d_sa5 = nullptr, *d_isa5 = nullptr, *d_bloom = nullptr;
 	int n_log = 0;
 	PinBuf h_sam, h_sam_off, h_lines, h_dest_off;
 	FinishOut fin_out;
@@ -201,6 +201,17 @@ __global__ void k_sa5_expand(FmView fm, uint64_t n_sa, uint8_t *sa5, uint8_t *is
 {
 	const uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (j < n_sa) sa5_expand(fm, j, sa5, isa5);
+}
+
+// Bloom filter over the text's K-mers (fm_kernels.h), one text position per thread
+__global__ void k_bloom_build(const uint8_t *__restrict__ pac, int64_t l_pac, int64_t n_pos, int K, uint64_t mask, unsigned long long *bloom)
+{
+	const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (p >= n_pos) return;
+	uint64_t word, bits;
+	bloom_of_text(pac, l_pac, p, K, mask, word, bits);
+	const unsigned long long old = atomicOr(bloom + 2 * word, (unsigned long long)bits);
+	if ((old & bits) == bits) atomicOr(bloom + 2 * word + 1, (unsigned long long)bits);     // seen before (or looks like it): "more than once"
 }
 
 Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac, int device)
@@ -297,6 +308,27 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 				        (inverse ? 2 : 1) * bytes / 1e9, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 		}
 	}
+	fm.bloom = nullptr; fm.bloom_mask = 0; fm.bloom_k = 0;
+	if (!(getenv("B200_BLOOM") && atoi(getenv("B200_BLOOM")) == 0) && (int64_t)fm.seq_len > 64) {
+		// Bloom filter over the text's 19-mers (the default min_seed_len; used whenever the caller's is at least that)
+		const int K = 19;
+		const uint64_t n_words = bloom_words_for(fm.seq_len);
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		if (n_words * 16 <= free_b / 4) {
+			const auto t0 = std::chrono::steady_clock::now();
+			CK(cudaMalloc(&e->d_bloom, n_words * 16));
+			CK(cudaMemset(e->d_bloom, 0, n_words * 16));
+			const int64_t n_pos = (int64_t)fm.seq_len - K + 1;
+			k_bloom_build<<<(unsigned)((n_pos + 255) / 256), 256>>>(fm.pac, fm.l_pac, n_pos, K, n_words - 1, (unsigned long long *)e->d_bloom);
+			CK(cudaGetLastError());
+			CK(cudaDeviceSynchronize());
+			fm.bloom = (const uint64_t *)e->d_bloom; fm.bloom_mask = n_words - 1; fm.bloom_k = K;
+			if (getenv("B200_DEBUG"))
+				fprintf(stderr, "[mpibwa_b200] Bloom filters over the text's %d-mers (present / more than once): %.2f GB, built in %.0f ms\n", K, n_words * 16 / 1e9,
+				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		}
+	}
 	{	// k-mer interval tables: every pattern of up to kmax bases, built level by level with the seeding kernels' own extension
 		// (B200_KMER_MAX: depth override, 0 = none; never more than half of the memory that is free now)
 		int kmax = ktab_default_kmax(fm.seq_len);
@@ -379,7 +411,7 @@ Engine *engine_clone(Engine *base)
 	e->owns_index = false;
 	e->d_bwt = base->d_bwt; e->d_sa = base->d_sa; e->d_pac = base->d_pac; e->d_ctg_off = base->d_ctg_off; e->d_ctg_len = base->d_ctg_len; e->d_ctg_alt = base->d_ctg_alt;
 	e->d_ctg_name_off = base->d_ctg_name_off; e->d_ctg_names = base->d_ctg_names; e->d_ctg_anno_off = base->d_ctg_anno_off; e->d_ctg_annos = base->d_ctg_annos;
-	e->d_logtab = base->d_logtab; e->n_log = base->n_log; e->d_ktab = base->d_ktab; e->d_sa5 = base->d_sa5; e->d_isa5 = base->d_isa5;
+	e->d_logtab = base->d_logtab; e->n_log = base->n_log; e->d_ktab = base->d_ktab; e->d_sa5 = base->d_sa5; e->d_isa5 = base->d_isa5; e->d_bloom = base->d_bloom;
 	e->bwt_bytes = base->bwt_bytes;
 	e->fm = base->fm;
 	engine_set_l2_window(e);
@@ -398,7 +430,7 @@ void engine_destroy(Engine *e)
 	e->h_sam.release(); e->h_sam_off.release(); e->h_lines.release(); e->h_dest_off.release();
 	if (e->owns_index) {
 		cudaFree(e->d_bwt); cudaFree(e->d_sa); cudaFree(e->d_pac); cudaFree(e->d_ctg_off); cudaFree(e->d_ctg_len); cudaFree(e->d_ctg_alt);
-		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab); cudaFree(e->d_ktab); cudaFree(e->d_sa5); cudaFree(e->d_isa5);
+		cudaFree(e->d_ctg_name_off); cudaFree(e->d_ctg_names); cudaFree(e->d_ctg_anno_off); cudaFree(e->d_ctg_annos); cudaFree(e->d_logtab); cudaFree(e->d_ktab); cudaFree(e->d_sa5); cudaFree(e->d_isa5); cudaFree(e->d_bloom);
 	}
 	cudaFree(e->d_cnt);
 	cudaEventDestroy(e->ev0); cudaEventDestroy(e->ev1); cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_sync);

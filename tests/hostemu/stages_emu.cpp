@@ -36,6 +36,7 @@ public:
 	std::vector<uint8_t> ctg_alt;
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
 	std::shared_ptr<std::vector<uint8_t>> isa5;
+	std::shared_ptr<std::vector<uint64_t>> bloom;
 	std::shared_ptr<std::vector<uint8_t>> sa5;       // the whole suffix array, expanded from the samples like the upload kernel does
 	std::shared_ptr<std::vector<Q4>> ktab;           // k-mer interval tables, built level by level with the routine the upload kernel runs
 	// finish stages
@@ -68,6 +69,18 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
 	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
+	e->fm.bloom = nullptr; e->fm.bloom_mask = 0; e->fm.bloom_k = 0;
+	if (!(getenv("B200_BLOOM") && atoi(getenv("B200_BLOOM")) == 0) && (int64_t)bwt->seq_len > 64) {
+		const int K = 19;
+		const uint64_t n_words = bloom_words_for(bwt->seq_len);
+		e->bloom = std::make_shared<std::vector<uint64_t>>(2 * n_words, 0);
+		for (int64_t p = 0; p + K <= (int64_t)bwt->seq_len; ++p) {
+			uint64_t word, bits;
+			bloom_of_text(pac, bns->l_pac, p, K, n_words - 1, word, bits);
+			bloom_insert(e->bloom->data(), word, bits);
+		}
+		e->fm.bloom = e->bloom->data(); e->fm.bloom_mask = n_words - 1; e->fm.bloom_k = K;
+	}
 	e->fm.sa5 = nullptr; e->fm.isa5 = nullptr;
 	const int sa_full = getenv("B200_SA_FULL") ? atoi(getenv("B200_SA_FULL")) : 2;
 	if (sa_full > 0) {
@@ -115,7 +128,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5; e->isa5 = base->isa5;
+	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5; e->isa5 = base->isa5; e->bloom = base->bloom;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;
@@ -254,7 +267,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					if (n_sw <= 0) continue;
 					BwdLane b;
 					uint32_t traj[2 * BwdLane::TRAJ];
-					b.begin(so, e->fm.kmax, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out, traj, 1);
+					b.begin(so, e->fm.kmax, e->fm.bloom && so.min_seed_len >= e->fm.bloom_k ? e->fm.bloom_k : 0, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out, traj, 1);
 					nd = b.advance(so, cap2);
 					while (nd) {
 						uint64_t o0, o1, o2;

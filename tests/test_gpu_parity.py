@@ -266,6 +266,8 @@ def test_seeding_and_sa_vs_oracle(aligner, orc, examples, kernel, monkeypatch):
         monkeypatch.setenv("B200_KMER_MAX", "0" if kernel == "sweeps_no_tables" else "5")
         if kernel == "sweeps_no_tables":
             monkeypatch.setenv("B200_SA_FULL", "0")        # ... and bwt_sa by the walk to a sampled row instead of the expanded array
+        else:
+            monkeypatch.setenv("B200_BLOOM", "0")          # ... and no Bloom filter in front of the backward chains
         aligner = M.Aligner(examples["idx"], device=0, n_threads=8, verbose=1)
     blocks0 = _aux_stats(aligner.lib)["fm_occ_blocks"]
     idxf = OL.IndexFiles(examples["idx"])

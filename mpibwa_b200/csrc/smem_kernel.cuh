@@ -171,6 +171,141 @@ B200_HD void fm_step_use(const FmView &fm, bool tab, int half, uint64_t x0, uint
 	fm_extend_use(fm, x0, x1, x2, is_back, c, rk, rl, o0, o1, o2, n_blocks);
 }
 
+/* ---------------------------------------------------------------- packed reads
+ * The sweeps ask for WINDOWS of a read (the bases of a table look-up, of a Bloom filter word, of a comparison with the text).
+ * Gathering them byte by byte is a loop only the asking lane runs while its warp waits; from a 2-bit copy of the read a window is
+ * two loads and a shift.  One chunk-wide pass (k_pack_reads) packs every read: 32 bases per 64-bit word, first base most
+ * significant, an ambiguous base stored as 0 and flagged in the mask word that follows (bit 31 - (t & 31) of its low half);
+ * `stride` word pairs per read, the pairs past the read's end are zero. */
+struct PackedRead {
+	const uint64_t *w; int n_words;          // word pair i: w[2 * i] bases, w[2 * i + 1] mask
+	B200_HD uint64_t bases_at(int i) const { return i >= 0 && i < n_words ? w[2 * i] : 0; }
+	B200_HD uint64_t mask_at(int i) const { return i >= 0 && i < n_words ? w[2 * i + 1] : 0; }
+	// the L <= 32 bases from position s on (positions outside the read give 0), right-aligned
+	B200_HD uint64_t window(int s, int L) const
+	{
+		const int i = s >> 5, o = s & 31;
+		const uint64_t hi = bases_at(i), lo = bases_at(i + 1);
+		const uint64_t v = o ? hi << (2 * o) | lo >> (64 - 2 * o) : hi;
+		return v >> (64 - 2 * L);
+	}
+	// ambiguity flags of the 32 positions from s on, position s in bit 31
+	B200_HD uint32_t flags(int s) const
+	{
+		const int i = s >> 5, o = s & 31;
+		const uint32_t hi = (uint32_t)mask_at(i), lo = (uint32_t)mask_at(i + 1);
+		return o ? hi << o | lo >> (32 - o) : hi;
+	}
+	// number of plain bases from s on, at most L <= 32 (the caller bounds L by the read's end)
+	B200_HD int plain_run(int s, int L) const
+	{
+		const uint32_t f = flags(s) & (L >= 32 ? 0xffffffffu : ~(0xffffffffu >> L));
+#if defined(__CUDA_ARCH__)
+		const int n = f ? __clz((int)f) : 32;
+#else
+		const int n = f ? __builtin_clz(f) : 32;
+#endif
+		return n < L ? n : L;
+	}
+	// position of the first ambiguous base at or after s, or `end`
+	B200_HD int next_flag_from(int s, int end) const
+	{
+		for (int p = s; p < end; p += 32) {
+			const int n = plain_run(p, end - p < 32 ? end - p : 32);
+			if (n < 32 || p + n >= end) return p + n < end ? p + n : end;
+		}
+		return end;
+	}
+	// position of the last ambiguous base before x, or -1
+	B200_HD int last_flag_before(int x) const
+	{
+		for (int i = (x - 1) >> 5; i >= 0; --i) {
+			uint32_t f = (uint32_t)mask_at(i);
+			if (i == (x - 1) >> 5 && ((x - 1) & 31) != 31) f &= ~(0xffffffffu >> (((x - 1) & 31) + 1));
+			if (f) {
+#if defined(__CUDA_ARCH__)
+				return (i << 5) + 31 - (__ffs((int)f) - 1);
+#else
+				return (i << 5) + 31 - __builtin_ctz(f);
+#endif
+			}
+		}
+		return -1;
+	}
+};
+// word pair `i` of a read's packed copy from its byte codes (0-3 plain, > 3 ambiguous)
+B200_HD void pack_read_word(const uint8_t *q, int len, int i, uint64_t &bases, uint64_t &mask)
+{
+	bases = 0; mask = 0;
+	for (int t = 0; t < 32; ++t) {
+		const int p = (i << 5) + t;
+		const int c = p < len ? q[p] : 0;
+		bases = bases << 2 | (uint64_t)(c > 3 ? 0 : c);
+		mask = mask << 1 | (uint64_t)(p < len && c > 3 ? 1 : 0);
+	}
+}
+B200_HD int packed_words_for(int max_len) { return (max_len + 31) / 32 + 1; }
+
+// 32 bases of the 2-bit text from forward position f on (f >= 0; bytes past the array's end must be readable: it is padded), left-aligned
+B200_HD uint64_t pac_window32(const uint8_t *pac, int64_t f)
+{
+	const uint8_t *p = pac + (f >> 2);
+	uint64_t v = 0;
+	for (int k = 0; k < 8; ++k) v = v << 8 | p[k];
+	const int o = (int)(f & 3);
+	return o ? v << (2 * o) | (uint64_t)p[8] >> (8 - 2 * o) : v;
+}
+// the bases of a 64-bit word (32 of them) in reverse order
+B200_HD uint64_t rev_bases32(uint64_t v)
+{
+#if defined(__CUDA_ARCH__)
+	v = __brevll(v);
+#else
+	v = (v >> 32) | (v << 32);
+	v = (v & 0xffff0000ffff0000ull) >> 16 | (v & 0x0000ffff0000ffffull) << 16;
+	v = (v & 0xff00ff00ff00ff00ull) >> 8 | (v & 0x00ff00ff00ff00ffull) << 8;
+	v = (v & 0xf0f0f0f0f0f0f0f0ull) >> 4 | (v & 0x0f0f0f0f0f0f0f0full) << 4;
+	v = (v & 0xccccccccccccccccull) >> 2 | (v & 0x3333333333333333ull) << 2;
+	v = (v & 0xaaaaaaaaaaaaaaaaull) >> 1 | (v & 0x5555555555555555ull) << 1;
+#endif
+	return (v & 0xaaaaaaaaaaaaaaaaull) >> 1 | (v & 0x5555555555555555ull) << 1;     // (bits reversed: put each base's two bits back in order)
+}
+// How far does the text go on like the read?  The read's bases from position i on (pr, at most n of them, all plain) against
+// 3 - T[p], 3 - T[p - 1], ... - the reverse-complement strand of the text read downwards from p (see the unique walk in
+// smem_sweeps.cuh) - 32 bases per round; returns the number of bases that agree (at most n, at most p + 1).
+B200_HD int text_match_down(const uint8_t *pac, int64_t l_pac, int64_t p, const PackedRead &pr, int i, int n)
+{
+	int m = 0;
+	while (m < n && p >= 0) {
+		int avail;               // text bases this round can compare, at most 32
+		uint64_t t;
+		if (p >= l_pac) {        // 3 - T[p - u] = pac[f + u], f = 2 l_pac - 1 - p: the forward strand read upwards
+			const int64_t f = (l_pac << 1) - 1 - p;
+			avail = l_pac - f < 32 ? (int)(l_pac - f) : 32;
+			t = pac_window32(pac, f);
+		} else {                 // 3 - pac[p - u]: the forward strand read downwards, complemented
+			avail = p + 1 < 32 ? (int)(p + 1) : 32;
+			const int64_t s = p - 31;
+			t = s >= 0 ? ~rev_bases32(pac_window32(pac, s)) : ~rev_bases32(pac_window32(pac, 0) >> (2 * (int)-s));
+		}
+		int want = n - m < 32 ? n - m : 32;
+		if (avail < want) want = avail;
+		const uint64_t r = pr.window(i + m, 32) << 0;
+		const uint64_t x = (r ^ (t >> 0)) & (want >= 32 ? ~0ull : ~(~0ull >> (2 * want)));
+		// r is right-aligned for L = 32 (a whole word), t left-aligned: both hold their first base in the top two bits
+		int eq;
+#if defined(__CUDA_ARCH__)
+		eq = x ? __clzll((long long)x) >> 1 : want;
+#else
+		eq = x ? __builtin_clzll(x) >> 1 : want;
+#endif
+		if (eq > want) eq = want;
+		m += eq; p -= eq;
+		if (eq < want) break;                  // (a round cut short by the strand boundary goes on across it)
+	}
+	return m;
+}
+
 // The interval list of one lane.  Entry k < quota lives in shared memory (sh[(k*4 + word) * stride]), the rest in the
 // lane's global strip (spill[(k - quota) * sstride]).  Values up to 2^33-1, end positions up to 2^29-1.
 struct SeedList {

@@ -34,7 +34,7 @@ struct SweepStrip {
 
 struct FwdLane {
 	enum { NEXT, FWD, FWD_JUMP, P3_NEXT, P3, DONE };
-	int len; const uint8_t *q; Intv *outp; Q4 *strip; int strip_cap;
+	int len; const uint8_t *q; PackedRead pr; Intv *outp; Q4 *strip; int strip_cap;
 	int mode;                   // 1: pass-1 sweeps then pass 3; 2: pass-2 sweeps
 	int st, x, sx, i, c;
 	uint64_t k0, k1, k2, min_intv; int kend;
@@ -49,8 +49,9 @@ struct FwdLane {
 	int uw_ok, uw_n; uint64_t t1;
 
 	// k_first: first interval of `outp` that pass 2 may re-seed (the greedy seeds of pass 3 come before it and are not candidates)
-	B200_HD void begin(const SeedOpt &so, const FmView &fm, int mode_, int len_, const uint8_t *q_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
+	B200_HD void begin(const SeedOpt &so, const FmView &fm, int mode_, int len_, const uint8_t *q_, const PackedRead &pr_, Intv *outp_, Q4 *strip_, int strip_cap_, int n_out_, int k_first)
 	{
+		pr = pr_;
 		kmax = fm.kmax; kj = fm.kmax < so.min_seed_len ? fm.kmax : so.min_seed_len; mode = mode_;
 		uw_ok = fm.sa5 != nullptr && fm.isa5 != nullptr; uw_n = 0; t1 = 0; n_impl = 0; len = len_; q = q_; outp = outp_; strip = strip_; strip_cap = strip_cap_;
 		n_out = n_out_; old_n = n_out_; k2i = k_first;
@@ -79,12 +80,7 @@ struct FwdLane {
 		W = q[x_];
 		st = FWD; n_impl = 0;
 		// the first kj bases at once when they are plain bases of the read: one look-up instead of kj - 1 steps
-		if (kj >= 2 && x_ + kj <= len) {
-			uint32_t w = W;
-			int m = 1;
-			for (; m < kj && q[x_ + m] < 4; ++m) w = w << 2 | q[x_ + m];
-			if (m == kj) { W = w; klen = kj; tab = 3; st = FWD_JUMP; }
-		}
+		if (kj >= 2 && x_ + kj <= len && pr.plain_run(x_, kj) == kj) { W = (uint32_t)pr.window(x_, kj); klen = kj; tab = 3; st = FWD_JUMP; }
 	}
 	B200_HD void end_sweep()      // the interval that could not be extended further closes the list; its end is the next x
 	{
@@ -133,12 +129,9 @@ struct FwdLane {
 				sx = x; i = x + 1; st = P3;
 				// no seed can be reported before the pattern has min_seed_len + 1 bases (src/bwt.c:369): the run of plain bases at sx,
 				// up to min(kmax, min_seed_len) of them, is ONE table look-up instead of an extension per base
-				int run = kmax < so.min_seed_len ? kmax : so.min_seed_len;
-				if (run > len - sx) run = len - sx;
-				W = q[x];
-				int m = 1;
-				for (; m < run && q[sx + m] < 4; ++m) W = W << 2 | q[sx + m];
-				if (m >= 2) { klen = m; i = sx + m - 1; tab = 2; c = 3 - q[i]; return true; }
+				const int run = kj < len - sx ? kj : len - sx;
+				const int m = run >= 2 ? pr.plain_run(sx, run) : 0;
+				if (m >= 2) { W = (uint32_t)pr.window(sx, m); klen = m; i = sx + m - 1; tab = 2; c = 3 - q[i]; return true; }
 				break;
 			}
 			case P3:
@@ -162,8 +155,7 @@ struct FwdLane {
 			// unique walk: the pattern's single occurrence is at a known place of the text, so the rest of the forward sweep is a
 			// comparison of the read with the reference (its reverse-complement strand read downwards, see fwd_lane_fetch)
 			t1 = o0;
-			int m = 0;
-			while (i + m < len && q[i + m] < 4 && t1 >= (uint64_t)(1 + m) && fm_base(fm.pac, fm.l_pac, (int64_t)(t1 - 1 - m)) == 3 - q[i + m]) ++m;
+			const int m = t1 >= 1 ? text_match_down(fm.pac, fm.l_pac, (int64_t)t1 - 1, pr, i, pr.next_flag_from(i, len) - i) : 0;
 			if (m == 0) { tab = 0; end_sweep(); return false; }   // (q[i] is a plain base: the text differs there, or ends)
 			uw_n = m; t1 -= m; tab = 5;
 			return true;
@@ -227,14 +219,13 @@ B200_HD void fwd_lane_fetch(const FmView &fm, const FwdLane &ln, uint64_t &o0, u
 // one look-up per entry plus the few extensions past kj bases, instead of the whole triangle of rows.
 struct BwdLane {
 	enum { NEXT, ENTRY, STEP, DONE };
-	int len; const uint8_t *q; Intv *outp; const Q4 *strip;
+	int len; const uint8_t *q; PackedRead pr; Intv *outp; const Q4 *strip;
 	int st, c, rpos, sweeps_left;
 	uint64_t k0, k1, k2, min_intv; int kend;      // the entry's interval as extended so far
 	int n_list, n_impl, j, x, b, b_lim, b_prev, n_out;   // n_impl: implicit entries after the n_list stored ones (forward extents n_impl .. 1)
 	int kmax, kj, tab, klen; uint32_t W;          // tab == 1: the pending step is a look-up of the klen bases in W; 2: a Bloom filter word
 	uint64_t PH, PL;                              // bases q[x-32 .. x) and q[x .. x+32), two bits each, first base most significant
 	int bk; uint64_t bv;                          // Bloom filter over the text's bk-mers (0: none); bv = hash of the window being asked for
-	int scan, last_n;                             // ambiguous bases seen so far: last_n = the last one before `scan`
 	// The reference merges entries whose sizes coincide in a row; independent chains walk such entries separately.  That is a few
 	// steps per entry on ordinary reads, but entries that survive TOGETHER for many bases (a read whose flank matches another copy
 	// of a repeat) would multiply the reference's work: a read that needs more than `budget` extensions in one kernel is handed to
@@ -258,12 +249,12 @@ struct BwdLane {
 		if (off - nw_base == nw_n && nw_n < TRAJ) { tr[((cur ^ 1) * TRAJ + nw_n) * tr_stride] = size < 0xffffffffu ? (uint32_t)size : 0xffffffffu; ++nw_n; }
 	}
 
-	B200_HD void begin(const SeedOpt &so, int kmax_, int bk_, int len_, const uint8_t *q_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_, uint32_t *tr_, int tr_stride_)
+	B200_HD void begin(const SeedOpt &so, int kmax_, int bk_, int len_, const uint8_t *q_, const PackedRead &pr_, Intv *outp_, const Q4 *strip_, int n_sweeps, int n_out_, uint32_t *tr_, int tr_stride_)
 	{
+		pr = pr_;
 		tr = tr_; tr_stride = tr_stride_; cur = 0; tr_n = 0; tr_base = 0; tr_b = 0; nw_n = 0; nw_base = 0;
 		kmax = kmax_; kj = kmax_ < so.min_seed_len ? kmax_ : so.min_seed_len; tab = 0; klen = 0; W = 0; PH = PL = 0; bk = bk_; bv = 0;
 		len = len_; q = q_; outp = outp_; strip = strip_; rpos = 0; sweeps_left = n_sweeps; n_out = n_out_;
-		scan = 0; last_n = -1;
 		steps = 0; budget = 4 * len_ + 64; over = 0;
 		st = NEXT;
 	}
@@ -293,15 +284,12 @@ struct BwdLane {
 				const Q4 h = strip[rpos];
 				++rpos;                                           // rpos -> first entry of the sweep
 				n_list = (int)(h.x & 0xffffu); n_impl = (int)(h.x >> 16); x = (int)h.y; min_intv = (uint64_t)h.w << 32 | h.z;
-				if (x < scan) { scan = 0; last_n = -1; }              // (pass 2 visits its starts in the order pass 1 reported the SMEMs)
-				for (; scan < x; ++scan) if (q[scan] > 3) last_n = scan;
-				b_lim = x - 1 - last_n;
+				b_lim = x - 1 - pr.last_flag_before(x);
 				PH = PL = 0;
 				if (kj || bk) {
 					const int span = bk > kj ? bk : kj;               // (no window asked for below reaches further from x than this)
-					for (int t = x - span; t < x; ++t) PH = PH << 2 | (uint64_t)(t >= 0 ? q[t] & 3 : 0);
-					for (int t = x; t < x + span; ++t) PL = PL << 2 | (uint64_t)(t < len ? q[t] & 3 : 0);
-					PL <<= 2 * (32 - span);
+					PH = pr.window(x - span, span);
+					PL = pr.window(x, span) << (2 * (32 - span));
 				}
 				j = 0; b_prev = -1; tr_n = 0;
 				st = ENTRY;
@@ -413,6 +401,7 @@ struct SweepArgs {
 	FmView fm; SeedOpt so;
 	int n_reads; const int64_t *off; const uint8_t *codes;
 	Intv *out; int cap;
+	const uint64_t *pk; int pk_stride;  // packed copy of read r (smem_kernel.cuh PackedRead): pk_stride word pairs at pk + 2 * r * pk_stride
 	Q4 *strips; int strip_cap;      // strip of read r at strips + r * strip_cap
 	int32_t *n_intv;                // running count of reported intervals per read (may exceed cap: overflow)
 	int32_t *n_first;               // number of pass-3 seeds at the head of a read's output (pass 2 skips them)
@@ -425,6 +414,17 @@ struct SweepArgs {
 
 // MINB: resident blocks per SM the kernel is compiled for (the register budget follows: 9 -> 56 registers, 12 -> 40, 16 -> 32; what
 // does not fit spills to thread-local memory - the cold part of the lane state - in exchange for more extensions in flight per SM)
+// the packed copies of the reads (PackedRead), one word pair per thread
+__global__ void k_pack_reads(int n_reads, const int64_t *__restrict__ off, const uint8_t *__restrict__ codes, int stride, uint64_t *pk)
+{
+	const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= (int64_t)n_reads * stride) return;
+	const int r = (int)(t / stride), i = (int)(t % stride);
+	uint64_t b, m;
+	pack_read_word(codes + off[r], (int)(off[r + 1] - off[r]), i, b, m);
+	pk[2 * t] = b; pk[2 * t + 1] = m;
+}
+
 template <int MODE, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 {
@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_fwd(SweepArgs a)
 			r = atomicAdd(a.next_read, 1);
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			if (MODE == 2 && a.n_sweeps[r] < 0) { r = -1; continue; }       // already handed to the general kernel
-			ln.begin(a.so, a.fm, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap,
+			const PackedRead pr = { a.pk + (int64_t)r * a.pk_stride * 2, a.pk_stride };
+			ln.begin(a.so, a.fm, MODE, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], pr, a.out + (int64_t)r * a.cap,
 			         a.strips + (int64_t)r * a.strip_cap, a.strip_cap, MODE == 1 ? 0 : a.n_intv[r], MODE == 1 ? 0 : a.n_first[r]);
 			if (MODE == 2 && ln.n_out > a.cap) ln.st = FwdLane::DONE;        // output overflow: the whole batch is rerun anyway
 			need = ln.advance(a.fm, a.so);
@@ -479,7 +480,8 @@ __global__ void __launch_bounds__(128, MINB) k_sweep_bwd(SweepArgs a)
 			if (r >= a.n_reads) { r = -1; drained = true; break; }
 			const int ns = a.n_sweeps[r];
 			if (ns <= 0) { r = -1; continue; }
-			ln.begin(a.so, a.fm.kmax, a.fm.bloom && a.so.min_seed_len >= a.fm.bloom_k ? a.fm.bloom_k : 0, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r], traj_sh + threadIdx.x, 128);
+			const PackedRead pr = { a.pk + (int64_t)r * a.pk_stride * 2, a.pk_stride };
+			ln.begin(a.so, a.fm.kmax, a.fm.bloom && a.so.min_seed_len >= a.fm.bloom_k ? a.fm.bloom_k : 0, (int)(a.off[r + 1] - a.off[r]), a.codes + a.off[r], pr, a.out + (int64_t)r * a.cap, a.strips + (int64_t)r * a.strip_cap, ns, a.n_intv[r], traj_sh + threadIdx.x, 128);
 			need = ln.advance(a.so, a.cap);
 		}
 		if (!__any_sync(0xffffffffu, need)) break;

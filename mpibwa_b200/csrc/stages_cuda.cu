@@ -105,7 +105,7 @@ public:
 	std::vector<int64_t> h_off;
 	DevBuf d_off, d_codes;
 	// scratch
-	DevBuf b_strips, b_nfirst, b_nsweeps;
+	DevBuf b_strips, b_nfirst, b_nsweeps, b_pk;
 	DevBuf b_chscr, b_chnodes, b_chnc, b_chns, b_chcoff, b_chsoff;
 	DevBuf b_xrec; int64_t n_rec = 0;      // B200_EXT_RECORD: every ksw_extend2 job of the last stage_extend call (for the one-batch replay)
 	DevBuf b_intv, b_scr, b_nintv, b_ioff, b_civ, b_slots, b_soff, b_seeds, b_lrep, b_seedoff, b_cub, b_wide;
@@ -626,6 +626,11 @@ static int64_t run_collect(Engine *e, const SeedOpt &so, int r0, int r1, const i
 			SweepArgs a;
 			a.fm = e->fm; a.so = so; a.n_reads = n; a.off = d_off + r0; a.codes = d_codes; a.out = out; a.cap = cap;
 			a.strips = e->b_strips.as<Q4>((size_t)n * strip_cap + 1); a.strip_cap = strip_cap;
+			a.pk_stride = packed_words_for(max_len);
+			uint64_t *pk = e->b_pk.as<uint64_t>((size_t)n * a.pk_stride * 2 + 2);
+			a.pk = pk;
+			k_pack_reads<<<grid_for((int64_t)n * a.pk_stride, 256), 256, 0, e->stream>>>(n, d_off + r0, d_codes, a.pk_stride, pk);
+			e->stats.n_launches += 1;
 			a.n_intv = n_intv; a.n_first = e->b_nfirst.as<int32_t>(n + 1); a.n_sweeps = e->b_nsweeps.as<int32_t>(n + 1);
 			a.worst = ctr + 1; a.n_over = ctr + 2; a.occ_blocks = &e->d_cnt->occ_blocks;
 			// B200_SEED_FILL < 1: the persistent sweeps take only that share of the blocks an SM could hold, leaving registers and
@@ -1888,6 +1893,11 @@ void stage_fetch_sam(Engine *e, const FinishArgs &a, SamChunk &out)
 {
 	CK(cudaSetDevice(e->device));
 	const FinishOut fo = e->fin_out;
+	if (getenv("B200_DEBUG")) {          // device memory at the end of a chunk: the index, its tables and every slot's buffers are allocated by now
+		size_t free_b = 0, total_b = 0;
+		CK(cudaMemGetInfo(&free_b, &total_b));
+		fprintf(stderr, "[mem] %.1f of %.1f GB of device memory in use\n", (total_b - free_b) / 1e9, total_b / 1e9);
+	}
 	// the text and (on request) the per-read offsets come back in page-locked memory
 	const double t0 = fin_clock_ms();
 	const bool routed = fo.routed != nullptr;

@@ -37,6 +37,7 @@ public:
 	std::shared_ptr<std::vector<uint32_t>> occ;      // occ sectors built from the reference layout (shared by clones)
 	std::shared_ptr<std::vector<uint8_t>> isa5;
 	std::shared_ptr<std::vector<uint64_t>> bloom;
+	std::shared_ptr<std::vector<uint8_t>> pac_padded;   // the 2-bit text with the slack the 9-byte window loads may read past its end
 	std::shared_ptr<std::vector<uint8_t>> sa5;       // the whole suffix array, expanded from the samples like the upload kernel does
 	std::shared_ptr<std::vector<Q4>> ktab;           // k-mer interval tables, built level by level with the routine the upload kernel runs
 	// finish stages
@@ -68,7 +69,9 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	e->fm.occ = e->occ->data(); e->fm.sa = bwt->sa; e->fm.primary = bwt->primary;
 	for (int i = 0; i < 5; ++i) e->fm.L2[i] = bwt->L2[i];
 	e->fm.seq_len = bwt->seq_len; e->fm.sa_intv = bwt->sa_intv;
-	e->fm.pac = pac; e->fm.l_pac = bns->l_pac;
+	e->pac_padded = std::make_shared<std::vector<uint8_t>>((size_t)(bns->l_pac / 4 + 1) + 16, 0);
+	memcpy(e->pac_padded->data(), pac, (size_t)(bns->l_pac / 4 + 1));
+	e->fm.pac = e->pac_padded->data(); e->fm.l_pac = bns->l_pac;
 	e->fm.bloom = nullptr; e->fm.bloom_mask = 0; e->fm.bloom_k = 0;
 	if (!(getenv("B200_BLOOM") && atoi(getenv("B200_BLOOM")) == 0) && (int64_t)bwt->seq_len > 64) {
 		const int K = 19;
@@ -128,7 +131,7 @@ Engine *engine_clone(Engine *base)
 {
 	Engine *e = new Engine();
 	e->fm = base->fm;
-	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5; e->isa5 = base->isa5; e->bloom = base->bloom;
+	e->occ = base->occ; e->ktab = base->ktab; e->sa5 = base->sa5; e->isa5 = base->isa5; e->bloom = base->bloom; e->pac_padded = base->pac_padded;
 	e->ctg_off = base->ctg_off; e->ctg_len = base->ctg_len; e->ctg_alt = base->ctg_alt;
 	e->fm.ctg_off = e->ctg_off.data(); e->fm.ctg_len = e->ctg_len.data();
 	e->ctg_name_off = base->ctg_name_off; e->ctg_anno_off = base->ctg_anno_off; e->ctg_names = base->ctg_names; e->ctg_annos = base->ctg_annos;
@@ -253,9 +256,13 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 				std::vector<Intv> out3(cap2);
 				int n_out = 0, n_first = 0, n_sw = 0;
 				int64_t blocks3 = 0;
+				const int pk_words = packed_words_for(len);
+				std::vector<uint64_t> pk(2 * pk_words);
+				for (int w = 0; w < pk_words; ++w) pack_read_word(codes + off[r], len, w, pk[2 * w], pk[2 * w + 1]);
+				const PackedRead pr = { pk.data(), pk_words };
 				for (int pass = 1; pass <= 2 && n_sw >= 0; ++pass) {
 					FwdLane f;
-					f.begin(so, e->fm, pass, len, codes + off[r], out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
+					f.begin(so, e->fm, pass, len, codes + off[r], pr, out3.data(), strip.data(), strip_cap, n_out, pass == 1 ? 0 : n_first);
 					bool nd = f.advance(e->fm, so);
 					while (nd) {
 						uint64_t o0, o1, o2;
@@ -267,7 +274,7 @@ void stage_collect_intv(Engine *e, const SeedOpt &so, int n_reads, const int64_t
 					if (n_sw <= 0) continue;
 					BwdLane b;
 					uint32_t traj[2 * BwdLane::TRAJ];
-					b.begin(so, e->fm.kmax, e->fm.bloom && so.min_seed_len >= e->fm.bloom_k ? e->fm.bloom_k : 0, len, codes + off[r], out3.data(), strip.data(), n_sw, n_out, traj, 1);
+					b.begin(so, e->fm.kmax, e->fm.bloom && so.min_seed_len >= e->fm.bloom_k ? e->fm.bloom_k : 0, len, codes + off[r], pr, out3.data(), strip.data(), n_sw, n_out, traj, 1);
 					nd = b.advance(so, cap2);
 					while (nd) {
 						uint64_t o0, o1, o2;
@@ -693,5 +700,91 @@ extern "C" int64_t b200_emu_pack_selftest(uint32_t seed)
 			bad += a != v[k][0] || b != v[k][1] || c != v[k][2] || e != end[k];
 		}
 	}
+	return bad;
+}
+
+// the derived index structures of round 2 (k-mer interval tables, whole suffix array and inverse, Bloom filters), built by the
+// routines the upload kernels run, against the plain FM-index routines: returns the number of disagreements
+extern "C" int64_t b200_emu_index_tables_selftest(const bwaidx_t *idx, uint32_t seed, int64_t *n_checked, double *bloom_fp_rate)
+{
+	using namespace b200;
+	Engine *e = engine_create(idx->bwt, idx->bns, idx->pac, 0);
+	const FmView &fm = e->fm;
+	uint64_t x = seed * 0x9e3779b97f4a7c15ull + 1;
+	auto rnd = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+	int64_t bad = 0, n = 0;
+	auto interval_of = [&](const int *pat, int L, Intv &ik) {      // forward extensions from the first base, like a forward sweep
+		fm_set_intv(fm, pat[0], ik);
+		for (int t = 1; t < L; ++t) { Intv ok[4]; fm_extend(fm, ik, ok, 0, nullptr); ik = ok[3 - pat[t]]; }
+	};
+	// 1. tables: random patterns of every length, half of them taken from the text so that long ones occur
+	for (int L = 1; L <= fm.kmax; ++L)
+		for (int t = 0; t < 400; ++t) {
+			int pat[32] = { 0 };
+			const int64_t p = (int64_t)(rnd() % (fm.seq_len - 40));
+			for (int k = 0; k < L; ++k) pat[k] = (t & 1) ? fm_base(fm.pac, fm.l_pac, p + k) : (int)(rnd() & 3);
+			uint32_t w = 0;
+			for (int k = 0; k < L; ++k) w = w << 2 | (uint32_t)pat[k];
+			Intv ik;
+			interval_of(pat, L, ik);
+			int half, tb;
+			const uint32_t *sec = ktab_sector(fm, L, w, half);
+			OccRaw r;
+			for (int k = 0; k < 8; ++k) r.w[k] = sec[k];
+			uint64_t t0, t1, t2;
+			ktab_unpack(r, half, t0, t1, t2, tb);
+			bad += t2 != ik.x2 || t0 != ik.x0 || t1 != ik.x1;       // (absent patterns included: the reference's coordinates of the empty interval)
+			// the same interval reached backwards (what the backward chains use the table for)
+			Intv bk;
+			fm_set_intv(fm, pat[L - 1], bk);
+			for (int k = L - 2; k >= 0 && bk.x2; --k) { Intv ok[4]; fm_extend(fm, bk, ok, 1, nullptr); bk = ok[pat[k]]; }
+			if (ik.x2) bad += bk.x0 != t0 || bk.x1 != t1 || bk.x2 != t2;
+			else bad += bk.x2 != 0;
+			++n;
+		}
+	// 2. suffix array and inverse
+	if (fm.sa5 && fm.isa5) {
+		FmView walk = fm;
+		walk.sa5 = nullptr;
+		for (int t = 0; t < 3000; ++t) {
+			const uint64_t k = 1 + rnd() % fm.seq_len;
+			const uint64_t p = fm_sa(walk, k, nullptr);
+			bad += sa5_read(fm.sa5, k) != p || sa5_read(fm.isa5, p) != k;
+			++n;
+		}
+		bad += sa5_read(fm.isa5, 0) != fm.primary || sa5_read(fm.isa5, fm.seq_len) != 0;
+	} else ++bad;
+	// 3. Bloom filters: no false negatives (every window of the text is "present", every repeated one "more than once"); few false positives
+	if (fm.bloom) {
+		const int K = fm.bloom_k;
+		for (int t = 0; t < 4000; ++t) {
+			const int64_t p = (int64_t)(rnd() % (fm.seq_len - K));
+			uint64_t word, bits;
+			bloom_of_text(fm.pac, fm.l_pac, p, K, fm.bloom_mask, word, bits);
+			bad += (fm.bloom[2 * word] & bits) != bits;
+			int pat[32] = { 0 };
+			for (int k = 0; k < K; ++k) pat[k] = fm_base(fm.pac, fm.l_pac, p + k);
+			Intv ik;
+			interval_of(pat, K, ik);
+			bad += ik.x2 < 1;
+			if (ik.x2 >= 2) bad += (fm.bloom[2 * word + 1] & bits) != bits;
+			++n;
+		}
+		int64_t fp = 0, absent = 0;
+		for (int t = 0; t < 20000; ++t) {
+			int pat[32] = { 0 };
+			uint64_t v = 0;
+			for (int k = 0; k < K; ++k) { pat[k] = (int)(rnd() & 3); v = v << 2 | (uint64_t)pat[k]; }
+			Intv ik;
+			interval_of(pat, K, ik);
+			if (ik.x2) continue;
+			++absent;
+			const uint64_t h = bloom_mix(v), bits = bloom_bits(h);
+			fp += (fm.bloom[2 * (h & fm.bloom_mask)] & bits) == bits;
+		}
+		*bloom_fp_rate = absent ? (double)fp / absent : 0.;
+	} else ++bad;
+	*n_checked = n;
+	engine_destroy(e);
 	return bad;
 }

@@ -252,3 +252,23 @@ def test_per_chromosome_routing(hostemu_built, examples, tmp_path, shape):
             args.append(_head(examples["R2_10K"], 1200, str(tmp_path / "b.fq")))
     n_disc = routing_check.check_driver(drv, ["-t", "4"] + args, prefix)
     assert (n_disc > 50) == (shape == "chimeric")
+
+
+def test_derived_index_structures(hostemu_built, examples):
+    """round 2's HBM-resident structures - k-mer interval tables, whole suffix array + inverse, Bloom filters over the text's 19-mers -
+    built by the routines the upload kernels run (tests/hostemu) against the plain FM-index routines: table entries == iterated
+    bwt_extend (forwards and backwards, absent patterns included), suffix array == the walk to a sampled row, filters without false
+    negatives and with a false-positive rate of a few percent"""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, ROOT)
+    import mpibwa_b200 as M
+    lib = M.load(os.path.join(hostemu_built, "libmpibwa_b200_hostemu.so"))
+    idx = lib.bwa_idx_load(examples["idx"].encode(), 7)
+    assert idx
+    fn = lib.b200_emu_index_tables_selftest
+    fn.restype = C.c_int64
+    fn.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+    n, fp = C.c_int64(), C.c_double()
+    assert fn(idx, 5, C.byref(n), C.byref(fp)) == 0
+    assert n.value > 10000 and fp.value < 0.05

@@ -286,57 +286,22 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 	fm.ctg_off = (const int64_t *)e->d_ctg_off; fm.ctg_len = (const int32_t *)e->d_ctg_len; fm.n_ctg = bns->n_seqs;
 	if (fm.sa_intv & (fm.sa_intv - 1)) die("suffix-array sampling interval must be a power of two");
 	if (fm.seq_len >> 33) die("references beyond 2^33 BWT symbols (4.29 Gbp) are not supported by the packed seeding lists");
-	fm.sa5 = nullptr; fm.isa5 = nullptr;
-	const int sa_full = getenv("B200_SA_FULL") ? atoi(getenv("B200_SA_FULL")) : 2;
-	if (sa_full > 0) {
-		// the whole suffix array and its inverse, five bytes per row / position, expanded from the samples (B200_SA_FULL=0: keep the
-		// samples only, 1: no inverse); the pair never takes more than half of the memory that is free now, the array alone a third
-		size_t free_b = 0, total_b = 0;
-		CK(cudaMemGetInfo(&free_b, &total_b));
-		const size_t bytes = ((size_t)fm.seq_len + 1) * 5 + 16;
-		const bool inverse = sa_full > 1 && 2 * bytes <= free_b / 2;
-		if ((inverse || bytes <= free_b / 3) && (fm.seq_len >> 40) == 0 && (uint64_t)bwt->n_sa == (fm.seq_len + fm.sa_intv) / fm.sa_intv) {
-			const auto t0 = std::chrono::steady_clock::now();
-			CK(cudaMalloc(&e->d_sa5, bytes));
-			if (inverse) { CK(cudaMalloc(&e->d_isa5, bytes)); CK(cudaMemset(e->d_isa5, 0, bytes)); }
-			k_sa5_expand<<<(unsigned)(((uint64_t)bwt->n_sa + 127) / 128), 128>>>(fm, (uint64_t)bwt->n_sa, (uint8_t *)e->d_sa5, (uint8_t *)e->d_isa5);
-			CK(cudaGetLastError());
-			CK(cudaDeviceSynchronize());
-			fm.sa5 = (const uint8_t *)e->d_sa5; fm.isa5 = (const uint8_t *)e->d_isa5;
-			if (getenv("B200_DEBUG"))
-				fprintf(stderr, "[mpibwa_b200] whole suffix array%s: %.2f GB, expanded from the samples in %.0f ms\n", inverse ? " and its inverse" : "",
-				        (inverse ? 2 : 1) * bytes / 1e9, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-		}
-	}
-	fm.bloom = nullptr; fm.bloom_mask = 0; fm.bloom_k = 0;
-	if (!(getenv("B200_BLOOM") && atoi(getenv("B200_BLOOM")) == 0) && (int64_t)fm.seq_len > 64) {
-		// Bloom filter over the text's 19-mers (the default min_seed_len; used whenever the caller's is at least that)
-		const int K = 19;
-		const uint64_t n_words = bloom_words_for(fm.seq_len);
-		size_t free_b = 0, total_b = 0;
-		CK(cudaMemGetInfo(&free_b, &total_b));
-		if (n_words * 16 <= free_b / 4) {
-			const auto t0 = std::chrono::steady_clock::now();
-			CK(cudaMalloc(&e->d_bloom, n_words * 16));
-			CK(cudaMemset(e->d_bloom, 0, n_words * 16));
-			const int64_t n_pos = (int64_t)fm.seq_len - K + 1;
-			k_bloom_build<<<(unsigned)((n_pos + 255) / 256), 256>>>(fm.pac, fm.l_pac, n_pos, K, n_words - 1, (unsigned long long *)e->d_bloom);
-			CK(cudaGetLastError());
-			CK(cudaDeviceSynchronize());
-			fm.bloom = (const uint64_t *)e->d_bloom; fm.bloom_mask = n_words - 1; fm.bloom_k = K;
-			if (getenv("B200_DEBUG"))
-				fprintf(stderr, "[mpibwa_b200] Bloom filters over the text's %d-mers (present / more than once): %.2f GB, built in %.0f ms\n", K, n_words * 16 / 1e9,
-				        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-		}
-	}
+	/* Derived index structures, in the order of what they buy per byte: k-mer interval tables, the whole suffix
+	 * array, its inverse, the Bloom filters.  Each is allocated only if it leaves `reserve` of the device's memory free for the chunk
+	 * slots (B200_TABLE_RESERVE_GB, default 72 GB or 40 % of a smaller device): a table that does not fit is skipped (the k-mer
+	 * tables: made shallower) and the kernels take the path without it. */
+	size_t total_b = 0;
+	{ size_t f = 0; CK(cudaMemGetInfo(&f, &total_b)); }
+	const size_t reserve = std::min<size_t>((size_t)((getenv("B200_TABLE_RESERVE_GB") ? atof(getenv("B200_TABLE_RESERVE_GB")) : 72.0) * 1e9), (size_t)(total_b * 0.4));
+	auto fits = [&](size_t bytes) { size_t f = 0, t = 0; CK(cudaMemGetInfo(&f, &t)); return bytes + reserve <= f; };
+	auto ms_since = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+	const bool dbg = getenv("B200_DEBUG") != nullptr;
+	fm.ktab = nullptr; fm.kmax = 0;
 	{	// k-mer interval tables: every pattern of up to kmax bases, built level by level with the seeding kernels' own extension
-		// (B200_KMER_MAX: depth override, 0 = none; never more than half of the memory that is free now)
+		// (B200_KMER_MAX: depth override, 0 = none)
 		int kmax = ktab_default_kmax(fm.seq_len);
 		if (getenv("B200_KMER_MAX")) kmax = std::max(0, std::min(16, atoi(getenv("B200_KMER_MAX"))));
-		size_t free_b = 0, total_b = 0;
-		CK(cudaMemGetInfo(&free_b, &total_b));
-		while (kmax > 0 && ktab_entries(kmax) * sizeof(Q4) > free_b / 2) --kmax;
-		fm.ktab = nullptr; fm.kmax = 0;
+		while (kmax > 0 && !fits(ktab_entries(kmax) * sizeof(Q4) + 64)) --kmax;
 		if (kmax > 0) {
 			const auto t0 = std::chrono::steady_clock::now();
 			CK(cudaMalloc(&e->d_ktab, ktab_entries(kmax) * sizeof(Q4) + 64));
@@ -348,9 +313,42 @@ Engine *engine_create(const bwt_t *bwt, const bntseq_t *bns, const uint8_t *pac,
 			}
 			CK(cudaDeviceSynchronize());
 			fm.kmax = kmax;
-			if (getenv("B200_DEBUG"))
-				fprintf(stderr, "[mpibwa_b200] k-mer interval tables: patterns of up to %d bases, %.2f GB, built in %.0f ms\n", kmax,
-				        ktab_entries(kmax) * sizeof(Q4) / 1e9, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+			if (dbg) fprintf(stderr, "[mpibwa_b200] k-mer interval tables: patterns of up to %d bases, %.2f GB, built in %.0f ms\n", kmax, ktab_entries(kmax) * sizeof(Q4) / 1e9, ms_since(t0));
+		}
+	}
+	fm.sa5 = nullptr; fm.isa5 = nullptr;
+	const int sa_full = getenv("B200_SA_FULL") ? atoi(getenv("B200_SA_FULL")) : 2;
+	if (sa_full > 0) {
+		// the whole suffix array and its inverse, five bytes per row / position, expanded from the samples (B200_SA_FULL=0: keep the
+		// samples only, 1: no inverse)
+		const size_t bytes = ((size_t)fm.seq_len + 1) * 5 + 16;
+		if (fits(bytes) && (fm.seq_len >> 40) == 0 && (uint64_t)bwt->n_sa == (fm.seq_len + fm.sa_intv) / fm.sa_intv) {
+			const auto t0 = std::chrono::steady_clock::now();
+			CK(cudaMalloc(&e->d_sa5, bytes));
+			const bool inverse = sa_full > 1 && fits(bytes);
+			if (inverse) { CK(cudaMalloc(&e->d_isa5, bytes)); CK(cudaMemset(e->d_isa5, 0, bytes)); }
+			k_sa5_expand<<<(unsigned)(((uint64_t)bwt->n_sa + 127) / 128), 128>>>(fm, (uint64_t)bwt->n_sa, (uint8_t *)e->d_sa5, (uint8_t *)e->d_isa5);
+			CK(cudaGetLastError());
+			CK(cudaDeviceSynchronize());
+			fm.sa5 = (const uint8_t *)e->d_sa5; fm.isa5 = (const uint8_t *)e->d_isa5;
+			if (dbg) fprintf(stderr, "[mpibwa_b200] whole suffix array%s: %.2f GB, expanded from the samples in %.0f ms\n", inverse ? " and its inverse" : "", (inverse ? 2 : 1) * bytes / 1e9, ms_since(t0));
+		}
+	}
+	fm.bloom = nullptr; fm.bloom_mask = 0; fm.bloom_k = 0;
+	if (!(getenv("B200_BLOOM") && atoi(getenv("B200_BLOOM")) == 0) && (int64_t)fm.seq_len > 64) {
+		// Bloom filters over the text's 19-mers (the default min_seed_len; used whenever the caller's is at least that)
+		const int K = 19;
+		const uint64_t n_words = bloom_words_for(fm.seq_len);
+		if (fits(n_words * 16)) {
+			const auto t0 = std::chrono::steady_clock::now();
+			CK(cudaMalloc(&e->d_bloom, n_words * 16));
+			CK(cudaMemset(e->d_bloom, 0, n_words * 16));
+			const int64_t n_pos = (int64_t)fm.seq_len - K + 1;
+			k_bloom_build<<<(unsigned)((n_pos + 255) / 256), 256>>>(fm.pac, fm.l_pac, n_pos, K, n_words - 1, (unsigned long long *)e->d_bloom);
+			CK(cudaGetLastError());
+			CK(cudaDeviceSynchronize());
+			fm.bloom = (const uint64_t *)e->d_bloom; fm.bloom_mask = n_words - 1; fm.bloom_k = K;
+			if (dbg) fprintf(stderr, "[mpibwa_b200] Bloom filters over the text's %d-mers (present / more than once): %.2f GB, built in %.0f ms\n", K, n_words * 16 / 1e9, ms_since(t0));
 		}
 	}
 

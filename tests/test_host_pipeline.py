@@ -272,3 +272,39 @@ def test_derived_index_structures(hostemu_built, examples):
     n, fp = C.c_int64(), C.c_double()
     assert fn(idx, 5, C.byref(n), C.byref(fp)) == 0
     assert n.value > 10000 and fp.value < 0.05
+
+
+SEEDING_SETS = [("min_seed_len=10", {}), ("min_seed_len=25,split_factor=1.1", {}), ("min_seed_len=32,max_occ=20", {}),
+                ("min_seed_len=19,split_width=2", {"B200_KMER_MAX": "12"}), ("min_seed_len=14", {"B200_KMER_MAX": "6", "B200_BLOOM": "0"}),
+                ("min_seed_len=19", {"B200_SA_FULL": "1"}), ("min_seed_len=21", {"B200_KMER_MAX": "0", "B200_SA_FULL": "0"})]
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", range(len(SEEDING_SETS)))
+def test_seeding_paths_under_options(hostemu_built, tmp_path, case):
+    """the table-driven seeding (k-mer tables, backward chains, Bloom filters, unique walks) under seed lengths below / at / above
+    the tables' depth and the filters' window, with shallow or absent tables, on reads full of ambiguous bases, of 20 to 330 bases
+    and with planted repeats: tests/hostemu cross-checks the sweeps against the plain restatement on EVERY read and aborts on a
+    difference; the SAM must be the compiled reference's"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from mpibwa_b200 import simulate, index_build
+    opts, env = SEEDING_SETS[case]
+    names, lengths, codes = simulate.make_reference(400_000, 3, seed=40 + case)
+    codes = codes.copy()
+    codes[150_000:158_000] = codes[20_000:28_000]            # an exact 8 kb repeat: long shared SMEMs, intervals of size 2
+    codes[300_000:301_500] = codes[21_000:22_500]            # ... and of size 3
+    prefix = str(tmp_path / "ref.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+    r1, r2 = simulate.simulate_pairs(codes, lengths, 700, read_len=330, sub=0.02, indel=0.004, max_indel=6, n_rate=0.01,
+                                     trim_to=(20, 330), unmappable_frac=0.05, seed=50 + case)
+    f1, f2 = str(tmp_path / "r1.fq"), str(tmp_path / "r2.fq")
+    open(f1, "wb").write(r1); open(f2, "wb").write(r2)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-T", "-K", "150000", "-o", opts, prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    r = subprocess.run([drv, "-t", "4"] + args, capture_output=True, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == want and want.count(b"\n") >= 1400

@@ -622,12 +622,14 @@ def main():
     roof = None
     if dom:
         kd = src[dom]
-        traffic = None
+        traffic = ncu_detail = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
-            traffic = json.load(open(tpath)).get(dom)      # DRAM bytes per launch from the committed ncu --set full capture
+            tj = json.load(open(tpath))
+            traffic = tj.get(dom)                          # DRAM bytes per launch from the committed ncu --set full capture
+            ncu_detail = tj.get(dom + "_detail")           # ... and its DRAM GB/s / L2 hit rates (north_star asks for both beside the roofline)
         roof = {"kernel": dom, "bound": kd["bound"], "achieved": kd["achieved"], "peak": kd["peak"], "unit": kd["unit"], "frac": kd["frac"],
-                "traffic": traffic, "algorithmic_bytes_per_launch": kd.get("bytes_per_step"), "touched_bytes_per_launch": kd.get("touched_bytes_per_step"),
+                "traffic": traffic, "ncu": ncu_detail, "algorithmic_bytes_per_launch": kd.get("bytes_per_step"), "touched_bytes_per_launch": kd.get("touched_bytes_per_step"),
                 "bytes_note": kd.get("bytes_note"), "peak_source": hbm_src if kd["bound"] == "hbm" else "int32 add/max issue rate measured live by b200_int32_peak()",
                 "random_sector_peak": {"value": rnd_peak, "unit": "GB/s", "table_bytes": occ_bytes,
                                        "frac_of_it": (kd["achieved"] / rnd_peak) if kd["bound"] == "hbm" and rnd_peak else None,

@@ -306,6 +306,46 @@ def kernel_table(agg, K, i32_peak, hbm_peak, ref_ratio=1.0):
     return kern
 
 
+def gpu_locality(torch, device):
+    """(numa node, set of CPUs) the PCI device of a GPU is local to, from sysfs; (-1, empty) when the platform does not say"""
+    try:
+        p = torch.cuda.get_device_properties(device)
+        base = "/sys/bus/pci/devices/%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            if part:
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        return node, cpus & os.sched_getaffinity(0)
+    except Exception:
+        return -1, set()
+
+
+def bind_near_gpu(torch, dist, local_rank, world, threads_per_rank):
+    """One MPI rank per GPU is normally started bound to the socket its GPU hangs on (mpirun --map-by / --bind-to, srun --cpu-bind);
+    torchrun binds nothing, so a rank's threads and its page-locked buffers may sit on the other socket and every H2D / D2H copy of
+    the chunk loop crosses the inter-socket link.  Each rank restricts itself to the CPUs local to its GPU - only if every rank's GPU
+    reports a node, the GPUs sit on at least two nodes and each node has enough CPUs for the ranks on it; B200_BENCH_NUMA=0 disables."""
+    if world <= 1 or os.environ.get("B200_BENCH_NUMA", "1") == "0":
+        return None
+    node, cpus = gpu_locality(torch, local_rank)
+    mine = torch.tensor([node, len(cpus)], dtype=torch.int64, device="cuda")
+    every = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(every, mine)
+    every = [t.tolist() for t in every]
+    nodes = [n for n, _ in every]
+    ok = all(n >= 0 for n in nodes) and len(set(nodes)) >= 2
+    for n, c in every:
+        ok = ok and c >= nodes.count(n) * max(2, threads_per_rank)
+    if ok:
+        try:
+            os.sched_setaffinity(0, cpus)
+        except OSError:
+            ok = False
+    return {"bound": bool(ok), "node": node, "cpus": len(cpus), "nodes_of_ranks": nodes}
+
+
 def main():
     # rank 0 prints exactly ONE line on stdout: everything libraries write there meanwhile (NCCL's version banner ...) goes to stderr
     real_stdout = os.dup(1)
@@ -336,6 +376,10 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    numa = bind_near_gpu(torch, dist, local_rank, world, max(1, (os.cpu_count() or 1) // world))
+    if numa:
+        log("[bench] rank %d: GPU %d on NUMA node %d with %d local CPUs -> %s" % (rank, local_rank, numa["node"], numa["cpus"], "bound" if numa["bound"] else "not bound"))
 
     def barrier():
         if world > 1:
@@ -518,8 +562,11 @@ def main():
             log("[bench] e2e job: " + " ".join("%s %.1f" % (k[3:], st[k]) for k in ("ms_total", "ms_upload", "ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_plan", "ms_global", "ms_sam_host", "ms_deliver", "ms_k_finish")))
 
     # the K chunks' fastq bytes sit in private host buffers (what the host's file read leaves) when the timed region starts
+    # (as long as K private copies fit in 12 GB of page-locked memory; beyond that every step copies its chunk into one of
+    # B200_INFLIGHT + 1 recycled buffers inside the timed region - a host-to-host copy the contract does not ask for and that
+    # eight ranks on one box compete over)
     raw = None
-    if args.steps <= 16:
+    if args.steps * (max_pairs * (rb1 + rb2) + 2) <= 12 << 30:
         raw = []
         for s in range(args.steps):
             b, e = chunks[(args.warmup + s) % len(chunks)]
@@ -660,7 +707,7 @@ def main():
         "stage_ms_per_step": {k: agg[k] / K for k in ("ms_upload", "ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_plan", "ms_global", "ms_sam_host", "ms_deliver", "ms_total")},
         "stage_ms_note": "walls per chunk job incl. waiting for the device turn: upload = encode + read text staging + H2D; seed; chain; extend; regs_host = de-duplication; rescue = insert-size statistics + mate rescue; sam_plan = pairing + record plan; global = CIGAR stage; sam_host = NM/MD + SAM text; deliver = D2H + hand-over (all but upload/deliver are device stages; the names are those of round 1's records)",
         "finish_kernels_ms_per_step": agg["ms_k_finish"] / K,
-        "host_threads": n_threads, "parity": parity,
+        "host_threads": n_threads, "numa_binding": numa, "parity": parity,
     }
     if world == 1 and not args.no_cpu_baseline and os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_driver")):
         cores = os.cpu_count() or 1

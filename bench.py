@@ -1,16 +1,19 @@
 #!/usr/bin/env python
 """bench.py - headline benchmark of the B200 alignment core (contract: see the task statement / DESIGN.md).
 
-Workload (BASELINE.json configs[1]): synthetic 100 Mbp reference (4 contigs, i.i.d. ACGT + 5 % planted diverged
-repeats), wgsim-style 2x150 bp pairs (insert N(400,50), 1 % substitutions, 0.1 % indels, 0.1 % N), chunked with the
-reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call on one chunk, made
-in its chunk-job form (b200_process_seqs_begin / _end, include/mpibwa_b200.h) so that several chunks are in flight: the device
-stages of chunk i+1 run under the host stages of chunk i.  The timed region covers exactly K chunks, first begin to last end.
+Workload (default: BASELINE.json configs[2]'s reference; --ref-bp 100000000 is configs[1]): synthetic 3.1 Gbp reference (24
+contigs, i.i.d. ACGT + 5 % planted diverged repeats), wgsim-style 2x150 bp pairs (insert N(400,50), 1 % substitutions, 0.1 % indels,
+0.1 % N), chunked with the reference hosts' rule at -K 100000000 (333 334 pairs per chunk).  A "step" is one mem_process_seqs call
+on one chunk, made in its chunk-job form (b200_align_seqs_begin / b200_align_fastq_begin + b200_align_chunk_end,
+include/mpibwa_b200.h) so that several chunks are in flight and their kernels share the SMs.  The timed region covers exactly K
+chunks, first begin to last end; the K chunks' fastq bytes sit in private page-locked host buffers when it starts.
 
   value  read pairs/s through mem_process_seqs with the chunk's encoded reads already resident in HBM
   e2e    read pairs/s from raw fastq bytes in (page-locked) host memory to SAM bytes in host memory: b200_align_fastq_begin /
          b200_align_chunk_end, every H2D/D2H copy inside - the reference-facing call with host buffers
-  roofline / kernels   per device stage: algorithmic work / CUDA-event kernel time vs the measured peak
+  roofline / kernels   per device stage: algorithmic work / CUDA-event kernel time vs the measured peak (seeding: the reference
+         algorithm's occ-block touches, counted by a pass of the general kernel over the same chunk)
+  parity               untimed leg: the SAM of one timed chunk per rank against the compiled reference's (md5); the run fails otherwise
   cpu_baseline         the compiled reference (oracle/_ref/ref_driver) on the box's host cores, bounded sample
 
 `--impl reference` times the reference's own CPU mem_process_seqs (oracle/_ref, all host threads) on bounded

@@ -1,19 +1,27 @@
-// smem_sweeps.cuh - SMEM seeding split into HOMOGENEOUS sweeps (the throughput path of the seeding stage).
+// smem_sweeps.cuh - SMEM seeding (mem_collect_intv, reference src/bwamem.c:114-162) as four sweeps: the throughput path of the
+// seeding stage.
 //
-// In the per-read state machine of smem_kernel.cuh the lanes of a warp sit in different states (forward sweep, backward
-// sweep, greedy pass, transitions) and a third of the issued instructions are register shuffles between those code
-// paths.  The dependencies of mem_collect_intv (reference src/bwamem.c:114-162) allow a coarser split:
-//   * the start of the next bwt_smem1a call is the END of the longest forward match (ret = curr[0].info after the
-//     reversal, src/bwt.c:319-322), i.e. it is known after the FORWARD sweep alone - so all forward sweeps of pass 1 of
-//     a read can run back to back, each leaving its interval list (src/bwt.c:304-318) in a per-read strip in HBM;
-//   * the greedy third pass (bwt_seed_strategy1) depends on nothing but the read;
-//   * every backward sweep (src/bwt.c:326-345) depends only on its own list;
-//   * pass 2 re-seeds inside the long, rare SMEMs that pass 1 reported: same two sweeps again.
-// So: k_sweep_fwd<1> (pass-1 forward sweeps + pass 3), k_sweep_bwd, k_sweep_fwd<2>, k_sweep_bwd.  Inside one kernel every
-// lane is in the same steady state; the only divergent code is the short hand-over from one sweep to the next.  Lanes are
-// persistent and pull reads from a counter.  A read whose strip would overflow (pathological repeats) is flagged and
-// redone by the general state-machine kernel (k_seed_lanes), which has no such limit.
-// Host/device code: tests/hostemu runs the same four sweeps on the CPU against the plain restatement in fm_kernels.h.
+// 1. The split.  In the per-read state machine of smem_kernel.cuh the lanes of a warp sit in different states (forward sweep,
+//    backward sweep, greedy pass, transitions).  The dependencies of mem_collect_intv allow a coarser split:
+//      * the start of the next bwt_smem1a call is the END of the longest forward match (ret = curr[0].info after the reversal,
+//        src/bwt.c:319-322), i.e. it is known after the FORWARD sweep alone - so all forward sweeps of pass 1 of a read run back
+//        to back, each leaving its interval list (src/bwt.c:304-318) in a per-read strip in HBM;
+//      * the greedy third pass (bwt_seed_strategy1) depends on nothing but the read;
+//      * every backward sweep (src/bwt.c:326-345) depends only on its own list;
+//      * pass 2 re-seeds inside the long, rare SMEMs that pass 1 reported: same two sweeps again.
+//    So: k_sweep_fwd<1> (pass-1 forward sweeps + pass 3), k_sweep_bwd, k_sweep_fwd<2>, k_sweep_bwd.  Lanes are persistent and pull
+//    reads from a counter; every trip of the warp loop is one memory access per lane.
+// 2. Touching less.  With extensions only, these kernels sit on the DRAM random-access roofline of a human-sized index.  What
+//    they do now instead of most extensions (every structure is a pure function of the index, built at upload):
+//      * k-mer interval tables: a step whose result is a pattern of at most kmax bases is one look-up (FwdLane tab 1-3, BwdLane tab 1);
+//      * backward sweeps as independent entry chains with the report rule taken from the chains' ends (BwdLane);
+//      * Bloom filters over the text's min_seed_len-mers in front of every chain (BwdLane tab 2);
+//      * unique walks: a one-row interval is compared with the 2-bit text through the whole suffix array and its inverse (FwdLane tab 4, 5);
+//      * packed 2-bit copies of the reads, so that the windows those look-ups need are word operations (PackedRead).
+//    The interval lists and SMEMs that come out are the reference's, bit for bit.
+// A read whose strip would overflow, or whose backward chains exceed their work budget, is flagged and redone by the general
+// state-machine kernel (k_seed_lanes: the reference's loops, no tables), which has no such limits.
+// Host/device code: tests/hostemu runs the same four sweeps on the CPU against the plain restatement on every read.
 #pragma once
 #include "smem_kernel.cuh"
 

@@ -565,11 +565,11 @@ def main():
             log("[bench] e2e job: " + " ".join("%s %.1f" % (k[3:], st[k]) for k in ("ms_total", "ms_upload", "ms_seed", "ms_chain_host", "ms_extend", "ms_regs_host", "ms_rescue", "ms_sam_plan", "ms_global", "ms_sam_host", "ms_deliver", "ms_k_finish")))
 
     # the K chunks' fastq bytes sit in private host buffers (what the host's file read leaves) when the timed region starts
-    # (as long as K private copies fit in 12 GB of page-locked memory; beyond that every step copies its chunk into one of
+    # (as long as K private copies fit in 6 GB of page-locked memory; beyond that every step copies its chunk into one of
     # B200_INFLIGHT + 1 recycled buffers inside the timed region - a host-to-host copy the contract does not ask for and that
     # eight ranks on one box compete over)
     raw = None
-    if args.steps * (max_pairs * (rb1 + rb2) + 2) <= 12 << 30:
+    if args.steps * (max_pairs * (rb1 + rb2) + 2) <= 6 << 30:
         raw = []
         for s in range(args.steps):
             b, e = chunks[(args.warmup + s) % len(chunks)]

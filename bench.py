@@ -253,7 +253,7 @@ def workload_config(args, what):
                         % (which, args.pairs, args.read_len, args.ref_bp, n_contigs(args), args.K),
             "step": "one mem_process_seqs call on one chunk (%d pairs at full size) in its chunk-job form, up to four chunks in flight, each as one batch per kernel" % ((args.K // 2) // args.read_len + 1),
             "path": what, "cache_policy": "steps cycle over the rank's %d chunks (consecutive steps never align the same chunk; with up to four chunks in "
-                                          "flight a chunk may be in flight twice); index (%d MB) + per-chunk buffers exceed the 126 MB L2; an L2-sized buffer "
+                                          "flight a chunk may be in flight twice); index (%d MB; with the structures derived from it at upload - k-mer tables, suffix array + inverse, Bloom filters - 20 times that) + per-chunk buffers exceed the 126 MB L2; an L2-sized buffer "
                                           "is rewritten before each timed region" % (max(1, -(-args.pairs // ((args.K // 2) // args.read_len + 1))), int(args.ref_bp * 1.75e-6))}
 
 

@@ -308,3 +308,51 @@ def test_seeding_paths_under_options(hostemu_built, tmp_path, case):
     r = subprocess.run([drv, "-t", "4"] + args, capture_output=True, env=dict(os.environ, **env))
     assert r.returncode == 0, r.stderr[-2000:]
     assert r.stdout == want and want.count(b"\n") >= 1400
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("env", [{}, {"B200_KMER_MAX": "6"}, {"B200_BLOOM": "0", "B200_SA_FULL": "0"}])
+def test_seeding_on_repeats(hostemu_built, tmp_path, env):
+    """reads out of tandem repeats, a homopolymer run and sixty 1-3 % diverged copies of a 300-base unit: backward entries that
+    survive together for many bases (the merge stand-in and the chain budget of the backward sweeps), huge intervals, long lists -
+    cross-checked per read inside tests/hostemu, SAM == the compiled reference's"""
+    import sys
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from mpibwa_b200 import simulate, index_build
+    rng = np.random.default_rng(5)
+    names, lengths, codes = simulate.make_reference(300_000, 2, seed=91)
+    codes = codes.copy()
+    unit = codes[1000:1300].copy()
+    for k in range(60):
+        u = unit.copy()
+        m = rng.random(300) < 0.02
+        u[m] = rng.integers(0, 4, m.sum())
+        codes[5000 + k * 2000:5300 + k * 2000] = u
+    codes[150000:151000] = np.tile(np.array([0, 1], dtype=codes.dtype), 500)
+    codes[152000:152600] = 0
+    codes[153000:154200] = np.tile(codes[153000:153012], 100)
+    prefix = str(tmp_path / "rep.fa")
+    index_build.build_index_from_codes(prefix, names, lengths, codes)
+
+    def fq(name, seq):
+        return ("@%s\n%s\n+\n%s\n" % (name, "".join("ACGT"[c] for c in seq), "I" * len(seq))).encode()
+
+    a = b = b""
+    for i in range(400):
+        z = [5000 + int(rng.integers(0, 60)) * 2000 + int(rng.integers(0, 150)), 150000 + int(rng.integers(0, 850)),
+             152000 + int(rng.integers(0, 450)), 153000 + int(rng.integers(0, 1050))][i % 4]
+        s = codes[z:z + 150].copy()
+        m = rng.random(150) < 0.01
+        s[m] = rng.integers(0, 4, m.sum())
+        a += fq("rep%d" % i, s)
+        b += fq("rep%d" % i, (3 - codes[z + 200:z + 350])[::-1])
+    f1, f2 = str(tmp_path / "q1.fq"), str(tmp_path / "q2.fq")
+    open(f1, "wb").write(a); open(f2, "wb").write(b)
+    drv = os.path.join(hostemu_built, "b200_driver_hostemu")
+    ref = os.path.join(ROOT, "oracle", "_ref", "ref_driver")
+    args = ["-K", "200000", prefix, f1, f2]
+    want = subprocess.run([ref, "-t", "4"] + args, capture_output=True, check=True).stdout
+    r = subprocess.run([drv, "-t", "4"] + args, capture_output=True, env=dict(os.environ, **env))
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert r.stdout == want and want.count(b"\n") >= 800
